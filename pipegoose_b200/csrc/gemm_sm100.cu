@@ -1,0 +1,219 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction (driver entry point resolved at
+// run time so the library links without libcuda), tile-shape selection, launch.
+#include "gemm_sm100.cuh"
+#include "launch.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+namespace pg {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || p == nullptr) {
+      fprintf(stderr, "pipegoose_b200: cuTensorMapEncodeTiled not available (%s)\n",
+              cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix (cols contiguous, leading
+// dimension ld elements) with a [box_rows, 64] box and 128-byte swizzle.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr,
+            "pipegoose_b200: cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu "
+            "box=%ux%u\n",
+            (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols,
+            (unsigned long long)ld, box_rows, box_cols);
+    return -1;
+  }
+  return 0;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (k.ld * 31 + k.box_rows) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+static int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
+                       uint64_t ld, uint32_t box_rows) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (make_tmap_bf16_2d(out, ptr, rows, cols, ld, box_rows, 64) != 0) return -1;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
+                      int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "pipegoose_b200: cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(e));
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
+  const int tiles = ((chunk_rows + BM - 1) / BM) * ((args.N + BN - 1) / BN) * args.num_chunks;
+  int grid = tiles < max_ctas ? tiles : max_ctas;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "pipegoose_b200: gemm launch failed: %s\n", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+static int pick_bn(int M_rows, int N, int chunks, int ctas) {
+  const int cand[4] = {256, 192, 128, 64};
+  const float eff[4] = {1.0f, 0.93f, 0.82f, 0.55f};
+  int best = 256;
+  float best_cost = 1e30f;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && N <= bn / 2) continue;
+    const long tiles = (long)((M_rows + BM - 1) / BM) * ((N + bn - 1) / bn) * chunks;
+    const long waves = (tiles + ctas - 1) / ctas;
+    const float cost = (float)waves * (float)bn / eff[i];
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
+  GemmArgs args;
+  memset(&args, 0, sizeof(args));
+  args.M = d->M;
+  args.N = d->N;
+  args.K = d->K;
+  args.out = d->out;
+  args.ldc = d->ldc;
+  args.bias = reinterpret_cast<const __nv_bfloat16*>(d->bias);
+  args.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  args.ldr = d->ldr;
+  args.aux = d->aux;
+  args.flags = d->flags;
+  args.num_chunks = d->num_chunks > 1 ? d->num_chunks : 1;
+  args.chunk_rows = d->chunk_rows;
+  args.first_chunk = d->first_chunk;
+  args.chunk_flags = d->chunk_flags;
+  args.flag_value = d->flag_value;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    args.out_peer[i] = d->out_peer[i];
+    args.arrive_ctr[i] = d->arrive_ctr[i];
+  }
+  if (args.num_chunks > 1 && (args.chunk_rows % BM) != 0) {
+    fprintf(stderr, "pipegoose_b200: chunk_rows (%d) must be a multiple of %d\n", args.chunk_rows, BM);
+    return -1;
+  }
+  int max_ctas = d->max_ctas > 0 ? d->max_ctas : num_sms();
+  const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
+  int bn = d->block_n > 0 ? d->block_n : pick_bn(chunk_rows, args.N, args.num_chunks, max_ctas);
+
+  CUtensorMap ta, tb;
+  // A: K-major  -> matrix [M, K] (ld = lda), box [128 rows, 64]
+  //    MN-major -> matrix [K, M] (ld = lda), box [64 k-rows, 64]
+  if (!d->a_mn) {
+    if (cached_tmap(&ta, d->A, d->M, d->K, d->lda, BM) != 0) return -1;
+  } else {
+    if (cached_tmap(&ta, d->A, d->K, d->M, d->lda, BK) != 0) return -1;
+  }
+  if (!d->b_mn) {
+    if (cached_tmap(&tb, d->B, d->N, d->K, d->ldb, bn) != 0) return -1;
+  } else {
+    if (cached_tmap(&tb, d->B, d->K, d->N, d->ldb, BK) != 0) return -1;
+  }
+
+#define PG_DISPATCH_BN(AMN, BMN)                                                          \
+  switch (bn) {                                                                           \
+    case 256: return launch_cfg<256, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
+    case 192: return launch_cfg<192, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
+    case 128: return launch_cfg<128, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
+    case 64: return launch_cfg<64, AMN, BMN>(ta, tb, args, max_ctas, stream);             \
+    default: fprintf(stderr, "pipegoose_b200: bad block_n %d\n", bn); return -1;          \
+  }
+  if (!d->a_mn && !d->b_mn) {
+    PG_DISPATCH_BN(false, false)
+  } else if (!d->a_mn && d->b_mn) {
+    PG_DISPATCH_BN(false, true)
+  } else if (d->a_mn && d->b_mn) {
+    PG_DISPATCH_BN(true, true)
+  } else {
+    PG_DISPATCH_BN(true, false)
+  }
+#undef PG_DISPATCH_BN
+}

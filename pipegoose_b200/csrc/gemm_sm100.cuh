@@ -1,0 +1,406 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor) -> 128B-swizzled smem ring -> tcgen05.mma (one issuing
+//   thread) -> fp32 accumulators double-buffered in TMEM -> tcgen05.ld epilogue.
+//
+// One kernel serves the three operand layouts a transformer training step needs
+//   NT : Y  = X  · Wᵀ   (A K-major,  B K-major)    forward
+//   NN : dX = dY · W    (A K-major,  B MN-major)   dgrad
+//   TN : dW = dYᵀ · X   (A MN-major, B MN-major)   wgrad
+// and the fused compute+collective forms used by tensor parallelism
+//   all-gather -> GEMM : M is split into `num_chunks` row chunks that become readable
+//                        at different times (a comm CTA group or a peer publishes a
+//                        flag per chunk); tiles are visited chunk by chunk, starting at
+//                        the local chunk, and the TMA producer acquires the chunk flag.
+//   GEMM -> reduce-scatter : the epilogue stores each tile straight into the owner
+//                        rank's staging slot through its NVLink peer mapping and bumps a
+//                        per-owner arrival counter with a system-scope release.
+// The epilogue applies bias / tanh-GELU (also emitting the pre-activation) /
+// GELU-backward / residual add / fp32 accumulate, so none of those is a separate pass.
+#pragma once
+#include "ptx.cuh"
+
+namespace pg {
+
+constexpr int kMaxPeers = 8;
+
+enum EpiFlags : int {
+  EPI_BIAS = 1,        // acc += bias[col]
+  EPI_GELU = 2,        // out = gelu_tanh(acc); if aux_out != null, aux_out = acc (pre-activation)
+  EPI_RESIDUAL = 4,    // out = acc + residual[row, col]
+  EPI_OUT_F32 = 8,     // out is fp32
+  EPI_ACCUM = 16,      // out += acc (fp32 out only)
+  EPI_DGELU = 32,      // out = acc * gelu_tanh'(aux_in[row, col])
+};
+
+struct GemmArgs {
+  int M, N, K;
+  void* out;
+  int ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  int ldr;
+  void* aux;  // EPI_GELU: pre-activation output; EPI_DGELU: pre-activation input (bf16, ld = ldc)
+  int flags;
+  // ---- chunked traversal (fused collectives); num_chunks == 1 for a plain GEMM
+  int num_chunks;
+  int chunk_rows;   // rows per chunk (multiple of 128 when num_chunks > 1)
+  int first_chunk;  // chunk visited first (the local one)
+  // all-gather -> GEMM: chunk c is readable once chunk_flags[c] >= flag_value
+  const uint32_t* chunk_flags;
+  uint32_t flag_value;
+  // GEMM -> reduce-scatter: rows of chunk c go to out_peer[c] (row index relative to chunk),
+  // then arrive_ctr[c] (+1 per finished tile, release.sys)
+  void* out_peer[kMaxPeers];
+  uint32_t* arrive_ctr[kMaxPeers];
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+PG_DEVICE float gelu_tanh(float x) {
+  // Bloom's GELU: x * 0.5 * (1 + tanh(0.79788456 x (1 + 0.044715 x^2)))
+  float u = 0.79788456f * x * (1.0f + 0.044715f * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+PG_DEVICE float gelu_tanh_grad(float x) {
+  float u = 0.79788456f * x * (1.0f + 0.044715f * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * ((1.0f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.0f + t);
+}
+
+struct TileCoord {
+  int m_blk, n_blk, chunk;
+};
+
+// Tiles are enumerated chunk-major (chunk order rotated to start at first_chunk); inside a
+// chunk, groups of 8 row-blocks sweep all column-blocks so that concurrently resident CTAs
+// share A and B tiles through L2.
+PG_DEVICE TileCoord map_tile(int t, int m_blks_per_chunk, int n_blks, int num_chunks,
+                             int first_chunk) {
+  const int per_chunk = m_blks_per_chunk * n_blks;
+  const int ci = t / per_chunk;
+  int r = t - ci * per_chunk;
+  int chunk = first_chunk + ci;
+  if (chunk >= num_chunks) chunk -= num_chunks;
+  constexpr int G = 8;
+  const int per_group = G * n_blks;
+  const int g = r / per_group;
+  const int first_m = g * G;
+  const int gsz = min(m_blks_per_chunk - first_m, G);
+  r -= g * per_group;
+  TileCoord c;
+  c.n_blk = r / gsz;
+  c.m_blk = chunk * m_blks_per_chunk + first_m + (r - c.n_blk * gsz);
+  c.chunk = chunk;
+  return c;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
+                     const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int chunk_rows = (args.num_chunks > 1) ? args.chunk_rows : args.M;
+  const int m_blks_per_chunk = (chunk_rows + BM - 1) / BM;
+  const int n_blks = (args.N + BN - 1) / BN;
+  const int num_tiles = m_blks_per_chunk * n_blks * args.num_chunks;
+  const int num_kb = (args.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    int stage = 0;
+    uint32_t phase = 0;
+    int seen_chunk = -1;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
+      if (args.chunk_flags != nullptr && tc.chunk != seen_chunk) {
+        if (lane == 0) {
+          while (ld_acquire_sys(args.chunk_flags + tc.chunk) < args.flag_value) {
+          }
+          fence_proxy_async_global();
+        }
+        __syncwarp();
+        seen_chunk = tc.chunk;
+      }
+      const int m0 = tc.m_blk * BM;
+      const int n0 = tc.n_blk * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem_a + stage * Cfg::kABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 16 elements = 32 bytes inside the 128B swizzle row; 8-row groups 1024B apart.
+            // MN-major: 16 k-rows of 128B; 64-wide MN atoms BK*128 B apart (LBO); 8 k-rows 1024B (SBO).
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
+            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue ============================
+    const int q = warp - 4;  // == warp % 4 -> TMEM lanes [32q, 32q+32)
+    int it = 0;
+    const bool out_f32 = (args.flags & EPI_OUT_F32) != 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = tc.m_blk * BM + q * 32 + lane;
+      const int n0 = tc.n_blk * BN;
+      // destination row pointer (possibly on a peer GPU)
+      uint8_t* out_base = reinterpret_cast<uint8_t*>(args.out);
+      int out_row = row;
+      int row_limit = args.M;
+      if (args.num_chunks > 1) {
+        row_limit = (tc.chunk + 1) * chunk_rows;
+        if (args.out_peer[0] != nullptr) {
+          out_base = reinterpret_cast<uint8_t*>(args.out_peer[tc.chunk]);
+          out_row = row - tc.chunk * chunk_rows;
+        }
+      }
+      const bool row_ok = row < row_limit && row < args.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= args.N) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        const int ncols = min(32, args.N - col0);  // multiple of 8
+        if (args.flags & EPI_BIAS) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < ncols) {
+              const uint4 b = ld_global_nc_v4(args.bias + col0 + g * 8);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 bf = unpack_bf16x2(bw[j]);
+                f[g * 8 + 2 * j] += bf.x;
+                f[g * 8 + 2 * j + 1] += bf.y;
+              }
+            }
+          }
+        }
+        if (out_f32) {
+          float* o = reinterpret_cast<float*>(out_base) + static_cast<size_t>(out_row) * args.ldc + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 4 < ncols) {
+              float4 val = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+              if (args.flags & EPI_ACCUM) {
+                const float4 old = *reinterpret_cast<const float4*>(o + g * 4);
+                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+              }
+              *reinterpret_cast<float4*>(o + g * 4) = val;
+            }
+          }
+          continue;
+        }
+        if (args.flags & EPI_GELU) {
+          if (args.aux != nullptr) {
+            __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(args.aux) +
+                               static_cast<size_t>(row) * args.ldc + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols) {
+                uint4 pk;
+                pk.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+                pk.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+                pk.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+                pk.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+                st_global_v4(a + g * 8, pk);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+        }
+        if (args.flags & EPI_DGELU) {
+          const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(args.aux) +
+                                   static_cast<size_t>(row) * args.ldc + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < ncols) {
+              const uint4 z = ld_global_nc_v4(a + g * 8);
+              const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 zf = unpack_bf16x2(zw[j]);
+                f[g * 8 + 2 * j] *= gelu_tanh_grad(zf.x);
+                f[g * 8 + 2 * j + 1] *= gelu_tanh_grad(zf.y);
+              }
+            }
+          }
+        }
+        if (args.flags & EPI_RESIDUAL) {
+          const __nv_bfloat16* r = args.residual + static_cast<size_t>(row) * args.ldr + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < ncols) {
+              const uint4 z = ld_global_nc_v4(r + g * 8);
+              const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 zf = unpack_bf16x2(zw[j]);
+                f[g * 8 + 2 * j] += zf.x;
+                f[g * 8 + 2 * j + 1] += zf.y;
+              }
+            }
+          }
+        }
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_base) +
+                           static_cast<size_t>(out_row) * args.ldc + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < ncols) {
+            uint4 pk;
+            pk.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+            pk.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            pk.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+            pk.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+            st_global_v4(o + g * 8, pk);
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr) {
+        // all four epilogue warps have stored their rows of this tile -> publish to the owner
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 4 && lane == 0) {
+          fence_acq_rel_sys();
+          red_add_release_sys(args.arrive_ctr[tc.chunk], 1u);
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace pg

@@ -1,0 +1,315 @@
+"""Runtime singleton describing how the job's ranks are arranged into TP x PP x DP (+ expert) groups.
+
+API parity target: reference ``pipegoose/distributed/parallel_context.py:49-407`` (constructor,
+``from_torch``, the getters/registrars, ``ranks2device``, ``destroy``).  Differences, all deliberate:
+
+* one process per GPU: with the ``nccl`` backend the CUDA device is bound (``set_device``) *before*
+  the first collective, so NCCL communicators live on the right GPU and peer (NVLink) mappings
+  can be created for the fused kernels;
+* no ``torch.distributed.rpc``: pipeline stages exchange activations with NCCL send/recv on a
+  static schedule, so there is no RPC agent to start (``rpc_worker_map``/``get_worker_name`` are
+  kept as pure name lookups);
+* ring helpers work on the *local* rank of this process (reference Q2: the global rank was fed
+  to a modulo over the group size);
+* besides the torch process groups, each mode can own a :class:`SymmetricWorkspace` (peer
+  pointers + signal pads over NVSwitch) created lazily by ``get_symmetric_workspace``.
+"""
+from __future__ import annotations
+
+import os
+import random
+from typing import Dict, List, Literal, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from pipegoose_b200.constants import SEED, WORKER_NAME
+from pipegoose_b200.distributed._initializers import (
+    DataParallelGroupInitializer,
+    ExpertDataParallelGroupInitializer,
+    ExpertShardGroupInitializer,
+    PipelineParallelGroupInitializer,
+    TensorParallelGroupInitializer,
+)
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.distributed.topology import Topology
+
+DistributedBackend = Literal["gloo", "mpi", "nccl"]
+RanksToDevice = Tuple[Tuple[ParallelMode, int], ...]
+
+_PARALLEL_CONTEXT: Optional["ParallelContext"] = None
+
+# modes that identify a device (reference: EXPERT_DATA is excluded from the device map)
+_DEVICE_MODES = (ParallelMode.GLOBAL, ParallelMode.TENSOR, ParallelMode.PIPELINE, ParallelMode.DATA)
+
+
+class ParallelContext:
+    @classmethod
+    def from_torch(
+        cls,
+        tensor_parallel_size: int,
+        pipeline_parallel_size: int,
+        data_parallel_size: int,
+        seed: int = SEED,
+        backend: DistributedBackend = "gloo",
+    ) -> "ParallelContext":
+        """Build the context from the environment variables set by ``torchrun``."""
+        env = os.environ
+        world_size = int(env["WORLD_SIZE"])
+        return cls(
+            rank=int(env["RANK"]),
+            local_rank=int(env.get("LOCAL_RANK", 0)),
+            world_size=world_size,
+            local_world_size=int(env.get("LOCAL_WORLD_SIZE", world_size)),
+            host=env.get("MASTER_ADDR", "127.0.0.1"),
+            port=int(env.get("MASTER_PORT", 29500)),
+            seed=seed,
+            backend=backend,
+            tensor_parallel_size=tensor_parallel_size,
+            pipeline_parallel_size=pipeline_parallel_size,
+            data_parallel_size=data_parallel_size,
+        )
+
+    def __init__(
+        self,
+        rank: int,
+        local_rank: int,
+        world_size: int,
+        local_world_size: int,
+        host: str,
+        port: int,
+        seed: int,
+        backend: DistributedBackend,
+        tensor_parallel_size: int,
+        pipeline_parallel_size: int,
+        data_parallel_size: int,
+    ):
+        model_ranks = tensor_parallel_size * pipeline_parallel_size
+        assert world_size % data_parallel_size == 0, "world size must be divisible by the data parallel size"
+        assert world_size % model_ranks == 0, (
+            "world size must be divisible by the number of ranks per model replica "
+            "(tensor_parallel_size * pipeline_parallel_size)"
+        )
+        assert model_ranks * data_parallel_size == world_size, (
+            "tensor_parallel_size * pipeline_parallel_size * data_parallel_size must equal the world size"
+        )
+
+        self.tensor_parallel_size = tensor_parallel_size
+        self.pipeline_parallel_size = pipeline_parallel_size
+        self.data_parallel_size = data_parallel_size
+        self.local_rank = local_rank
+        self.local_world_size = local_world_size
+        self.backend = backend
+        self.topology = Topology(world_size, tensor_parallel_size, pipeline_parallel_size, data_parallel_size)
+
+        self._global_ranks: Dict[ParallelMode, int] = {}
+        self._local_ranks: Dict[ParallelMode, int] = {}
+        self._world_sizes: Dict[ParallelMode, int] = {}
+        self._groups: Dict[ParallelMode, dist.ProcessGroup] = {}
+        self._ranks_in_group: Dict[ParallelMode, List[int]] = {}
+        self._ranks_to_device: Dict[RanksToDevice, int] = {}
+        self._symm_workspaces = {}
+        self._owns_default_group = False
+
+        if backend == "nccl":
+            # bind the GPU before any communicator is created
+            self._bind_device(rank)
+        self.init_global_dist(rank, world_size, backend, host, port)
+        self.init_parallel_groups()
+        self.map_rank_to_device()
+
+        self.rpc_worker_map = {r: WORKER_NAME.format(r) for r in self.get_ranks_in_group(ParallelMode.GLOBAL)}
+        self.init_rpc_workers(host, port)
+
+        self.set_seed(seed)
+        self._set_context()
+
+    # ------------------------------------------------------------------ singleton
+    def _set_context(self):
+        global _PARALLEL_CONTEXT
+        _PARALLEL_CONTEXT = self
+
+    @staticmethod
+    def get_context() -> Optional["ParallelContext"]:
+        """The most recently constructed (and not destroyed) context."""
+        return _PARALLEL_CONTEXT
+
+    # ------------------------------------------------------------------ bring-up
+    def _bind_device(self, rank: int):
+        n = torch.cuda.device_count()
+        if n > 0:
+            torch.cuda.set_device(self.local_rank % n if self.local_world_size <= n else rank % n)
+
+    def init_global_dist(self, rank: int, world_size: int, backend: DistributedBackend, host: str, port: int):
+        """Create the default (world) process group and register it as ``ParallelMode.GLOBAL``."""
+        if not dist.is_initialized():
+            kwargs = {}
+            if backend == "nccl" and torch.cuda.is_available():
+                kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
+            dist.init_process_group(
+                rank=rank, world_size=world_size, backend=backend, init_method=f"tcp://{host}:{port}", **kwargs
+            )
+            self._owns_default_group = True
+        ranks = list(range(world_size))
+        group = dist.new_group(ranks=ranks)
+        self._register_dist(rank, world_size, group, ranks_in_group=ranks, parallel_mode=ParallelMode.GLOBAL)
+        self.add_global_rank(ParallelMode.GLOBAL, rank)
+
+    def init_parallel_groups(self):
+        """Create the TENSOR / PIPELINE / DATA / EXPERT_DATA (+ EXPERT) groups."""
+        rank = self.get_global_rank()
+        world_size = self.get_world_size(ParallelMode.GLOBAL)
+        dist.barrier()  # every rank has joined the world group
+        params = dict(
+            rank=rank,
+            world_size=world_size,
+            tensor_parallel_size=self.tensor_parallel_size,
+            pipeline_parallel_size=self.pipeline_parallel_size,
+            data_parallel_size=self.data_parallel_size,
+        )
+        for initializer in (
+            TensorParallelGroupInitializer,
+            PipelineParallelGroupInitializer,
+            DataParallelGroupInitializer,
+            ExpertDataParallelGroupInitializer,
+            ExpertShardGroupInitializer,
+        ):
+            self._register_dist(**initializer(**params).init_dist_group())
+
+    def init_rpc_workers(self, host: str, port: int):
+        """No RPC agents: the pipeline engine uses NCCL p2p on a static schedule (reference
+        parallel_context.py:200-225 started TensorPipe here)."""
+        return None
+
+    def _register_dist(self, local_rank, local_world_size, process_group, ranks_in_group, parallel_mode):
+        self.add_local_rank(parallel_mode, local_rank)
+        self.add_world_size(parallel_mode, local_world_size)
+        self.add_group(parallel_mode, process_group)
+        self.add_ranks_in_group(parallel_mode, ranks_in_group)
+
+    def set_device(self):
+        """Bind this process to its GPU (one process per GPU)."""
+        self._bind_device(self.get_global_rank())
+
+    def set_seed(self, seed: int):
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(seed)
+
+    def map_rank_to_device(self):
+        """``((mode, local_rank), ...) -> global rank`` for the four device-identifying modes.
+
+        The reference all-gathers each rank's local ranks (parallel_context.py:263-287); the
+        topology is arithmetic, so every rank can fill the table without communication.
+        """
+        for r in range(self.get_world_size(ParallelMode.GLOBAL)):
+            key = tuple((m, self.topology.local_rank(r, m)) for m in _DEVICE_MODES)
+            self._ranks_to_device[key] = r
+
+    def ranks2device(self, ranks: RanksToDevice) -> int:
+        ranks = tuple(ranks)
+        assert ranks in self._ranks_to_device, f"{ranks} not in {list(self._ranks_to_device)}"
+        return self._ranks_to_device[ranks]
+
+    # ------------------------------------------------------------------ getters / registrars
+    def is_initialized(self, parallel_mode: ParallelMode) -> bool:
+        return parallel_mode in self._groups
+
+    def get_global_rank(self) -> int:
+        return self._global_ranks[ParallelMode.GLOBAL]
+
+    def add_global_rank(self, parallel_mode: ParallelMode, rank: int):
+        self._global_ranks[parallel_mode] = rank
+
+    def get_local_rank(self, parallel_mode: ParallelMode) -> int:
+        return self._local_ranks[parallel_mode]
+
+    def add_local_rank(self, parallel_mode: ParallelMode, rank: int):
+        self._local_ranks[parallel_mode] = rank
+
+    def get_global_rank_from_local_rank(self, local_rank: int, parallel_mode: ParallelMode) -> int:
+        return self._ranks_in_group[parallel_mode][local_rank]
+
+    def get_world_size(self, parallel_mode: ParallelMode) -> int:
+        return self._world_sizes[parallel_mode]
+
+    def add_world_size(self, parallel_mode: ParallelMode, world_size: int):
+        self._world_sizes[parallel_mode] = world_size
+
+    def add_group(self, parallel_mode: ParallelMode, group: dist.ProcessGroup):
+        self._groups[parallel_mode] = group
+
+    def get_group(self, parallel_mode: ParallelMode) -> dist.ProcessGroup:
+        return self._groups[parallel_mode]
+
+    def add_ranks_in_group(self, parallel_mode: ParallelMode, ranks_in_group: List[int]):
+        self._ranks_in_group[parallel_mode] = ranks_in_group
+
+    def get_ranks_in_group(self, parallel_mode: ParallelMode) -> List[int]:
+        return self._ranks_in_group[parallel_mode]
+
+    # ring neighbours --------------------------------------------------
+    def get_next_local_rank(self, rank: int, parallel_mode: ParallelMode) -> int:
+        return (rank + 1) % self.get_world_size(parallel_mode)
+
+    def get_prev_local_rank(self, rank: int, parallel_mode: ParallelMode) -> int:
+        return (rank - 1) % self.get_world_size(parallel_mode)
+
+    def get_next_global_rank(self, parallel_mode: ParallelMode) -> int:
+        nxt = self.get_next_local_rank(self.get_local_rank(parallel_mode), parallel_mode)
+        return self.get_ranks_in_group(parallel_mode)[nxt]
+
+    def get_prev_global_rank(self, parallel_mode: ParallelMode) -> int:
+        prv = self.get_prev_local_rank(self.get_local_rank(parallel_mode), parallel_mode)
+        return self.get_ranks_in_group(parallel_mode)[prv]
+
+    def is_first_rank(self, parallel_mode: ParallelMode) -> bool:
+        return self.get_local_rank(parallel_mode) == 0
+
+    def is_last_rank(self, parallel_mode: ParallelMode) -> bool:
+        return self.get_local_rank(parallel_mode) == self.get_world_size(parallel_mode) - 1
+
+    def get_worker_name(self, rank: int) -> str:
+        return self.rpc_worker_map[rank]
+
+    # ------------------------------------------------------------------ device helpers
+    @property
+    def device(self) -> torch.device:
+        if self.backend == "nccl" and torch.cuda.is_available():
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
+
+    def get_symmetric_workspace(self, parallel_mode: ParallelMode, nbytes: int = 0):
+        """Lazily create (or grow) the NVLink peer-mapped workspace of ``parallel_mode``'s group."""
+        from pipegoose_b200.distributed.symmetric import SymmetricWorkspace
+
+        ws = self._symm_workspaces.get(parallel_mode)
+        if ws is None or ws.nbytes < nbytes:
+            if ws is not None:
+                ws.close()
+            ws = SymmetricWorkspace(self, parallel_mode, nbytes)
+            self._symm_workspaces[parallel_mode] = ws
+        return ws
+
+    # ------------------------------------------------------------------ teardown
+    def destroy(self):
+        assert self.is_initialized(ParallelMode.GLOBAL), "the global group must be initialised before destroying"
+        global _PARALLEL_CONTEXT
+        for ws in self._symm_workspaces.values():
+            ws.close()
+        self._symm_workspaces.clear()
+        for mode, group in list(self._groups.items()):
+            if mode is ParallelMode.GLOBAL:
+                continue
+            dist.barrier(group=group)
+            dist.destroy_process_group(group)
+        dist.barrier()
+        dist.destroy_process_group(self._groups[ParallelMode.GLOBAL])
+        if self._owns_default_group and dist.is_initialized():
+            dist.destroy_process_group()
+        self._groups.clear()
+        if _PARALLEL_CONTEXT is self:
+            _PARALLEL_CONTEXT = None
