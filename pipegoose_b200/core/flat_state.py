@@ -1,0 +1,128 @@
+"""Flat parameter / gradient storage.
+
+``FlatModelState`` re-points every parameter of a module at a view of ONE contiguous buffer of
+the model dtype and gives every parameter an fp32 ``main_grad`` view of ONE contiguous gradient
+buffer.  That layout is what the B200 path is built around:
+
+* the wgrad GEMM epilogue accumulates straight into ``param.main_grad`` (no ``.grad`` tensors,
+  no bf16->fp32 cast pass);
+* the data-parallel reducer walks the gradient buffer in fixed-size buckets (NVLink peer
+  reduce-scatter/all-reduce kernels need contiguous, 16-byte aligned ranges);
+* the ZeRO-1 optimizer owns a contiguous ``1/dp`` slice of the buffer and updates it with one
+  fused Adam launch, then all-gathers the bf16 parameter buffer.
+
+(The reference's ``Bucket`` re-points ``tensor.data`` the same way, core/bucket/bucket.py:52-54,
+but nothing in the reference uses it.)
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+_ALIGN = 128  # elements; keeps every view 256B-aligned for bf16 and 512B for fp32
+
+
+def unique_parameters(module_or_params) -> List[nn.Parameter]:
+    params = module_or_params.parameters() if isinstance(module_or_params, nn.Module) else module_or_params
+    seen, out = set(), []
+    for p in params:
+        if id(p) not in seen and p.requires_grad:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
+class FlatModelState:
+    def __init__(self, params: Iterable[nn.Parameter], pad_to_multiple_of: int = 1, grad_dtype=torch.float32):
+        self.params: List[nn.Parameter] = unique_parameters(list(params))
+        assert len(self.params) > 0
+        p0 = self.params[0]
+        self.device, self.dtype = p0.device, p0.dtype
+        assert all(p.device == self.device and p.dtype == self.dtype for p in self.params), \
+            "all parameters of a flat state must share device and dtype"
+        self.offsets: Dict[int, Tuple[int, int]] = {}
+        off = 0
+        for p in self.params:
+            self.offsets[id(p)] = (off, p.numel())
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        mult = max(pad_to_multiple_of, 1) * _ALIGN
+        self.numel = (off + mult - 1) // mult * mult
+        self.flat_param = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
+        self.flat_grad = torch.zeros(self.numel, dtype=grad_dtype, device=self.device)
+        for p in self.params:
+            o, n = self.offsets[id(p)]
+            view = self.flat_param[o:o + n].view_as(p.data)
+            view.copy_(p.data)
+            p.data = view
+            p.main_grad = self.flat_grad[o:o + n].view_as(p.data)
+            p._pg_flat_state = self
+            p._mg_fresh = False
+            p.grad = None
+
+    @classmethod
+    def of(cls, module: nn.Module, **kw) -> "FlatModelState":
+        state = getattr(module, "_flat_state", None)
+        if state is None:
+            state = cls.find(module.parameters())
+            if state is None:
+                state = cls(module.parameters(), **kw)
+            else:
+                mult = max(kw.get("pad_to_multiple_of", 1), 1) * _ALIGN
+                assert state.numel % mult == 0, "existing flat state is not padded for this data parallel size"
+            module._flat_state = state
+        return state
+
+    @staticmethod
+    def find(params) -> Optional["FlatModelState"]:
+        """The flat state the given parameters already live in, if any."""
+        for p in params:
+            st = getattr(p, "_pg_flat_state", None)
+            if st is not None:
+                return st
+        return None
+
+    def zero_grad(self, lazy: bool = True):
+        """Reset gradients.  ``lazy``: matrices are not memset — the first wgrad GEMM of the step
+        overwrites instead of accumulating (``param._mg_fresh``); only the small 1-D parameters,
+        whose gradients are built with atomics, are cleared here."""
+        if not lazy:
+            self.flat_grad.zero_()
+            for p in self.params:
+                p._mg_fresh = False
+            return
+        for p in self.params:
+            if p.dim() < 2:
+                p.main_grad.zero_()
+                p._mg_fresh = False
+            else:
+                p._mg_fresh = True
+
+    def finalize_grads(self):
+        """Parameters that received no gradient this step (still fresh) must read as zero."""
+        for p in self.params:
+            if getattr(p, "_mg_fresh", False):
+                p.main_grad.zero_()
+                p._mg_fresh = False
+
+    def param_range(self, p: nn.Parameter) -> Tuple[int, int]:
+        return self.offsets[id(p)]
+
+    def shard_range(self, rank: int, world: int) -> Tuple[int, int]:
+        assert self.numel % world == 0
+        n = self.numel // world
+        return rank * n, (rank + 1) * n
+
+    def materialize_grads(self):
+        """Expose ``main_grad`` as ``.grad`` in the parameter dtype (for stock torch optimizers)."""
+        for p in self.params:
+            p.grad = p.main_grad.to(p.dtype)
+
+    def rebind(self):
+        """Re-point the parameters after the module was moved (``.to`` creates new storages)."""
+        for p in self.params:
+            o, n = self.offsets[id(p)]
+            if p.data.data_ptr() != self.flat_param[o:o + n].data_ptr():
+                self.flat_param[o:o + n].view_as(p.data).copy_(p.data)
+                p.data = self.flat_param[o:o + n].view_as(p.data)

@@ -1,0 +1,193 @@
+"""Bucketed, backward-overlapped gradient reduction over the flat fp32 gradient buffer.
+
+Replaces the reference's one blocking ``all_reduce`` per parameter inside an autograd hook
+(nn/data_parallel/data_parallel.py:28-43).  The flat gradient buffer is cut into fixed-size
+buckets (``BUCKET_SIZE_MB``, constants.py); a bucket is reduced as soon as every parameter in it
+has its gradient, on a side stream, while backward keeps running.  Modes:
+
+* ``all_reduce``      every rank ends with the averaged gradients (any optimizer works)
+* ``reduce_scatter``  rank ``r`` ends with slice ``r`` of every bucket (what the fused ZeRO-1
+                      optimizer consumes) — half the bytes of an all-reduce
+
+On NVLink-connected B200s the collective is the hand-written peer-memory kernel from
+``pipegoose_b200.ops.comm`` (fused with the 1/dp scale); NCCL/gloo is the fallback.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from pipegoose_b200.constants import BUCKET_SIZE_MB
+from pipegoose_b200.core.flat_state import FlatModelState, _ALIGN
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+
+class _Bucket:
+    __slots__ = ("index", "start", "end", "params", "pending", "launched", "work")
+
+    def __init__(self, index, start, end):
+        self.index, self.start, self.end = index, start, end
+        self.params: List[nn.Parameter] = []
+        self.pending = 0
+        self.launched = False
+        self.work = None
+
+
+class GradReducer:
+    def __init__(self, module: nn.Module, parallel_context, bucket_size_mb: float = BUCKET_SIZE_MB,
+                 mode: str = "all_reduce"):
+        self.module = module
+        self.ctx = parallel_context
+        self.dp = parallel_context.get_world_size(ParallelMode.DATA)
+        self.dp_rank = parallel_context.get_local_rank(ParallelMode.DATA)
+        self.mode = mode
+        self.bucket_size_mb = bucket_size_mb
+        self.flat: Optional[FlatModelState] = None
+        self.buckets: List[_Bucket] = []
+        self._bucket_of: Dict[int, List[_Bucket]] = {}
+        self._callback_queued = False
+        self._sync = True
+        self._fused = None  # set by ops.comm when the NVLink kernels are usable
+        self.post_reduce_hooks = []
+
+    # ------------------------------------------------------------------ construction
+    def build(self):
+        if self.flat is not None:
+            return
+        gran = self.dp * _ALIGN
+        self.bucket_numel = max(gran, int(self.bucket_size_mb * 1024 * 1024 / 4) // gran * gran)
+        self.flat = FlatModelState.of(self.module, pad_to_multiple_of=self.dp)
+        # pad the flat buffers so that every bucket (including the last) divides by dp
+        n = self.flat.numel
+        self.buckets = []
+        start, i = 0, 0
+        while start < n:
+            end = min(n, start + self.bucket_numel)
+            self.buckets.append(_Bucket(i, start, end))
+            start, i = end, i + 1
+        for p in self.flat.params:
+            o, cnt = self.flat.param_range(p)
+            first, last = o // self.bucket_numel, (o + cnt - 1) // self.bucket_numel
+            owners = self.buckets[first:last + 1]
+            self._bucket_of[id(p)] = owners
+            for b in owners:
+                b.params.append(p)
+            p._pg_grad_ready = self._on_param_ready
+            if not hasattr(p, "_pg_autograd_hook"):
+                p._pg_autograd_hook = p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+        self._reset_pending()
+
+    def _reset_pending(self):
+        for b in self.buckets:
+            b.pending = sum(getattr(p, "_pg_grad_contribs", 1) for p in b.params)
+            b.launched = False
+            b.work = None
+        self._contribs_seen: Dict[int, int] = {}
+
+    # ------------------------------------------------------------------ gradient arrival
+    def _on_autograd_grad(self, p: nn.Parameter):
+        """A gradient delivered through autograd (``p.grad``): fold it into the fp32 main grad."""
+        if p.grad is None:
+            return
+        from pipegoose_b200.ops.functional import acquire_main_grad
+        from pipegoose_b200.ops import kernels as K
+
+        mg, accumulate = acquire_main_grad(p, will_overwrite=True)
+        K.accumulate_grad(p.grad, mg, accumulate)
+        p.grad = None
+        self._on_param_ready(p)
+
+    def _on_param_ready(self, p: nn.Parameter):
+        if not self._callback_queued:
+            self._callback_queued = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.finalize)
+        if not self._sync or self.dp == 1:
+            return
+        seen = self._contribs_seen.get(id(p), 0) + 1
+        self._contribs_seen[id(p)] = seen
+        if seen > getattr(p, "_pg_grad_contribs", 1):
+            return
+        for b in self._bucket_of[id(p)]:
+            b.pending -= 1
+            if b.pending == 0 and not b.launched:
+                self._launch(b)
+
+    # ------------------------------------------------------------------ collectives
+    def _group_for(self, b: _Bucket):
+        return self.ctx.get_group(ParallelMode.DATA)
+
+    def _launch(self, b: _Bucket):
+        b.launched = True
+        for p in b.params:  # parameters that got no gradient this step read as zero
+            if getattr(p, "_mg_fresh", False):
+                p.main_grad.zero_()
+                p._mg_fresh = False
+        view = self.flat.flat_grad[b.start:b.end]
+        group = self._group_for(b)
+        if self._fused is not None:
+            b.work = self._fused.reduce_bucket(view, self.mode)
+            return
+        backend = dist.get_backend(group)
+        if backend == "nccl":
+            if self.mode == "reduce_scatter":
+                n = view.numel() // self.dp
+                out = view[self.dp_rank * n:(self.dp_rank + 1) * n]
+                b.work = dist.reduce_scatter_tensor(out, view, op=dist.ReduceOp.AVG, group=group, async_op=True)
+            else:
+                b.work = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=group, async_op=True)
+        else:
+            view.div_(self.dp)
+            b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def finalize(self):
+        """End of backward: launch what is left, reduce TP-partial gradients, wait for everything."""
+        self._callback_queued = False
+        if self.flat is None:
+            return
+        self._reduce_tp_partial()
+        if self._sync and self.dp > 1:
+            for b in reversed(self.buckets):
+                if not b.launched:
+                    self._launch(b)
+            for b in self.buckets:
+                if b.work is not None:
+                    b.work.wait()
+        else:
+            self.flat.finalize_grads()
+        for hook in self.post_reduce_hooks:
+            hook()
+        self._reset_pending()
+
+    def _reduce_tp_partial(self):
+        """Sequence-parallel layers compute gradients of TP-replicated parameters (LayerNorms,
+        row-parallel biases) from their token shard only: sum them over the TENSOR group."""
+        tp = self.ctx.get_world_size(ParallelMode.TENSOR)
+        if tp == 1:
+            return
+        ps = [p for p in self.flat.params if getattr(p, "tp_partial_grad", False)]
+        if not ps:
+            return
+        for p in ps:
+            if getattr(p, "_mg_fresh", False):
+                p.main_grad.zero_()
+                p._mg_fresh = False
+        flat = torch.cat([p.main_grad.reshape(-1) for p in ps])
+        dist.all_reduce(flat, group=self.ctx.get_group(ParallelMode.TENSOR))
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.main_grad.copy_(flat[off:off + n].view_as(p.main_grad))
+            off += n
+
+    @contextmanager
+    def no_sync(self):
+        """Skip gradient reduction (gradient accumulation over several backward passes)."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev

@@ -5,6 +5,7 @@
 #include <c10/cuda/CUDAGuard.h>
 
 #include "launch.h"
+#include <cmath>
 
 namespace {
 
@@ -85,6 +86,112 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   TORCH_CHECK(pg_gemm_bf16(&d, cur_stream()) == 0, "pg_gemm_bf16 failed");
 }
 
+
+#define PG_CUDA(t) TORCH_CHECK((t).is_cuda() && (t).is_contiguous(), #t " must be a contiguous CUDA tensor")
+#define PG_BF16(t) TORCH_CHECK((t).scalar_type() == torch::kBFloat16, #t " must be bf16")
+#define PG_F32(t) TORCH_CHECK((t).scalar_type() == torch::kFloat32, #t " must be fp32")
+
+const void* opt_ptr(const c10::optional<torch::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+// y = LN(x) (or LN(table[ids]) / table[ids] when ids is given); returns nothing, fills y/mean/rstd
+void layernorm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& ids, int64_t vocab_start,
+                   int64_t vocab_end, const torch::Tensor& gamma, const torch::Tensor& beta, torch::Tensor y,
+                   c10::optional<torch::Tensor> mean, c10::optional<torch::Tensor> rstd, double eps, bool apply_ln) {
+  PG_CUDA(x); PG_BF16(x); PG_CUDA(y); PG_BF16(y); PG_CUDA(gamma); PG_BF16(gamma); PG_CUDA(beta); PG_BF16(beta);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = (int)y.size(-1);
+  const int rows = (int)(y.numel() / h);
+  TORCH_CHECK(x.size(-1) == h, "hidden size mismatch");
+  const int64_t* idp = nullptr;
+  if (ids.has_value()) { PG_CUDA(*ids); TORCH_CHECK(ids->scalar_type() == torch::kInt64 && ids->numel() == rows, "ids must be int64 [rows]"); idp = ids->data_ptr<int64_t>(); }
+  else { TORCH_CHECK(x.numel() == y.numel(), "x/y size mismatch"); }
+  float* mp = mean.has_value() ? mean->data_ptr<float>() : nullptr;
+  float* rp = rstd.has_value() ? rstd->data_ptr<float>() : nullptr;
+  TORCH_CHECK(pg_layernorm_fwd(x.data_ptr(), idp, (int)vocab_start, (int)vocab_end, gamma.data_ptr(), beta.data_ptr(),
+                               y.data_ptr(), mp, rp, rows, h, (float)eps, apply_ln, cur_stream()) == 0, "layernorm_fwd failed");
+}
+
+void layernorm_bwd(const torch::Tensor& dy, const torch::Tensor& x, const torch::Tensor& gamma, const torch::Tensor& mean,
+                   const torch::Tensor& rstd, const c10::optional<torch::Tensor>& dx_extra, torch::Tensor dx,
+                   c10::optional<torch::Tensor> dgamma, c10::optional<torch::Tensor> dbeta) {
+  PG_CUDA(dy); PG_BF16(dy); PG_CUDA(x); PG_BF16(x); PG_CUDA(dx); PG_BF16(dx); PG_CUDA(mean); PG_F32(mean); PG_CUDA(rstd); PG_F32(rstd);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int h = (int)x.size(-1);
+  const int rows = (int)(x.numel() / h);
+  float* dg = nullptr; float* db = nullptr;
+  if (dgamma.has_value()) { PG_F32(*dgamma); PG_F32(*dbeta); dg = dgamma->data_ptr<float>(); db = dbeta->data_ptr<float>(); }
+  TORCH_CHECK(pg_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                               opt_ptr(dx_extra), dx.data_ptr(), dg, db, rows, h, cur_stream()) == 0, "layernorm_bwd failed");
+}
+
+void colsum(const torch::Tensor& x, torch::Tensor out) {
+  check_bf16_2d(x, "x"); PG_CUDA(out); PG_F32(out);
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(out.numel() == x.size(1), "out must have one entry per column");
+  TORCH_CHECK(pg_colsum(x.data_ptr(), (int)x.stride(0), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), cur_stream()) == 0, "colsum failed");
+}
+
+void embedding_bwd(const torch::Tensor& dx, const torch::Tensor& ids, torch::Tensor dw, int64_t vocab_start, int64_t vocab_end) {
+  PG_CUDA(dx); PG_BF16(dx); PG_CUDA(ids); PG_CUDA(dw); PG_F32(dw);
+  c10::cuda::CUDAGuard guard(dx.device());
+  const int h = (int)dx.size(-1);
+  const int rows = (int)(dx.numel() / h);
+  TORCH_CHECK(ids.scalar_type() == torch::kInt64 && ids.numel() == rows, "ids must be int64 [rows]");
+  TORCH_CHECK(pg_embedding_bwd(dx.data_ptr(), ids.data_ptr<int64_t>(), dw.data_ptr<float>(), rows, h, (int)vocab_start, (int)vocab_end, cur_stream()) == 0, "embedding_bwd failed");
+}
+
+void ce_stats(const torch::Tensor& logits, const torch::Tensor& targets, torch::Tensor stats, int64_t vocab_start) {
+  check_bf16_2d(logits, "logits"); PG_CUDA(targets); PG_CUDA(stats); PG_F32(stats);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = (int)logits.size(0);
+  TORCH_CHECK(targets.scalar_type() == torch::kInt64 && targets.numel() == rows && stats.numel() == rows * 3, "bad targets/stats");
+  TORCH_CHECK(pg_ce_stats(logits.data_ptr(), (int)logits.stride(0), targets.data_ptr<int64_t>(), stats.data_ptr<float>(), rows, (int)logits.size(1), (int)vocab_start, cur_stream()) == 0, "ce_stats failed");
+}
+
+void ce_finalize(torch::Tensor logits, const torch::Tensor& targets, const torch::Tensor& gstats, torch::Tensor loss_rows,
+                 int64_t vocab_start, const c10::optional<torch::Tensor>& grad_scale, int64_t ignore_index, bool write_grad) {
+  const float* gsp = nullptr;
+  if (grad_scale.has_value()) { PG_CUDA(*grad_scale); PG_F32(*grad_scale); gsp = grad_scale->data_ptr<float>(); }
+  check_bf16_2d(logits, "logits"); PG_CUDA(targets); PG_CUDA(gstats); PG_F32(gstats); PG_CUDA(loss_rows); PG_F32(loss_rows);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = (int)logits.size(0);
+  TORCH_CHECK(pg_ce_finalize(logits.data_ptr(), (int)logits.stride(0), targets.data_ptr<int64_t>(), gstats.data_ptr<float>(), loss_rows.data_ptr<float>(),
+                             rows, (int)logits.size(1), (int)vocab_start, gsp, ignore_index, write_grad, cur_stream()) == 0, "ce_finalize failed");
+}
+
+void adam_step(torch::Tensor master, torch::Tensor m, torch::Tensor v, const torch::Tensor& grad, c10::optional<torch::Tensor> param_bf16,
+               double lr, double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale, bool adamw) {
+  PG_CUDA(master); PG_F32(master); PG_CUDA(m); PG_F32(m); PG_CUDA(v); PG_F32(v); PG_CUDA(grad); PG_F32(grad);
+  c10::cuda::CUDAGuard guard(master.device());
+  const int64_t n = master.numel();
+  TORCH_CHECK(m.numel() == n && v.numel() == n && grad.numel() == n, "adam: size mismatch");
+  void* pb = nullptr;
+  if (param_bf16.has_value()) { PG_CUDA(*param_bf16); PG_BF16(*param_bf16); TORCH_CHECK(param_bf16->numel() == n, "adam: bf16 param size mismatch"); pb = param_bf16->data_ptr(); }
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  TORCH_CHECK(pg_adam(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), grad.data_ptr<float>(), pb, n, (float)lr, (float)beta1, (float)beta2,
+                      (float)eps, (float)wd, (float)bc1, (float)bc2, (float)grad_scale, adamw, cur_stream()) == 0, "adam failed");
+}
+
+void sgd_step(torch::Tensor master, c10::optional<torch::Tensor> mom, const torch::Tensor& grad, c10::optional<torch::Tensor> param_bf16,
+              double lr, double momentum, double wd, double grad_scale, bool first_step) {
+  PG_CUDA(master); PG_F32(master); PG_CUDA(grad); PG_F32(grad);
+  c10::cuda::CUDAGuard guard(master.device());
+  const int64_t n = master.numel();
+  float* mp = nullptr;
+  if (mom.has_value()) { PG_CUDA(*mom); PG_F32(*mom); mp = mom->data_ptr<float>(); }
+  TORCH_CHECK(momentum == 0.0 || mp != nullptr, "sgd: momentum buffer required");
+  void* pb = nullptr;
+  if (param_bf16.has_value()) { PG_CUDA(*param_bf16); PG_BF16(*param_bf16); pb = param_bf16->data_ptr(); }
+  TORCH_CHECK(pg_sgd(master.data_ptr<float>(), mp, grad.data_ptr<float>(), pb, n, (float)lr, (float)momentum, (float)wd, (float)grad_scale, first_step, cur_stream()) == 0, "sgd failed");
+}
+
+void accum_bf16_to_f32(const torch::Tensor& src, torch::Tensor dst, double scale, bool accumulate) {
+  PG_CUDA(src); PG_BF16(src); PG_CUDA(dst); PG_F32(dst);
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.numel() == dst.numel(), "size mismatch");
+  TORCH_CHECK(pg_accum_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), (float)scale, accumulate, cur_stream()) == 0, "accum failed");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -95,4 +202,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("num_chunks") = 1, py::arg("first_chunk") = 0, py::arg("chunk_flags_ptr") = 0,
         py::arg("flag_value") = 0, py::arg("out_peer_ptrs") = std::vector<int64_t>{},
         py::arg("arrive_ctr_ptrs") = std::vector<int64_t>{});
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("colsum", &colsum);
+  m.def("embedding_bwd", &embedding_bwd);
+  m.def("ce_stats", &ce_stats);
+  m.def("ce_finalize", &ce_finalize);
+  m.def("adam_step", &adam_step);
+  m.def("sgd_step", &sgd_step);
+  m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
 }

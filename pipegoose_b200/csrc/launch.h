@@ -35,6 +35,29 @@ typedef struct PgGemmDesc {
 
 int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream);
 
+// ---- elementwise.cu
+int pg_layernorm_fwd(const void* x, const int64_t* ids, int vocab_start, int vocab_end,
+                     const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                     int rows, int h, float eps, int apply_ln, cudaStream_t s);
+int pg_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                     const float* rstd, const void* dx_extra, void* dx, float* dgamma, float* dbeta,
+                     int rows, int h, cudaStream_t s);
+int pg_colsum(const void* x, int ld, float* out, int rows, int cols, cudaStream_t s);
+int pg_embedding_bwd(const void* dx, const int64_t* ids, float* dw, int rows, int h,
+                     int vocab_start, int vocab_end, cudaStream_t s);
+int pg_ce_stats(const void* logits, int ld, const int64_t* targets, float* stats, int rows,
+                int vocab_local, int vocab_start, cudaStream_t s);
+int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gstats,
+                   float* loss_rows, int rows, int vocab_local, int vocab_start,
+                   const float* grad_scale, int64_t ignore_index, int write_grad, cudaStream_t s);
+int pg_adam(float* master, float* m, float* v, const float* grad, void* param_bf16, int64_t n,
+            float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+            float grad_scale, int adamw, cudaStream_t s);
+int pg_sgd(float* master, float* mom, const float* grad, void* param_bf16, int64_t n, float lr,
+           float momentum, float wd, float grad_scale, int first_step, cudaStream_t s);
+int pg_accum_bf16_to_f32(const void* src, float* dst, int64_t n, float scale, int accumulate,
+                         cudaStream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,285 @@
+"""B200-native Bloom (``BloomForCausalLM``) with the same module tree and parameter names as
+🤗 transformers' Bloom, so HF state dicts load unchanged and the name-based parallel mappings
+(reference nn/tensor_parallel/parallel_mapping.py:4-52) apply to both.
+
+The forward is built from the four fused sub-layer functions in ``pipegoose_b200.ops.functional``;
+activations are 2-D ``[tokens, hidden]`` bf16 tensors (token-sharded under tensor parallelism),
+attention is the flash ALiBi kernel, the lm_head is fused with a vocab-parallel cross entropy
+(no ``[tokens, vocab]`` fp32 tensor, no all-gather of logits).
+
+Dropout: Bloom's ``hidden_dropout`` / ``attention_dropout`` default to 0.0 and the fused path
+supports exactly that.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from pipegoose_b200.ops import functional as PF
+from pipegoose_b200.ops import kernels as K
+from pipegoose_b200.ops.attention import alibi_attention
+
+
+@dataclass
+class BloomConfig:
+    """Subset of transformers.BloomConfig that defines the architecture."""
+
+    vocab_size: int = 250880
+    hidden_size: int = 64
+    n_layer: int = 2
+    n_head: int = 8
+    layer_norm_epsilon: float = 1e-5
+    initializer_range: float = 0.02
+    hidden_dropout: float = 0.0
+    attention_dropout: float = 0.0
+    apply_residual_connection_post_layernorm: bool = False
+    tie_word_embeddings: bool = True
+
+    @classmethod
+    def from_hf(cls, hf_config) -> "BloomConfig":
+        return cls(
+            vocab_size=hf_config.vocab_size,
+            hidden_size=hf_config.hidden_size,
+            n_layer=hf_config.n_layer,
+            n_head=hf_config.n_head,
+            layer_norm_epsilon=hf_config.layer_norm_epsilon,
+            initializer_range=hf_config.initializer_range,
+            hidden_dropout=hf_config.hidden_dropout,
+            attention_dropout=hf_config.attention_dropout,
+            apply_residual_connection_post_layernorm=hf_config.apply_residual_connection_post_layernorm,
+        )
+
+    @classmethod
+    def bloom_560m(cls):
+        return cls(hidden_size=1024, n_layer=24, n_head=16)
+
+    @classmethod
+    def bloom_1b7(cls):
+        return cls(hidden_size=2048, n_layer=24, n_head=16)
+
+    @classmethod
+    def bloom_3b(cls):
+        return cls(hidden_size=2560, n_layer=30, n_head=32)
+
+    @classmethod
+    def bloom_7b1(cls):
+        return cls(hidden_size=4096, n_layer=30, n_head=32)
+
+
+@dataclass
+class CausalLMOutput:
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+
+    def __getitem__(self, i):
+        return (self.loss, self.logits)[i]
+
+
+class BloomAttention(nn.Module):
+    def __init__(self, config: BloomConfig):
+        super().__init__()
+        h = config.hidden_size
+        self.hidden_size = h
+        self.num_heads = config.n_head
+        self.head_dim = h // config.n_head
+        self.query_key_value = nn.Linear(h, 3 * h, bias=True)
+        self.dense = nn.Linear(h, h, bias=True)
+        self.register_buffer("alibi_slopes", K.alibi_slopes(config.n_head), persistent=False)
+
+
+class BloomMLP(nn.Module):
+    def __init__(self, config: BloomConfig):
+        super().__init__()
+        h = config.hidden_size
+        self.dense_h_to_4h = nn.Linear(h, 4 * h)
+        self.dense_4h_to_h = nn.Linear(4 * h, h)
+
+    def forward(self, hidden_states: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+        """HF-compatible signature ``mlp(layernorm_output, residual)`` (used by the MoE wrapper)."""
+        shape = hidden_states.shape
+        x = hidden_states.reshape(-1, shape[-1])
+        y = PF.mlp_residual(x, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias,
+                            self.dense_4h_to_h.weight, self.dense_4h_to_h.bias, residual.reshape(-1, shape[-1]))
+        return y.view(shape)
+
+
+class BloomBlock(nn.Module):
+    def __init__(self, config: BloomConfig):
+        super().__init__()
+        h = config.hidden_size
+        self.eps = config.layer_norm_epsilon
+        self.input_layernorm = nn.LayerNorm(h, eps=self.eps)
+        self.self_attention = BloomAttention(config)
+        self.post_attention_layernorm = nn.LayerNorm(h, eps=self.eps)
+        self.mlp = BloomMLP(config)
+        self.tp = None  # set by TensorParallel (sequence-parallel communicator)
+
+    def forward(self, x: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
+        """``x``: ``[tokens_local, hidden]`` (token-sharded when ``self.tp`` is set)."""
+        attn = self.self_attention
+        tp = self.tp
+        qkv = PF.layernorm_linear(x, self.input_layernorm.weight, self.input_layernorm.bias,
+                                  attn.query_key_value.weight, attn.query_key_value.bias, self.eps, tp)
+        n_head_local = attn.query_key_value.weight.shape[0] // (3 * attn.head_dim)
+        ctx = alibi_attention(qkv, attn.alibi_slopes_local(n_head_local), batch, seq, n_head_local, attn.head_dim)
+        x = PF.linear_residual(ctx, attn.dense.weight, attn.dense.bias, x, tp)
+        mlp = self.mlp
+        if isinstance(mlp, BloomMLP):
+            x = PF.layernorm_mlp(x, self.post_attention_layernorm.weight, self.post_attention_layernorm.bias,
+                                 mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias,
+                                 mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias, self.eps, tp)
+        else:
+            # replaced MLP (e.g. ExpertLayer): HF contract mlp(layernorm_output, residual)
+            ln = fused_layer_norm(x, self.post_attention_layernorm.weight, self.post_attention_layernorm.bias, self.eps)
+            x = mlp(ln, x)
+        return x
+
+
+def _alibi_slopes_local(self: BloomAttention, n_head_local: int) -> torch.Tensor:
+    """Slopes of the heads this tensor-parallel rank owns (heads are sharded contiguously)."""
+    if n_head_local == self.num_heads:
+        return self.alibi_slopes
+    rank = getattr(self, "tp_rank", 0)
+    return self.alibi_slopes[rank * n_head_local:(rank + 1) * n_head_local].contiguous()
+
+
+BloomAttention.alibi_slopes_local = _alibi_slopes_local
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """Stand-alone fused LayerNorm (used where the LN is not followed by one of our GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        y, mean, rstd = K.layernorm_fwd(x2, gamma, beta, eps)
+        ctx.save_for_backward(x2, gamma, beta, mean, rstd)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, beta, mean, rstd = ctx.saved_tensors
+        dx, dg, db = PF._ln_bwd(dy.reshape(x2.shape).contiguous(), x2, gamma, beta, mean, rstd)
+        return dx.view(ctx.shape), dg, db, None
+
+
+def fused_layer_norm(x, gamma, beta, eps=1e-5):
+    return _LayerNormFn.apply(x, gamma, beta, eps)
+
+
+class BloomModel(nn.Module):
+    def __init__(self, config: BloomConfig):
+        super().__init__()
+        h = config.hidden_size
+        self.config = config
+        self.word_embeddings = nn.Embedding(config.vocab_size, h)
+        self.word_embeddings_layernorm = nn.LayerNorm(h, eps=config.layer_norm_epsilon)
+        self.h = nn.ModuleList([BloomBlock(config) for _ in range(config.n_layer)])
+        self.ln_f = nn.LayerNorm(h, eps=config.layer_norm_epsilon)
+
+
+class BloomForCausalLM(nn.Module):
+    base_model_prefix = "transformer"
+
+    def __init__(self, config: BloomConfig):
+        super().__init__()
+        assert config.hidden_dropout == 0.0 and config.attention_dropout == 0.0, \
+            "the fused Bloom path implements Bloom's default (0.0) dropout"
+        assert not config.apply_residual_connection_post_layernorm
+        self.config = config
+        self.transformer = BloomModel(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.lm_head.weight = self.transformer.word_embeddings.weight  # tied
+        self.tp = None
+        self.vocab_start = 0
+        self.apply(self._init_weights)
+
+    def _init_weights(self, module):
+        std = self.config.initializer_range
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    # ------------------------------------------------------------------ helpers
+    def get_input_embeddings(self):
+        return self.transformer.word_embeddings
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def num_parameters(self) -> int:
+        seen, n = set(), 0
+        for p in self.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                n += p.numel()
+        return n
+
+    def flops_per_token(self, seq_len: int) -> float:
+        """Model FLOPs per token for fwd+bwd (6*N_matmul + causal attention)."""
+        c = self.config
+        h, L, V = c.hidden_size, c.n_layer, c.vocab_size
+        per_layer = 12 * h * h
+        attn = 2 * seq_len * h  # QK^T + PV, causal half of 4*S*h
+        return 3 * 2 * (L * (per_layer + attn) + V * h)
+
+    # ------------------------------------------------------------------ forward
+    def hidden_states(self, input_ids: torch.Tensor) -> torch.Tensor:
+        t = self.transformer
+        B, S = input_ids.shape
+        x = PF.embedding_layernorm(input_ids, t.word_embeddings.weight, t.word_embeddings_layernorm.weight,
+                                   t.word_embeddings_layernorm.bias, self.config.layer_norm_epsilon,
+                                   self.vocab_start, self.tp)
+        for block in t.h:
+            x = block(x, B, S)
+        return x
+
+    def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, **_unused) -> CausalLMOutput:
+        t = self.transformer
+        B, S = input_ids.shape
+        x = self.hidden_states(input_ids)
+        eps = self.config.layer_norm_epsilon
+        if labels is not None:
+            # HF semantics: position s predicts token s+1; the last position has no target
+            shifted = torch.full_like(labels, -100)
+            shifted[:, :-1] = labels[:, 1:]
+            loss = PF.lm_head_cross_entropy(x, t.ln_f.weight, t.ln_f.bias, self.lm_head.weight, shifted, eps,
+                                            self.vocab_start, -100, self.tp)
+            return CausalLMOutput(loss=loss, logits=None)
+        ln = fused_layer_norm(x, t.ln_f.weight, t.ln_f.bias, eps)
+        if self.tp is not None:
+            ln = self.tp.all_gather_rows(ln)
+        logits = K.gemm_nt(ln, self.lm_head.weight)
+        if self.tp is not None:
+            logits = self.tp.all_gather_cols(logits)[:, : self.config.vocab_size]
+        return CausalLMOutput(loss=None, logits=logits.view(B, S, -1))
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, **_unused) -> torch.Tensor:
+        """Greedy decoding (full recompute per token: the training library has no KV cache)."""
+        out = input_ids
+        for _ in range(max_new_tokens):
+            logits = self(out).logits
+            nxt = logits[:, -1, :].float().argmax(-1, keepdim=True)
+            out = torch.cat([out, nxt], dim=1)
+        return out
+
+    # ------------------------------------------------------------------ HF interop
+    @classmethod
+    def from_hf(cls, hf_model) -> "BloomForCausalLM":
+        model = cls(BloomConfig.from_hf(hf_model.config))
+        model.load_state_dict(hf_model.state_dict(), strict=False)
+        return model

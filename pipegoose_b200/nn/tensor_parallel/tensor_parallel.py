@@ -1,0 +1,141 @@
+"""Tensor parallelism wrapper (parity: reference nn/tensor_parallel/tensor_parallel.py:18-82).
+
+``TensorParallel(module, parallel_context).parallelize()`` shards the module in place:
+
+* ``pipegoose_b200.models`` models take the **sequence-parallel fast path**: weights are sliced,
+  every block gets a :class:`TensorParallelComm`, activations between sub-layers are token
+  shards and the collectives are fused into the GEMM kernels (AG->GEMM / GEMM->RS over NVLink);
+  attention heads are sharded (the reference replicates attention on every rank);
+* any other model (e.g. 🤗 ``BloomForCausalLM``) takes the **replicated-activation path** with the
+  reference's semantics: every leaf that a parallelizer accepts becomes Column/RowParallelLinear,
+  ParallelEmbedding or LayerNorm; leaves under an ``ExpertLayer`` are skipped.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.nn.parallel import Parallel
+from pipegoose_b200.nn.tensor_parallel.parallelizer import (
+    EmbeddingParallelizer,
+    LayerNormParallelizer,
+    LinearParallelizer,
+    LMHeadParallelizer,
+    ModuleParallelizer,
+    _mark_sliced,
+    get_partition,
+)
+
+
+class TensorParallel(Parallel):
+    PARALLELIZERS = [EmbeddingParallelizer, LinearParallelizer, LayerNormParallelizer, LMHeadParallelizer]
+
+    def __init__(self, module: nn.Module, parallel_context: ParallelContext, sequence_parallel: Optional[bool] = None):
+        super().__init__(module, parallel_context)
+        self.sequence_parallel = sequence_parallel
+
+    @torch.no_grad()
+    def parallelize(self) -> nn.Module:
+        module, ctx = self.module, self.parallel_context
+        if ctx.tensor_parallel_size > 1:
+            from pipegoose_b200.models.bloom import BloomForCausalLM as FastBloom
+
+            use_sp = isinstance(module, FastBloom) if self.sequence_parallel is None else self.sequence_parallel
+            if use_sp:
+                assert isinstance(module, FastBloom), "the sequence-parallel path needs a pipegoose_b200.models model"
+                _parallelize_fast_bloom(module, ctx)
+            else:
+                # remember weight tying before the embedding's parameter object is replaced by its slice
+                if hasattr(module, "get_input_embeddings") and hasattr(module, "get_output_embeddings"):
+                    emb, head = module.get_input_embeddings(), module.get_output_embeddings()
+                    if emb is not None and head is not None and head.weight is emb.weight:
+                        head._pg_tied_to_embedding = True
+                for name, leaf in self._get_leaf_modules(module):
+                    parallelizer = self._find_parallelizer(name, leaf)
+                    if parallelizer is not None:
+                        parallelizer(name, leaf, module, ctx).parallelize()
+            self._save_metadata(module, ctx)
+        return module
+
+    def _get_leaf_modules(self, model: nn.Module) -> List[Tuple[str, nn.Module]]:
+        """Leaves outside any ExpertLayer (experts are sharded by ExpertParallel, not sliced)."""
+        from pipegoose_b200.nn.expert_parallel.layers import ExpertLayer
+
+        expert_prefixes = [n for n, m in model.named_modules() if isinstance(m, ExpertLayer)]
+        leaves = []
+        for name, mod in model.named_modules():
+            if any(name == p or name.startswith(p + ".") for p in expert_prefixes):
+                continue
+            if len(list(mod.children())) == 0:
+                leaves.append((name, mod))
+        return leaves
+
+    def _find_parallelizer(self, module_name: str, module: nn.Module) -> Optional[ModuleParallelizer]:
+        for parallelizer in self.PARALLELIZERS:
+            if parallelizer.is_parallelizable(module_name, module):
+                return parallelizer
+        return None
+
+    @torch.no_grad()
+    def deparallelize(self) -> nn.Module:
+        raise NotImplementedError("re-create the model and load a checkpoint to undo tensor parallelism")
+
+
+def _slice_param(param: nn.Parameter, ctx, dim: int) -> nn.Parameter:
+    new = nn.Parameter(get_partition(param.data, ctx, dim=dim), requires_grad=param.requires_grad)
+    _mark_sliced(new)
+    return new
+
+
+def _parallelize_fast_bloom(model, ctx: ParallelContext):
+    """Slice a pipegoose_b200 Bloom for the sequence-parallel path."""
+    from pipegoose_b200.parallel.tp_comm import TensorParallelComm
+
+    world = ctx.get_world_size(ParallelMode.TENSOR)
+    rank = ctx.get_local_rank(ParallelMode.TENSOR)
+    cfg = model.config
+    assert cfg.n_head % world == 0, "attention heads must divide by the tensor parallel size"
+    comm = TensorParallelComm(ctx)
+    t = model.transformer
+
+    # vocab-parallel (tied) embedding / lm_head, zero-padded to a multiple of the group size
+    table = t.word_embeddings.weight.data
+    vocab = table.shape[0]
+    padded = (vocab + world * 8 - 1) // (world * 8) * (world * 8)
+    if padded != vocab:
+        table = torch.cat([table, table.new_zeros(padded - vocab, table.shape[1])], dim=0)
+    sliced = nn.Parameter(get_partition(table, ctx, dim=0))
+    _mark_sliced(sliced)
+    sliced._pg_grad_contribs = 2  # lm_head wgrad + embedding backward
+    t.word_embeddings.weight = sliced
+    model.lm_head.weight = sliced
+    model.vocab_start = rank * (padded // world)
+    model.tp = comm
+
+    def partial(p):  # gradient is a partial sum over this rank's token shard
+        p.tp_partial_grad = True
+
+    for ln in (t.word_embeddings_layernorm, t.ln_f):
+        partial(ln.weight), partial(ln.bias)
+    for block in t.h:
+        attn, mlp = block.self_attention, block.mlp
+        attn.query_key_value.weight = _slice_param(attn.query_key_value.weight, ctx, 0)  # whole heads
+        attn.query_key_value.bias = _slice_param(attn.query_key_value.bias, ctx, 0)
+        attn.dense.weight = _slice_param(attn.dense.weight, ctx, 1)
+        attn.tp_rank = rank
+        partial(attn.dense.bias)
+        if hasattr(mlp, "dense_h_to_4h"):
+            mlp.dense_h_to_4h.weight = _slice_param(mlp.dense_h_to_4h.weight, ctx, 0)
+            mlp.dense_h_to_4h.bias = _slice_param(mlp.dense_h_to_4h.bias, ctx, 0)
+            mlp.dense_4h_to_h.weight = _slice_param(mlp.dense_4h_to_h.weight, ctx, 1)
+            partial(mlp.dense_4h_to_h.bias)
+        for ln in (block.input_layernorm, block.post_attention_layernorm):
+            partial(ln.weight), partial(ln.bias)
+        block.tp = comm
+    hooks = getattr(model, "_pg_after_move_hooks", [])
+    hooks.append(lambda m: comm.enable_fused())
+    model._pg_after_move_hooks = hooks

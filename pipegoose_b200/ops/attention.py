@@ -1,0 +1,69 @@
+"""Causal ALiBi self-attention on Bloom's fused QKV layout.
+
+``qkv`` is ``[B*S, n_head*3*D]`` with each row laid out ``[head][q|k|v][D]`` (the layout HF Bloom's
+``query_key_value`` produces), the result is ``[B*S, n_head*D]``.  Scores are
+``q.k / sqrt(D) + slope[head] * key_position`` under a causal mask, softmax in fp32.
+
+Two implementations share this contract: the sm_100a flash kernel (``csrc/attention_sm100.cu``:
+tcgen05 QK^T / PV with TMEM accumulators, online softmax, never materialising ``[S, S]``) and
+the PyTorch reference below (CPU tests, numerics oracle).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from pipegoose_b200.ops import has_kernel, native, use_native
+
+
+def alibi_attention_reference(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int) -> torch.Tensor:
+    x = qkv.view(B, S, n_head, 3, D)
+    q, k, v = (x[:, :, :, i].permute(0, 2, 1, 3).float() for i in range(3))  # [B, H, S, D]
+    scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(D)
+    pos = torch.arange(S, device=qkv.device, dtype=torch.float32)
+    scores = scores + slopes.float().view(1, n_head, 1, 1) * pos.view(1, 1, 1, S)
+    causal = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    scores = scores.masked_fill(~causal, float("-inf"))
+    p = torch.softmax(scores, dim=-1)
+    out = torch.matmul(p, v)  # [B, H, S, D]
+    return out.permute(0, 2, 1, 3).reshape(B * S, n_head * D).to(qkv.dtype)
+
+
+class _AlibiAttentionNative(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, slopes, B, S, n_head, D):
+        out = torch.empty(B * S, n_head * D, dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty(B, n_head, S, dtype=torch.float32, device=qkv.device)
+        native().attention_fwd(qkv, slopes, out, lse, B, S, n_head, D)
+        ctx.save_for_backward(qkv, slopes, out, lse)
+        ctx.dims = (B, S, n_head, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, slopes, out, lse = ctx.saved_tensors
+        B, S, n_head, D = ctx.dims
+        dqkv = torch.empty_like(qkv)
+        native().attention_bwd(qkv, slopes, out, lse, dout.contiguous(), dqkv, B, S, n_head, D)
+        return dqkv, None, None, None, None, None
+
+
+def _native_attention_available(D: int) -> bool:
+    return has_kernel("attention_fwd") and D in (64, 128)
+
+
+def alibi_attention(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int) -> torch.Tensor:
+    if use_native(qkv) and _native_attention_available(D):
+        return _AlibiAttentionNative.apply(qkv, slopes, B, S, n_head, D)
+    if qkv.is_cuda:
+        # library fallback for head sizes the flash kernel does not cover yet (e.g. D=80, bloom-3b)
+        x = qkv.view(B, S, n_head, 3, D)
+        q, k, v = (x[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+        pos = torch.arange(S, device=qkv.device, dtype=torch.float32)
+        bias = slopes.float().view(1, n_head, 1, 1) * pos.view(1, 1, 1, S)
+        causal = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+        bias = bias.expand(1, n_head, S, S).masked_fill(~causal, float("-inf")).to(qkv.dtype)
+        out = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias)
+        return out.permute(0, 2, 1, 3).reshape(B * S, n_head * D)
+    return alibi_attention_reference(qkv, slopes, B, S, n_head, D)

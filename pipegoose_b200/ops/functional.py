@@ -1,0 +1,379 @@
+"""Autograd functions of the fast path: each one is a *sub-layer* (several kernels with a
+hand-written backward), not a single op, so a transformer block is four autograd nodes and no
+elementwise kernel runs outside a GEMM epilogue or a fused normalisation kernel.
+
+Weight gradients are accumulated by the wgrad GEMM epilogue straight into ``param.main_grad``
+(fp32, a view into the flat gradient buffer that the fused data-parallel reducer and the fused
+ZeRO-1 optimizer consume) when the parameter has one; otherwise they are returned through
+autograd like any other gradient, so the same layers work under a stock ``torch.optim``.
+
+Tensor parallelism is expressed through a ``tp`` communicator object (``None`` for TP=1) with
+the sequence-parallel contract: activations between sub-layers are sharded along the token
+dimension (``[M/T, h]``); column-parallel GEMMs consume an all-gather (fused: AG->GEMM) and
+row-parallel GEMMs produce a reduce-scatter (fused: GEMM->RS).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from pipegoose_b200.ops import kernels as K
+
+
+def _main_grad(p: Optional[torch.Tensor]):
+    return getattr(p, "main_grad", None) if p is not None else None
+
+
+def acquire_main_grad(p, will_overwrite: bool):
+    """``(main_grad, accumulate)`` for the next gradient contribution to ``p``.
+
+    After a lazy ``zero_grad`` the buffer still holds last step's values (``p._mg_fresh``): the
+    first contribution overwrites it (GEMM epilogue without the accumulate flag) or, for
+    atomically-built gradients, clears it first."""
+    mg = p.main_grad
+    if getattr(p, "_mg_fresh", False):
+        p._mg_fresh = False
+        if will_overwrite:
+            return mg, False
+        mg.zero_()
+    return mg, True
+
+
+def notify_grad_ready(p):
+    """Tell the gradient reducer (if any) that ``p.main_grad`` received a contribution."""
+    hook = getattr(p, "_pg_grad_ready", None)
+    if hook is not None:
+        hook(p)
+
+
+def _wgrad(dy, x, weight):
+    """dW = dy^T x, accumulated into weight.main_grad when present (returns None then)."""
+    if _main_grad(weight) is not None:
+        mg, accumulate = acquire_main_grad(weight, will_overwrite=True)
+        K.gemm_tn(dy, x, accum_into=mg, accumulate=accumulate)
+        notify_grad_ready(weight)
+        return None
+    return K.gemm_tn(dy, x).to(weight.dtype)
+
+
+def _bgrad(dy, bias):
+    if bias is None:
+        return None
+    if _main_grad(bias) is not None:
+        mg, _ = acquire_main_grad(bias, will_overwrite=False)
+        K.colsum(dy, accum_into=mg)
+        notify_grad_ready(bias)
+        return None
+    return K.colsum(dy).to(bias.dtype)
+
+
+def _ln_bwd(dy, x, gamma, beta, mean, rstd, dx_extra=None):
+    if _main_grad(gamma) is not None and _main_grad(beta) is not None:
+        mg_g, _ = acquire_main_grad(gamma, will_overwrite=False)
+        mg_b, _ = acquire_main_grad(beta, will_overwrite=False)
+        dx, _, _ = K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra, mg_g, mg_b)
+        notify_grad_ready(gamma)
+        notify_grad_ready(beta)
+        return dx, None, None
+    return K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra)
+
+
+class LayerNormLinear(torch.autograd.Function):
+    """``y = Linear(LayerNorm(x))`` — LN kernel, then (all-gather ->) GEMM with the bias in the epilogue.
+
+    Column-parallel under TP: ``x`` is the local token shard ``[M/T, h]``, ``weight`` is
+    ``[N/T, h]``, the result is ``[M, N/T]``.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, weight, bias, eps, tp):
+        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+        if tp is not None and tp.fused:
+            y, ln_full = tp.ag_gemm(ln, weight, bias)
+        else:
+            ln_full = tp.all_gather_rows(ln) if tp is not None else ln
+            y = K.gemm_nt(ln_full, weight, bias)
+        ctx.save_for_backward(x, gamma, beta, weight, bias, mean, rstd, ln_full)
+        ctx.tp = tp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, weight, bias, mean, rstd, ln_full = ctx.saved_tensors
+        tp = ctx.tp
+        dy = dy.contiguous()
+        if tp is not None and tp.fused:
+            dln = tp.gemm_rs_nn(dy, weight)
+        else:
+            dln_full = K.gemm_nn(dy, weight)
+            dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
+        dw = _wgrad(dy, ln_full, weight)
+        db = _bgrad(dy, bias)
+        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd)
+        return dx, dgamma, dbeta, dw, db, None, None
+
+
+class LinearResidual(torch.autograd.Function):
+    """``y = a @ W^T + b + residual`` with bias and residual in the GEMM epilogue.
+
+    Row-parallel under TP: ``a`` is ``[M, K/T]``, ``weight`` ``[N, K/T]``; the partial products
+    are reduce-scattered over tokens (fused: GEMM->RS) so the result and ``residual`` are the
+    local shard ``[M/T, N]``.
+    """
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, residual, tp):
+        if tp is None:
+            y = K.gemm_nt(a, weight, bias, residual)
+        elif tp.fused:
+            y = tp.gemm_rs(a, weight, bias, residual)
+        else:
+            part = K.gemm_nt(a, weight)
+            y = tp.reduce_scatter_rows(part)
+            y = y + bias + residual if bias is not None else y + residual
+        ctx.save_for_backward(a, weight, bias)
+        ctx.tp = tp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight, bias = ctx.saved_tensors
+        tp = ctx.tp
+        dy = dy.contiguous()
+        if tp is None:
+            dy_full = dy
+            da = K.gemm_nn(dy_full, weight)
+        elif tp.fused:
+            da, dy_full = tp.ag_gemm_nn(dy, weight)
+        else:
+            dy_full = tp.all_gather_rows(dy)
+            da = K.gemm_nn(dy_full, weight)
+        dw = _wgrad(dy_full, a, weight)
+        # the bias is replicated across TP ranks: each rank sums its own token shard and the
+        # gradient reducer adds the TP group's partial sums (see DataParallel / grad buffer).
+        db = _bgrad(dy, bias)
+        return da, dw, db, dy, None
+
+
+class LayerNormMLP(torch.autograd.Function):
+    """``y = fc2(gelu(fc1(LayerNorm(x)))) + b2 + x``: LN kernel, GEMM(+bias+GELU epilogue, keeps the
+    pre-activation), GEMM(+bias+residual epilogue).  Backward fuses GELU' into the fc2 dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w1, b1, w2, b2, eps, tp):
+        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+        if tp is not None and tp.fused:
+            z_holder = {}
+            h1, ln_full = tp.ag_gemm(ln, w1, b1, gelu=True, aux_holder=z_holder)
+            z = z_holder["aux"]
+            y = tp.gemm_rs(h1, w2, b2, x)
+        else:
+            ln_full = tp.all_gather_rows(ln) if tp is not None else ln
+            z = torch.empty(ln_full.shape[0], w1.shape[0], dtype=ln_full.dtype, device=ln_full.device)
+            h1 = K.gemm_nt(ln_full, w1, b1, gelu=True, aux_out=z)
+            if tp is None:
+                y = K.gemm_nt(h1, w2, b2, x)
+            else:
+                y = tp.reduce_scatter_rows(K.gemm_nt(h1, w2)) + b2 + x
+        ctx.save_for_backward(x, gamma, beta, w1, b1, w2, b2, mean, rstd, ln_full, z, h1)
+        ctx.tp = tp
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, w1, b1, w2, b2, mean, rstd, ln_full, z, h1 = ctx.saved_tensors
+        tp = ctx.tp
+        dy = dy.contiguous()
+        if tp is None:
+            dy_full = dy
+            dz = K.gemm_nn(dy_full, w2, dgelu_aux=z)
+        elif tp.fused:
+            dz, dy_full = tp.ag_gemm_nn(dy, w2, dgelu_aux=z)
+        else:
+            dy_full = tp.all_gather_rows(dy)
+            dz = K.gemm_nn(dy_full, w2, dgelu_aux=z)
+        dw2 = _wgrad(dy_full, h1, w2)
+        db2 = _bgrad(dy, b2)
+        if tp is not None and tp.fused:
+            dln = tp.gemm_rs_nn(dz, w1)
+        else:
+            dln_full = K.gemm_nn(dz, w1)
+            dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
+        dw1 = _wgrad(dz, ln_full, w1)
+        db1 = _bgrad(dz, b1)
+        # residual gradient (dy) is added inside the LN backward kernel
+        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dy)
+        return dx, dgamma, dbeta, dw1, db1, dw2, db2, None, None
+
+
+class Linear(torch.autograd.Function):
+    """``y = x @ W^T + b`` for any leading shape: tcgen05 GEMM (bias in the epilogue), dgrad and wgrad
+    GEMMs in backward.  Used by the reference-compatible Column/RowParallelLinear layers."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = K.gemm_nt(x2, weight, bias)
+        ctx.save_for_backward(x2, weight, bias)
+        ctx.shape = shape
+        return y.view(*shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, bias = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = K.gemm_nn(dy2, weight).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(dy2, x2, weight) if ctx.needs_input_grad[1] else None
+        db = _bgrad(dy2, bias) if bias is not None and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """Drop-in for ``F.linear`` that runs on the sm_100a GEMM when ``x`` is a CUDA bf16 tensor."""
+    from pipegoose_b200.ops import use_native
+
+    if use_native(x, weight) and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0:
+        return Linear.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+class MLPResidual(torch.autograd.Function):
+    """``y = fc2(gelu(fc1(x))) + b2 + residual`` (no LayerNorm, no TP): the dense MLP used as an MoE
+    expert and behind HF's ``mlp(hidden_states, residual)`` signature."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        z = torch.empty(x.shape[0], w1.shape[0], dtype=x.dtype, device=x.device)
+        h1 = K.gemm_nt(x, w1, b1, gelu=True, aux_out=z)
+        y = K.gemm_nt(h1, w2, b2, residual)
+        ctx.save_for_backward(x, w1, b1, w2, b2, z, h1)
+        ctx.has_residual = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, b1, w2, b2, z, h1 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dz = K.gemm_nn(dy, w2, dgelu_aux=z)
+        dw2 = _wgrad(dy, h1, w2)
+        db2 = _bgrad(dy, b2)
+        dx = K.gemm_nn(dz, w1)
+        dw1 = _wgrad(dz, x, w1)
+        db1 = _bgrad(dz, b1)
+        return dx, dw1, db1, dw2, db2, (dy if ctx.has_residual else None)
+
+
+class EmbeddingLayerNorm(torch.autograd.Function):
+    """``LayerNorm(table[ids])`` in one kernel (vocab-parallel aware); backward scatter-adds into
+    the table's fp32 main grad."""
+
+    @staticmethod
+    def forward(ctx, ids, table, gamma, beta, eps, vocab_start, tp):
+        vocab_end = vocab_start + table.shape[0]
+        flat = ids.reshape(-1)
+        if tp is None:
+            y, mean, rstd = K.layernorm_fwd(table, gamma, beta, eps, ids=flat, vocab_start=vocab_start, vocab_end=vocab_end)
+            e = None
+        else:
+            part, _, _ = K.layernorm_fwd(table, gamma, beta, eps, ids=flat, vocab_start=vocab_start,
+                                         vocab_end=vocab_end, apply_ln=False)
+            e = tp.reduce_scatter_rows(part.contiguous())  # [M/T, h] complete embeddings of the local tokens
+            y, mean, rstd = K.layernorm_fwd(e, gamma, beta, eps)
+        ctx.save_for_backward(flat, table, gamma, beta, mean, rstd, e if e is not None else torch.empty(0))
+        ctx.tp = tp
+        ctx.eps = eps
+        ctx.vocab_start = vocab_start
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        flat, table, gamma, beta, mean, rstd, e = ctx.saved_tensors
+        tp = ctx.tp
+        vocab_start = ctx.vocab_start
+        vocab_end = vocab_start + table.shape[0]
+        dy = dy.contiguous()
+        if tp is None:
+            e, _, _ = K.layernorm_fwd(table, gamma, beta, ctx.eps, ids=flat, vocab_start=vocab_start,
+                                      vocab_end=vocab_end, apply_ln=False)
+        de, dgamma, dbeta = _ln_bwd(dy, e, gamma, beta, mean, rstd)
+        de_full = tp.all_gather_rows(de) if tp is not None else de
+        mg = acquire_main_grad(table, will_overwrite=False)[0] if _main_grad(table) is not None else None
+        dtable = K.embedding_bwd(de_full, flat, table.shape[0], vocab_start, vocab_end, accum_into=mg)
+        if mg is not None:
+            notify_grad_ready(table)
+        return None, dtable, dgamma, dbeta, None, None, None
+
+
+class LMHeadCrossEntropy(torch.autograd.Function):
+    """``mean CE(LayerNorm(x) @ table^T, labels)`` with a vocab-parallel softmax.
+
+    The logits GEMM writes bf16 logits once; one stats kernel + one finalize kernel turn them into
+    the loss and, in place, ``dlogits`` (already scaled by 1/num_tokens), which feed the dgrad and
+    wgrad GEMMs directly.  Across TP ranks only ``[M, 3]`` floats are exchanged (max, sum-exp,
+    target logit) instead of the reference's all-gather of ``[M, V]`` logits.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp):
+        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+        ln_full = tp.all_gather_rows(ln) if tp is not None else ln
+        logits = K.gemm_nt(ln_full, table)  # [M, V/T]
+        tgt = labels.reshape(-1)
+        stats = K.ce_local_stats(logits, tgt, vocab_start)
+        if tp is not None:
+            gstats = K.ce_combine_stats(tp.all_gather_stack(stats))
+        else:
+            gstats = stats
+        n_valid = (tgt != ignore_index).sum().clamp(min=1).to(torch.float32)
+        loss_rows = K.ce_finalize(logits, tgt, gstats, vocab_start, None, ignore_index, write_grad=False)
+        loss = loss_rows.sum() / n_valid
+        ctx.save_for_backward(x, gamma, beta, table, mean, rstd, ln_full, logits, n_valid, tgt, gstats)
+        ctx.tp = tp
+        ctx.vocab_start = vocab_start
+        ctx.ignore_index = ignore_index
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, gamma, beta, table, mean, rstd, ln_full, logits, n_valid, tgt, gstats = ctx.saved_tensors
+        tp = ctx.tp
+        # dlogits = (softmax - onehot) * dloss / n_valid, written over the logits in one pass; the
+        # scale stays on the device (no host sync)
+        scale = (dloss.float() / n_valid).reshape(1)
+        K.ce_finalize(logits, tgt, gstats, ctx.vocab_start, scale, ctx.ignore_index, write_grad=True)
+        dlogits = logits
+        dln_full = K.gemm_nn(dlogits, table)
+        dtable = _wgrad(dlogits, ln_full, table)
+        dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
+        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd)
+        return dx, dgamma, dbeta, dtable, None, None, None, None, None
+
+
+def layernorm_linear(x, gamma, beta, weight, bias, eps=1e-5, tp=None):
+    return LayerNormLinear.apply(x, gamma, beta, weight, bias, eps, tp)
+
+
+def linear_residual(a, weight, bias, residual, tp=None):
+    return LinearResidual.apply(a, weight, bias, residual, tp)
+
+
+def layernorm_mlp(x, gamma, beta, w1, b1, w2, b2, eps=1e-5, tp=None):
+    return LayerNormMLP.apply(x, gamma, beta, w1, b1, w2, b2, eps, tp)
+
+
+def mlp_residual(x, w1, b1, w2, b2, residual=None):
+    return MLPResidual.apply(x, w1, b1, w2, b2, residual)
+
+
+def embedding_layernorm(ids, table, gamma, beta, eps=1e-5, vocab_start=0, tp=None):
+    return EmbeddingLayerNorm.apply(ids, table, gamma, beta, eps, vocab_start, tp)
+
+
+def lm_head_cross_entropy(x, gamma, beta, table, labels, eps=1e-5, vocab_start=0, ignore_index=-100, tp=None):
+    return LMHeadCrossEntropy.apply(x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp)

@@ -1,0 +1,115 @@
+"""Fused Adam/AdamW over a :class:`FlatModelState`.
+
+fp32 master weights and moments live in flat buffers — all of them for plain training, only this
+rank's slice of every gradient bucket under ZeRO-1 (``set_bucket_shards``).  A step is one kernel
+launch per contiguous slice: it reads the (already averaged) fp32 gradient buffer, updates master
+and moments and writes the bf16 model copy in place.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from pipegoose_b200.core.flat_state import FlatModelState
+from pipegoose_b200.ops import native, use_native
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 adamw: bool = False, flat_state: Optional[FlatModelState] = None):
+        params = list(params)
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw)
+        super().__init__(params, defaults)
+        self.flat: Optional[FlatModelState] = flat_state
+        self._segments: Optional[List[Tuple[int, int]]] = None  # [(flat_start, flat_end)] owned by this rank
+        self._step = 0
+        self.master = self.exp_avg = self.exp_avg_sq = None
+
+    def ensure_flat(self):
+        if self.flat is None:
+            params = [p for g in self.param_groups for p in g["params"]]
+            self.flat = FlatModelState.find(params) or FlatModelState(params)
+        return self.flat
+
+    # ------------------------------------------------------------------ ZeRO-1 sharding
+    def set_shard(self, start: int, end: int):
+        assert self.master is None, "set_shard must be called before the first step"
+        self._segments = [(start, end)]
+
+    def set_bucket_shards(self, bucket_numel: int, rank: int, world: int):
+        """This rank owns slice ``rank`` of every gradient bucket (what reduce-scatter leaves here)."""
+        assert self.master is None, "sharding must be fixed before the first step"
+        n = self.ensure_flat().numel
+        segs = []
+        for start in range(0, n, bucket_numel):
+            end = min(n, start + bucket_numel)
+            seg = (end - start) // world
+            segs.append((start + rank * seg, start + (rank + 1) * seg))
+        self._segments = segs
+
+    def _lazy_init(self):
+        self.ensure_flat()
+        if self._segments is None:
+            self._segments = [(0, self.flat.numel)]
+        if self.master is None:
+            total = sum(e - s for s, e in self._segments)
+            self.master = torch.empty(total, dtype=torch.float32, device=self.flat.device)
+            off = 0
+            for s, e in self._segments:
+                self.master[off:off + e - s].copy_(self.flat.flat_param[s:e])
+                off += e - s
+            self.exp_avg = torch.zeros_like(self.master)
+            self.exp_avg_sq = torch.zeros_like(self.master)
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = closure() if closure is not None else None
+        self._lazy_init()
+        self._step += 1
+        g = self.param_groups[0]
+        lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
+        off = 0
+        for s, e in self._segments:
+            n = e - s
+            grad = self.flat.flat_grad[s:e]
+            param = self.flat.flat_param[s:e]
+            master, m, v = self.master[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n]
+            off += n
+            if use_native(param):
+                native().adam_step(master, m, v, grad, param, lr, b1, b2, eps, wd, self._step, grad_scale, g["adamw"])
+            else:
+                gr = grad.float() * grad_scale
+                if wd != 0 and not g["adamw"]:
+                    gr = gr + wd * master
+                m.mul_(b1).add_(gr, alpha=1 - b1)
+                v.mul_(b2).addcmul_(gr, gr, value=1 - b2)
+                bc1, bc2 = 1 - b1 ** self._step, 1 - b2 ** self._step
+                if wd != 0 and g["adamw"]:
+                    master.mul_(1 - lr * wd)
+                master.addcdiv_(m / bc1, (v / bc2).sqrt() + eps, value=-lr)
+                param.copy_(master.to(param.dtype))
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.ensure_flat().zero_grad()
+        for p in self.flat.params:
+            p.grad = None
+
+    def state_dict(self):
+        self._lazy_init()
+        return {"step": self._step, "segments": list(self._segments), "master": self.master, "exp_avg": self.exp_avg,
+                "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self._segments = [tuple(x) for x in sd["segments"]]
+        self._lazy_init()
+        self._step = sd["step"]
+        self.master.copy_(sd["master"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        off = 0
+        for s, e in self._segments:
+            self.flat.flat_param[s:e].copy_(self.master[off:off + e - s].to(self.flat.dtype))
+            off += e - s

@@ -1,0 +1,3 @@
+from pipegoose_b200.optim.zero.optim import DistributedOptimizer
+
+__all__ = ["DistributedOptimizer"]

@@ -1,0 +1,160 @@
+"""ZeRO-1 ``DistributedOptimizer`` (parity: reference optim/zero/optim.py:14-75).
+
+Two execution paths behind the reference's API:
+
+* **fused** (``optim`` is a :class:`pipegoose_b200.optim.FusedAdam`): the gradient reducer is
+  switched to reduce-scatter, this rank's contiguous slice of every bucket is updated by ONE fused
+  Adam launch (fp32 master/moments only for the slice), and the updated bf16 slices are
+  all-gathered back into the flat parameter buffer.  Optimizer state per rank ~ 1/dp.
+* **generic** (any ``torch.optim.Optimizer``): parameters are assigned to data-parallel ranks
+  greedily (``OptimizerStateSharding``), the wrapped optimizer only keeps this rank's
+  parameters, and after the local step each owner broadcasts its updated parameters as one flat
+  tensor (the reference issues dp x groups flatten+broadcast+copy sequences).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.distributed as dist
+from torch.optim import Optimizer
+
+from pipegoose_b200.distributed.functional import broadcast
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.optim.base_optim import BaseDistributedOptimizer
+from pipegoose_b200.optim.zero.sharding import OptimizerStateSharding
+from pipegoose_b200.optim.zero.utils import copy_flatten_tensor_to_unflatten_tensors, flatten_a_list_tensor
+
+
+class DistributedOptimizer(BaseDistributedOptimizer):
+    def __init__(self, optim: Optimizer, parallel_context: ParallelContext):
+        self.optim = optim
+        self.parallel_context = parallel_context
+        self.dp = parallel_context.get_world_size(ParallelMode.DATA)
+        self.dp_rank = parallel_context.get_local_rank(ParallelMode.DATA)
+        from pipegoose_b200.optim.fused_adam import FusedAdam
+
+        self._fused = isinstance(optim, FusedAdam)
+        self._all_params = [p for g in optim.param_groups for p in g["params"]]
+        if self._fused:
+            self._zero_ready = False
+        else:
+            self._setup_generic()
+
+    # ------------------------------------------------------------------ generic path
+    def _setup_generic(self):
+        sharded = OptimizerStateSharding(self.optim.param_groups, self.parallel_context, ParallelMode.DATA).shard()
+        ranks_in_group = self.parallel_context.get_ranks_in_group(ParallelMode.DATA)
+        self._rank_to_param_groups: Dict[int, List[Dict]] = {rank: groups for rank, groups in zip(ranks_in_group, sharded)}
+        self._local_rank_to_param_groups = sharded
+        if self.dp > 1:
+            self.optim.param_groups = sharded[self.dp_rank]
+
+    def _broadcast_updated_params(self):
+        for owner in range(self.dp):
+            params = [p for g in self._local_rank_to_param_groups[owner] for p in g["params"]]
+            if not params:
+                continue
+            flat = flatten_a_list_tensor([p.data for p in params])
+            broadcast(flat, src=owner, parallel_context=self.parallel_context, parallel_mode=ParallelMode.DATA)
+            if owner != self.dp_rank:
+                copy_flatten_tensor_to_unflatten_tensors(flat, [p.data for p in params])
+
+    def _materialize_grads_from_main(self):
+        """Stock optimizers read ``p.grad``; the fused layers accumulate into ``p.main_grad``."""
+        for g in self.optim.param_groups:
+            for p in g["params"]:
+                mg = getattr(p, "main_grad", None)
+                if mg is not None and p.grad is None:
+                    p.grad = mg.to(p.dtype)
+
+    # ------------------------------------------------------------------ fused path
+    def _setup_fused(self):
+        optim = self.optim
+        flat = optim.flat
+        if flat is None:
+            optim.ensure_flat()
+            flat = optim.flat
+        self._reducer = None
+        if self.dp > 1:
+            # the module's gradient reducer (installed by DataParallel) shares the flat state
+            for p in flat.params:
+                hook = getattr(p, "_pg_grad_ready", None)
+                if hook is not None:
+                    self._reducer = hook.__self__
+                    break
+            assert self._reducer is not None and self._reducer.flat is flat, \
+                "DistributedOptimizer(FusedAdam) with dp>1 expects the module to be wrapped by DataParallel first"
+            self._reducer.mode = "reduce_scatter"
+            optim.set_bucket_shards(self._reducer.bucket_numel, self.dp_rank, self.dp)
+        self._zero_ready = True
+
+    def _all_gather_params(self):
+        flat = self.optim.flat
+        group = self.parallel_context.get_group(ParallelMode.DATA)
+        fused = getattr(self._reducer, "_fused", None)
+        if fused is not None:
+            fused.all_gather_params(flat.flat_param, self._reducer.bucket_numel)
+            return
+        B = self._reducer.bucket_numel
+        n = flat.numel
+        works = []
+        for start in range(0, n, B):
+            end = min(n, start + B)
+            seg = (end - start) // self.dp
+            view = flat.flat_param[start:end]
+            mine = view[self.dp_rank * seg:(self.dp_rank + 1) * seg]
+            if dist.get_backend(group) == "nccl":
+                works.append(dist.all_gather_into_tensor(view, mine, group=group, async_op=True))
+            else:
+                parts = [torch.empty_like(mine) for _ in range(self.dp)]
+                dist.all_gather(parts, mine.clone(), group=group)
+                view.copy_(torch.cat(parts))
+        for w in works:
+            w.wait()
+
+    # ------------------------------------------------------------------ optimizer API
+    @property
+    def defaults(self):
+        return self.optim.defaults
+
+    @property
+    def param_groups(self):
+        return self.optim.param_groups
+
+    def add_param_group(self, *args, **kwargs):
+        self.optim.add_param_group(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.optim.load_state_dict(*args, **kwargs)
+
+    def state_dict(self, *args, **kwargs):
+        return self.optim.state_dict(*args, **kwargs)
+
+    @torch.no_grad()
+    def step(self, *args, **kwargs):
+        if self._fused:
+            if not self._zero_ready:
+                self._setup_fused()
+            self.optim.step(*args, **kwargs)
+            if self.dp > 1:
+                self._all_gather_params()
+            return
+        self._materialize_grads_from_main()
+        self.optim.step(*args, **kwargs)
+        if self.dp > 1:
+            self._broadcast_updated_params()
+
+    def zero_grad(self):
+        if self._fused:
+            if not self._zero_ready:
+                self._setup_fused()
+            self.optim.zero_grad()
+            return
+        for p in self._all_params:
+            p.grad = None
+            if hasattr(p, "main_grad"):
+                p._mg_fresh = p.dim() >= 2
+                if p.dim() < 2:
+                    p.main_grad.zero_()

@@ -1,0 +1,80 @@
+"""Sequence-parallel tensor-parallel communicator used by the fused sub-layer functions.
+
+Library mode (``fused=False``): NCCL/gloo all-gather / reduce-scatter around plain GEMMs — the
+correctness baseline, and what CPU tests run.  Fused mode (``fused=True``): the hand-written
+sm_100a kernels in which the collective is part of the GEMM (``pipegoose_b200.ops.comm``):
+
+    ag_gemm     all-gather -> GEMM      (column-parallel forward, row-parallel dgrad)
+    gemm_rs     GEMM -> reduce-scatter  (row-parallel forward, column-parallel dgrad)
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+
+class TensorParallelComm:
+    def __init__(self, parallel_context, parallel_mode: ParallelMode = ParallelMode.TENSOR, fused=None):
+        self.ctx = parallel_context
+        self.mode = parallel_mode
+        self.group = parallel_context.get_group(parallel_mode)
+        self.size = parallel_context.get_world_size(parallel_mode)
+        self.rank = parallel_context.get_local_rank(parallel_mode)
+        self._engine = None
+        want = os.environ.get("PIPEGOOSE_B200_FUSED_TP", "1") == "1" if fused is None else fused
+        self.fused = False
+        self._want_fused = want and dist.get_backend(self.group) == "nccl" and torch.cuda.is_available()
+
+    def enable_fused(self):
+        """Create the NVLink peer-memory engine (symmetric workspace + fused kernels); collective call."""
+        if self._want_fused and self._engine is None:
+            from pipegoose_b200.ops.comm import FusedTPEngine
+
+            self._engine = FusedTPEngine(self)
+            self.fused = True
+
+    # ------------------------------------------------------------------ library collectives
+    def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.contiguous()
+        out = torch.empty((x.shape[0] * self.size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=self.group)
+        return out
+
+    def all_gather_stack(self, x: torch.Tensor) -> torch.Tensor:
+        return self.all_gather_rows(x.unsqueeze(0))
+
+    def all_gather_cols(self, x: torch.Tensor) -> torch.Tensor:
+        full = self.all_gather_rows(x.unsqueeze(0))  # [T, M, n]
+        return full.permute(1, 0, 2).reshape(x.shape[0], -1)
+
+    def reduce_scatter_rows(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.contiguous()
+        assert x.shape[0] % self.size == 0
+        rows = x.shape[0] // self.size
+        if dist.get_backend(self.group) == "gloo":
+            dist.all_reduce(x, group=self.group)
+            return x[self.rank * rows:(self.rank + 1) * rows].clone()
+        out = torch.empty((rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, x, group=self.group)
+        return out
+
+    def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(x, group=self.group)
+        return x
+
+    # ------------------------------------------------------------------ fused kernels
+    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
+        return self._engine.ag_gemm(x_shard, weight, bias, gelu, aux_holder)
+
+    def gemm_rs(self, a, weight, bias=None, residual=None):
+        return self._engine.gemm_rs(a, weight, bias, residual)
+
+    def ag_gemm_nn(self, dy_shard, weight, dgelu_aux=None):
+        return self._engine.ag_gemm_nn(dy_shard, weight, dgelu_aux)
+
+    def gemm_rs_nn(self, dy, weight):
+        return self._engine.gemm_rs_nn(dy, weight)

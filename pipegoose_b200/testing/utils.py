@@ -1,0 +1,110 @@
+"""Multi-process test harness (parity: reference pipegoose/testing/utils.py:16-133).
+
+``spawn`` starts ``world_size`` local processes with a real backend (gloo on CPU, nccl on GPU
+boxes); nothing is mocked.
+"""
+from __future__ import annotations
+
+import os
+import random
+import socket
+from functools import partial
+from typing import Callable
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+
+skip_in_github_actions = pytest.mark.skipif(os.getenv("GITHUB_ACTIONS") == "true", reason="Test skipped in GitHub Actions")
+skip_if_no_cuda = pytest.mark.skipif(not torch.cuda.is_available(), reason="Test requires CUDA")
+
+
+def find_free_port(min_port: int = 2000, max_port: int = 65000) -> int:
+    while True:
+        port = random.randint(min_port, max_port)
+        try:
+            with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+                sock.bind(("127.0.0.1", port))
+                return port
+        except OSError:
+            continue
+
+
+def _entry(rank: int, world_size: int, port: int, func: Callable, kwargs: dict):
+    func(rank=rank, world_size=world_size, port=port, **kwargs)
+
+
+def spawn(func: Callable, world_size: int = 1, **kwargs):
+    """Run ``func(rank, world_size, port, **kwargs)`` in ``world_size`` fresh processes."""
+    if kwargs.get("port") is None:
+        kwargs.pop("port", None)
+        port = find_free_port()
+    else:
+        port = kwargs.pop("port")
+    mp.spawn(_entry, args=(world_size, port, func, kwargs), nprocs=world_size, join=True)
+
+
+def init_parallel_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size, data_parallel_size,
+                          backend: str = "gloo", host: str = "127.0.0.1", seed: int = 69) -> ParallelContext:
+    return ParallelContext(
+        rank=rank,
+        local_rank=rank,
+        world_size=world_size,
+        local_world_size=world_size,
+        host=host,
+        port=port,
+        seed=seed,
+        backend=backend,
+        tensor_parallel_size=tensor_parallel_size,
+        pipeline_parallel_size=pipeline_parallel_size,
+        data_parallel_size=data_parallel_size,
+    )
+
+
+def init_pipeline_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size, data_parallel_size,
+                          n_partitions=None, n_microbatches=None):
+    from pipegoose_b200.nn.pipeline_parallel.pipeline_context import PipelineContext
+    from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType, get_scheduler
+
+    parallel_context = init_parallel_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size,
+                                             data_parallel_size)
+    n_partitions = n_partitions or pipeline_parallel_size
+    n_microbatches = n_microbatches or 4
+    scheduler = get_scheduler(SchedulerType.GPIPE)(n_microbatches, n_partitions)
+    pipeline_context = PipelineContext(scheduler, parallel_context)
+    return pipeline_context, parallel_context
+
+
+def get_partition(data: torch.Tensor, dim: int, parallel_context: ParallelContext) -> torch.Tensor:
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+    local_world_size = parallel_context.get_world_size(ParallelMode.TENSOR)
+    local_rank = parallel_context.get_local_rank(ParallelMode.TENSOR)
+    chunks = torch.chunk(data, chunks=local_world_size, dim=dim)
+    return chunks[local_rank]
+
+
+def get_microbatch(inputs, labels, parallel_context: ParallelContext, parallel_mode):
+    local_rank = parallel_context.get_local_rank(parallel_mode)
+    world_size = parallel_context.get_world_size(parallel_mode)
+    input_chunks = torch.chunk(inputs["input_ids"], chunks=world_size)
+    attention_chunks = torch.chunk(inputs["attention_mask"], chunks=world_size)
+    label_chunks = torch.chunk(labels, chunks=world_size)
+    return input_chunks[local_rank], attention_chunks[local_rank], label_chunks[local_rank]
+
+
+def calculate_parameter_similarity(module1: nn.Module, module2: nn.Module, rtol: float = 1e-3) -> float:
+    """Fraction of parameter elements that agree within ``rtol`` between two modules."""
+    total, close = 0, 0
+    for p1, p2 in zip(module1.parameters(), module2.parameters()):
+        assert p1.size() == p2.size()
+        total += p1.numel()
+        close += torch.isclose(p1, p2, rtol=rtol).sum().item()
+    return close / max(total, 1)
+
+
+def count_model_parameters(model: nn.Module) -> int:
+    return sum(p.numel() for p in model.parameters())
