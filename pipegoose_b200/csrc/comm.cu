@@ -1,0 +1,293 @@
+// Collective kernels over NVLink peer mappings (NVSwitch: every peer at full bandwidth, so all
+// of these are direct all-to-all patterns, no rings):
+//   rs_reduce      second half of GEMM->reduce-scatter: sum the T staged partial tiles (+bias,
+//                  +residual) once every source's arrival counter says its tiles landed
+//   allreduce_f32  data-parallel gradient bucket: two-shot (reduce-scatter by pulling peers'
+//                  slices, then all-gather by pushing the reduced slice), fused with the 1/dp
+//                  scale; reduce_scatter_only leaves rank r with slice r (ZeRO-1)
+//   allgather_bf16 ZeRO-1 parameter all-gather: push my updated bf16 slices to every peer
+//   barrier_peers  flag barrier (release/acquire at system scope)
+// plus the cudaIpc-based symmetric allocation helpers.
+#include "launch.h"
+#include "ptx.cuh"
+#include <cstdio>
+#include <cstring>
+
+namespace pg {
+
+__global__ void __launch_bounds__(256) rs_reduce_kernel(
+    const __nv_bfloat16* __restrict__ staging, int num_src, int64_t src_stride,
+    const uint32_t* __restrict__ arrive_ctr, uint32_t expected, const __nv_bfloat16* __restrict__ bias,
+    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int rows, int cols) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_src; ++s)
+      while (ld_acquire_sys(arrive_ctr + s) < expected) {
+      }
+  }
+  __syncthreads();
+  const int64_t nvec = static_cast<int64_t>(rows) * cols / 8;
+  const int cvec = cols / 8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < num_src; ++s) {
+      const uint4 v = ld_global_v4(staging + s * src_stride + i * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    if (bias != nullptr) {
+      const uint4 v = ld_global_nc_v4(bias + (i % cvec) * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    if (residual != nullptr) {
+      const uint4 v = ld_global_nc_v4(residual + i * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    st_global_v4(out + i * 8, make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7])));
+  }
+}
+
+struct PeerPtrs {
+  float* buf[PG_MAX_PEERS];
+  uint32_t* flag[PG_MAX_PEERS];
+};
+
+// flag layout per rank: flags[phase * PG_MAX_PEERS + src]
+PG_DEVICE void peer_barrier(const PeerPtrs& p, int world, int rank, uint32_t value, int phase) {
+  // executed by one block; thread t < world signals peer t, then waits for peer t's signal
+  if (threadIdx.x < world) {
+    fence_acq_rel_sys();
+    st_release_sys(p.flag[threadIdx.x] + phase * PG_MAX_PEERS + rank, value);
+    while (ld_acquire_sys(p.flag[rank] + phase * PG_MAX_PEERS + threadIdx.x) < value) {
+    }
+  }
+}
+
+// Two-shot all-reduce (average) of buf[offset : offset+n) in place on every rank.
+// grid-wide phases are separated by a device-wide counter (cooperative-free: all CTAs resident).
+__global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int world, int rank,
+                                                            int64_t offset, int64_t n, float scale,
+                                                            int rs_only, uint32_t epoch,
+                                                            uint32_t* __restrict__ grid_ctr) {
+  // phase 0: everyone's bucket is complete locally (kernel boundary) -> cross-rank barrier
+  if (blockIdx.x == 0) peer_barrier(p, world, rank, epoch, 0);
+  // release the other CTAs of this rank
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence();
+      atomicExch(grid_ctr, epoch);
+    } else {
+      while (ld_acquire_sys(grid_ctr) < epoch) {
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t seg = n / world;  // n is a multiple of world * 4
+  const int64_t my0 = offset + rank * seg;
+  const int64_t nvec = seg / 4;
+  // reduce my slice: pull the same slice from every peer
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int s = 0; s < world; ++s) {
+      int src = rank + s;
+      if (src >= world) src -= world;
+      const float4 v = *reinterpret_cast<const float4*>(p.buf[src] + my0 + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+    if (rs_only) {
+      *reinterpret_cast<float4*>(p.buf[rank] + my0 + i * 4) = acc;
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < world; ++s) {
+        int dst = rank + s;
+        if (dst >= world) dst -= world;
+        *reinterpret_cast<float4*>(p.buf[dst] + my0 + i * 4) = acc;
+      }
+    }
+  }
+  // phase 1: all ranks finished reading my buffer / writing into it
+  __syncthreads();
+  __shared__ uint32_t last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(grid_ctr + 1, 1u) == gridDim.x * epoch - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (last) peer_barrier(p, world, rank, epoch, 1);
+}
+
+struct PeerPtrsBf16 {
+  __nv_bfloat16* buf[PG_MAX_PEERS];
+  uint32_t* flag[PG_MAX_PEERS];
+};
+
+// push my slice of every bucket of the flat bf16 parameter buffer to all peers
+__global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int world, int rank,
+                                                             int64_t bucket_elems, int64_t total_elems,
+                                                             uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
+  const int64_t nb = (total_elems + bucket_elems - 1) / bucket_elems;
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t start = b * bucket_elems;
+    const int64_t len = min(bucket_elems, total_elems - start);
+    const int64_t seg = len / world;
+    const int64_t my0 = start + rank * seg;
+    const int64_t nvec = seg / 8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const uint4 v = ld_global_v4(p.buf[rank] + my0 + i * 8);
+#pragma unroll 1
+      for (int s = 1; s < world; ++s) {
+        int dst = rank + s;
+        if (dst >= world) dst -= world;
+        st_global_v4(p.buf[dst] + my0 + i * 8, v);
+      }
+    }
+  }
+  __syncthreads();
+  __shared__ uint32_t last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(grid_ctr + 1, 1u) == gridDim.x * epoch - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (last) {
+    PeerPtrs q;
+    for (int i = 0; i < PG_MAX_PEERS; ++i) q.flag[i] = p.flag[i];
+    peer_barrier(q, world, rank, epoch, 1);
+  }
+}
+
+__global__ void barrier_kernel(PeerPtrs p, int world, int rank, uint32_t epoch) {
+  peer_barrier(p, world, rank, epoch, 0);
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+#define PG_CHECK_LAUNCH(name)                                                       \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      fprintf(stderr, "pipegoose_b200: %s launch failed: %s\n", name, cudaGetErrorString(e__)); \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+extern "C" int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride_elems,
+                            const uint32_t* arrive_ctr, uint32_t expected, const void* bias,
+                            const void* residual, void* out, int rows, int cols, cudaStream_t s) {
+  if (rows == 0) return 0;
+  if (cols % 8 != 0) return -1;
+  const int64_t nvec = static_cast<int64_t>(rows) * cols / 8;
+  int blocks = static_cast<int>((nvec + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rs_reduce_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)staging, num_src, src_stride_elems,
+                                          arrive_ctr, expected, (const __nv_bfloat16*)bias,
+                                          (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, rows, cols);
+  PG_CHECK_LAUNCH("rs_reduce");
+  return 0;
+}
+
+// grid_ctr: two uint32 in LOCAL memory right after the flag area: peer_flags[rank] + 2*PG_MAX_PEERS
+extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems,
+                                int64_t n, float scale, int reduce_scatter_only,
+                                uint32_t* const* peer_flags, uint32_t epoch, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (n % (world * 4) != 0) return -1;
+  PeerPtrs p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < world; ++i) {
+    p.buf[i] = peer_bufs[i];
+    p.flag[i] = peer_flags[i];
+  }
+  // few CTAs: the kernel is NVLink-bound and must leave the SMs to the backward GEMMs it overlaps
+  const int blocks = 16;
+  allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, world, rank, offset_elems, n, scale,
+                                              reduce_scatter_only, epoch,
+                                              peer_flags[rank] + 2 * PG_MAX_PEERS);
+  PG_CHECK_LAUNCH("allreduce_f32");
+  return 0;
+}
+
+extern "C" int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, int64_t offset_elems,
+                                 int64_t n_per_rank, int64_t bucket_elems, int64_t total_elems,
+                                 uint32_t* const* peer_flags, uint32_t epoch, cudaStream_t s) {
+  (void)offset_elems;
+  (void)n_per_rank;
+  PeerPtrsBf16 p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < world; ++i) {
+    p.buf[i] = (__nv_bfloat16*)peer_bufs[i];
+    p.flag[i] = peer_flags[i];
+  }
+  const int blocks = 32;
+  allgather_bf16_kernel<<<blocks, 512, 0, s>>>(p, world, rank, bucket_elems, total_elems, epoch,
+                                               peer_flags[rank] + 2 * PG_MAX_PEERS);
+  PG_CHECK_LAUNCH("allgather_bf16");
+  return 0;
+}
+
+extern "C" int pg_barrier_peers(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch,
+                                cudaStream_t s) {
+  PeerPtrs p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < world; ++i) p.flag[i] = peer_flags[i];
+  barrier_kernel<<<1, 32, 0, s>>>(p, world, rank, epoch);
+  PG_CHECK_LAUNCH("barrier_peers");
+  return 0;
+}
+
+extern "C" int pg_symm_alloc(int64_t nbytes, void** ptr, void* handle64) {
+  cudaError_t e = cudaMalloc(ptr, nbytes);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "pipegoose_b200: symmetric cudaMalloc(%lld) failed: %s\n", (long long)nbytes, cudaGetErrorString(e));
+    return -1;
+  }
+  cudaMemset(*ptr, 0, nbytes);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "pipegoose_b200: cudaIpcGetMemHandle failed: %s\n", cudaGetErrorString(e));
+    return -1;
+  }
+  static_assert(sizeof(h) == 64, "ipc handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int pg_symm_open(const void* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "pipegoose_b200: cudaIpcOpenMemHandle failed: %s\n", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+extern "C" int pg_symm_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? 0 : -1; }
+extern "C" int pg_symm_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? 0 : -1; }

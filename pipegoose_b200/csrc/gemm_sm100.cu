@@ -119,7 +119,9 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
   }
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
   const int tiles = ((chunk_rows + BM - 1) / BM) * ((args.N + BN - 1) / BN) * args.num_chunks;
-  int grid = tiles < max_ctas ? tiles : max_ctas;
+  int gemm_ctas = max_ctas - args.n_comm;
+  if (gemm_ctas < 1) gemm_ctas = 1;
+  int grid = (tiles < gemm_ctas ? tiles : gemm_ctas) + args.n_comm;
   if (grid < 1) grid = 1;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
   cudaError_t e = cudaGetLastError();
@@ -176,13 +178,23 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
     args.out_peer[i] = d->out_peer[i];
     args.arrive_ctr[i] = d->arrive_ctr[i];
   }
+  args.n_comm = d->n_comm;
+  args.ag_dst = d->ag_dst;
+  args.ag_chunk_bytes = d->ag_chunk_bytes;
+  args.ag_ready = d->ag_ready;
+  args.ag_epoch = d->ag_epoch;
+  args.my_rank = d->my_rank;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    args.ag_src[i] = d->ag_src[i];
+    args.ag_peer_flag[i] = d->ag_peer_flag[i];
+  }
   if (args.num_chunks > 1 && (args.chunk_rows % BM) != 0) {
     fprintf(stderr, "pipegoose_b200: chunk_rows (%d) must be a multiple of %d\n", args.chunk_rows, BM);
     return -1;
   }
   int max_ctas = d->max_ctas > 0 ? d->max_ctas : num_sms();
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
-  int bn = d->block_n > 0 ? d->block_n : pick_bn(chunk_rows, args.N, args.num_chunks, max_ctas);
+  int bn = d->block_n > 0 ? d->block_n : pick_bn(chunk_rows, args.N, args.num_chunks, max_ctas - args.n_comm);
 
   CUtensorMap ta, tb;
   // A: K-major  -> matrix [M, K] (ld = lda), box [128 rows, 64]

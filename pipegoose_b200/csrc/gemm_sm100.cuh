@@ -48,6 +48,16 @@ struct GemmArgs {
   // all-gather -> GEMM: chunk c is readable once chunk_flags[c] >= flag_value
   const uint32_t* chunk_flags;
   uint32_t flag_value;
+  // comm CTAs (blockIdx.x < n_comm) pull every rank's shard into the local gathered A matrix with
+  // bulk async copies (peer global -> smem -> local global) and publish chunk_flags (+1 per CTA)
+  int n_comm;
+  const void* ag_src[kMaxPeers];     // rank r's shard (NVLink peer mapping; ag_src[my_rank] is local)
+  void* ag_dst;                      // local gathered matrix [num_chunks * chunk_rows, K]
+  uint64_t ag_chunk_bytes;           // bytes of one shard
+  uint32_t* ag_peer_flag[kMaxPeers]; // &peer_r.shard_ready[my_rank]: tell rank r that my shard is readable
+  const uint32_t* ag_ready;          // local shard_ready[src] (written by src), wait >= ag_epoch
+  uint32_t ag_epoch;
+  int my_rank;
   // GEMM -> reduce-scatter: rows of chunk c go to out_peer[c] (row index relative to chunk),
   // then arrive_ctr[c] (+1 per finished tile, release.sys)
   void* out_peer[kMaxPeers];
@@ -138,6 +148,67 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int num_tiles = m_blks_per_chunk * n_blks * args.num_chunks;
   const int num_kb = (args.K + BK - 1) / BK;
 
+  if (static_cast<int>(blockIdx.x) < args.n_comm) {
+    // ============================ communication CTA ============================
+    // One thread drives a ring of bulk copies: peer shard -> shared memory -> local gathered
+    // matrix, 32 KB per copy, kCommStages copies in flight.  Shards are visited starting with the
+    // local one so the GEMM CTAs can start immediately.
+    constexpr uint32_t kSlice = 32 * 1024;
+    constexpr int kCommStages = 6;
+    uint64_t* cbar = reinterpret_cast<uint64_t*>(smem + kCommStages * kSlice);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kCommStages; ++i) mbar_init(&cbar[i], 1);
+      fence_mbar_init();
+      if (blockIdx.x == 0) {
+        // my shard was produced by the previous kernel on this stream: publish it to every peer
+        fence_acq_rel_sys();
+        for (int p = 0; p < args.num_chunks; ++p)
+          if (p != args.my_rank) st_release_sys(args.ag_peer_flag[p], args.ag_epoch);
+      }
+      uint32_t ph[kCommStages];
+      for (int i = 0; i < kCommStages; ++i) ph[i] = 0;
+      const uint64_t nslices = (args.ag_chunk_bytes + kSlice - 1) / kSlice;
+      for (int i = 0; i < args.num_chunks; ++i) {
+        int src = args.my_rank + i;
+        if (src >= args.num_chunks) src -= args.num_chunks;
+        if (src != args.my_rank) {
+          while (ld_acquire_sys(args.ag_ready + src) < args.ag_epoch) {
+          }
+        }
+        const uint8_t* from = reinterpret_cast<const uint8_t*>(args.ag_src[src]);
+        uint8_t* to = reinterpret_cast<uint8_t*>(args.ag_dst) + static_cast<uint64_t>(src) * args.ag_chunk_bytes;
+        // software pipeline over this CTA's slices: issue loads kCommStages ahead of the stores
+        uint64_t issued = 0, stored = 0;
+        const uint64_t first = blockIdx.x, step = args.n_comm;
+        const uint64_t mine = (nslices > first) ? (nslices - first + step - 1) / step : 0;
+        while (stored < mine) {
+          while (issued < mine && issued - stored < kCommStages) {
+            const int st = issued % kCommStages;
+            const uint64_t off = (first + issued * step) * kSlice;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kSlice), args.ag_chunk_bytes - off));
+            if (issued >= static_cast<uint64_t>(kCommStages)) tma_store_wait_read<0>();
+            mbar_arrive_expect_tx(&cbar[st], bytes);
+            bulk_load_1d(smem + st * kSlice, from + off, bytes, &cbar[st]);
+            ++issued;
+          }
+          const int st = stored % kCommStages;
+          const uint64_t off = (first + stored * step) * kSlice;
+          const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kSlice), args.ag_chunk_bytes - off));
+          mbar_wait(&cbar[st], ph[st]);
+          ph[st] ^= 1;
+          bulk_store_1d(to + off, smem + st * kSlice, bytes);
+          tma_store_commit();
+          ++stored;
+        }
+        tma_store_wait<0>();  // this CTA's part of the shard is written
+        fence_proxy_async_global();
+        __threadfence();
+        atomicAdd(const_cast<uint32_t*>(args.chunk_flags) + src, 1u);
+      }
+    }
+    return;
+  }
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -167,7 +238,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int seen_chunk = -1;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm) {
       const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
       if (args.chunk_flags != nullptr && tc.chunk != seen_chunk) {
         if (lane == 0) {
@@ -214,7 +285,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -251,7 +322,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int q = warp - 4;  // == warp % 4 -> TMEM lanes [32q, 32q+32)
     int it = 0;
     const bool out_f32 = (args.flags & EPI_OUT_F32) != 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm, ++it) {
       const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;

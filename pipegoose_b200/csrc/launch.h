@@ -31,7 +31,36 @@ typedef struct PgGemmDesc {
   uint32_t flag_value;
   void* out_peer[PG_MAX_PEERS];
   uint32_t* arrive_ctr[PG_MAX_PEERS];
+  // all-gather -> GEMM communication CTAs
+  int n_comm;
+  const void* ag_src[PG_MAX_PEERS];
+  void* ag_dst;
+  uint64_t ag_chunk_bytes;
+  uint32_t* ag_peer_flag[PG_MAX_PEERS];
+  const uint32_t* ag_ready;
+  uint32_t ag_epoch;
+  int my_rank;
 } PgGemmDesc;
+
+// ---- comm.cu
+// out[rows, cols] = sum_src staging[src][rows, cols] (+ bias) (+ residual), after every source's
+// arrival counter reached `expected`
+int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride_elems, const uint32_t* arrive_ctr,
+                 uint32_t expected, const void* bias, const void* residual, void* out, int rows, int cols,
+                 cudaStream_t s);
+// flat fp32 gradient bucket: in-place all-reduce / reduce-scatter average over NVLink peers
+int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n,
+                     float scale, int reduce_scatter_only, uint32_t* const* peer_flags, uint32_t epoch,
+                     cudaStream_t s);
+int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n_per_rank,
+                      int64_t bucket_elems, int64_t total_elems, uint32_t* const* peer_flags, uint32_t epoch,
+                      cudaStream_t s);
+int pg_barrier_peers(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, cudaStream_t s);
+// symmetric memory (cudaIpc)
+int pg_symm_alloc(int64_t nbytes, void** ptr, void* handle64);
+int pg_symm_open(const void* handle64, void** ptr);
+int pg_symm_close(void* ptr);
+int pg_symm_free(void* ptr);
 
 int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream);
 
