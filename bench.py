@@ -259,8 +259,12 @@ def run_reference(args):
         return
 
     tp, dp = parallel_layout(args.gpus)
+    # The reference issues collectives on CPU tensors during bring-up (parallel_context.py:263-287), which a
+    # pure "nccl" group rejects; torch's per-device backend string gives it gloo for those and NCCL for CUDA
+    # tensors.  This is an argument of the reference's public API, not a change to it.
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     ctx = ParallelContext.from_torch(tensor_parallel_size=tp, pipeline_parallel_size=1, data_parallel_size=dp,
-                                     backend="nccl")
+                                     backend="cpu:gloo,cuda:nccl")
     ctx.set_device()
     rank = ctx.get_global_rank()
     dev = torch.device("cuda", torch.cuda.current_device())

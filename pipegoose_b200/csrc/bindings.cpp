@@ -25,7 +25,7 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
           const c10::optional<torch::Tensor>& aux, int64_t flags, int64_t block_n,
           int64_t max_ctas, int64_t num_chunks, int64_t first_chunk, int64_t chunk_flags_ptr,
           int64_t flag_value, std::vector<int64_t> out_peer_ptrs,
-          std::vector<int64_t> arrive_ctr_ptrs) {
+          std::vector<int64_t> arrive_ctr_ptrs, const py::dict& ag) {
   check_bf16_2d(a, "a");
   check_bf16_2d(b, "b");
   c10::cuda::CUDAGuard guard(a.device());
@@ -83,6 +83,18 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   d.flag_value = (uint32_t)flag_value;
   for (size_t i = 0; i < out_peer_ptrs.size() && i < PG_MAX_PEERS; ++i) d.out_peer[i] = reinterpret_cast<void*>(out_peer_ptrs[i]);
   for (size_t i = 0; i < arrive_ctr_ptrs.size() && i < PG_MAX_PEERS; ++i) d.arrive_ctr[i] = reinterpret_cast<uint32_t*>(arrive_ctr_ptrs[i]);
+  if (ag.size() > 0) {
+    d.n_comm = ag["n_comm"].cast<int>();
+    d.ag_dst = reinterpret_cast<void*>(ag["dst"].cast<int64_t>());
+    d.ag_chunk_bytes = (uint64_t)ag["chunk_bytes"].cast<int64_t>();
+    d.ag_ready = reinterpret_cast<const uint32_t*>(ag["ready"].cast<int64_t>());
+    d.ag_epoch = (uint32_t)ag["epoch"].cast<int64_t>();
+    d.my_rank = ag["rank"].cast<int>();
+    auto src = ag["src"].cast<std::vector<int64_t>>();
+    auto pf = ag["peer_flag"].cast<std::vector<int64_t>>();
+    for (size_t i = 0; i < src.size() && i < PG_MAX_PEERS; ++i) d.ag_src[i] = reinterpret_cast<const void*>(src[i]);
+    for (size_t i = 0; i < pf.size() && i < PG_MAX_PEERS; ++i) d.ag_peer_flag[i] = reinterpret_cast<uint32_t*>(pf[i]);
+  }
   TORCH_CHECK(pg_gemm_bf16(&d, cur_stream()) == 0, "pg_gemm_bf16 failed");
 }
 
@@ -192,6 +204,81 @@ void accum_bf16_to_f32(const torch::Tensor& src, torch::Tensor dst, double scale
   TORCH_CHECK(pg_accum_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), (float)scale, accumulate, cur_stream()) == 0, "accum failed");
 }
 
+
+void attention_fwd(const torch::Tensor& qkv, const torch::Tensor& slopes, torch::Tensor out, torch::Tensor lse,
+                   int64_t B, int64_t S, int64_t H, int64_t D) {
+  PG_CUDA(qkv); PG_BF16(qkv); PG_CUDA(out); PG_BF16(out); PG_CUDA(slopes); PG_F32(slopes); PG_CUDA(lse); PG_F32(lse);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.numel() == B * S * H * 3 * D && out.numel() == B * S * H * D && lse.numel() == B * H * S && slopes.numel() == H, "attention_fwd: shape mismatch");
+  TORCH_CHECK(pg_attention_fwd(qkv.data_ptr(), slopes.data_ptr<float>(), out.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, cur_stream()) == 0, "attention_fwd failed");
+}
+
+void attention_bwd(const torch::Tensor& qkv, const torch::Tensor& slopes, const torch::Tensor& out, const torch::Tensor& lse,
+                   const torch::Tensor& dout, torch::Tensor dqkv, int64_t B, int64_t S, int64_t H, int64_t D) {
+  PG_CUDA(qkv); PG_BF16(qkv); PG_CUDA(out); PG_BF16(out); PG_CUDA(dout); PG_BF16(dout); PG_CUDA(dqkv); PG_BF16(dqkv); PG_CUDA(lse); PG_F32(lse);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(dout.numel() == out.numel() && dqkv.numel() == qkv.numel(), "attention_bwd: shape mismatch");
+  auto dq_acc = torch::empty({B * S, H * D}, qkv.options().dtype(torch::kFloat32));
+  auto delta = torch::empty({B, H, S}, qkv.options().dtype(torch::kFloat32));
+  TORCH_CHECK(pg_attention_bwd(qkv.data_ptr(), slopes.data_ptr<float>(), out.data_ptr(), lse.data_ptr<float>(), dout.data_ptr(), dqkv.data_ptr(),
+                               dq_acc.data_ptr<float>(), delta.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, cur_stream()) == 0, "attention_bwd failed");
+}
+
+// ---------------------------------------------------------------- symmetric memory / collectives
+py::tuple symm_alloc(int64_t nbytes) {
+  void* ptr = nullptr;
+  char handle[64];
+  TORCH_CHECK(pg_symm_alloc(nbytes, &ptr, handle) == 0, "symm_alloc failed");
+  return py::make_tuple(reinterpret_cast<int64_t>(ptr), py::bytes(handle, 64));
+}
+int64_t symm_open(const std::string& handle) {
+  TORCH_CHECK(handle.size() == 64, "bad ipc handle");
+  void* ptr = nullptr;
+  TORCH_CHECK(pg_symm_open(handle.data(), &ptr) == 0, "symm_open failed");
+  return reinterpret_cast<int64_t>(ptr);
+}
+void symm_close(int64_t ptr) { pg_symm_close(reinterpret_cast<void*>(ptr)); }
+void symm_free(int64_t ptr) { pg_symm_free(reinterpret_cast<void*>(ptr)); }
+
+torch::Tensor tensor_from_ptr(int64_t ptr, int64_t nbytes, int64_t device_index) {
+  auto opts = torch::TensorOptions().dtype(torch::kUInt8).device(torch::kCUDA, (int)device_index);
+  return torch::from_blob(reinterpret_cast<void*>(ptr), {nbytes}, [](void*) {}, opts);
+}
+
+void rs_reduce(int64_t staging_ptr, int64_t num_src, int64_t src_stride, int64_t ctr_ptr, int64_t expected,
+               const c10::optional<torch::Tensor>& bias, const c10::optional<torch::Tensor>& residual, torch::Tensor out) {
+  PG_CUDA(out); PG_BF16(out);
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(pg_rs_reduce(reinterpret_cast<const void*>(staging_ptr), (int)num_src, src_stride,
+                           reinterpret_cast<const uint32_t*>(ctr_ptr), (uint32_t)expected, opt_ptr(bias), opt_ptr(residual),
+                           out.data_ptr(), (int)out.size(0), (int)out.size(1), cur_stream()) == 0, "rs_reduce failed");
+}
+
+void allreduce_f32(std::vector<int64_t> peer_bufs, int64_t rank, int64_t offset, int64_t n, double scale, bool rs_only,
+                   std::vector<int64_t> peer_flags, int64_t epoch) {
+  float* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
+  const int world = (int)peer_bufs.size();
+  TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
+  for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<float*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  TORCH_CHECK(pg_allreduce_f32(bufs, world, (int)rank, offset, n, (float)scale, rs_only, flags, (uint32_t)epoch, cur_stream()) == 0, "allreduce_f32 failed");
+}
+
+void allgather_bf16(std::vector<int64_t> peer_bufs, int64_t rank, int64_t bucket_elems, int64_t total_elems,
+                    std::vector<int64_t> peer_flags, int64_t epoch) {
+  void* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
+  const int world = (int)peer_bufs.size();
+  TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
+  for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<void*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
+  TORCH_CHECK(pg_allgather_bf16(bufs, world, (int)rank, 0, 0, bucket_elems, total_elems, flags, (uint32_t)epoch, cur_stream()) == 0, "allgather_bf16 failed");
+}
+
+void barrier_peers(std::vector<int64_t> peer_flags, int64_t rank, int64_t epoch) {
+  uint32_t* flags[PG_MAX_PEERS];
+  const int world = (int)peer_flags.size();
+  for (int i = 0; i < world; ++i) flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]);
+  TORCH_CHECK(pg_barrier_peers(flags, world, (int)rank, (uint32_t)epoch, cur_stream()) == 0, "barrier_peers failed");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -201,7 +288,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("flags") = 0, py::arg("block_n") = 0, py::arg("max_ctas") = 0,
         py::arg("num_chunks") = 1, py::arg("first_chunk") = 0, py::arg("chunk_flags_ptr") = 0,
         py::arg("flag_value") = 0, py::arg("out_peer_ptrs") = std::vector<int64_t>{},
-        py::arg("arrive_ctr_ptrs") = std::vector<int64_t>{});
+        py::arg("arrive_ctr_ptrs") = std::vector<int64_t>{}, py::arg("ag") = py::dict());
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("colsum", &colsum);
@@ -211,4 +298,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adam_step", &adam_step);
   m.def("sgd_step", &sgd_step);
   m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
+  m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
+  m.def("symm_alloc", &symm_alloc);
+  m.def("symm_open", &symm_open);
+  m.def("symm_close", &symm_close);
+  m.def("symm_free", &symm_free);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("rs_reduce", &rs_reduce);
+  m.def("allreduce_f32", &allreduce_f32);
+  m.def("allgather_bf16", &allgather_bf16);
+  m.def("barrier_peers", &barrier_peers);
 }

@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int worl
   __shared__ uint32_t last;
   if (threadIdx.x == 0) {
     __threadfence_system();
-    last = (atomicAdd(grid_ctr + 1, 1u) == gridDim.x * epoch - 1) ? 1u : 0u;
+    const uint32_t old = atomicAdd(grid_ctr + 1, 1u);
+    last = (old == gridDim.x - 1) ? 1u : 0u;
+    if (last) atomicExch(grid_ctr + 1, 0u);
   }
   __syncthreads();
   if (last) peer_barrier(p, world, rank, epoch, 1);
@@ -169,7 +171,9 @@ __global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int
   __shared__ uint32_t last;
   if (threadIdx.x == 0) {
     __threadfence_system();
-    last = (atomicAdd(grid_ctr + 1, 1u) == gridDim.x * epoch - 1) ? 1u : 0u;
+    const uint32_t old = atomicAdd(grid_ctr + 1, 1u);
+    last = (old == gridDim.x - 1) ? 1u : 0u;
+    if (last) atomicExch(grid_ctr + 1, 0u);
   }
   __syncthreads();
   if (last) {

@@ -42,6 +42,12 @@ typedef struct PgGemmDesc {
   int my_rank;
 } PgGemmDesc;
 
+// ---- attention_sm100.cu
+int pg_attention_fwd(const void* qkv, const float* slopes, void* out, float* lse, int B, int S, int H, int D,
+                     cudaStream_t s);
+int pg_attention_bwd(const void* qkv, const float* slopes, const void* out, const float* lse, const void* dout,
+                     void* dqkv, float* dq_acc, float* delta, int B, int S, int H, int D, cudaStream_t s);
+
 // ---- comm.cu
 // out[rows, cols] = sum_src staging[src][rows, cols] (+ bias) (+ residual), after every source's
 // arrival counter reached `expected`

@@ -1,0 +1,58 @@
+"""``ExpertParallel`` wrapper (parity: reference nn/expert_parallel/expert_parallel.py:13-83):
+turn the MLPs of selected transformer blocks into mixture-of-experts layers whose experts are
+sharded over the TENSOR group."""
+from __future__ import annotations
+
+import re
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.nn.expert_parallel.layers import ExpertLayer
+from pipegoose_b200.nn.parallel import Parallel
+
+
+class ExpertParallel(Parallel):
+    def __init__(self, module: nn.Module, num_experts: int, expert: Optional[nn.Module] = None,
+                 mapping: Optional[List[int]] = None, router: nn.Module = None,
+                 enable_tensor_parallelism: bool = False, parallel_context: ParallelContext = None):
+        super().__init__(module, parallel_context)
+        tensor_parallel_size = parallel_context.get_world_size(ParallelMode.TENSOR)
+        assert num_experts % tensor_parallel_size == 0, \
+            "the number of experts must be divisible by the tensor parallel size"
+        num_layers = self._num_blocks(module)
+        if mapping is None:  # reference Q6: default to every layer (applied before validating)
+            mapping = list(range(num_layers))
+        assert all(0 <= i < num_layers for i in mapping), "a mapped layer index does not exist in the model"
+        assert router is not None, "a router is required"
+        self.num_experts = num_experts
+        self.expert = expert
+        self.mapping = mapping
+        self.router = router
+        self.enable_tensor_parallelism = enable_tensor_parallelism
+
+    @staticmethod
+    def _blocks(module: nn.Module):
+        pattern = re.compile(r"^transformer\.h\.(\d+)$")
+        return [(int(pattern.match(n).group(1)), m) for n, m in module.named_modules() if pattern.match(n)]
+
+    @classmethod
+    def _num_blocks(cls, module: nn.Module) -> int:
+        return len(cls._blocks(module))
+
+    @torch.no_grad()
+    def parallelize(self) -> nn.Module:
+        for layer_idx, block in self._blocks(self.module):
+            if layer_idx not in self.mapping:
+                continue
+            expert = self.expert if self.expert is not None else block.mlp
+            block.mlp = ExpertLayer(self.num_experts, expert, self.router, self.enable_tensor_parallelism,
+                                    self.parallel_context)
+        return self.module
+
+    @torch.no_grad()
+    def deparallelize(self) -> nn.Module:
+        raise NotImplementedError("mixture-of-experts layers cannot be merged back into a dense MLP")

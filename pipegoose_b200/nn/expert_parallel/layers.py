@@ -1,5 +1,56 @@
+"""``ExpertLayer``: router + sharded experts (parity: reference nn/expert_parallel/layers.py:11-48).
+
+Drop-in replacement for a transformer block's MLP.  With HF Bloom's calling convention
+``mlp(hidden_states, residual)`` the residual is kept out of the experts:
+``y = residual + sum_k w_k * Expert_k(x)`` (tokens dropped by the capacity limit pass through on
+the residual path only).
+"""
+from __future__ import annotations
+
+import torch
 from torch import nn
 
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+from pipegoose_b200.nn.expert_parallel.experts import Experts
+from pipegoose_b200.nn.expert_parallel.routers import RouterOutput
+from pipegoose_b200.nn.expert_parallel.utils import get_num_local_experts
 
-class ExpertLayer(nn.Module):  # placeholder, replaced below in this commit series
-    pass
+
+class ExpertLayer(nn.Module):
+    def __init__(self, num_experts: int, expert: nn.Module, router: nn.Module, enable_tensor_parallel: bool,
+                 parallel_context: ParallelContext):
+        super().__init__()
+        self.num_experts = num_experts
+        self.router = router
+        self.parallel_context = parallel_context
+        if enable_tensor_parallel:
+            self.num_local_experts = num_experts
+        else:
+            self.num_local_experts = get_num_local_experts(num_experts, parallel_context)
+        self._experts = Experts(self.num_local_experts, expert, enable_tensor_parallel, parallel_context)
+
+    @property
+    def experts(self) -> nn.ModuleList:
+        return self._experts.experts
+
+    def forward(self, *args, **kwargs) -> torch.Tensor:
+        inputs = args[0]
+        routed = self.router(inputs)
+        ctx = ExpertContext.get_instance()
+        if isinstance(routed, RouterOutput):
+            ctx.push_aux_loss(routed.aux_loss)
+            ctx.push_z_loss(routed.z_loss)
+            order, weights = routed.dispatching_order, routed.weight
+        else:  # bare expert ids, e.g. a test router
+            order, weights = routed, None
+        residual = None
+        rest = list(args[1:])
+        if rest and isinstance(rest[0], torch.Tensor) and rest[0].shape == inputs.shape:
+            # HF Bloom: mlp(layernorm_output, residual) -> keep the residual outside the experts
+            residual = rest[0]
+            rest[0] = torch.zeros_like(residual)
+        out = self._experts(inputs, order, inputs, *rest, weights=weights, **kwargs)
+        if residual is not None:
+            out = out + residual
+        return out

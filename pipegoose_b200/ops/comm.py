@@ -1,0 +1,178 @@
+"""Fused compute+collective engines over NVLink peer memory.
+
+``FusedTPEngine`` drives the two tensor-parallel kernels
+
+* **all-gather -> GEMM** (`ag_gemm`, `ag_gemm_nn`): ONE launch of the tcgen05 GEMM kernel in which
+  a few communication CTAs pull every peer's activation shard through NVSwitch with bulk async
+  copies into the local gathered operand while the remaining CTAs run the MMA tiles, visiting the
+  row chunks in arrival order (local shard first) and acquiring a per-chunk counter before the
+  TMA loads of that chunk;
+* **GEMM -> reduce-scatter** (`gemm_rs`, `gemm_rs_nn`): the GEMM epilogue stores each output tile
+  straight into the owner rank's staging slot (peer ``st.global``) and bumps the owner's arrival
+  counter; a small reduce kernel on the owner sums the T partial tiles with bias and residual as
+  soon as the counters say they landed.
+
+Buffers are double-buffered by operation parity; all flags/counters are monotonic (no resets).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from pipegoose_b200.distributed import symmetric as S
+from pipegoose_b200.ops import kernels as K
+from pipegoose_b200.ops import native
+
+_BM = 128
+N_COMM_CTAS = 8
+
+
+def pick_block_n(rows: int, n: int, chunks: int, ctas: int) -> int:
+    """Mirror of ``pick_bn`` in csrc/gemm_sm100.cu (both sides of a reduce-scatter must agree on the tiling)."""
+    best, best_cost = 256, float("inf")
+    for bn, eff in ((256, 1.0), (192, 0.93), (128, 0.82), (64, 0.55)):
+        if bn > 64 and n <= bn // 2:
+            continue
+        tiles = ((rows + _BM - 1) // _BM) * ((n + bn - 1) // bn) * chunks
+        waves = (tiles + ctas - 1) // ctas
+        cost = waves * bn / eff
+        if cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+class FusedTPEngine:
+    def __init__(self, comm, ag_bytes: int = 0, rs_bytes: int = 0):
+        self.comm = comm
+        self.T = comm.size
+        self.rank = comm.rank
+        self.ctx = comm.ctx
+        self.mode = comm.mode
+        self.ws: Optional[S.SymmetricWorkspace] = None
+        self._ag_slot_bytes = 0
+        self._rs_slot_bytes = 0
+        self.ag_epoch = 0
+        self.rs_calls = 0
+        self.rs_expected = 0
+        self.num_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        self._dummy = {}
+
+    # ------------------------------------------------------------------ workspace
+    def _ensure(self, ag_slot: int, rs_slot: int):
+        ag_slot = (ag_slot + 1023) // 1024 * 1024
+        rs_slot = (rs_slot + 1023) // 1024 * 1024
+        if self.ws is not None and ag_slot <= self._ag_slot_bytes and rs_slot <= self._rs_slot_bytes:
+            return
+        self._ag_slot_bytes = max(self._ag_slot_bytes, ag_slot)
+        self._rs_slot_bytes = max(self._rs_slot_bytes, rs_slot)
+        if self.ws is not None:
+            self.ws.close()
+        total = 2 * self._ag_slot_bytes + 2 * self._rs_slot_bytes
+        self.ws = S.SymmetricWorkspace(self.ctx, self.mode, total)
+        self.ag_epoch = 0
+        self.rs_calls = 0
+        self.rs_expected = 0
+
+    def _ag_off(self, slot: int) -> int:
+        return slot * self._ag_slot_bytes
+
+    def _rs_off(self, slot: int) -> int:
+        return 2 * self._ag_slot_bytes + slot * self._rs_slot_bytes
+
+    def _dummy_out(self, n: int, device):
+        t = self._dummy.get(n)
+        if t is None:
+            t = torch.empty(1, n, dtype=torch.bfloat16, device=device)
+            self._dummy[n] = t
+        return t
+
+    def supports(self, rows_local: int) -> bool:
+        return rows_local % _BM == 0
+
+    # ------------------------------------------------------------------ all-gather -> GEMM
+    def _ag_gemm(self, x_shard, weight, b_mn, bias, flags, aux, out_cols):
+        T, r = self.T, self.rank
+        m_local, k = x_shard.shape
+        m = m_local * T
+        shard_bytes = m_local * k * 2
+        # largest reduce-scatter staging seen so far is kept; grow lazily (collective)
+        self._ensure(shard_bytes, self._rs_slot_bytes)
+        ws = self.ws
+        self.ag_epoch += 1
+        slot = self.ag_epoch & 1
+        stage = ws.local_tensor(self._ag_off(slot), (m_local, k), torch.bfloat16)
+        stage.copy_(x_shard)
+        x_full = torch.empty(m, k, dtype=torch.bfloat16, device=x_shard.device)
+        out = torch.empty(m, out_cols, dtype=torch.bfloat16, device=x_shard.device)
+        ag = dict(
+            n_comm=N_COMM_CTAS, dst=x_full.data_ptr(), chunk_bytes=shard_bytes,
+            ready=ws.sig_ptr(r, S.SIG_AG_READY), epoch=self.ag_epoch, rank=r,
+            src=[ws.data_ptr(p, self._ag_off(slot)) for p in range(T)],
+            peer_flag=[ws.sig_ptr(p, S.SIG_AG_READY + r) for p in range(T)],
+        )
+        native().gemm(x_full, weight, out, False, b_mn, bias, None, aux, flags, 0, 0,
+                      T, r, ws.sig_ptr(r, S.SIG_CHUNK_CTR), N_COMM_CTAS * self.ag_epoch, [], [], ag)
+        return out, x_full
+
+    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
+        """``(gather(x) @ W^T + b [gelu], gather(x))`` with ``x_shard`` = this rank's token shard."""
+        if not self.supports(x_shard.shape[0]):
+            x_full = self.comm.all_gather_rows(x_shard)
+            z = torch.empty(x_full.shape[0], weight.shape[0], dtype=x_full.dtype, device=x_full.device) if gelu else None
+            y = K.gemm_nt(x_full, weight, bias, gelu=gelu, aux_out=z)
+            if aux_holder is not None:
+                aux_holder["aux"] = z
+            return y, x_full
+        aux = None
+        if gelu:
+            aux = torch.empty(x_shard.shape[0] * self.T, weight.shape[0], dtype=torch.bfloat16, device=x_shard.device)
+            if aux_holder is not None:
+                aux_holder["aux"] = aux
+        return self._ag_gemm(x_shard.contiguous(), weight, False, bias, K.EPI_GELU if gelu else 0, aux, weight.shape[0])
+
+    def ag_gemm_nn(self, dy_shard, weight, dgelu_aux=None):
+        """``(gather(dy) @ W [* gelu'(aux)], gather(dy))`` — dgrad of a row-parallel linear."""
+        if not self.supports(dy_shard.shape[0]):
+            dy_full = self.comm.all_gather_rows(dy_shard)
+            return K.gemm_nn(dy_full, weight, dgelu_aux=dgelu_aux), dy_full
+        flags = K.EPI_DGELU if dgelu_aux is not None else 0
+        return self._ag_gemm(dy_shard.contiguous(), weight, True, None, flags, dgelu_aux, weight.shape[1])
+
+    # ------------------------------------------------------------------ GEMM -> reduce-scatter
+    def _gemm_rs(self, a, weight, b_mn, bias, residual, n):
+        T, r = self.T, self.rank
+        m = a.shape[0]
+        m_local = m // T
+        slot_bytes = T * m_local * n * 2
+        self._ensure(self._ag_slot_bytes, slot_bytes)
+        ws = self.ws
+        self.rs_calls += 1
+        slot = self.rs_calls & 1
+        bn = pick_block_n(m_local, n, T, self.num_sms)
+        tiles_per_chunk = ((m_local + _BM - 1) // _BM) * ((n + bn - 1) // bn)
+        self.rs_expected += tiles_per_chunk
+        src_stride = m_local * n  # elements between two sources' slots
+        out_peer = [ws.data_ptr(p, self._rs_off(slot) + r * src_stride * 2) for p in range(T)]
+        arrive = [ws.sig_ptr(p, S.SIG_RS_ARRIVE + r) for p in range(T)]
+        native().gemm(a, weight, self._dummy_out(n, a.device), False, b_mn, None, None, None, 0, bn, 0,
+                      T, (r + 1) % T, 0, 0, out_peer, arrive)
+        out = torch.empty(m_local, n, dtype=torch.bfloat16, device=a.device)
+        native().rs_reduce(ws.data_ptr(r, self._rs_off(slot)), T, src_stride, ws.sig_ptr(r, S.SIG_RS_ARRIVE),
+                           self.rs_expected, bias, residual, out)
+        return out
+
+    def gemm_rs(self, a, weight, bias=None, residual=None):
+        """``reduce_scatter_rows(a @ W^T) + b + residual`` — forward of a row-parallel linear."""
+        if not self.supports(a.shape[0] // self.T):
+            y = self.comm.reduce_scatter_rows(K.gemm_nt(a, weight))
+            if bias is not None:
+                y = y + bias
+            return y + residual if residual is not None else y
+        return self._gemm_rs(a.contiguous(), weight, False, bias, residual, weight.shape[0])
+
+    def gemm_rs_nn(self, dy, weight):
+        """``reduce_scatter_rows(dy @ W)`` — dgrad of a column-parallel linear."""
+        if not self.supports(dy.shape[0] // self.T):
+            return self.comm.reduce_scatter_rows(K.gemm_nn(dy, weight))
+        return self._gemm_rs(dy.contiguous(), weight, True, None, None, weight.shape[1])

@@ -179,3 +179,24 @@ def test_bloom_matches_fp32_reference():
         if r > 8e-2:
             bad.append((n, r))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("D,H,S,B", [(64, 4, 512, 2), (64, 16, 1024, 2), (128, 2, 384, 1), (128, 4, 1024, 2)])
+def test_flash_alibi_attention(D, H, S, B):
+    from pipegoose_b200.ops import kernels as K
+    from pipegoose_b200.ops.attention import _AlibiAttentionNative, alibi_attention_reference
+
+    torch.manual_seed(7)
+    qkv = torch.randn(B * S, H * 3 * D, device="cuda", dtype=torch.bfloat16)
+    slopes = K.alibi_slopes(H, device="cuda")
+    qkv_g = qkv.clone().requires_grad_(True)
+    out = _AlibiAttentionNative.apply(qkv_g, slopes, B, S, H, D)
+    ref_in = qkv.float().requires_grad_(True)
+    ref = alibi_attention_reference(ref_in, slopes, B, S, H, D)
+    assert _rel(out, ref) < 2e-2
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    ref.backward(dout.float())
+    g, r = qkv_g.grad.view(B * S, H, 3, D).float(), ref_in.grad.view(B * S, H, 3, D)
+    for i, name in enumerate("qkv"):
+        assert _rel(g[:, :, i], r[:, :, i]) < 3e-2, name
