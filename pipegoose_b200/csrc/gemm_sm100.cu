@@ -37,6 +37,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -1;
+  // driver entry points need the primary context bound to the calling thread (autograd worker
+  // threads have not necessarily touched the runtime yet)
+  cudaFree(nullptr);
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};

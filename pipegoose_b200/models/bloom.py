@@ -88,7 +88,7 @@ class BloomAttention(nn.Module):
         self.head_dim = h // config.n_head
         self.query_key_value = nn.Linear(h, 3 * h, bias=True)
         self.dense = nn.Linear(h, h, bias=True)
-        self.register_buffer("alibi_slopes", K.alibi_slopes(config.n_head), persistent=False)
+        self._slopes_cache = {}
 
 
 class BloomMLP(nn.Module):
@@ -140,11 +140,17 @@ class BloomBlock(nn.Module):
 
 
 def _alibi_slopes_local(self: BloomAttention, n_head_local: int) -> torch.Tensor:
-    """Slopes of the heads this tensor-parallel rank owns (heads are sharded contiguously)."""
-    if n_head_local == self.num_heads:
-        return self.alibi_slopes
-    rank = getattr(self, "tp_rank", 0)
-    return self.alibi_slopes[rank * n_head_local:(rank + 1) * n_head_local].contiguous()
+    """fp32 slopes of the heads this tensor-parallel rank owns (heads are sharded contiguously);
+    kept out of the module's buffers so that ``model.to(bfloat16)`` cannot round them."""
+    device = self.query_key_value.weight.device
+    key = (n_head_local, str(device))
+    slopes = self._slopes_cache.get(key)
+    if slopes is None:
+        full = K.alibi_slopes(self.num_heads, device=device)
+        rank = getattr(self, "tp_rank", 0) if n_head_local != self.num_heads else 0
+        slopes = full[rank * n_head_local:(rank + 1) * n_head_local].contiguous()
+        self._slopes_cache[key] = slopes
+    return slopes
 
 
 BloomAttention.alibi_slopes_local = _alibi_slopes_local
@@ -196,6 +202,9 @@ class BloomForCausalLM(nn.Module):
         self.transformer = BloomModel(config)
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         self.lm_head.weight = self.transformer.word_embeddings.weight  # tied
+        # the tied table receives two gradient contributions per backward (lm_head wgrad + embedding
+        # scatter): the gradient reducer must wait for both before reducing its bucket
+        self.lm_head.weight._pg_grad_contribs = 2
         self.tp = None
         self.vocab_start = 0
         self.apply(self._init_weights)
@@ -261,10 +270,10 @@ class BloomForCausalLM(nn.Module):
             return CausalLMOutput(loss=loss, logits=None)
         ln = fused_layer_norm(x, t.ln_f.weight, t.ln_f.bias, eps)
         if self.tp is not None:
-            ln = self.tp.all_gather_rows(ln)
-        logits = K.gemm_nt(ln, self.lm_head.weight)
+            ln = self.tp.gather_rows(ln)
+        logits = PF.linear(ln, self.lm_head.weight)
         if self.tp is not None:
-            logits = self.tp.all_gather_cols(logits)[:, : self.config.vocab_size]
+            logits = self.tp.gather_cols(logits)[:, : self.config.vocab_size]
         return CausalLMOutput(loss=None, logits=logits.view(B, S, -1))
 
     @torch.no_grad()

@@ -1,0 +1,172 @@
+"""Structural pipeline partitioning (parity: reference nn/pipeline_parallel/partitioner.py:29-244).
+
+The reference symbolically traces the model with ``transformers.utils.fx`` (removed in
+transformers 5) and cuts the FX graph at transformer-block boundaries once a shard holds its share
+of the (non-embedding) parameters.  This partitioner reaches the same cuts without tracing: it
+reads the model's block list (``<base_model_prefix>.h`` / ``.layers`` or the children of an
+``nn.Sequential``), balances blocks by parameter count, and returns one ``nn.Module`` per stage
+whose forward consumes the previous stage's hidden states.
+"""
+from __future__ import annotations
+
+from enum import Enum, auto
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+
+class PartitionPolicy(Enum):
+    UNIFORM = auto()
+
+
+def _balanced_cuts(costs: List[int], n_parts: int) -> List[int]:
+    """Contiguous split of ``costs`` into ``n_parts`` groups minimising the largest group (greedy on the
+    running prefix, same rule as the reference: move to the next shard once its share is reached)."""
+    total = sum(costs)
+    bounds, acc, part = [0], 0, 1
+    for i, c in enumerate(costs):
+        remaining_items = len(costs) - i
+        remaining_parts = n_parts - part + 1
+        if part < n_parts and (acc >= total * part / n_parts or remaining_items < remaining_parts) and i > bounds[-1]:
+            bounds.append(i)
+            part += 1
+        acc += c
+    while len(bounds) < n_parts:
+        bounds.append(min(bounds[-1] + 1, len(costs)))
+    bounds.append(len(costs))
+    return bounds
+
+
+class SequentialStage(nn.Module):
+    def __init__(self, layers: List[nn.Module]):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+
+class BloomStage(nn.Module):
+    """A contiguous slice of a Bloom-style causal LM: [embedding +] blocks [+ final norm + lm head].
+
+    Works for ``pipegoose_b200.models.BloomForCausalLM`` (fused blocks on 2-D token tensors) and for
+    🤗 ``BloomForCausalLM`` (blocks called with alibi / causal mask)."""
+
+    def __init__(self, model: nn.Module, start: int, end: int, is_first: bool, is_last: bool):
+        super().__init__()
+        t = model.transformer
+        self.is_first, self.is_last = is_first, is_last
+        self.config = model.config
+        self.fast = hasattr(model, "hidden_states")  # our fused model
+        if is_first:
+            self.word_embeddings = t.word_embeddings
+            self.word_embeddings_layernorm = t.word_embeddings_layernorm
+        self.h = nn.ModuleList([t.h[i] for i in range(start, end)])
+        if is_last:
+            self.ln_f = t.ln_f
+            self.lm_head = model.lm_head
+        self._model_ref = [model]  # not registered: avoids duplicating parameters
+
+    def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, batch_seq=None):
+        model = self._model_ref[0]
+        if self.fast:
+            from pipegoose_b200.models.bloom import fused_layer_norm
+            from pipegoose_b200.ops import functional as PF
+            from pipegoose_b200.ops import kernels as K
+
+            eps = self.config.layer_norm_epsilon
+            if self.is_first:
+                B, S = x.shape
+                h = PF.embedding_layernorm(x, self.word_embeddings.weight, self.word_embeddings_layernorm.weight,
+                                           self.word_embeddings_layernorm.bias, eps, model.vocab_start, model.tp)
+            else:
+                B, S = batch_seq
+                h = x
+            for block in self.h:
+                h = block(h, B, S)
+            if not self.is_last:
+                return h
+            if labels is not None:
+                shifted = torch.full_like(labels, -100)
+                shifted[:, :-1] = labels[:, 1:]
+                return PF.lm_head_cross_entropy(h, self.ln_f.weight, self.ln_f.bias, self.lm_head.weight, shifted,
+                                                eps, model.vocab_start, -100, model.tp)
+            ln = fused_layer_norm(h, self.ln_f.weight, self.ln_f.bias, eps)
+            return K.gemm_nt(ln, self.lm_head.weight).view(B, S, -1)
+        # ---- 🤗 Bloom blocks
+        from transformers.models.bloom.modeling_bloom import build_alibi_tensor
+
+        if self.is_first:
+            ids = x
+            B, S = ids.shape
+            h = self.word_embeddings_layernorm(self.word_embeddings(ids))
+        else:
+            h = x
+            B, S = h.shape[:2]
+        if attention_mask is None:
+            attention_mask = torch.ones(B, S, dtype=torch.long, device=h.device)
+        alibi = build_alibi_tensor(attention_mask, self.config.n_head, dtype=h.dtype)
+        causal = torch.ones(S, S, dtype=torch.bool, device=h.device).triu(1)[None, None].expand(B, 1, S, S)
+        for block in self.h:
+            out = block(h, alibi=alibi, attention_mask=causal)
+            h = out[0] if isinstance(out, tuple) else out
+        if not self.is_last:
+            return h
+        logits = self.lm_head(self.ln_f(h))
+        if labels is not None:
+            shift_logits = logits[..., :-1, :].contiguous().float()
+            shift_labels = labels[..., 1:].contiguous()
+            return torch.nn.functional.cross_entropy(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.view(-1))
+        return logits
+
+
+class UniformPartitioner:
+    def __init__(self, module: nn.Module, parallel_context: ParallelContext):
+        self.module = module
+        self.parallel_context = parallel_context
+
+    def _n_partitions(self) -> int:
+        return self.parallel_context.pipeline_parallel_size
+
+    @staticmethod
+    def _block_list(model: nn.Module) -> Optional[nn.ModuleList]:
+        base = getattr(model, getattr(model, "base_model_prefix", "transformer"), None)
+        if base is None:
+            return None
+        for name in ("h", "layers", "layer", "blocks"):
+            blocks = getattr(base, name, None)
+            if isinstance(blocks, nn.ModuleList):
+                return blocks
+        return None
+
+    def split(self, input_names: Optional[List[str]] = None) -> List[nn.Module]:
+        n = self._n_partitions()
+        model = self.module
+        if isinstance(model, nn.Sequential):
+            layers = list(model.children())
+            costs = [sum(p.numel() for p in l.parameters()) or 1 for l in layers]
+            b = _balanced_cuts(costs, n)
+            return [SequentialStage(layers[b[i]:b[i + 1]]) for i in range(n)]
+        blocks = self._block_list(model)
+        assert blocks is not None and hasattr(model, "transformer"), \
+            "UniformPartitioner supports nn.Sequential and Bloom-style causal LMs"
+        assert len(blocks) >= n, "more pipeline stages than transformer blocks"
+        costs = [sum(p.numel() for p in blk.parameters()) for blk in blocks]  # embeddings excluded, as in the reference
+        b = _balanced_cuts(costs, n)
+        return [BloomStage(model, b[i], b[i + 1], is_first=(i == 0), is_last=(i == n - 1)) for i in range(n)]
+
+
+def get_model_partition(module: nn.Module, policy: PartitionPolicy, parallel_context: ParallelContext) -> nn.Module:
+    """The stage of ``module`` that belongs to this rank."""
+    assert policy is PartitionPolicy.UNIFORM
+    stages = UniformPartitioner(module, parallel_context).split()
+    from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
+
+    return stages[get_partition_idx(parallel_context)]

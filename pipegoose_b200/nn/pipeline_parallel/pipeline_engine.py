@@ -1,0 +1,286 @@
+"""Pipeline engine: runs this rank's stage through a static schedule with NCCL/gloo point-to-point
+transfers between neighbouring stages (parity target: reference
+nn/pipeline_parallel/pipeline_engine.py:36-157, which drives the same thing through RPC packages,
+worker threads, a progress tracker with per-task sleeps and two global barriers per clock).
+
+Two modes behind ``module.forward``:
+
+* ``model(input_ids, attention_mask)`` (no labels) — **GPipe forward**: returns one output per
+  micro-batch (real outputs on the last stage, stand-in scalars elsewhere).  The transfers are
+  autograd functions, so the reference's usage ``for out in outputs: out.sum().backward()`` drives
+  the backward pipeline on every stage.
+* ``model(input_ids, attention_mask, labels=...)`` — **training step**: the engine executes the
+  whole schedule (GPipe or 1F1B), backward included, and returns the mean loss.  In the 1F1B steady
+  state a stage's send and the receive it waits for next are issued as one batched p2p group, so
+  the cross pattern cannot deadlock and transfers overlap with compute.
+
+Activation shapes are static: they are discovered once per micro-batch size by a forward-only
+handshake and never sent again (the reference sends dtype/shape/requires_grad with every tensor).
+"""
+from __future__ import annotations
+
+from contextlib import nullcontext
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_context import ParallelContext
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.nn.pipeline_parallel import microbatch as mb_utils
+from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
+from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
+from pipegoose_b200.nn.pipeline_parallel.scheduler import BaseScheduler
+from pipegoose_b200.nn.pipeline_parallel.task import Task
+
+
+class _P2PLink:
+    """Point-to-point ops with the previous / next pipeline stage."""
+
+    def __init__(self, ctx: ParallelContext):
+        self.ctx = ctx
+        self.group = ctx.get_group(ParallelMode.PIPELINE)
+        self.is_nccl = dist.get_backend(self.group) == "nccl"
+        self.prev = ctx.get_prev_global_rank(ParallelMode.PIPELINE)
+        self.next = ctx.get_next_global_rank(ParallelMode.PIPELINE)
+
+    def _device(self):
+        return self.ctx.device if self.is_nccl else torch.device("cpu")
+
+    def exchange(self, sends: List[Tuple[torch.Tensor, int]], recvs: List[Tuple[torch.Tensor, int]]):
+        """Issue the sends and receives as ONE batched group and wait for completion."""
+        ops = [dist.P2POp(dist.isend, t.contiguous(), peer, self.group) for t, peer in sends]
+        ops += [dist.P2POp(dist.irecv, t, peer, self.group) for t, peer in recvs]
+        if not ops:
+            return
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def send_shape(self, shape, dtype, peer):
+        from pipegoose_b200.distributed._p2p import DTYPE_TO_ID
+
+        meta = torch.zeros(10, dtype=torch.long)
+        meta[0], meta[1] = DTYPE_TO_ID[dtype], len(shape)
+        for i, s in enumerate(shape):
+            meta[2 + i] = s
+        dist.send(meta.to(self._device()), dst=peer, group=self.group)
+
+    def recv_shape(self, peer):
+        from pipegoose_b200.distributed._p2p import ID_TO_DTYPE
+
+        meta = torch.zeros(10, dtype=torch.long, device=self._device())
+        dist.recv(meta, src=peer, group=self.group)
+        meta = meta.cpu().tolist()
+        return tuple(meta[2:2 + meta[1]]), ID_TO_DTYPE[meta[0]]
+
+
+class _RecvFromPrev(torch.autograd.Function):
+    """forward: receive the activation from the previous stage; backward: send its gradient back."""
+
+    @staticmethod
+    def forward(ctx, anchor, link, shape, dtype, device):
+        buf = torch.empty(shape, dtype=dtype, device=device)
+        link.exchange([], [(buf, link.prev)])
+        ctx.link = link
+        return buf
+
+    @staticmethod
+    def backward(ctx, grad):
+        ctx.link.exchange([(grad, ctx.link.prev)], [])
+        return None, None, None, None, None
+
+
+class _SendToNext(torch.autograd.Function):
+    """forward: send the activation to the next stage and return a scalar stand-in; backward:
+    receive the activation's gradient from the next stage."""
+
+    @staticmethod
+    def forward(ctx, act, link):
+        link.exchange([(act.detach(), link.next)], [])
+        ctx.link = link
+        ctx.meta = (act.shape, act.dtype, act.device)
+        return act.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, _grad_of_standin):
+        shape, dtype, device = ctx.meta
+        g = torch.empty(shape, dtype=dtype, device=device)
+        ctx.link.exchange([], [(g, ctx.link.next)])
+        return g, None
+
+
+class PipelineEngine:
+    def __init__(self, module: nn.Module, scheduler: BaseScheduler, parallel_context: ParallelContext,
+                 pipeline_context=None, full_module: Optional[nn.Module] = None):
+        self.module = module  # this rank's stage
+        self.full_module = full_module
+        self.scheduler = scheduler
+        self.parallel_context = parallel_context
+        self.pipeline_context = pipeline_context
+        self.partition_idx = get_partition_idx(parallel_context)
+        self.n_partitions = parallel_context.pipeline_parallel_size
+        self.is_first = self.partition_idx == 0
+        self.is_last = self.partition_idx == self.n_partitions - 1
+        self.link = _P2PLink(parallel_context)
+        self._in_meta: Dict[tuple, Tuple[tuple, torch.dtype]] = {}
+        self._anchor = None
+
+    # ------------------------------------------------------------------ helpers
+    def _device(self):
+        p = next(self.module.parameters(), None)
+        return p.device if p is not None else torch.device("cpu")
+
+    def _stage_forward(self, x, mb: Dict, with_labels: bool):
+        kwargs = {}
+        fwd = self.module.forward
+        code = getattr(fwd, "__code__", None)
+        names = code.co_varnames[:code.co_argcount] if code is not None else ()
+        if "attention_mask" in names and mb.get("attention_mask") is not None:
+            kwargs["attention_mask"] = mb["attention_mask"]
+        if with_labels and self.is_last and "labels" in names:
+            kwargs["labels"] = mb["labels"]
+        if "batch_seq" in names and "input_ids" in mb:
+            kwargs["batch_seq"] = tuple(mb["input_ids"].shape[:2])
+        return self.module(x, **kwargs)
+
+    def _first_input(self, mb: Dict):
+        return mb["input_ids"] if "input_ids" in mb else next(iter(mb.values()))
+
+    def _mb_key(self, mb: Dict) -> tuple:
+        return tuple(self._first_input(mb).shape)
+
+    def _handshake(self, microbatches: List[Dict]):
+        """Discover this stage's input shape for every distinct micro-batch size (forward-only dry run)."""
+        dev = self._device()
+        for mb in microbatches:
+            key = self._mb_key(mb)
+            if key in self._in_meta:
+                continue
+            with torch.no_grad():
+                if self.is_first:
+                    x = self._first_input(mb).to(dev)
+                    self._in_meta[key] = (tuple(x.shape), x.dtype)
+                else:
+                    shape, dtype = self.link.recv_shape(self.link.prev)
+                    self._in_meta[key] = (shape, dtype)
+                    x = torch.zeros(shape, dtype=dtype, device=dev)
+                if not self.is_last:
+                    out = self._stage_forward(x, {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in mb.items()}, False)
+                    self.link.send_shape(tuple(out.shape), out.dtype, self.link.next)
+
+    def _prepare(self, inputs: Dict) -> List[Dict]:
+        n = self.scheduler.n_microbatches
+        dev = self._device()
+        inputs = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in inputs.items() if v is not None}
+        mbs = mb_utils.split(inputs, n)
+        self._handshake(mbs)
+        return mbs
+
+    # ------------------------------------------------------------------ GPipe forward (autograd-driven backward)
+    def forward_only(self, inputs: Dict) -> List[torch.Tensor]:
+        mbs = self._prepare(inputs)
+        dev = self._device()
+        if self._anchor is None or self._anchor.device != dev:
+            self._anchor = torch.zeros((), device=dev, requires_grad=True)
+        outputs = []
+        for mb in mbs:
+            if self.is_first:
+                x = self._first_input(mb)
+            else:
+                shape, dtype = self._in_meta[self._mb_key(mb)]
+                x = _RecvFromPrev.apply(self._anchor, self.link, shape, dtype, dev)
+            out = self._stage_forward(x, mb, False)
+            outputs.append(out if self.is_last else _SendToNext.apply(out, self.link))
+        return outputs
+
+    # ------------------------------------------------------------------ scheduled training step
+    def train_step(self, inputs: Dict) -> torch.Tensor:
+        mbs = self._prepare(inputs)
+        dev = self._device()
+        m = len(mbs)
+        order: List[Task] = self.scheduler.get_stage_order(self.partition_idx)
+        saved_in: Dict[int, torch.Tensor] = {}
+        saved_out: Dict[int, torch.Tensor] = {}
+        recv_act: Dict[int, torch.Tensor] = {}
+        recv_grad: Dict[int, torch.Tensor] = {}
+        losses = []
+        reducer = getattr(self.full_module, "_pg_grad_reducer", None) if self.full_module is not None else None
+        n_bwd_done = 0
+
+        def act_buffer(i):
+            shape, dtype = self._in_meta[self._mb_key(mbs[i])]
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        def needs_recv(task: Task):
+            if task.job_type is JobType.FORWARD:
+                return None if self.is_first or task.microbatch_idx in recv_act else ("act", task.microbatch_idx)
+            return None if self.is_last or task.microbatch_idx in recv_grad else ("grad", task.microbatch_idx)
+
+        def post_recv(kind, i, sends):
+            if kind == "act":
+                buf = act_buffer(i)
+                recv_act[i] = buf
+                self.link.exchange(sends, [(buf, self.link.prev)])
+            else:
+                buf = torch.empty_like(saved_out[i])
+                recv_grad[i] = buf
+                self.link.exchange(sends, [(buf, self.link.next)])
+
+        for idx, task in enumerate(order):
+            i = task.microbatch_idx
+            need = needs_recv(task)
+            if need is not None:
+                post_recv(need[0], need[1], [])
+            pending_send = None
+            if task.job_type is JobType.FORWARD:
+                if self.is_first:
+                    x = self._first_input(mbs[i])
+                else:
+                    x = recv_act.pop(i).requires_grad_(True)
+                out = self._stage_forward(x, mbs[i], True)
+                saved_in[i] = x
+                if self.is_last:
+                    loss = out / m
+                    saved_out[i] = loss
+                    losses.append(loss.detach())
+                else:
+                    saved_out[i] = out
+                    pending_send = (out.detach(), self.link.next)
+            else:
+                out = saved_out.pop(i)
+                x = saved_in.pop(i)
+                n_bwd_done += 1
+                sync = nullcontext() if (reducer is None or n_bwd_done == m) else reducer.no_sync()
+                with sync:
+                    if self.is_last:
+                        torch.autograd.backward(out)
+                    else:
+                        torch.autograd.backward(out, recv_grad.pop(i))
+                if not self.is_first:
+                    pending_send = (x.grad, self.link.prev)
+            if pending_send is not None:
+                # pair the send with the receive the next task is going to wait for (1F1B steady state)
+                nxt = order[idx + 1] if idx + 1 < len(order) else None
+                need_next = needs_recv(nxt) if nxt is not None else None
+                if need_next is not None:
+                    post_recv(need_next[0], need_next[1], [pending_send])
+                else:
+                    self.link.exchange([pending_send], [])
+        if self.is_last:
+            total = torch.stack(losses).sum()
+        else:
+            total = torch.zeros((), device=dev)
+        return total
+
+    # ------------------------------------------------------------------ entry point used as module.forward
+    def run(self, input_ids=None, attention_mask=None, labels=None, **kwargs):
+        inputs = {"input_ids": input_ids, "attention_mask": attention_mask, "labels": labels}
+        inputs.update(kwargs)
+        if labels is None:
+            return self.forward_only(inputs)
+        from pipegoose_b200.models.bloom import CausalLMOutput
+
+        loss = self.train_step(inputs)
+        # backward already ran inside the schedule: hand back a leaf so `loss.backward()` is harmless
+        return CausalLMOutput(loss=loss.detach().requires_grad_(True), logits=None)

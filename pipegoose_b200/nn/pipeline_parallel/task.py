@@ -1,0 +1,12 @@
+from dataclasses import dataclass
+
+from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
+
+
+@dataclass(frozen=True)
+class Task:
+    """One unit of pipeline work: run ``job_type`` for a micro-batch on a partition."""
+
+    job_type: JobType
+    microbatch_idx: int
+    partition_idx: int

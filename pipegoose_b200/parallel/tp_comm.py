@@ -39,7 +39,7 @@ class TensorParallelComm:
 
     # ------------------------------------------------------------------ library collectives
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
-        x = x.contiguous()
+        x = x.detach().contiguous()
         out = torch.empty((x.shape[0] * self.size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x, group=self.group)
         return out
@@ -52,7 +52,7 @@ class TensorParallelComm:
         return full.permute(1, 0, 2).reshape(x.shape[0], -1)
 
     def reduce_scatter_rows(self, x: torch.Tensor) -> torch.Tensor:
-        x = x.contiguous()
+        x = x.detach().contiguous()
         assert x.shape[0] % self.size == 0
         rows = x.shape[0] // self.size
         if dist.get_backend(self.group) == "gloo":
@@ -66,6 +66,13 @@ class TensorParallelComm:
         dist.all_reduce(x, group=self.group)
         return x
 
+    # differentiable forms (used outside the fused sub-layer functions, e.g. the logits path)
+    def gather_rows(self, x: torch.Tensor) -> torch.Tensor:
+        return _GatherRows.apply(x, self)
+
+    def gather_cols(self, x: torch.Tensor) -> torch.Tensor:
+        return _GatherCols.apply(x, self)
+
     # ------------------------------------------------------------------ fused kernels
     def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
         return self._engine.ag_gemm(x_shard, weight, bias, gelu, aux_holder)
@@ -78,3 +85,30 @@ class TensorParallelComm:
 
     def gemm_rs_nn(self, dy, weight):
         return self._engine.gemm_rs_nn(dy, weight)
+
+
+class _GatherRows(torch.autograd.Function):
+    """all-gather along tokens; backward reduce-scatters the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, comm):
+        ctx.comm = comm
+        return comm.all_gather_rows(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.comm.reduce_scatter_rows(g), None
+
+
+class _GatherCols(torch.autograd.Function):
+    """all-gather along features (every rank uses the full result); backward keeps the local slice."""
+
+    @staticmethod
+    def forward(ctx, x, comm):
+        ctx.comm, ctx.width = comm, x.shape[-1]
+        return comm.all_gather_cols(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        r = ctx.comm.rank
+        return g[:, r * ctx.width:(r + 1) * ctx.width].contiguous(), None

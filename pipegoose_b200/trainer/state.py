@@ -1,0 +1,25 @@
+from dataclasses import dataclass
+from enum import Enum, auto
+
+
+class TrainerStatus(Enum):
+    INITIALIZING = auto()
+    RUNNING = auto()
+    FINISHED = auto()
+
+
+class TrainerStage(Enum):
+    TRAINING = auto()
+    VALIDATING = auto()
+    TESTING = auto()
+    PREDICTING = auto()
+
+
+@dataclass
+class TrainerState:
+    status: TrainerStatus = TrainerStatus.INITIALIZING
+    stage: TrainerStage = TrainerStage.TRAINING
+    epoch: int = 0
+    step: int = 0
+    tokens_seen: int = 0
+    last_loss: float = float("nan")

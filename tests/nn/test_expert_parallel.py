@@ -1,0 +1,150 @@
+"""Mixture of experts: routers, ExpertLayer, ExpertLoss/ExpertContext and the ExpertParallel wrapper."""
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import ExpertParallel, TensorParallel
+from pipegoose_b200.nn.expert_parallel import (ExpertContext, ExpertLayer, ExpertLoss, RouterOutput, SwitchNoisePolicy,
+                                               Top1Router, Top2Router)
+from pipegoose_b200.nn.expert_parallel.utils import get_num_local_experts
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+@pytest.mark.parametrize("router_cls,k", [(Top1Router, 1), (Top2Router, 2)])
+def test_topk_router(router_cls, k):
+    torch.manual_seed(0)
+    E, d, tokens = 4, 16, 40
+    router = router_cls(SwitchNoisePolicy(), E, d)
+    router.train()
+    out = router(torch.randn(5, 8, d))
+    assert isinstance(out, RouterOutput)
+    assert out.dispatching_order.shape == (tokens, E) and out.weight.shape == (tokens, E)
+    assert torch.all(out.dispatching_order.sum(-1) == k)
+    assert torch.all((out.weight > 0).sum(-1) == k)
+    assert out.aux_loss.dim() == 0 and out.z_loss.dim() == 0
+    (out.aux_loss + out.z_loss + out.weight.sum()).backward()
+    assert router.gate.weight.grad.abs().sum() > 0
+
+
+def test_router_capacity():
+    torch.manual_seed(0)
+    E, d, tokens = 4, 16, 64
+    router = Top1Router(None, E, d, expert_capacity=(1.0, 2.0))
+    router.train()
+    out = router(torch.randn(tokens, d))
+    cap = tokens // E
+    assert torch.all(out.dispatching_order.sum(0) <= cap)
+    router.eval()
+    assert torch.all(router(torch.randn(tokens, d)).dispatching_order.sum(0) <= 2 * cap)
+
+
+def test_switch_noise_policy_range():
+    noise = SwitchNoisePolicy(eps=0.1).sample_like(torch.zeros(1000))
+    assert noise.min() >= 0.9 and noise.max() < 1.1
+
+
+def test_expert_context_and_loss():
+    ctx = ExpertContext.get_instance()
+    ctx.pop_all_aux_loss(), ctx.pop_all_z_loss()
+    ctx.push_aux_loss(torch.tensor(1.0)), ctx.push_aux_loss(torch.tensor(2.0)), ctx.push_z_loss(torch.tensor(4.0))
+    loss = ExpertLoss(nn.MSELoss(), aux_weight=0.1, z_weight=0.5)
+    assert len(loss.aux_loss) == 2 and len(loss.z_loss) == 1
+    x = torch.ones(3)
+    total = loss(x, torch.zeros(3))
+    assert torch.isclose(total, torch.tensor(1.0 + 0.1 * 3.0 + 0.5 * 4.0))
+    assert loss.aux_loss == [] and loss.z_loss == []
+
+
+class DummyRouter(nn.Module):
+    """Routes token i to expert i % E (bare expert ids, like the reference's test router)."""
+
+    def __init__(self, num_experts):
+        super().__init__()
+        self.num_experts = num_experts
+
+    def forward(self, inputs):
+        n = inputs.reshape(-1, inputs.shape[-1]).shape[0]
+        return torch.arange(n) % self.num_experts
+
+
+def run_expert_parallel(rank, world_size, port, tp, num_experts, state, ids, ref_loss):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    model.load_state_dict(state)
+    model = ExpertParallel(model, num_experts, mapping=[0], router=DummyRouter(num_experts), parallel_context=ctx).parallelize()
+    layer = model.transformer.h[0].mlp
+    assert isinstance(layer, ExpertLayer)
+    assert not isinstance(model.transformer.h[1].mlp, ExpertLayer)
+    assert len(layer.experts) == num_experts // tp == get_num_local_experts(num_experts, ctx)
+    assert all(getattr(p, "is_expert", False) for p in layer.experts.parameters())
+    # experts are copies of the dense MLP and every token visits exactly one -> same loss as the dense model
+    loss = model(ids, labels=ids).loss
+    assert torch.allclose(loss, ref_loss, atol=1e-5)
+    loss.backward()
+    first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+    n_tokens = ids.numel()
+    for local_idx, expert in enumerate(layer.experts):
+        routed = (torch.arange(n_tokens) % num_experts == first + local_idx).any()
+        has_grad = all(p.grad is not None and p.grad.abs().sum() > 0 for p in expert.parameters() if p.dim() == 2)
+        assert has_grad == bool(routed)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,num_experts", [(1, 4), (2, 4)])
+def test_expert_parallel_matches_dense_with_identical_experts(tp, num_experts):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    ids = torch.randint(0, 96, (2, 8))
+    ref_loss = model(ids, labels=ids).loss.detach()
+    spawn(run_expert_parallel, world_size=tp, tp=tp, num_experts=num_experts, state=copy.deepcopy(model.state_dict()),
+          ids=ids, ref_loss=ref_loss)
+
+
+def run_moe_with_real_router(rank, world_size, port):
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    torch.manual_seed(0)
+    d = 16
+    expert = nn.Sequential(nn.Linear(d, 2 * d), nn.GELU(), nn.Linear(2 * d, d))
+    router = Top2Router(None, 4, d)
+    layer = ExpertLayer(4, expert, router, enable_tensor_parallel=False, parallel_context=ctx)
+    # make the experts different from each other but identical across ranks
+    for i, e in enumerate(layer.experts):
+        g = torch.Generator().manual_seed(10 + ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts) + i)
+        for p in e.parameters():
+            p.data = torch.randn(p.shape, generator=g) * 0.1
+    x = torch.randn(6, d, requires_grad=True)
+    y = layer(x)
+    # dense re-computation of y = sum_k w_k * Expert_k(x) with all 4 experts
+    all_experts = []
+    for gidx in range(4):
+        e = copy.deepcopy(expert)
+        g = torch.Generator().manual_seed(10 + gidx)
+        for p in e.parameters():
+            p.data = torch.randn(p.shape, generator=g) * 0.1
+        all_experts.append(e)
+    routed = router(x)
+    want = sum(routed.weight[:, k:k + 1] * all_experts[k](x) for k in range(4))
+    assert torch.allclose(y, want, atol=1e-5)
+    y.sum().backward()
+    assert x.grad is not None and router.gate.weight.grad is not None
+    ExpertContext.get_instance().pop_all_aux_loss(), ExpertContext.get_instance().pop_all_z_loss()
+    ctx.destroy()
+
+
+def test_expert_layer_applies_gate_weights_across_ranks():
+    spawn(run_moe_with_real_router, world_size=2)
+
+
+def test_expert_parallel_default_mapping_covers_all_layers():
+    def run(rank, world_size, port):
+        ctx = init_parallel_context(rank, world_size, port, 1, 1, 1)
+        model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=3, n_head=4))
+        model = ExpertParallel(model, 2, router=DummyRouter(2), parallel_context=ctx).parallelize()
+        assert all(isinstance(b.mlp, ExpertLayer) for b in model.transformer.h)
+        ctx.destroy()
+
+    run(0, 1, __import__("pipegoose_b200.testing.utils", fromlist=["find_free_port"]).find_free_port())

@@ -1,0 +1,110 @@
+"""Whole-model tensor parallelism: the 🤗 Bloom replicated-activation path (reference semantics) and
+the sequence-parallel fast path of pipegoose_b200's own Bloom, both against the unsharded model."""
+import copy
+
+import pytest
+import torch
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import TensorParallel
+from pipegoose_b200.nn.tensor_parallel.embedding import ParallelEmbedding
+from pipegoose_b200.nn.tensor_parallel.layer_norm import LayerNorm
+from pipegoose_b200.nn.tensor_parallel.linear import ColumnParallelLinear, RowParallelLinear
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+def run_hf_bloom(rank, world_size, port, tp, state, ids, ref_logits, ref_generated):
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    model = HFBloom(HFConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    # every leaf except activations / dropout is one of the four parallel classes
+    for name, mod in model.named_modules():
+        if len(list(mod.children())) == 0 and len(list(mod.parameters(recurse=False))) > 0:
+            assert isinstance(mod, (ColumnParallelLinear, RowParallelLinear, ParallelEmbedding, LayerNorm)), name
+    assert model.lm_head.weight is model.transformer.word_embeddings.weight
+    assert model.transformer.word_embeddings.weight.shape[0] == 128 // tp
+    out = model(input_ids=ids, labels=ids)
+    assert torch.allclose(out.logits, ref_logits, atol=1e-4)
+    gen = model.generate(ids, max_new_tokens=1, do_sample=False)
+    assert torch.equal(gen, ref_generated)
+    out.loss.backward()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    opt.step()
+    for p in model.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    ctx.destroy()
+
+
+def test_hf_bloom_tensor_parallel_matches_unsharded():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    torch.manual_seed(0)
+    model = HFBloom(HFConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)).eval()
+    ids = torch.randint(0, 128, (2, 8))
+    with torch.no_grad():
+        ref_logits = model(input_ids=ids).logits
+        ref_gen = model.generate(ids, max_new_tokens=1, do_sample=False)
+    spawn(run_hf_bloom, world_size=2, tp=2, state=model.state_dict(), ids=ids, ref_logits=ref_logits, ref_generated=ref_gen)
+
+
+def run_fast_bloom(rank, world_size, port, tp, state, ids, ref_loss, ref_grads, ref_logits):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    cfg = BloomConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    r = ctx.get_local_rank(ParallelMode.TENSOR)
+    blk = model.transformer.h[0]
+    assert blk.self_attention.query_key_value.weight.shape == (3 * 32 // tp, 32)
+    assert blk.self_attention.dense.weight.shape == (32, 32 // tp)
+    assert blk.mlp.dense_h_to_4h.weight.shape == (128 // tp, 32)
+    assert blk.mlp.dense_4h_to_h.weight.shape == (32, 128 // tp)
+    assert model.lm_head.weight is model.transformer.word_embeddings.weight
+    loss = model(ids, labels=ids).loss
+    assert torch.allclose(loss, ref_loss, atol=1e-5), (loss, ref_loss)
+    loss.backward()
+    logits = model(ids).logits
+    assert torch.allclose(logits, ref_logits, atol=1e-4)
+
+    def shard(name, g):
+        if "query_key_value" in name or "dense_h_to_4h" in name:
+            return g.chunk(tp, 0)[r]
+        if ("self_attention.dense.weight" in name) or ("dense_4h_to_h.weight" in name):
+            return g.chunk(tp, 1)[r]
+        if "word_embeddings.weight" in name:
+            return g.chunk(tp, 0)[r]
+        return g
+
+    import torch.distributed as dist
+
+    for name, p in model.named_parameters():
+        g = p.grad.clone()
+        if getattr(p, "tp_partial_grad", False):  # partial sums over token shards -> add over the TP group
+            dist.all_reduce(g, group=ctx.get_group(ParallelMode.TENSOR))
+        want = shard(name, ref_grads[name])
+        assert torch.allclose(g, want, atol=2e-5), name
+    ctx.destroy()
+
+
+def test_fast_bloom_sequence_parallel_matches_unsharded():
+    torch.manual_seed(0)
+    cfg = BloomConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "layernorm" in n or "ln_f" in n or "bias" in n:
+                p.add_(torch.randn_like(p) * 0.1)
+    ids = torch.randint(0, 128, (4, 8))
+    loss = model(ids, labels=ids).loss
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    with torch.no_grad():
+        logits = model(ids).logits
+    spawn(run_fast_bloom, world_size=2, tp=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach(),
+          ref_grads=grads, ref_logits=logits)
