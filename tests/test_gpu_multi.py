@@ -1,0 +1,132 @@
+"""Multi-GPU numerics (skipped on single-GPU boxes): fused all-gather->GEMM / GEMM->reduce-scatter
+kernels against NCCL + torch.matmul, and the TP2 sequence-parallel Bloom against the single-GPU model."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpus(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def run_fused_tp(rank, world_size, port):
+    import torch.distributed as dist
+
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.parallel.tp_comm import TensorParallelComm
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1, backend="nccl")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    comm = TensorParallelComm(ctx, fused=True)
+    comm.enable_fused()
+    assert comm.fused
+    T = world_size
+    torch.manual_seed(0)  # same full tensors on every rank
+    M, K, N = 1024 * T, 512, 768
+    x_full = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
+    bias = torch.randn(N, device=dev, dtype=torch.bfloat16)
+    x_shard = x_full.chunk(T)[rank].contiguous()
+
+    def rel(a, b):
+        return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-6)
+
+    for it in range(3):  # several epochs: exercises the double-buffered flags/counters
+        # ---- all-gather -> GEMM (column-parallel forward), with bias and with GELU + pre-activation
+        y, gathered = comm.ag_gemm(x_shard, w, bias)
+        assert torch.equal(gathered, x_full)
+        assert rel(y, x_full.float() @ w.float().t() + bias.float()) < 2e-2
+        holder = {}
+        y2, _ = comm.ag_gemm(x_shard, w, bias, gelu=True, aux_holder=holder)
+        pre = x_full.float() @ w.float().t() + bias.float()
+        from pipegoose_b200.ops import kernels as Kk
+
+        assert rel(holder["aux"], pre) < 2e-2 and rel(y2, Kk.gelu_tanh(pre)) < 2e-2
+        # ---- GEMM -> reduce-scatter (row-parallel forward) with bias + residual
+        a_full = torch.randn(M, K * T, device=dev, dtype=torch.bfloat16)
+        w_row = torch.randn(N, K * T, device=dev, dtype=torch.bfloat16) * 0.05
+        res = torch.randn(M // T, N, device=dev, dtype=torch.bfloat16)
+        a_loc = a_full[:, rank * K:(rank + 1) * K].contiguous()
+        w_loc = w_row[:, rank * K:(rank + 1) * K].contiguous()
+        out = comm.gemm_rs(a_loc, w_loc, bias, res)
+        want = (a_full.float() @ w_row.float().t()).chunk(T)[rank] + bias.float() + res.float()
+        assert rel(out, want) < 2e-2
+        # ---- dgrad forms
+        dy = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        dx = comm.gemm_rs_nn(dy, w)  # partial [M, K] summed over ranks then scattered
+        full = dy.float() @ w.float()
+        assert rel(dx, (full * T).chunk(T)[rank]) < 2e-2  # every rank holds the same dy/w here -> T x
+        dy_shard = dy.chunk(T)[rank].contiguous()
+        da, dy_g = comm.ag_gemm_nn(dy_shard, w)
+        assert torch.equal(dy_g, dy) and rel(da, full) < 2e-2
+    torch.cuda.synchronize()
+    dist.barrier()
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_tp_kernels(world):
+    _need_gpus(world)
+    from pipegoose_b200.testing.utils import spawn
+
+    spawn(run_fused_tp, world_size=world)
+
+
+def run_tp_bloom(rank, world_size, port, fused, state, ids, ref_loss, ref_gnorm):
+    import torch.distributed as dist
+
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import TensorParallel
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    os.environ["PIPEGOOSE_B200_FUSED_TP"] = "1" if fused else "0"
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1, backend="nccl")
+    cfg = BloomConfig(vocab_size=4096, hidden_size=256, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    model.load_state_dict(state)
+    model = model.to(torch.bfloat16)
+    model = TensorParallel(model, ctx).parallelize()
+    model.to("cuda")
+    ids = ids.cuda()
+    loss = model(ids, labels=ids).loss
+    loss.backward()
+    assert abs(loss.item() - ref_loss) < 3e-2, (loss.item(), ref_loss)
+    # global gradient norm (sharded params: sum of squares over ranks; replicated: TP-reduced partials)
+    sq = torch.zeros((), device="cuda")
+    for n, p in model.named_parameters():
+        g = p.grad.float()
+        if getattr(p, "tp_partial_grad", False):
+            dist.all_reduce(g, group=ctx.get_group(ParallelMode.TENSOR))
+            sq += g.pow(2).sum() / world_size
+        elif hasattr(p, "parallel_metadata"):
+            sq += g.pow(2).sum()
+        else:
+            sq += g.pow(2).sum() / world_size
+    dist.all_reduce(sq)
+    assert abs(sq.sqrt().item() - ref_gnorm) / ref_gnorm < 5e-2, (sq.sqrt().item(), ref_gnorm)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_tp2_bloom_matches_single_gpu(fused):
+    _need_gpus(2)
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.testing.utils import spawn
+
+    torch.manual_seed(0)
+    cfg = BloomConfig(vocab_size=4096, hidden_size=256, n_layer=2, n_head=4)
+    ref = BloomForCausalLM(cfg)
+    state = copy.deepcopy(ref.state_dict())
+    ids = torch.randint(0, 4096, (2, 256))
+    model = copy.deepcopy(ref).to(torch.bfloat16).cuda()
+    loss = model(ids.cuda(), labels=ids.cuda()).loss
+    loss.backward()
+    gnorm = torch.sqrt(sum(p.grad.float().pow(2).sum() for p in model.parameters())).item()
+    spawn(run_tp_bloom, world_size=2, fused=fused, state=state, ids=ids, ref_loss=loss.item(), ref_gnorm=gnorm)
