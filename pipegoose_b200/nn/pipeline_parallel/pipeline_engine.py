@@ -125,6 +125,8 @@ class PipelineEngine:
         self.link = _P2PLink(parallel_context)
         self._in_meta: Dict[tuple, Tuple[tuple, torch.dtype]] = {}
         self._anchor = None
+        self.tied_group = None
+        self.tied_param = None
 
     # ------------------------------------------------------------------ helpers
     def _device(self):
@@ -267,11 +269,25 @@ class PipelineEngine:
                     post_recv(need_next[0], need_next[1], [pending_send])
                 else:
                     self.link.exchange([pending_send], [])
+        self.sync_tied_embedding_grad()
         if self.is_last:
             total = torch.stack(losses).sum()
         else:
             total = torch.zeros((), device=dev)
         return total
+
+    def sync_tied_embedding_grad(self):
+        """Sum the tied embedding / lm_head table's gradient over the first and last stage."""
+        if self.tied_group is None or self.tied_param is None or not (self.is_first or self.is_last):
+            return
+        p = self.tied_param
+        g = getattr(p, "main_grad", None)
+        if g is None:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g = p.grad
+        t = g if dist.get_backend(self.tied_group) != "nccl" or g.is_cuda else g.cuda()
+        dist.all_reduce(t, group=self.tied_group)
 
     # ------------------------------------------------------------------ entry point used as module.forward
     def run(self, input_ids=None, attention_mask=None, labels=None, **kwargs):

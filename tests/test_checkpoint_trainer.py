@@ -1,0 +1,64 @@
+import os
+
+import pytest
+import torch
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import DataParallel, TensorParallel
+from pipegoose_b200.nn.utils import from_pretrained, save_pretrained
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+def run_checkpoint(rank, world_size, port, tp, dp, ckp_path):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    model = TensorParallel(model, ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    want = {k: v.clone() for k, v in model.state_dict().items()}
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    name = f"pytorch_model_tp_{ctx.get_local_rank(ParallelMode.TENSOR)}_pp_0.bin"
+    assert os.path.exists(os.path.join(ckp_path, name))
+    with torch.no_grad():
+        for p in model.parameters():
+            p.zero_()
+    from_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("world,tp,dp", [(1, 1, 1), (4, 2, 2)])
+def test_save_and_load_sharded_checkpoint(tmp_path, world, tp, dp):
+    spawn(run_checkpoint, world_size=world, tp=tp, dp=dp, ckp_path=str(tmp_path / "ckpt"))
+
+
+def test_trainer_fits_and_logs():
+    import io
+
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.trainer import Callback, DistributedLogger, Trainer, TrainerStatus
+
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=32, n_layer=1, n_head=4))
+    data = [{"input_ids": torch.randint(0, 64, (2, 8))} for _ in range(6)]
+    events = []
+
+    class Rec(Callback):
+        def on_fit_start(self, trainer):
+            events.append("start")
+
+        def on_step_end(self, trainer, loss):
+            events.append(float(loss))
+
+        def on_fit_end(self, trainer):
+            events.append("end")
+
+    stream = io.StringIO()
+    trainer = Trainer(model, data, optim=FusedAdam(model.parameters(), lr=1e-2), num_epochs=2, callbacks=[Rec()],
+                      loggers=[DistributedLogger(stream=stream)], log_every=3)
+    state = trainer.fit()
+    assert state.status is TrainerStatus.FINISHED and state.step == 12 and state.tokens_seen == 12 * 16
+    assert events[0] == "start" and events[-1] == "end" and events[-2] < events[1]  # loss went down
+    assert "tokens/s" in stream.getvalue()
