@@ -1,0 +1,55 @@
+"""3D-parallel Bloom training with pipegoose_b200 (the reference's examples/hybrid_parallelism.py flow).
+
+    torchrun --standalone --nnodes=1 --nproc-per-node 4 examples/hybrid_parallelism.py --tp 2 --dp 2
+
+Synthetic token ids are used (no dataset / tokenizer download needed).
+"""
+import argparse
+
+import torch
+
+from pipegoose_b200.distributed import ParallelContext, ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import DataParallel, PipelineParallel, TensorParallel
+from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tp", type=int, default=2)
+    ap.add_argument("--pp", type=int, default=1)
+    ap.add_argument("--dp", type=int, default=2)
+    ap.add_argument("--model", default="bloom_560m")
+    ap.add_argument("--batch", type=int, default=8, help="sequences per data-parallel replica")
+    ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--microbatches", type=int, default=4)
+    ap.add_argument("--backend", default="nccl" if torch.cuda.is_available() else "gloo")
+    args = ap.parse_args()
+
+    parallel_context = ParallelContext.from_torch(
+        tensor_parallel_size=args.tp, pipeline_parallel_size=args.pp, data_parallel_size=args.dp, backend=args.backend)
+    rank = parallel_context.get_global_rank()
+
+    cfg = getattr(BloomConfig, args.model)()
+    model = BloomForCausalLM(cfg)
+    if args.backend == "nccl":
+        model = model.to(torch.bfloat16)
+    model = TensorParallel(model, parallel_context).parallelize()
+    if args.pp > 1:
+        model = PipelineParallel(model, num_microbatches=args.microbatches, parallel_context=parallel_context).parallelize()
+    model = DataParallel(model, parallel_context).parallelize()
+    if args.backend == "nccl":
+        model.to("cuda")
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-4), parallel_context)
+
+    device = next(model.parameters()).device
+    gen = torch.Generator().manual_seed(parallel_context.get_local_rank(ParallelMode.DATA))
+    for step in range(args.steps):
+        ids = torch.randint(0, cfg.vocab_size, (args.batch, args.seq), generator=gen).to(device)
+        outputs = model(ids, labels=ids)
+        optim.zero_grad()
+        outputs.loss.backward()
+        optim.step()
+        if rank == parallel_context.get_world_size(ParallelMode.GLOBAL) - 1 or args.pp == 1 and rank == 0:
+            print(f"step {step} loss {outputs.loss.item():.4f}", flush=True)
+    parallel_context.destroy()

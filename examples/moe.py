@@ -1,0 +1,41 @@
+"""Switch-style mixture of experts on Bloom: experts sharded over the tensor group.
+
+    torchrun --standalone --nnodes=1 --nproc-per-node 2 examples/moe.py --tp 2 --experts 4
+"""
+import argparse
+
+import torch
+
+from pipegoose_b200.distributed import ParallelContext
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import DataParallel, ExpertParallel, TensorParallel
+from pipegoose_b200.nn.expert_parallel import ExpertContext, SwitchNoisePolicy, Top1Router
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tp", type=int, default=2)
+    ap.add_argument("--dp", type=int, default=1)
+    ap.add_argument("--experts", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--backend", default="gloo")
+    args = ap.parse_args()
+    ctx = ParallelContext.from_torch(tensor_parallel_size=args.tp, pipeline_parallel_size=1, data_parallel_size=args.dp,
+                                     backend=args.backend)
+    cfg = BloomConfig(vocab_size=1024, hidden_size=128, n_layer=4, n_head=8)
+    model = BloomForCausalLM(cfg)
+    router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
+    model = ExpertParallel(model, args.experts, mapping=[0, 2], router=router, parallel_context=ctx).parallelize()
+    model = TensorParallel(model, ctx, sequence_parallel=False).parallelize() if False else model
+    model = DataParallel(model, ctx).parallelize()
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    expert_ctx = ExpertContext.get_instance()
+    for step in range(args.steps):
+        ids = torch.randint(0, cfg.vocab_size, (4, 32))
+        loss = model(ids, labels=ids).loss
+        loss = loss + 0.01 * sum(expert_ctx.pop_all_aux_loss()) + 0.001 * sum(expert_ctx.pop_all_z_loss())
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        if ctx.get_global_rank() == 0:
+            print(f"step {step} loss {loss.item():.4f}", flush=True)
+    ctx.destroy()

@@ -35,7 +35,8 @@ def unique_parameters(module_or_params) -> List[nn.Parameter]:
 
 
 class FlatModelState:
-    def __init__(self, params: Iterable[nn.Parameter], pad_to_multiple_of: int = 1, grad_dtype=torch.float32):
+    def __init__(self, params: Iterable[nn.Parameter], pad_to_multiple_of: int = 1, grad_dtype=torch.float32,
+                 buffer_factory=None):
         self.params: List[nn.Parameter] = unique_parameters(list(params))
         assert len(self.params) > 0
         p0 = self.params[0]
@@ -49,8 +50,13 @@ class FlatModelState:
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         mult = max(pad_to_multiple_of, 1) * _ALIGN
         self.numel = (off + mult - 1) // mult * mult
-        self.flat_param = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
-        self.flat_grad = torch.zeros(self.numel, dtype=grad_dtype, device=self.device)
+        if buffer_factory is not None:
+            # externally owned storage (NVLink peer-mapped symmetric memory for the fused DP/ZeRO kernels)
+            self.flat_param, self.flat_grad = buffer_factory(self.numel, self.dtype, grad_dtype)
+            self.flat_param.zero_(), self.flat_grad.zero_()
+        else:
+            self.flat_param = torch.zeros(self.numel, dtype=self.dtype, device=self.device)
+            self.flat_grad = torch.zeros(self.numel, dtype=grad_dtype, device=self.device)
         for p in self.params:
             o, n = self.offsets[id(p)]
             view = self.flat_param[o:o + n].view_as(p.data)

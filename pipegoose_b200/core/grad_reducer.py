@@ -60,7 +60,7 @@ class GradReducer:
             return
         gran = self.dp * _ALIGN
         self.bucket_numel = max(gran, int(self.bucket_size_mb * 1024 * 1024 / 4) // gran * gran)
-        self.flat = FlatModelState.of(self.module, pad_to_multiple_of=self.dp)
+        self.flat = self._make_flat_state()
         # pad the flat buffers so that every bucket (including the last) divides by dp
         n = self.flat.numel
         self.buckets = []
@@ -80,6 +80,27 @@ class GradReducer:
             if not hasattr(p, "_pg_autograd_hook"):
                 p._pg_autograd_hook = p.register_post_accumulate_grad_hook(self._on_autograd_grad)
         self._reset_pending()
+
+    def _make_flat_state(self) -> FlatModelState:
+        """Flat state in NVLink peer-mapped memory when the fused data-parallel kernels can run
+        (CUDA bf16 parameters, NCCL group, dp > 1); plain device memory otherwise."""
+        import os
+
+        module = self.module
+        existing = getattr(module, "_flat_state", None) or FlatModelState.find(module.parameters())
+        p0 = next(module.parameters())
+        group = self.ctx.get_group(ParallelMode.DATA)
+        want_fused = (existing is None and self.dp > 1 and p0.is_cuda and p0.dtype == torch.bfloat16
+                      and dist.get_backend(group) == "nccl" and os.environ.get("PIPEGOOSE_B200_FUSED_DP", "1") == "1")
+        if not want_fused:
+            return FlatModelState.of(module, pad_to_multiple_of=self.dp)
+        from pipegoose_b200.ops.comm import FusedDPEngine
+
+        engine = FusedDPEngine(self.ctx, ParallelMode.DATA)
+        state = FlatModelState(module.parameters(), pad_to_multiple_of=self.dp, buffer_factory=engine.allocate)
+        module._flat_state = state
+        self._fused = engine
+        return state
 
     def _reset_pending(self):
         for b in self.buckets:

@@ -176,3 +176,71 @@ class FusedTPEngine:
         if not self.supports(dy.shape[0] // self.T):
             return self.comm.reduce_scatter_rows(K.gemm_nn(dy, weight))
         return self._gemm_rs(dy.contiguous(), weight, True, None, None, weight.shape[1])
+
+
+class _StreamWork:
+    """`Work`-like handle: the collective ran on a side stream; ``wait`` orders the caller's stream after it."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class FusedDPEngine:
+    """Data-parallel gradient reduction and ZeRO-1 parameter all-gather as hand-written NVLink kernels.
+
+    The flat fp32 gradient buffer and the flat bf16 parameter buffer live in a peer-mapped workspace.
+    ``reduce_bucket`` launches (on a side stream, overlapped with backward) a two-shot kernel: every
+    rank pulls slice ``r`` of the bucket from all peers, sums it, scales by 1/dp and - for
+    all-reduce - pushes the result to all peers; for ZeRO-1 (reduce-scatter) it keeps the slice.
+    ``all_gather_params`` pushes this rank's updated bf16 slices of every bucket to all peers in
+    one launch.
+    """
+
+    def __init__(self, parallel_context, parallel_mode):
+        self.ctx = parallel_context
+        self.mode = parallel_mode
+        self.world = parallel_context.get_world_size(parallel_mode)
+        self.rank = parallel_context.get_local_rank(parallel_mode)
+        self.ws: Optional[S.SymmetricWorkspace] = None
+        self.epoch = 0
+        self.stream = torch.cuda.Stream()
+        self._grad_off = 0
+        self._param_off = 0
+
+    def allocate(self, numel: int, param_dtype, grad_dtype):
+        assert param_dtype == torch.bfloat16 and grad_dtype == torch.float32
+        grad_bytes = numel * 4
+        param_bytes = numel * 2
+        self._grad_off = 0
+        self._param_off = (grad_bytes + 1023) // 1024 * 1024
+        self.ws = S.SymmetricWorkspace(self.ctx, self.mode, self._param_off + param_bytes)
+        grad = self.ws.local_tensor(self._grad_off, (numel,), torch.float32)
+        param = self.ws.local_tensor(self._param_off, (numel,), torch.bfloat16)
+        self._grad_base = grad.data_ptr()
+        self.numel = numel
+        return param, grad
+
+    def _flag_ptrs(self):
+        return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
+
+    def reduce_bucket(self, view: torch.Tensor, mode: str):
+        offset = (view.data_ptr() - self._grad_base) // 4
+        n = view.numel()
+        ready = torch.cuda.Event()
+        ready.record()  # gradients of this bucket were produced on the current stream
+        self.epoch += 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            native().allreduce_f32([self.ws.data_ptr(p, self._grad_off) for p in range(self.world)], self.rank,
+                                   offset, n, 1.0 / self.world, mode == "reduce_scatter", self._flag_ptrs(), self.epoch)
+            done = torch.cuda.Event()
+            done.record()
+        return _StreamWork(done)
+
+    def all_gather_params(self, flat_param: torch.Tensor, bucket_numel: int):
+        self.epoch += 1
+        native().allgather_bf16([self.ws.data_ptr(p, self._param_off) for p in range(self.world)], self.rank,
+                                bucket_numel, flat_param.numel(), self._flag_ptrs(), self.epoch)
