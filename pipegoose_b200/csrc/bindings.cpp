@@ -90,6 +90,7 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
     d.ag_ready = reinterpret_cast<const uint32_t*>(ag["ready"].cast<int64_t>());
     d.ag_epoch = (uint32_t)ag["epoch"].cast<int64_t>();
     d.my_rank = ag["rank"].cast<int>();
+    d.a_local = reinterpret_cast<const void*>(ag["local"].cast<int64_t>());
     auto src = ag["src"].cast<std::vector<int64_t>>();
     auto pf = ag["peer_flag"].cast<std::vector<int64_t>>();
     for (size_t i = 0; i < src.size() && i < PG_MAX_PEERS; ++i) d.ag_src[i] = reinterpret_cast<const void*>(src[i]);

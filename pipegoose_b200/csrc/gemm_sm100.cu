@@ -106,8 +106,8 @@ static int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args,
-                      int max_ctas, cudaStream_t stream) {
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
+                      const GemmArgs& args, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -126,7 +126,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmAr
   if (gemm_ctas < 1) gemm_ctas = 1;
   int grid = (tiles < gemm_ctas ? tiles : gemm_ctas) + args.n_comm;
   if (grid < 1) grid = 1;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tal, args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     fprintf(stderr, "pipegoose_b200: gemm launch failed: %s\n", cudaGetErrorString(e));
@@ -199,7 +199,8 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
   int bn = d->block_n > 0 ? d->block_n : pick_bn(chunk_rows, args.N, args.num_chunks, max_ctas - args.n_comm);
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tal;
+  args.a_local_chunk = -1;
   // A: K-major  -> matrix [M, K] (ld = lda), box [128 rows, 64]
   //    MN-major -> matrix [K, M] (ld = lda), box [64 k-rows, 64]
   if (!d->a_mn) {
@@ -213,12 +214,19 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
     if (cached_tmap(&tb, d->B, d->K, d->N, d->ldb, BK) != 0) return -1;
   }
 
+  tal = ta;
+  if (d->a_local != nullptr && !d->a_mn && args.num_chunks > 1) {
+    // the local shard of an all-gather -> GEMM is read in place: [chunk_rows, K] matrix
+    if (cached_tmap(&tal, d->a_local, args.chunk_rows, d->K, d->K, BM) != 0) return -1;
+    args.a_local_chunk = d->my_rank;
+  }
+
 #define PG_DISPATCH_BN(AMN, BMN)                                                          \
   switch (bn) {                                                                           \
-    case 256: return launch_cfg<256, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
-    case 192: return launch_cfg<192, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
-    case 128: return launch_cfg<128, AMN, BMN>(ta, tb, args, max_ctas, stream);           \
-    case 64: return launch_cfg<64, AMN, BMN>(ta, tb, args, max_ctas, stream);             \
+    case 256: return launch_cfg<256, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
+    case 192: return launch_cfg<192, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
+    case 128: return launch_cfg<128, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
+    case 64: return launch_cfg<64, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);             \
     default: fprintf(stderr, "pipegoose_b200: bad block_n %d\n", bn); return -1;          \
   }
   if (!d->a_mn && !d->b_mn) {

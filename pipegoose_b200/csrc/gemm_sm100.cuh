@@ -58,6 +58,7 @@ struct GemmArgs {
   const uint32_t* ag_ready;          // local shard_ready[src] (written by src), wait >= ag_epoch
   uint32_t ag_epoch;
   int my_rank;
+  int a_local_chunk;  // >= 0: tiles of this chunk load A through tma_a_local (rows relative to the chunk)
   // GEMM -> reduce-scatter: rows of chunk c go to out_peer[c] (row index relative to chunk),
   // then arrive_ctr[c] (+1 per finished tile, release.sys)
   void* out_peer[kMaxPeers];
@@ -77,7 +78,8 @@ struct GemmCfg {
   static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kEpiStageBytes = 4 * 32 * 128;  // 4 epilogue warps x [32 rows x 128 B]
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 PG_DEVICE float gelu_tanh(float x) {
@@ -124,7 +126,8 @@ PG_DEVICE TileCoord map_tile(int t, int m_blks_per_chunk, int n_blks, int num_ch
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
-                     const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
+                     const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_a_local, const GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -151,10 +155,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   if (static_cast<int>(blockIdx.x) < args.n_comm) {
     // ============================ communication CTA ============================
     // One thread drives a ring of bulk copies: peer shard -> shared memory -> local gathered
-    // matrix, 32 KB per copy, kCommStages copies in flight.  Shards are visited starting with the
-    // local one so the GEMM CTAs can start immediately.
-    constexpr uint32_t kSlice = 32 * 1024;
-    constexpr int kCommStages = 6;
+    // matrix, 16 KB per copy, 8 loads in flight per CTA (~1 MB in flight over 8 CTAs: the NVLink
+    // bandwidth-delay product).
+    constexpr uint32_t kSlice = 16 * 1024;
+    constexpr int kCommStages = 12;  // smem ring slots
+    constexpr int kLoadsInFlight = 8;  // => up to kCommStages - kLoadsInFlight stores may still be reading smem
     uint64_t* cbar = reinterpret_cast<uint64_t*>(smem + kCommStages * kSlice);
     if (threadIdx.x == 0) {
       for (int i = 0; i < kCommStages; ++i) mbar_init(&cbar[i], 1);
@@ -168,7 +173,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t ph[kCommStages];
       for (int i = 0; i < kCommStages; ++i) ph[i] = 0;
       const uint64_t nslices = (args.ag_chunk_bytes + kSlice - 1) / kSlice;
-      for (int i = 0; i < args.num_chunks; ++i) {
+      const uint64_t first = blockIdx.x, step = args.n_comm;
+      const uint64_t mine = (nslices > first) ? (nslices - first + step - 1) / step : 0;
+      uint64_t ring = 0;  // slices issued so far over all shards -> ring slot = ring % kCommStages
+      for (int i = 1; i <= args.num_chunks; ++i) {
+        // remote shards first (rank+1, rank+2, ...); the local one last: the GEMM reads it in place,
+        // the copy into the gathered matrix is only needed by later consumers (wgrad)
         int src = args.my_rank + i;
         if (src >= args.num_chunks) src -= args.num_chunks;
         if (src != args.my_rank) {
@@ -177,21 +187,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         const uint8_t* from = reinterpret_cast<const uint8_t*>(args.ag_src[src]);
         uint8_t* to = reinterpret_cast<uint8_t*>(args.ag_dst) + static_cast<uint64_t>(src) * args.ag_chunk_bytes;
-        // software pipeline over this CTA's slices: issue loads kCommStages ahead of the stores
         uint64_t issued = 0, stored = 0;
-        const uint64_t first = blockIdx.x, step = args.n_comm;
-        const uint64_t mine = (nslices > first) ? (nslices - first + step - 1) / step : 0;
         while (stored < mine) {
-          while (issued < mine && issued - stored < kCommStages) {
-            const int st = issued % kCommStages;
+          while (issued < mine && issued - stored < kLoadsInFlight) {
+            const int st = static_cast<int>((ring + issued) % kCommStages);
             const uint64_t off = (first + issued * step) * kSlice;
             const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kSlice), args.ag_chunk_bytes - off));
-            if (issued >= static_cast<uint64_t>(kCommStages)) tma_store_wait_read<0>();
+            // the store that last used this slot is >= kCommStages - kLoadsInFlight stores old
+            tma_store_wait_read<kCommStages - kLoadsInFlight>();
             mbar_arrive_expect_tx(&cbar[st], bytes);
             bulk_load_1d(smem + st * kSlice, from + off, bytes, &cbar[st]);
             ++issued;
           }
-          const int st = stored % kCommStages;
+          const int st = static_cast<int>((ring + stored) % kCommStages);
           const uint64_t off = (first + stored * step) * kSlice;
           const uint32_t bytes = static_cast<uint32_t>(min(static_cast<uint64_t>(kSlice), args.ag_chunk_bytes - off));
           mbar_wait(&cbar[st], ph[st]);
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           tma_store_commit();
           ++stored;
         }
+        ring += mine;
         tma_store_wait<0>();  // this CTA's part of the shard is written
         fence_proxy_async_global();
         __threadfence();
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int seen_chunk = -1;
     for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm) {
       const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
-      if (args.chunk_flags != nullptr && tc.chunk != seen_chunk) {
+      if (args.chunk_flags != nullptr && tc.chunk != seen_chunk && tc.chunk != args.a_local_chunk) {
         if (lane == 0) {
           while (ld_acquire_sys(args.chunk_flags + tc.chunk) < args.flag_value) {
           }
@@ -249,8 +258,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         __syncwarp();
         seen_chunk = tc.chunk;
       }
-      const int m0 = tc.m_blk * BM;
+      int m0 = tc.m_blk * BM;
       const int n0 = tc.n_blk * BN;
+      // all-gather -> GEMM: the local shard is read in place from its (peer-visible) staging buffer
+      const CUtensorMap* map_a = &tma_a;
+      if (args.a_local_chunk >= 0 && tc.chunk == args.a_local_chunk) {
+        map_a = &tma_a_local;
+        m0 -= tc.chunk * chunk_rows;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
@@ -258,11 +273,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sa, map_a, &full_bar[stage], kb * BK, m0);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)
-              tma_load_2d(sa + i * (BK * 128), &tma_a, &full_bar[stage], m0 + i * 64, kb * BK);
+              tma_load_2d(sa + i * (BK * 128), map_a, &full_bar[stage], m0 + i * 64, kb * BK);
           }
           if constexpr (!B_MN) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
@@ -342,6 +357,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
       const bool row_ok = row < row_limit && row < args.M;
+      const int warp_row0 = tc.m_blk * BM + q * 32;          // first row handled by this warp
+      const int warp_out_row0 = out_row - lane;               // its destination row index
+      const int rows_ok = max(0, min(32, min(row_limit, args.M) - warp_row0));
+      uint8_t* stg_warp = smem_epi + q * 4096;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -349,17 +368,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= args.N) continue;
+        const int ncols = max(0, min(32, args.N - col0));  // multiple of 8
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const int ncols = min(32, args.N - col0);  // multiple of 8
-        if (args.flags & EPI_BIAS) {
+        const bool active = row_ok && ncols > 0;
+        if (active && (args.flags & EPI_BIAS)) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < ncols) {
-              const uint4 b = ld_global_nc_v4(args.bias + col0 + g * 8);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              const uint4 bb = ld_global_nc_v4(args.bias + col0 + g * 8);
+              const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 bf = unpack_bf16x2(bw[j]);
@@ -370,46 +389,58 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           }
         }
         if (out_f32) {
-          float* o = reinterpret_cast<float*>(out_base) + static_cast<size_t>(out_row) * args.ldc + col0;
+          // fp32 output (wgrad into the main-grad buffer): each thread owns a full 128-byte line
+          if (active) {
+            float* o = reinterpret_cast<float*>(out_base) + static_cast<size_t>(out_row) * args.ldc + col0;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g * 4 < ncols) {
-              float4 val = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-              if (args.flags & EPI_ACCUM) {
-                const float4 old = *reinterpret_cast<const float4*>(o + g * 4);
-                val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+            for (int g = 0; g < 8; ++g) {
+              if (g * 4 < ncols) {
+                float4 val = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                if (args.flags & EPI_ACCUM) {
+                  const float4 old = *reinterpret_cast<const float4*>(o + g * 4);
+                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + g * 4) = val;
               }
-              *reinterpret_cast<float4*>(o + g * 4) = val;
             }
           }
           continue;
         }
-        if (args.flags & EPI_GELU) {
-          if (args.aux != nullptr) {
-            __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(args.aux) +
-                               static_cast<size_t>(row) * args.ldc + col0;
+        const int half = (c & 1) * 4;  // which 64-byte half of the 128-byte staging row
+        if ((args.flags & EPI_GELU) && args.aux != nullptr) {
+          // pre-activation goes out through the same staged, coalesced path (second buffer pass)
+          uint8_t* stg = stg_warp + lane * 128;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols) {
-                uint4 pk;
-                pk.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-                pk.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-                pk.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-                pk.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-                st_global_v4(a + g * 8, pk);
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg + (((half + g) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+          __syncwarp();
+          {
+            __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(args.aux);
+            const int ch = lane & 3;  // 16-byte chunk inside this 64-byte half
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              if (rr < rows_ok && ch * 8 < ncols) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 128 + (((half + ch) ^ (rr & 7)) << 4));
+                st_global_v4(aux + static_cast<size_t>(warp_row0 + rr) * args.ldc + col0 + ch * 8, val);
               }
             }
           }
+          __syncwarp();
+        }
+        if (args.flags & EPI_GELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
         }
-        if (args.flags & EPI_DGELU) {
-          const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(args.aux) +
-                                   static_cast<size_t>(row) * args.ldc + col0;
+        if (active && (args.flags & EPI_DGELU)) {
+          const __nv_bfloat16* az = reinterpret_cast<const __nv_bfloat16*>(args.aux) +
+                                    static_cast<size_t>(row) * args.ldc + col0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < ncols) {
-              const uint4 z = ld_global_nc_v4(a + g * 8);
+              const uint4 z = ld_global_nc_v4(az + g * 8);
               const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -420,12 +451,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           }
         }
-        if (args.flags & EPI_RESIDUAL) {
-          const __nv_bfloat16* r = args.residual + static_cast<size_t>(row) * args.ldr + col0;
+        if (active && (args.flags & EPI_RESIDUAL)) {
+          const __nv_bfloat16* rp = args.residual + static_cast<size_t>(row) * args.ldr + col0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < ncols) {
-              const uint4 z = ld_global_nc_v4(r + g * 8);
+              const uint4 z = ld_global_nc_v4(rp + g * 8);
               const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -436,18 +467,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           }
         }
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_base) +
-                           static_cast<size_t>(out_row) * args.ldc + col0;
+        // stage this thread's 32 bf16 (64 B) into the warp's [32 rows x 128 B] buffer (16-byte chunks
+        // XOR-swizzled by row); every second chunk the warp writes 128-byte row segments to global
+        // (or peer) memory: 8 lanes per row, 4 rows per store instruction
+        {
+          uint8_t* stg = stg_warp + lane * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 < ncols) {
-            uint4 pk;
-            pk.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-            pk.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-            pk.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-            pk.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-            st_global_v4(o + g * 8, pk);
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg + (((half + g) ^ (lane & 7)) << 4)) =
+                make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+        }
+        if ((c & 1) == 1 || c == BN / 32 - 1) {
+          __syncwarp();
+          const int colbase = n0 + (c & ~1) * 32;                 // first column of the staged 64-column span
+          const int span = max(0, min((c & 1) ? 64 : 32, args.N - colbase));
+          __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_base);
+          const int ch = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            if (rr < rows_ok && ch * 8 < span) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              st_global_v4(ob + static_cast<size_t>(warp_out_row0 + rr) * args.ldc + colbase + ch * 8, val);
+            }
           }
+          __syncwarp();
         }
       }
       // accumulator drained -> hand the TMEM stage back to the MMA warp

@@ -40,6 +40,7 @@ typedef struct PgGemmDesc {
   const uint32_t* ag_ready;
   uint32_t ag_epoch;
   int my_rank;
+  const void* a_local;  // all-gather -> GEMM: this rank's shard [chunk_rows, K] (read in place)
 } PgGemmDesc;
 
 // ---- attention_sm100.cu

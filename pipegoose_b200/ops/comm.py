@@ -91,6 +91,15 @@ class FusedTPEngine:
         return rows_local % _BM == 0
 
     # ------------------------------------------------------------------ all-gather -> GEMM
+    def ag_input_buffer(self, rows_local: int, cols: int) -> Optional[torch.Tensor]:
+        """The peer-visible staging buffer the NEXT all-gather will publish: producers (LayerNorm)
+        write their output straight into it so no copy precedes the fused kernel."""
+        if not self.supports(rows_local):
+            return None
+        self._ensure(rows_local * cols * 2, self._rs_slot_bytes)
+        slot = (self.ag_epoch + 1) & 1
+        return self.ws.local_tensor(self._ag_off(slot), (rows_local, cols), torch.bfloat16)
+
     def _ag_gemm(self, x_shard, weight, b_mn, bias, flags, aux, out_cols):
         T, r = self.T, self.rank
         m_local, k = x_shard.shape
@@ -102,12 +111,13 @@ class FusedTPEngine:
         self.ag_epoch += 1
         slot = self.ag_epoch & 1
         stage = ws.local_tensor(self._ag_off(slot), (m_local, k), torch.bfloat16)
-        stage.copy_(x_shard)
+        if x_shard.data_ptr() != stage.data_ptr():
+            stage.copy_(x_shard)
         x_full = torch.empty(m, k, dtype=torch.bfloat16, device=x_shard.device)
         out = torch.empty(m, out_cols, dtype=torch.bfloat16, device=x_shard.device)
         ag = dict(
             n_comm=N_COMM_CTAS, dst=x_full.data_ptr(), chunk_bytes=shard_bytes,
-            ready=ws.sig_ptr(r, S.SIG_AG_READY), epoch=self.ag_epoch, rank=r,
+            ready=ws.sig_ptr(r, S.SIG_AG_READY), epoch=self.ag_epoch, rank=r, local=stage.data_ptr(),
             src=[ws.data_ptr(p, self._ag_off(slot)) for p in range(T)],
             peer_flag=[ws.sig_ptr(p, S.SIG_AG_READY + r) for p in range(T)],
         )

@@ -88,7 +88,8 @@ class LayerNormLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, weight, bias, eps, tp):
-        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+        stage = tp.ag_input_buffer(x.shape[0], x.shape[1]) if (tp is not None and tp.fused) else None
+        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
         if tp is not None and tp.fused:
             y, ln_full = tp.ag_gemm(ln, weight, bias)
         else:
@@ -162,7 +163,8 @@ class LayerNormMLP(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, w1, b1, w2, b2, eps, tp):
-        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+        stage = tp.ag_input_buffer(x.shape[0], x.shape[1]) if (tp is not None and tp.fused) else None
+        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
         if tp is not None and tp.fused:
             z_holder = {}
             h1, ln_full = tp.ag_gemm(ln, w1, b1, gelu=True, aux_holder=z_holder)

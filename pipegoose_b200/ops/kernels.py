@@ -125,12 +125,13 @@ def accumulate_grad(grad, main_grad, accumulate: bool = True, scale: float = 1.0
 # ----------------------------------------------------------------------------------------------
 # LayerNorm (+ fused embedding gather)
 # ----------------------------------------------------------------------------------------------
-def layernorm_fwd(x, gamma, beta, eps, ids=None, vocab_start=0, vocab_end=0, apply_ln=True):
-    """Returns ``(y, mean, rstd)``.  With ``ids`` the input rows are gathered from the table ``x``."""
+def layernorm_fwd(x, gamma, beta, eps, ids=None, vocab_start=0, vocab_end=0, apply_ln=True, out=None):
+    """Returns ``(y, mean, rstd)``.  With ``ids`` the input rows are gathered from the table ``x``.
+    ``out``: optional preallocated bf16 destination (e.g. a peer-visible all-gather staging buffer)."""
     if use_native(x):
         h = x.shape[-1]
         rows = ids.numel() if ids is not None else x.numel() // h
-        y = torch.empty(rows, h, dtype=torch.bfloat16, device=x.device)
+        y = out if out is not None else torch.empty(rows, h, dtype=torch.bfloat16, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         native().layernorm_fwd(x, ids.reshape(-1) if ids is not None else None, vocab_start, vocab_end,

@@ -74,6 +74,9 @@ class TensorParallelComm:
         return _GatherCols.apply(x, self)
 
     # ------------------------------------------------------------------ fused kernels
+    def ag_input_buffer(self, rows_local: int, cols: int):
+        return self._engine.ag_input_buffer(rows_local, cols) if self.fused else None
+
     def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
         return self._engine.ag_gemm(x_shard, weight, bias, gelu, aux_holder)
 
