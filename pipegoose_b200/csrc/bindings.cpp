@@ -33,8 +33,9 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   memset(&d, 0, sizeof(d));
   const int64_t M = a_mn ? a.size(1) : a.size(0);
   const int64_t K = a_mn ? a.size(0) : a.size(1);
-  const int64_t N = b_mn ? b.size(1) : b.size(0);
-  const int64_t Kb = b_mn ? b.size(0) : b.size(1);
+  const int64_t groups = ag.contains("b_chunk_rows") ? num_chunks : 1;  // stacked (grouped) B
+  const int64_t N = b_mn ? b.size(1) : b.size(0) / groups;
+  const int64_t Kb = b_mn ? b.size(0) / groups : b.size(1);
   TORCH_CHECK(K == Kb, "gemm: contraction dims differ: ", K, " vs ", Kb);
   TORCH_CHECK(N % 8 == 0, "gemm: N must be a multiple of 8");
   d.A = a.data_ptr();
@@ -54,7 +55,7 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   TORCH_CHECK(d.ldc % 8 == 0, "out leading dimension must be a multiple of 8");
   d.flags = (int)flags | (f32 ? 8 : 0);
   if (bias.has_value()) {
-    TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->numel() == N && bias->is_contiguous(), "bias must be contiguous bf16 [N]");
+    TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->numel() % N == 0 && bias->is_contiguous(), "bias must be contiguous bf16 [N] (or [groups, N])");
     d.bias = bias->data_ptr();
     d.flags |= 1;
   }
@@ -83,7 +84,16 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   d.flag_value = (uint32_t)flag_value;
   for (size_t i = 0; i < out_peer_ptrs.size() && i < PG_MAX_PEERS; ++i) d.out_peer[i] = reinterpret_cast<void*>(out_peer_ptrs[i]);
   for (size_t i = 0; i < arrive_ctr_ptrs.size() && i < PG_MAX_PEERS; ++i) d.arrive_ctr[i] = reinterpret_cast<uint32_t*>(arrive_ctr_ptrs[i]);
-  if (ag.size() > 0) {
+  if (ag.contains("b_chunk_rows")) {
+    d.b_chunk_rows = ag["b_chunk_rows"].cast<int>();
+    d.bias_chunk_stride = ag.contains("bias_chunk_stride") ? ag["bias_chunk_stride"].cast<int>() : 0;
+    if (ag.contains("row_ret")) {
+      d.row_ret = reinterpret_cast<const int*>(ag["row_ret"].cast<int64_t>());
+      d.row_scale = reinterpret_cast<const float*>(ag["row_scale"].cast<int64_t>());
+      d.scatter_rows_per_src = ag["rows_per_src"].cast<int>();
+    }
+  }
+  if (ag.contains("n_comm")) {
     d.n_comm = ag["n_comm"].cast<int>();
     d.ag_dst = reinterpret_cast<void*>(ag["dst"].cast<int64_t>());
     d.ag_chunk_bytes = (uint64_t)ag["chunk_bytes"].cast<int64_t>();
@@ -225,6 +235,32 @@ void attention_bwd(const torch::Tensor& qkv, const torch::Tensor& slopes, const 
                                dq_acc.data_ptr<float>(), delta.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, cur_stream()) == 0, "attention_bwd failed");
 }
 
+void moe_route(const torch::Tensor& x, const torch::Tensor& wg, const c10::optional<torch::Tensor>& bg,
+               const c10::optional<torch::Tensor>& jitter, int64_t top_k, int64_t capacity, torch::Tensor probs,
+               torch::Tensor topk_idx, torch::Tensor topk_prob, torch::Tensor pos, torch::Tensor counts,
+               torch::Tensor prob_sum, torch::Tensor zsum, torch::Tensor lse) {
+  PG_CUDA(x); PG_BF16(x); PG_CUDA(wg); PG_BF16(wg); PG_CUDA(probs); PG_F32(probs);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int n = (int)x.size(0), h = (int)x.size(1), E = (int)wg.size(0);
+  const float* jp = jitter.has_value() ? jitter->data_ptr<float>() : nullptr;
+  TORCH_CHECK(pg_moe_route(x.data_ptr(), wg.data_ptr(), opt_ptr(bg), jp, n, h, E, (int)top_k, (int)capacity,
+                           probs.data_ptr<float>(), topk_idx.data_ptr<int>(), topk_prob.data_ptr<float>(), pos.data_ptr<int>(),
+                           counts.data_ptr<int>(), prob_sum.data_ptr<float>(), zsum.data_ptr<float>(), lse.data_ptr<float>(), cur_stream()) == 0, "moe_route failed");
+}
+
+void moe_dispatch(const torch::Tensor& x, const torch::Tensor& topk_idx, const torch::Tensor& topk_prob, const torch::Tensor& pos,
+                  std::vector<int64_t> peer_buf, std::vector<int64_t> peer_row_ret, std::vector<int64_t> peer_row_scale,
+                  std::vector<int64_t> peer_arrive, int64_t top_k, int64_t E_local, int64_t C, int64_t my_rank, bool scale_by_prob, int64_t blocks) {
+  PG_CUDA(x); PG_BF16(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int T = (int)peer_buf.size();
+  void* bufs[PG_MAX_PEERS]; int* rets[PG_MAX_PEERS]; float* scs[PG_MAX_PEERS]; uint32_t* arr[PG_MAX_PEERS];
+  for (int i = 0; i < T; ++i) { bufs[i] = reinterpret_cast<void*>(peer_buf[i]); rets[i] = reinterpret_cast<int*>(peer_row_ret[i]);
+    scs[i] = reinterpret_cast<float*>(peer_row_scale[i]); arr[i] = reinterpret_cast<uint32_t*>(peer_arrive[i]); }
+  TORCH_CHECK(pg_moe_dispatch(x.data_ptr(), topk_idx.data_ptr<int>(), topk_prob.data_ptr<float>(), pos.data_ptr<int>(), bufs, rets, scs, arr,
+                              (int)x.size(0), (int)x.size(1), (int)top_k, (int)E_local, T, (int)C, (int)my_rank, scale_by_prob, (int)blocks, cur_stream()) == 0, "moe_dispatch failed");
+}
+
 // ---------------------------------------------------------------- symmetric memory / collectives
 py::tuple symm_alloc(int64_t nbytes) {
   void* ptr = nullptr;
@@ -301,6 +337,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
+  m.def("moe_route", &moe_route);
+  m.def("moe_dispatch", &moe_dispatch);
   m.def("symm_alloc", &symm_alloc);
   m.def("symm_open", &symm_open);
   m.def("symm_close", &symm_close);

@@ -181,6 +181,11 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
     args.out_peer[i] = d->out_peer[i];
     args.arrive_ctr[i] = d->arrive_ctr[i];
   }
+  args.b_chunk_rows = d->b_chunk_rows;
+  args.bias_chunk_stride = d->bias_chunk_stride;
+  args.row_ret = d->row_ret;
+  args.row_scale = d->row_scale;
+  args.scatter_rows_per_src = d->scatter_rows_per_src > 0 ? d->scatter_rows_per_src : 1;
   args.n_comm = d->n_comm;
   args.ag_dst = d->ag_dst;
   args.ag_chunk_bytes = d->ag_chunk_bytes;
@@ -208,10 +213,11 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   } else {
     if (cached_tmap(&ta, d->A, d->K, d->M, d->lda, BK) != 0) return -1;
   }
+  const uint64_t b_groups = d->b_chunk_rows > 0 ? (uint64_t)args.num_chunks : 1;  // stacked expert weights
   if (!d->b_mn) {
-    if (cached_tmap(&tb, d->B, d->N, d->K, d->ldb, bn) != 0) return -1;
+    if (cached_tmap(&tb, d->B, d->N * b_groups, d->K, d->ldb, bn) != 0) return -1;
   } else {
-    if (cached_tmap(&tb, d->B, d->K, d->N, d->ldb, BK) != 0) return -1;
+    if (cached_tmap(&tb, d->B, d->K * b_groups, d->N, d->ldb, BK) != 0) return -1;
   }
 
   tal = ta;

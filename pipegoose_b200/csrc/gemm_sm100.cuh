@@ -30,6 +30,7 @@ enum EpiFlags : int {
   EPI_OUT_F32 = 8,     // out is fp32
   EPI_ACCUM = 16,      // out += acc (fp32 out only)
   EPI_DGELU = 32,      // out = acc * gelu_tanh'(aux_in[row, col])
+  EPI_SCATTER = 64,    // MoE combine: out row -> out_peer[src][row_ret[row]], scaled by row_scale[row]
 };
 
 struct GemmArgs {
@@ -59,6 +60,15 @@ struct GemmArgs {
   uint32_t ag_epoch;
   int my_rank;
   int a_local_chunk;  // >= 0: tiles of this chunk load A through tma_a_local (rows relative to the chunk)
+  // grouped GEMM (one chunk per expert): B / bias of chunk c start b_chunk_rows*c rows / bias_chunk_stride*c
+  // elements further (stacked expert weights)
+  int b_chunk_rows;
+  int bias_chunk_stride;
+  // EPI_SCATTER: row r (inside its chunk) came from rank r / scatter_rows_per_src; it returns to row
+  // row_ret[r] of that rank's buffer out_peer[rank] (row_ret < 0: empty slot), scaled by row_scale[r]
+  const int* row_ret;
+  const float* row_scale;
+  int scatter_rows_per_src;
   // GEMM -> reduce-scatter: rows of chunk c go to out_peer[c] (row index relative to chunk),
   // then arrive_ctr[c] (+1 per finished tile, release.sys)
   void* out_peer[kMaxPeers];
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // bandwidth-delay product).
     constexpr uint32_t kSlice = 16 * 1024;
     constexpr int kCommStages = 12;  // smem ring slots
-    constexpr int kLoadsInFlight = 8;  // => up to kCommStages - kLoadsInFlight stores may still be reading smem
+    constexpr int kLoadsInFlight = 10;  // => up to kCommStages - kLoadsInFlight stores may still be reading smem
     uint64_t* cbar = reinterpret_cast<uint64_t*>(smem + kCommStages * kSlice);
     if (threadIdx.x == 0) {
       for (int i = 0; i < kCommStages; ++i) mbar_init(&cbar[i], 1);
@@ -280,11 +290,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               tma_load_2d(sa + i * (BK * 128), map_a, &full_bar[stage], m0 + i * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0 + tc.chunk * args.b_chunk_rows);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK);
+              tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK + tc.chunk * args.b_chunk_rows);
           }
         }
         __syncwarp();
@@ -351,7 +361,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int row_limit = args.M;
       if (args.num_chunks > 1) {
         row_limit = (tc.chunk + 1) * chunk_rows;
-        if (args.out_peer[0] != nullptr) {
+        if (args.out_peer[0] != nullptr && !(args.flags & EPI_SCATTER)) {
           out_base = reinterpret_cast<uint8_t*>(args.out_peer[tc.chunk]);
           out_row = row - tc.chunk * chunk_rows;
         }
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < ncols) {
-              const uint4 bb = ld_global_nc_v4(args.bias + col0 + g * 8);
+              const uint4 bb = ld_global_nc_v4(args.bias + tc.chunk * args.bias_chunk_stride + col0 + g * 8);
               const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -467,6 +477,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           }
         }
+        if (active && (args.flags & EPI_SCATTER)) {
+          const float sc = args.row_scale[row];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] *= sc;
+        }
         // stage this thread's 32 bf16 (64 B) into the warp's [32 rows x 128 B] buffer (16-byte chunks
         // XOR-swizzled by row); every second chunk the warp writes 128-byte row segments to global
         // (or peer) memory: 8 lanes per row, 4 rows per store instruction
@@ -489,7 +504,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const int rr = i * 4 + (lane >> 3);
             if (rr < rows_ok && ch * 8 < span) {
               const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 128 + ((ch ^ (rr & 7)) << 4));
-              st_global_v4(ob + static_cast<size_t>(warp_out_row0 + rr) * args.ldc + colbase + ch * 8, val);
+              if (args.flags & EPI_SCATTER) {
+                const int gr = warp_row0 + rr;
+                const int ret = args.row_ret[gr];
+                if (ret >= 0) {
+                  const int src = (gr - tc.chunk * chunk_rows) / args.scatter_rows_per_src;
+                  st_global_v4(reinterpret_cast<__nv_bfloat16*>(args.out_peer[src]) +
+                                   static_cast<size_t>(ret) * args.ldc + colbase + ch * 8, val);
+                }
+              } else {
+                st_global_v4(ob + static_cast<size_t>(warp_out_row0 + rr) * args.ldc + colbase + ch * 8, val);
+              }
             }
           }
           __syncwarp();
@@ -499,7 +524,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr) {
+      if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr && !(args.flags & EPI_SCATTER)) {
         // all four epilogue warps have stored their rows of this tile -> publish to the owner
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (warp == 4 && lane == 0) {

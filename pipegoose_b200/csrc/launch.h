@@ -41,6 +41,11 @@ typedef struct PgGemmDesc {
   uint32_t ag_epoch;
   int my_rank;
   const void* a_local;  // all-gather -> GEMM: this rank's shard [chunk_rows, K] (read in place)
+  // grouped GEMM / MoE combine
+  int b_chunk_rows, bias_chunk_stride;
+  const int* row_ret;
+  const float* row_scale;
+  int scatter_rows_per_src;
 } PgGemmDesc;
 
 // ---- attention_sm100.cu
@@ -48,6 +53,16 @@ int pg_attention_fwd(const void* qkv, const float* slopes, void* out, float* lse
                      cudaStream_t s);
 int pg_attention_bwd(const void* qkv, const float* slopes, const void* out, const float* lse, const void* dout,
                      void* dqkv, float* dq_acc, float* delta, int B, int S, int H, int D, cudaStream_t s);
+
+// ---- moe.cu
+int pg_moe_route(const void* x, const void* wg, const void* bg, const float* jitter, int n, int h, int E, int top_k,
+                 int capacity, float* probs, int* topk_idx, float* topk_prob, int* pos, int* counts,
+                 float* prob_sum, float* zsum, float* lse_out, cudaStream_t s);
+int pg_moe_dispatch(const void* x, const int* topk_idx, const float* topk_prob, const int* pos,
+                    void* const* peer_buf, int* const* peer_row_ret, float* const* peer_row_scale,
+                    uint32_t* const* peer_arrive, int n, int h, int top_k, int E_local, int T, int C, int my_rank,
+                    int scale_by_prob, int blocks, cudaStream_t s);
+int pg_fill_i32(int* p, int v, int64_t n, cudaStream_t s);
 
 // ---- comm.cu
 // out[rows, cols] = sum_src staging[src][rows, cols] (+ bias) (+ residual), after every source's

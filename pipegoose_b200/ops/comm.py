@@ -25,7 +25,9 @@ from pipegoose_b200.ops import kernels as K
 from pipegoose_b200.ops import native
 
 _BM = 128
-N_COMM_CTAS = 8
+import os
+
+N_COMM_CTAS = int(os.environ.get("PIPEGOOSE_B200_NCOMM", "16"))
 
 
 def pick_block_n(rows: int, n: int, chunks: int, ctas: int) -> int:
