@@ -18,7 +18,8 @@ from pipegoose_b200.nn.parallel import Parallel
 class ExpertParallel(Parallel):
     def __init__(self, module: nn.Module, num_experts: int, expert: Optional[nn.Module] = None,
                  mapping: Optional[List[int]] = None, router: nn.Module = None,
-                 enable_tensor_parallelism: bool = False, parallel_context: ParallelContext = None):
+                 enable_tensor_parallelism: bool = False, parallel_context: ParallelContext = None,
+                 fused: Optional[bool] = None):
         super().__init__(module, parallel_context)
         tensor_parallel_size = parallel_context.get_world_size(ParallelMode.TENSOR)
         assert num_experts % tensor_parallel_size == 0, \
@@ -33,6 +34,7 @@ class ExpertParallel(Parallel):
         self.mapping = mapping
         self.router = router
         self.enable_tensor_parallelism = enable_tensor_parallelism
+        self.fused = fused
 
     @staticmethod
     def _blocks(module: nn.Module):
@@ -49,9 +51,31 @@ class ExpertParallel(Parallel):
             if layer_idx not in self.mapping:
                 continue
             expert = self.expert if self.expert is not None else block.mlp
-            block.mlp = ExpertLayer(self.num_experts, expert, self.router, self.enable_tensor_parallelism,
-                                    self.parallel_context)
+            if self._use_fused(expert):
+                # NVLink all-to-all dispatch/combine + grouped tcgen05 expert GEMMs (ops/moe.py)
+                from pipegoose_b200.ops.moe import FusedExpertLayer
+
+                block.mlp = FusedExpertLayer(self.num_experts, expert, self.router, self.parallel_context)
+            else:
+                block.mlp = ExpertLayer(self.num_experts, expert, self.router, self.enable_tensor_parallelism,
+                                        self.parallel_context)
         return self.module
+
+    def _use_fused(self, expert: nn.Module) -> bool:
+        """Fused path: pipegoose_b200 Bloom (token-sharded 2-D activations), BloomMLP experts, a Top-k
+        router with a linear gate, NCCL/CUDA.  ``fused=None`` picks it automatically."""
+        import torch.distributed as dist
+
+        from pipegoose_b200.models.bloom import BloomMLP
+
+        if self.fused is False or self.enable_tensor_parallelism:
+            return False
+        ok = (isinstance(expert, BloomMLP) and hasattr(self.module, "hidden_states") and hasattr(self.router, "gate")
+              and torch.cuda.is_available()
+              and dist.get_backend(self.parallel_context.get_group(ParallelMode.TENSOR)) == "nccl")
+        if self.fused is True and not ok:
+            raise ValueError("fused=True needs a pipegoose_b200 Bloom model, BloomMLP experts, a gate router and NCCL")
+        return ok
 
     @torch.no_grad()
     def deparallelize(self) -> nn.Module:

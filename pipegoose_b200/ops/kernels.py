@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from pipegoose_b200.ops import native, use_native
 
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ACCUM, EPI_DGELU = 1, 2, 4, 8, 16, 32
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ACCUM, EPI_DGELU, EPI_SCATTER = 1, 2, 4, 8, 16, 32, 64
 
 
 def gelu_tanh(x: torch.Tensor) -> torch.Tensor:

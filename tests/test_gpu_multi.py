@@ -207,3 +207,67 @@ def test_fused_moe_layer(top_k):
     from pipegoose_b200.testing.utils import spawn
 
     spawn(run_fused_moe, world_size=2, top_k=top_k)
+
+
+def run_dp_zero(rank, world_size, port, fused_dp, state, ids, ref_losses):
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import DataParallel
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    os.environ["PIPEGOOSE_B200_FUSED_DP"] = "1" if fused_dp else "0"
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size, backend="nccl")
+    cfg = BloomConfig(vocab_size=4096, hidden_size=256, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    model.load_state_dict(state)
+    model = model.to(torch.bfloat16)
+    model = DataParallel(model, ctx, bucket_size_mb=1.0).parallelize()
+    model.to("cuda")
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-3), ctx)
+    local = ids.chunk(world_size)[rank].cuda()
+    losses = []
+    for _ in range(len(ref_losses)):
+        loss = model(local, labels=local).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        losses.append(loss.item())
+    assert (model._pg_grad_reducer._fused is not None) == fused_dp
+    import torch.distributed as dist
+
+    t = torch.tensor(losses, device="cuda")
+    dist.all_reduce(t)
+    mean_losses = (t / world_size).tolist()
+    for a, b in zip(mean_losses, ref_losses):
+        assert abs(a - b) < 5e-2, (mean_losses, ref_losses)
+    # replicas hold identical parameters after ZeRO-1's all-gather
+    flat = model._flat_state.flat_param.float()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(flat, ref)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fused_dp", [False, True])
+def test_dp2_zero1_matches_single_gpu(fused_dp):
+    _need_gpus(2)
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.testing.utils import spawn
+
+    torch.manual_seed(0)
+    cfg = BloomConfig(vocab_size=4096, hidden_size=256, n_layer=2, n_head=4)
+    ref = BloomForCausalLM(cfg)
+    state = copy.deepcopy(ref.state_dict())
+    ids = torch.randint(0, 4096, (4, 256))
+    model = copy.deepcopy(ref).to(torch.bfloat16).cuda()
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    ref_losses = []
+    for _ in range(3):
+        loss = model(ids.cuda(), labels=ids.cuda()).loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(loss.item())
+    spawn(run_dp_zero, world_size=2, fused_dp=fused_dp, state=state, ids=ids, ref_losses=ref_losses)
