@@ -54,7 +54,11 @@ struct AttFwdCfg {
   static constexpr int kTileBytes = ATT_BM * D * 2;       // Q, K or V tile
   static constexpr int kPBytes = ATT_BM * ATT_BN * 2;     // 32 KB
   static constexpr int kStages = 2;
-  static constexpr int kSmemBytes = kTileBytes * (1 + 2 * kStages) + kPBytes + 1024 + 256;
+  // D == 64: one S buffer and 256 TMEM columns so that TWO CTAs fit per SM (112 KB smem each) and
+  // overlap each other's softmax / MMA phases; D == 128: S double-buffered inside one CTA per SM.
+  static constexpr int kSBufs = (D == 64) ? 1 : 2;
+  static constexpr int kTmemCols = (D == 64) ? 256 : 512;
+  static constexpr int kSmemBytes = kTileBytes * (1 + 2 * kStages) + kPBytes + 256;  // base is 1024-aligned
   static constexpr int kThreads = 192;
 };
 
@@ -67,12 +71,13 @@ struct AttFwdArgs {
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttFwdArgs args) {
   using Cfg = AttFwdCfg<D>;
   constexpr int ST = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int SB = Cfg::kSBufs;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kTileBytes;
   uint8_t* sV = sK + ST * Cfg::kTileBytes;
@@ -113,15 +118,15 @@ __global__ void __launch_bounds__(192, 1)
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S0 = tmem_base;           // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;      // D columns
+  const uint32_t tmem_S0 = tmem_base;              // SB x 128 columns
+  const uint32_t tmem_O = tmem_base + SB * 128;    // D columns
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -161,10 +166,10 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll
       for (int k = 0; k < D / 16; ++k) {
         const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-        umma_f16(tmem_S0 + (j & 1) * 128, make_smem_desc_sw128(aQ + off, 0, 1024),
+        umma_f16(tmem_S0 + (j % SB) * 128, make_smem_desc_sw128(aQ + off, 0, 1024),
                  make_smem_desc_sw128(aK + off, 0, 1024), idesc_s, k != 0 ? 1u : 0u);
       }
-      umma_commit(&s_full[j & 1]);
+      umma_commit(&s_full[j % SB]);
     };
     int stage = 0;
     uint32_t phase = 0;
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(192, 1)
         const int nstage = (stage + 1 == ST) ? 0 : stage + 1;
         const uint32_t nphase = (stage + 1 == ST) ? phase ^ 1 : phase;
         mbar_wait(&kv_full[nstage], nphase);
-        if (j + 1 >= 2) mbar_wait(&s_free[(j + 1) & 1], (((j + 1) >> 1) - 1) & 1);
+        if (j + 1 >= SB) mbar_wait(&s_free[(j + 1) % SB], (((j + 1) / SB) - 1) & 1);
         tc_fence_after();
         if (lane == 0) issue_s(j + 1, nstage);
         __syncwarp();
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(192, 1)
     for (int i = 0; i < D; ++i) acc[i] = 0.f;
 
     for (int j = 0; j < num_kb; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
-      const uint32_t tS = tmem_S0 + (j & 1) * 128 + lane_addr;
+      const uint32_t tS = tmem_S0 + (j % SB) * 128 + lane_addr;
       const bool diag = (j == qb);
       const int kbase = j * ATT_BN - qpos;  // key_pos - query_pos for column 0
       // pass 1: row max of x = s*scale_log2 + slope2*(kpos - qpos), masked
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(192, 1)
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(p_ready);
-      mbar_arrive(&s_free[j & 1]);
+      mbar_arrive(&s_free[j % SB]);
     }
     // last block's O
     mbar_wait(o_full, (num_kb - 1) & 1);
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(192, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -104,26 +104,45 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int worl
   const int64_t seg = n / world;  // n is a multiple of world * 4
   const int64_t my0 = offset + rank * seg;
   const int64_t nvec = seg / 4;
-  // reduce my slice: pull the same slice from every peer
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // reduce my slice: pull the same slice from every peer.  kU independent 16-byte loads per thread per
+  // peer are issued before any is consumed (NVLink latency ~2 us: bytes in flight, not threads, set the rate)
+  constexpr int kU = 8;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
+    float4 acc[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int s = 0; s < world; ++s) {
       int src = rank + s;
       if (src >= world) src -= world;
-      const float4 v = *reinterpret_cast<const float4*>(p.buf[src] + my0 + i * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      const float* base = p.buf[src] + my0;
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        v[u] = (i < nvec) ? *reinterpret_cast<const float4*>(base + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+      }
     }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    if (rs_only) {
-      *reinterpret_cast<float4*>(p.buf[rank] + my0 + i * 4) = acc;
-    } else {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= nvec) continue;
+      float4 r = acc[u];
+      r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+      if (rs_only) {
+        *reinterpret_cast<float4*>(p.buf[rank] + my0 + i * 4) = r;
+      } else {
 #pragma unroll 1
-      for (int s = 0; s < world; ++s) {
-        int dst = rank + s;
-        if (dst >= world) dst -= world;
-        *reinterpret_cast<float4*>(p.buf[dst] + my0 + i * 4) = acc;
+        for (int s = 0; s < world; ++s) {
+          int dst = rank + s;
+          if (dst >= world) dst -= world;
+          *reinterpret_cast<float4*>(p.buf[dst] + my0 + i * 4) = r;
+        }
       }
     }
   }
@@ -156,14 +175,24 @@ __global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int
     const int64_t seg = len / world;
     const int64_t my0 = start + rank * seg;
     const int64_t nvec = seg / 8;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-      const uint4 v = ld_global_v4(p.buf[rank] + my0 + i * 8);
+    constexpr int kU = 4;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
+      uint4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        v[u] = (i < nvec) ? ld_global_v4(p.buf[rank] + my0 + i * 8) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll 1
       for (int s = 1; s < world; ++s) {
         int dst = rank + s;
         if (dst >= world) dst -= world;
-        st_global_v4(p.buf[dst] + my0 + i * 8, v);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int64_t i = i0 + u * stride;
+          if (i < nvec) st_global_v4(p.buf[dst] + my0 + i * 8, v[u]);
+        }
       }
     }
   }
@@ -228,7 +257,7 @@ extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, in
     p.flag[i] = peer_flags[i];
   }
   // few CTAs: the kernel is NVLink-bound and must leave the SMs to the backward GEMMs it overlaps
-  const int blocks = 16;
+  const int blocks = 24;
   allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, world, rank, offset_elems, n, scale,
                                               reduce_scatter_only, epoch,
                                               peer_flags[rank] + 2 * PG_MAX_PEERS);
