@@ -98,12 +98,13 @@ class FlatModelState:
             for p in self.params:
                 p._mg_fresh = False
             return
+        small = getattr(self, "_small_grads", None)
+        if small is None:
+            small = self._small_grads = [p.main_grad for p in self.params if p.dim() < 2]
+        if small:
+            torch._foreach_zero_(small)  # one multi-tensor launch instead of one fill per bias / LN vector
         for p in self.params:
-            if p.dim() < 2:
-                p.main_grad.zero_()
-                p._mg_fresh = False
-            else:
-                p._mg_fresh = True
+            p._mg_fresh = p.dim() >= 2
 
     def finalize_grads(self):
         """Parameters that received no gradient this step (still fresh) must read as zero."""

@@ -93,6 +93,7 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
       d.scatter_rows_per_src = ag["rows_per_src"].cast<int>();
     }
   }
+  if (ag.contains("k_splits")) d.k_splits = ag["k_splits"].cast<int>();
   if (ag.contains("n_comm")) {
     d.n_comm = ag["n_comm"].cast<int>();
     d.ag_dst = reinterpret_cast<void*>(ag["dst"].cast<int64_t>());

@@ -121,7 +121,8 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     attr_set = true;
   }
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
-  const int tiles = ((chunk_rows + BM - 1) / BM) * ((args.N + BN - 1) / BN) * args.num_chunks;
+  const int tiles = ((chunk_rows + BM - 1) / BM) * ((args.N + BN - 1) / BN) * args.num_chunks *
+                    (args.k_splits > 1 ? args.k_splits : 1);
   int gemm_ctas = max_ctas - args.n_comm;
   if (gemm_ctas < 1) gemm_ctas = 1;
   int grid = (tiles < gemm_ctas ? tiles : gemm_ctas) + args.n_comm;
@@ -135,20 +136,32 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   return 0;
 }
 
-static int pick_bn(int M_rows, int N, int chunks, int ctas) {
+// Tile width (and, for fp32-accumulating outputs, a K split) by a wave-quantisation cost model:
+// cost = waves * (k-blocks per work item * BN / efficiency(BN)) + one exposed epilogue.
+static int pick_bn(int M_rows, int N, int K, int chunks, int ctas, bool allow_split, int* k_splits) {
   const int cand[4] = {256, 192, 128, 64};
   const float eff[4] = {1.0f, 0.93f, 0.82f, 0.55f};
+  const int num_kb = (K + BK - 1) / BK;
   int best = 256;
   float best_cost = 1e30f;
+  *k_splits = 1;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
     if (bn > 64 && N <= bn / 2) continue;
     const long tiles = (long)((M_rows + BM - 1) / BM) * ((N + bn - 1) / bn) * chunks;
-    const long waves = (tiles + ctas - 1) / ctas;
-    const float cost = (float)waves * (float)bn / eff[i];
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+    const int max_split = allow_split ? 8 : 1;
+    for (int s = 1; s <= max_split; ++s) {
+      const int per = (num_kb + s - 1) / s;
+      if (s > 1 && (per < 16 || (long)(s - 1) * per >= num_kb)) break;
+      const long waves = (tiles * s + ctas - 1) / ctas;
+      // the epilogue of the last wave is exposed; atomics cost about twice a plain store
+      const float epi = (s > 1 ? 16.0f : 8.0f) * (float)bn;
+      const float cost = (float)waves * (float)per * (float)bn / eff[i] + epi;
+      if (cost < best_cost * 0.97f) {
+        best_cost = cost;
+        best = bn;
+        *k_splits = s;
+      }
     }
   }
   return best;
@@ -202,7 +215,35 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   }
   int max_ctas = d->max_ctas > 0 ? d->max_ctas : num_sms();
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
-  int bn = d->block_n > 0 ? d->block_n : pick_bn(chunk_rows, args.N, args.num_chunks, max_ctas - args.n_comm);
+  if ((args.flags & EPI_DGELU) && (args.flags & EPI_RESIDUAL)) {
+    fprintf(stderr, "pipegoose_b200: EPI_DGELU and EPI_RESIDUAL are mutually exclusive\n");
+    return -1;
+  }
+  // split-K only where the epilogue can add partial sums: plain fp32 outputs (wgrad into main grads)
+  const bool allow_split = (args.flags & EPI_OUT_F32) && args.num_chunks == 1 && args.bias == nullptr &&
+                           d->k_splits != 1 && (d->ldc % 4) == 0;
+  int auto_splits = 1;
+  int bn = pick_bn(chunk_rows, args.N, args.K, args.num_chunks, max_ctas - args.n_comm, allow_split, &auto_splits);
+  if (d->block_n > 0) {
+    bn = d->block_n;
+    auto_splits = 1;
+  }
+  args.k_splits = (allow_split && d->k_splits > 1) ? d->k_splits : auto_splits;
+  {
+    const int num_kb = (args.K + BK - 1) / BK;
+    if (args.k_splits > num_kb) args.k_splits = num_kb;
+    if (args.k_splits > 1) {
+      const int per = (num_kb + args.k_splits - 1) / args.k_splits;
+      args.k_splits = (num_kb + per - 1) / per;  // no empty split
+    }
+  }
+  if (args.k_splits > 1) {
+    if (!(args.flags & EPI_ACCUM)) {
+      // partial sums are added atomically: an overwriting GEMM starts from zero
+      cudaMemset2DAsync(args.out, (size_t)args.ldc * 4, 0, (size_t)args.N * 4, (size_t)args.M, stream);
+    }
+    args.flags |= EPI_ATOMIC | EPI_ACCUM;
+  }
 
   CUtensorMap ta, tb, tal;
   args.a_local_chunk = -1;

@@ -31,10 +31,12 @@ enum EpiFlags : int {
   EPI_ACCUM = 16,      // out += acc (fp32 out only)
   EPI_DGELU = 32,      // out = acc * gelu_tanh'(aux_in[row, col])
   EPI_SCATTER = 64,    // MoE combine: out row -> out_peer[src][row_ret[row]], scaled by row_scale[row]
+  EPI_ATOMIC = 128,    // fp32 out += acc with red.global.add (split-K partial sums)
 };
 
 struct GemmArgs {
   int M, N, K;
+  int k_splits;  // >1: the K loop is split over k_splits work items per tile (EPI_ATOMIC epilogue)
   void* out;
   int ldc;
   const __nv_bfloat16* bias;
@@ -78,7 +80,7 @@ struct GemmArgs {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 
 template <int BN>
 struct GemmCfg {
@@ -88,7 +90,7 @@ struct GemmCfg {
   static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kEpiStageBytes = 4 * 32 * 128;  // 4 epilogue warps x [32 rows x 128 B]
+  static constexpr int kEpiStageBytes = 8 * 32 * 64;  // 8 epilogue warps x [32 rows x 64 B]
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -161,6 +163,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int n_blks = (args.N + BN - 1) / BN;
   const int num_tiles = m_blks_per_chunk * n_blks * args.num_chunks;
   const int num_kb = (args.K + BK - 1) / BK;
+  const int k_splits = args.k_splits > 1 ? args.k_splits : 1;
+  const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
+  const int num_work = num_tiles * k_splits;  // work item t: tile t % num_tiles, K split t / num_tiles
 
   if (static_cast<int>(blockIdx.x) < args.n_comm) {
     // ============================ communication CTA ============================
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_mbar_init();
   }
@@ -257,8 +262,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int seen_chunk = -1;
-    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm) {
-      const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
+    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm) {
+      const TileCoord tc = map_tile(t % num_tiles, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
+      const int kb_begin = (t / num_tiles) * kb_per_split;
+      const int kb_end = min(num_kb, kb_begin + kb_per_split);
       if (args.chunk_flags != nullptr && tc.chunk != seen_chunk && tc.chunk != args.a_local_chunk) {
         if (lane == 0) {
           while (ld_acquire_sys(args.chunk_flags + tc.chunk) < args.flag_value) {
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         map_a = &tma_a_local;
         m0 -= tc.chunk * chunk_rows;
       }
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -310,13 +317,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm, ++it) {
+    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb_begin = (t / num_tiles) * kb_per_split;
+      const int kb_end = min(num_kb, kb_begin + kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -330,10 +339,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
-            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -344,15 +353,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp >= 4) {
     // ============================ epilogue ============================
-    const int q = warp - 4;  // == warp % 4 -> TMEM lanes [32q, 32q+32)
-    int it = 0;
+    // 8 warps: warp e = 4 + q + 4h drains TMEM lanes [32q, 32q+32) (a warp may only touch the lane
+    // quarter warp%4) and takes every second 32-column chunk (c = h, h+2, ...).  Every global access
+    // is coalesced through a per-warp [32 rows x 64 B] staging buffer (16-byte chunks XOR-swizzled by
+    // row pair): 4 lanes cover one 64-byte row segment, 8 rows per instruction.  Epilogue inputs
+    // (residual / GELU' pre-activation) are prefetched one chunk ahead into registers.
+    const int e = warp - 4;
+    const int q = e & 3;  // == warp % 4
+    const int h = e >> 2;
+    constexpr int NCH = BN / 32;
     const bool out_f32 = (args.flags & EPI_OUT_F32) != 0;
-    for (int t = blockIdx.x - args.n_comm; t < num_tiles; t += gridDim.x - args.n_comm, ++it) {
-      const TileCoord tc = map_tile(t, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
+    const __nv_bfloat16* in_ptr = nullptr;
+    int in_ld = 0;
+    if (!out_f32) {
+      if (args.flags & EPI_DGELU) {
+        in_ptr = reinterpret_cast<const __nv_bfloat16*>(args.aux);
+        in_ld = args.ldc;
+      } else if (args.flags & EPI_RESIDUAL) {
+        in_ptr = args.residual;
+        in_ld = args.ldr;
+      }
+    }
+    uint8_t* stg_warp = smem_epi + e * 2048;
+    uint8_t* stg_own = stg_warp + lane * 64;         // this thread's row (64 B)
+    const int own_sw = (lane >> 1) & 3;               // swizzle of this thread's row
+    const int co_r = lane >> 2;                       // coalesced pattern: row inside a group of 8
+    const int co_ch = lane & 3;                       // 16-byte chunk of the 64-byte segment
+    int it = 0;
+    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm, ++it) {
+      const TileCoord tc = map_tile(t % num_tiles, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = tc.m_blk * BM + q * 32 + lane;
       const int n0 = tc.n_blk * BN;
       // destination row pointer (possibly on a peer GPU)
@@ -370,12 +401,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const int warp_row0 = tc.m_blk * BM + q * 32;          // first row handled by this warp
       const int warp_out_row0 = out_row - lane;               // its destination row index
       const int rows_ok = max(0, min(32, min(row_limit, args.M) - warp_row0));
-      uint8_t* stg_warp = smem_epi + q * 4096;
+      uint4 pre[4];
+      auto prefetch_in = [&](int c) {
+        const int col = n0 + c * 32 + co_ch * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + co_r;
+          pre[i] = make_uint4(0, 0, 0, 0);
+          if (rr < rows_ok && col < args.N)
+            pre[i] = ld_global_nc_v4(in_ptr + static_cast<size_t>(warp_row0 + rr) * in_ld + col);
+        }
+      };
+      if (in_ptr != nullptr && h < NCH) prefetch_in(h);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = h; c < NCH; c += 2) {
         uint32_t v[32];
-        __syncwarp();
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        if (in_ptr != nullptr) {
+          // park the prefetched inputs in the staging buffer, start fetching the next chunk's
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + co_r;
+            *reinterpret_cast<uint4*>(stg_warp + rr * 64 + ((co_ch ^ ((rr >> 1) & 3)) << 4)) = pre[i];
+          }
+          __syncwarp();
+          if (c + 2 < NCH) prefetch_in(c + 2);
+        }
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
         const int ncols = max(0, min(32, args.N - col0));  // multiple of 8
@@ -406,71 +459,62 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             for (int g = 0; g < 8; ++g) {
               if (g * 4 < ncols) {
                 float4 val = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                if (args.flags & EPI_ACCUM) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + g * 4);
-                  val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                if (args.flags & EPI_ATOMIC) {
+                  red_add_v4_f32(o + g * 4, val);  // split-K partial sums
+                } else {
+                  if (args.flags & EPI_ACCUM) {
+                    const float4 old = *reinterpret_cast<const float4*>(o + g * 4);
+                    val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(o + g * 4) = val;
                 }
-                *reinterpret_cast<float4*>(o + g * 4) = val;
               }
             }
           }
           continue;
         }
-        const int half = (c & 1) * 4;  // which 64-byte half of the 128-byte staging row
-        if ((args.flags & EPI_GELU) && args.aux != nullptr) {
-          // pre-activation goes out through the same staged, coalesced path (second buffer pass)
-          uint8_t* stg = stg_warp + lane * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(stg + (((half + g) ^ (lane & 7)) << 4)) =
-                make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                           pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+        // coalesced store of the staged [32 x 64 B] block to rows dst_row0.. of a bf16 matrix
+        auto store_block = [&](__nv_bfloat16* base, int dst_row0, int ld) {
           __syncwarp();
-          {
-            __nv_bfloat16* aux = reinterpret_cast<__nv_bfloat16*>(args.aux);
-            const int ch = lane & 3;  // 16-byte chunk inside this 64-byte half
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = i * 8 + (lane >> 2);
-              if (rr < rows_ok && ch * 8 < ncols) {
-                const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 128 + (((half + ch) ^ (rr & 7)) << 4));
-                st_global_v4(aux + static_cast<size_t>(warp_row0 + rr) * args.ldc + col0 + ch * 8, val);
-              }
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + co_r;
+            if (rr < rows_ok && co_ch * 8 < ncols) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 64 + ((co_ch ^ ((rr >> 1) & 3)) << 4));
+              st_global_v4(base + static_cast<size_t>(dst_row0 + rr) * ld + col0 + co_ch * 8, val);
             }
           }
           __syncwarp();
-        }
+        };
+        auto stage_own = [&]() {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg_own + ((g ^ own_sw) << 4)) =
+                make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
+                           pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
+        };
         if (args.flags & EPI_GELU) {
+          if (args.aux != nullptr) {
+            // the pre-activation goes out through the same staged, coalesced path
+            stage_own();
+            store_block(reinterpret_cast<__nv_bfloat16*>(args.aux), warp_row0, args.ldc);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
         }
-        if (active && (args.flags & EPI_DGELU)) {
-          const __nv_bfloat16* az = reinterpret_cast<const __nv_bfloat16*>(args.aux) +
-                                    static_cast<size_t>(row) * args.ldc + col0;
+        if (in_ptr != nullptr) {
+          const bool dgelu = (args.flags & EPI_DGELU) != 0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (g * 8 < ncols) {
-              const uint4 z = ld_global_nc_v4(az + g * 8);
-              const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+            const uint4 z = *reinterpret_cast<const uint4*>(stg_own + ((g ^ own_sw) << 4));
+            const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 zf = unpack_bf16x2(zw[j]);
+            for (int j = 0; j < 4; ++j) {
+              const float2 zf = unpack_bf16x2(zw[j]);
+              if (dgelu) {
                 f[g * 8 + 2 * j] *= gelu_tanh_grad(zf.x);
                 f[g * 8 + 2 * j + 1] *= gelu_tanh_grad(zf.y);
-              }
-            }
-          }
-        }
-        if (active && (args.flags & EPI_RESIDUAL)) {
-          const __nv_bfloat16* rp = args.residual + static_cast<size_t>(row) * args.ldr + col0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g * 8 < ncols) {
-              const uint4 z = ld_global_nc_v4(rp + g * 8);
-              const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 zf = unpack_bf16x2(zw[j]);
+              } else {
                 f[g * 8 + 2 * j] += zf.x;
                 f[g * 8 + 2 * j + 1] += zf.y;
               }
@@ -482,42 +526,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] *= sc;
         }
-        // stage this thread's 32 bf16 (64 B) into the warp's [32 rows x 128 B] buffer (16-byte chunks
-        // XOR-swizzled by row); every second chunk the warp writes 128-byte row segments to global
-        // (or peer) memory: 8 lanes per row, 4 rows per store instruction
-        {
-          uint8_t* stg = stg_warp + lane * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(stg + (((half + g) ^ (lane & 7)) << 4)) =
-                make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
-                           pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
-        }
-        if ((c & 1) == 1 || c == BN / 32 - 1) {
+        stage_own();
+        if (args.flags & EPI_SCATTER) {
           __syncwarp();
-          const int colbase = n0 + (c & ~1) * 32;                 // first column of the staged 64-column span
-          const int span = max(0, min((c & 1) ? 64 : 32, args.N - colbase));
-          __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_base);
-          const int ch = lane & 7;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3);
-            if (rr < rows_ok && ch * 8 < span) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 128 + ((ch ^ (rr & 7)) << 4));
-              if (args.flags & EPI_SCATTER) {
-                const int gr = warp_row0 + rr;
-                const int ret = args.row_ret[gr];
-                if (ret >= 0) {
-                  const int src = (gr - tc.chunk * chunk_rows) / args.scatter_rows_per_src;
-                  st_global_v4(reinterpret_cast<__nv_bfloat16*>(args.out_peer[src]) +
-                                   static_cast<size_t>(ret) * args.ldc + colbase + ch * 8, val);
-                }
-              } else {
-                st_global_v4(ob + static_cast<size_t>(warp_out_row0 + rr) * args.ldc + colbase + ch * 8, val);
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + co_r;
+            if (rr < rows_ok && co_ch * 8 < ncols) {
+              const int gr = warp_row0 + rr;
+              const int ret = args.row_ret[gr];
+              if (ret >= 0) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg_warp + rr * 64 + ((co_ch ^ ((rr >> 1) & 3)) << 4));
+                const int src = (gr - tc.chunk * chunk_rows) / args.scatter_rows_per_src;
+                st_global_v4(reinterpret_cast<__nv_bfloat16*>(args.out_peer[src]) +
+                                 static_cast<size_t>(ret) * args.ldc + col0 + co_ch * 8, val);
               }
             }
           }
           __syncwarp();
+        } else {
+          store_block(reinterpret_cast<__nv_bfloat16*>(out_base), warp_out_row0, args.ldc);
         }
       }
       // accumulator drained -> hand the TMEM stage back to the MMA warp
@@ -525,8 +553,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr && !(args.flags & EPI_SCATTER)) {
-        // all four epilogue warps have stored their rows of this tile -> publish to the owner
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // all eight epilogue warps have stored their part of this tile -> publish to the owner
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 4 && lane == 0) {
           fence_acq_rel_sys();
           red_add_release_sys(args.arrive_ctr[tc.chunk], 1u);

@@ -25,6 +25,7 @@ typedef struct PgGemmDesc {
   void* aux;  // bf16 [M, ldc]
   int flags;  // EpiFlags
   int block_n;   // 0 = auto
+  int k_splits;  // 0 = auto (fp32 outputs only), 1 = never split, >1 = forced
   int max_ctas;  // 0 = all SMs
   int num_chunks, chunk_rows, first_chunk;
   const uint32_t* chunk_flags;

@@ -298,6 +298,11 @@ PG_DEVICE void st_global_na_v4(void* p, uint4 v) {
                : "memory");
 }
 
+PG_DEVICE void red_add_v4_f32(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 PG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

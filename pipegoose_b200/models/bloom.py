@@ -122,11 +122,11 @@ class BloomBlock(nn.Module):
         """``x``: ``[tokens_local, hidden]`` (token-sharded when ``self.tp`` is set)."""
         attn = self.self_attention
         tp = self.tp
-        qkv = PF.layernorm_linear(x, self.input_layernorm.weight, self.input_layernorm.bias,
-                                  attn.query_key_value.weight, attn.query_key_value.bias, self.eps, tp)
         n_head_local = attn.query_key_value.weight.shape[0] // (3 * attn.head_dim)
-        ctx = alibi_attention(qkv, attn.alibi_slopes_local(n_head_local), batch, seq, n_head_local, attn.head_dim)
-        x = PF.linear_residual(ctx, attn.dense.weight, attn.dense.bias, x, tp)
+        x = PF.attention_sublayer(x, self.input_layernorm.weight, self.input_layernorm.bias,
+                                  attn.query_key_value.weight, attn.query_key_value.bias,
+                                  attn.dense.weight, attn.dense.bias, attn.alibi_slopes_local(n_head_local),
+                                  self.eps, batch, seq, n_head_local, attn.head_dim, tp)
         mlp = self.mlp
         if isinstance(mlp, BloomMLP):
             x = PF.layernorm_mlp(x, self.post_attention_layernorm.weight, self.post_attention_layernorm.bias,

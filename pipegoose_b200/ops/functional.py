@@ -79,6 +79,55 @@ def _ln_bwd(dy, x, gamma, beta, mean, rstd, dx_extra=None):
     return K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra)
 
 
+def _ln_linear_fwd(x, gamma, beta, weight, bias, eps, tp):
+    """LN kernel, then (all-gather ->) GEMM with the bias in the epilogue; returns (y, mean, rstd, ln_full)."""
+    stage = tp.ag_input_buffer(x.shape[0], x.shape[1]) if (tp is not None and tp.fused) else None
+    ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
+    if tp is not None and tp.fused:
+        y, ln_full = tp.ag_gemm(ln, weight, bias)
+    else:
+        ln_full = tp.all_gather_rows(ln) if tp is not None else ln
+        y = K.gemm_nt(ln_full, weight, bias)
+    return y, mean, rstd, ln_full
+
+
+def _ln_linear_bwd(dy, x, gamma, beta, weight, bias, mean, rstd, ln_full, tp, dx_extra=None):
+    if tp is not None and tp.fused:
+        dln = tp.gemm_rs_nn(dy, weight)
+    else:
+        dln_full = K.gemm_nn(dy, weight)
+        dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
+    dw = _wgrad(dy, ln_full, weight)
+    db = _bgrad(dy, bias)
+    dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dx_extra)
+    return dx, dgamma, dbeta, dw, db
+
+
+def _linear_residual_fwd(a, weight, bias, residual, tp):
+    if tp is None:
+        return K.gemm_nt(a, weight, bias, residual)
+    if tp.fused:
+        return tp.gemm_rs(a, weight, bias, residual)
+    y = tp.reduce_scatter_rows(K.gemm_nt(a, weight))
+    return y + bias + residual if bias is not None else y + residual
+
+
+def _linear_residual_bwd(dy, a, weight, bias, tp):
+    if tp is None:
+        dy_full = dy
+        da = K.gemm_nn(dy_full, weight)
+    elif tp.fused:
+        da, dy_full = tp.ag_gemm_nn(dy, weight)
+    else:
+        dy_full = tp.all_gather_rows(dy)
+        da = K.gemm_nn(dy_full, weight)
+    dw = _wgrad(dy_full, a, weight)
+    # the bias is replicated across TP ranks: each rank sums its own token shard and the
+    # gradient reducer adds the TP group's partial sums (see DataParallel / grad buffer).
+    db = _bgrad(dy, bias)
+    return da, dw, db
+
+
 class LayerNormLinear(torch.autograd.Function):
     """``y = Linear(LayerNorm(x))`` — LN kernel, then (all-gather ->) GEMM with the bias in the epilogue.
 
@@ -88,13 +137,7 @@ class LayerNormLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, weight, bias, eps, tp):
-        stage = tp.ag_input_buffer(x.shape[0], x.shape[1]) if (tp is not None and tp.fused) else None
-        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
-        if tp is not None and tp.fused:
-            y, ln_full = tp.ag_gemm(ln, weight, bias)
-        else:
-            ln_full = tp.all_gather_rows(ln) if tp is not None else ln
-            y = K.gemm_nt(ln_full, weight, bias)
+        y, mean, rstd, ln_full = _ln_linear_fwd(x, gamma, beta, weight, bias, eps, tp)
         ctx.save_for_backward(x, gamma, beta, weight, bias, mean, rstd, ln_full)
         ctx.tp = tp
         return y
@@ -102,16 +145,8 @@ class LayerNormLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, gamma, beta, weight, bias, mean, rstd, ln_full = ctx.saved_tensors
-        tp = ctx.tp
-        dy = dy.contiguous()
-        if tp is not None and tp.fused:
-            dln = tp.gemm_rs_nn(dy, weight)
-        else:
-            dln_full = K.gemm_nn(dy, weight)
-            dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
-        dw = _wgrad(dy, ln_full, weight)
-        db = _bgrad(dy, bias)
-        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd)
+        dx, dgamma, dbeta, dw, db = _ln_linear_bwd(dy.contiguous(), x, gamma, beta, weight, bias, mean, rstd,
+                                                   ln_full, ctx.tp)
         return dx, dgamma, dbeta, dw, db, None, None
 
 
@@ -125,14 +160,7 @@ class LinearResidual(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, weight, bias, residual, tp):
-        if tp is None:
-            y = K.gemm_nt(a, weight, bias, residual)
-        elif tp.fused:
-            y = tp.gemm_rs(a, weight, bias, residual)
-        else:
-            part = K.gemm_nt(a, weight)
-            y = tp.reduce_scatter_rows(part)
-            y = y + bias + residual if bias is not None else y + residual
+        y = _linear_residual_fwd(a, weight, bias, residual, tp)
         ctx.save_for_backward(a, weight, bias)
         ctx.tp = tp
         return y
@@ -140,21 +168,44 @@ class LinearResidual(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         a, weight, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        da, dw, db = _linear_residual_bwd(dy, a, weight, bias, ctx.tp)
+        return da, dw, db, dy, None
+
+
+class AttentionSubLayer(torch.autograd.Function):
+    """``y = dense(flash_alibi_attention(qkv(LayerNorm(x)))) + x`` as ONE autograd node (native path):
+    LN kernel, (AG->)GEMM+bias, tcgen05 flash attention, GEMM(->RS)+bias+residual.  The residual-stream
+    gradient is added inside the LN backward kernel instead of by an autograd accumulation pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, wqkv, bqkv, wd, bd, slopes, eps, B, S, n_head, D, tp):
+        from pipegoose_b200.ops import native
+
+        qkv, mean, rstd, ln_full = _ln_linear_fwd(x, gamma, beta, wqkv, bqkv, eps, tp)
+        att = torch.empty(B * S, n_head * D, dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty(B, n_head, S, dtype=torch.float32, device=qkv.device)
+        native().attention_fwd(qkv, slopes, att, lse, B, S, n_head, D)
+        y = _linear_residual_fwd(att, wd, bd, x, tp)
+        ctx.save_for_backward(x, gamma, beta, wqkv, bqkv, wd, bd, slopes, mean, rstd, ln_full, qkv, att, lse)
+        ctx.tp = tp
+        ctx.dims = (B, S, n_head, D)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from pipegoose_b200.ops import native
+
+        x, gamma, beta, wqkv, bqkv, wd, bd, slopes, mean, rstd, ln_full, qkv, att, lse = ctx.saved_tensors
+        B, S, n_head, D = ctx.dims
         tp = ctx.tp
         dy = dy.contiguous()
-        if tp is None:
-            dy_full = dy
-            da = K.gemm_nn(dy_full, weight)
-        elif tp.fused:
-            da, dy_full = tp.ag_gemm_nn(dy, weight)
-        else:
-            dy_full = tp.all_gather_rows(dy)
-            da = K.gemm_nn(dy_full, weight)
-        dw = _wgrad(dy_full, a, weight)
-        # the bias is replicated across TP ranks: each rank sums its own token shard and the
-        # gradient reducer adds the TP group's partial sums (see DataParallel / grad buffer).
-        db = _bgrad(dy, bias)
-        return da, dw, db, dy, None
+        datt, dwd, dbd = _linear_residual_bwd(dy, att, wd, bd, tp)
+        dqkv = torch.empty_like(qkv)
+        native().attention_bwd(qkv, slopes, att, lse, datt, dqkv, B, S, n_head, D)
+        dx, dgamma, dbeta, dwqkv, dbqkv = _ln_linear_bwd(dqkv, x, gamma, beta, wqkv, bqkv, mean, rstd, ln_full, tp,
+                                                         dx_extra=dy)
+        return dx, dgamma, dbeta, dwqkv, dbqkv, dwd, dbd, None, None, None, None, None, None, None
 
 
 class LayerNormMLP(torch.autograd.Function):
@@ -359,6 +410,18 @@ class LMHeadCrossEntropy(torch.autograd.Function):
 
 def layernorm_linear(x, gamma, beta, weight, bias, eps=1e-5, tp=None):
     return LayerNormLinear.apply(x, gamma, beta, weight, bias, eps, tp)
+
+
+def attention_sublayer(x, gamma, beta, wqkv, bqkv, wd, bd, slopes, eps, B, S, n_head, D, tp=None):
+    """LN -> QKV -> causal ALiBi attention -> dense + residual (``x`` is the residual stream)."""
+    from pipegoose_b200.ops import use_native
+    from pipegoose_b200.ops.attention import _native_attention_available, alibi_attention
+
+    if use_native(x, wqkv) and _native_attention_available(D):
+        return AttentionSubLayer.apply(x, gamma, beta, wqkv, bqkv, wd, bd, slopes, eps, B, S, n_head, D, tp)
+    qkv = LayerNormLinear.apply(x, gamma, beta, wqkv, bqkv, eps, tp)
+    att = alibi_attention(qkv, slopes, B, S, n_head, D)
+    return LinearResidual.apply(att, wd, bd, x, tp)
 
 
 def linear_residual(a, weight, bias, residual, tp=None):

@@ -33,6 +33,8 @@ def run_case(M, N, K, a_mn, b_mn, bn, epi):
         ref = ref + bias.float() + res.float()
     elif epi == "f32acc":
         out = torch.randn(M, N, device=dev, dtype=torch.float32); ref = ref + out; flags = 16
+    elif epi == "f32over":
+        out = torch.full((M, N), 7.0, device=dev, dtype=torch.float32)
     elif epi == "dgelu":
         aux = torch.randn(M, N, device=dev, dtype=torch.bfloat16); flags = 32
         z = aux.float().requires_grad_(True); g = torch.autograd.grad(gelu(z).sum(), z)[0]; ref = ref * g
@@ -64,6 +66,11 @@ for epi in ["bias", "bias_gelu", "bias_res", "f32acc", "dgelu"]:
     all_ok &= run_case(2048, 1024, 512, False, False, 0, epi)
     all_ok &= run_case(640, 328, 136, False, False, 128, epi)
 all_ok &= run_case(1024, 4096, 8192, True, True, 0, "f32acc")
+# small outputs with a long K: the host picks a split-K (atomic fp32 partial sums), overwrite and accumulate
+for epi in ["f32acc", "f32over"]:
+    all_ok &= run_case(1024, 1024, 8192, True, True, 0, epi)
+    all_ok &= run_case(512, 768, 4096, True, True, 0, epi)
+    all_ok &= run_case(256, 264, 2048, True, True, 0, epi)
 results["all_ok"] = bool(all_ok)
 
 def bench(fn, iters=20):
@@ -78,6 +85,47 @@ def bench(fn, iters=20):
         ts.append(s.elapsed_time(e))
     ts.sort()
     return ts[len(ts) // 2], ts[0]
+
+# fused-epilogue GEMMs at the flagship (bloom-560m, 8192 tokens) shapes
+def epi_perf():
+    M, h = 8192, 1024
+    x = torch.randn(M, h, device=dev, dtype=torch.bfloat16)
+    x4 = torch.randn(M, 4 * h, device=dev, dtype=torch.bfloat16)
+    w1 = torch.randn(4 * h, h, device=dev, dtype=torch.bfloat16)
+    w2 = torch.randn(h, 4 * h, device=dev, dtype=torch.bfloat16)
+    wd = torch.randn(h, h, device=dev, dtype=torch.bfloat16)
+    b4 = torch.randn(4 * h, device=dev, dtype=torch.bfloat16)
+    b1 = torch.randn(h, device=dev, dtype=torch.bfloat16)
+    o1 = torch.empty(M, h, device=dev, dtype=torch.bfloat16)
+    o4 = torch.empty(M, 4 * h, device=dev, dtype=torch.bfloat16)
+    z4 = torch.randn(M, 4 * h, device=dev, dtype=torch.bfloat16)
+    g1 = torch.zeros(h, h, device=dev, dtype=torch.float32)
+    g4 = torch.zeros(4 * h, h, device=dev, dtype=torch.float32)
+    cases = {
+        "fc1_bias_gelu_aux": (lambda: _C.gemm(x, w1, o4, False, False, b4, None, z4, 2), 2.0 * M * h * 4 * h),
+        "fc1_bias_only": (lambda: _C.gemm(x, w1, o4, False, False, b4, None, None, 0), 2.0 * M * h * 4 * h),
+        "fc2_bias_residual": (lambda: _C.gemm(x4, w2, o1, False, False, b1, x, None, 0), 2.0 * M * h * 4 * h),
+        "dense_bias_residual": (lambda: _C.gemm(x, wd, o1, False, False, b1, x, None, 0), 2.0 * M * h * h),
+        "fc2_dgrad_dgelu": (lambda: _C.gemm(x, w2, o4, False, True, None, None, z4, 32), 2.0 * M * h * 4 * h),
+        "fc1_dgrad": (lambda: _C.gemm(x4, w1, o1, False, True), 2.0 * M * h * 4 * h),
+        "dense_dgrad": (lambda: _C.gemm(x, wd, o1, False, True), 2.0 * M * h * h),
+        "dense_wgrad_f32acc": (lambda: _C.gemm(x, x, g1, True, True, None, None, None, 16), 2.0 * M * h * h),
+        "dense_wgrad_f32over": (lambda: _C.gemm(x, x, g1, True, True, None, None, None, 0), 2.0 * M * h * h),
+        "fc1_wgrad_f32acc": (lambda: _C.gemm(x4, x, g4, True, True, None, None, None, 16), 2.0 * M * h * 4 * h),
+    }
+    out = {}
+    for name, (fn, fl) in cases.items():
+        med, best = bench(fn)
+        out[name] = dict(ms=med, tflops=fl / med / 1e9)
+        print(name, f"{med*1e3:.1f} us  {fl/med/1e9:.0f} TFLOP/s", flush=True)
+    return out
+
+results["epi_perf"] = epi_perf()
+if stage == "epi":
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(results, open("gpurun_out/gemm_check.json", "w"), indent=1)
+    print("ALL_OK", all_ok)
+    sys.exit(0)
 
 shapes = [(8192, 8192, 8192), (8192, 3072, 1024), (8192, 1024, 1024), (8192, 4096, 1024), (8192, 1024, 4096),
           (4096, 1024, 1024), (16384, 12288, 4096), (8192, 250880 // 2, 1024)]
