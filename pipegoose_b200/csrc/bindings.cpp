@@ -94,6 +94,7 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
     }
   }
   if (ag.contains("k_splits")) d.k_splits = ag["k_splits"].cast<int>();
+  if (ag.contains("cta_pair")) d.cta_pair = ag["cta_pair"].cast<int>();
   if (ag.contains("n_comm")) {
     d.n_comm = ag["n_comm"].cast<int>();
     d.ag_dst = reinterpret_cast<void*>(ag["dst"].cast<int64_t>());

@@ -105,11 +105,12 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CTA2>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tal,
                       const GemmArgs& args, int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CTA2>;
+  constexpr int BM_T = CTA2 ? 2 * BM : BM;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -121,14 +122,28 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     attr_set = true;
   }
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
-  const int tiles = ((chunk_rows + BM - 1) / BM) * ((args.N + BN - 1) / BN) * args.num_chunks *
+  const int tiles = ((chunk_rows + BM_T - 1) / BM_T) * ((args.N + BN - 1) / BN) * args.num_chunks *
                     (args.k_splits > 1 ? args.k_splits : 1);
-  int gemm_ctas = max_ctas - args.n_comm;
-  if (gemm_ctas < 1) gemm_ctas = 1;
-  int grid = (tiles < gemm_ctas ? tiles : gemm_ctas) + args.n_comm;
-  if (grid < 1) grid = 1;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tal, args);
-  cudaError_t e = cudaGetLastError();
+  int units = (max_ctas - args.n_comm) / (CTA2 ? 2 : 1);  // CTAs or CTA pairs that run GEMM tiles
+  if (units < 1) units = 1;
+  if (tiles < units) units = tiles;
+  if (units < 1) units = 1;
+  const int grid = units * (CTA2 ? 2 : 1) + args.n_comm;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, args);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     fprintf(stderr, "pipegoose_b200: gemm launch failed: %s\n", cudaGetErrorString(e));
     return -1;
@@ -138,25 +153,45 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 // Tile width (and, for fp32-accumulating outputs, a K split) by a wave-quantisation cost model:
 // cost = waves * (k-blocks per work item * BN / efficiency(BN)) + one exposed epilogue.
-static int pick_bn(int M_rows, int N, int K, int chunks, int ctas, bool allow_split, int* k_splits) {
+// `cta2`: in -1 never / 0 auto / 1 always use CTA pairs (cta_group::2, 256-row tiles); out: the choice.
+// Measured on B200 (profiles/gemm_check_r1_v3_cta_pair.json): pairs win where the L2->SM operand feed is the
+// limit (long K, or many tiles per SM: +5..+16%), and lose a few percent on short problems (coarser tiles,
+// deeper prologue) and on the fp32 read-modify-write epilogue of the small wgrads.
+static int pick_bn(int M_rows, int N, int K, int chunks, int ctas, bool allow_split, bool b_mn, bool out_f32,
+                   int* k_splits, int* cta2) {
   const int cand[4] = {256, 192, 128, 64};
-  const float eff[4] = {1.0f, 0.93f, 0.82f, 0.55f};
+  const float eff1[4] = {1.0f, 0.93f, 0.82f, 0.55f};   // 1-CTA tiles 128 x BN
+  const float eff2[4] = {1.0f, 0.80f, 0.70f, 0.0f};    // CTA-pair tiles 256 x BN (relative to each other)
   const int num_kb = (K + BK - 1) / BK;
+  int mode = *cta2;
+  if (mode == 0) {
+    const long tiles1 = (long)((M_rows + BM - 1) / BM) * ((N + 255) / 256) * chunks;
+    const bool pair = out_f32 ? (tiles1 >= 6L * ctas) : (K >= 2048 || tiles1 >= 3L * ctas);
+    mode = (pair && M_rows >= 2 * BM) ? 1 : -1;
+  }
+  if (mode > 0 && (ctas < 2 || (chunks > 1 && (M_rows % (2 * BM)) != 0))) mode = -1;
+  const int pair = mode > 0 ? 1 : 0;
+  const int bm = pair ? 2 * BM : BM;
+  const int units = pair ? ctas / 2 : ctas;
   int best = 256;
   float best_cost = 1e30f;
   *k_splits = 1;
+  *cta2 = pair;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
+    const float eff = pair ? eff2[i] : eff1[i];
+    if (eff <= 0.f) continue;
+    if (pair && b_mn && (bn / 2) % 64 != 0) continue;  // MN-major B is staged in 64-column atoms
     if (bn > 64 && N <= bn / 2) continue;
-    const long tiles = (long)((M_rows + BM - 1) / BM) * ((N + bn - 1) / bn) * chunks;
+    const long tiles = (long)((M_rows + bm - 1) / bm) * ((N + bn - 1) / bn) * chunks;
     const int max_split = allow_split ? 8 : 1;
     for (int s = 1; s <= max_split; ++s) {
       const int per = (num_kb + s - 1) / s;
       if (s > 1 && (per < 16 || (long)(s - 1) * per >= num_kb)) break;
-      const long waves = (tiles * s + ctas - 1) / ctas;
+      const long waves = (tiles * s + units - 1) / units;
       // the epilogue of the last wave is exposed; atomics cost about twice a plain store
       const float epi = (s > 1 ? 16.0f : 8.0f) * (float)bn;
-      const float cost = (float)waves * (float)per * (float)bn / eff[i] + epi;
+      const float cost = (float)waves * (float)per * (float)bn / eff + epi;
       if (cost < best_cost * 0.97f) {
         best_cost = cost;
         best = bn;
@@ -223,10 +258,19 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   const bool allow_split = (args.flags & EPI_OUT_F32) && args.num_chunks == 1 && args.bias == nullptr &&
                            d->k_splits != 1 && (d->ldc % 4) == 0;
   int auto_splits = 1;
-  int bn = pick_bn(chunk_rows, args.N, args.K, args.num_chunks, max_ctas - args.n_comm, allow_split, &auto_splits);
+  int cta2 = d->cta_pair;
+  if (args.n_comm & 1) cta2 = -1;  // comm CTAs must fill whole clusters
+  int bn = pick_bn(chunk_rows, args.N, args.K, args.num_chunks, max_ctas - args.n_comm, allow_split, d->b_mn != 0,
+                   (args.flags & EPI_OUT_F32) != 0, &auto_splits, &cta2);
   if (d->block_n > 0) {
     bn = d->block_n;
     auto_splits = 1;
+    cta2 = d->cta_pair > 0 ? 1 : 0;
+    if (cta2 && (bn == 64 || (d->b_mn && (bn / 2) % 64 != 0) || (args.n_comm & 1) ||
+                 (args.num_chunks > 1 && args.chunk_rows % (2 * BM) != 0))) {
+      fprintf(stderr, "pipegoose_b200: block_n %d cannot run as a CTA pair here\n", bn);
+      return -1;
+    }
   }
   args.k_splits = (allow_split && d->k_splits > 1) ? d->k_splits : auto_splits;
   {
@@ -256,7 +300,7 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   }
   const uint64_t b_groups = d->b_chunk_rows > 0 ? (uint64_t)args.num_chunks : 1;  // stacked expert weights
   if (!d->b_mn) {
-    if (cached_tmap(&tb, d->B, d->N * b_groups, d->K, d->ldb, bn) != 0) return -1;
+    if (cached_tmap(&tb, d->B, d->N * b_groups, d->K, d->ldb, cta2 ? bn / 2 : bn) != 0) return -1;
   } else {
     if (cached_tmap(&tb, d->B, d->K * b_groups, d->N, d->ldb, BK) != 0) return -1;
   }
@@ -268,13 +312,25 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
     args.a_local_chunk = d->my_rank;
   }
 
-#define PG_DISPATCH_BN(AMN, BMN)                                                          \
-  switch (bn) {                                                                           \
-    case 256: return launch_cfg<256, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
-    case 192: return launch_cfg<192, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
-    case 128: return launch_cfg<128, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);           \
-    case 64: return launch_cfg<64, AMN, BMN>(ta, tb, tal, args, max_ctas, stream);             \
-    default: fprintf(stderr, "pipegoose_b200: bad block_n %d\n", bn); return -1;          \
+#define PG_DISPATCH_BN(AMN, BMN)                                                               \
+  if (cta2) {                                                                                  \
+    switch (bn) {                                                                              \
+      case 256: return launch_cfg<256, AMN, BMN, true>(ta, tb, tal, args, max_ctas, stream);    \
+      case 192:                                                                                \
+        if constexpr (!BMN) return launch_cfg<192, AMN, BMN, true>(ta, tb, tal, args, max_ctas, stream); \
+        break;                                                                                 \
+      case 128: return launch_cfg<128, AMN, BMN, true>(ta, tb, tal, args, max_ctas, stream);    \
+      default: break;                                                                          \
+    }                                                                                          \
+    fprintf(stderr, "pipegoose_b200: bad CTA-pair block_n %d\n", bn);                          \
+    return -1;                                                                                 \
+  }                                                                                            \
+  switch (bn) {                                                                                \
+    case 256: return launch_cfg<256, AMN, BMN, false>(ta, tb, tal, args, max_ctas, stream);     \
+    case 192: return launch_cfg<192, AMN, BMN, false>(ta, tb, tal, args, max_ctas, stream);     \
+    case 128: return launch_cfg<128, AMN, BMN, false>(ta, tb, tal, args, max_ctas, stream);     \
+    case 64: return launch_cfg<64, AMN, BMN, false>(ta, tb, tal, args, max_ctas, stream);       \
+    default: fprintf(stderr, "pipegoose_b200: bad block_n %d\n", bn); return -1;               \
   }
   if (!d->a_mn && !d->b_mn) {
     PG_DISPATCH_BN(false, false)

@@ -82,12 +82,17 @@ constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 
-template <int BN>
+// CTA2: the two CTAs of a 2-CTA cluster (one TPC) compute ONE 256 x BN tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader CTA's MMA thread
+// issues the pair-wide instruction, each CTA's TMEM receives its 128 accumulator rows.  Per SM that is
+// 32 KB of operands per 128x256x64 MACs instead of 48 KB: the L2->SM feed is what bounds the 1-CTA kernel.
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;  // rows (N) of B this CTA stages
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
+  static constexpr int kMaxStages = (208 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kEpiStageBytes = 8 * 32 * 64;  // 8 epilogue warps x [32 rows x 64 B]
@@ -135,12 +140,13 @@ PG_DEVICE TileCoord map_tile(int t, int m_blks_per_chunk, int n_blks, int num_ch
   return c;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_a_local, const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  constexpr int BM_T = CTA2 ? 2 * BM : BM;  // rows of one work tile (CTA pair: 256)
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -159,7 +165,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int lane = threadIdx.x & 31;
 
   const int chunk_rows = (args.num_chunks > 1) ? args.chunk_rows : args.M;
-  const int m_blks_per_chunk = (chunk_rows + BM - 1) / BM;
+  const int m_blks_per_chunk = (chunk_rows + BM_T - 1) / BM_T;
+  // work distribution unit: a CTA (1-CTA kernel) or a CTA pair; both CTAs of a pair walk the same tiles
+  uint32_t cta_rank = 0;
+  if constexpr (CTA2) cta_rank = cluster_ctarank();
+  const int unit0 = CTA2 ? (static_cast<int>(blockIdx.x) - args.n_comm) / 2 : static_cast<int>(blockIdx.x) - args.n_comm;
+  const int unit_stride = CTA2 ? (static_cast<int>(gridDim.x) - args.n_comm) / 2 : static_cast<int>(gridDim.x) - args.n_comm;
+  const int row_in_tile0 = static_cast<int>(cta_rank) * BM;  // this CTA's first row inside the work tile
   const int n_blks = (args.N + BN - 1) / BN;
   const int num_tiles = m_blks_per_chunk * n_blks * args.num_chunks;
   const int num_kb = (args.K + BK - 1) / BK;
@@ -244,16 +256,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], CTA2 ? 16 : 8);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_cta2(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish_cta2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int seen_chunk = -1;
-    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm) {
+    for (int t = unit0; t < num_work; t += unit_stride) {
       const TileCoord tc = map_tile(t % num_tiles, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
       const int kb_begin = (t / num_tiles) * kb_per_split;
       const int kb_end = min(num_kb, kb_begin + kb_per_split);
@@ -275,8 +293,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         __syncwarp();
         seen_chunk = tc.chunk;
       }
-      int m0 = tc.m_blk * BM;
-      const int n0 = tc.n_blk * BN;
+      int m0 = tc.m_blk * BM_T + row_in_tile0;
+      const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;  // this CTA's part of the B tile
       // all-gather -> GEMM: the local shard is read in place from its (peer-visible) staging buffer
       const CUtensorMap* map_a = &tma_a;
       if (args.a_local_chunk >= 0 && tc.chunk == args.a_local_chunk) {
@@ -286,22 +304,41 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, map_a, &full_bar[stage], kb * BK, m0);
-          } else {
+          if constexpr (CTA2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (the only one the MMA thread waits on)
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d_cta2(sa, map_a, bar, kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tma_load_2d(sa + i * (BK * 128), map_a, &full_bar[stage], m0 + i * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0 + tc.chunk * args.b_chunk_rows);
-          } else {
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d_cta2(sa + i * (BK * 128), map_a, bar, m0 + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_cta2(sb, &tma_b, bar, kb * BK, n0 + tc.chunk * args.b_chunk_rows);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK + tc.chunk * args.b_chunk_rows);
+              for (int i = 0; i < Cfg::kBRows / 64; ++i)
+                tma_load_2d_cta2(sb + i * (BK * 128), &tma_b, bar, n0 + i * 64, kb * BK + tc.chunk * args.b_chunk_rows);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, map_a, &full_bar[stage], kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d(sa + i * (BK * 128), map_a, &full_bar[stage], m0 + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n0 + tc.chunk * args.b_chunk_rows);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sb + i * (BK * 128), &tma_b, &full_bar[stage], n0 + i * 64, kb * BK + tc.chunk * args.b_chunk_rows);
+            }
           }
         }
         __syncwarp();
@@ -311,13 +348,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ============================ MMA issuer (the pair's leader CTA only) ============================
+    constexpr uint32_t idesc = make_idesc_bf16(BM_T, BN, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm, ++it) {
+    for (int t = unit0; t < num_work; t += unit_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -339,10 +376,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                      : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
-            umma_f16(tmem_d, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            if constexpr (CTA2) {
+              umma_f16_cta2(tmem_d, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            } else {
+              umma_f16(tmem_d, da, db, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
+          if constexpr (CTA2) {
+            umma_commit_cta2(&empty_bar[stage], 3);  // frees the stage in BOTH CTAs
+            if (kb == kb_end - 1) umma_commit_cta2(&tmem_full[acc], 3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -380,11 +426,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int co_r = lane >> 2;                       // coalesced pattern: row inside a group of 8
     const int co_ch = lane & 3;                       // 16-byte chunk of the 64-byte segment
     int it = 0;
-    for (int t = blockIdx.x - args.n_comm; t < num_work; t += gridDim.x - args.n_comm, ++it) {
+    for (int t = unit0; t < num_work; t += unit_stride, ++it) {
       const TileCoord tc = map_tile(t % num_tiles, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row = tc.m_blk * BM + q * 32 + lane;
+      const int row = tc.m_blk * BM_T + row_in_tile0 + q * 32 + lane;
       const int n0 = tc.n_blk * BN;
       // destination row pointer (possibly on a peer GPU)
       uint8_t* out_base = reinterpret_cast<uint8_t*>(args.out);
@@ -398,7 +444,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
       const bool row_ok = row < row_limit && row < args.M;
-      const int warp_row0 = tc.m_blk * BM + q * 32;          // first row handled by this warp
+      const int warp_row0 = tc.m_blk * BM_T + row_in_tile0 + q * 32;  // first row handled by this warp
       const int warp_out_row0 = out_row - lane;               // its destination row index
       const int rows_ok = max(0, min(32, min(row_limit, args.M) - warp_row0));
       uint4 pre[4];
@@ -551,7 +597,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // accumulator drained -> hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) {
+          mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // the leader's MMA thread waits on it
+        } else {
+          mbar_arrive(&tmem_empty[acc]);
+        }
+      }
       if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr && !(args.flags & EPI_SCATTER)) {
         // all eight epilogue warps have stored their part of this tile -> publish to the owner
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -566,9 +618,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync();  // no CTA of the pair leaves (or frees TMEM) while the other still signals it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTA2) {
+      tmem_dealloc_cta2(tmem_base, Cfg::kTmemCols);
+    } else {
+      tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
   }
 }
 
