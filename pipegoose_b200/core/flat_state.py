@@ -39,6 +39,10 @@ class FlatModelState:
                  buffer_factory=None):
         self.params: List[nn.Parameter] = unique_parameters(list(params))
         assert len(self.params) > 0
+        # parameters whose gradients are partial sums over the tensor-parallel group (sequence-parallel
+        # LayerNorms / row-parallel biases) come first, contiguously: ONE all-reduce of flat_grad[:n] sums them
+        self.params.sort(key=lambda p: 0 if getattr(p, "tp_partial_grad", False) else 1)  # stable
+        self.tp_partial_numel = 0
         p0 = self.params[0]
         self.device, self.dtype = p0.device, p0.dtype
         assert all(p.device == self.device and p.dtype == self.dtype for p in self.params), \
@@ -48,6 +52,8 @@ class FlatModelState:
         for p in self.params:
             self.offsets[id(p)] = (off, p.numel())
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            if getattr(p, "tp_partial_grad", False):
+                self.tp_partial_numel = off
         mult = max(pad_to_multiple_of, 1) * _ALIGN
         self.numel = (off + mult - 1) // mult * mult
         if buffer_factory is not None:

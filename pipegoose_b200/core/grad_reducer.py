@@ -27,7 +27,7 @@ from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
 
 class _Bucket:
-    __slots__ = ("index", "start", "end", "params", "pending", "launched", "work")
+    __slots__ = ("index", "start", "end", "params", "pending", "launched", "work", "deferred")
 
     def __init__(self, index, start, end):
         self.index, self.start, self.end = index, start, end
@@ -35,6 +35,7 @@ class _Bucket:
         self.pending = 0
         self.launched = False
         self.work = None
+        self.deferred = False  # holds TP-partial gradients: reduced over DATA only after the TENSOR all-reduce
 
 
 class GradReducer:
@@ -76,6 +77,8 @@ class GradReducer:
             self._bucket_of[id(p)] = owners
             for b in owners:
                 b.params.append(p)
+                if getattr(p, "tp_partial_grad", False) and self.ctx.get_world_size(ParallelMode.TENSOR) > 1:
+                    b.deferred = True
             p._pg_grad_ready = self._on_param_ready
             if not hasattr(p, "_pg_autograd_hook"):
                 p._pg_autograd_hook = p.register_post_accumulate_grad_hook(self._on_autograd_grad)
@@ -138,14 +141,14 @@ class GradReducer:
             return
         for b in self._bucket_of[id(p)]:
             b.pending -= 1
-            if b.pending == 0 and not b.launched:
+            if b.pending == 0 and not b.launched and not b.deferred:
                 self._launch(b)
 
     # ------------------------------------------------------------------ collectives
     def _group_for(self, b: _Bucket):
         return self.ctx.get_group(ParallelMode.DATA)
 
-    def _launch(self, b: _Bucket):
+    def _launch(self, b: _Bucket, tail: bool = False):
         b.launched = True
         for p in b.params:  # parameters that got no gradient this step read as zero
             if getattr(p, "_mg_fresh", False):
@@ -154,7 +157,9 @@ class GradReducer:
         view = self.flat.flat_grad[b.start:b.end]
         group = self._group_for(b)
         if self._fused is not None:
-            b.work = self._fused.reduce_bucket(view, self.mode)
+            if not tail:
+                self._fused.begin_overlap()
+            b.work = self._fused.reduce_bucket(view, self.mode, tail=tail)
             return
         backend = dist.get_backend(group)
         if backend == "nccl":
@@ -174,10 +179,12 @@ class GradReducer:
         if self.flat is None:
             return
         self._reduce_tp_partial()
+        if self._fused is not None:
+            self._fused.end_overlap()
         if self._sync and self.dp > 1:
             for b in reversed(self.buckets):
                 if not b.launched:
-                    self._launch(b)
+                    self._launch(b, tail=True)
             for b in self.buckets:
                 if b.work is not None:
                     b.work.wait()
@@ -189,24 +196,30 @@ class GradReducer:
 
     def _reduce_tp_partial(self):
         """Sequence-parallel layers compute gradients of TP-replicated parameters (LayerNorms,
-        row-parallel biases) from their token shard only: sum them over the TENSOR group."""
+        row-parallel biases) from their token shard only: sum them over the TENSOR group.  They sit at
+        the head of the flat gradient buffer (FlatModelState sorts them first), so this is ONE in-place
+        all-reduce; their buckets are held back (``deferred``) until it is enqueued."""
         tp = self.ctx.get_world_size(ParallelMode.TENSOR)
         if tp == 1:
             return
         ps = [p for p in self.flat.params if getattr(p, "tp_partial_grad", False)]
         if not ps:
             return
+        fresh = [p.main_grad for p in ps if getattr(p, "_mg_fresh", False)]
+        if fresh:
+            torch._foreach_zero_(fresh)
         for p in ps:
-            if getattr(p, "_mg_fresh", False):
-                p.main_grad.zero_()
-                p._mg_fresh = False
+            p._mg_fresh = False
+        n = getattr(self.flat, "tp_partial_numel", 0)
+        group = self.ctx.get_group(ParallelMode.TENSOR)
+        if all(sum(self.flat.param_range(p)) <= n for p in ps):
+            dist.all_reduce(self.flat.flat_grad[:n], group=group)
+            return
+        # parameters tagged after the flat state was laid out: gather / scatter fallback
         flat = torch.cat([p.main_grad.reshape(-1) for p in ps])
-        dist.all_reduce(flat, group=self.ctx.get_group(ParallelMode.TENSOR))
-        off = 0
-        for p in ps:
-            n = p.numel()
-            p.main_grad.copy_(flat[off:off + n].view_as(p.main_grad))
-            off += n
+        dist.all_reduce(flat, group=group)
+        torch._foreach_copy_([p.main_grad for p in ps],
+                             [f.view_as(p.main_grad) for f, p in zip(flat.split([p.numel() for p in ps]), ps)])
 
     @contextmanager
     def no_sync(self):

@@ -294,12 +294,12 @@ void rs_reduce(int64_t staging_ptr, int64_t num_src, int64_t src_stride, int64_t
 }
 
 void allreduce_f32(std::vector<int64_t> peer_bufs, int64_t rank, int64_t offset, int64_t n, double scale, bool rs_only,
-                   std::vector<int64_t> peer_flags, int64_t epoch) {
+                   std::vector<int64_t> peer_flags, int64_t epoch, int64_t blocks) {
   float* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
   const int world = (int)peer_bufs.size();
   TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
   for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<float*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
-  TORCH_CHECK(pg_allreduce_f32(bufs, world, (int)rank, offset, n, (float)scale, rs_only, flags, (uint32_t)epoch, cur_stream()) == 0, "allreduce_f32 failed");
+  TORCH_CHECK(pg_allreduce_f32(bufs, world, (int)rank, offset, n, (float)scale, rs_only, flags, (uint32_t)epoch, (int)blocks, cur_stream()) == 0, "allreduce_f32 failed");
 }
 
 void allgather_bf16(std::vector<int64_t> peer_bufs, int64_t rank, int64_t bucket_elems, int64_t total_elems,
@@ -347,7 +347,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_free", &symm_free);
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("rs_reduce", &rs_reduce);
-  m.def("allreduce_f32", &allreduce_f32);
+  m.def("allreduce_f32", &allreduce_f32, py::arg("peer_bufs"), py::arg("rank"), py::arg("offset"), py::arg("n"),
+        py::arg("scale"), py::arg("rs_only"), py::arg("peer_flags"), py::arg("epoch"), py::arg("blocks") = 0);
+  m.def("set_gemm_cta_cap", [](int64_t n) { pg_set_gemm_cta_cap((int)n); });
   m.def("allgather_bf16", &allgather_bf16);
   m.def("barrier_peers", &barrier_peers);
 }

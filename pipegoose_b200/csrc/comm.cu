@@ -247,7 +247,7 @@ extern "C" int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride
 // grid_ctr: two uint32 in LOCAL memory right after the flag area: peer_flags[rank] + 2*PG_MAX_PEERS
 extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems,
                                 int64_t n, float scale, int reduce_scatter_only,
-                                uint32_t* const* peer_flags, uint32_t epoch, cudaStream_t s) {
+                                uint32_t* const* peer_flags, uint32_t epoch, int blocks, cudaStream_t s) {
   if (n == 0) return 0;
   if (n % (world * 4) != 0) return -1;
   PeerPtrs p;
@@ -256,8 +256,9 @@ extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, in
     p.buf[i] = peer_bufs[i];
     p.flag[i] = peer_flags[i];
   }
-  // few CTAs: the kernel is NVLink-bound and must leave the SMs to the backward GEMMs it overlaps
-  const int blocks = 24;
+  // overlapped with backward: a handful of CTAs on the SMs the persistent GEMMs leave free (pg_set_gemm_cta_cap);
+  // after backward (nothing else runs): enough CTAs to keep ~3 MB in flight over NVLink
+  if (blocks <= 0) blocks = 24;
   allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, world, rank, offset_elems, n, scale,
                                               reduce_scatter_only, epoch,
                                               peer_flags[rank] + 2 * PG_MAX_PEERS);

@@ -206,6 +206,9 @@ static int pick_bn(int M_rows, int N, int K, int chunks, int ctas, bool allow_sp
 
 using namespace pg;
 
+static int g_cta_cap = 0;
+extern "C" void pg_set_gemm_cta_cap(int ctas) { g_cta_cap = ctas > 0 ? ctas : 0; }
+
 extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   if (d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
   GemmArgs args;
@@ -249,6 +252,7 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
     return -1;
   }
   int max_ctas = d->max_ctas > 0 ? d->max_ctas : num_sms();
+  if (d->max_ctas <= 0 && g_cta_cap > 0 && g_cta_cap < max_ctas) max_ctas = g_cta_cap;
   const int chunk_rows = args.num_chunks > 1 ? args.chunk_rows : args.M;
   if ((args.flags & EPI_DGELU) && (args.flags & EPI_RESIDUAL)) {
     fprintf(stderr, "pipegoose_b200: EPI_DGELU and EPI_RESIDUAL are mutually exclusive\n");

@@ -75,7 +75,7 @@ int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride_elems, con
 // flat fp32 gradient bucket: in-place all-reduce / reduce-scatter average over NVLink peers
 int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n,
                      float scale, int reduce_scatter_only, uint32_t* const* peer_flags, uint32_t epoch,
-                     cudaStream_t s);
+                     int blocks, cudaStream_t s);
 int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n_per_rank,
                       int64_t bucket_elems, int64_t total_elems, uint32_t* const* peer_flags, uint32_t epoch,
                       cudaStream_t s);
@@ -87,6 +87,8 @@ int pg_symm_close(void* ptr);
 int pg_symm_free(void* ptr);
 
 int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream);
+// persistent GEMM grids use at most `ctas` CTAs (0 = all SMs): leaves SMs to overlapped communication kernels
+void pg_set_gemm_cta_cap(int ctas);
 
 // ---- elementwise.cu
 int pg_layernorm_fwd(const void* x, const int64_t* ids, int vocab_start, int vocab_end,

@@ -30,18 +30,27 @@ import os
 N_COMM_CTAS = int(os.environ.get("PIPEGOOSE_B200_NCOMM", "16"))
 
 
-def pick_block_n(rows: int, n: int, chunks: int, ctas: int) -> int:
-    """Mirror of ``pick_bn`` in csrc/gemm_sm100.cu (both sides of a reduce-scatter must agree on the tiling)."""
+def pick_tiling(rows: int, n: int, k: int, chunks: int, ctas: int, b_mn: bool):
+    """``(block_n, cta_pair)`` for a GEMM -> reduce-scatter: mirror of ``pick_bn`` in csrc/gemm_sm100.cu (the
+    arrival counters of a reduce-scatter are counted in tiles, so both sides must agree on the tiling).
+    CTA pairs (tcgen05 ``cta_group::2``, 256-row tiles) where the operand feed is the limit: long K or many tiles."""
+    tiles1 = ((rows + _BM - 1) // _BM) * ((n + 255) // 256) * chunks
+    pair = rows % (2 * _BM) == 0 and ctas >= 2 and (k >= 2048 or tiles1 >= 3 * ctas)
+    bm = 2 * _BM if pair else _BM
+    units = ctas // 2 if pair else ctas
+    cands = ((256, 1.0), (192, 0.80), (128, 0.70)) if pair else ((256, 1.0), (192, 0.93), (128, 0.82), (64, 0.55))
     best, best_cost = 256, float("inf")
-    for bn, eff in ((256, 1.0), (192, 0.93), (128, 0.82), (64, 0.55)):
+    for bn, eff in cands:
+        if pair and b_mn and (bn // 2) % 64 != 0:
+            continue
         if bn > 64 and n <= bn // 2:
             continue
-        tiles = ((rows + _BM - 1) // _BM) * ((n + bn - 1) // bn) * chunks
-        waves = (tiles + ctas - 1) // ctas
+        tiles = ((rows + bm - 1) // bm) * ((n + bn - 1) // bn) * chunks
+        waves = (tiles + units - 1) // units
         cost = waves * bn / eff
-        if cost < best_cost:
+        if cost < best_cost * 0.97:
             best, best_cost = bn, cost
-    return best
+    return best, pair
 
 
 class FusedTPEngine:
@@ -161,14 +170,16 @@ class FusedTPEngine:
         ws = self.ws
         self.rs_calls += 1
         slot = self.rs_calls & 1
-        bn = pick_block_n(m_local, n, T, self.num_sms)
+        k = a.shape[1]
+        bn, pair = pick_tiling(m_local, n, k, T, self.num_sms, b_mn)
+        # every CTA bumps the owner's counter once per tile it stored (both CTAs of a pair do)
         tiles_per_chunk = ((m_local + _BM - 1) // _BM) * ((n + bn - 1) // bn)
         self.rs_expected += tiles_per_chunk
         src_stride = m_local * n  # elements between two sources' slots
         out_peer = [ws.data_ptr(p, self._rs_off(slot) + r * src_stride * 2) for p in range(T)]
         arrive = [ws.sig_ptr(p, S.SIG_RS_ARRIVE + r) for p in range(T)]
         native().gemm(a, weight, self._dummy_out(n, a.device), False, b_mn, None, None, None, 0, bn, 0,
-                      T, (r + 1) % T, 0, 0, out_peer, arrive)
+                      T, (r + 1) % T, 0, 0, out_peer, arrive, {"cta_pair": 1 if pair else -1})
         out = torch.empty(m_local, n, dtype=torch.bfloat16, device=a.device)
         native().rs_reduce(ws.data_ptr(r, self._rs_off(slot)), T, src_stride, ws.sig_ptr(r, S.SIG_RS_ARRIVE),
                            self.rs_expected, bias, residual, out)
@@ -238,7 +249,23 @@ class FusedDPEngine:
     def _flag_ptrs(self):
         return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
 
-    def reduce_bucket(self, view: torch.Tensor, mode: str):
+    OVERLAP_CTAS = 6   # CTAs of a gradient reduction that overlaps backward (the GEMMs leave them that many SMs)
+    TAIL_CTAS = 64     # after backward nothing else runs: NVLink-bound
+
+    def begin_overlap(self):
+        """Backward starts reducing buckets: persistent GEMM grids leave ``OVERLAP_CTAS`` SMs to the reducer
+        (a persistent GEMM whose CTAs cannot all be resident stalls behind the reducer's CTAs)."""
+        if not getattr(self, "_capped", False):
+            sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            native().set_gemm_cta_cap((sms - self.OVERLAP_CTAS) // 2 * 2)
+            self._capped = True
+
+    def end_overlap(self):
+        if getattr(self, "_capped", False):
+            native().set_gemm_cta_cap(0)
+            self._capped = False
+
+    def reduce_bucket(self, view: torch.Tensor, mode: str, tail: bool = False):
         offset = (view.data_ptr() - self._grad_base) // 4
         n = view.numel()
         ready = torch.cuda.Event()
@@ -247,7 +274,8 @@ class FusedDPEngine:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
             native().allreduce_f32([self.ws.data_ptr(p, self._grad_off) for p in range(self.world)], self.rank,
-                                   offset, n, 1.0 / self.world, mode == "reduce_scatter", self._flag_ptrs(), self.epoch)
+                                   offset, n, 1.0 / self.world, mode == "reduce_scatter", self._flag_ptrs(), self.epoch,
+                                   self.TAIL_CTAS if tail else self.OVERLAP_CTAS)
             done = torch.cuda.Event()
             done.record()
         return _StreamWork(done)
