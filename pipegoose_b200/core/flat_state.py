@@ -99,6 +99,8 @@ class FlatModelState:
         """Reset gradients.  ``lazy``: matrices are not memset — the first wgrad GEMM of the step
         overwrites instead of accumulating (``param._mg_fresh``); only the small 1-D parameters,
         whose gradients are built with atomics, are cleared here."""
+        if getattr(self, "hold_grads", False):
+            return  # produced by a pipeline schedule inside forward and not consumed by the optimizer yet
         if not lazy:
             self.flat_grad.zero_()
             for p in self.params:

@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
       const uint32_t tS = tmem_S0 + (j % SB) * 128 + lane_addr;
       const bool diag = (j == qb);
       const int kbase = j * ATT_BN - qpos;  // key_pos - query_pos for column 0
-      // pass 1: row max of x = s*scale_log2 + slope2*(kpos - qpos), masked
+      // x = s*scale_log2 + slope2*(kpos - qpos) = fma(s, scale_log2, fma(slope2, i, bias_c)): two FMAs per score,
+      // the column index is an immediate; the causal mask only costs instructions on the diagonal block
+      const float bias0 = slope2 * static_cast<float>(kbase);
+      // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -236,12 +239,18 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
         __syncwarp();
         tmem_ld_32x32(tS + c * 32, v);
         tmem_ld_wait();
+        const float bias_c = fmaf(slope2, static_cast<float>(c * 32), bias0);
+        if (diag) {
+          const int lim = -(kbase + c * 32);  // column i is visible iff i <= lim
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int rel = kbase + c * 32 + i;
-          float x = __uint_as_float(v[i]) * args.scale_log2 + slope2 * static_cast<float>(rel);
-          if (diag && rel > 0) x = -INFINITY;
-          mx = fmaxf(mx, x);
+          for (int i = 0; i < 32; ++i) {
+            const float x = fmaf(__uint_as_float(v[i]), args.scale_log2, fmaf(slope2, static_cast<float>(i), bias_c));
+            mx = fmaxf(mx, i > lim ? -INFINITY : x);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), args.scale_log2, fmaf(slope2, static_cast<float>(i), bias_c)));
         }
       }
       const float m_new = fmaxf(m_run, mx);
@@ -270,17 +279,33 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
         tmem_ld_32x32(tS + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        const float b2 = fmaf(slope2, static_cast<float>(c * 32), bias0) - m_new;  // exponent bias of this chunk
+        if (diag) {
+          const int lim = -(kbase + c * 32);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p[2];
+          for (int i = 0; i < 16; ++i) {
+            float p[2];
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int rel = kbase + c * 32 + 2 * i + h2;
-            float x = __uint_as_float(v[2 * i + h2]) * args.scale_log2 + slope2 * static_cast<float>(rel);
-            p[h2] = (diag && rel > 0) ? 0.f : fast_exp2(x - m_new);
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int col = 2 * i + h2;
+              const float e = fast_exp2(fmaf(__uint_as_float(v[col]), args.scale_log2, fmaf(slope2, static_cast<float>(col), b2)));
+              p[h2] = col > lim ? 0.f : e;
+            }
+            rs += p[0] + p[1];
+            pk[i] = pack_bf16x2(p[0], p[1]);
           }
-          rs += p[0] + p[1];
-          pk[i] = pack_bf16x2(p[0], p[1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p[2];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int col = 2 * i + h2;
+              p[h2] = fast_exp2(fmaf(__uint_as_float(v[col]), args.scale_log2, fmaf(slope2, static_cast<float>(col), b2)));
+            }
+            rs += p[0] + p[1];
+            pk[i] = pack_bf16x2(p[0], p[1]);
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -334,29 +359,37 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
 // -----------------------------------------------------------------------------------------------
 // backward
 // -----------------------------------------------------------------------------------------------
-// delta[b,h,i] = sum_d dO[i,d] * O[i,d]
+// delta[b,h,i] = sum_d dO[i,d] * O[i,d].  One warp per token row: every lane loads 16-byte chunks of the
+// [H*D] row (fully coalesced), the D/8 lanes that share a head reduce with shuffles.
 __global__ void __launch_bounds__(256) attention_delta_kernel(const __nv_bfloat16* __restrict__ dout,
                                                               const __nv_bfloat16* __restrict__ out,
                                                               float* __restrict__ delta, int B, int S, int H,
                                                               int D) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int total = B * S * H;
-  if (warp >= total) return;
-  const int row = warp / H, head = warp % H;
-  const __nv_bfloat16* a = dout + static_cast<size_t>(row) * H * D + head * D;
-  const __nv_bfloat16* b = out + static_cast<size_t>(row) * H * D + head * D;
-  float s = 0.f;
-  for (int c = lane; c < D / 8; c += 32) {
-    const uint4 x = ld_global_nc_v4(a + c * 8), y = ld_global_nc_v4(b + c * 8);
-    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B * S) return;
+  const int cph = D / 8;                 // 16-byte chunks (= lanes) per head: 8 or 16
+  const int nchunks = H * cph;
+  const __nv_bfloat16* a = dout + static_cast<size_t>(row) * H * D;
+  const __nv_bfloat16* b = out + static_cast<size_t>(row) * H * D;
+  const int bidx = row / S, spos = row % S;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    float s = 0.f;
+    if (c < nchunks) {
+      const uint4 x = ld_global_nc_v4(a + c * 8), y = ld_global_nc_v4(b + c * 8);
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(xw[j]), g = unpack_bf16x2(yw[j]);
-      s += f.x * g.x + f.y * g.y;
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(xw[j]), g = unpack_bf16x2(yw[j]);
+        s += f.x * g.x + f.y * g.y;
+      }
+    }
+    for (int o = cph >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (c < nchunks && (lane & (cph - 1)) == 0) {
+      const int head = c / cph;
+      delta[(static_cast<size_t>(bidx) * H + head) * S + spos] = s;
     }
   }
-  s = warp_sum(s);
-  if (lane == 0) delta[(static_cast<size_t>(row / S) * H + head) * S + (row % S)] = s;
 }
 
 template <int D>
@@ -378,8 +411,13 @@ struct AttBwdArgs {
   float scale, scale_log2;
 };
 
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = compute.  Compute warp w owns TMEM lanes
+// [32*(w%4), +32) (one query row per thread) and the 64-column half (w-2)/4 of every S/dP tile: two warps per
+// scheduler hide each other's TMEM/MUFU latency and halve the serial softmax/dS time between MMA batches.
+constexpr int kBwdThreads = 320;
+
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
     attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                          const AttBwdArgs args) {
   using Cfg = AttBwdCfg<D>;
@@ -420,10 +458,10 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(&q_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(pds_ready, 128);
+    mbar_init(s_free, 256);
+    mbar_init(pds_ready, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
+    mbar_init(dq_free, 256);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -541,6 +579,7 @@ __global__ void __launch_bounds__(192, 1)
   } else {
     // ===================== compute warps: one query row per thread =====================
     const int q4 = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 64 columns of S/dP (and which part of dQ/dK/dV) this warp handles
     const int r = q4 * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
     const float slope2 = args.slopes[head] * kLog2e;
@@ -553,26 +592,33 @@ __global__ void __launch_bounds__(192, 1)
       const float dlt = row_ok ? args.delta[stat_idx] : 0.f;
       const bool diag = (it == 0);
       const int kbase = jb * ATT_BN - qpos;
+      // p = exp2(s*scale_log2 + slope2*(kpos-qpos) - lse2) = exp2(fma(s, scale_log2, fma(slope2, i, bias_c)));
+      // dS = p * (dP - delta) * scale = p * fma(dP, scale, -delta*scale).  Rows past the sequence get p = 0
+      // through an infinite negative bias; the causal mask only costs instructions on the diagonal block.
+      const float bias0 = row_ok ? fmaf(slope2, static_cast<float>(kbase), -lse2) : -INFINITY;
+      const float nds = -dlt * args.scale;
       mbar_wait(s_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = half * 2; c < half * 2 + 2; ++c) {
         uint32_t vs[32], vd[32];
         __syncwarp();
         tmem_ld_32x32(tS + lane_addr + c * 32, vs);
         tmem_ld_32x32(tdP + lane_addr + c * 32, vd);
         tmem_ld_wait();
         uint32_t pp[16], ds[16];
+        const float bias_c = fmaf(slope2, static_cast<float>(c * 32), bias0);
+        const int lim = diag ? -(kbase + c * 32) : 64;  // column i of this chunk is visible iff i <= lim
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float p[2], g[2];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const int rel = kbase + c * 32 + 2 * i + h2;
-            const float x = __uint_as_float(vs[2 * i + h2]) * args.scale_log2 + slope2 * static_cast<float>(rel);
-            const bool masked = (diag && rel > 0) || !row_ok;
-            p[h2] = masked ? 0.f : fast_exp2(x - lse2);
-            g[h2] = p[h2] * (__uint_as_float(vd[2 * i + h2]) - dlt) * args.scale;
+            const int col = 2 * i + h2;
+            float e = fast_exp2(fmaf(__uint_as_float(vs[col]), args.scale_log2, fmaf(slope2, static_cast<float>(col), bias_c)));
+            if (diag) e = col > lim ? 0.f : e;
+            p[h2] = e;
+            g[h2] = e * fmaf(__uint_as_float(vd[col]), args.scale, nds);
           }
           pp[i] = pack_bf16x2(p[0], p[1]);
           ds[i] = pack_bf16x2(g[0], g[1]);
@@ -593,7 +639,7 @@ __global__ void __launch_bounds__(192, 1)
       tc_fence_after();
       float* dq_row = args.dq_acc + static_cast<size_t>(batch * args.S + qpos) * (args.H * D) + head * D;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(tdQ + lane_addr + c * 32, v);
@@ -618,7 +664,7 @@ __global__ void __launch_bounds__(192, 1)
       const uint32_t t = which == 0 ? tdK : tdV;
       __nv_bfloat16* dst = which == 0 ? dk_row : dv_row;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(t + lane_addr + c * 32, v);
@@ -736,7 +782,7 @@ static int launch_att_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const A
     set = true;
   }
   dim3 grid((a.S + ATT_BN - 1) / ATT_BN, a.H, a.B);
-  attention_bwd_kernel<D><<<grid, 192, Cfg::kSmemBytes, s>>>(tq, tdo, a);
+  attention_bwd_kernel<D><<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, a);
   PG_CHECK_LAUNCH("attention_bwd");
   return 0;
 }
@@ -752,8 +798,7 @@ extern "C" int pg_attention_bwd(const void* qkv, const float* slopes, const void
   if (att_tmap(&tdo, dout, rows, static_cast<uint64_t>(H) * D) != 0) return -1;
   if (cudaMemsetAsync(dq_acc, 0, rows * H * D * sizeof(float), s) != cudaSuccess) return -1;
   {
-    const int64_t warps = rows * H;
-    attention_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(
+    attention_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, S, H, D);
     PG_CHECK_LAUNCH("attention_delta");
   }

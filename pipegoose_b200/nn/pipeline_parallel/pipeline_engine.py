@@ -75,6 +75,22 @@ class _P2PLink:
         return tuple(meta[2:2 + meta[1]]), ID_TO_DTYPE[meta[0]]
 
 
+class _InstallGrads(torch.autograd.Function):
+    """Identity on the loss; backward adds the gradients the pipeline schedule already computed to ``.grad``."""
+
+    @staticmethod
+    def forward(ctx, loss, parked):
+        ctx.parked = parked
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        for p, g in ctx.parked:
+            p.grad = g if p.grad is None else p.grad + g
+        ctx.parked = []
+        return None, None
+
+
 class _RecvFromPrev(torch.autograd.Function):
     """forward: receive the activation from the previous stage; backward: send its gradient back."""
 
@@ -197,7 +213,22 @@ class PipelineEngine:
         return outputs
 
     # ------------------------------------------------------------------ scheduled training step
+    def _flat_state(self):
+        for p in self.module.parameters():
+            st = getattr(p, "_pg_flat_state", None)
+            if st is not None:
+                return st
+        return None
+
     def train_step(self, inputs: Dict) -> torch.Tensor:
+        # Backward runs inside this call, i.e. BEFORE the user's `optim.zero_grad()` of the canonical loop
+        # (`out = model(...); optim.zero_grad(); out.loss.backward(); optim.step()`).  Flat fp32 main grads are
+        # cleared here and then held until the optimizer consumed them; autograd `.grad`s are parked and
+        # installed by `loss.backward()` (see _InstallGrads).
+        flat = self._flat_state()
+        if flat is not None:
+            flat.hold_grads = False
+            flat.zero_grad()
         mbs = self._prepare(inputs)
         dev = self._device()
         m = len(mbs)
@@ -270,6 +301,8 @@ class PipelineEngine:
                 else:
                     self.link.exchange([pending_send], [])
         self.sync_tied_embedding_grad()
+        if flat is not None:
+            flat.hold_grads = True  # survive the zero_grad() that follows forward in the canonical loop
         if self.is_last:
             total = torch.stack(losses).sum()
         else:
@@ -298,5 +331,11 @@ class PipelineEngine:
         from pipegoose_b200.models.bloom import CausalLMOutput
 
         loss = self.train_step(inputs)
-        # backward already ran inside the schedule: hand back a leaf so `loss.backward()` is harmless
-        return CausalLMOutput(loss=loss.detach().requires_grad_(True), logits=None)
+        # backward already ran inside the schedule.  Gradients that live in `.grad` are parked and re-installed
+        # by `loss.backward()`, so a `zero_grad()` between forward and backward does not lose them.
+        parked = []
+        for p in self.module.parameters():
+            if p.grad is not None and getattr(p, "main_grad", None) is None:
+                parked.append((p, p.grad))
+                p.grad = None
+        return CausalLMOutput(loss=_InstallGrads.apply(loss.detach().requires_grad_(True), parked), logits=None)

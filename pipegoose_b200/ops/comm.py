@@ -249,13 +249,16 @@ class FusedDPEngine:
     def _flag_ptrs(self):
         return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
 
-    OVERLAP_CTAS = 6   # CTAs of a gradient reduction that overlaps backward (the GEMMs leave them that many SMs)
-    TAIL_CTAS = 64     # after backward nothing else runs: NVLink-bound
+    # CTAs of a gradient reduction that overlaps backward / runs after it (nothing else runs then: NVLink-bound)
+    OVERLAP_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_OVERLAP_CTAS", "64"))
+    TAIL_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_TAIL_CTAS", "96"))
+    # 1: persistent GEMM grids leave OVERLAP_CTAS SMs free while reductions overlap backward
+    CAP_GEMMS = os.environ.get("PIPEGOOSE_B200_DP_CAP_GEMMS", "0") == "1"
 
     def begin_overlap(self):
         """Backward starts reducing buckets: persistent GEMM grids leave ``OVERLAP_CTAS`` SMs to the reducer
         (a persistent GEMM whose CTAs cannot all be resident stalls behind the reducer's CTAs)."""
-        if not getattr(self, "_capped", False):
+        if self.CAP_GEMMS and not getattr(self, "_capped", False):
             sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
             native().set_gemm_cta_cap((sms - self.OVERLAP_CTAS) // 2 * 2)
             self._capped = True

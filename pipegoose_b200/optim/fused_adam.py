@@ -66,6 +66,7 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = closure() if closure is not None else None
         self._lazy_init()
+        self._fold_autograd_grads()
         self._step += 1
         g = self.param_groups[0]
         lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
@@ -89,7 +90,21 @@ class FusedAdam(torch.optim.Optimizer):
                     master.mul_(1 - lr * wd)
                 master.addcdiv_(m / bc1, (v / bc2).sqrt() + eps, value=-lr)
                 param.copy_(master.to(param.dtype))
+        self.flat.hold_grads = False
         return loss
+
+    def _fold_autograd_grads(self):
+        """Gradients delivered through autograd (``p.grad``: layers without a fused wgrad, or a backward that ran
+        before the flat state existed) are added to the fp32 main grads the kernels update."""
+        for p in self.flat.params:
+            if p.grad is not None:
+                if getattr(p, "_mg_fresh", False):
+                    p.main_grad.copy_(p.grad)
+                    p._mg_fresh = False
+                else:
+                    p.main_grad.add_(p.grad)
+                p.grad = None
+        self.flat.finalize_grads()
 
     def zero_grad(self, set_to_none: bool = True):
         self.ensure_flat().zero_grad()

@@ -1,0 +1,66 @@
+"""3-D composition TensorParallel -> PipelineParallel -> DataParallel -> DistributedOptimizer(FusedAdam) with the
+canonical training loop (forward, zero_grad, backward, step) on 8 gloo processes: the loss trajectory must
+follow the single-process model (BASELINE.json config #5 in miniature: TP2 x PP2 x DP2 + ZeRO-1, 1F1B)."""
+import copy
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import DataParallel, PipelineParallel, TensorParallel
+from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+CFG = dict(vocab_size=96, hidden_size=32, n_layer=4, n_head=4)
+STEPS = 3
+
+
+def run(rank, world_size, port, tp, pp, dp, n_mb, state, ids, ref_losses):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, dp)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    model = PipelineParallel(model, num_microbatches=n_mb, parallel_context=ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    losses = []
+    for _ in range(STEPS):
+        out = model(local, labels=local)
+        optim.zero_grad()       # after forward, as in the reference's README loop
+        out.loss.backward()
+        optim.step()
+        losses.append(out.loss.item())
+    t = torch.tensor(losses)
+    if not ctx.is_last_rank(ParallelMode.PIPELINE):
+        t.zero_()
+    dist.all_reduce(t)
+    mean = (t / (world_size // pp)).tolist()
+    for a, b in zip(mean, ref_losses):
+        assert abs(a - b) < 2e-3, (mean, ref_losses)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,pp,dp", [(2, 2, 2), (1, 2, 2)])
+def test_3d_training_follows_single_process(tp, pp, dp):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (8, 8))
+    n_mb = 2
+    opt = FusedAdam(model.parameters(), lr=1e-2)
+    chunks = [mb for rep in ids.chunk(dp) for mb in rep.chunk(n_mb)]
+    ref_losses = []
+    for _ in range(STEPS):
+        opt.zero_grad()
+        total = 0.0
+        for mb in chunks:
+            loss = model(mb, labels=mb).loss / len(chunks)
+            loss.backward()
+            total += loss.item()
+        opt.step()
+        ref_losses.append(total)
+    assert ref_losses[-1] < ref_losses[0]
+    spawn(run, world_size=tp * pp * dp, tp=tp, pp=pp, dp=dp, n_mb=n_mb, state=state, ids=ids, ref_losses=ref_losses)
