@@ -142,20 +142,38 @@ def run_ours(args):
     from pipegoose_b200.optim.fused_adam import FusedAdam
 
     tp, dp = parallel_layout(args.gpus)
-    ctx = ParallelContext.from_torch(tensor_parallel_size=tp, pipeline_parallel_size=1, data_parallel_size=dp,
+    pp = max(args.pp, 1)
+    if args.tp > 0 or pp > 1:
+        # the other BASELINE.json configs: --tp 8 (bloom-7b1), --tp 2 --pp 2 (bloom-3b, 1F1B), --experts 8 (Switch MoE)
+        tp = args.tp if args.tp > 0 else 1
+        assert args.gpus % (tp * pp) == 0, "--gpus must be a multiple of tp * pp"
+        dp = args.gpus // (tp * pp)
+    ctx = ParallelContext.from_torch(tensor_parallel_size=tp, pipeline_parallel_size=pp, data_parallel_size=dp,
                                      backend="nccl")
     rank = ctx.get_global_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
     cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
     torch.manual_seed(1234)
     model = BloomForCausalLM(cfg).to(torch.bfloat16)
+    if args.experts > 0:
+        from pipegoose_b200.nn import ExpertParallel
+        from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
+
+        router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
+        layers = list(range(0, cfg.n_layer, max(args.moe_every, 1)))
+        model = ExpertParallel(model, args.experts, mapping=layers, router=router.to(torch.bfloat16),
+                               parallel_context=ctx).parallelize()
     model = TensorParallel(model, ctx).parallelize()
+    if pp > 1:
+        from pipegoose_b200.nn import PipelineParallel
+
+        model = PipelineParallel(model, num_microbatches=args.microbatches, parallel_context=ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
     model.to("cuda")
     optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=args.lr), ctx)
 
     S = args.seq_len
-    b_rep = args.batch_per_gpu * tp  # sequences per model replica (DP rank)
+    b_rep = args.batch_per_gpu * tp * pp  # sequences per model replica (DP rank)
     gen = torch.Generator().manual_seed(1000 + ctx.get_local_rank(ParallelMode.DATA))
     n_host = args.steps + args.warmup + 1
     host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen).pin_memory() for _ in range(n_host)]
@@ -176,7 +194,7 @@ def run_ours(args):
         optim.zero_grad()
         loss.backward()
         optim.step()
-        last["loss"] = loss.item()  # device -> host read of the step's result
+        last["loss"] = loss.item()  # device -> host read of the step's result (0 on non-final pipeline stages)
 
     for i in range(args.warmup):
         step_e2e(i)
@@ -207,7 +225,8 @@ def run_ours(args):
         "impl": "pipegoose_b200",
         "config": {
             "model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": S,
-            "parallelism": f"tp{tp}dp{dp}" + ("+zero1" if dp > 1 else ""),
+            "parallelism": f"tp{tp}" + (f"pp{pp}(1f1b,{args.microbatches}mb)" if pp > 1 else "") + f"dp{dp}"
+            + ("+zero1" if dp > 1 else "") + (f"+moe{args.experts}e" if args.experts > 0 else ""),
             "optimizer": "Adam (fp32 master + moments, fused)", "batch_per_gpu": args.batch_per_gpu,
             "l2": "no explicit flush: per-step working set (1.1 GB bf16 weights + >6 GB activations) >> 126 MB L2",
         },
@@ -322,7 +341,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic token ids (uniform random), random-init weights",
         "config": {"model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": S,
-                   "parallelism": f"tp{tp}dp{dp}" + ("+zero1" if dp > 1 else ""), "optimizer": "torch.optim.Adam via reference DistributedOptimizer",
+                   "parallelism": f"tp{tp}" + (f"pp{pp}(1f1b,{args.microbatches}mb)" if pp > 1 else "") + f"dp{dp}"
+            + ("+zero1" if dp > 1 else "") + (f"+moe{args.experts}e" if args.experts > 0 else ""), "optimizer": "torch.optim.Adam via reference DistributedOptimizer",
                    "batch_per_gpu": args.batch_per_gpu},
         "e2e": {"value": tokens_per_step * args.steps / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(host_ids[0].numel() * host_ids[0].element_size()), "d2h_bytes_per_step": 4},
@@ -349,6 +369,12 @@ def main():
     ap.add_argument("--seq-len", type=int, default=1024)
     ap.add_argument("--batch-per-gpu", type=int, default=8)
     ap.add_argument("--lr", type=float, default=1e-4)
+    # non-default layouts (ours arm only): BASELINE.json configs #3-#5
+    ap.add_argument("--tp", type=int, default=0, help="tensor parallel size (0: 1 GPU -> 1, else 2)")
+    ap.add_argument("--pp", type=int, default=1, help="pipeline stages (1F1B)")
+    ap.add_argument("--microbatches", type=int, default=8)
+    ap.add_argument("--experts", type=int, default=0, help="Switch-MoE experts (sharded over the tensor group)")
+    ap.add_argument("--moe-every", type=int, default=2, help="every n-th block gets a MoE MLP")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     _env_defaults()

@@ -5,6 +5,10 @@
 Synthetic token ids are used (no dataset / tokenizer download needed).
 """
 import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a source checkout
 
 import torch
 

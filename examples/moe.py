@@ -3,6 +3,10 @@
     torchrun --standalone --nnodes=1 --nproc-per-node 2 examples/moe.py --tp 2 --experts 4
 """
 import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a source checkout
 
 import torch
 
@@ -25,7 +29,7 @@ if __name__ == "__main__":
     model = BloomForCausalLM(cfg)
     router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
     model = ExpertParallel(model, args.experts, mapping=[0, 2], router=router, parallel_context=ctx).parallelize()
-    model = TensorParallel(model, ctx, sequence_parallel=False).parallelize() if False else model
+    model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
     optim = torch.optim.Adam(model.parameters(), lr=1e-3)
     expert_ctx = ExpertContext.get_instance()

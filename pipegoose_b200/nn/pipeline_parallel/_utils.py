@@ -14,3 +14,10 @@ def is_last_stage(parallel_context: ParallelContext) -> bool:
 
 def is_first_stage(parallel_context: ParallelContext) -> bool:
     return get_partition_idx(parallel_context) == 0
+
+
+def sleep(seconds: float = 0.05):
+    """Blocking sleep (parity: reference nn/pipeline_parallel/_utils.py:7-9; the runtime itself never polls)."""
+    import time
+
+    time.sleep(seconds)

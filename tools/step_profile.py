@@ -78,12 +78,34 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    import time
+
+    # host-side cost of enqueueing one step (GPU queue empty, no sync inside): if this is close to the device
+    # time of a step, the step is launch-bound
+    cpu = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        cpu.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
     torch.cuda.profiler.start()
     step(timed=True)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print(json.dumps({"fwd_ms": ev[0].elapsed_time(ev[1]), "bwd_ms": ev[1].elapsed_time(ev[2]),
-                      "optim_ms": ev[2].elapsed_time(ev[3])}))
+                      "optim_ms": ev[2].elapsed_time(ev[3]), "cpu_enqueue_ms": cpu}))
+    if os.environ.get("PG_CPROFILE"):
+        import cProfile
+        import pstats
+
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        step()
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
 
 
 if __name__ == "__main__":
