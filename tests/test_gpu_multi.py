@@ -249,9 +249,9 @@ def run_dp_zero(rank, world_size, port, fused_dp, state, ids, ref_losses):
     ctx.destroy()
 
 
-@pytest.mark.parametrize("fused_dp", [False, True])
-def test_dp2_zero1_matches_single_gpu(fused_dp):
-    _need_gpus(2)
+@pytest.mark.parametrize("fused_dp,world", [(False, 2), (True, 2), (True, 4)])
+def test_dp_zero1_matches_single_gpu(fused_dp, world):
+    _need_gpus(world)
     from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
     from pipegoose_b200.optim import FusedAdam
     from pipegoose_b200.testing.utils import spawn
@@ -260,7 +260,7 @@ def test_dp2_zero1_matches_single_gpu(fused_dp):
     cfg = BloomConfig(vocab_size=4096, hidden_size=256, n_layer=2, n_head=4)
     ref = BloomForCausalLM(cfg)
     state = copy.deepcopy(ref.state_dict())
-    ids = torch.randint(0, 4096, (4, 256))
+    ids = torch.randint(0, 4096, (2 * world, 256))
     model = copy.deepcopy(ref).to(torch.bfloat16).cuda()
     opt = FusedAdam(model.parameters(), lr=1e-3)
     ref_losses = []
@@ -270,4 +270,4 @@ def test_dp2_zero1_matches_single_gpu(fused_dp):
         loss.backward()
         opt.step()
         ref_losses.append(loss.item())
-    spawn(run_dp_zero, world_size=2, fused_dp=fused_dp, state=state, ids=ids, ref_losses=ref_losses)
+    spawn(run_dp_zero, world_size=world, fused_dp=fused_dp, state=state, ids=ids, ref_losses=ref_losses)
