@@ -61,7 +61,9 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   }
   if (residual.has_value()) {
     check_bf16_2d(*residual, "residual");
-    TORCH_CHECK(residual->size(0) == M && residual->size(1) == N, "residual shape mismatch");
+    // fused reduce-scatter: the residual is the local token shard [M / num_chunks, N]
+    TORCH_CHECK((residual->size(0) == M || (ag.contains("rs_in") && residual->size(0) * num_chunks == M)) &&
+                    residual->size(1) == N, "residual shape mismatch");
     d.residual = residual->data_ptr();
     d.ldr = (int)residual->stride(0);
     d.flags |= 4;
@@ -92,6 +94,13 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
       d.row_scale = reinterpret_cast<const float*>(ag["row_scale"].cast<int64_t>());
       d.scatter_rows_per_src = ag["rows_per_src"].cast<int>();
     }
+  }
+  if (ag.contains("rs_in")) {
+    auto in = ag["rs_in"].cast<std::vector<int64_t>>();
+    for (size_t i = 0; i < in.size() && i < PG_MAX_PEERS; ++i) d.rs_in[i] = reinterpret_cast<const void*>(in[i]);
+    d.rs_wait_ctr = reinterpret_cast<const uint32_t*>(ag["rs_wait"].cast<int64_t>());
+    d.rs_wait_value = (uint32_t)ag["rs_wait_value"].cast<int64_t>();
+    d.my_rank = ag["rank"].cast<int>();
   }
   if (ag.contains("k_splits")) d.k_splits = ag["k_splits"].cast<int>();
   if (ag.contains("cta_pair")) d.cta_pair = ag["cta_pair"].cast<int>();

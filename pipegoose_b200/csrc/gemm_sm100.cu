@@ -231,7 +231,10 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   for (int i = 0; i < kMaxPeers; ++i) {
     args.out_peer[i] = d->out_peer[i];
     args.arrive_ctr[i] = d->arrive_ctr[i];
+    args.rs_in[i] = reinterpret_cast<const __nv_bfloat16*>(d->rs_in[i]);
   }
+  args.rs_wait_ctr = d->rs_wait_ctr;
+  args.rs_wait_value = d->rs_wait_value;
   args.b_chunk_rows = d->b_chunk_rows;
   args.bias_chunk_stride = d->bias_chunk_stride;
   args.row_ret = d->row_ret;

@@ -75,6 +75,12 @@ struct GemmArgs {
   // then arrive_ctr[c] (+1 per finished tile, release.sys)
   void* out_peer[kMaxPeers];
   uint32_t* arrive_ctr[kMaxPeers];
+  // fused reduction of the LOCAL chunk (visited last): once every peer's arrival counter reached rs_wait_value,
+  // the epilogue of this rank's own tiles adds the peers' staged partial tiles (+ bias + residual) and writes the
+  // final rows to `out`; no separate reduce kernel, the own partial never goes through memory
+  const __nv_bfloat16* rs_in[kMaxPeers];  // local staging slot of source s (rs_in[my_rank] unused); null = off
+  const uint32_t* rs_wait_ctr;            // local arrival counters, one per source
+  uint32_t rs_wait_value;
 };
 
 constexpr int BM = 128;
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int own_sw = (lane >> 1) & 3;               // swizzle of this thread's row
     const int co_r = lane >> 2;                       // coalesced pattern: row inside a group of 8
     const int co_ch = lane & 3;                       // 16-byte chunk of the 64-byte segment
+    bool rs_ready = false;                            // peers' partial tiles of the local chunk have landed
     int it = 0;
     for (int t = unit0; t < num_work; t += unit_stride, ++it) {
       const TileCoord tc = map_tile(t % num_tiles, m_blks_per_chunk, n_blks, args.num_chunks, args.first_chunk);
@@ -443,29 +450,52 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           out_row = row - tc.chunk * chunk_rows;
         }
       }
+      // GEMM -> reduce-scatter with the reduction fused into the local chunk's epilogue
+      const bool rs_mode = args.rs_wait_ctr != nullptr && args.num_chunks > 1;
+      const bool rs_local = rs_mode && tc.chunk == args.my_rank;
+      if (rs_local) {
+        out_base = reinterpret_cast<uint8_t*>(args.out);
+        out_row = row - tc.chunk * chunk_rows;
+        if (!rs_ready) {
+          // peers computed my chunk FIRST; by the time I reach it their tiles have normally landed
+          if (lane == 0) {
+            for (int s2 = 0; s2 < args.num_chunks; ++s2)
+              if (s2 != args.my_rank)
+                while (ld_acquire_sys(args.rs_wait_ctr + s2) < args.rs_wait_value) {
+                }
+          }
+          __syncwarp();
+          rs_ready = true;
+        }
+      }
       const bool row_ok = row < row_limit && row < args.M;
       const int warp_row0 = tc.m_blk * BM_T + row_in_tile0 + q * 32;  // first row handled by this warp
       const int warp_out_row0 = out_row - lane;               // its destination row index
       const int rows_ok = max(0, min(32, min(row_limit, args.M) - warp_row0));
+      const int local_row0 = warp_row0 - tc.chunk * chunk_rows;
+      // bias / residual of a fused reduce-scatter belong to the final (local) rows, not to partials sent to peers;
+      // the residual is then the local token shard [chunk_rows, N]
+      const bool use_in = in_ptr != nullptr && (!rs_mode || rs_local);
+      const bool use_bias = (args.flags & EPI_BIAS) && (!rs_mode || rs_local);
       uint4 pre[4];
       auto prefetch_in = [&](int c) {
         const int col = n0 + c * 32 + co_ch * 8;
+        const __nv_bfloat16* base = in_ptr + static_cast<size_t>(rs_local ? local_row0 : warp_row0) * in_ld;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = i * 8 + co_r;
           pre[i] = make_uint4(0, 0, 0, 0);
-          if (rr < rows_ok && col < args.N)
-            pre[i] = ld_global_nc_v4(in_ptr + static_cast<size_t>(warp_row0 + rr) * in_ld + col);
+          if (rr < rows_ok && col < args.N) pre[i] = ld_global_nc_v4(base + static_cast<size_t>(rr) * in_ld + col);
         }
       };
-      if (in_ptr != nullptr && h < NCH) prefetch_in(h);
+      if (use_in && h < NCH) prefetch_in(h);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int c = h; c < NCH; c += 2) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
-        if (in_ptr != nullptr) {
+        if (use_in) {
           // park the prefetched inputs in the staging buffer, start fetching the next chunk's
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -482,7 +512,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         const bool active = row_ok && ncols > 0;
-        if (active && (args.flags & EPI_BIAS)) {
+        if (active && use_bias) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < ncols) {
@@ -548,7 +578,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
         }
-        if (in_ptr != nullptr) {
+        if (use_in) {
           const bool dgelu = (args.flags & EPI_DGELU) != 0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -566,6 +596,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               }
             }
           }
+        }
+        if (rs_local) {
+          // add every peer's staged partial of this chunk (local memory, written through NVLink and acquired above)
+#pragma unroll 1
+          for (int src = 0; src < args.num_chunks; ++src) {
+            if (src == args.my_rank) continue;
+            const __nv_bfloat16* base = args.rs_in[src] + static_cast<size_t>(local_row0) * args.N + col0 + co_ch * 8;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + co_r;
+              uint4 val = make_uint4(0, 0, 0, 0);
+              if (rr < rows_ok && co_ch * 8 < ncols) val = ld_global_v4(base + static_cast<size_t>(rr) * args.N);
+              *reinterpret_cast<uint4*>(stg_warp + rr * 64 + ((co_ch ^ ((rr >> 1) & 3)) << 4)) = val;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 z = *reinterpret_cast<const uint4*>(stg_own + ((g ^ own_sw) << 4));
+              const uint32_t zw[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 zf = unpack_bf16x2(zw[j]);
+                f[g * 8 + 2 * j] += zf.x;
+                f[g * 8 + 2 * j + 1] += zf.y;
+              }
+            }
+          }
+          __syncwarp();
         }
         if (active && (args.flags & EPI_SCATTER)) {
           const float sc = args.row_scale[row];
@@ -604,7 +663,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           mbar_arrive(&tmem_empty[acc]);
         }
       }
-      if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr && !(args.flags & EPI_SCATTER)) {
+      if (args.num_chunks > 1 && args.arrive_ctr[0] != nullptr && !(args.flags & EPI_SCATTER) && !rs_local) {
         // all eight epilogue warps have stored their part of this tile -> publish to the owner
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 4 && lane == 0) {

@@ -33,6 +33,10 @@ typedef struct PgGemmDesc {
   uint32_t flag_value;
   void* out_peer[PG_MAX_PEERS];
   uint32_t* arrive_ctr[PG_MAX_PEERS];
+  // GEMM -> reduce-scatter with the reduction fused into the local chunk's epilogue (see GemmArgs)
+  const void* rs_in[PG_MAX_PEERS];
+  const uint32_t* rs_wait_ctr;
+  uint32_t rs_wait_value;
   // all-gather -> GEMM communication CTAs
   int n_comm;
   const void* ag_src[PG_MAX_PEERS];

@@ -28,14 +28,22 @@ _BM = 128
 import os
 
 N_COMM_CTAS = int(os.environ.get("PIPEGOOSE_B200_NCOMM", "16"))
+# 1: GEMM -> reduce-scatter reduces the local chunk in its own epilogue (no reduce kernel; measured 10 us slower per
+# op at T=2 because the staged partials are read without prefetch); 0 (default): separate rs_reduce kernel
+RS_FUSED_REDUCE = os.environ.get("PIPEGOOSE_B200_RS_FUSED_REDUCE", "0") == "1"
 
 
-def pick_tiling(rows: int, n: int, k: int, chunks: int, ctas: int, b_mn: bool):
+RS_PAIR = os.environ.get("PIPEGOOSE_B200_RS_PAIR", "auto")  # CTA pairs in GEMM -> reduce-scatter: auto / 0 / 1
+
+
+def pick_tiling(rows: int, n: int, k: int, chunks: int, ctas: int, b_mn: bool, pair_mode: str = "auto"):
     """``(block_n, cta_pair)`` for a GEMM -> reduce-scatter: mirror of ``pick_bn`` in csrc/gemm_sm100.cu (the
     arrival counters of a reduce-scatter are counted in tiles, so both sides must agree on the tiling).
     CTA pairs (tcgen05 ``cta_group::2``, 256-row tiles) where the operand feed is the limit: long K or many tiles."""
     tiles1 = ((rows + _BM - 1) // _BM) * ((n + 255) // 256) * chunks
     pair = rows % (2 * _BM) == 0 and ctas >= 2 and (k >= 2048 or tiles1 >= 3 * ctas)
+    if pair_mode in ("0", "1"):
+        pair = pair_mode == "1" and rows % (2 * _BM) == 0 and ctas >= 2
     bm = 2 * _BM if pair else _BM
     units = ctas // 2 if pair else ctas
     cands = ((256, 1.0), (192, 0.80), (128, 0.70)) if pair else ((256, 1.0), (192, 0.93), (128, 0.82), (64, 0.55))
@@ -171,16 +179,24 @@ class FusedTPEngine:
         self.rs_calls += 1
         slot = self.rs_calls & 1
         k = a.shape[1]
-        bn, pair = pick_tiling(m_local, n, k, T, self.num_sms, b_mn)
+        bn, pair = pick_tiling(m_local, n, k, T, self.num_sms, b_mn, RS_PAIR)
         # every CTA bumps the owner's counter once per tile it stored (both CTAs of a pair do)
         tiles_per_chunk = ((m_local + _BM - 1) // _BM) * ((n + bn - 1) // bn)
         self.rs_expected += tiles_per_chunk
         src_stride = m_local * n  # elements between two sources' slots
         out_peer = [ws.data_ptr(p, self._rs_off(slot) + r * src_stride * 2) for p in range(T)]
         arrive = [ws.sig_ptr(p, S.SIG_RS_ARRIVE + r) for p in range(T)]
+        out = torch.empty(m_local, n, dtype=torch.bfloat16, device=a.device)
+        if RS_FUSED_REDUCE:
+            # the epilogue of this rank's own (last visited) chunk adds the peers' staged partials + bias + residual
+            ag = {"cta_pair": 1 if pair else -1, "rank": r, "rs_wait": ws.sig_ptr(r, S.SIG_RS_ARRIVE),
+                  "rs_wait_value": self.rs_expected,
+                  "rs_in": [ws.data_ptr(r, self._rs_off(slot) + s * src_stride * 2) for s in range(T)]}
+            native().gemm(a, weight, out, False, b_mn, bias, residual, None, 0, bn, 0,
+                          T, (r + 1) % T, 0, 0, out_peer, arrive, ag)
+            return out
         native().gemm(a, weight, self._dummy_out(n, a.device), False, b_mn, None, None, None, 0, bn, 0,
                       T, (r + 1) % T, 0, 0, out_peer, arrive, {"cta_pair": 1 if pair else -1})
-        out = torch.empty(m_local, n, dtype=torch.bfloat16, device=a.device)
         native().rs_reduce(ws.data_ptr(r, self._rs_off(slot)), T, src_stride, ws.sig_ptr(r, S.SIG_RS_ARRIVE),
                            self.rs_expected, bias, residual, out)
         return out
