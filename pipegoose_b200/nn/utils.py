@@ -48,3 +48,61 @@ def save_pretrained(module: nn.Module, ckp_name: str = CHECKPOINT_WEIGHTS_NAME, 
         import torch.distributed as dist
 
         dist.barrier(group=parallel_context.get_group(ParallelMode.DATA))
+
+
+# ------------------------------------------------------------------------------------------------
+# resume: optimizer shards + RNG + step (the reference only saves model weights)
+# ------------------------------------------------------------------------------------------------
+def _optim_file(ckp_path: str, parallel_context: ParallelContext) -> str:
+    from pipegoose_b200.constants import CHECKPOINT_OPTIM_NAME
+
+    return os.path.join(ckp_path, CHECKPOINT_OPTIM_NAME.format(
+        parallel_context.get_local_rank(ParallelMode.TENSOR), parallel_context.get_local_rank(ParallelMode.PIPELINE),
+        parallel_context.get_local_rank(ParallelMode.DATA)))
+
+
+def _layout(parallel_context: ParallelContext) -> dict:
+    return {"tp": parallel_context.tensor_parallel_size, "pp": parallel_context.pipeline_parallel_size,
+            "dp": parallel_context.data_parallel_size}
+
+
+def save_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
+                        step: int = 0, extra: dict = None):
+    """Every rank writes ITS optimizer shard (ZeRO-1: 1/dp of the fp32 master weights and moments) as
+    ``optimizer_tp_{tp}_pp_{pp}_dp_{dp}.bin`` together with the step counter, the RNG states and the parallel
+    layout the shard belongs to."""
+    Path(ckp_path).mkdir(parents=True, exist_ok=True)
+    sd = optim.state_dict()
+
+    def to_cpu(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().cpu()
+        if isinstance(x, dict):
+            return {k: to_cpu(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(to_cpu(v) for v in x)
+        return x
+
+    blob = {"optimizer": to_cpu(sd), "step": int(step), "layout": _layout(parallel_context),
+            "rng": {"torch": torch.get_rng_state(),
+                    "cuda": torch.cuda.get_rng_state() if torch.cuda.is_available() else None},
+            "extra": extra or {}}
+    torch.save(blob, _optim_file(ckp_path, parallel_context))
+
+
+def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
+                        restore_rng: bool = True) -> dict:
+    """Restore what :func:`save_training_state` wrote; returns ``{"step": ..., "extra": ...}``."""
+    path = _optim_file(ckp_path, parallel_context)
+    if not os.path.exists(path):
+        raise ValueError(f"optimizer checkpoint {path} does not exist")
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    if blob["layout"] != _layout(parallel_context):
+        raise ValueError(f"checkpoint was written for layout {blob['layout']}, this job runs {_layout(parallel_context)}: "
+                         "optimizer shards are tied to the parallel layout")
+    optim.load_state_dict(blob["optimizer"])
+    if restore_rng:
+        torch.set_rng_state(blob["rng"]["torch"])
+        if blob["rng"]["cuda"] is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(blob["rng"]["cuda"])
+    return {"step": blob["step"], "extra": blob["extra"]}

@@ -62,3 +62,47 @@ def test_trainer_fits_and_logs():
     assert state.status is TrainerStatus.FINISHED and state.step == 12 and state.tokens_seen == 12 * 16
     assert events[0] == "start" and events[-1] == "end" and events[-2] < events[1]  # loss went down
     assert "tokens/s" in stream.getvalue()
+
+
+def run_resume(rank, world_size, port, tp, dp, ckp_path):
+    from pipegoose_b200.nn.utils import load_training_state, save_training_state
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    cfg = BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)
+    ids = torch.randint(0, 96, (4, 8), generator=torch.Generator().manual_seed(7 + ctx.get_local_rank(ParallelMode.DATA)))
+
+    def build():
+        torch.manual_seed(0)
+        model = BloomForCausalLM(cfg)
+        model = TensorParallel(model, ctx).parallelize()
+        model = DataParallel(model, ctx).parallelize()
+        return model, DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+
+    def step(model, optim):
+        loss = model(ids, labels=ids).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        return loss.item()
+
+    model, optim = build()
+    for _ in range(2):
+        step(model, optim)
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    save_training_state(optim, ckp_path=ckp_path, parallel_context=ctx, step=2, extra={"tokens": 64})
+    want = step(model, optim)  # the third step of the uninterrupted run
+
+    model2, optim2 = build()
+    step(model2, optim2)  # build the lazily created optimizer state, then overwrite everything
+    from_pretrained(model2, ckp_path=ckp_path, parallel_context=ctx)
+    meta = load_training_state(optim2, ckp_path=ckp_path, parallel_context=ctx)
+    assert meta == {"step": 2, "extra": {"tokens": 64}}
+    got = step(model2, optim2)
+    assert abs(got - want) < 1e-5, (got, want)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("world,tp,dp", [(1, 1, 1), (4, 2, 2)])
+def test_resume_from_sharded_optimizer_checkpoint(tmp_path, world, tp, dp):
+    spawn(run_resume, world_size=world, tp=tp, dp=dp, ckp_path=str(tmp_path / "ckpt"))
