@@ -387,7 +387,15 @@ def main():
             os.execv(sys.executable, cmd)
         raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
     if args.impl == "reference":
-        run_reference(args)
+        try:
+            run_reference(args)
+        except Exception as e:  # the reference's own code path failed on this layout: report it, do not crash the driver
+            import traceback
+
+            traceback.print_exc()
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "n_gpus": args.gpus,
+                                  "unavailable": f"reference failed at run time: {type(e).__name__}: {e}"[:300]}), flush=True)
     else:
         run_ours(args)
 
