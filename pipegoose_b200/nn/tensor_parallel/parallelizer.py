@@ -110,6 +110,7 @@ class EmbeddingParallelizer(ModuleParallelizer):
         world = ctx.get_world_size(ParallelMode.TENSOR)
         rank = ctx.get_local_rank(ParallelMode.TENSOR)
         if not _is_sliced(module.weight):
+            old = module.weight
             weight = module.weight.data
             vocab = weight.shape[0]
             padded = (vocab + world - 1) // world * world
@@ -117,6 +118,10 @@ class EmbeddingParallelizer(ModuleParallelizer):
                 weight = torch.cat([weight, weight.new_zeros(padded - vocab, weight.shape[1])], dim=0)
             module.weight = nn.Parameter(get_partition(weight, ctx, dim=0), requires_grad=module.weight.requires_grad)
             _mark_sliced(module.weight)
+            # modules that shared the table (a tied lm_head) must pick up the shard, not slice their own copy
+            for other in self.model.modules():
+                if other is not module and getattr(other, "weight", None) is old:
+                    other._pg_tied_to_embedding = True
         else:
             padded = module.weight.shape[0] * world
         module.__class__ = ParallelEmbedding
