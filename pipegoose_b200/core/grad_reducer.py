@@ -26,6 +26,87 @@ from pipegoose_b200.core.flat_state import FlatModelState, _ALIGN
 from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
 
+def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelState] = None):
+    """Sum the gradients of ``tp_partial_grad`` parameters over the TENSOR group, in place.  Gradients live in
+    ``param.main_grad`` (flat fp32 buffer: one all-reduce of its head when the tagged parameters are laid out
+    there) or, for parameters without a flat state, in ``param.grad`` (gathered into one flat tensor)."""
+    if parallel_context.get_world_size(ParallelMode.TENSOR) == 1:
+        return
+    ps = [p for p in params if getattr(p, "tp_partial_grad", False)]
+    if not ps:
+        return
+    group = parallel_context.get_group(ParallelMode.TENSOR)
+    if flat is not None and all(getattr(p, "main_grad", None) is not None for p in ps):
+        fresh = [p.main_grad for p in ps if getattr(p, "_mg_fresh", False)]
+        if fresh:
+            torch._foreach_zero_(fresh)
+        for p in ps:
+            p._mg_fresh = False
+        n = getattr(flat, "tp_partial_numel", 0)
+        if all(sum(flat.param_range(p)) <= n for p in ps):
+            dist.all_reduce(flat.flat_grad[:n], group=group)
+            return
+    grads = []
+    for p in ps:
+        g = getattr(p, "main_grad", None)
+        if g is None:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g = p.grad
+        elif getattr(p, "_mg_fresh", False):
+            g.zero_()
+            p._mg_fresh = False
+        grads.append(g)
+    buf = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(buf, group=group)
+    torch._foreach_copy_(grads, [f.view_as(g) for f, g in zip(buf.split([g.numel() for g in grads]), grads)])
+
+
+class TensorPartialGradSync:
+    """Tensor parallelism WITHOUT a data-parallel reducer (dp == 1): the sequence-parallel layers still produce
+    partial gradients for the TP-replicated parameters, so something must sum them over the TENSOR group before
+    the optimizer step.  Installed by ``TensorParallel``; steps aside as soon as a :class:`GradReducer` owns the
+    module (it does the same reduction in its ``finalize``).  ``no_sync()`` for gradient accumulation: reduce only
+    after the last backward of a step."""
+
+    def __init__(self, module: nn.Module, parallel_context):
+        self.module = module
+        self.ctx = parallel_context
+        self._sync = True
+        self._queued = False
+        self.params = [p for p in module.parameters() if getattr(p, "tp_partial_grad", False)]
+        for p in self.params:
+            if getattr(p, "_pg_grad_ready", None) is None:
+                p._pg_grad_ready = self._on_ready
+            if not hasattr(p, "_pg_tp_sync_hook"):
+                p._pg_tp_sync_hook = p.register_post_accumulate_grad_hook(self._on_ready)
+
+    def _reducer_active(self) -> bool:
+        r = getattr(self.module, "_pg_grad_reducer", None)
+        return r is not None and r.flat is not None
+
+    def _on_ready(self, p):
+        if self._queued or self._reducer_active():
+            return
+        self._queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(self.finalize)
+
+    def finalize(self):
+        self._queued = False
+        if not self._sync or self._reducer_active():
+            return
+        flat = FlatModelState.find(self.params)
+        reduce_tp_partial_grads(self.params, self.ctx, flat)
+
+    @contextmanager
+    def no_sync(self):
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
+
+
 class _Bucket:
     __slots__ = ("index", "start", "end", "params", "pending", "launched", "work", "deferred")
 
@@ -178,7 +259,8 @@ class GradReducer:
         self._callback_queued = False
         if self.flat is None:
             return
-        self._reduce_tp_partial()
+        if self._sync:
+            self._reduce_tp_partial()  # accumulation steps keep partial sums; only the last backward reduces
         if self._fused is not None:
             self._fused.end_overlap()
         if self._sync and self.dp > 1:
@@ -199,27 +281,7 @@ class GradReducer:
         row-parallel biases) from their token shard only: sum them over the TENSOR group.  They sit at
         the head of the flat gradient buffer (FlatModelState sorts them first), so this is ONE in-place
         all-reduce; their buckets are held back (``deferred``) until it is enqueued."""
-        tp = self.ctx.get_world_size(ParallelMode.TENSOR)
-        if tp == 1:
-            return
-        ps = [p for p in self.flat.params if getattr(p, "tp_partial_grad", False)]
-        if not ps:
-            return
-        fresh = [p.main_grad for p in ps if getattr(p, "_mg_fresh", False)]
-        if fresh:
-            torch._foreach_zero_(fresh)
-        for p in ps:
-            p._mg_fresh = False
-        n = getattr(self.flat, "tp_partial_numel", 0)
-        group = self.ctx.get_group(ParallelMode.TENSOR)
-        if all(sum(self.flat.param_range(p)) <= n for p in ps):
-            dist.all_reduce(self.flat.flat_grad[:n], group=group)
-            return
-        # parameters tagged after the flat state was laid out: gather / scatter fallback
-        flat = torch.cat([p.main_grad.reshape(-1) for p in ps])
-        dist.all_reduce(flat, group=group)
-        torch._foreach_copy_([p.main_grad for p in ps],
-                             [f.view_as(p.main_grad) for f, p in zip(flat.split([p.numel() for p in ps]), ps)])
+        reduce_tp_partial_grads(self.flat.params, self.ctx, self.flat)
 
     @contextmanager
     def no_sync(self):

@@ -239,6 +239,8 @@ class PipelineEngine:
         recv_grad: Dict[int, torch.Tensor] = {}
         losses = []
         reducer = getattr(self.full_module, "_pg_grad_reducer", None) if self.full_module is not None else None
+        if reducer is None and self.full_module is not None:
+            reducer = getattr(self.full_module, "_pg_tp_grad_sync", None)  # tp > 1 without data parallelism
         n_bwd_done = 0
 
         def act_buffer(i):

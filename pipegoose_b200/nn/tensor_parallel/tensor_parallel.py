@@ -48,6 +48,13 @@ class TensorParallel(Parallel):
             if use_sp:
                 assert isinstance(module, FastBloom), "the sequence-parallel path needs a pipegoose_b200.models model"
                 _parallelize_fast_bloom(module, ctx)
+                # partial gradients of the TP-replicated parameters are summed over the TENSOR group after every
+                # backward, also when no DataParallel reducer is installed (dp == 1)
+                from pipegoose_b200.core.grad_reducer import TensorPartialGradSync
+
+                module._pg_tp_grad_sync = TensorPartialGradSync(module, ctx)
+                if not hasattr(module, "no_sync") or getattr(module, "_pg_grad_reducer", None) is None:
+                    module.no_sync = module._pg_tp_grad_sync.no_sync
             else:
                 # remember weight tying before the embedding's parameter object is replaced by its slice
                 if hasattr(module, "get_input_embeddings") and hasattr(module, "get_output_embeddings"):

@@ -81,12 +81,10 @@ def run_fast_bloom(rank, world_size, port, tp, state, ids, ref_loss, ref_grads, 
             return g.chunk(tp, 0)[r]
         return g
 
-    import torch.distributed as dist
-
     for name, p in model.named_parameters():
+        # gradients of TP-replicated parameters are partial sums over the token shards; TensorParallel's
+        # TensorPartialGradSync has already summed them over the tensor group when backward returned
         g = p.grad.clone()
-        if getattr(p, "tp_partial_grad", False):  # partial sums over token shards -> add over the TP group
-            dist.all_reduce(g, group=ctx.get_group(ParallelMode.TENSOR))
         want = shard(name, ref_grads[name])
         assert torch.allclose(g, want, atol=2e-5), name
     ctx.destroy()
@@ -108,3 +106,68 @@ def test_fast_bloom_sequence_parallel_matches_unsharded():
         logits = model(ids).logits
     spawn(run_fast_bloom, world_size=2, tp=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach(),
           ref_grads=grads, ref_logits=logits)
+
+
+def run_tp_only_training(rank, world_size, port, state, ids, ref_losses, ref_ln_grad):
+    """tp=2, dp=1: no DataParallel reducer exists, yet LayerNorm / row-parallel-bias gradients (partial sums over
+    the token shards) must be summed over the TENSOR group, and the replicated parameters must stay identical."""
+    import torch.distributed as dist
+
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    cfg = BloomConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+
+    # gradient accumulation over two micro-batches: partial sums are reduced once, after the last backward
+    optim.zero_grad()
+    halves = ids.chunk(2)
+    with model.no_sync():
+        (model(halves[0], labels=halves[0]).loss / 2).backward()
+    (model(halves[1], labels=halves[1]).loss / 2).backward()
+    ln = model.transformer.h[0].input_layernorm.weight
+    g = ln.main_grad if getattr(ln, "main_grad", None) is not None else ln.grad
+    assert torch.allclose(g.float(), ref_ln_grad, atol=2e-5), (g, ref_ln_grad)
+
+    losses = []
+    for _ in range(len(ref_losses)):
+        loss = model(ids, labels=ids).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        losses.append(loss.item())
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3, (losses, ref_losses)
+    for name, p in model.named_parameters():
+        if getattr(p, "tp_partial_grad", False):
+            other = p.detach().clone()
+            dist.broadcast(other, src=0)
+            assert torch.allclose(p.detach(), other, atol=1e-7), f"{name} diverged across the tensor group"
+    ctx.destroy()
+
+
+def test_tensor_parallel_without_data_parallel_trains_like_a_single_process():
+    from pipegoose_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    cfg = BloomConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)
+    model = BloomForCausalLM(cfg)
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 128, (4, 8))
+    halves = ids.chunk(2)
+    for h in halves:
+        (model(h, labels=h).loss / 2).backward()
+    ref_ln_grad = model.transformer.h[0].input_layernorm.weight.grad.clone()
+    model.zero_grad()
+    opt = FusedAdam(model.parameters(), lr=1e-2)
+    ref_losses = []
+    for _ in range(3):
+        loss = model(ids, labels=ids).loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(loss.item())
+    spawn(run_tp_only_training, world_size=2, state=state, ids=ids, ref_losses=ref_losses, ref_ln_grad=ref_ln_grad)

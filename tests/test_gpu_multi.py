@@ -98,12 +98,12 @@ def run_tp_bloom(rank, world_size, port, fused, state, ids, ref_loss, ref_gnorm)
     loss = model(ids, labels=ids).loss
     loss.backward()
     assert abs(loss.item() - ref_loss) < 3e-2, (loss.item(), ref_loss)
-    # global gradient norm (sharded params: sum of squares over ranks; replicated: TP-reduced partials)
+    # global gradient norm (sharded params: sum of squares over ranks; replicated params: their partial gradients
+    # were already summed over the tensor group by TensorParallel's TensorPartialGradSync, count them once)
     sq = torch.zeros((), device="cuda")
     for n, p in model.named_parameters():
         g = p.grad.float()
         if getattr(p, "tp_partial_grad", False):
-            dist.all_reduce(g, group=ctx.get_group(ParallelMode.TENSOR))
             sq += g.pow(2).sum() / world_size
         elif hasattr(p, "parallel_metadata"):
             sq += g.pow(2).sum()
