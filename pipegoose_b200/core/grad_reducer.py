@@ -59,7 +59,7 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
         grads.append(g)
     buf = torch.cat([g.reshape(-1).float() for g in grads])
     dist.all_reduce(buf, group=group)
-    torch._foreach_copy_(grads, [f.view_as(g) for f, g in zip(buf.split([g.numel() for g in grads]), grads)])
+    torch._foreach_copy_(grads, [f.view_as(g).to(g.dtype) for f, g in zip(buf.split([g.numel() for g in grads]), grads)])
 
 
 class TensorPartialGradSync:
