@@ -52,6 +52,21 @@ class SequentialStage(nn.Module):
         return x
 
 
+_HF_BLOOM_BOOL_MASK = None
+
+
+def _hf_bloom_uses_boolean_mask() -> bool:
+    """Old 🤗 Bloom blocks take a boolean mask (``masked_fill``), newer ones an additive float mask."""
+    global _HF_BLOOM_BOOL_MASK
+    if _HF_BLOOM_BOOL_MASK is None:
+        import inspect
+
+        from transformers.models.bloom.modeling_bloom import BloomAttention
+
+        _HF_BLOOM_BOOL_MASK = "masked_fill" in inspect.getsource(BloomAttention.forward)
+    return _HF_BLOOM_BOOL_MASK
+
+
 class BloomStage(nn.Module):
     """A contiguous slice of a Bloom-style causal LM: [embedding +] blocks [+ final norm + lm head].
 
@@ -114,8 +129,46 @@ class BloomStage(nn.Module):
             attention_mask = torch.ones(B, S, dtype=torch.long, device=h.device)
         alibi = build_alibi_tensor(attention_mask, self.config.n_head, dtype=h.dtype)
         causal = torch.ones(S, S, dtype=torch.bool, device=h.device).triu(1)[None, None].expand(B, 1, S, S)
+        if not _hf_bloom_uses_boolean_mask():
+            # newer transformers ADD the mask to the scores: 0 where visible, a large negative where masked
+            causal = torch.zeros(B, 1, S, S, dtype=h.dtype, device=h.device).masked_fill(causal, torch.finfo(h.dtype).min)
         for block in self.h:
             out = block(h, alibi=alibi, attention_mask=causal)
+            h = out[0] if isinstance(out, tuple) else out
+        if not self.is_last:
+            return h
+        logits = self.lm_head(self.ln_f(h))
+        if labels is not None:
+            shift_logits = logits[..., :-1, :].contiguous().float()
+            shift_labels = labels[..., 1:].contiguous()
+            return torch.nn.functional.cross_entropy(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.view(-1))
+        return logits
+
+
+class GPT2Stage(nn.Module):
+    """A contiguous slice of a 🤗 GPT-2 style causal LM (``transformer.{wte,wpe,drop,h,ln_f}`` + ``lm_head``) —
+    the second model family the reference's partitioner is tested with (tests/nn/pipeline_parallel/test_partitioner.py)."""
+
+    def __init__(self, model: nn.Module, start: int, end: int, is_first: bool, is_last: bool):
+        super().__init__()
+        t = model.transformer
+        self.is_first, self.is_last = is_first, is_last
+        if is_first:
+            self.wte, self.wpe, self.drop = t.wte, t.wpe, t.drop
+        self.h = nn.ModuleList([t.h[i] for i in range(start, end)])
+        if is_last:
+            self.ln_f = t.ln_f
+            self.lm_head = model.lm_head
+
+    def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, batch_seq=None):
+        if self.is_first:
+            pos = torch.arange(x.shape[1], device=x.device)[None]
+            h = self.drop(self.wte(x) + self.wpe(pos))
+        else:
+            h = x
+        for block in self.h:
+            out = block(h)
             h = out[0] if isinstance(out, tuple) else out
         if not self.is_last:
             return h
@@ -156,11 +209,12 @@ class UniformPartitioner:
             return [SequentialStage(layers[b[i]:b[i + 1]]) for i in range(n)]
         blocks = self._block_list(model)
         assert blocks is not None and hasattr(model, "transformer"), \
-            "UniformPartitioner supports nn.Sequential and Bloom-style causal LMs"
+            "UniformPartitioner supports nn.Sequential, Bloom-style and GPT-2-style causal LMs"
         assert len(blocks) >= n, "more pipeline stages than transformer blocks"
         costs = [sum(p.numel() for p in blk.parameters()) for blk in blocks]  # embeddings excluded, as in the reference
         b = _balanced_cuts(costs, n)
-        return [BloomStage(model, b[i], b[i + 1], is_first=(i == 0), is_last=(i == n - 1)) for i in range(n)]
+        stage_cls = GPT2Stage if hasattr(model.transformer, "wte") else BloomStage
+        return [stage_cls(model, b[i], b[i + 1], is_first=(i == 0), is_last=(i == n - 1)) for i in range(n)]
 
 
 def get_model_partition(module: nn.Module, policy: PartitionPolicy, parallel_context: ParallelContext) -> nn.Module:
