@@ -12,7 +12,6 @@ supports exactly that.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 
@@ -21,7 +20,6 @@ from torch import nn
 
 from pipegoose_b200.ops import functional as PF
 from pipegoose_b200.ops import kernels as K
-from pipegoose_b200.ops.attention import alibi_attention
 
 
 @dataclass

@@ -16,7 +16,6 @@ import torch
 from torch import nn
 
 from pipegoose_b200.distributed.parallel_context import ParallelContext
-from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
 
 class PartitionPolicy(Enum):

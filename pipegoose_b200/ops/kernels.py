@@ -10,7 +10,6 @@ import math
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 
 from pipegoose_b200.ops import native, use_native
 

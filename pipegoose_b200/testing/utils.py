@@ -8,7 +8,6 @@ from __future__ import annotations
 import os
 import random
 import socket
-from functools import partial
 from typing import Callable
 
 import pytest

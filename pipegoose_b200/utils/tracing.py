@@ -4,7 +4,7 @@ launching stream, synchronised on both sides, max over the ranks of a group."""
 from __future__ import annotations
 
 from contextlib import contextmanager
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 
