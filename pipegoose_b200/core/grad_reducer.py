@@ -272,9 +272,16 @@ class GradReducer:
                     b.work.wait()
         else:
             self.flat.finalize_grads()
+        if self._sync and not self._fused_optimizer_attached():
+            # a stock optimizer (torch.optim.*) reads ``p.grad``: expose the reduced fp32 main grads there
+            self.flat.materialize_grads()
         for hook in self.post_reduce_hooks:
             hook()
         self._reset_pending()
+
+    def _fused_optimizer_attached(self) -> bool:
+        """FusedAdam (alone or inside DistributedOptimizer) consumes ``main_grad`` directly and marks its parameters."""
+        return any(getattr(p, "_pg_fused_optim", False) for p in self.flat.params)
 
     def _reduce_tp_partial(self):
         """Sequence-parallel layers compute gradients of TP-replicated parameters (LayerNorms,

@@ -21,6 +21,8 @@ class FusedAdam(torch.optim.Optimizer):
         params = list(params)
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw)
         super().__init__(params, defaults)
+        for p in params:
+            p._pg_fused_optim = True  # gradients are consumed from ``main_grad``; nobody needs a ``.grad`` copy
         self.flat: Optional[FlatModelState] = flat_state
         self._segments: Optional[List[Tuple[int, int]]] = None  # [(flat_start, flat_end)] owned by this rank
         self._step = 0

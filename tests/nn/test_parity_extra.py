@@ -233,18 +233,19 @@ def run_dp_replicas(rank, world_size, port, state, ids):
     model.load_state_dict(state)
     model = DataParallel(model, ctx).parallelize()
     opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
     for _ in range(2):
         local = ids.chunk(world_size)[rank]
         loss = model(local, labels=local).loss
         opt.zero_grad()
-        loss.backward()
-        if hasattr(model, "_flat_state"):
-            model._flat_state.materialize_grads()
+        loss.backward()  # the reducer exposes the averaged gradients as ``p.grad`` for the stock optimizer
+        assert all(p.grad is not None for p in model.parameters())
         opt.step()
     for name, p in model.named_parameters():
         ref = p.detach().clone()
         dist.broadcast(ref, src=0)
         assert torch.allclose(p.detach(), ref, atol=1e-7), name  # replicas stay bit-identical
+    assert sum(int(not torch.equal(p.detach(), before[n])) for n, p in model.named_parameters()) > 10, "nothing was trained"
     ctx.destroy()
 
 
