@@ -229,6 +229,10 @@ class PipelineEngine:
         if flat is not None:
             flat.hold_grads = False
             flat.zero_grad()
+        # the schedule produces this step's gradients from scratch: a ``.grad`` left over from the previous step
+        # (stock optimizers do not clear it, and zero_grad() only comes after forward) must not be accumulated into
+        for p in self.module.parameters():
+            p.grad = None
         mbs = self._prepare(inputs)
         dev = self._device()
         m = len(mbs)
@@ -337,7 +341,7 @@ class PipelineEngine:
         # by `loss.backward()`, so a `zero_grad()` between forward and backward does not lose them.
         parked = []
         for p in self.module.parameters():
-            if p.grad is not None and getattr(p, "main_grad", None) is None:
+            if p.grad is not None:  # autograd grads, or main grads the data-parallel reducer materialised
                 parked.append((p, p.grad))
                 p.grad = None
         return CausalLMOutput(loss=_InstallGrads.apply(loss.detach().requires_grad_(True), parked), logits=None)

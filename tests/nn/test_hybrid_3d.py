@@ -64,3 +64,50 @@ def test_3d_training_follows_single_process(tp, pp, dp):
         ref_losses.append(total)
     assert ref_losses[-1] < ref_losses[0]
     spawn(run, world_size=tp * pp * dp, tp=tp, pp=pp, dp=dp, n_mb=n_mb, state=state, ids=ids, ref_losses=ref_losses)
+
+
+def run_pp_dp_stock_optimizer(rank, world_size, port, state, ids, ref_losses):
+    """PP x DP with a plain torch optimizer and the canonical loop: the schedule's gradients survive zero_grad()."""
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 2)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    optim = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-1)
+    local = ids.chunk(2)[ctx.get_local_rank(ParallelMode.DATA)]
+    losses = []
+    for _ in range(STEPS):
+        out = model(local, labels=local)
+        optim.zero_grad()
+        out.loss.backward()
+        optim.step()
+        losses.append(out.loss.item())
+    t = torch.tensor(losses)
+    if not ctx.is_last_rank(ParallelMode.PIPELINE):
+        t.zero_()
+    dist.all_reduce(t)
+    mean = (t / 2).tolist()
+    for a, b in zip(mean, ref_losses):
+        assert abs(a - b) < 2e-3, (mean, ref_losses)
+    ctx.destroy()
+
+
+def test_pipeline_x_data_parallel_with_a_stock_optimizer():
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (8, 8))
+    opt = torch.optim.SGD(model.parameters(), lr=1e-1)
+    chunks = [mb for rep in ids.chunk(2) for mb in rep.chunk(2)]
+    ref_losses = []
+    for _ in range(STEPS):
+        opt.zero_grad()
+        total = 0.0
+        for mb in chunks:
+            loss = model(mb, labels=mb).loss / len(chunks)
+            loss.backward()
+            total += loss.item()
+        opt.step()
+        ref_losses.append(total)
+    assert ref_losses[-1] < ref_losses[0]
+    spawn(run_pp_dp_stock_optimizer, world_size=4, state=state, ids=ids, ref_losses=ref_losses)
