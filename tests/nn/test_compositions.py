@@ -1,0 +1,106 @@
+"""Compositions of the wrappers that the single-feature tests do not reach (CPU / gloo):
+* fast Bloom TP x DP with a *stock* torch optimizer behind DistributedOptimizer (generic ZeRO-1 path);
+* Switch-MoE (ExpertParallel) x TP x DP x ZeRO-1 training: the trajectory with experts sharded over 2 ranks equals
+  the trajectory with all experts on one rank."""
+import copy
+import json
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import DataParallel, ExpertParallel, TensorParallel
+from pipegoose_b200.nn.expert_parallel import ExpertLoss, SwitchNoisePolicy, Top1Router
+from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+CFG = dict(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)
+STEPS = 3
+
+
+def run_tp_dp_generic(rank, world_size, port, tp, dp, state, ids, ref_losses):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(torch.optim.Adam(model.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    losses = []
+    for _ in range(STEPS):
+        loss = model(local, labels=local).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        losses.append(loss.item())
+    t = torch.tensor(losses)
+    dist.all_reduce(t)
+    mean = (t / world_size).tolist()
+    for a, b in zip(mean, ref_losses):
+        assert abs(a - b) < 2e-3, (mean, ref_losses)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,dp", [(2, 2), (2, 1)])
+def test_fast_bloom_tp_dp_with_generic_zero1(tp, dp):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    ref_losses = []
+    for _ in range(STEPS):
+        opt.zero_grad()
+        total = 0.0
+        for rep in ids.chunk(dp):
+            loss = model(rep, labels=rep).loss / dp
+            loss.backward()
+            total += loss.item()
+        opt.step()
+        ref_losses.append(total)
+    spawn(run_tp_dp_generic, world_size=tp * dp, tp=tp, dp=dp, state=state, ids=ids, ref_losses=ref_losses)
+
+
+def run_moe(rank, world_size, port, tp, dp, state, gate_state, ids, out_file):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 4, CFG["hidden_size"])
+    router.load_state_dict(gate_state)
+    model = ExpertParallel(model, 4, mapping=[1], router=router, parallel_context=ctx).parallelize()
+    model = TensorParallel(model, ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    model.eval()  # deterministic routing (no Switch noise)
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    loss_fn = ExpertLoss(lambda out: out.loss, aux_weight=0.01, z_weight=0.001)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    losses = []
+    for _ in range(STEPS):
+        out = model(local, labels=local)
+        loss = loss_fn(out)
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        losses.append(loss.item())
+    t = torch.tensor(losses)
+    dist.all_reduce(t)
+    if rank == 0:
+        json.dump((t / world_size).tolist(), open(out_file, "w"))
+    ctx.destroy()
+
+
+def test_moe_sharded_experts_train_like_unsharded_experts(tmp_path):
+    torch.manual_seed(0)
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
+    gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 4, CFG["hidden_size"]).state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    runs = {}
+    for name, (tp, dp) in {"ep1": (1, 2), "ep2": (2, 2)}.items():
+        f = str(tmp_path / f"{name}.json")
+        spawn(run_moe, world_size=tp * dp, tp=tp, dp=dp, state=state, gate_state=gate_state, ids=ids, out_file=f)
+        runs[name] = json.load(open(f))
+    assert runs["ep1"][-1] < runs["ep1"][0]
+    for a, b in zip(runs["ep1"], runs["ep2"]):
+        assert abs(a - b) < 2e-3, runs
