@@ -89,7 +89,84 @@ class TensorParallel(Parallel):
 
     @torch.no_grad()
     def deparallelize(self) -> nn.Module:
-        raise NotImplementedError("re-create the model and load a checkpoint to undo tensor parallelism")
+        """Undo :meth:`parallelize` (unimplemented in the reference, nn/tensor_parallel/tensor_parallel.py:79-82):
+        every rank all-gathers the shards and ends up with the full, unsharded module again (collective)."""
+        module, ctx = self.module, self.parallel_context
+        if ctx.tensor_parallel_size == 1:
+            return module
+        from pipegoose_b200.distributed.functional import all_gather
+        from pipegoose_b200.models.bloom import BloomForCausalLM as FastBloom
+        from pipegoose_b200.nn.tensor_parallel.embedding import ParallelEmbedding
+        from pipegoose_b200.nn.tensor_parallel.layer_norm import LayerNorm
+        from pipegoose_b200.nn.tensor_parallel.linear import ColumnParallelLinear, RowParallelLinear
+
+        def gathered(param: nn.Parameter, dim: int, keep: Optional[int] = None) -> nn.Parameter:
+            full = all_gather(param.data.contiguous(), dim=dim, parallel_context=ctx, parallel_mode=ParallelMode.TENSOR)
+            if keep is not None:  # drop the zero padding that made the vocabulary divisible
+                full = full.narrow(dim, 0, keep).contiguous()
+            return nn.Parameter(full, requires_grad=param.requires_grad)
+
+        if isinstance(module, FastBloom) and getattr(module, "tp", None) is not None:
+            t, cfg = module.transformer, module.config
+            table = gathered(t.word_embeddings.weight, 0, keep=cfg.vocab_size)
+            table._pg_grad_contribs = 2
+            t.word_embeddings.weight = table
+            module.lm_head.weight = table
+            module.vocab_start, module.tp = 0, None
+            for block in t.h:
+                attn, mlp = block.self_attention, block.mlp
+                attn.query_key_value.weight = gathered(attn.query_key_value.weight, 0)
+                attn.query_key_value.bias = gathered(attn.query_key_value.bias, 0)
+                attn.dense.weight = gathered(attn.dense.weight, 1)
+                attn.tp_rank = 0
+                attn._slopes_cache = {}
+                if hasattr(mlp, "dense_h_to_4h"):
+                    mlp.dense_h_to_4h.weight = gathered(mlp.dense_h_to_4h.weight, 0)
+                    mlp.dense_h_to_4h.bias = gathered(mlp.dense_h_to_4h.bias, 0)
+                    mlp.dense_4h_to_h.weight = gathered(mlp.dense_4h_to_h.weight, 1)
+                block.tp = None
+            for p in module.parameters():
+                if hasattr(p, "tp_partial_grad"):
+                    del p.tp_partial_grad
+            if hasattr(module, "_pg_tp_grad_sync"):
+                del module._pg_tp_grad_sync
+            return module
+
+        # class-swap path (any model): gather the slices and give the leaves their torch classes back
+        emb = module.get_input_embeddings() if hasattr(module, "get_input_embeddings") else None
+        vocab = getattr(getattr(module, "config", None), "vocab_size", None)
+        tied_table = None
+        for _, leaf in self._get_leaf_modules(module):
+            if isinstance(leaf, ParallelEmbedding):
+                leaf.weight = gathered(leaf.weight, 0, keep=vocab)
+                leaf.num_embeddings = leaf.weight.shape[0]
+                for attr in ("vocab_start_idx", "vocab_end_idx", "world_size", "parallel_context"):
+                    if hasattr(leaf, attr):
+                        delattr(leaf, attr)
+                leaf.__class__ = nn.Embedding
+                if leaf is emb:
+                    tied_table = leaf.weight
+        for _, leaf in self._get_leaf_modules(module):
+            if isinstance(leaf, ColumnParallelLinear):
+                if getattr(leaf, "_pg_tied_to_embedding", False) and tied_table is not None:
+                    leaf.weight = tied_table
+                else:
+                    is_head = leaf.weight.shape[0] * ctx.tensor_parallel_size != getattr(leaf, "out_features", -1)
+                    leaf.weight = gathered(leaf.weight, 0, keep=leaf.out_features if is_head else None)
+                if leaf.bias is not None:
+                    leaf.bias = gathered(leaf.bias, 0)
+                leaf.__class__ = nn.Linear
+            elif isinstance(leaf, RowParallelLinear):
+                leaf.weight = gathered(leaf.weight, 1)
+                leaf.__class__ = nn.Linear
+            elif isinstance(leaf, LayerNorm):
+                leaf.__class__ = nn.LayerNorm
+            else:
+                continue
+            for attr in ("gather_output", "parallel_context"):
+                if attr in leaf.__dict__:
+                    delattr(leaf, attr)
+        return module
 
 
 def _slice_param(param: nn.Parameter, ctx, dim: int) -> nn.Parameter:

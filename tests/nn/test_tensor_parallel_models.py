@@ -171,3 +171,43 @@ def test_tensor_parallel_without_data_parallel_trains_like_a_single_process():
         opt.step()
         ref_losses.append(loss.item())
     spawn(run_tp_only_training, world_size=2, state=state, ids=ids, ref_losses=ref_losses, ref_ln_grad=ref_ln_grad)
+
+
+def run_deparallelize(rank, world_size, port, fast, state, ids, ref_logits):
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    if fast:
+        model = BloomForCausalLM(BloomConfig(vocab_size=99, hidden_size=32, n_layer=2, n_head=4))
+    else:
+        from transformers import BloomConfig as HFConfig
+        from transformers import BloomForCausalLM as HFBloom
+
+        model = HFBloom(HFConfig(vocab_size=99, hidden_size=32, n_layer=2, n_head=4)).eval()
+    model.load_state_dict(state)
+    wrapper = TensorParallel(model, ctx)
+    model = wrapper.parallelize()
+    assert model.lm_head.weight.shape[0] < 99  # sharded
+    model = wrapper.deparallelize()
+    got = {k: v for k, v in model.state_dict().items()}
+    for k, v in state.items():
+        assert got[k].shape == v.shape and torch.equal(got[k], v), k
+    assert model.lm_head.weight is model.get_input_embeddings().weight  # still tied
+    with torch.no_grad():
+        logits = model(ids).logits
+    assert torch.allclose(logits, ref_logits, atol=1e-5)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_tensor_parallel_deparallelize_restores_the_model(fast):
+    torch.manual_seed(0)
+    if fast:
+        model = BloomForCausalLM(BloomConfig(vocab_size=99, hidden_size=32, n_layer=2, n_head=4))
+    else:
+        from transformers import BloomConfig as HFConfig
+        from transformers import BloomForCausalLM as HFBloom
+
+        model = HFBloom(HFConfig(vocab_size=99, hidden_size=32, n_layer=2, n_head=4)).eval()
+    ids = torch.randint(0, 99, (2, 8))
+    with torch.no_grad():
+        ref = model(ids).logits
+    spawn(run_deparallelize, world_size=2, fast=fast, state=copy.deepcopy(model.state_dict()), ids=ids, ref_logits=ref)
