@@ -1,3 +1,4 @@
+"""Expert-parallel helpers (parity: reference nn/expert_parallel/utils.py:5-8)."""
 from pipegoose_b200.distributed.parallel_context import ParallelContext
 from pipegoose_b200.distributed.parallel_mode import ParallelMode
 

@@ -1,3 +1,4 @@
+"""Pipeline helpers (parity: reference nn/pipeline_parallel/_utils.py:7-22)."""
 from pipegoose_b200.distributed.parallel_context import ParallelContext
 from pipegoose_b200.distributed.parallel_mode import ParallelMode
 

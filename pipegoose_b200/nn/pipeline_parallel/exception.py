@@ -1,3 +1,4 @@
+"""Pipeline exceptions (parity: reference nn/pipeline_parallel/exception.py:1-14, plus PipelineScheduleError)."""
 class PipelineGradientFlowError(Exception):
     """Gradients did not flow to a stage boundary."""
 

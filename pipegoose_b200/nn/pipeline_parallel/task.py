@@ -1,3 +1,4 @@
+"""Schedule entry (parity: reference nn/pipeline_parallel/task.py:6-10)."""
 from dataclasses import dataclass
 
 from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType

@@ -1,3 +1,4 @@
+"""Trainer state (parity: reference trainer/state.py; the reference Trainer never updates it, this one does)."""
 from dataclasses import dataclass
 from enum import Enum, auto
 
