@@ -1,0 +1,135 @@
+"""More compositions (CPU / gloo): checkpoints of pipeline stages, FusedAdam's AdamW / weight-decay modes against
+torch, 🤗 Bloom under TensorParallel (class-swap) x PipelineParallel, experts with tensor parallelism enabled."""
+import copy
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import ExpertParallel, PipelineParallel, TensorParallel
+from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
+from pipegoose_b200.nn.utils import from_pretrained, save_pretrained
+from pipegoose_b200.optim import FusedAdam
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+CFG = dict(vocab_size=96, hidden_size=32, n_layer=4, n_head=4)
+
+
+def run_pp_checkpoint(rank, world_size, port, state, ckp_path):
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    stage = model._pg_pipeline_stage
+    want = {k: v.clone() for k, v in stage.state_dict().items()}
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    assert os.path.exists(os.path.join(ckp_path, f"pytorch_model_tp_0_pp_{rank}.bin"))
+    with torch.no_grad():
+        for p in stage.parameters():
+            p.zero_()
+    from_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    for k, v in stage.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    ctx.destroy()
+
+
+def test_checkpoint_of_pipeline_stages(tmp_path):
+    torch.manual_seed(0)
+    spawn(run_pp_checkpoint, world_size=2, state=BloomForCausalLM(BloomConfig(**CFG)).state_dict(),
+          ckp_path=str(tmp_path / "ckpt"))
+
+
+@pytest.mark.parametrize("adamw,wd", [(False, 0.0), (False, 0.1), (True, 0.1)])
+def test_fused_adam_modes_match_torch(adamw, wd):
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    mine = copy.deepcopy(ref)
+    topt = (torch.optim.AdamW if adamw else torch.optim.Adam)(ref.parameters(), lr=1e-2, weight_decay=wd)
+    fopt = FusedAdam(mine.parameters(), lr=1e-2, weight_decay=wd, adamw=adamw)
+    x = torch.randn(16, 8)
+    for _ in range(4):
+        for model, opt in ((ref, topt), (mine, fopt)):
+            opt.zero_grad()
+            model(x).pow(2).mean().backward()
+            opt.step()
+    for a, b in zip(ref.parameters(), mine.parameters()):
+        assert torch.allclose(a, b, atol=1e-5)
+
+
+def _hf_bloom():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    return HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+
+
+def run_hf_tp_pp(rank, world_size, port, state, ids, ref_loss):
+    ctx = init_parallel_context(rank, world_size, port, 2, 2, 1)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    out = model(ids, labels=ids)
+    if ctx.is_last_rank(ParallelMode.PIPELINE):
+        assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+    out.loss.backward()
+    grads = [p.grad for p in model._pg_pipeline_stage.parameters()]
+    assert all(g is not None and torch.isfinite(g).all() for g in grads)
+    ctx.destroy()
+
+
+def test_hf_bloom_tensor_x_pipeline_parallel_loss():
+    torch.manual_seed(0)
+    model = _hf_bloom()
+    ids = torch.randint(0, 96, (4, 8))
+    loss = torch.stack([model(input_ids=c, labels=c).loss for c in ids.chunk(2)]).mean()
+    spawn(run_hf_tp_pp, world_size=4, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach())
+
+
+def run_experts_with_tp(rank, world_size, port, state, gate_state, ids, ref_loss):
+    """``enable_tensor_parallelism=True``: every rank holds ALL experts and the experts' linears are tensor-parallel
+    (reference nn/expert_parallel/layers.py:28-31) — the loss equals the single-process MoE model's."""
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 2, 32)
+    router.load_state_dict(gate_state)
+    model = ExpertParallel(model, 2, mapping=[0], router=router, enable_tensor_parallelism=True,
+                           parallel_context=ctx).parallelize()
+    layer = model.transformer.h[0].mlp
+    assert len(layer.experts.experts if hasattr(layer.experts, "experts") else layer.experts) == 2
+    model = TensorParallel(model, ctx).parallelize()
+    model.eval()
+    with torch.no_grad():
+        loss = model(input_ids=ids, labels=ids).loss
+    assert torch.allclose(loss, ref_loss, atol=1e-5), (loss, ref_loss)
+    ctx.destroy()
+
+
+def test_expert_layer_with_tensor_parallel_experts(tmp_path):
+    torch.manual_seed(0)
+    model = _hf_bloom()
+    state = copy.deepcopy(model.state_dict())
+    gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 2, 32).state_dict())
+    ids = torch.randint(0, 96, (2, 8))
+    f = str(tmp_path / "ref.pt")
+
+    def ref_run(rank, world_size, port):
+        ctx = init_parallel_context(rank, world_size, port, 1, 1, 1)
+        m = _hf_bloom()
+        m.load_state_dict(state)
+        r = Top1Router(SwitchNoisePolicy(), 2, 32)
+        r.load_state_dict(gate_state)
+        m = ExpertParallel(m, 2, mapping=[0], router=r, enable_tensor_parallelism=True, parallel_context=ctx).parallelize()
+        m.eval()
+        with torch.no_grad():
+            torch.save(m(input_ids=ids, labels=ids).loss, f)
+        ctx.destroy()
+
+    # the single-process MoE reference runs in-process through a world-size-1 context
+    port = 29000 + os.getpid() % 2000
+    ref_run(0, 1, port)
+    spawn(run_experts_with_tp, world_size=2, state=state, gate_state=gate_state, ids=ids, ref_loss=torch.load(f))
