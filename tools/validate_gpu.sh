@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# One-call GPU validation (run under gpurun; pass the number of GPUs of the box):
+#   gpurun --gpus 4 --timeout 1200 -- 'bash tools/validate_gpu.sh 4'
+# Steps (each writes to gpurun_out/): kernel numerics + GEMM perf table, the gpu test-suite, bench at every
+# power-of-two N up to the box size, the fused-TP micro-bench (N>=2), a per-kernel step breakdown (N=1, ncu).
+# Box-to-box variance is ~10 %: compare numbers from ONE call only.
+set -uo pipefail
+N="${1:-1}"
+mkdir -p gpurun_out
+echo "== gemm_check (correctness of every layout / epilogue / CTA-pair variant + perf vs cuBLAS)"
+timeout 400 python tools/gemm_check.py epi > gpurun_out/gemm_check.log 2>&1; grep -c "^OK" gpurun_out/gemm_check.log; grep "FAIL" gpurun_out/gemm_check.log | head; grep "cta1:" gpurun_out/gemm_check.log
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for n in 1 2 4 8; do
+  if [ "$n" -le "$N" ]; then
+    echo "== bench N=$n"
+    python bench.py --gpus "$n" --steps 10 --warmup 3 | tee "gpurun_out/bench_${n}gpu.json" | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print(d['n_gpus'], 'GPUs', round(d['ms_per_step'], 2), 'ms/step', round(d['value']), 'tok/s e2e', round(d['e2e']['ms_per_step'], 2), d['clocks'])
+"
+  fi
+done
+if [ "$N" -ge 2 ]; then
+  echo "== fused TP kernels vs NCCL + GEMM (T=2)"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/tp_bench.py 2>&1 | grep "^{" | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['op'], 'fused', round(d['fused_ms'] * 1e3, 1), 'us  nccl+gemm', round(d['nccl_plus_gemm_ms'] * 1e3, 1), ' gemm only', round(d['gemm_only_ms'] * 1e3, 1), ' frac of roofline', round(d['fused_frac_of_roofline'], 2))
+"
+  echo "== TP2 step breakdown (torch profiler, diagnosis only)"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -24
+fi
+echo "== 1-GPU step breakdown (ncu launch list)"
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py > /dev/null 2>&1
+python tools/step_profile.py --aggregate gpurun_out/step_launches.csv gpurun_out/step_breakdown.json | head -22
