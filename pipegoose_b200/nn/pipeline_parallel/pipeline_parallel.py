@@ -38,8 +38,42 @@ class PipelineParallel(Parallel):
             self._save_metadata(module, ctx)
         return module
 
+    @torch.no_grad()
     def deparallelize(self) -> nn.Module:
-        raise NotImplementedError
+        """Undo :meth:`parallelize`: every stage broadcasts its parameters over the PIPELINE group so that each rank
+        holds the whole module again, and ``module.forward`` is the model's own forward (collective; unimplemented
+        in the reference)."""
+        import torch.distributed as dist
+
+        from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+        module, ctx = self.module, self.parallel_context
+        if ctx.pipeline_parallel_size == 1 or not hasattr(module, "_pg_pipeline_stage"):
+            return module
+        group = ctx.get_group(ParallelMode.PIPELINE)
+        ranks = ctx.get_ranks_in_group(ParallelMode.PIPELINE)
+        stage_ids = {id(p) for p in module._pg_pipeline_stage.parameters()}
+        mine = {n: tuple(p.shape) for n, p in module.named_parameters() if id(p) in stage_ids}
+        owned = [None] * len(ranks)
+        dist.all_gather_object(owned, mine, group=group)
+        backend_dev = ctx.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        for name, p in module.named_parameters():
+            owner = next(i for i, shapes in enumerate(owned) if name in shapes)  # tied table: the first stage
+            shape = owned[owner][name]
+            if id(p) in stage_ids and tuple(p.shape) == shape:
+                buf = p.data.to(backend_dev)
+            else:
+                buf = torch.empty(shape, dtype=p.dtype, device=backend_dev)
+            dist.broadcast(buf, src=ranks[owner], group=group)
+            if not (id(p) in stage_ids and tuple(p.shape) == shape):
+                p.data = buf.to(p.device if p.numel() > 0 else (ctx.device if backend_dev.type == "cuda" else "cpu"))
+                p.requires_grad_(True)
+        for attr in ("_pg_pipeline_stage", "_pg_pipeline_engine"):
+            if hasattr(module, attr):
+                delattr(module, attr)
+        if "forward" in module.__dict__:
+            del module.__dict__["forward"]  # back to the class's forward
+        return module
 
 
 def _drop_foreign_parameters(module: nn.Module, stage: nn.Module):

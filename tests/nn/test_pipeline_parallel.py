@@ -221,3 +221,30 @@ def test_partitioner_and_engine_on_hf_models(family, pp):
     loss.backward()
     spawn(run_hf_partitioner, world_size=pp, pp=pp, family=family, state=copy.deepcopy(model.state_dict()), ids=ids,
           ref_logits=ref_logits, ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
+
+
+def run_pp_deparallelize(rank, world_size, port, pp, state, ids, ref_logits):
+    ctx = init_parallel_context(rank, world_size, port, 1, pp, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    wrapper = PipelineParallel(model, num_microbatches=2, parallel_context=ctx)
+    model = wrapper.parallelize()
+    assert sum(p.numel() == 0 for p in model.parameters()) > 0  # foreign stages were dropped
+    model(ids, labels=ids)  # one scheduled step still works
+    model = wrapper.deparallelize()
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, state[k]), k
+    assert model.lm_head.weight is model.transformer.word_embeddings.weight
+    with torch.no_grad():
+        assert torch.allclose(model(ids).logits, ref_logits, atol=1e-5)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("pp", [2, 4])
+def test_pipeline_parallel_deparallelize_restores_the_model(pp):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    ids = torch.randint(0, 96, (4, 8))
+    with torch.no_grad():
+        ref = model(ids).logits
+    spawn(run_pp_deparallelize, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_logits=ref)
