@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import itertools
 import random
+import threading
 import string
 from abc import ABC, abstractmethod
 from enum import Enum, auto
@@ -45,6 +46,7 @@ class Job(ABC):
         self._output: Optional[Package] = None
         self._key = _make_key()
         self.error: Optional[BaseException] = None
+        self._finished = threading.Event()  # set when compute() returned or raised
         self.add_cbs(cbs)
         self._run_callback(CallbackEvent.AFTER_CREATE)
 
@@ -82,6 +84,12 @@ class Job(ABC):
             self.error = e
             self._run_callback(CallbackEvent.ON_FAILURE)
             raise
+        finally:
+            self._finished.set()
+
+    def wait(self, timeout: Optional[float] = None) -> bool:
+        """Block until a worker finished (or failed) this job."""
+        return self._finished.wait(timeout)
 
     @abstractmethod
     def run_compute(self):

@@ -38,6 +38,7 @@ class Worker(threading.Thread):
         while True:
             job = self._selected_jobs.get()
             if job is _STOP:
+                self._selected_jobs.task_done()
                 return
             with self.lock:
                 self._running = True
@@ -51,6 +52,7 @@ class Worker(threading.Thread):
                     self._failed.append((job, e))
                 finally:
                     self._running = False
+                    self._selected_jobs.task_done()
 
 
 class JobSelector(threading.Thread):
@@ -65,8 +67,10 @@ class JobSelector(threading.Thread):
         while True:
             job = self._pending_jobs.get()
             if job is _STOP:
+                self._pending_jobs.task_done()
                 return
-            self._selected_jobs.put(job)
+            self._selected_jobs.put(job)   # counted as unfinished in `selected` BEFORE it leaves `pending`
+            self._pending_jobs.task_done()
 
 
 class WorkerPoolWatcher(threading.Thread):
@@ -137,11 +141,13 @@ class WorkerManager:
         """Block until both queues are drained and no worker is running."""
         import time
 
+        # Queue.unfinished_tasks counts a job from put() until the consumer's task_done(): a job is never
+        # "nowhere" between the selector and a worker, so this cannot report idle while a job is in flight
         end = time.monotonic() + timeout
         while time.monotonic() < end:
-            if self._pending_jobs.empty() and self._selected_jobs.empty() and not any(w.is_running for w in self._worker_pool):
+            if self._pending_jobs.unfinished_tasks == 0 and self._selected_jobs.unfinished_tasks == 0:
                 return True
-            time.sleep(0.005)
+            time.sleep(0.002)
         return False
 
     def destroy(self):

@@ -16,10 +16,14 @@ from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType, get_sch
 
 class PipelineParallel(Parallel):
     def __init__(self, module: nn.Module, num_microbatches: int, parallel_context: ParallelContext,
-                 scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B):
+                 scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B, runtime: str = "static"):
+        """``runtime``: ``"static"`` (default) — schedule tables + batched p2p (pipeline_engine.py); ``"jobs"`` — the
+        reference's execution model: jobs from packages, worker threads, progress tracker (job_engine.py, GPipe)."""
         super().__init__(module, parallel_context)
+        assert runtime in ("static", "jobs")
         self.num_microbatches = num_microbatches
-        self.scheduler_type = scheduler_type
+        self.scheduler_type = scheduler_type if runtime == "static" else SchedulerType.GPIPE
+        self.runtime = runtime
 
     @torch.no_grad()
     def parallelize(self) -> nn.Module:
@@ -29,7 +33,12 @@ class PipelineParallel(Parallel):
             stage = partitions[get_partition_idx(ctx)]
             scheduler = get_scheduler(self.scheduler_type)(self.num_microbatches, ctx.pipeline_parallel_size)
             pipeline_context = PipelineContext(scheduler, ctx)
-            engine = PipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
+            if self.runtime == "jobs":
+                from pipegoose_b200.nn.pipeline_parallel.job_engine import JobPipelineEngine
+
+                engine = JobPipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
+            else:
+                engine = PipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
             engine.tied_group, engine.tied_param = _tied_embedding_group(module, ctx)
             _drop_foreign_parameters(module, stage)
             module._pg_pipeline_stage = stage

@@ -100,6 +100,10 @@ class ProgressTracker(Handshake):
     def initiate(self, progress: Progress):
         """Publish the table of tasks per clock cycle (master only; other ranks pick it up lazily)."""
         if self.parallel_context.get_global_rank() == self._global_master():
+            # the previous table must be complete on every rank before a new one replaces it: a slower stage may
+            # still be confirming tasks of the old schedule
+            if self._load() and len(self._progress) > 0:
+                self.wait_for_clock(len(self._progress) - 1)
             # a re-initiation (e.g. the backward schedule after the forward one) starts a new round
             while self._store.check([self._k("init")]):
                 self._round += 1
@@ -115,18 +119,33 @@ class ProgressTracker(Handshake):
     def _sync_round(self):
         if self._store.check(["round"]):
             r = int(self._store.get("round"))
-            if r != self._round:
+            if r > self._round:  # rounds only move forward (the key is written after the table it announces)
                 self._round, self._progress, self._clock_idx = r, None, 0
 
     def is_initiated(self) -> bool:
         self._sync_round()
         return self._load()
 
+    def wait_initiated(self, round_idx: int, timeout_s: float = 60.0):
+        """Block until the master published the table of round ``round_idx`` (0 for the first ``initiate``)."""
+        import datetime
+
+        self._store.wait([f"r{round_idx}/init"], datetime.timedelta(seconds=timeout_s))
+        if self._round != round_idx:
+            self._round, self._progress, self._clock_idx = round_idx, None, 0
+        assert self._load()
+
     def confirm(self, task) -> None:
-        """Mark ``task`` of the current clock cycle as done, for every rank."""
+        """Mark ``task`` as done, for every rank.  A task that belongs to a later clock cycle than the current one
+        (a stage running ahead of the others) first waits until the cycles before it are complete."""
         assert self.is_initiated(), "the progress tracker was not initiated"
         self._refresh()
         clock = self._clock_idx
+        if clock >= len(self._progress) or task not in self._progress[clock]:
+            later = [c for c in range(clock + 1, len(self._progress)) if task in self._progress[c]]
+            assert later, f"task {task!r} is not part of clock cycle {clock} or any later one"
+            self.wait_for_clock(later[0] - 1)
+            clock = self._clock_idx
         assert task in self._progress[clock], f"task {task!r} is not part of clock cycle {clock}"
         self._store.set(self._k(f"c{clock}/{task!r}"), "1")
         n = self._store.add(self._k(f"n{clock}"), 1)

@@ -304,3 +304,43 @@ def run_handshake(rank, world_size, port, tp, pp, dp):
 
 def test_parallel_group_handshake():
     spawn(run_handshake, world_size=4, tp=2, pp=1, dp=2)
+
+
+# ------------------------------------------------------------------------------------------ engine made of jobs
+def run_job_engine(rank, world_size, port, pp, state, ids, ref_loss, ref_grads):
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import PipelineParallel
+
+    ctx = init_parallel_context(rank, world_size, port, 1, pp, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=4, parallel_context=ctx, runtime="jobs").parallelize()
+    engine = model._pg_pipeline_engine
+    for _ in range(2):  # a second step re-uses the workers and starts new tracker rounds
+        out = model(ids, labels=ids)
+        if rank == pp - 1:
+            assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+        for p in model._pg_pipeline_stage.parameters():
+            assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
+    # the tracker saw every task of the last (backward) schedule (earlier stages may still be finishing theirs)
+    engine.tracker.wait_for_clock(len(engine.tracker.progress) - 1)
+    assert all(all(done.values()) for done in engine.tracker.progress.values())
+    assert not engine.worker_manager.failed_jobs
+    engine.destroy()
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("pp", [2, 4])
+def test_job_runtime_engine_matches_sequential_training_step(pp):
+    import copy
+
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    ids = torch.randint(0, 96, (8, 8))
+    loss = torch.stack([model(c, labels=c).loss for c in ids.chunk(4)]).mean()
+    loss.backward()
+    spawn(run_job_engine, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach(),
+          ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
