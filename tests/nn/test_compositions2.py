@@ -133,3 +133,47 @@ def test_expert_layer_with_tensor_parallel_experts(tmp_path):
     port = 29000 + os.getpid() % 2000
     ref_run(0, 1, port)
     spawn(run_experts_with_tp, world_size=2, state=state, gate_state=gate_state, ids=ids, ref_loss=torch.load(f))
+
+
+def run_moe_pp(rank, world_size, port, state, gate_state, ids, ref_loss):
+    """Switch-MoE blocks inside pipeline stages (ExpertParallel -> PipelineParallel): the scheduled step computes the
+    same language-model loss as the unpartitioned MoE model."""
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"])
+    router.load_state_dict(gate_state)
+    model = ExpertParallel(model, 2, mapping=[0, 3], router=router, parallel_context=ctx).parallelize()
+    model.eval()
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    out = model(ids, labels=ids)
+    if ctx.is_last_rank(ParallelMode.PIPELINE):
+        assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+    out.loss.backward()
+    grads = [p.grad for p in model._pg_pipeline_stage.parameters() if p.requires_grad]
+    assert any(g is not None and g.abs().sum() > 0 for g in grads)
+    assert all(g is None or torch.isfinite(g).all() for g in grads)
+    ctx.destroy()
+
+
+def test_moe_blocks_inside_pipeline_stages(tmp_path):
+    torch.manual_seed(0)
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
+    gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"]).state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    f = str(tmp_path / "ref.pt")
+
+    def ref_run(port):
+        ctx = init_parallel_context(0, 1, port, 1, 1, 1)
+        m = BloomForCausalLM(BloomConfig(**CFG))
+        m.load_state_dict(state)
+        r = Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"])
+        r.load_state_dict(gate_state)
+        m = ExpertParallel(m, 2, mapping=[0, 3], router=r, parallel_context=ctx).parallelize()
+        m.eval()
+        with torch.no_grad():
+            torch.save(torch.stack([m(c, labels=c).loss for c in ids.chunk(2)]).mean(), f)
+        ctx.destroy()
+
+    ref_run(31000 + os.getpid() % 2000)
+    spawn(run_moe_pp, world_size=2, state=state, gate_state=gate_state, ids=ids, ref_loss=torch.load(f))
