@@ -758,8 +758,10 @@ static int launch_att_fwd(const CUtensorMap& tm, const AttFwdArgs& a, cudaStream
   return 0;
 }
 
+// softmax_scale <= 0: 1/sqrt(D).  An explicit scale lets a head that was zero-padded to a supported width (e.g. D=80
+// -> 128: the padded columns contribute nothing to Q.K) keep the scale of its true width.
 extern "C" int pg_attention_fwd(const void* qkv, const float* slopes, void* out, float* lse, int B, int S, int H,
-                                int D, cudaStream_t s) {
+                                int D, float softmax_scale, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   CUtensorMap tm;
   if (att_tmap(&tm, qkv, static_cast<uint64_t>(B) * S, static_cast<uint64_t>(H) * 3 * D) != 0) return -1;
@@ -769,7 +771,7 @@ extern "C" int pg_attention_fwd(const void* qkv, const float* slopes, void* out,
   a.slopes = slopes;
   a.B = B; a.S = S; a.H = H;
   a.ld_out = H * D;
-  a.scale_log2 = kLog2e / sqrtf(static_cast<float>(D));
+  a.scale_log2 = kLog2e * (softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf(static_cast<float>(D)));
   return D == 64 ? launch_att_fwd<64>(tm, a, s) : launch_att_fwd<128>(tm, a, s);
 }
 
@@ -790,7 +792,7 @@ static int launch_att_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const A
 // dq_acc: fp32 workspace [B*S, H*D]; delta: fp32 [B, H, S]
 extern "C" int pg_attention_bwd(const void* qkv, const float* slopes, const void* out, const float* lse,
                                 const void* dout, void* dqkv, float* dq_acc, float* delta, int B, int S, int H,
-                                int D, cudaStream_t s) {
+                                int D, float softmax_scale, cudaStream_t s) {
   if (D != 64 && D != 128) return -1;
   const int64_t rows = static_cast<int64_t>(B) * S;
   CUtensorMap tq, tdo;
@@ -806,7 +808,7 @@ extern "C" int pg_attention_bwd(const void* qkv, const float* slopes, const void
   a.lse = lse; a.delta = delta; a.slopes = slopes; a.dq_acc = dq_acc;
   a.dqkv = (__nv_bfloat16*)dqkv;
   a.B = B; a.S = S; a.H = H;
-  a.scale = 1.0f / sqrtf(static_cast<float>(D));
+  a.scale = softmax_scale > 0.f ? softmax_scale : 1.0f / sqrtf(static_cast<float>(D));
   a.scale_log2 = a.scale * kLog2e;
   const int rc = D == 64 ? launch_att_bwd<64>(tq, tdo, a, s) : launch_att_bwd<128>(tq, tdo, a, s);
   if (rc != 0) return rc;

@@ -228,22 +228,23 @@ void accum_bf16_to_f32(const torch::Tensor& src, torch::Tensor dst, double scale
 
 
 void attention_fwd(const torch::Tensor& qkv, const torch::Tensor& slopes, torch::Tensor out, torch::Tensor lse,
-                   int64_t B, int64_t S, int64_t H, int64_t D) {
+                   int64_t B, int64_t S, int64_t H, int64_t D, double softmax_scale) {
   PG_CUDA(qkv); PG_BF16(qkv); PG_CUDA(out); PG_BF16(out); PG_CUDA(slopes); PG_F32(slopes); PG_CUDA(lse); PG_F32(lse);
   c10::cuda::CUDAGuard guard(qkv.device());
   TORCH_CHECK(qkv.numel() == B * S * H * 3 * D && out.numel() == B * S * H * D && lse.numel() == B * H * S && slopes.numel() == H, "attention_fwd: shape mismatch");
-  TORCH_CHECK(pg_attention_fwd(qkv.data_ptr(), slopes.data_ptr<float>(), out.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, cur_stream()) == 0, "attention_fwd failed");
+  TORCH_CHECK(pg_attention_fwd(qkv.data_ptr(), slopes.data_ptr<float>(), out.data_ptr(), lse.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, (float)softmax_scale, cur_stream()) == 0, "attention_fwd failed");
 }
 
 void attention_bwd(const torch::Tensor& qkv, const torch::Tensor& slopes, const torch::Tensor& out, const torch::Tensor& lse,
-                   const torch::Tensor& dout, torch::Tensor dqkv, int64_t B, int64_t S, int64_t H, int64_t D) {
+                   const torch::Tensor& dout, torch::Tensor dqkv, int64_t B, int64_t S, int64_t H, int64_t D,
+                   double softmax_scale) {
   PG_CUDA(qkv); PG_BF16(qkv); PG_CUDA(out); PG_BF16(out); PG_CUDA(dout); PG_BF16(dout); PG_CUDA(dqkv); PG_BF16(dqkv); PG_CUDA(lse); PG_F32(lse);
   c10::cuda::CUDAGuard guard(qkv.device());
   TORCH_CHECK(dout.numel() == out.numel() && dqkv.numel() == qkv.numel(), "attention_bwd: shape mismatch");
   auto dq_acc = torch::empty({B * S, H * D}, qkv.options().dtype(torch::kFloat32));
   auto delta = torch::empty({B, H, S}, qkv.options().dtype(torch::kFloat32));
   TORCH_CHECK(pg_attention_bwd(qkv.data_ptr(), slopes.data_ptr<float>(), out.data_ptr(), lse.data_ptr<float>(), dout.data_ptr(), dqkv.data_ptr(),
-                               dq_acc.data_ptr<float>(), delta.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, cur_stream()) == 0, "attention_bwd failed");
+                               dq_acc.data_ptr<float>(), delta.data_ptr<float>(), (int)B, (int)S, (int)H, (int)D, (float)softmax_scale, cur_stream()) == 0, "attention_bwd failed");
 }
 
 void moe_route(const torch::Tensor& x, const torch::Tensor& wg, const c10::optional<torch::Tensor>& bg,
@@ -346,8 +347,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adam_step", &adam_step);
   m.def("sgd_step", &sgd_step);
   m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
-  m.def("attention_fwd", &attention_fwd);
-  m.def("attention_bwd", &attention_bwd);
+  m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("slopes"), py::arg("out"), py::arg("lse"), py::arg("B"),
+        py::arg("S"), py::arg("H"), py::arg("D"), py::arg("softmax_scale") = 0.0);
+  m.def("attention_bwd", &attention_bwd, py::arg("qkv"), py::arg("slopes"), py::arg("out"), py::arg("lse"), py::arg("dout"),
+        py::arg("dqkv"), py::arg("B"), py::arg("S"), py::arg("H"), py::arg("D"), py::arg("softmax_scale") = 0.0);
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("symm_alloc", &symm_alloc);
