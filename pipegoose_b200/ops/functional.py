@@ -21,6 +21,14 @@ import torch
 from pipegoose_b200.ops import kernels as K
 
 
+# lm_head under tensor parallelism through the fused all-gather->GEMM / GEMM->reduce-scatter kernels instead of NCCL
+# around a plain GEMM.  Written without GPU access: off until a 2-GPU numerics run (tests/test_gpu_multi.py::
+# test_tp2_bloom_matches_single_gpu with PIPEGOOSE_B200_FUSED_LM_HEAD=1) has confirmed it.
+import os as _os
+
+_FUSED_LM_HEAD = _os.environ.get("PIPEGOOSE_B200_FUSED_LM_HEAD", "0") == "1"
+
+
 def _main_grad(p: Optional[torch.Tensor]):
     return getattr(p, "main_grad", None) if p is not None else None
 
@@ -374,9 +382,16 @@ class LMHeadCrossEntropy(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp):
-        ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
-        ln_full = tp.all_gather_rows(ln) if tp is not None else ln
-        logits = K.gemm_nt(ln_full, table)  # [M, V/T]
+        fused = tp is not None and tp.fused and _FUSED_LM_HEAD
+        if fused:
+            # all-gather -> GEMM like every other column-parallel linear (LN writes into the gather staging buffer)
+            stage = tp.ag_input_buffer(x.shape[0], x.shape[1])
+            ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
+            logits, ln_full = tp.ag_gemm(ln, table)
+        else:
+            ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
+            ln_full = tp.all_gather_rows(ln) if tp is not None else ln
+            logits = K.gemm_nt(ln_full, table)  # [M, V/T]
         tgt = labels.reshape(-1)
         stats = K.ce_local_stats(logits, tgt, vocab_start)
         if tp is not None:
@@ -401,9 +416,12 @@ class LMHeadCrossEntropy(torch.autograd.Function):
         scale = (dloss.float() / n_valid).reshape(1)
         K.ce_finalize(logits, tgt, gstats, ctx.vocab_start, scale, ctx.ignore_index, write_grad=True)
         dlogits = logits
-        dln_full = K.gemm_nn(dlogits, table)
+        if tp is not None and tp.fused and _FUSED_LM_HEAD:
+            dln = tp.gemm_rs_nn(dlogits, table)  # GEMM -> reduce-scatter over NVLink, no [M, h] NCCL round trip
+        else:
+            dln_full = K.gemm_nn(dlogits, table)
+            dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
         dtable = _wgrad(dlogits, ln_full, table)
-        dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
         dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd)
         return dx, dgamma, dbeta, dtable, None, None, None, None, None
 
