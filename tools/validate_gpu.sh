@@ -29,6 +29,17 @@ import sys, json
 for l in sys.stdin:
     d = json.loads(l); print(d['op'], 'fused', round(d['fused_ms'] * 1e3, 1), 'us  nccl+gemm', round(d['nccl_plus_gemm_ms'] * 1e3, 1), ' gemm only', round(d['gemm_only_ms'] * 1e3, 1), ' frac of roofline', round(d['fused_frac_of_roofline'], 2))
 "
+  echo "== candidate switches (written without GPU access; flip the defaults if they pass and win)"
+  PIPEGOOSE_B200_FUSED_LM_HEAD=1 timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -k "tp2_bloom" 2>&1 | tail -2
+  for sw in "PIPEGOOSE_B200_FUSED_LM_HEAD=1" "PIPEGOOSE_B200_RS_FUSED_REDUCE=1" "PIPEGOOSE_B200_NCOMM=8"; do
+    echo "-- $sw"
+    env $sw python bench.py --gpus 2 --steps 10 --warmup 3 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print(round(d['ms_per_step'], 2), 'ms/step', 'loss', d['final_loss'])
+"
+  done
   echo "== TP2 step breakdown (torch profiler, diagnosis only)"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -24
 fi
