@@ -27,6 +27,8 @@ from pipegoose_b200.ops import kernels as K
 import os as _os
 
 _FUSED_LM_HEAD = _os.environ.get("PIPEGOOSE_B200_FUSED_LM_HEAD", "0") == "1"
+# LayerNorm backward writes dx into the staging slot of the next backward all-gather (same status: unvalidated, off)
+_LNBWD_TO_STAGE = _os.environ.get("PIPEGOOSE_B200_LNBWD_TO_STAGE", "0") == "1"
 
 
 def _main_grad(p: Optional[torch.Tensor]):
@@ -76,15 +78,20 @@ def _bgrad(dy, bias):
     return K.colsum(dy).to(bias.dtype)
 
 
-def _ln_bwd(dy, x, gamma, beta, mean, rstd, dx_extra=None):
+def _ln_bwd(dy, x, gamma, beta, mean, rstd, dx_extra=None, tp=None):
+    # Under fused TP the dx of a sub-layer is the dy of the one before it, whose first backward op is an
+    # all-gather->GEMM: writing dx straight into that all-gather's staging slot saves a 16 MB copy per sub-layer.
+    dx_out = None
+    if _LNBWD_TO_STAGE and tp is not None and tp.fused:
+        dx_out = tp.ag_input_buffer(x.shape[0], x.shape[1])
     if _main_grad(gamma) is not None and _main_grad(beta) is not None:
         mg_g, _ = acquire_main_grad(gamma, will_overwrite=False)
         mg_b, _ = acquire_main_grad(beta, will_overwrite=False)
-        dx, _, _ = K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra, mg_g, mg_b)
+        dx, _, _ = K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra, mg_g, mg_b, dx_out=dx_out)
         notify_grad_ready(gamma)
         notify_grad_ready(beta)
         return dx, None, None
-    return K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra)
+    return K.layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra, dx_out=dx_out)
 
 
 def _ln_linear_fwd(x, gamma, beta, weight, bias, eps, tp):
@@ -107,7 +114,7 @@ def _ln_linear_bwd(dy, x, gamma, beta, weight, bias, mean, rstd, ln_full, tp, dx
         dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
     dw = _wgrad(dy, ln_full, weight)
     db = _bgrad(dy, bias)
-    dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dx_extra)
+    dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dx_extra, tp=tp)
     return dx, dgamma, dbeta, dw, db
 
 
@@ -264,7 +271,7 @@ class LayerNormMLP(torch.autograd.Function):
         dw1 = _wgrad(dz, ln_full, w1)
         db1 = _bgrad(dz, b1)
         # residual gradient (dy) is added inside the LN backward kernel
-        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dy)
+        dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd, dx_extra=dy, tp=tp)
         return dx, dgamma, dbeta, dw1, db1, dw2, db2, None, None
 
 

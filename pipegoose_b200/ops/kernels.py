@@ -152,10 +152,11 @@ def layernorm_fwd(x, gamma, beta, eps, ids=None, vocab_start=0, vocab_end=0, app
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra=None, dgamma_acc=None, dbeta_acc=None):
-    """Returns ``(dx, dgamma, dbeta)``; the parameter grads are ``None`` when accumulated in place."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra=None, dgamma_acc=None, dbeta_acc=None, dx_out=None):
+    """Returns ``(dx, dgamma, dbeta)``; the parameter grads are ``None`` when accumulated in place.  ``dx_out``:
+    write dx into this buffer (the next all-gather's staging slot) instead of a fresh tensor."""
     if use_native(dy):
-        dx = torch.empty_like(x)
+        dx = dx_out if dx_out is not None else torch.empty_like(x)
         if dgamma_acc is None:
             dg = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
             db = torch.zeros_like(dg)

@@ -31,7 +31,7 @@ for l in sys.stdin:
 "
   echo "== candidate switches (written without GPU access; flip the defaults if they pass and win)"
   PIPEGOOSE_B200_FUSED_LM_HEAD=1 timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -k "tp2_bloom" 2>&1 | tail -2
-  for sw in "PIPEGOOSE_B200_FUSED_LM_HEAD=1" "PIPEGOOSE_B200_RS_FUSED_REDUCE=1" "PIPEGOOSE_B200_NCOMM=8"; do
+  for sw in "PIPEGOOSE_B200_FUSED_LM_HEAD=1" "PIPEGOOSE_B200_LNBWD_TO_STAGE=1" "PIPEGOOSE_B200_RS_FUSED_REDUCE=1" "PIPEGOOSE_B200_NCOMM=8"; do
     echo "-- $sw"
     env $sw python bench.py --gpus 2 --steps 10 --warmup 3 | python -c "
 import sys, json
