@@ -43,7 +43,7 @@ def _load():
 
 
 # kernels launched per binding call (everything else launches exactly one)
-_LAUNCHES_PER_CALL = {"layernorm_bwd": 2}
+_LAUNCHES_PER_CALL = {"layernorm_bwd": 2, "attention_bwd": 3}  # dx + params; delta + bwd + dQ convert
 _launch_count = 0
 _PROXY = None
 
