@@ -43,6 +43,10 @@ for l in sys.stdin:
   echo "== TP2 step breakdown (torch profiler, diagnosis only)"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -24
 fi
+if [ "$N" -ge 4 ]; then
+  echo "== convergence: TP2 x DP2 + ZeRO-1 (bf16, fused kernels) next to a single-GPU model"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29535 examples/convergence_hybrid.py --tp 2 --dp 2 --steps 60 2>&1 | grep "^step\|^loss" | tee gpurun_out/convergence_tp2dp2.txt | tail -5
+fi
 echo "== 1-GPU step breakdown (ncu launch list)"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py > /dev/null 2>&1
 python tools/step_profile.py --aggregate gpurun_out/step_launches.csv gpurun_out/step_breakdown.json | head -22
