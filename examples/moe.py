@@ -20,7 +20,7 @@ if __name__ == "__main__":
     ap.add_argument("--tp", type=int, default=2)
     ap.add_argument("--dp", type=int, default=1)
     ap.add_argument("--experts", type=int, default=4)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--backend", default="gloo")
     args = ap.parse_args()
     ctx = ParallelContext.from_torch(tensor_parallel_size=args.tp, pipeline_parallel_size=1, data_parallel_size=args.dp,
@@ -31,15 +31,24 @@ if __name__ == "__main__":
     model = ExpertParallel(model, args.experts, mapping=[0, 2], router=router, parallel_context=ctx).parallelize()
     model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
-    optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    optim = torch.optim.Adam(model.parameters(), lr=3e-3)
     expert_ctx = ExpertContext.get_instance()
+
+    def make_batch(step, batch=8, seq=32):
+        """Noisy counting sequences (learnable): next token = current + 3 (mod vocab), 5 % noise."""
+        g = torch.Generator().manual_seed(1000 + step)
+        start = torch.randint(0, cfg.vocab_size, (batch, 1), generator=g)
+        ids = (start + 3 * torch.arange(seq)[None, :]) % cfg.vocab_size
+        noise = torch.rand(batch, seq, generator=g) < 0.05
+        return torch.where(noise, torch.randint(0, cfg.vocab_size, (batch, seq), generator=g), ids)
+
     for step in range(args.steps):
-        ids = torch.randint(0, cfg.vocab_size, (4, 32))
+        ids = make_batch(step)
         loss = model(ids, labels=ids).loss
         loss = loss + 0.01 * sum(expert_ctx.pop_all_aux_loss()) + 0.001 * sum(expert_ctx.pop_all_z_loss())
         optim.zero_grad()
         loss.backward()
         optim.step()
-        if ctx.get_global_rank() == 0:
+        if ctx.get_global_rank() == 0 and (step % 5 == 0 or step == args.steps - 1):
             print(f"step {step} loss {loss.item():.4f}", flush=True)
     ctx.destroy()
