@@ -29,6 +29,8 @@ import sys, json
 for l in sys.stdin:
     d = json.loads(l); print(d['op'], 'fused', round(d['fused_ms'] * 1e3, 1), 'us  nccl+gemm', round(d['nccl_plus_gemm_ms'] * 1e3, 1), ' gemm only', round(d['gemm_only_ms'] * 1e3, 1), ' frac of roofline', round(d['fused_frac_of_roofline'], 2))
 "
+  echo "== fused MoE layer vs reference-style layer (T=2; config #4 wants T=8: gpurun --gpus 8)"
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29536 tools/moe_bench.py 2>&1 | grep "^{" | cut -c1-400
   echo "== candidate switches (written without GPU access; flip the defaults if they pass and win)"
   PIPEGOOSE_B200_FUSED_LM_HEAD=1 timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -k "tp2_bloom" 2>&1 | tail -2
   for sw in "PIPEGOOSE_B200_FUSED_LM_HEAD=1" "PIPEGOOSE_B200_LNBWD_TO_STAGE=1" "PIPEGOOSE_B200_RS_FUSED_REDUCE=1" "PIPEGOOSE_B200_NCOMM=8"; do
