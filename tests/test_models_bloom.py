@@ -1,0 +1,46 @@
+"""``pipegoose_b200.models.bloom`` against 🤗 transformers' Bloom (random init, no downloads): same module tree and
+parameter names, same logits / loss / gradients / greedy generation."""
+import torch
+
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+
+def _hf():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    torch.manual_seed(0)
+    return HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)).eval()
+
+
+def test_from_hf_matches_transformers_bloom():
+    hf = _hf()
+    model = BloomForCausalLM.from_hf(hf).eval()
+    # identical parameter names / shapes: state dicts load in both directions
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in hf.state_dict().items() if k in model.state_dict()}
+    hf.load_state_dict(model.state_dict(), strict=False)
+    ids = torch.randint(0, 96, (2, 8))
+    a = hf(input_ids=ids, labels=ids)
+    b = model(ids, labels=ids)
+    assert torch.allclose(a.loss, b.loss, atol=1e-5)
+    a.loss.backward()
+    b.loss.backward()
+    hf_grads = dict(hf.named_parameters())
+    for n, p in model.named_parameters():
+        assert torch.allclose(p.grad, hf_grads[n].grad, atol=2e-5), n
+    with torch.no_grad():
+        assert torch.allclose(hf(input_ids=ids).logits, model(ids).logits, atol=1e-5)
+        gen_hf = hf.generate(ids, max_new_tokens=3, do_sample=False)
+        gen = model.generate(ids, max_new_tokens=3)
+    assert torch.equal(gen, gen_hf)
+
+
+def test_config_presets_and_flops():
+    assert BloomConfig.bloom_560m().hidden_size == 1024 and BloomConfig.bloom_560m().n_layer == 24
+    assert BloomConfig.bloom_3b().hidden_size // BloomConfig.bloom_3b().n_head == 80
+    assert BloomConfig.bloom_7b1().n_head == 32
+    m = BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=16, n_layer=1, n_head=2))
+    assert m.lm_head.weight is m.transformer.word_embeddings.weight  # tied
+    assert m.num_parameters() == sum(p.numel() for p in set(m.parameters()))
+    assert m.flops_per_token(128) > 6 * (12 * 16 * 16 + 64 * 16)
