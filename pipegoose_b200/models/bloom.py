@@ -52,6 +52,11 @@ class BloomConfig:
         )
 
     @classmethod
+    def bloom_tiny(cls):
+        """A toy size for CPU smoke runs of the examples."""
+        return cls(vocab_size=1024, hidden_size=128, n_layer=4, n_head=8)
+
+    @classmethod
     def bloom_560m(cls):
         return cls(hidden_size=1024, n_layer=24, n_head=16)
 
