@@ -53,6 +53,7 @@ class ParallelContext:
         data_parallel_size: int,
         seed: int = SEED,
         backend: DistributedBackend = "gloo",
+        enable_rpc: bool = False,
     ) -> "ParallelContext":
         """Build the context from the environment variables set by ``torchrun``."""
         env = os.environ
@@ -69,6 +70,7 @@ class ParallelContext:
             tensor_parallel_size=tensor_parallel_size,
             pipeline_parallel_size=pipeline_parallel_size,
             data_parallel_size=data_parallel_size,
+            enable_rpc=enable_rpc,
         )
 
     def __init__(
@@ -84,7 +86,10 @@ class ParallelContext:
         tensor_parallel_size: int,
         pipeline_parallel_size: int,
         data_parallel_size: int,
+        enable_rpc: bool = False,
     ):
+        self._enable_rpc = enable_rpc
+        self._rpc_started = False
         model_ranks = tensor_parallel_size * pipeline_parallel_size
         assert world_size % data_parallel_size == 0, "world size must be divisible by the data parallel size"
         assert world_size % model_ranks == 0, (
@@ -178,8 +183,19 @@ class ParallelContext:
             self._register_dist(**initializer(**params).init_dist_group())
 
     def init_rpc_workers(self, host: str, port: int):
-        """No RPC agents: the pipeline engine uses NCCL p2p on a static schedule (reference
-        parallel_context.py:200-225 started TensorPipe here)."""
+        """The library itself needs no RPC agents (the pipeline engines use p2p on static schedules; the reference
+        started TensorPipe here whenever pp > 1, parallel_context.py:200-225).  With ``enable_rpc=True`` one agent per
+        rank is started under the reference's worker names (``get_worker_name(rank)``) for user code that wants
+        ``torch.distributed.rpc``; ``destroy()`` shuts it down."""
+        if not self._enable_rpc or self.get_world_size(ParallelMode.GLOBAL) == 1:
+            return None
+        from torch.distributed import rpc
+
+        options = rpc.TensorPipeRpcBackendOptions(init_method=f"tcp://{host}:{port + 1}")
+        rank = self.get_global_rank()
+        rpc.init_rpc(name=self.get_worker_name(rank), rank=rank, world_size=self.get_world_size(ParallelMode.GLOBAL),
+                     rpc_backend_options=options)
+        self._rpc_started = True
         return None
 
     def _register_dist(self, local_rank, local_world_size, process_group, ranks_in_group, parallel_mode):
@@ -298,6 +314,11 @@ class ParallelContext:
     def destroy(self):
         assert self.is_initialized(ParallelMode.GLOBAL), "the global group must be initialised before destroying"
         global _PARALLEL_CONTEXT
+        if self._rpc_started:
+            from torch.distributed import rpc
+
+            rpc.shutdown()
+            self._rpc_started = False
         for ws in self._symm_workspaces.values():
             ws.close()
         self._symm_workspaces.clear()

@@ -78,3 +78,29 @@ def test_bad_sizes_rejected():
     with pytest.raises(AssertionError):
         ParallelContext(rank=0, local_rank=0, world_size=4, local_world_size=4, host="127.0.0.1", port=1, seed=1,
                         backend="gloo", tensor_parallel_size=3, pipeline_parallel_size=1, data_parallel_size=1)
+
+
+def _rpc_echo(x):
+    return x * 2
+
+
+def run_rpc(rank, world_size, port):
+    """Opt-in RPC agents under the reference's worker names (parity: reference tests/distributed/test_rpc.py)."""
+    from torch.distributed import rpc
+
+    from pipegoose_b200.distributed.parallel_context import ParallelContext
+
+    ctx = ParallelContext(rank=rank, local_rank=rank, world_size=world_size, local_world_size=world_size,
+                          host="127.0.0.1", port=port, seed=69, backend="gloo", tensor_parallel_size=1,
+                          pipeline_parallel_size=world_size, data_parallel_size=1, enable_rpc=True)
+    peer = ctx.get_worker_name((rank + 1) % world_size)
+    assert peer == f"RPC_GLOBAL_WORKER_{(rank + 1) % world_size}"
+    assert rpc.rpc_sync(peer, _rpc_echo, args=(torch.tensor([rank + 1.0]),)).item() == 2.0 * (rank + 1)
+    fut = rpc.rpc_async(peer, _rpc_echo, args=(torch.tensor([3.0]),))
+    assert fut.wait().item() == 6.0
+    ctx.destroy()  # shuts the agent down
+    assert not ctx._rpc_started
+
+
+def test_optional_rpc_workers():
+    spawn(run_rpc, world_size=2)
