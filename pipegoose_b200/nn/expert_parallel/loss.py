@@ -1,9 +1,19 @@
-"""Task loss + router auxiliary losses (parity: reference nn/expert_parallel/loss.py:8-29)."""
-from typing import Callable
+"""Task loss plus the routers' auxiliary losses (parity: reference nn/expert_parallel/loss.py:8-29).
+
+    loss_fn = ExpertLoss(torch.nn.CrossEntropyLoss(), aux_weight=0.01, z_weight=0.1)
+    loss = loss_fn(logits, targets)      # = CE + 0.01 * sum(load-balancing losses) + 0.1 * sum(router z-losses)
+
+The auxiliary terms are whatever the expert layers pushed into :class:`ExpertContext` since the last call; calling the
+loss consumes them, so every forward pass is counted exactly once."""
+from typing import Callable, List
 
 import torch
 
 from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+
+def _weighted_sum(weight: float, terms: List[torch.Tensor]):
+    return weight * torch.stack([t.float().reshape(()) for t in terms]).sum() if terms else None
 
 
 class ExpertLoss:
@@ -12,20 +22,20 @@ class ExpertLoss:
         self.aux_weight = aux_weight
         self.z_weight = z_weight
 
+    # peeking does not consume
     @property
-    def aux_loss(self):
+    def aux_loss(self) -> List[torch.Tensor]:
         return ExpertContext.get_instance().aux_loss
 
     @property
-    def z_loss(self):
+    def z_loss(self) -> List[torch.Tensor]:
         return ExpertContext.get_instance().z_loss
 
     def __call__(self, *args, **kwargs) -> torch.Tensor:
-        loss = self.loss_func(*args, **kwargs)
-        ctx = ExpertContext.get_instance()
-        aux, z = ctx.pop_all_aux_loss(), ctx.pop_all_z_loss()
-        if aux:
-            loss = loss + self.aux_weight * sum(aux)
-        if z:
-            loss = loss + self.z_weight * sum(z)
-        return loss
+        total = self.loss_func(*args, **kwargs)
+        store = ExpertContext.get_instance()
+        for weight, terms in ((self.aux_weight, store.pop_all_aux_loss()), (self.z_weight, store.pop_all_z_loss())):
+            extra = _weighted_sum(weight, terms)
+            if extra is not None:
+                total = total + extra.to(total.dtype)
+        return total
