@@ -14,6 +14,7 @@ from pipegoose_b200.distributed import ParallelContext
 from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
 from pipegoose_b200.nn import DataParallel, ExpertParallel, TensorParallel
 from pipegoose_b200.nn.expert_parallel import ExpertContext, SwitchNoisePolicy, Top1Router
+from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -28,10 +29,16 @@ if __name__ == "__main__":
     cfg = BloomConfig(vocab_size=1024, hidden_size=128, n_layer=4, n_head=8)
     model = BloomForCausalLM(cfg)
     router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
+    gpu = args.backend == "nccl"
+    if gpu:  # bf16 on the B200 path: router kernel + NVLink dispatch + grouped tcgen05 expert GEMMs
+        model, router = model.to(torch.bfloat16), router.to(torch.bfloat16)
     model = ExpertParallel(model, args.experts, mapping=[0, 2], router=router, parallel_context=ctx).parallelize()
     model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
-    optim = torch.optim.Adam(model.parameters(), lr=3e-3)
+    if gpu:
+        model.to("cuda")
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=3e-3), ctx) if gpu \
+        else torch.optim.Adam(model.parameters(), lr=3e-3)
     expert_ctx = ExpertContext.get_instance()
 
     def make_batch(step, batch=8, seq=32):
@@ -44,6 +51,8 @@ if __name__ == "__main__":
 
     for step in range(args.steps):
         ids = make_batch(step)
+        if gpu:
+            ids = ids.cuda()
         loss = model(ids, labels=ids).loss
         loss = loss + 0.01 * sum(expert_ctx.pop_all_aux_loss()) + 0.001 * sum(expert_ctx.pop_all_z_loss())
         optim.zero_grad()
