@@ -340,8 +340,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic token ids (uniform random), random-init weights",
         "config": {"model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": S,
-                   "parallelism": f"tp{tp}" + (f"pp{pp}(1f1b,{args.microbatches}mb)" if pp > 1 else "") + f"dp{dp}"
-            + ("+zero1" if dp > 1 else "") + (f"+moe{args.experts}e" if args.experts > 0 else ""), "optimizer": "torch.optim.Adam via reference DistributedOptimizer",
+                   "parallelism": f"tp{tp}dp{dp}" + ("+zero1" if dp > 1 else ""),
+                   "optimizer": "torch.optim.Adam via reference DistributedOptimizer",
                    "batch_per_gpu": args.batch_per_gpu},
         "e2e": {"value": tokens_per_step * args.steps / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(host_ids[0].numel() * host_ids[0].element_size()), "d2h_bytes_per_step": 4},

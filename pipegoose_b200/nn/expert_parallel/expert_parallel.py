@@ -79,4 +79,14 @@ class ExpertParallel(Parallel):
 
     @torch.no_grad()
     def deparallelize(self) -> nn.Module:
-        raise NotImplementedError("mixture-of-experts layers cannot be merged back into a dense MLP")
+        """Undo the expert *sharding* (unimplemented in the reference): afterwards every rank holds all the experts
+        of every MoE layer and runs them locally — the layers stay mixture-of-experts layers (a trained MoE cannot
+        be folded back into one dense MLP), but the module no longer needs the TENSOR group, e.g. to export one
+        consolidated checkpoint.  Fused layers are converted to plain ``ExpertLayer``s first."""
+        for _, block in self._blocks(self.module):
+            mlp = getattr(block, "mlp", None)
+            if isinstance(mlp, ExpertLayer):
+                mlp.gather_experts_()
+            elif hasattr(mlp, "to_expert_layer"):
+                block.mlp = mlp.to_expert_layer().gather_experts_()
+        return self.module

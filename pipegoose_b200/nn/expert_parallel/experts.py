@@ -32,6 +32,8 @@ class Experts(nn.Module):
         self.enable_tensor_parallel = enable_tensor_parallel
         self.parallel_context = parallel_context
         self.num_local_experts = num_local_experts
+        # sharded: this rank holds a slice of the layer's experts and the outputs are summed over the group
+        self.sharded = not enable_tensor_parallel
         self.experts = nn.ModuleList([deepcopy(expert) for _ in range(num_local_experts)])
         self._set_expert_attr(self.experts)
 
@@ -42,7 +44,7 @@ class Experts(nn.Module):
             p.is_expert = True
 
     def _first_global_expert(self) -> int:
-        if self.enable_tensor_parallel:
+        if not self.sharded:
             return 0
         return self.parallel_context.get_local_rank(ParallelMode.TENSOR) * self.num_local_experts
 
@@ -79,6 +81,39 @@ class Experts(nn.Module):
             if w is not None:
                 y = y * w[rows, e].unsqueeze(-1).to(y.dtype)
             out = out.index_add(0, rows, y.to(out.dtype))
-        if not self.enable_tensor_parallel and self.parallel_context.get_world_size(ParallelMode.TENSOR) > 1:
+        if self.sharded and self.parallel_context.get_world_size(ParallelMode.TENSOR) > 1:
             out = reduce_to_tensor_group(out, self.parallel_context)
         return out.view(shape)
+
+    @torch.no_grad()
+    def gather_(self) -> "Experts":
+        """Undo the expert sharding in place: all-gather every expert's parameters and buffers over the TENSOR group
+        so that each rank holds all ``T * num_local_experts`` experts in global order (no combine afterwards)."""
+        import torch.distributed as dist
+
+        T = self.parallel_context.get_world_size(ParallelMode.TENSOR)
+        if not self.sharded:
+            return self
+        if T > 1:
+            group = self.parallel_context.get_group(ParallelMode.TENSOR)
+            rank = self.parallel_context.get_local_rank(ParallelMode.TENSOR)
+            El = self.num_local_experts
+            full = [None] * (T * El)
+            for j, expert in enumerate(self.experts):
+                tensors = [t for t in list(expert.parameters()) + list(expert.buffers())]
+                flat = torch.cat([t.detach().reshape(-1).float() for t in tensors]) if tensors else torch.zeros(0)
+                parts = [torch.empty_like(flat) for _ in range(T)]
+                dist.all_gather(parts, flat.contiguous(), group=group)
+                for r in range(T):
+                    clone = expert if r == rank else deepcopy(expert)
+                    if r != rank:
+                        off = 0
+                        for t in list(clone.parameters()) + list(clone.buffers()):
+                            t.copy_(parts[r][off:off + t.numel()].view_as(t).to(t.dtype))
+                            off += t.numel()
+                    full[r * El + j] = clone
+            self.experts = nn.ModuleList(full)
+            self.num_local_experts = T * El
+            self._set_expert_attr(self.experts)
+        self.sharded = False
+        return self

@@ -34,6 +34,13 @@ class ExpertLayer(nn.Module):
     def experts(self) -> nn.ModuleList:
         return self._experts.experts
 
+    @torch.no_grad()
+    def gather_experts_(self) -> "ExpertLayer":
+        """Every rank ends up with all ``num_experts`` experts (used by ``ExpertParallel.deparallelize``)."""
+        self._experts.gather_()
+        self.num_local_experts = self._experts.num_local_experts
+        return self
+
     def forward(self, *args, **kwargs) -> torch.Tensor:
         inputs = args[0]
         routed = self.router(inputs)

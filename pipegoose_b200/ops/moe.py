@@ -311,6 +311,29 @@ class FusedExpertLayer(nn.Module):
         eng._bepoch = getattr(eng, "_bepoch", 0) + 1
         native().barrier_peers([eng.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(eng.T)], eng.rank, eng._bepoch)
 
+    @torch.no_grad()
+    def to_expert_layer(self):
+        """The same layer as a plain ``ExpertLayer`` (per-expert ``BloomMLP`` modules holding this rank's slices of the
+        stacked weights, the same router object) — the form ``ExpertParallel.deparallelize`` and checkpoint export use."""
+        from types import SimpleNamespace
+
+        from pipegoose_b200.models.bloom import BloomMLP
+        from pipegoose_b200.nn.expert_parallel.layers import ExpertLayer
+
+        h = self.w1.shape[2]
+        template = BloomMLP(SimpleNamespace(hidden_size=h)).to(device=self.w1.device, dtype=self.w1.dtype)
+        layer = ExpertLayer(self.num_experts, template, self.router, False, self.parallel_context)
+        for j, expert in enumerate(layer.experts):
+            expert.dense_h_to_4h.weight.copy_(self.w1[j])
+            expert.dense_h_to_4h.bias.copy_(self.b1[j])
+            expert.dense_4h_to_h.weight.copy_(self.w2[j])
+            expert.dense_4h_to_h.bias.copy_(self.b2[j])
+        for p in self.router.parameters():
+            if hasattr(p, "tp_partial_grad"):
+                del p.tp_partial_grad   # replicated tokens: the gate gradient is complete on every rank
+        layer.train(self.training)
+        return layer
+
     # ------------------------------------------------------------------ forward
     def forward(self, hidden_states: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
         from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext

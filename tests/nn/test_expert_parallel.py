@@ -148,3 +148,52 @@ def test_expert_parallel_default_mapping_covers_all_layers():
         ctx.destroy()
 
     run(0, 1, __import__("pipegoose_b200.testing.utils", fromlist=["find_free_port"]).find_free_port())
+
+
+def run_expert_deparallelize(rank, world_size, port, fused_layer):
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    tp_rank = ctx.get_local_rank(ParallelMode.TENSOR)
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    router = Top2Router(None, 4, 32)
+    wrapper = ExpertParallel(model, 4, mapping=[1], router=router, parallel_context=ctx, fused=False)
+    model = wrapper.parallelize()
+    layer = model.transformer.h[1].mlp
+    # distinct experts: global expert e gets weights seeded by e
+    for i, e in enumerate(layer.experts):
+        g = torch.Generator().manual_seed(50 + tp_rank * len(layer.experts) + i)
+        for p in e.parameters():
+            p.data = torch.randn(p.shape, generator=g) * 0.05
+    if fused_layer:
+        # the fused layer's parameter layout (stacked [E_local, ...] weights) converted back through to_expert_layer()
+        from pipegoose_b200.ops.moe import FusedExpertLayer
+
+        fl = FusedExpertLayer(4, layer.experts[0], router, ctx)
+        for j, e in enumerate(layer.experts):
+            fl.w1.data[j], fl.b1.data[j] = e.dense_h_to_4h.weight.data, e.dense_h_to_4h.bias.data
+            fl.w2.data[j], fl.b2.data[j] = e.dense_4h_to_h.weight.data, e.dense_4h_to_h.bias.data
+        model.transformer.h[1].mlp = fl
+        want = None
+    else:
+        ids = torch.arange(16).view(2, 8) % 96
+        want = model(ids).logits.detach().clone()
+        ExpertContext.get_instance().pop_all_aux_loss(), ExpertContext.get_instance().pop_all_z_loss()
+    model = wrapper.deparallelize()
+    layer = model.transformer.h[1].mlp
+    assert isinstance(layer, ExpertLayer) and len(layer.experts) == 4 and layer.num_local_experts == 4
+    for gidx, e in enumerate(layer.experts):
+        g = torch.Generator().manual_seed(50 + gidx)
+        for p in e.parameters():
+            assert torch.allclose(p.data, torch.randn(p.shape, generator=g) * 0.05), f"expert {gidx} is not the global expert"
+            assert p.is_expert
+    if want is not None:
+        # all experts local, no combine over the group: same logits as the sharded layer
+        got = model(ids).logits
+        assert torch.allclose(got, want, atol=1e-5)
+        ExpertContext.get_instance().pop_all_aux_loss(), ExpertContext.get_instance().pop_all_z_loss()
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fused_layer", [False, True])
+def test_expert_parallel_deparallelize_gathers_all_experts(fused_layer):
+    spawn(run_expert_deparallelize, world_size=2, fused_layer=fused_layer)

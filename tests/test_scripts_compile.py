@@ -25,3 +25,46 @@ def test_script_compiles_and_imports_resolve(path):
                 assert alias.name == "*" or hasattr(mod, alias.name) or \
                     importlib.util.find_spec(f"{node.module}.{alias.name}") is not None, \
                     f"{path.name}: {node.module} has no attribute {alias.name}"
+
+
+def _undefined_names(path):
+    """Names that a function reads as globals although the module never binds them (what pyflakes calls an
+    undefined name) — the bug class that only shows up when the GPU-only code path finally runs."""
+    import builtins
+    import symtable
+
+    src = path.read_text()
+    top = symtable.symtable(src, str(path), "exec")
+    if any(isinstance(n, ast.ImportFrom) and any(a.name == "*" for a in n.names) for n in ast.walk(ast.parse(src))):
+        return []
+    bound = {s.get_name() for s in top.get_symbols() if s.is_assigned() or s.is_imported() or s.is_namespace()}
+    bound |= set(dir(builtins)) | {"__file__", "__name__", "__doc__", "__builtins__", "__spec__", "__path__", "__class__"}
+    # names bound through ``global x`` inside a function
+    stack, missing = [top], []
+    tables = []
+    while stack:
+        t = stack.pop()
+        tables.append(t)
+        stack.extend(t.get_children())
+    for t in tables:
+        for s in t.get_symbols():
+            if t is not top and s.is_declared_global() and s.is_assigned():
+                bound.add(s.get_name())
+    for t in tables:
+        if t is top:
+            continue
+        for s in t.get_symbols():
+            if s.is_global() and s.is_referenced() and s.get_name() not in bound:
+                missing.append(f"{t.get_name()}:{s.get_name()}")
+    for s in top.get_symbols():
+        if s.is_referenced() and not (s.is_assigned() or s.is_imported() or s.is_namespace()) and s.get_name() not in bound:
+            missing.append(f"<module>:{s.get_name()}")
+    return missing
+
+
+PACKAGE = sorted((ROOT / "pipegoose_b200").rglob("*.py"))
+
+
+@pytest.mark.parametrize("path", SCRIPTS + PACKAGE, ids=lambda p: str(p.relative_to(ROOT)))
+def test_no_undefined_names(path):
+    assert _undefined_names(path) == []
