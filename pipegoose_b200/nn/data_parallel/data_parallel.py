@@ -37,13 +37,16 @@ class DataParallel(Parallel):
             reducer = GradReducer(module, ctx, self.bucket_size_mb)
             module._pg_grad_reducer = reducer
             module.no_sync = reducer.no_sync
-            module.register_forward_pre_hook(_build_on_first_forward)
+            module._pg_dp_build_hook = module.register_forward_pre_hook(_build_on_first_forward)
             if self.broadcast_parameters:
                 module._pg_needs_param_broadcast = True
             self._save_metadata(module, ctx)
         return module
 
     def deparallelize(self) -> nn.Module:
+        """Detach the gradient reducer: hooks removed, ``no_sync`` and the gradient-ready notifications handed back to
+        the tensor-parallel partial-gradient sync when the module has one (TP without DP still has to sum the
+        gradients of the TP-replicated parameters)."""
         module = self.module
         for p in module.parameters():
             h = getattr(p, "_pg_autograd_hook", None)
@@ -52,8 +55,19 @@ class DataParallel(Parallel):
                 del p._pg_autograd_hook
             if hasattr(p, "_pg_grad_ready"):
                 del p._pg_grad_ready
+        h = getattr(module, "_pg_dp_build_hook", None)
+        if h is not None:
+            h.remove()
+            del module._pg_dp_build_hook
         if hasattr(module, "_pg_grad_reducer"):
             del module._pg_grad_reducer
+        tp_sync = getattr(module, "_pg_tp_grad_sync", None)
+        if tp_sync is not None:
+            for p in tp_sync.params:
+                p._pg_grad_ready = tp_sync._on_ready
+            module.no_sync = tp_sync.no_sync
+        elif "no_sync" in module.__dict__:
+            del module.no_sync
         return module
 
 

@@ -21,8 +21,9 @@ class FusedAdam(torch.optim.Optimizer):
         params = list(params)
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, adamw=adamw)
         super().__init__(params, defaults)
-        for p in params:
-            p._pg_fused_optim = True  # gradients are consumed from ``main_grad``; nobody needs a ``.grad`` copy
+        for group in self.param_groups:  # (``params`` may be a list of group dicts)
+            for p in group["params"]:
+                p._pg_fused_optim = True  # gradients are consumed from ``main_grad``; nobody needs a ``.grad`` copy
         self.flat: Optional[FlatModelState] = flat_state
         self._segments: Optional[List[Tuple[int, int]]] = None  # [(flat_start, flat_end)] owned by this rank
         self._step = 0
@@ -70,15 +71,13 @@ class FusedAdam(torch.optim.Optimizer):
         self._lazy_init()
         self._fold_autograd_grads()
         self._step += 1
-        g = self.param_groups[0]
-        lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
-        off = 0
-        for s, e in self._segments:
+        for off, s, e, gi in self._plan():
             n = e - s
+            g = self.param_groups[gi]
+            lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
             grad = self.flat.flat_grad[s:e]
             param = self.flat.flat_param[s:e]
             master, m, v = self.master[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n]
-            off += n
             if use_native(param):
                 native().adam_step(master, m, v, grad, param, lr, b1, b2, eps, wd, self._step, grad_scale, g["adamw"])
             else:
@@ -94,6 +93,46 @@ class FusedAdam(torch.optim.Optimizer):
                 param.copy_(master.to(param.dtype))
         self.flat.hold_grads = False
         return loss
+
+    def _plan(self) -> List[Tuple[int, int, int, int]]:
+        """``[(offset in the optimizer state, flat start, flat end, param-group index)]``: one kernel launch each.
+        One parameter group (the common case): one launch per owned segment, alignment padding included.  Several
+        groups (e.g. no weight decay for biases / LayerNorms): the owned segments are cut at the group boundaries
+        of the flat layout; neighbouring parameters of the same group share a launch."""
+        key = (tuple(self._segments), len(self.param_groups))
+        if getattr(self, "_plan_key", None) == key:
+            return self._plan_cache
+        plan = []
+        if len(self.param_groups) == 1:
+            off = 0
+            for s, e in self._segments:
+                plan.append((off, s, e, 0))
+                off += e - s
+        else:
+            group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+            spans = sorted((self.flat.param_range(p)[0], sum(self.flat.param_range(p)), group_of[id(p)])
+                           for p in self.flat.params if id(p) in group_of)
+            off = 0
+            for s, e in self._segments:
+                runs = []
+                for a, b, gi in spans:
+                    a, b = max(a, s), min(b, e)
+                    if a >= b:
+                        continue
+                    if runs and runs[-1][2] == gi:
+                        runs[-1][1] = b       # same group: swallow the alignment gap between the two parameters
+                    else:
+                        runs.append([a, b, gi])
+                plan.extend((off + a - s, a, b, gi) for a, b, gi in runs)
+                off += e - s
+        self._plan_key, self._plan_cache = key, plan
+        return plan
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._plan_key = None
+        for p in self.param_groups[-1]["params"]:
+            p._pg_fused_optim = True
 
     def _fold_autograd_grads(self):
         """Gradients delivered through autograd (``p.grad``: layers without a fused wgrad, or a backward that ran

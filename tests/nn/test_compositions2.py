@@ -59,6 +59,43 @@ def test_fused_adam_modes_match_torch(adamw, wd):
         assert torch.allclose(a, b, atol=1e-5)
 
 
+@pytest.mark.parametrize("sharded", [False, True])
+def test_fused_adam_parameter_groups_match_torch(sharded):
+    """Per-group hyper-parameters (no weight decay and a different lr for biases) — also when this rank only owns a
+    slice of the flat buffer that cuts through parameters (ZeRO-1 segments)."""
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 4))
+    mine = copy.deepcopy(ref)
+
+    def groups(model):
+        decay = [p for p in model.parameters() if p.dim() >= 2]
+        rest = [p for p in model.parameters() if p.dim() < 2]
+        return [{"params": decay, "weight_decay": 0.1}, {"params": rest, "weight_decay": 0.0, "lr": 3e-2}]
+
+    topt = torch.optim.AdamW(groups(ref), lr=1e-2)
+    fopt = FusedAdam(groups(mine), lr=1e-2, adamw=True)
+    assert all(p._pg_fused_optim for p in mine.parameters())
+    if sharded:
+        n = fopt.ensure_flat().numel
+        fopt.set_shard(n // 4, n // 4 + n // 2)
+    before = [p.detach().clone() for p in mine.parameters()]
+    x = torch.randn(16, 8)
+    for _ in range(1 if sharded else 4):   # (a lone shard owner sees stale peers' slices after the first step)
+        for model, opt in ((ref, topt), (mine, fopt)):
+            opt.zero_grad()
+            model(x).pow(2).mean().backward()
+            opt.step()
+    assert len({gi for _, _, _, gi in fopt._plan()}) == 2
+    flat = fopt.flat
+    s, e = fopt._segments[0]
+    for a, b, b0 in zip(ref.parameters(), mine.parameters(), before):
+        o, cnt = flat.param_range(b)
+        idx = torch.arange(o, o + cnt)
+        owned = ((idx >= s) & (idx < e)).view_as(b)
+        assert torch.allclose(a[owned], b[owned], atol=1e-5)        # owned elements follow torch's AdamW
+        assert torch.equal(b[~owned], b0[~owned])                   # the rest is another rank's to update
+
+
 def _hf_bloom():
     from transformers import BloomConfig as HFConfig
     from transformers import BloomForCausalLM as HFBloom

@@ -123,3 +123,41 @@ def test_flatten_helpers():
     outs = [torch.zeros(2, 3), torch.zeros(4)]
     copy_flatten_tensor_to_unflatten_tensors(flat, outs)
     assert torch.equal(outs[0], ts[0]) and torch.equal(outs[1], ts[1])
+
+
+def run_dp_deparallelize(rank, world_size, port, tp, state, ids, ref_grads):
+    from pipegoose_b200.nn import TensorParallel
+
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 2)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    if tp > 1:
+        model = TensorParallel(model, ctx).parallelize()
+    wrapper = DataParallel(model, ctx)
+    model = wrapper.parallelize()
+    local = ids.chunk(2)[ctx.get_local_rank(ParallelMode.DATA)]
+    model(local, labels=local).loss.backward()           # a reduced step: the reducer is built and used
+    model = wrapper.deparallelize()
+    assert not hasattr(model, "_pg_grad_reducer")
+    assert hasattr(model, "no_sync") == (tp > 1)           # handed back to the tensor-parallel partial-gradient sync
+    model._flat_state.zero_grad(lazy=False)
+    model(local, labels=local).loss.backward()           # must still run, now WITHOUT the data-parallel average
+    for name in ("transformer.ln_f.weight", "transformer.h.0.input_layernorm.bias", "transformer.h.1.self_attention.dense.bias"):
+        p = dict(model.named_parameters())[name]
+        want = ref_grads[ctx.get_local_rank(ParallelMode.DATA)][name]
+        assert torch.allclose(p.main_grad, want, atol=2e-5), name   # local-batch gradient, summed over the TENSOR group
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp", [1, 2])
+def test_data_parallel_deparallelize_detaches_the_reducer(tp):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    ref_grads = []
+    for local in ids.chunk(2):
+        model.zero_grad()
+        model(local, labels=local).loss.backward()
+        ref_grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    spawn(run_dp_deparallelize, world_size=2 * tp, tp=tp, state=state, ids=ids, ref_grads=ref_grads)
