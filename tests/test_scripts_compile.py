@@ -68,3 +68,37 @@ PACKAGE = sorted((ROOT / "pipegoose_b200").rglob("*.py"))
 @pytest.mark.parametrize("path", SCRIPTS + PACKAGE, ids=lambda p: str(p.relative_to(ROOT)))
 def test_no_undefined_names(path):
     assert _undefined_names(path) == []
+
+
+@pytest.mark.parametrize("path", SCRIPTS + PACKAGE, ids=lambda p: str(p.relative_to(ROOT)))
+def test_module_alias_attributes_and_native_bindings_exist(path):
+    """``K.gemm_tn`` / ``S.SymmetricWorkspace`` / ``native().attention_fwd`` style references: the attribute exists in
+    the aliased ``pipegoose_b200`` module, and every ``native().<name>`` is a function the extension binds."""
+    import re
+
+    bound = set(re.findall(r'm\.def\("([a-z_0-9]+)"', (ROOT / "pipegoose_b200" / "csrc" / "bindings.cpp").read_text()))
+    tree = ast.parse(path.read_text())
+    aliases = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Import):
+            aliases.update({a.asname: a.name for a in node.names if a.asname and a.name.startswith("pipegoose_b200")})
+        elif isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("pipegoose_b200"):
+            for a in node.names:
+                if a.name != "*" and importlib.util.find_spec(node.module) is not None:
+                    try:
+                        is_module = importlib.util.find_spec(f"{node.module}.{a.name}") is not None
+                    except ModuleNotFoundError:
+                        is_module = False
+                    if is_module:
+                        aliases[a.asname or a.name] = f"{node.module}.{a.name}"
+    missing = []
+    for node in ast.walk(tree):
+        if not isinstance(node, ast.Attribute):
+            continue
+        if isinstance(node.value, ast.Name) and node.value.id in aliases:
+            if not hasattr(importlib.import_module(aliases[node.value.id]), node.attr):
+                missing.append(f"line {node.lineno}: {node.value.id}.{node.attr}")
+        elif isinstance(node.value, ast.Call) and isinstance(node.value.func, ast.Name) and node.value.func.id == "native":
+            if node.attr not in bound:
+                missing.append(f"line {node.lineno}: native().{node.attr}")
+    assert missing == []
