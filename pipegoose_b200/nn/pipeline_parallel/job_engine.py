@@ -27,6 +27,7 @@ from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
 from pipegoose_b200.nn.pipeline_parallel._package import Metadata, Package, TrainingMetadata
 from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
 from pipegoose_b200.nn.pipeline_parallel._worker import WorkerManager
+from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import broadcast_loss_from_last_stage
 from pipegoose_b200.nn.pipeline_parallel.scheduler import GPipeScheduler
 from pipegoose_b200.nn.pipeline_parallel.sync.handshake import ProgressTracker
 
@@ -124,6 +125,7 @@ class JobPipelineEngine:
             self._run_job(create_job(self.module, pkg, ctx, self.pipeline_context))
         self._sync_tied_embedding_grad()
         total = torch.stack(losses).sum() if self.is_last else torch.zeros(())
+        total = broadcast_loss_from_last_stage(total, self.parallel_context)
         return CausalLMOutput(loss=total.detach().requires_grad_(True), logits=None)
 
     def _sync_tied_embedding_grad(self):

@@ -35,6 +35,23 @@ from pipegoose_b200.nn.pipeline_parallel.scheduler import BaseScheduler
 from pipegoose_b200.nn.pipeline_parallel.task import Task
 
 
+
+def broadcast_loss_from_last_stage(loss: torch.Tensor, parallel_context) -> torch.Tensor:
+    """The loss is computed on the last stage; every stage returns it (a 4-byte broadcast over the PIPELINE group,
+    enqueued on the stream — no host sync) so that ``loss.item()`` means the same thing on every rank, e.g. for
+    logging from global rank 0, which is a first stage."""
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+    if parallel_context.get_world_size(ParallelMode.PIPELINE) == 1:
+        return loss
+    group = parallel_context.get_group(ParallelMode.PIPELINE)
+    src = parallel_context.get_ranks_in_group(ParallelMode.PIPELINE)[-1]
+    buf = loss.detach().float().reshape(1).clone()
+    if dist.get_backend(group) == "nccl" and not buf.is_cuda:
+        buf = buf.cuda()
+    dist.broadcast(buf, src=src, group=group)
+    return buf.reshape(()).to(loss.device)
+
 class _P2PLink:
     """Point-to-point ops with the previous / next pipeline stage."""
 
@@ -313,7 +330,7 @@ class PipelineEngine:
             total = torch.stack(losses).sum()
         else:
             total = torch.zeros((), device=dev)
-        return total
+        return broadcast_loss_from_last_stage(total, self.parallel_context)
 
     def sync_tied_embedding_grad(self):
         """Sum the tied embedding / lm_head table's gradient over the first and last stage."""

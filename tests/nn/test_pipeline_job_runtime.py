@@ -319,8 +319,7 @@ def run_job_engine(rank, world_size, port, pp, state, ids, ref_loss, ref_grads):
     engine = model._pg_pipeline_engine
     for _ in range(2):  # a second step re-uses the workers and starts new tracker rounds
         out = model(ids, labels=ids)
-        if rank == pp - 1:
-            assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+        assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)  # broadcast from the last stage
         for p in model._pg_pipeline_stage.parameters():
             assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
     # the tracker saw every task of the last (backward) schedule (earlier stages may still be finishing theirs)

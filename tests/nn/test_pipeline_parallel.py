@@ -151,8 +151,7 @@ def run_1f1b_bloom(rank, world_size, port, pp, sched, state, ids, ref_loss, ref_
     names = {id(p): n for n, p in model.named_parameters()}
     model = PipelineParallel(model, num_microbatches=4, parallel_context=ctx, scheduler_type=sched).parallelize()
     out = model(ids, labels=ids)
-    if rank == pp - 1:
-        assert torch.allclose(out.loss, ref_loss, atol=1e-5)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-5)  # computed on the last stage, broadcast to every stage
     out.loss.backward()  # harmless: the schedule already ran backward
     for p in model._pg_pipeline_stage.parameters():
         n = names[id(p)]
@@ -248,3 +247,30 @@ def test_pipeline_parallel_deparallelize_restores_the_model(pp):
     with torch.no_grad():
         ref = model(ids).logits
     spawn(run_pp_deparallelize, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_logits=ref)
+
+
+def run_engine_facade(rank, world_size, port, state, ids, ref_loss):
+    from pipegoose_b200.nn.pipeline_parallel.pipeline import _PipelineEngine
+    from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    with pytest.raises(ValueError):
+        _PipelineEngine(model, num_concurrent=2, max_concurrent=1, parallel_context=ctx)
+    with pytest.raises(TypeError):
+        _PipelineEngine(model, parallel_context=None)
+    engine = _PipelineEngine(model, scheduler=SchedulerType.GPIPE, parallel_context=ctx, num_microbatches=2)
+    assert engine.parallelize() is model
+    loss = engine(ids, labels=ids).loss
+    assert torch.allclose(loss.detach().float().cpu(), ref_loss, atol=1e-5)
+    ctx.destroy()
+
+
+def test_pipeline_engine_facade_runs_a_pipelined_step():
+    """Reference nn/pipeline_parallel/pipeline.py (_PipelineEngine, a stub there) as a working front door."""
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    ids = torch.randint(0, 96, (4, 8))
+    ref = torch.stack([model(c, labels=c).loss for c in ids.chunk(2)]).mean().detach()
+    spawn(run_engine_facade, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=ref)
