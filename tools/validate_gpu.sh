@@ -49,6 +49,23 @@ if [ "$N" -ge 4 ]; then
   echo "== convergence: TP2 x DP2 + ZeRO-1 (bf16, fused kernels) next to a single-GPU model"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29535 examples/convergence_hybrid.py --tp 2 --dp 2 --steps 60 2>&1 | grep "^step\|^loss" | tee gpurun_out/convergence_tp2dp2.txt | tail -5
 fi
+if [ "$N" -ge 8 ]; then
+  echo "== BASELINE.json configs #3-#5 (first runs at full size: each under its own timeout)"
+  for cfg in "--model bloom-7b1 --tp 8 --seq-len 2048 --batch-per-gpu 1" \
+             "--tp 8 --experts 8" \
+             "--model bloom-3b --tp 2 --pp 2 --microbatches 8 --batch-per-gpu 2"; do
+    echo "-- bench.py --gpus 8 $cfg"
+    timeout 420 python bench.py --gpus 8 --steps 5 --warmup 3 $cfg 2>&1 | grep "^{" | tee -a gpurun_out/bench_8gpu_other_configs.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['config']['model'], d['config']['parallelism'], round(d['ms_per_step'], 2), 'ms/step', round(d['value']), 'tok/s', 'loss', d['final_loss'])
+"
+  done
+  echo "-- fused TP kernels at bloom-7b1 shapes (T=8)"
+  TPB_MODEL=7b1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29537 tools/tp_bench.py 2>&1 | grep "^{" | cut -c1-300
+  echo "-- fused MoE layer (T=8)"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29538 tools/moe_bench.py 2>&1 | grep "^{" | cut -c1-400
+fi
 echo "== 1-GPU step breakdown (ncu launch list)"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py > /dev/null 2>&1
 python tools/step_profile.py --aggregate gpurun_out/step_launches.csv gpurun_out/step_breakdown.json | head -22
