@@ -178,8 +178,18 @@ def run_ours(args):
     host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen).pin_memory() for _ in range(n_host)]
     dev_ids = host_ids[0].to(dev)
 
+    def total_loss(ids):
+        loss = model(ids, labels=ids).loss
+        if args.experts > 0:
+            # Switch training objective: task loss + load-balancing and router-z terms the MoE layers pushed
+            from pipegoose_b200.nn.expert_parallel import ExpertContext
+
+            store = ExpertContext.get_instance()
+            loss = loss + 0.01 * sum(store.pop_all_aux_loss()) + 0.001 * sum(store.pop_all_z_loss())
+        return loss
+
     def step_device(i):
-        loss = model(dev_ids, labels=dev_ids).loss
+        loss = total_loss(dev_ids)
         optim.zero_grad()
         loss.backward()
         optim.step()
@@ -189,7 +199,7 @@ def run_ours(args):
 
     def step_e2e(i):
         ids = host_ids[i % n_host].to(dev, non_blocking=True)
-        loss = model(ids, labels=ids).loss
+        loss = total_loss(ids)
         optim.zero_grad()
         loss.backward()
         optim.step()
