@@ -35,13 +35,14 @@ class Experts(nn.Module):
         # sharded: this rank holds a slice of the layer's experts and the outputs are summed over the group
         self.sharded = not enable_tensor_parallel
         self.experts = nn.ModuleList([deepcopy(expert) for _ in range(num_local_experts)])
-        self._set_expert_attr(self.experts)
+        self._set_expert_attr(self.experts, replicated=not self.sharded)
 
     @staticmethod
-    def _set_expert_attr(experts: nn.ModuleList):
+    def _set_expert_attr(experts: nn.ModuleList, replicated: bool = False):
         # expert parameters are averaged over the EXPERT_DATA group by DataParallel
         for p in experts.parameters():
             p.is_expert = True
+            p._pg_expert_replicated = replicated  # every tensor-group rank holds this expert (norms count it once)
 
     def _first_global_expert(self) -> int:
         if not self.sharded:
@@ -114,6 +115,6 @@ class Experts(nn.Module):
                     full[r * El + j] = clone
             self.experts = nn.ModuleList(full)
             self.num_local_experts = T * El
-            self._set_expert_attr(self.experts)
         self.sharded = False
+        self._set_expert_attr(self.experts, replicated=True)
         return self

@@ -40,6 +40,8 @@ class PipelineParallel(Parallel):
             else:
                 engine = PipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
             engine.tied_group, engine.tied_param = _tied_embedding_group(module, ctx)
+            if engine.tied_group is not None and engine.tied_param is not None:
+                engine.tied_param._pg_pp_shared = 2  # lives on the first and the last stage (global norms: half each)
             _drop_foreign_parameters(module, stage)
             module._pg_pipeline_stage = stage
             module._pg_pipeline_engine = engine

@@ -1,4 +1,5 @@
+from pipegoose_b200.optim.clip import clip_grad_norm_, global_grad_norm
 from pipegoose_b200.optim.fused_adam import FusedAdam
 from pipegoose_b200.optim.zero.optim import DistributedOptimizer
 
-__all__ = ["DistributedOptimizer", "FusedAdam"]
+__all__ = ["DistributedOptimizer", "FusedAdam", "clip_grad_norm_", "global_grad_norm"]

@@ -28,6 +28,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._segments: Optional[List[Tuple[int, int]]] = None  # [(flat_start, flat_end)] owned by this rank
         self._step = 0
         self.master = self.exp_avg = self.exp_avg_sq = None
+        self.pending_grad_scale = 1.0  # set by optim.clip.clip_grad_norm_, applied once by the next step()
 
     def ensure_flat(self):
         if self.flat is None:
@@ -70,6 +71,7 @@ class FusedAdam(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         self._lazy_init()
         self._fold_autograd_grads()
+        grad_scale, self.pending_grad_scale = grad_scale * self.pending_grad_scale, 1.0
         self._step += 1
         for off, s, e, gi in self._plan():
             n = e - s

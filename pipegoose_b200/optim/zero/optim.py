@@ -146,6 +146,13 @@ class DistributedOptimizer(BaseDistributedOptimizer):
         if self.dp > 1:
             self._broadcast_updated_params()
 
+    def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
+        """Clip the norm of the whole model's gradient (every parameter counted once across the tensor / pipeline /
+        data groups, optim/clip.py); call between ``backward()`` and ``step()``.  Returns the norm before clipping."""
+        from pipegoose_b200.optim.clip import clip_grad_norm_
+
+        return clip_grad_norm_(self, max_norm, self.parallel_context)
+
     def zero_grad(self):
         if self._fused:
             if not self._zero_ready:
