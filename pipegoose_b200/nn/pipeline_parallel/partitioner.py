@@ -103,8 +103,10 @@ class BloomStage(nn.Module):
             else:
                 B, S = batch_seq
                 h = x
+            from pipegoose_b200.models.bloom import run_block
+
             for block in self.h:
-                h = block(h, B, S)
+                h = run_block(block, h, B, S, self.config)
             if not self.is_last:
                 return h
             if labels is not None:

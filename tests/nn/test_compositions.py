@@ -20,13 +20,16 @@ CFG = dict(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)
 STEPS = 3
 
 
-def run_tp_dp_generic(rank, world_size, port, tp, dp, state, ids, ref_losses):
+def run_tp_dp_generic(rank, world_size, port, tp, dp, state, ids, ref_losses, recompute="none"):
     ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
-    model = BloomForCausalLM(BloomConfig(**CFG))
+    model = BloomForCausalLM(BloomConfig(**CFG, recompute=recompute))
     model.load_state_dict(state)
     model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
-    optim = DistributedOptimizer(torch.optim.Adam(model.parameters(), lr=1e-2), ctx)
+    if recompute == "block":  # activation recomputation with the fused optimizer: wgrads accumulate into main_grad
+        optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    else:
+        optim = DistributedOptimizer(torch.optim.Adam(model.parameters(), lr=1e-2), ctx)
     local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
     losses = []
     for _ in range(STEPS):
@@ -43,8 +46,8 @@ def run_tp_dp_generic(rank, world_size, port, tp, dp, state, ids, ref_losses):
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,dp", [(2, 2)])
-def test_fast_bloom_tp_dp_with_generic_zero1(tp, dp):
+@pytest.mark.parametrize("tp,dp,recompute", [(2, 2, "none"), (2, 2, "block")])
+def test_fast_bloom_tp_dp_with_generic_zero1(tp, dp, recompute):
     torch.manual_seed(0)
     model = BloomForCausalLM(BloomConfig(**CFG))
     state = copy.deepcopy(model.state_dict())
@@ -60,7 +63,8 @@ def test_fast_bloom_tp_dp_with_generic_zero1(tp, dp):
             total += loss.item()
         opt.step()
         ref_losses.append(total)
-    spawn(run_tp_dp_generic, world_size=tp * dp, tp=tp, dp=dp, state=state, ids=ids, ref_losses=ref_losses)
+    spawn(run_tp_dp_generic, world_size=tp * dp, tp=tp, dp=dp, state=state, ids=ids, ref_losses=ref_losses,
+          recompute=recompute)
 
 
 def run_moe(rank, world_size, port, tp, dp, state, gate_state, ids, out_file):

@@ -44,3 +44,32 @@ def test_config_presets_and_flops():
     assert m.lm_head.weight is m.transformer.word_embeddings.weight  # tied
     assert m.num_parameters() == sum(p.numel() for p in set(m.parameters()))
     assert m.flops_per_token(128) > 6 * (12 * 16 * 16 + 64 * 16)
+
+
+def test_block_recompute_gives_identical_loss_and_gradients():
+    """config.recompute="block": same numbers, fewer saved activations."""
+    import copy
+
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+    torch.manual_seed(0)
+    base = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=3, n_head=4))
+    ckpt = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=3, n_head=4, recompute="block"))
+    ckpt.load_state_dict(copy.deepcopy(base.state_dict()))
+    ids = torch.randint(0, 96, (2, 8))
+    saved = {}
+    for name, model in (("base", base), ("ckpt", ckpt)):
+        count = [0]
+
+        def pack(t, count=count):
+            count[0] += t.numel()
+            return t
+
+        with torch.autograd.graph.saved_tensors_hooks(pack, lambda t: t):
+            loss = model(ids, labels=ids).loss
+        saved[name] = count[0]
+        loss.backward()
+    assert torch.equal(base(ids, labels=ids).loss, ckpt(ids, labels=ids).loss)
+    for (n, a), (_, b) in zip(base.named_parameters(), ckpt.named_parameters()):
+        assert torch.allclose(a.grad, b.grad, atol=1e-6), n
+    assert saved["ckpt"] < 0.6 * saved["base"], saved
