@@ -31,7 +31,10 @@ class ParallelEmbedding(nn.Module):
             local_ids = (inputs - self.vocab_start_idx).masked_fill(outside, 0)
         else:
             outside, local_ids = None, inputs
-        out = F.embedding(local_ids, self.weight)
+        pad = getattr(self, "padding_idx", None)   # class-swapped nn.Embedding: the padding row still gets no gradient
+        if pad is not None and self.world_size > 1:
+            pad = pad - self.vocab_start_idx if self.vocab_start_idx <= pad < self.vocab_end_idx else None
+        out = F.embedding(local_ids, self.weight, padding_idx=pad)
         if outside is not None:
             out = out.masked_fill(outside.unsqueeze(-1), 0.0)
         return reduce_to_tensor_group(out, self.parallel_context)

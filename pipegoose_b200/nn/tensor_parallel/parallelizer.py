@@ -101,9 +101,16 @@ class LinearParallelizer(ModuleParallelizer):
 
 
 class EmbeddingParallelizer(ModuleParallelizer):
+    # token-embedding names of the supported 🤗 families (Bloom / BERT / Albert, OPT / LLaMA, GPT-NeoX, GPT-2);
+    # position / token-type tables and embedding subclasses with their own forward (scaled embeddings) stay as they are
+    TOKEN_EMBEDDING_NAMES = ("word_embeddings", "embed_tokens", "embed_in", "wte")
+
     @staticmethod
     def is_parallelizable(module_name: str, module: nn.Module) -> bool:
-        return isinstance(module, nn.Embedding) and "word_embeddings" in module_name
+        if "word_embeddings" in module_name:
+            return isinstance(module, nn.Embedding)
+        leaf = module_name.rsplit(".", 1)[-1]
+        return type(module) is nn.Embedding and leaf in EmbeddingParallelizer.TOKEN_EMBEDDING_NAMES
 
     def parallelize(self) -> nn.Module:
         module, ctx = self.module, self.parallel_context
@@ -176,6 +183,18 @@ class LMHeadParallelizer(ModuleParallelizer):
                 weight = torch.cat([weight, weight.new_zeros(padded - vocab, weight.shape[1])], dim=0)
             module.weight = nn.Parameter(get_partition(weight, ctx, dim=0), requires_grad=module.weight.requires_grad)
             _mark_sliced(module.weight)
+        if module.bias is not None and not _is_sliced(module.bias):
+            # heads with an output bias (BERT's ``cls.predictions.decoder``): slice it like the rows of the weight
+            world = ctx.get_world_size(ParallelMode.TENSOR)
+            old, bias = module.bias, module.bias.data
+            padded = module.weight.shape[0] * world
+            if padded != bias.shape[0]:
+                bias = torch.cat([bias, bias.new_zeros(padded - bias.shape[0])])
+            module.bias = nn.Parameter(get_partition(bias, ctx, dim=0), requires_grad=old.requires_grad)
+            _mark_sliced(module.bias)
+            for other in self.model.modules():  # 🤗 keeps a second handle on the same bias (``predictions.bias``)
+                if other is not module and getattr(other, "bias", None) is old:
+                    other.bias = module.bias
         module.__class__ = ColumnParallelLinear
         module.gather_output = True
         module.parallel_context = ctx
