@@ -36,10 +36,14 @@ class ExpertParallel(Parallel):
         self.enable_tensor_parallelism = enable_tensor_parallelism
         self.fused = fused
 
-    @staticmethod
-    def _blocks(module: nn.Module):
-        pattern = re.compile(r"^transformer\.h\.(\d+)$")
-        return [(int(pattern.match(n).group(1)), m) for n, m in module.named_modules() if pattern.match(n)]
+    # where the transformer blocks live: Bloom / GPT-2 (the reference's only case, expert_parallel.py:60-66), LLaMA-style
+    # decoders and GPT-NeoX; a block qualifies when it has an ``mlp`` child to replace
+    BLOCK_PATTERN = re.compile(r"^(?:transformer\.h|model\.layers|gpt_neox\.layers)\.(\d+)$")
+
+    @classmethod
+    def _blocks(cls, module: nn.Module):
+        return [(int(cls.BLOCK_PATTERN.match(n).group(1)), m) for n, m in module.named_modules()
+                if cls.BLOCK_PATTERN.match(n) and hasattr(m, "mlp")]
 
     @classmethod
     def _num_blocks(cls, module: nn.Module) -> int:

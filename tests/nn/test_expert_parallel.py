@@ -197,3 +197,26 @@ def run_expert_deparallelize(rank, world_size, port, fused_layer):
 @pytest.mark.parametrize("fused_layer", [False, True])
 def test_expert_parallel_deparallelize_gathers_all_experts(fused_layer):
     spawn(run_expert_deparallelize, world_size=2, fused_layer=fused_layer)
+
+
+def test_expert_parallel_on_a_llama_style_model():
+    """Blocks are found under ``model.layers.N`` too (the reference only knows ``transformer.h.N``)."""
+    import transformers as T
+
+    def run(rank, world_size, port):
+        ctx = init_parallel_context(rank, world_size, port, 1, 1, 1)
+        torch.manual_seed(0)
+        cfg = T.LlamaConfig(vocab_size=96, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                            num_key_value_heads=4, max_position_embeddings=32)
+        model = T.LlamaForCausalLM(cfg)
+        ids = torch.randint(0, 96, (2, 8))
+        dense = model(input_ids=ids, labels=ids).loss.detach()
+        model = ExpertParallel(model, 2, mapping=[1], router=DummyRouter(2), parallel_context=ctx).parallelize()
+        assert isinstance(model.model.layers[1].mlp, ExpertLayer) and not isinstance(model.model.layers[0].mlp, ExpertLayer)
+        loss = model(input_ids=ids, labels=ids).loss
+        assert torch.allclose(loss, dense, atol=1e-5)   # experts are copies of the dense MLP, one expert per token
+        loss.backward()
+        assert all(p.grad is not None for p in model.model.layers[1].mlp.experts.parameters())
+        ctx.destroy()
+
+    run(0, 1, __import__("pipegoose_b200.testing.utils", fromlist=["find_free_port"]).find_free_port())
