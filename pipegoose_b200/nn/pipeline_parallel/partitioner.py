@@ -181,6 +181,47 @@ class GPT2Stage(nn.Module):
         return logits
 
 
+class RotaryDecoderStage(nn.Module):
+    """A contiguous slice of a 🤗 LLaMA-style causal LM (``model.{embed_tokens,layers,norm,rotary_emb}`` + ``lm_head``:
+    LLaMA, Mistral, Qwen2, ... — pre-norm blocks with rotary position embeddings).  Every stage recomputes the rotary
+    tables from its own (parameter-free) ``rotary_emb`` and builds the additive causal mask, so only hidden states
+    travel between stages."""
+
+    def __init__(self, model: nn.Module, start: int, end: int, is_first: bool, is_last: bool):
+        super().__init__()
+        base = model.model
+        self.is_first, self.is_last = is_first, is_last
+        if is_first:
+            self.embed_tokens = base.embed_tokens
+        self.layers = nn.ModuleList([base.layers[i] for i in range(start, end)])
+        self.rotary_emb = base.rotary_emb
+        if is_last:
+            self.norm = base.norm
+            self.lm_head = model.lm_head
+
+    def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                labels: Optional[torch.Tensor] = None, batch_seq=None):
+        h = self.embed_tokens(x) if self.is_first else x
+        B, S = h.shape[:2]
+        pos = torch.arange(S, device=h.device)[None]
+        rope = self.rotary_emb(h, pos)
+        hidden = torch.ones(S, S, dtype=torch.bool, device=h.device).triu(1)[None, None]
+        if attention_mask is not None:  # padding: keys of padded positions are invisible
+            hidden = hidden | (attention_mask[:, None, None, :] == 0)
+        mask = torch.zeros(B, 1, S, S, dtype=h.dtype, device=h.device).masked_fill(hidden, torch.finfo(h.dtype).min)
+        for layer in self.layers:
+            out = layer(h, attention_mask=mask, position_ids=pos, position_embeddings=rope)
+            h = out[0] if isinstance(out, tuple) else out
+        if not self.is_last:
+            return h
+        logits = self.lm_head(self.norm(h))
+        if labels is not None:
+            shift_logits = logits[..., :-1, :].contiguous().float()
+            shift_labels = labels[..., 1:].contiguous()
+            return torch.nn.functional.cross_entropy(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.view(-1))
+        return logits
+
+
 class UniformPartitioner:
     def __init__(self, module: nn.Module, parallel_context: ParallelContext):
         self.module = module
@@ -209,12 +250,16 @@ class UniformPartitioner:
             b = _balanced_cuts(costs, n)
             return [SequentialStage(layers[b[i]:b[i + 1]]) for i in range(n)]
         blocks = self._block_list(model)
-        assert blocks is not None and hasattr(model, "transformer"), \
-            "UniformPartitioner supports nn.Sequential, Bloom-style and GPT-2-style causal LMs"
+        rotary = blocks is not None and hasattr(getattr(model, "model", None), "rotary_emb") and hasattr(model, "lm_head")
+        assert blocks is not None and (hasattr(model, "transformer") or rotary), \
+            "UniformPartitioner supports nn.Sequential, Bloom-style, GPT-2-style and LLaMA-style causal LMs"
         assert len(blocks) >= n, "more pipeline stages than transformer blocks"
         costs = [sum(p.numel() for p in blk.parameters()) for blk in blocks]  # embeddings excluded, as in the reference
         b = _balanced_cuts(costs, n)
-        stage_cls = GPT2Stage if hasattr(model.transformer, "wte") else BloomStage
+        if rotary:
+            stage_cls = RotaryDecoderStage
+        else:
+            stage_cls = GPT2Stage if hasattr(model.transformer, "wte") else BloomStage
         return [stage_cls(model, b[i], b[i + 1], is_first=(i == 0), is_last=(i == n - 1)) for i in range(n)]
 
 

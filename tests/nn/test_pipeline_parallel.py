@@ -179,6 +179,12 @@ def _hf_model(family):
 
         return GPT2LMHeadModel(GPT2Config(vocab_size=96, n_positions=32, n_embd=32, n_layer=6, n_head=4,
                                           resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0))
+    if family == "llama":
+        from transformers import LlamaConfig, LlamaForCausalLM
+
+        return LlamaForCausalLM(LlamaConfig(vocab_size=96, hidden_size=32, intermediate_size=64, num_hidden_layers=6,
+                                            num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=32,
+                                            tie_word_embeddings=True))
     from transformers import BloomConfig as HFBloomConfig
     from transformers import BloomForCausalLM as HFBloom
 
@@ -190,7 +196,7 @@ def run_hf_partitioner(rank, world_size, port, pp, family, state, ids, ref_logit
     model = _hf_model(family)
     model.load_state_dict(state)
     stages = UniformPartitioner(model, ctx).split(["input_ids"])
-    assert len(stages) == pp and sum(len(s.h) for s in stages) == 6
+    assert len(stages) == pp and sum(len(s.h if hasattr(s, "h") else s.layers) for s in stages) == 6
     x = ids
     with torch.no_grad():
         for s in stages:  # the reference's acceptance test: chained partitions reproduce the full model's logits
@@ -208,7 +214,7 @@ def run_hf_partitioner(rank, world_size, port, pp, family, state, ids, ref_logit
     ctx.destroy()
 
 
-@pytest.mark.parametrize("family,pp", [("gpt2", 3), ("bloom", 2)])
+@pytest.mark.parametrize("family,pp", [("gpt2", 3), ("bloom", 2), ("llama", 2)])
 def test_partitioner_and_engine_on_hf_models(family, pp):
     torch.manual_seed(0)
     model = _hf_model(family).eval()
