@@ -33,6 +33,9 @@ def find_free_port(min_port: int = 2000, max_port: int = 65000) -> int:
 
 
 def _entry(rank: int, world_size: int, port: int, func: Callable, kwargs: dict):
+    if not torch.cuda.is_available() and world_size > 1:
+        # CPU ranks share the host's cores: one intra-op thread each (world_size x all-cores threads only contend)
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world_size))
     func(rank=rank, world_size=world_size, port=port, **kwargs)
 
 

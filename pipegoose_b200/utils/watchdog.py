@@ -6,8 +6,9 @@ Two small tools, both host-side and off the hot path:
 * :class:`RankWatchdog` — every rank publishes a heartbeat counter in the job's c10d key-value store (the TCPStore
   that ``init_process_group`` created; no extra sockets, no collectives, nothing on the GPU) from a daemon thread,
   and checks its peers' counters.  A peer whose counter has not moved for ``timeout_s`` is reported through
-  ``on_failure(dead_ranks)``; the default handler prints every thread's stack and interrupts the main thread, which
-  turns a silent hang into a ``RankFailure`` at the next Python instruction boundary.
+  ``on_failure(dead_ranks)``; the default handler prints every thread's stack and sends the process a SIGINT, which
+  turns a silent hang into a ``RankFailure`` (and, with ``abort_after_s``, ends a process whose main thread is stuck
+  inside a CUDA / NCCL call so that the launcher can restart the job).
 * :func:`step_deadline` — ``with step_deadline(120): train_step()`` dumps all thread stacks (``faulthandler``) when a
   step overruns, which is what one wants to see from a job that is stuck inside NCCL or a spinning flag wait.
 """
@@ -34,7 +35,7 @@ class RankFailure(RuntimeError):
 class RankWatchdog:
     def __init__(self, parallel_context=None, timeout_s: float = 60.0, interval_s: float = 1.0,
                  on_failure: Optional[Callable[[List[int]], None]] = None, ranks: Optional[List[int]] = None,
-                 store=None, tag: str = "watchdog"):
+                 store=None, tag: str = "watchdog", abort_after_s: Optional[float] = None):
         """``ranks``: the global ranks to watch (default: the whole job).  ``store``: any c10d ``Store`` (default: the
         job's own)."""
         self.rank = parallel_context.get_global_rank() if parallel_context is not None else dist.get_rank()
@@ -43,6 +44,7 @@ class RankWatchdog:
         base = store if store is not None else dist.distributed_c10d._get_default_store()
         self.store = dist.PrefixStore(f"pg_b200/{tag}", base)
         self.timeout_s, self.interval_s = float(timeout_s), float(interval_s)
+        self.abort_after_s = abort_after_s  # default handler only: hard-exit if the main thread ignores the interrupt
         self.on_failure = on_failure or self._default_handler
         self.failed: List[int] = []
         self._stop = threading.Event()
@@ -132,10 +134,20 @@ class RankWatchdog:
     def _default_handler(self, dead: List[int]):
         sys.stderr.write(f"[pipegoose_b200 watchdog] rank {self.rank}: ranks {dead} stopped responding\n")
         faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
-        import _thread
+        import os
+        import signal
 
         self._pending_failure = RankFailure(dead)
-        _thread.interrupt_main()  # KeyboardInterrupt in the main thread; callers may convert it with ``translate()``
+        # a real SIGINT (not ``_thread.interrupt_main``): it also wakes a main thread blocked in sleep / select / a
+        # lock; callers convert the resulting KeyboardInterrupt with ``translate()``
+        os.kill(os.getpid(), signal.SIGINT)
+        if self.abort_after_s is not None:
+            # a main thread stuck inside a CUDA / NCCL call never returns to the interpreter: give it a grace period,
+            # then end the process so that the launcher (torchrun --max-restarts) can restart the job
+            if not self._stop.wait(self.abort_after_s):
+                sys.stderr.write(f"[pipegoose_b200 watchdog] rank {self.rank}: main thread did not react, exiting\n")
+                sys.stderr.flush()
+                os._exit(1)
 
     @contextmanager
     def translate(self):

@@ -19,7 +19,7 @@ def run_watchdog(rank, world_size, port, scenario):
     if rank == 1:
         # "silent": the heartbeat thread dies without saying goodbye (a crashed / wedged rank);  "clean": orderly exit
         wd.stop(announce=(scenario == "clean"))
-        time.sleep(4.0)
+        time.sleep(2.5)
     else:
         if scenario == "interrupt":
             with pytest.raises(RankFailure) as info:
