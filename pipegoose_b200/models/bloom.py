@@ -39,6 +39,11 @@ class BloomConfig:
     # "block": keep only each block's input and recompute its activations during backward (~1/3 more forward FLOPs
     # for ~n_layer x fewer saved activations); "none": save everything (default, fastest)
     recompute: str = "none"
+    # architecture switches used by the other model families built from the same blocks (models/gpt2.py):
+    # "alibi" (Bloom) or "learned" absolute position embeddings; LayerNorm right after the token embedding or not
+    position_embedding: str = "alibi"
+    n_positions: int = 0
+    embedding_layernorm: bool = True
 
     @classmethod
     def from_hf(cls, hf_config) -> "BloomConfig":
@@ -94,6 +99,7 @@ class BloomAttention(nn.Module):
         self.head_dim = h // config.n_head
         self.query_key_value = nn.Linear(h, 3 * h, bias=True)
         self.dense = nn.Linear(h, h, bias=True)
+        self.use_alibi = getattr(config, "position_embedding", "alibi") == "alibi"
         self._slopes_cache = {}
 
 
@@ -152,7 +158,10 @@ def _alibi_slopes_local(self: BloomAttention, n_head_local: int) -> torch.Tensor
     key = (n_head_local, str(device))
     slopes = self._slopes_cache.get(key)
     if slopes is None:
-        full = K.alibi_slopes(self.num_heads, device=device)
+        if getattr(self, "use_alibi", True):
+            full = K.alibi_slopes(self.num_heads, device=device)
+        else:  # no position bias inside attention (learned absolute positions): the flash kernel runs with zero slopes
+            full = torch.zeros(self.num_heads, dtype=torch.float32, device=device)
         rank = getattr(self, "tp_rank", 0) if n_head_local != self.num_heads else 0
         slopes = full[rank * n_head_local:(rank + 1) * n_head_local].contiguous()
         self._slopes_cache[key] = slopes
@@ -185,6 +194,20 @@ def fused_layer_norm(x, gamma, beta, eps=1e-5):
     return _LayerNormFn.apply(x, gamma, beta, eps)
 
 
+def embed_tokens(owner: nn.Module, input_ids: torch.Tensor, config, vocab_start: int, tp) -> torch.Tensor:
+    """Token ids -> ``[tokens_local, hidden]`` input of the first block.  ``owner`` holds ``word_embeddings`` and either
+    ``word_embeddings_layernorm`` (Bloom) or ``position_embeddings`` (GPT-2): the model's ``transformer`` or a first
+    pipeline stage."""
+    if getattr(config, "position_embedding", "alibi") == "learned":
+        assert input_ids.shape[-1] <= config.n_positions, "sequence longer than the position table"
+        assert not getattr(config, "embedding_layernorm", False)
+        return PF.embedding_positions(input_ids, owner.word_embeddings.weight, owner.position_embeddings.weight,
+                                      vocab_start, tp)
+    ln = owner.word_embeddings_layernorm
+    return PF.embedding_layernorm(input_ids, owner.word_embeddings.weight, ln.weight, ln.bias,
+                                  config.layer_norm_epsilon, vocab_start, tp)
+
+
 def run_block(block: nn.Module, x: torch.Tensor, batch: int, seq: int, config) -> torch.Tensor:
     """One transformer block, with activation recomputation when ``config.recompute == "block"`` (training only)."""
     if getattr(config, "recompute", "none") == "block" and torch.is_grad_enabled() and x.requires_grad:
@@ -200,7 +223,11 @@ class BloomModel(nn.Module):
         h = config.hidden_size
         self.config = config
         self.word_embeddings = nn.Embedding(config.vocab_size, h)
-        self.word_embeddings_layernorm = nn.LayerNorm(h, eps=config.layer_norm_epsilon)
+        if config.embedding_layernorm:
+            self.word_embeddings_layernorm = nn.LayerNorm(h, eps=config.layer_norm_epsilon)
+        if config.position_embedding == "learned":
+            assert config.n_positions > 0, "learned position embeddings need n_positions"
+            self.position_embeddings = nn.Embedding(config.n_positions, h)
         self.h = nn.ModuleList([BloomBlock(config) for _ in range(config.n_layer)])
         self.ln_f = nn.LayerNorm(h, eps=config.layer_norm_epsilon)
 
@@ -263,9 +290,7 @@ class BloomForCausalLM(nn.Module):
     def hidden_states(self, input_ids: torch.Tensor) -> torch.Tensor:
         t = self.transformer
         B, S = input_ids.shape
-        x = PF.embedding_layernorm(input_ids, t.word_embeddings.weight, t.word_embeddings_layernorm.weight,
-                                   t.word_embeddings_layernorm.bias, self.config.layer_norm_epsilon,
-                                   self.vocab_start, self.tp)
+        x = embed_tokens(t, input_ids, self.config, self.vocab_start, self.tp)
         for block in t.h:
             x = run_block(block, x, B, S, self.config)
         return x

@@ -80,7 +80,9 @@ class BloomStage(nn.Module):
         self.fast = hasattr(model, "hidden_states")  # our fused model
         if is_first:
             self.word_embeddings = t.word_embeddings
-            self.word_embeddings_layernorm = t.word_embeddings_layernorm
+            for name in ("word_embeddings_layernorm", "position_embeddings"):  # Bloom / GPT-2 style front end
+                if hasattr(t, name):
+                    setattr(self, name, getattr(t, name))
         self.h = nn.ModuleList([t.h[i] for i in range(start, end)])
         if is_last:
             self.ln_f = t.ln_f
@@ -98,8 +100,9 @@ class BloomStage(nn.Module):
             eps = self.config.layer_norm_epsilon
             if self.is_first:
                 B, S = x.shape
-                h = PF.embedding_layernorm(x, self.word_embeddings.weight, self.word_embeddings_layernorm.weight,
-                                           self.word_embeddings_layernorm.bias, eps, model.vocab_start, model.tp)
+                from pipegoose_b200.models.bloom import embed_tokens
+
+                h = embed_tokens(self, x, self.config, model.vocab_start, model.tp)
             else:
                 B, S = batch_seq
                 h = x

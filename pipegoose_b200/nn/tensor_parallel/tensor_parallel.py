@@ -203,8 +203,11 @@ def _parallelize_fast_bloom(model, ctx: ParallelContext):
     def partial(p):  # gradient is a partial sum over this rank's token shard
         p.tp_partial_grad = True
 
-    for ln in (t.word_embeddings_layernorm, t.ln_f):
-        partial(ln.weight), partial(ln.bias)
+    for ln in (getattr(t, "word_embeddings_layernorm", None), t.ln_f):
+        if ln is not None:
+            partial(ln.weight), partial(ln.bias)
+    if hasattr(t, "position_embeddings"):  # replicated; every rank sees the positions of its token shard only
+        partial(t.position_embeddings.weight)
     for block in t.h:
         attn, mlp = block.self_attention, block.mlp
         attn.query_key_value.weight = _slice_param(attn.query_key_value.weight, ctx, 0)  # whole heads

@@ -378,6 +378,53 @@ class EmbeddingLayerNorm(torch.autograd.Function):
         return None, dtable, dgamma, dbeta, None, None, None
 
 
+class EmbeddingPositions(torch.autograd.Function):
+    """``table[ids] + positions[pos]`` for models with learned position embeddings (GPT-2), vocab-parallel and
+    sequence-parallel aware: under TP every rank gathers the rows of its vocabulary slice for ALL tokens, the partial
+    results are reduce-scattered over the token dimension, and the position rows of the LOCAL tokens are added.  The
+    backward scatter-adds into the table's fp32 main grad like :class:`EmbeddingLayerNorm`; the position-table gradient
+    is a partial sum over this rank's tokens (the parameter is tagged ``tp_partial_grad``)."""
+
+    @staticmethod
+    def forward(ctx, ids, table, positions, vocab_start, tp):
+        vocab_end = vocab_start + table.shape[0]
+        flat = ids.reshape(-1)
+        seq = ids.shape[-1]
+        dummy = positions[0]  # gamma / beta arguments of the gather kernel (unused with apply_ln=False)
+        part, _, _ = K.layernorm_fwd(table, dummy, dummy, 0.0, ids=flat, vocab_start=vocab_start, vocab_end=vocab_end,
+                                     apply_ln=False)
+        e = tp.reduce_scatter_rows(part.contiguous()) if tp is not None else part
+        rows = e.shape[0]
+        first = tp.rank * rows if tp is not None else 0
+        pos = (torch.arange(rows, device=e.device) + first) % seq
+        ctx.save_for_backward(flat, table, positions, pos)
+        ctx.tp = tp
+        ctx.vocab_start = vocab_start
+        return e + positions.index_select(0, pos)
+
+    @staticmethod
+    def backward(ctx, dy):
+        flat, table, positions, pos = ctx.saved_tensors
+        tp, vocab_start = ctx.tp, ctx.vocab_start
+        vocab_end = vocab_start + table.shape[0]
+        dy = dy.contiguous()
+        dpos = torch.zeros(positions.shape, dtype=torch.float32, device=dy.device).index_add_(0, pos, dy.float())
+        mg_pos = _main_grad(positions)
+        if mg_pos is not None:
+            acc, accumulate = acquire_main_grad(positions, will_overwrite=True)
+            acc.add_(dpos) if accumulate else acc.copy_(dpos)
+            notify_grad_ready(positions)
+            dpos = None
+        else:
+            dpos = dpos.to(positions.dtype)
+        de_full = tp.all_gather_rows(dy) if tp is not None else dy
+        mg = acquire_main_grad(table, will_overwrite=False)[0] if _main_grad(table) is not None else None
+        dtable = K.embedding_bwd(de_full, flat, table.shape[0], vocab_start, vocab_end, accum_into=mg)
+        if mg is not None:
+            notify_grad_ready(table)
+        return None, dtable, dpos, None, None
+
+
 class LMHeadCrossEntropy(torch.autograd.Function):
     """``mean CE(LayerNorm(x) @ table^T, labels)`` with a vocab-parallel softmax.
 
@@ -463,6 +510,10 @@ def mlp_residual(x, w1, b1, w2, b2, residual=None):
 
 def embedding_layernorm(ids, table, gamma, beta, eps=1e-5, vocab_start=0, tp=None):
     return EmbeddingLayerNorm.apply(ids, table, gamma, beta, eps, vocab_start, tp)
+
+
+def embedding_positions(ids, table, positions, vocab_start=0, tp=None):
+    return EmbeddingPositions.apply(ids, table, positions, vocab_start, tp)
 
 
 def lm_head_cross_entropy(x, gamma, beta, table, labels, eps=1e-5, vocab_start=0, ignore_index=-100, tp=None):
