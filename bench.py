@@ -151,9 +151,15 @@ def run_ours(args):
                                      backend="nccl")
     rank = ctx.get_global_rank()
     dev = torch.device("cuda", torch.cuda.current_device())
-    cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
     torch.manual_seed(1234)
-    model = BloomForCausalLM(cfg).to(torch.bfloat16)
+    if args.model.startswith("gpt2"):  # not a BASELINE.json config: the second model family on the same kernels
+        from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+        cfg = getattr(GPT2Config, args.model.replace("-", "_"))()
+        model = GPT2LMHeadModel(cfg).to(torch.bfloat16)
+    else:
+        cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
+        model = BloomForCausalLM(cfg).to(torch.bfloat16)
     if args.experts > 0:
         from pipegoose_b200.nn import ExpertParallel
         from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router

@@ -22,7 +22,7 @@ if __name__ == "__main__":
     ap.add_argument("--tp", type=int, default=2)
     ap.add_argument("--pp", type=int, default=1)
     ap.add_argument("--dp", type=int, default=2)
-    ap.add_argument("--model", default="bloom_560m")
+    ap.add_argument("--model", default="bloom_560m", help="bloom_tiny | bloom_560m | bloom_1b7 | bloom_3b | bloom_7b1 | gpt2_tiny | gpt2 | gpt2_medium | gpt2_large")
     ap.add_argument("--batch", type=int, default=8, help="sequences per data-parallel replica")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=20)
@@ -34,8 +34,14 @@ if __name__ == "__main__":
         tensor_parallel_size=args.tp, pipeline_parallel_size=args.pp, data_parallel_size=args.dp, backend=args.backend)
     rank = parallel_context.get_global_rank()
 
-    cfg = getattr(BloomConfig, args.model)()
-    model = BloomForCausalLM(cfg)
+    if args.model.startswith("gpt2"):  # the GPT-2 family runs on the same fused blocks (models/gpt2.py)
+        from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+        cfg = getattr(GPT2Config, args.model)()
+        model = GPT2LMHeadModel(cfg)
+    else:
+        cfg = getattr(BloomConfig, args.model)()
+        model = BloomForCausalLM(cfg)
     if args.backend == "nccl":
         model = model.to(torch.bfloat16)
     model = TensorParallel(model, parallel_context).parallelize()
