@@ -54,7 +54,7 @@ def run_context(rank, world_size, port, tp, pp, dp):
     assert ParallelContext.get_context() is None
 
 
-@pytest.mark.parametrize("world_size,tp,pp,dp", [(1, 1, 1, 1), (8, 2, 2, 2), (4, 2, 1, 2)])
+@pytest.mark.parametrize("world_size,tp,pp,dp", [(1, 1, 1, 1), (8, 2, 2, 2), (4, 2, 1, 2), (16, 2, 4, 2)])
 def test_parallel_context(world_size, tp, pp, dp):
     spawn(run_context, world_size=world_size, tp=tp, pp=pp, dp=dp)
 

@@ -46,7 +46,7 @@ def run_tp_dp_generic(rank, world_size, port, tp, dp, state, ids, ref_losses, re
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,dp,recompute", [(2, 2, "none"), (2, 2, "block")])
+@pytest.mark.parametrize("tp,dp,recompute", [(2, 2, "none"), (2, 1, "none"), (2, 2, "block"), (4, 1, "block")])
 def test_fast_bloom_tp_dp_with_generic_zero1(tp, dp, recompute):
     torch.manual_seed(0)
     model = BloomForCausalLM(BloomConfig(**CFG))

@@ -43,7 +43,7 @@ def run(rank, world_size, port, tp, pp, dp, n_mb, state, ids, ref_losses):
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,pp,dp", [(2, 2, 2)])
+@pytest.mark.parametrize("tp,pp,dp", [(2, 2, 2), (1, 2, 2), (2, 2, 1), (1, 4, 2)])
 def test_3d_training_follows_single_process(tp, pp, dp):
     torch.manual_seed(0)
     model = BloomForCausalLM(BloomConfig(**CFG))

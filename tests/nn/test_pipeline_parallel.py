@@ -214,7 +214,7 @@ def run_hf_partitioner(rank, world_size, port, pp, family, state, ids, ref_logit
     ctx.destroy()
 
 
-@pytest.mark.parametrize("family,pp", [("gpt2", 3), ("bloom", 2), ("llama", 2)])
+@pytest.mark.parametrize("family,pp", [("gpt2", 2), ("gpt2", 3), ("bloom", 2), ("bloom", 3), ("llama", 2), ("llama", 3)])
 def test_partitioner_and_engine_on_hf_models(family, pp):
     torch.manual_seed(0)
     model = _hf_model(family).eval()

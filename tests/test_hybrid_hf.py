@@ -54,7 +54,7 @@ def run_hybrid(rank, world_size, port, tp, dp, state, ids, ref_loss, ref_params)
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,dp", [(2, 2)])
+@pytest.mark.parametrize("tp,dp", [(2, 1), (2, 2), (4, 1)])
 def test_hf_bloom_tensor_x_data_parallel_one_adam_step(tp, dp):
     torch.manual_seed(0)
     model = _hf_bloom()
