@@ -164,6 +164,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._segments = [tuple(x) for x in sd["segments"]]
         self._lazy_init()
         self._step = sd["step"]
+        for group, saved in zip(self.param_groups, sd.get("param_groups", [])):
+            group.update({k: v for k, v in saved.items() if k != "params"})  # lr (schedulers), betas, eps, weight decay
         self.master.copy_(sd["master"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -89,6 +89,12 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             self._reducer.mode = "reduce_scatter"
             optim.set_bucket_shards(self._reducer.bucket_numel, self.dp_rank, self.dp)
         self._zero_ready = True
+        pending = getattr(self, "_pending_state", None)
+        if pending is not None:
+            self._pending_state = None
+            want = [tuple(x) for x in pending[0]["segments"]]
+            assert want == list(optim._segments), "the checkpointed optimizer shard does not match this layout"
+            optim.load_state_dict(pending[0], *pending[1], **pending[2])
 
     def _all_gather_params(self):
         flat = self.optim.flat
@@ -126,8 +132,12 @@ class DistributedOptimizer(BaseDistributedOptimizer):
     def add_param_group(self, *args, **kwargs):
         self.optim.add_param_group(*args, **kwargs)
 
-    def load_state_dict(self, *args, **kwargs):
-        self.optim.load_state_dict(*args, **kwargs)
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        if self._fused and not self._zero_ready and self.dp > 1:
+            # the ZeRO-1 slices are laid out when the gradient reducer exists (first forward): apply the state then
+            self._pending_state = (state_dict, args, kwargs)
+            return
+        self.optim.load_state_dict(state_dict, *args, **kwargs)
 
     def state_dict(self, *args, **kwargs):
         return self.optim.state_dict(*args, **kwargs)

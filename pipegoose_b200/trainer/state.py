@@ -24,3 +24,4 @@ class TrainerState:
     step: int = 0
     tokens_seen: int = 0
     last_loss: float = float("nan")
+    last_grad_norm: float = float("nan")

@@ -1,6 +1,7 @@
-"""A minimal working trainer (the reference's Trainer.fit/train bodies are ``pass``,
-trainer/trainer.py:13-35): epochs over a dataloader of ``{"input_ids", ["attention_mask"], ["labels"]}``
-batches, loss/backward/step, callbacks, tokens/s logging with device-side timing."""
+"""A working trainer (the reference's Trainer.fit/train bodies are ``pass``, trainer/trainer.py:13-35): epochs over a
+dataloader of ``{"input_ids", ["attention_mask"], ["labels"]}`` batches, loss/backward/step, callbacks, tokens/s
+logging — plus what a long run needs: gradient accumulation (``no_sync`` on all but the last micro-step), global
+gradient-norm clipping, an LR scheduler, periodic sharded checkpoints with resume, and a rank watchdog."""
 from __future__ import annotations
 
 import time
@@ -17,7 +18,16 @@ from pipegoose_b200.trainer.state import TrainerStage, TrainerState, TrainerStat
 class Trainer:
     def __init__(self, module: nn.Module, train_loader, eval_loader=None, optim=None, num_epochs: int = 1,
                  callbacks: Optional[List[Callback]] = None, loggers: Optional[List[DistributedLogger]] = None,
-                 parallel_context=None, log_every: int = 10):
+                 parallel_context=None, log_every: int = 10, grad_accum_steps: int = 1,
+                 max_grad_norm: Optional[float] = None, lr_scheduler=None, checkpoint_dir: Optional[str] = None,
+                 checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None):
+        """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
+        norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
+        ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
+        and optimizer / RNG / step state (save_training_state) every N optimizer steps; ``resume=True`` restores the
+        latest one before training and skips the batches it had consumed.  ``watchdog_timeout_s``: start a
+        :class:`RankWatchdog` for the duration of ``fit``."""
+        assert grad_accum_steps >= 1
         self.module = module
         self.train_loader = train_loader
         self.eval_loader = eval_loader
@@ -27,7 +37,16 @@ class Trainer:
         self.loggers = loggers or []
         self.parallel_context = parallel_context
         self.log_every = log_every
+        self.grad_accum_steps = grad_accum_steps
+        self.max_grad_norm = max_grad_norm
+        self.lr_scheduler = lr_scheduler
+        self.checkpoint_dir = checkpoint_dir
+        self.checkpoint_every = checkpoint_every
+        self.resume = resume
+        self.watchdog_timeout_s = watchdog_timeout_s
         self.state = TrainerState()
+        self._micro = 0
+        self._skip_batches = 0
 
     def _device(self):
         return next(self.module.parameters()).device
@@ -41,21 +60,87 @@ class Trainer:
             lg.info(msg)
 
     def train_step(self, batch) -> torch.Tensor:
+        """One micro-batch: forward + backward; the optimizer steps on every ``grad_accum_steps``-th call."""
+        from contextlib import nullcontext
+
         dev = self._device()
         batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
         labels = batch.pop("labels", batch["input_ids"])
-        out = self.module(**batch, labels=labels)
-        loss = out.loss if hasattr(out, "loss") else out[0]
-        self.optim.zero_grad()
-        loss.backward()
-        self.optim.step()
+        first = self._micro == 0
+        last = self._micro == self.grad_accum_steps - 1
+        no_sync = getattr(self.module, "no_sync", None)
+        with (no_sync() if (no_sync is not None and not last) else nullcontext()):
+            out = self.module(**batch, labels=labels)
+            loss = out.loss if hasattr(out, "loss") else out[0]
+            if first:
+                self.optim.zero_grad()   # after the forward, as in the reference's README loop
+            (loss / self.grad_accum_steps if self.grad_accum_steps > 1 else loss).backward()
         self.state.tokens_seen += int(batch["input_ids"].numel())
+        self._micro += 1
+        if last:
+            self._micro = 0
+            if self.max_grad_norm is not None:
+                from pipegoose_b200.optim.clip import clip_grad_norm_
+
+                ctx = self.parallel_context if self.parallel_context is not None else _SingleProcess()
+                self.state.last_grad_norm = float(clip_grad_norm_(self.optim, self.max_grad_norm, ctx))
+            self.optim.step()
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step()
+            self.state.step += 1
+            if self.checkpoint_dir and self.checkpoint_every and self.state.step % self.checkpoint_every == 0:
+                self.save_checkpoint()
         return loss
+
+    # ------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self):
+        from pipegoose_b200.nn.utils import save_pretrained, save_training_state
+
+        ctx = self.parallel_context
+        assert ctx is not None, "checkpoints are sharded by (tp, pp, dp) rank: a ParallelContext is required"
+        save_pretrained(self.module, ckp_path=self.checkpoint_dir, parallel_context=ctx)
+        extra = {"epoch": self.state.epoch, "tokens_seen": self.state.tokens_seen,
+                 "lr_scheduler": self.lr_scheduler.state_dict() if hasattr(self.lr_scheduler, "state_dict") else None}
+        save_training_state(self.optim, self.checkpoint_dir, ctx, step=self.state.step, extra=extra)
+        self._log(f"checkpoint written at step {self.state.step} -> {self.checkpoint_dir}")
+
+    def load_checkpoint(self) -> bool:
+        """Restore the latest checkpoint of ``checkpoint_dir`` if there is one; returns whether it did."""
+        from pipegoose_b200.nn.utils import _optim_file, from_pretrained, load_training_state
+
+        ctx = self.parallel_context
+        if ctx is None or not self.checkpoint_dir:
+            return False
+        import os
+
+        if not os.path.exists(_optim_file(self.checkpoint_dir, ctx)):
+            return False
+        from_pretrained(self.module, ckp_path=self.checkpoint_dir, parallel_context=ctx)
+        meta = load_training_state(self.optim, self.checkpoint_dir, ctx)
+        self.state.step = meta["step"]
+        extra = meta.get("extra") or {}
+        self.state.tokens_seen = extra.get("tokens_seen", 0)
+        if self.lr_scheduler is not None and extra.get("lr_scheduler") is not None:
+            self.lr_scheduler.load_state_dict(extra["lr_scheduler"])
+        self._skip_batches = self.state.step * self.grad_accum_steps
+        self._log(f"resumed from step {self.state.step}")
+        return True
 
     def fit(self):
         self.state.status = TrainerStatus.RUNNING
+        if self.resume:
+            self.load_checkpoint()
+        watchdog = None
+        if self.watchdog_timeout_s is not None and self.parallel_context is not None:
+            from pipegoose_b200.utils.watchdog import RankWatchdog
+
+            watchdog = RankWatchdog(self.parallel_context, timeout_s=self.watchdog_timeout_s).start()
         self._call("on_fit_start")
-        self.train()
+        try:
+            self.train()
+        finally:
+            if watchdog is not None:
+                watchdog.stop()
         self._call("on_fit_end")
         self.state.status = TrainerStatus.FINISHED
         return self.state
@@ -64,18 +149,23 @@ class Trainer:
         self.state.stage = TrainerStage.TRAINING
         self.module.train()
         t0, tok0 = time.time(), self.state.tokens_seen
+        seen = 0
         for epoch in range(self.num_epochs):
             self.state.epoch = epoch
             self._call("on_epoch_start")
             for batch in self.train_loader:
+                seen += 1
+                if seen <= self._skip_batches:   # consumed before the checkpoint this run resumed from
+                    continue
+                before = self.state.step
                 loss = self.train_step(batch)
-                self.state.step += 1
-                if self.state.step % self.log_every == 0:
-                    self.state.last_loss = float(loss.item())
-                    dt = max(time.time() - t0, 1e-9)
-                    self._log(f"step {self.state.step} loss {self.state.last_loss:.4f} "
-                              f"tokens/s {(self.state.tokens_seen - tok0) / dt:.0f}")
-                self._call("on_step_end", loss)
+                if self.state.step != before:
+                    if self.state.step % self.log_every == 0:
+                        self.state.last_loss = float(loss.item())
+                        dt = max(time.time() - t0, 1e-9)
+                        self._log(f"step {self.state.step} loss {self.state.last_loss:.4f} "
+                                  f"tokens/s {(self.state.tokens_seen - tok0) / dt:.0f}")
+                    self._call("on_step_end", loss)
             self._call("on_epoch_end")
 
     @torch.no_grad()
@@ -92,3 +182,10 @@ class Trainer:
             total += float((out.loss if hasattr(out, "loss") else out[0]).item())
             n += 1
         return total / max(n, 1)
+
+
+class _SingleProcess:
+    """Stands in for a ParallelContext when the trainer runs without one (every group has one member)."""
+
+    def get_world_size(self, mode):
+        return 1

@@ -106,3 +106,47 @@ def run_resume(rank, world_size, port, tp, dp, ckp_path):
 @pytest.mark.parametrize("world,tp,dp", [(1, 1, 1), (4, 2, 2)])
 def test_resume_from_sharded_optimizer_checkpoint(tmp_path, world, tp, dp):
     spawn(run_resume, world_size=world, tp=tp, dp=dp, ckp_path=str(tmp_path / "ckpt"))
+
+
+def run_trainer_resume(rank, world_size, port, tp, dp, ckp_dir):
+    from pipegoose_b200.nn import DataParallel, TensorParallel
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    cfg = BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)
+    g = torch.Generator().manual_seed(11 + ctx.get_local_rank(ParallelMode.DATA))
+    data = [{"input_ids": torch.randint(0, 96, (2, 8), generator=g)} for _ in range(12)]  # 12 micro-batches = 6 steps
+
+    def build(**kw):
+        torch.manual_seed(0)
+        model = BloomForCausalLM(cfg)
+        model = TensorParallel(model, ctx).parallelize()
+        model = DataParallel(model, ctx).parallelize()
+        optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2, eps=1e-3), ctx)
+        sched = torch.optim.lr_scheduler.LambdaLR(optim.optim, lambda step: 1.0 / (1 + step))
+        trainer = Trainer(model, data, optim=optim, parallel_context=ctx, grad_accum_steps=2, max_grad_norm=0.05,
+                          lr_scheduler=sched, **kw)
+        return model, optim, trainer
+
+    # uninterrupted run: 6 optimizer steps
+    model_a, optim_a, trainer_a = build()
+    state = trainer_a.fit()
+    assert state.step == 6 and state.tokens_seen == 12 * 16 and state.last_grad_norm > 0.05
+    assert abs(optim_a.optim.param_groups[0]["lr"] - 1e-2 / 7) < 1e-9
+    # interrupted after 4 steps (checkpoint every 2) ...
+    model_b, optim_b, trainer_b = build(checkpoint_dir=ckp_dir, checkpoint_every=2)
+    trainer_b.train_loader = data[:8]
+    assert trainer_b.fit().step == 4
+    # ... and resumed by a fresh process-local model / optimizer / trainer
+    model_c, optim_c, trainer_c = build(checkpoint_dir=ckp_dir, checkpoint_every=0, resume=True)
+    state = trainer_c.fit()
+    assert state.step == 6 and state.tokens_seen == 12 * 16
+    for (n, a), (_, c) in zip(model_a.named_parameters(), model_c.named_parameters()):
+        assert torch.allclose(a, c, atol=1e-6), n
+    assert abs(optim_c.optim.param_groups[0]["lr"] - 1e-2 / 7) < 1e-9
+    ctx.destroy()
+
+
+def test_trainer_accumulates_clips_schedules_checkpoints_and_resumes(tmp_path):
+    spawn(run_trainer_resume, world_size=4, tp=2, dp=2, ckp_dir=str(tmp_path / "run"))
