@@ -1,15 +1,34 @@
-"""Pipeline exceptions (parity: reference nn/pipeline_parallel/exception.py:1-14, plus PipelineScheduleError)."""
-class PipelineGradientFlowError(Exception):
-    """Gradients did not flow to a stage boundary."""
+"""What can go wrong inside a pipeline schedule (parity: reference nn/pipeline_parallel/exception.py:1-14; the schedule
+error is new).  All share :class:`PipelineError`, and the two lookup failures say which (micro-batch, partition) slot was
+asked for, because "no saved activation" without coordinates is undebuggable in a 1F1B steady state."""
 
 
-class PipelineNoSavedActivationError(Exception):
-    """No saved activation for the requested (microbatch, partition)."""
+class PipelineError(RuntimeError):
+    pass
 
 
-class PipelineNoSavedInput(Exception):
-    """No saved input for the requested (microbatch, partition)."""
+class _SlotError(PipelineError, KeyError):
+    what = "entry"
+
+    def __init__(self, microbatch_idx=None, partition_idx=None):
+        where = "" if microbatch_idx is None else f" for micro-batch {microbatch_idx}, partition {partition_idx}"
+        super().__init__(f"no saved {self.what}{where}")
+
+    def __str__(self):
+        return self.args[0]
 
 
-class PipelineScheduleError(Exception):
-    """The static schedule is inconsistent (e.g. backward before forward)."""
+class PipelineNoSavedActivationError(_SlotError):
+    what = "activation"
+
+
+class PipelineNoSavedInput(_SlotError):
+    what = "input"
+
+
+class PipelineGradientFlowError(PipelineError):
+    """A stage boundary received no gradient: the graph between the stage's input and its output is broken."""
+
+
+class PipelineScheduleError(PipelineError):
+    """The static schedule is inconsistent (e.g. a backward task before its forward)."""

@@ -86,8 +86,7 @@ def get_input_activations(microbatch_idx: int, partition_idx: int):
     try:
         return InputActivations.get_saved_activations((microbatch_idx, partition_idx))
     except KeyError:
-        raise PipelineNoSavedInput(
-            f"no saved input for microbatch_idx={microbatch_idx}, partition_idx={partition_idx}") from None
+        raise PipelineNoSavedInput(microbatch_idx, partition_idx) from None
 
 
 def save_output_activations(output, microbatch_idx: int, partition_idx: int):
@@ -101,8 +100,7 @@ def get_output_activations(microbatch_idx: int, partition_idx: int, is_pipeline:
         try:
             out = _SAVED_ACTIVATIONS[(microbatch_idx, partition_idx)]
         except KeyError:
-            raise PipelineNoSavedActivationError(
-                f"no saved activation for microbatch_idx={microbatch_idx}, partition_idx={partition_idx}") from None
+            raise PipelineNoSavedActivationError(microbatch_idx, partition_idx) from None
     if is_pipeline:
         return out
     return out.detach().requires_grad_(True)

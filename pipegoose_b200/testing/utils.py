@@ -40,7 +40,10 @@ def _entry(rank: int, world_size: int, port: int, func: Callable, kwargs: dict):
 
 
 _FORKSERVER_PRELOAD = ["torch", "torch.distributed", "pipegoose_b200", "pipegoose_b200.nn", "pipegoose_b200.optim",
-                       "pipegoose_b200.models.bloom", "pipegoose_b200.testing.utils"]
+                       "pipegoose_b200.models.bloom", "pipegoose_b200.testing.utils",
+                       "pipegoose_b200.nn.data_parallel.data_parallel", "pipegoose_b200.nn.tensor_parallel.tensor_parallel",
+                       "pipegoose_b200.nn.pipeline_parallel.pipeline_parallel",
+                       "pipegoose_b200.nn.expert_parallel.expert_parallel"]
 _start_method_cache = None
 
 
