@@ -124,6 +124,11 @@ class JobPipelineEngine:
                 pkg = recv_package(nxt, ctx)
             self._run_job(create_job(self.module, pkg, ctx, self.pipeline_context))
         self._sync_tied_embedding_grad()
+        # the job runtime mirrors the reference: router losses of MoE stages are not part of its objective; drain them so
+        # that they (and their graphs) do not pile up across steps
+        from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+        ExpertContext.get_instance().pop_all_aux_loss(), ExpertContext.get_instance().pop_all_z_loss()
         total = torch.stack(losses).sum() if self.is_last else torch.zeros(())
         total = broadcast_loss_from_last_stage(total, self.parallel_context)
         return CausalLMOutput(loss=total.detach().requires_grad_(True), logits=None)

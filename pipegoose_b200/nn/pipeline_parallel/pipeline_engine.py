@@ -160,6 +160,9 @@ class PipelineEngine:
         self._anchor = None
         self.tied_group = None
         self.tied_param = None
+        # weights of the MoE router losses every stage adds to its backward (ExpertLoss defaults; 0 disables a term)
+        self.aux_loss_weight = 0.01
+        self.z_loss_weight = 0.001
 
     # ------------------------------------------------------------------ helpers
     def _device(self):
@@ -258,6 +261,7 @@ class PipelineEngine:
         saved_out: Dict[int, torch.Tensor] = {}
         recv_act: Dict[int, torch.Tensor] = {}
         recv_grad: Dict[int, torch.Tensor] = {}
+        saved_aux: Dict[int, torch.Tensor] = {}
         losses = []
         reducer = getattr(self.full_module, "_pg_grad_reducer", None) if self.full_module is not None else None
         if reducer is None and self.full_module is not None:
@@ -296,12 +300,17 @@ class PipelineEngine:
                     x = recv_act.pop(i).requires_grad_(True)
                 out = self._stage_forward(x, mbs[i], True)
                 saved_in[i] = x
+                extra = self._moe_auxiliary_loss()   # router losses of THIS stage's MoE layers for this micro-batch
                 if self.is_last:
                     loss = out / m
+                    if extra is not None:
+                        loss = loss + extra / m
                     saved_out[i] = loss
-                    losses.append(loss.detach())
+                    losses.append((out / m).detach())   # reported: the language-model loss, as without pipelining
                 else:
                     saved_out[i] = out
+                    if extra is not None:
+                        saved_aux[i] = extra / m
                     pending_send = (out.detach(), self.link.next)
             else:
                 out = saved_out.pop(i)
@@ -312,7 +321,11 @@ class PipelineEngine:
                     if self.is_last:
                         torch.autograd.backward(out)
                     else:
-                        torch.autograd.backward(out, recv_grad.pop(i))
+                        aux = saved_aux.pop(i, None)
+                        if aux is None:
+                            torch.autograd.backward(out, recv_grad.pop(i))
+                        else:  # second root: this stage's share of the auxiliary objective
+                            torch.autograd.backward([out, aux], [recv_grad.pop(i), torch.ones_like(aux)])
                 if not self.is_first:
                     pending_send = (x.grad, self.link.prev)
             if pending_send is not None:
@@ -331,6 +344,21 @@ class PipelineEngine:
         else:
             total = torch.zeros((), device=dev)
         return broadcast_loss_from_last_stage(total, self.parallel_context)
+
+    def _moe_auxiliary_loss(self) -> Optional[torch.Tensor]:
+        """Drain the expert context after a stage forward: ``aux_weight * sum(load-balancing) + z_weight * sum(router-z)``
+        of the MoE layers this stage ran (None without MoE layers).  Every stage back-propagates its own share — the
+        reference leaves the terms of all but the last stage unused, and never drains them."""
+        from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+        store = ExpertContext.get_instance()
+        aux, z = store.pop_all_aux_loss(), store.pop_all_z_loss()
+        terms = [self.aux_loss_weight * t for t in aux if self.aux_loss_weight] + \
+                [self.z_loss_weight * t for t in z if self.z_loss_weight]
+        terms = [t for t in terms if isinstance(t, torch.Tensor) and t.requires_grad]
+        if not terms:
+            return None
+        return torch.stack([t.float().reshape(()) for t in terms]).sum()
 
     def sync_tied_embedding_grad(self):
         """Sum the tied embedding / lm_head table's gradient over the first and last stage."""

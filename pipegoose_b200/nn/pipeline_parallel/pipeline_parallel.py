@@ -16,7 +16,8 @@ from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType, get_sch
 
 class PipelineParallel(Parallel):
     def __init__(self, module: nn.Module, num_microbatches: int, parallel_context: ParallelContext,
-                 scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B, runtime: str = "static"):
+                 scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B, runtime: str = "static",
+                 aux_loss_weight: float = 0.01, z_loss_weight: float = 0.001):
         """``runtime``: ``"static"`` (default) — schedule tables + batched p2p (pipeline_engine.py); ``"jobs"`` — the
         reference's execution model: jobs from packages, worker threads, progress tracker (job_engine.py, GPipe)."""
         super().__init__(module, parallel_context)
@@ -24,6 +25,8 @@ class PipelineParallel(Parallel):
         self.num_microbatches = num_microbatches
         self.scheduler_type = scheduler_type if runtime == "static" else SchedulerType.GPIPE
         self.runtime = runtime
+        # Switch-MoE stages: weights of the load-balancing / router-z losses each stage back-propagates (static runtime)
+        self.aux_loss_weight, self.z_loss_weight = aux_loss_weight, z_loss_weight
 
     @torch.no_grad()
     def parallelize(self) -> nn.Module:
@@ -39,6 +42,7 @@ class PipelineParallel(Parallel):
                 engine = JobPipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
             else:
                 engine = PipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
+            engine.aux_loss_weight, engine.z_loss_weight = self.aux_loss_weight, self.z_loss_weight
             engine.tied_group, engine.tied_param = _tied_embedding_group(module, ctx)
             if engine.tied_group is not None and engine.tied_param is not None:
                 engine.tied_param._pg_pp_shared = 2  # lives on the first and the last stage (global norms: half each)

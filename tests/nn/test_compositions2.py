@@ -214,3 +214,82 @@ def test_moe_blocks_inside_pipeline_stages(tmp_path):
 
     ref_run(31000 + os.getpid() % 2000)
     spawn(run_moe_pp, world_size=2, state=state, gate_state=gate_state, ids=ids, ref_loss=torch.load(f))
+
+
+def run_moe_4d(rank, world_size, port, tp, pp, dp, state, gate_state, ids, ref_losses, tol):
+    """ExpertParallel -> TensorParallel -> PipelineParallel -> DataParallel -> ZeRO-1: every stage back-propagates the
+    router losses of its own MoE layers, so the trajectory follows the unpartitioned MoE model trained on
+    LM + 0.01 aux + 0.001 z."""
+    from pipegoose_b200.nn import DataParallel
+    from pipegoose_b200.nn.expert_parallel import ExpertContext
+    from pipegoose_b200.optim import DistributedOptimizer
+
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, dp)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"])
+    router.load_state_dict(gate_state)
+    model = ExpertParallel(model, 2, mapping=[0, 3], router=router, parallel_context=ctx).parallelize()
+    model.eval()
+    model = TensorParallel(model, ctx).parallelize()
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    store = ExpertContext.get_instance()
+    for want in ref_losses:
+        loss = model(local, labels=local).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        assert not store.aux_loss and not store.z_loss          # drained by the engine, nothing piles up
+        t = loss.detach().float().reshape(1).clone()
+        torch.distributed.all_reduce(t)
+        assert abs(t.item() / world_size - want) < tol, (t.item() / world_size, ref_losses)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,tol", [(1, 3e-4), (2, 8e-3)])
+def test_moe_tensor_pipeline_data_parallel_training(tmp_path, tp, tol):
+    # tp=1: the pipeline reproduces the unpartitioned objective (router losses of every stage included) almost exactly;
+    # tp=2: the sequence-parallel MoE layers compute the load-balancing statistics over each rank's token shard, which
+    # perturbs the (0.01-weighted) auxiliary term slightly
+    torch.manual_seed(0)
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
+    gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"]).state_dict())
+    ids = torch.randint(0, 96, (8, 8))
+    dp, n_mb = 2, 2
+    f = str(tmp_path / "ref.pt")
+
+    def ref_run(port):
+        from pipegoose_b200.nn.expert_parallel import ExpertContext
+
+        ctx = init_parallel_context(0, 1, port, 1, 1, 1)
+        m = BloomForCausalLM(BloomConfig(**CFG))
+        m.load_state_dict(state)
+        r = Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"])
+        r.load_state_dict(gate_state)
+        m = ExpertParallel(m, 2, mapping=[0, 3], router=r, parallel_context=ctx).parallelize()
+        m.eval()
+        opt = FusedAdam(m.parameters(), lr=1e-2)
+        store = ExpertContext.get_instance()
+        chunks = [mb for rep in ids.chunk(dp) for mb in rep.chunk(n_mb)]
+        out = []
+        for _ in range(3):
+            opt.zero_grad()
+            lm_total = 0.0
+            for mb in chunks:
+                lm = m(mb, labels=mb).loss
+                total = lm + 0.01 * sum(store.pop_all_aux_loss()) + 0.001 * sum(store.pop_all_z_loss())
+                (total / len(chunks)).backward()
+                lm_total += lm.item() / len(chunks)
+            opt.step()
+            out.append(lm_total)
+        torch.save(out, f)
+        ctx.destroy()
+
+    ref_run(33000 + os.getpid() % 2000)
+    ref_losses = torch.load(f)
+    assert ref_losses[-1] < ref_losses[0]
+    spawn(run_moe_4d, world_size=tp * 2 * dp, tp=tp, pp=2, dp=dp, state=state, gate_state=gate_state, ids=ids,
+          ref_losses=ref_losses, tol=tol)
