@@ -24,6 +24,8 @@ from pipegoose_b200.nn.pipeline_parallel._job.forward import (
     SaveInputActivationsCallback,
     SendForwardPackageCallback,
 )
+from pipegoose_b200.nn.pipeline_parallel import queue as Q
+from pipegoose_b200.nn.pipeline_parallel._job.callback import Callback
 from pipegoose_b200.nn.pipeline_parallel._job.job import Job
 from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
 from pipegoose_b200.nn.pipeline_parallel._package import Package
@@ -35,9 +37,36 @@ class JobCreator(ABC):
         raise NotImplementedError
 
 
+class ScheduleBackwardJobCallback(Callback):
+    """The backward trigger as a forward-job callback (parity: reference _job/creator.py:36-61).  On the last stage
+    it swaps the job's output for the recording wrapper of :func:`schedule_backward_execution` and keeps it in the
+    scheduled-activations store, so whatever loss the caller computes from the job output, ``loss.backward()`` parks
+    d loss / d output in the grad-loss store where the backward jobs pick it up.  The reference runs the ENTIRE
+    backward schedule from inside that autograd hook (with sleeps and RPC); here the engine drives the backward tasks
+    from its static table, so every micro-batch is treated alike and no hook blocks autograd."""
+
+    order = 3
+
+    def __init__(self, parallel_context, pipeline_context=None):
+        self.parallel_context = parallel_context
+        self.pipeline_context = pipeline_context
+
+    def after_compute(self):
+        from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+        if not self.parallel_context.is_last_rank(ParallelMode.PIPELINE):
+            return
+        package = self.job.output
+        meta = package.metadata
+        recorded = schedule_backward_execution(package)
+        Q._SAVED_SCHEDULED_ACTIVATIONS[(meta.microbatch_idx, meta.partition_idx)] = recorded
+        self.job.output = Package(recorded, meta)
+
+
 class _ForwardJobCreator(JobCreator):
     @classmethod
-    def create(cls, function: Callable, package: Package, parallel_context, pipeline_context=None) -> ForwardJob:
+    def create(cls, function: Callable, package: Package, parallel_context, pipeline_context=None,
+               schedule_backward: bool = False) -> ForwardJob:
         cbs = [
             SaveInputActivationsCallback(),
             CreateForwardOutputPackageCallback(parallel_context, pipeline_context),
@@ -45,6 +74,8 @@ class _ForwardJobCreator(JobCreator):
             SendForwardPackageCallback(parallel_context),
             ConfirmCompleteATaskToProgressTracker(parallel_context),
         ]
+        if schedule_backward:
+            cbs.append(ScheduleBackwardJobCallback(parallel_context, pipeline_context))
         return ForwardJob(function, package, cbs)
 
 
@@ -62,10 +93,15 @@ class _BackwardJobCreator(JobCreator):
 _CREATORS = {JobType.FORWARD: _ForwardJobCreator, JobType.BACKWARD: _BackwardJobCreator}
 
 
-def create_job(function: Callable, package: Package, parallel_context, pipeline_context=None) -> Job:
-    """Forward or backward job for ``package`` with the standard callbacks."""
+def create_job(function: Callable, package: Package, parallel_context, pipeline_context=None,
+               schedule_backward: bool = False) -> Job:
+    """Forward or backward job for ``package`` with the standard callbacks (``schedule_backward``: forward jobs of the
+    last stage also get :class:`ScheduleBackwardJobCallback`)."""
     assert isinstance(package, Package), f"package must be a Package, got {type(package)}"
-    return _CREATORS[package.metadata.job_type].create(function, package, parallel_context, pipeline_context)
+    creator = _CREATORS[package.metadata.job_type]
+    if package.metadata.job_type is JobType.FORWARD:
+        return creator.create(function, package, parallel_context, pipeline_context, schedule_backward=schedule_backward)
+    return creator.create(function, package, parallel_context, pipeline_context)
 
 
 def schedule_backward_execution(package: Package):

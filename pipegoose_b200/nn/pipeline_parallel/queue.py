@@ -17,6 +17,7 @@ ActivationKey = Tuple[int, int]
 _LOCK = threading.RLock()
 _INPUT_ACTIVATIONS: Dict[ActivationKey, Any] = {}
 _SAVED_ACTIVATIONS: Dict[ActivationKey, Any] = {}
+_SAVED_SCHEDULED_ACTIVATIONS: Dict[ActivationKey, Any] = {}   # last-stage outputs wrapped for the backward trigger
 _SAVED_GRAD_LOSS: Dict[ActivationKey, torch.Tensor] = {}
 _SAVED_METADATA_of_GRAD_LOSS: Dict[ActivationKey, Any] = {}
 
@@ -119,6 +120,7 @@ def get_grad_loss(microbatch_idx: int, partition_idx: int) -> torch.Tensor:
 
 def clear_all():
     with _LOCK:
-        for d in (_INPUT_ACTIVATIONS, _SAVED_ACTIVATIONS, _SAVED_GRAD_LOSS, _SAVED_METADATA_of_GRAD_LOSS):
+        for d in (_INPUT_ACTIVATIONS, _SAVED_ACTIVATIONS, _SAVED_SCHEDULED_ACTIVATIONS, _SAVED_GRAD_LOSS,
+                  _SAVED_METADATA_of_GRAD_LOSS):
             d.clear()
     JobQueue.clear()

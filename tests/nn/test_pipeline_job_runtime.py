@@ -179,7 +179,7 @@ def test_send_recv_package(dtype):
     spawn(run_send_recv_package, world_size=2, dtype=dtype)
 
 
-def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, ref_input_grad, ref_loss):
+def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, ref_input_grad, ref_loss, use_callback=False):
     """Two stages, GPipe order, every step a job created by ``create_job`` from a package."""
     ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
     Q.clear_all()
@@ -209,12 +209,16 @@ def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, 
         for i in range(n_mb):
             pkg = recv_package(0, ctx)
             assert pkg.metadata.microbatch_idx == i and pkg.metadata.partition_idx == 1
-            job = create_job(stage, pkg, ctx)
+            job = create_job(stage, pkg, ctx, schedule_backward=use_callback)
             job.compute()
             outs.append(job.output)
         for i in reversed(range(n_mb)):
             # loss.backward() only records d loss / d output; the backward job replays it through the stage
-            y = schedule_backward_execution(outs[i])
+            if use_callback:   # ScheduleBackwardJobCallback already swapped the output for the recording wrapper
+                y = outs[i].data
+                assert y is Q._SAVED_SCHEDULED_ACTIVATIONS[(i, 1)] and y.requires_grad
+            else:
+                y = schedule_backward_execution(outs[i])
             loss = y.pow(2).sum() / batch.shape[0]
             losses.append(loss.item())
             loss.backward()
@@ -227,7 +231,8 @@ def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, 
     ctx.destroy()
 
 
-def test_forward_backward_jobs_match_sequential_execution():
+@pytest.mark.parametrize("use_callback", [False, True])
+def test_forward_backward_jobs_match_sequential_execution(use_callback):
     torch.manual_seed(1)
     stages = [nn.Sequential(nn.Linear(8, 8), nn.Tanh()) for _ in range(2)]
     batch = torch.randn(6, 8)
@@ -236,7 +241,7 @@ def test_forward_backward_jobs_match_sequential_execution():
     loss.backward()
     ref_grads = [{n: p.grad.clone() for n, p in s.named_parameters()} for s in stages]
     spawn(run_pipeline_of_jobs, world_size=2, state_dicts=[s.state_dict() for s in stages], batch=batch,
-          ref_grads=ref_grads, ref_input_grad=x.grad.clone(), ref_loss=loss.item())
+          ref_grads=ref_grads, ref_input_grad=x.grad.clone(), ref_loss=loss.item(), use_callback=use_callback)
 
 
 # ------------------------------------------------------------------------------------------ sync
