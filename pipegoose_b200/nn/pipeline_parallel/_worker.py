@@ -96,7 +96,17 @@ class WorkerPoolWatcher(threading.Thread):
                 self.spawn_worker()
 
 
-class WorkerManager:
+class BaseWorkerManager:
+    """Life cycle of a worker pool (parity: reference _worker.py:88-95)."""
+
+    def spawn(self):
+        raise NotImplementedError
+
+    def destroy(self):
+        raise NotImplementedError
+
+
+class WorkerManager(BaseWorkerManager):
     def __init__(self, num_workers: int = PIPELINE_MIN_WORKERS, min_workers: int = PIPELINE_MIN_WORKERS,
                  max_workers: int = PIPELINE_MAX_WORKERS, pending_jobs: Queue = None, selected_jobs: Queue = None):
         assert min_workers <= num_workers <= max_workers or (min_workers <= max_workers and num_workers <= max_workers)

@@ -30,5 +30,9 @@ class PipelineGradientFlowError(PipelineError):
     """A stage boundary received no gradient: the graph between the stage's input and its output is broken."""
 
 
+class PipelineInputNotRequiresGrad(PipelineError):
+    """A backward job was asked for the gradient of a stage input that does not require grad."""
+
+
 class PipelineScheduleError(PipelineError):
     """The static schedule is inconsistent (e.g. a backward task before its forward)."""

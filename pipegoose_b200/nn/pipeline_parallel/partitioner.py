@@ -225,7 +225,14 @@ class RotaryDecoderStage(nn.Module):
         return logits
 
 
-class UniformPartitioner:
+class BasePartitioner:
+    """``split(input_names) -> [stage modules]`` (parity: reference partitioner.py:20-26)."""
+
+    def split(self, input_names: Optional[List[str]] = None) -> List[nn.Module]:
+        raise NotImplementedError
+
+
+class UniformPartitioner(BasePartitioner):
     def __init__(self, module: nn.Module, parallel_context: ParallelContext):
         self.module = module
         self.parallel_context = parallel_context
@@ -266,10 +273,14 @@ class UniformPartitioner:
         return [stage_cls(model, b[i], b[i + 1], is_first=(i == 0), is_last=(i == n - 1)) for i in range(n)]
 
 
+def _get_partitioner(policy: PartitionPolicy):
+    """The partitioner class that implements ``policy``."""
+    return {PartitionPolicy.UNIFORM: UniformPartitioner}[policy]
+
+
 def get_model_partition(module: nn.Module, policy: PartitionPolicy, parallel_context: ParallelContext) -> nn.Module:
     """The stage of ``module`` that belongs to this rank."""
-    assert policy is PartitionPolicy.UNIFORM
-    stages = UniformPartitioner(module, parallel_context).split()
+    stages = _get_partitioner(policy)(module, parallel_context).split()
     from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
 
     return stages[get_partition_idx(parallel_context)]

@@ -29,7 +29,7 @@ class ParallelEmbedding(nn.Embedding):
         self.parallel_context = parallel_context
         self.world_size = group
         self.vocab_start_idx, self.vocab_end_idx = VocabUtility.get_vocab_range_from_global_vocab_size(
-            num_embeddings, parallel_context.get_local_rank(ParallelMode.TENSOR), group)
+            group, parallel_context.get_local_rank(ParallelMode.TENSOR), num_embeddings)
 
     def _local_padding_idx(self) -> Optional[int]:
         """The padding row keeps a zero gradient when it lives in this rank's block."""

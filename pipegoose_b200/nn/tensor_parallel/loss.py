@@ -23,7 +23,7 @@ class _VocabParallelCrossEntropy(torch.autograd.Function):
         world = parallel_context.get_world_size(ParallelMode.TENSOR)
         rank = parallel_context.get_local_rank(ParallelMode.TENSOR)
         v_local = parallel_logits.shape[-1]
-        vocab_start, _ = VocabUtility.get_vocab_range_from_per_partition_vocab_size(v_local, rank)
+        vocab_start, _ = VocabUtility.get_vocab_range_idx_from_partition_size(v_local, rank)
         logits2 = parallel_logits.reshape(-1, v_local)
         if not logits2.is_contiguous():
             logits2 = logits2.contiguous()

@@ -135,7 +135,7 @@ class EmbeddingParallelizer(ModuleParallelizer):
         module.parallel_context = ctx
         module.world_size = world
         module.num_embeddings = padded
-        module.vocab_start_idx, module.vocab_end_idx = VocabUtility.get_vocab_range_from_global_vocab_size(padded, rank, world)
+        module.vocab_start_idx, module.vocab_end_idx = VocabUtility.get_vocab_range_from_global_vocab_size(world, rank, padded)
         return module
 
     def deparallelize(self):

@@ -19,7 +19,19 @@ def _tensor_bytes(obj) -> int:
     return 0
 
 
-class ProfileByMemory:
+class ProfileStrategy:
+    """What a partitioning cost model looks like: ``profile(input) -> [cost per child]`` (parity: reference
+    partitioning/profile.py:9-16)."""
+
+    def __init__(self, module: nn.Module, device=None):
+        self.module = module
+        self.device = device
+
+    def profile(self, input: torch.Tensor) -> List[int]:
+        raise NotImplementedError
+
+
+class ProfileByMemory(ProfileStrategy):
     def __init__(self, module: nn.Sequential, device=None):
         self.module = module
         self.device = torch.device(device) if device is not None else (

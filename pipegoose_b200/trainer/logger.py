@@ -13,6 +13,17 @@ class DistributedLogger:
         self.stream = stream or sys.stdout
         self.records = []
 
+    LEVELS = {"DEBUG": 10, "INFO": 20, "WARNING": 30, "ERROR": 40}
+
+    def set_level(self, level: str = "INFO"):
+        """Messages below ``level`` are recorded but not printed."""
+        assert level in self.LEVELS, f"unknown level {level}"
+        self.level = level
+        return self
+
+    def log(self, msg: str, level: str = "INFO"):
+        self._log(level, msg)
+
     def _should_log(self) -> bool:
         if self.parallel_context is None:
             return True
@@ -20,7 +31,7 @@ class DistributedLogger:
 
     def _log(self, level: str, msg: str):
         self.records.append((level, msg))
-        if self._should_log():
+        if self._should_log() and self.LEVELS.get(level, 20) >= self.LEVELS[getattr(self, "level", "DEBUG")]:
             self.stream.write(f"[{time.strftime('%H:%M:%S')}] [{self.name}] [{level}] {msg}\n")
             self.stream.flush()
 

@@ -282,3 +282,34 @@ def test_padded_head_attention_is_exact(D):
     ref.backward(g)
     got.backward(g)
     assert torch.allclose(qkv2.grad, qkv.grad, atol=1e-6)
+
+
+def test_remaining_reference_symbols():
+    """Smaller public names of the reference that the other tests do not touch."""
+    import io
+
+    from pipegoose_b200.nn.pipeline_parallel._worker import BaseWorkerManager, WorkerManager
+    from pipegoose_b200.nn.pipeline_parallel.exception import PipelineError, PipelineInputNotRequiresGrad, PipelineNoSavedInput
+    from pipegoose_b200.nn.pipeline_parallel.partitioner import BasePartitioner, PartitionPolicy, UniformPartitioner, _get_partitioner
+    from pipegoose_b200.nn.pipeline_parallel.scheduler import GPipeScheduler
+    from pipegoose_b200.nn.pipeline_parallel.sync.progress_tracker import get_progresses_from_pipeline_context
+    from pipegoose_b200.partitioning.profile import ProfileByMemory, ProfileStrategy
+    from pipegoose_b200.trainer import DistributedLogger
+
+    assert _get_partitioner(PartitionPolicy.UNIFORM) is UniformPartitioner and issubclass(UniformPartitioner, BasePartitioner)
+    assert issubclass(WorkerManager, BaseWorkerManager) and issubclass(ProfileByMemory, ProfileStrategy)
+    assert issubclass(PipelineInputNotRequiresGrad, PipelineError)
+    assert "micro-batch 3, partition 1" in str(PipelineNoSavedInput(3, 1))
+
+    class Ctx:  # only ``schedules`` is read
+        schedules = GPipeScheduler(2, 2).get_schedules()
+
+    table = get_progresses_from_pipeline_context(Ctx)
+    assert len(table) == len(Ctx.schedules) and table[0] == {(0, 0): False}
+    assert all(v is False for clock in table.values() for v in clock.values())
+
+    stream = io.StringIO()
+    log = DistributedLogger(stream=stream).set_level("WARNING")
+    log.info("quiet"), log.warning("loud"), log.log("also loud", "ERROR")
+    assert "quiet" not in stream.getvalue() and "loud" in stream.getvalue() and "also loud" in stream.getvalue()
+    assert [lvl for lvl, _ in log.records] == ["INFO", "WARNING", "ERROR"]

@@ -108,5 +108,6 @@ def test_parallel_mapping():
 def test_vocab_utility():
     from pipegoose_b200.nn.tensor_parallel._utils import VocabUtility
 
+    assert VocabUtility.get_vocab_range_idx_from_partition_size(10, 2) == (20, 30)          # (partition_size, rank)
+    assert VocabUtility.get_vocab_range_from_global_vocab_size(4, 3, 40) == (30, 40)          # (world_size, rank, vocab_size)
     assert VocabUtility.get_vocab_range_from_per_partition_vocab_size(10, 2) == (20, 30)
-    assert VocabUtility.get_vocab_range_from_global_vocab_size(40, 3, 4) == (30, 40)
