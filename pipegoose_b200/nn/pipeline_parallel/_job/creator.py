@@ -47,7 +47,13 @@ class ScheduleBackwardJobCallback(Callback):
 
     order = 3
 
-    def __init__(self, parallel_context, pipeline_context=None):
+    def __init__(self, pipeline_context=None, parallel_context=None):
+        if parallel_context is None:
+            parallel_context = getattr(pipeline_context, "parallel_context", None)
+        if parallel_context is None:
+            from pipegoose_b200.distributed.parallel_context import ParallelContext
+
+            parallel_context = ParallelContext.get_context()
         self.parallel_context = parallel_context
         self.pipeline_context = pipeline_context
 
@@ -75,7 +81,7 @@ class _ForwardJobCreator(JobCreator):
             ConfirmCompleteATaskToProgressTracker(parallel_context),
         ]
         if schedule_backward:
-            cbs.append(ScheduleBackwardJobCallback(parallel_context, pipeline_context))
+            cbs.append(ScheduleBackwardJobCallback(pipeline_context, parallel_context))
         return ForwardJob(function, package, cbs)
 
 
@@ -104,7 +110,7 @@ def create_job(function: Callable, package: Package, parallel_context, pipeline_
     return creator.create(function, package, parallel_context, pipeline_context)
 
 
-def schedule_backward_execution(package: Package):
+def schedule_backward_execution(package: Package, pipeline_context=None):
     """Wrap the last stage's output so that ``loss.backward()`` records d loss / d output in the grad-loss
     store (``queue.get_grad_loss``) instead of flowing into the stage: backward jobs start from it."""
     return save_grad_loss(package)

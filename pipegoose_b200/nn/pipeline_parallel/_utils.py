@@ -24,6 +24,6 @@ def is_last_stage(parallel_context: ParallelContext) -> bool:
     return get_partition_idx(parallel_context) + 1 == parallel_context.pipeline_parallel_size
 
 
-def sleep(seconds: float = 0.05):
+def sleep(timeout: float = 0.05):
     """The reference's polling interval helper (:7-9).  Kept for API parity; nothing in this runtime polls."""
-    time.sleep(seconds)
+    time.sleep(timeout)

@@ -233,8 +233,8 @@ class BasePartitioner:
 
 
 class UniformPartitioner(BasePartitioner):
-    def __init__(self, module: nn.Module, parallel_context: ParallelContext):
-        self.module = module
+    def __init__(self, model: nn.Module, parallel_context: ParallelContext):
+        self.module = model
         self.parallel_context = parallel_context
 
     def _n_partitions(self) -> int:

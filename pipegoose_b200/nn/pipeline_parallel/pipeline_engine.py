@@ -144,8 +144,11 @@ class _SendToNext(torch.autograd.Function):
 
 
 class PipelineEngine:
-    def __init__(self, module: nn.Module, scheduler: BaseScheduler, parallel_context: ParallelContext,
-                 pipeline_context=None, full_module: Optional[nn.Module] = None):
+    def __init__(self, module: nn.Module, scheduler: BaseScheduler, worker_manager=None,
+                 parallel_context: ParallelContext = None, pipeline_context=None, full_module: Optional[nn.Module] = None):
+        # ``worker_manager``: the reference's third argument (pipeline_engine.py:36-58); the static runtime executes its
+        # schedule on the calling thread and only keeps the object for callers that pass one
+        self.worker_manager = worker_manager
         self.module = module  # this rank's stage
         self.full_module = full_module
         self.scheduler = scheduler

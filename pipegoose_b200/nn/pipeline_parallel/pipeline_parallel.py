@@ -41,7 +41,8 @@ class PipelineParallel(Parallel):
 
                 engine = JobPipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
             else:
-                engine = PipelineEngine(stage, scheduler, ctx, pipeline_context, full_module=module)
+                engine = PipelineEngine(stage, scheduler, parallel_context=ctx, pipeline_context=pipeline_context,
+                                        full_module=module)
             engine.aux_loss_weight, engine.z_loss_weight = self.aux_loss_weight, self.z_loss_weight
             engine.tied_group, engine.tied_param = _tied_embedding_group(module, ctx)
             if engine.tied_group is not None and engine.tied_param is not None:

@@ -24,9 +24,9 @@ _PROGRESS_TRACKER: Optional["ProgressTracker"] = None
 _INSTANCES = 0
 
 
-def set_progress_tracker(tracker):
+def set_progress_tracker(progress_tracker):
     global _PROGRESS_TRACKER
-    _PROGRESS_TRACKER = tracker
+    _PROGRESS_TRACKER = progress_tracker
 
 
 def get_progress_tracker() -> Optional["ProgressTracker"]:
@@ -61,11 +61,11 @@ class Handshake(ABC):
         ...
 
     @abstractmethod
-    def is_confirmed(self, *args, **kwargs) -> bool:
+    def is_confirmed(self, clock_idx: int = None) -> bool:
         ...
 
     @abstractmethod
-    def is_all_confirmed(self, *args, **kwargs) -> bool:
+    def is_all_confirmed(self, clock_idx: int = None) -> bool:
         ...
 
 

@@ -59,17 +59,18 @@ class _Reduce(torch.autograd.Function):
         return grad, None
 
 
-def broadcast_to_tensor_group(tensor, parallel_context):
-    return _Broadcast.apply(tensor, parallel_context)
+# keyword names as in the reference (``input=...``), so call sites written against it keep working
+def broadcast_to_tensor_group(input, parallel_context):  # noqa: A002
+    return _Broadcast.apply(input, parallel_context)
 
 
-def gather_to_tensor_group(tensor, dim, parallel_context):
-    return _Gather.apply(tensor, dim, parallel_context)
+def gather_to_tensor_group(input, dim, parallel_context):  # noqa: A002
+    return _Gather.apply(input, dim, parallel_context)
 
 
-def scatter_to_tensor_group(tensor, dim, parallel_context):
-    return _Scatter.apply(tensor, dim, parallel_context)
+def scatter_to_tensor_group(input, dim, parallel_context):  # noqa: A002
+    return _Scatter.apply(input, dim, parallel_context)
 
 
-def reduce_to_tensor_group(tensor, parallel_context):
-    return _Reduce.apply(tensor, parallel_context)
+def reduce_to_tensor_group(input, parallel_context):  # noqa: A002
+    return _Reduce.apply(input, parallel_context)

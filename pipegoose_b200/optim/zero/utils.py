@@ -10,14 +10,14 @@ def delete_tensor_from_memory(tensor: torch.Tensor):
     del tensor
 
 
-def flatten_a_list_tensor(list_tensor: List[torch.Tensor]) -> torch.Tensor:
-    return torch.cat([t.reshape(-1) for t in list_tensor]) if len(list_tensor) > 0 else torch.empty(0)
+def flatten_a_list_tensor(list: List[torch.Tensor]) -> torch.Tensor:  # noqa: A002 (the reference's keyword)
+    return torch.cat([t.reshape(-1) for t in list]) if len(list) > 0 else torch.empty(0)
 
 
-def copy_flatten_tensor_to_unflatten_tensors(flatten: torch.Tensor, tensors: List[torch.Tensor]):
+def copy_flatten_tensor_to_unflatten_tensors(flat: torch.Tensor, tensors: List[torch.Tensor]):
     offset = 0
     for t in tensors:
         n = t.numel()
-        t.copy_(flatten[offset:offset + n].view_as(t))
+        t.copy_(flat[offset:offset + n].view_as(t))
         offset += n
-    assert offset == flatten.numel(), "flat tensor and tensor list sizes differ"
+    assert offset == flat.numel(), "flat tensor and tensor list sizes differ"

@@ -3,10 +3,10 @@ class Callback:
 
     order = 0
 
-    def on_fit_start(self, trainer):
+    def on_fit_start(self, trainer, pl_module=None):
         pass
 
-    def on_fit_end(self, trainer):
+    def on_fit_end(self, trainer, pl_module=None):
         pass
 
     def on_epoch_start(self, trainer):

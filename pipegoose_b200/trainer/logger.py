@@ -6,7 +6,7 @@ import time
 
 
 class DistributedLogger:
-    def __init__(self, name: str = "pipegoose_b200", parallel_context=None, rank: int = 0, stream=None):
+    def __init__(self, parallel_context=None, name: str = "pipegoose_b200", rank: int = 0, stream=None):
         self.name = name
         self.parallel_context = parallel_context
         self.rank = rank

@@ -52,8 +52,16 @@ class Trainer:
         return next(self.module.parameters()).device
 
     def _call(self, name, *args):
+        import inspect
+
         for cb in self.callbacks:
-            getattr(cb, name)(self, *args)
+            hook = getattr(cb, name)
+            if name in ("on_fit_start", "on_fit_end") and not args:
+                # the reference's signature is (trainer, pl_module); callbacks written as (trainer) keep working
+                if len(inspect.signature(hook).parameters) >= 2:
+                    hook(self, self.module)
+                    continue
+            hook(self, *args)
 
     def _log(self, msg):
         for lg in self.loggers:
