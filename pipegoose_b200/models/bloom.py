@@ -12,6 +12,7 @@ supports exactly that.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Optional
 
@@ -317,14 +318,65 @@ class BloomForCausalLM(nn.Module):
         return CausalLMOutput(loss=None, logits=logits.view(B, S, -1))
 
     @torch.no_grad()
-    def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, **_unused) -> torch.Tensor:
-        """Greedy decoding (full recompute per token: the training library has no KV cache)."""
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True, **_unused) -> torch.Tensor:
+        """Greedy decoding.  ``use_cache`` (unsharded model, dense MLPs): keys and values of every layer are kept, the
+        prompt is processed once and each new token costs one position; otherwise (tensor-parallel or MoE models)
+        every token recomputes the whole sequence through the training forward."""
+        dense = all(isinstance(b.mlp, BloomMLP) for b in self.transformer.h)
+        if not (use_cache and self.tp is None and dense):
+            out = input_ids
+            for _ in range(max_new_tokens):
+                logits = self(out).logits
+                out = torch.cat([out, logits[:, -1, :].float().argmax(-1, keepdim=True)], dim=1)
+            return out
+        cache = [None] * len(self.transformer.h)
         out = input_ids
+        logits = self._incremental_logits(input_ids, cache, 0)          # prefill
         for _ in range(max_new_tokens):
-            logits = self(out).logits
             nxt = logits[:, -1, :].float().argmax(-1, keepdim=True)
             out = torch.cat([out, nxt], dim=1)
+            if out.shape[1] - input_ids.shape[1] == max_new_tokens:
+                break
+            logits = self._incremental_logits(nxt, cache, out.shape[1] - 1)
         return out
+
+    def _incremental_logits(self, ids: torch.Tensor, cache: list, past: int) -> torch.Tensor:
+        """Inference-only forward of ``ids`` (positions ``past .. past+T-1``) against the cached keys / values; plain
+        tensor ops on the module's weights (the fused training kernels are built around full sequences)."""
+        import torch.nn.functional as F
+
+        t, cfg = self.transformer, self.config
+        B, T = ids.shape
+        h, n_head = cfg.hidden_size, cfg.n_head
+        D = h // n_head
+        x = F.embedding(ids, t.word_embeddings.weight)
+        if cfg.position_embedding == "learned":
+            x = x + t.position_embeddings.weight[past:past + T]
+        else:
+            x = F.layer_norm(x, (h,), t.word_embeddings_layernorm.weight, t.word_embeddings_layernorm.bias, cfg.layer_norm_epsilon)
+        for li, block in enumerate(t.h):
+            attn = block.self_attention
+            ln = F.layer_norm(x, (h,), block.input_layernorm.weight, block.input_layernorm.bias, block.eps)
+            qkv = F.linear(ln, attn.query_key_value.weight, attn.query_key_value.bias).view(B, T, n_head, 3, D)
+            q, k, v = (qkv[:, :, :, i].transpose(1, 2) for i in range(3))               # [B, H, T, D]
+            if cache[li] is not None:
+                k, v = torch.cat([cache[li][0], k], dim=2), torch.cat([cache[li][1], v], dim=2)
+            cache[li] = (k, v)
+            S = k.shape[2]
+            scores = torch.matmul(q.float(), k.float().transpose(-1, -2)) / math.sqrt(D)   # [B, H, T, S]
+            key_pos = torch.arange(S, device=ids.device, dtype=torch.float32)
+            if attn.use_alibi:
+                scores = scores + K.alibi_slopes(n_head, device=ids.device).view(1, n_head, 1, 1) * key_pos
+            query_pos = torch.arange(past, past + T, device=ids.device).view(T, 1)
+            scores = scores.masked_fill(key_pos.view(1, S) > query_pos, float("-inf"))
+            ctx = torch.matmul(scores.softmax(-1).to(v.dtype), v).transpose(1, 2).reshape(B, T, h)
+            x = x + F.linear(ctx, attn.dense.weight, attn.dense.bias)
+            ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
+            mlp = block.mlp
+            x = x + F.linear(K.gelu_tanh(F.linear(ln, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
+                             mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
+        x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
+        return F.linear(x, self.lm_head.weight)
 
     # ------------------------------------------------------------------ HF interop
     @classmethod

@@ -1,5 +1,6 @@
 """``pipegoose_b200.models.bloom`` against 🤗 transformers' Bloom (random init, no downloads): same module tree and
 parameter names, same logits / loss / gradients / greedy generation."""
+import pytest
 import torch
 
 from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
@@ -73,3 +74,23 @@ def test_block_recompute_gives_identical_loss_and_gradients():
     for (n, a), (_, b) in zip(base.named_parameters(), ckpt.named_parameters()):
         assert torch.allclose(a.grad, b.grad, atol=1e-6), n
     assert saved["ckpt"] < 0.6 * saved["base"], saved
+
+
+@pytest.mark.parametrize("family", ["bloom", "gpt2"])
+def test_cached_generation_equals_full_recompute(family):
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+    torch.manual_seed(0)
+    if family == "bloom":
+        model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=3, n_head=4))
+    else:
+        model = GPT2LMHeadModel(GPT2Config(vocab_size=96, hidden_size=32, n_layer=3, n_head=4, n_positions=32))
+    for p in model.parameters():
+        if p.dim() == 1:
+            p.data.normal_(std=0.3)   # biases / LayerNorm parameters that matter
+    ids = torch.randint(0, 96, (3, 7))
+    fast = model.generate(ids, max_new_tokens=6)
+    slow = model.generate(ids, max_new_tokens=6, use_cache=False)
+    assert fast.shape == (3, 13) and torch.equal(fast, slow)
+    assert torch.equal(model.generate(ids, max_new_tokens=1), slow[:, :8])
