@@ -49,7 +49,8 @@ class Experts(nn.Module):
             return 0
         return self.parallel_context.get_local_rank(ParallelMode.TENSOR) * self.num_local_experts
 
-    def forward(self, inputs: torch.Tensor, dispatch_order, *args, weights: Optional[torch.Tensor] = None, **kwargs):
+    def forward(self, inputs: torch.Tensor, dispatch_order, *args, weights: Optional[torch.Tensor] = None,
+                combine: bool = True, **kwargs):
         """``inputs``: ``[..., d]``; extra positional args that are tensors of the same token shape
         (HF Bloom passes the residual) are dispatched alongside."""
         shape = inputs.shape
@@ -82,8 +83,8 @@ class Experts(nn.Module):
             if w is not None:
                 y = y * w[rows, e].unsqueeze(-1).to(y.dtype)
             out = out.index_add(0, rows, y.to(out.dtype))
-        if self.sharded and self.parallel_context.get_world_size(ParallelMode.TENSOR) > 1:
-            out = reduce_to_tensor_group(out, self.parallel_context)
+        if combine and self.sharded and self.parallel_context.get_world_size(ParallelMode.TENSOR) > 1:
+            out = reduce_to_tensor_group(out, self.parallel_context)   # (combine=False: the caller reduce-scatters)
         return out.view(shape)
 
     @torch.no_grad()

@@ -43,21 +43,44 @@ class ExpertLayer(nn.Module):
 
     def forward(self, *args, **kwargs) -> torch.Tensor:
         inputs = args[0]
+        comm = getattr(self, "token_comm", None)   # set by the sequence-parallel TensorParallel path: tokens are sharded
+        group_size = comm.size if comm is not None else 1
+        sharded_tokens = comm is not None and group_size > 1
+        # sharded experts + sharded tokens: every rank needs ALL tokens to feed the experts it owns.  Megatron-SP shape:
+        # all-gather the tokens, run the local experts on whatever is routed to them, reduce-scatter the partial sums.
+        exchange = sharded_tokens and self._experts.sharded
+        local_shape = inputs.shape
+        if exchange:
+            inputs = comm.gather_rows(inputs.reshape(-1, local_shape[-1]))
         routed = self.router(inputs)
         ctx = ExpertContext.get_instance()
         if isinstance(routed, RouterOutput):
-            ctx.push_aux_loss(routed.aux_loss)
-            ctx.push_z_loss(routed.z_loss)
+            aux, z = routed.aux_loss, routed.z_loss
+            if sharded_tokens:
+                # every rank of the group adds these terms to ITS loss while the router parameters' gradients are summed
+                # over the group: keep the value, give each rank 1/T of the gradient
+                aux, z = _scale_grad(aux, 1.0 / group_size), _scale_grad(z, 1.0 / group_size)
+            ctx.push_aux_loss(aux)
+            ctx.push_z_loss(z)
             order, weights = routed.dispatching_order, routed.weight
         else:  # bare expert ids, e.g. a test router
             order, weights = routed, None
         residual = None
         rest = list(args[1:])
-        if rest and isinstance(rest[0], torch.Tensor) and rest[0].shape == inputs.shape:
+        if rest and isinstance(rest[0], torch.Tensor) and rest[0].shape == local_shape:
             # HF Bloom: mlp(layernorm_output, residual) -> keep the residual outside the experts
             residual = rest[0]
-            rest[0] = torch.zeros_like(residual)
-        out = self._experts(inputs, order, inputs, *rest, weights=weights, **kwargs)
+            rest[0] = torch.zeros_like(inputs)
+        out = self._experts(inputs, order, inputs, *rest, weights=weights, combine=not exchange, **kwargs)
+        if exchange:
+            out = comm.scatter_rows(out.reshape(-1, local_shape[-1])).view(local_shape)
         if residual is not None:
             out = out + residual
         return out
+
+
+def _scale_grad(t, factor: float):
+    """Same value, gradient multiplied by ``factor``."""
+    if not isinstance(t, torch.Tensor) or not t.requires_grad:
+        return t
+    return t.detach() + (t - t.detach()) * factor

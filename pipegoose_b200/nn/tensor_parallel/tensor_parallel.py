@@ -124,6 +124,8 @@ class TensorParallel(Parallel):
                     mlp.dense_h_to_4h.weight = gathered(mlp.dense_h_to_4h.weight, 0)
                     mlp.dense_h_to_4h.bias = gathered(mlp.dense_h_to_4h.bias, 0)
                     mlp.dense_4h_to_h.weight = gathered(mlp.dense_4h_to_h.weight, 1)
+                if hasattr(mlp, "token_comm"):
+                    mlp.token_comm = None
                 block.tp = None
             for p in module.parameters():
                 if hasattr(p, "tp_partial_grad"):
@@ -222,6 +224,14 @@ def _parallelize_fast_bloom(model, ctx: ParallelContext):
             partial(mlp.dense_4h_to_h.bias)
         for ln in (block.input_layernorm, block.post_attention_layernorm):
             partial(ln.weight), partial(ln.bias)
+        from pipegoose_b200.nn.expert_parallel.layers import ExpertLayer
+
+        if isinstance(mlp, ExpertLayer):
+            # token-sharded activations: the layer exchanges tokens itself (all-gather / reduce-scatter around its local
+            # experts); the router's gradients are partial sums over the group
+            mlp.token_comm = comm
+            for p in mlp.router.parameters():
+                partial(p)
         block.tp = comm
     hooks = getattr(model, "_pg_after_move_hooks", [])
     hooks.append(lambda m: comm.enable_fused())

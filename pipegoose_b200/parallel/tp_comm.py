@@ -73,6 +73,11 @@ class TensorParallelComm:
     def gather_cols(self, x: torch.Tensor) -> torch.Tensor:
         return _GatherCols.apply(x, self)
 
+    def scatter_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """Sum partial ``[tokens, h]`` results over the group and keep this rank's token block (the conjugate of
+        :meth:`gather_rows`: reduce-scatter forward, all-gather backward)."""
+        return _ScatterRows.apply(x, self)
+
     # ------------------------------------------------------------------ fused kernels
     def ag_input_buffer(self, rows_local: int, cols: int):
         return self._engine.ag_input_buffer(rows_local, cols) if self.fused else None
@@ -101,6 +106,19 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return ctx.comm.reduce_scatter_rows(g), None
+
+
+class _ScatterRows(torch.autograd.Function):
+    """reduce-scatter along tokens; backward all-gathers the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, comm):
+        ctx.comm = comm
+        return comm.reduce_scatter_rows(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.comm.all_gather_rows(g.contiguous()), None
 
 
 class _GatherCols(torch.autograd.Function):

@@ -74,6 +74,12 @@ def run_moe(rank, world_size, port, tp, dp, state, gate_state, ids, out_file):
     router = Top1Router(SwitchNoisePolicy(), 4, CFG["hidden_size"])
     router.load_state_dict(gate_state)
     model = ExpertParallel(model, 4, mapping=[1], router=router, parallel_context=ctx).parallelize()
+    layer = model.transformer.h[1].mlp
+    first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+    for i, e in enumerate(layer.experts):   # DISTINCT experts (global expert g is seeded by g on every layout)
+        g = torch.Generator().manual_seed(500 + first + i)
+        for p in e.parameters():
+            p.data = p.data + 0.05 * torch.randn(p.shape, generator=g)
     model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
     model.eval()  # deterministic routing (no Switch noise)
@@ -107,4 +113,4 @@ def test_moe_sharded_experts_train_like_unsharded_experts(tmp_path):
         runs[name] = json.load(open(f))
     assert runs["ep1"][-1] < runs["ep1"][0]
     for a, b in zip(runs["ep1"], runs["ep2"]):
-        assert abs(a - b) < 2e-3, runs
+        assert abs(a - b) < 2e-4, runs   # token exchange (all-gather / reduce-scatter) makes the sharded layer exact

@@ -249,11 +249,10 @@ def run_moe_4d(rank, world_size, port, tp, pp, dp, state, gate_state, ids, ref_l
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,tol", [(1, 3e-4), (2, 8e-3)])
+@pytest.mark.parametrize("tp,tol", [(1, 3e-4), (2, 3e-4)])
 def test_moe_tensor_pipeline_data_parallel_training(tmp_path, tp, tol):
-    # tp=1: the pipeline reproduces the unpartitioned objective (router losses of every stage included) almost exactly;
-    # tp=2: the sequence-parallel MoE layers compute the load-balancing statistics over each rank's token shard, which
-    # perturbs the (0.01-weighted) auxiliary term slightly
+    # the pipeline reproduces the unpartitioned objective (router losses of every stage included); with tp=2 the
+    # sequence-parallel MoE layers exchange tokens (all-gather / reduce-scatter) so routing statistics stay global
     torch.manual_seed(0)
     state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
     gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 2, CFG["hidden_size"]).state_dict())
