@@ -343,7 +343,12 @@ class FusedExpertLayer(nn.Module):
         res = residual.reshape(-1, shape[-1])
         gate = self.router.gate
         y, aux, zl, _probs, _lse = _FusedMoE.apply(x, res, gate.weight, gate.bias, self.w1, self.b1, self.w2, self.b2, self)
+        # every rank of the group adds its (local-token) router losses to its loss while the gate's gradients are summed
+        # over the group: 1/T of the gradient per rank keeps the objective's weight independent of the group size
+        from pipegoose_b200.nn.expert_parallel.layers import _scale_grad
+
+        T = self.parallel_context.get_world_size(self.parallel_mode)
         ectx = ExpertContext.get_instance()
-        ectx.push_aux_loss(aux)
-        ectx.push_z_loss(zl)
+        ectx.push_aux_loss(_scale_grad(aux, 1.0 / T))
+        ectx.push_z_loss(_scale_grad(zl, 1.0 / T))
         return y.view(shape)
