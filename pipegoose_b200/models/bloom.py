@@ -300,6 +300,12 @@ class BloomForCausalLM(nn.Module):
                 labels: Optional[torch.Tensor] = None, **_unused) -> CausalLMOutput:
         t = self.transformer
         B, S = input_ids.shape
+        if attention_mask is not None:
+            # The fused attention is purely causal.  RIGHT padding is harmless under a causal mask (real tokens never
+            # attend to later pads; give the pads label -100).  LEFT padding would shift the real tokens' ALiBi /
+            # absolute positions and let them attend to pads: refuse it loudly (device-side assert, no host sync).
+            torch._assert_async(attention_mask[:, 0].ne(0).all(),
+                                "pipegoose_b200 models support right padding only (attention_mask[:, 0] must be 1)")
         x = self.hidden_states(input_ids)
         eps = self.config.layer_norm_epsilon
         if labels is not None:

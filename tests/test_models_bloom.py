@@ -94,3 +94,24 @@ def test_cached_generation_equals_full_recompute(family):
     slow = model.generate(ids, max_new_tokens=6, use_cache=False)
     assert fast.shape == (3, 13) and torch.equal(fast, slow)
     assert torch.equal(model.generate(ids, max_new_tokens=1), slow[:, :8])
+
+
+def test_right_padding_is_harmless_and_left_padding_is_refused():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    from pipegoose_b200.models.bloom import BloomForCausalLM
+
+    torch.manual_seed(0)
+    hf = HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)).eval()
+    mine = BloomForCausalLM.from_hf(hf)
+    ids = torch.randint(0, 96, (2, 8))
+    mask = torch.ones(2, 8, dtype=torch.long)
+    mask[1, 5:] = 0                                   # right padding on the second sequence
+    labels = ids.masked_fill(mask == 0, -100)
+    want = hf(input_ids=ids, attention_mask=mask, labels=labels).loss
+    got = mine(ids, attention_mask=mask, labels=labels).loss
+    assert torch.allclose(got, want, atol=1e-5)
+    left = mask.flip(1)
+    with pytest.raises((RuntimeError, AssertionError)):
+        mine(ids, attention_mask=left, labels=labels)
