@@ -313,7 +313,7 @@ class BloomForCausalLM(nn.Module):
             shifted = torch.full_like(labels, -100)
             shifted[:, :-1] = labels[:, 1:]
             loss = PF.lm_head_cross_entropy(x, t.ln_f.weight, t.ln_f.bias, self.lm_head.weight, shifted, eps,
-                                            self.vocab_start, -100, self.tp)
+                                            self.vocab_start, -100, self.tp, vocab_size=self.config.vocab_size)
             return CausalLMOutput(loss=loss, logits=None)
         ln = fused_layer_norm(x, t.ln_f.weight, t.ln_f.bias, eps)
         if self.tp is not None:

@@ -116,7 +116,8 @@ class BloomStage(nn.Module):
                 shifted = torch.full_like(labels, -100)
                 shifted[:, :-1] = labels[:, 1:]
                 return PF.lm_head_cross_entropy(h, self.ln_f.weight, self.ln_f.bias, self.lm_head.weight, shifted,
-                                                eps, model.vocab_start, -100, model.tp)
+                                                eps, model.vocab_start, -100, model.tp,
+                                                vocab_size=self.config.vocab_size)
             ln = fused_layer_norm(h, self.ln_f.weight, self.ln_f.bias, eps)
             return K.gemm_nt(ln, self.lm_head.weight).view(B, S, -1)
         # ---- 🤗 Bloom blocks

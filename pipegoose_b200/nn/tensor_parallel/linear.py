@@ -51,7 +51,9 @@ class ColumnParallelLinear(_ShardedLinear):
         local = fused_linear(replicated, self.weight, self.bias)
         if not self.gather_output:
             return local
-        return comm.gather_to_tensor_group(local, dim=-1, parallel_context=self.parallel_context)
+        full = comm.gather_to_tensor_group(local, dim=-1, parallel_context=self.parallel_context)
+        keep = getattr(self, "unpadded_out_features", None)   # an LM head whose vocabulary was padded to split evenly
+        return full if keep is None or keep == full.shape[-1] else full[..., :keep]
 
 
 class RowParallelLinear(_ShardedLinear):

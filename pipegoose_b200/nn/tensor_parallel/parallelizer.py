@@ -195,6 +195,9 @@ class LMHeadParallelizer(ModuleParallelizer):
             for other in self.model.modules():  # 🤗 keeps a second handle on the same bias (``predictions.bias``)
                 if other is not module and getattr(other, "bias", None) is old:
                     other.bias = module.bias
+        world = ctx.get_world_size(ParallelMode.TENSOR)
+        if module.weight.shape[0] * world != module.out_features:
+            module.unpadded_out_features = module.out_features   # phantom classes are cut off after the gather
         module.__class__ = ColumnParallelLinear
         module.gather_output = True
         module.parallel_context = ctx

@@ -165,7 +165,7 @@ class TensorParallel(Parallel):
                 leaf.__class__ = nn.LayerNorm
             else:
                 continue
-            for attr in ("gather_output", "parallel_context"):
+            for attr in ("gather_output", "parallel_context", "unpadded_out_features"):
                 if attr in leaf.__dict__:
                     delattr(leaf, attr)
         return module

@@ -435,7 +435,7 @@ class LMHeadCrossEntropy(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp):
+    def forward(ctx, x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp, vocab_size=None):
         fused = tp is not None and tp.fused and _FUSED_LM_HEAD
         if fused:
             # all-gather -> GEMM like every other column-parallel linear (LN writes into the gather staging buffer)
@@ -446,6 +446,12 @@ class LMHeadCrossEntropy(torch.autograd.Function):
             ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
             ln_full = tp.all_gather_rows(ln) if tp is not None else ln
             logits = K.gemm_nt(ln_full, table)  # [M, V/T]
+        if vocab_size is not None:
+            # rows the table was zero-padded with (vocabulary made divisible by the group size) are not classes: their
+            # logits leave the softmax (-inf: exp 0, gradient 0).  Only the last shard(s) have any; no-op otherwise.
+            real = min(max(vocab_size - vocab_start, 0), logits.shape[1])
+            if real < logits.shape[1]:
+                logits[:, real:] = float("-inf")
         tgt = labels.reshape(-1)
         stats = K.ce_local_stats(logits, tgt, vocab_start)
         if tp is not None:
@@ -477,7 +483,7 @@ class LMHeadCrossEntropy(torch.autograd.Function):
             dln = tp.reduce_scatter_rows(dln_full) if tp is not None else dln_full
         dtable = _wgrad(dlogits, ln_full, table)
         dx, dgamma, dbeta = _ln_bwd(dln, x, gamma, beta, mean, rstd)
-        return dx, dgamma, dbeta, dtable, None, None, None, None, None
+        return dx, dgamma, dbeta, dtable, None, None, None, None, None, None
 
 
 def layernorm_linear(x, gamma, beta, weight, bias, eps=1e-5, tp=None):
@@ -516,5 +522,7 @@ def embedding_positions(ids, table, positions, vocab_start=0, tp=None):
     return EmbeddingPositions.apply(ids, table, positions, vocab_start, tp)
 
 
-def lm_head_cross_entropy(x, gamma, beta, table, labels, eps=1e-5, vocab_start=0, ignore_index=-100, tp=None):
-    return LMHeadCrossEntropy.apply(x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp)
+def lm_head_cross_entropy(x, gamma, beta, table, labels, eps=1e-5, vocab_start=0, ignore_index=-100, tp=None,
+                          vocab_size=None):
+    """``vocab_size``: the true (global) vocabulary size when the table was padded for tensor parallelism."""
+    return LMHeadCrossEntropy.apply(x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp, vocab_size)

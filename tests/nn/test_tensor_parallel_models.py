@@ -211,3 +211,74 @@ def test_tensor_parallel_deparallelize_restores_the_model(fast):
     with torch.no_grad():
         ref = model(ids).logits
     spawn(run_deparallelize, world_size=2, fast=fast, state=copy.deepcopy(model.state_dict()), ids=ids, ref_logits=ref)
+
+
+# ---------------------------------------------------------------- vocabulary sizes that do not split evenly
+def run_odd_vocab_fast(rank, world_size, port, state, ids, ref_loss, ref_logits, ref_losses):
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=101, hidden_size=32, n_layer=2, n_head=4))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    assert model.lm_head.weight.shape[0] * 2 > 101                      # zero-padded table
+    assert torch.allclose(model(ids, labels=ids).loss, ref_loss, atol=1e-5)   # phantom classes are not in the softmax
+    logits = model(ids).logits
+    assert logits.shape == ref_logits.shape and torch.allclose(logits, ref_logits, atol=1e-4)
+    opt = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    for want in ref_losses:
+        loss = model(ids, labels=ids).loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - want) < 1e-4, (loss.item(), ref_losses)
+    ctx.destroy()
+
+
+def test_fast_bloom_with_a_vocabulary_that_needs_padding():
+    from pipegoose_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=101, hidden_size=32, n_layer=2, n_head=4))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 101, (2, 8))
+    ref_loss, ref_logits = model(ids, labels=ids).loss.detach(), model(ids).logits.detach()
+    opt, ref_losses = FusedAdam(model.parameters(), lr=1e-2), []
+    for _ in range(3):
+        loss = model(ids, labels=ids).loss
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(loss.item())
+    spawn(run_odd_vocab_fast, world_size=2, state=state, ids=ids, ref_loss=ref_loss, ref_logits=ref_logits,
+          ref_losses=ref_losses)
+
+
+def run_odd_vocab_hf(rank, world_size, port, state, ids, ref_loss, ref_logits):
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    model = HFBloom(HFConfig(vocab_size=101, hidden_size=32, n_layer=2, n_head=4))
+    model.load_state_dict(state)
+    wrapper = TensorParallel(model, ctx)
+    model = wrapper.parallelize()
+    out = model(input_ids=ids, labels=ids)
+    assert out.logits.shape == ref_logits.shape and torch.allclose(out.logits, ref_logits, atol=1e-4)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-5)
+    out.loss.backward()
+    model = wrapper.deparallelize()
+    assert model.lm_head.weight.shape == (101, 32) and torch.allclose(model(input_ids=ids).logits, ref_logits, atol=1e-4)
+    ctx.destroy()
+
+
+def test_hf_bloom_with_a_vocabulary_that_needs_padding():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    torch.manual_seed(0)
+    model = HFBloom(HFConfig(vocab_size=101, hidden_size=32, n_layer=2, n_head=4)).eval()
+    ids = torch.randint(0, 101, (2, 8))
+    out = model(input_ids=ids, labels=ids)
+    spawn(run_odd_vocab_hf, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=out.loss.detach(),
+          ref_logits=out.logits.detach())
