@@ -199,6 +199,9 @@ def embed_tokens(owner: nn.Module, input_ids: torch.Tensor, config, vocab_start:
     """Token ids -> ``[tokens_local, hidden]`` input of the first block.  ``owner`` holds ``word_embeddings`` and either
     ``word_embeddings_layernorm`` (Bloom) or ``position_embeddings`` (GPT-2): the model's ``transformer`` or a first
     pipeline stage."""
+    if tp is not None and input_ids.numel() % tp.size != 0:
+        raise ValueError(f"the sequence-parallel path shards the {input_ids.numel()} tokens of a batch (batch x seq) over "
+                         f"{tp.size} tensor-parallel ranks: pad the batch so that batch x seq is a multiple of {tp.size}")
     if getattr(config, "position_embedding", "alibi") == "learned":
         assert input_ids.shape[-1] <= config.n_positions, "sequence longer than the position table"
         assert not getattr(config, "embedding_layernorm", False)
@@ -331,9 +334,15 @@ class BloomForCausalLM(nn.Module):
         dense = all(isinstance(b.mlp, BloomMLP) for b in self.transformer.h)
         if not (use_cache and self.tp is None and dense):
             out = input_ids
+            group = self.tp.size if self.tp is not None else 1
             for _ in range(max_new_tokens):
-                logits = self(out).logits
-                out = torch.cat([out, logits[:, -1, :].float().argmax(-1, keepdim=True)], dim=1)
+                B, S = out.shape
+                pad = 0
+                while (B * (S + pad)) % group:   # token-sharded activations: right-pad (harmless under a causal mask)
+                    pad += 1
+                padded = out if pad == 0 else torch.cat([out, out.new_zeros(B, pad)], dim=1)
+                logits = self(padded).logits
+                out = torch.cat([out, logits[:, S - 1, :].float().argmax(-1, keepdim=True)], dim=1)
             return out
         cache = [None] * len(self.transformer.h)
         out = input_ids

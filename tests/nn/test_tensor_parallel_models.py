@@ -53,7 +53,7 @@ def test_hf_bloom_tensor_parallel_matches_unsharded():
     spawn(run_hf_bloom, world_size=2, tp=2, state=model.state_dict(), ids=ids, ref_logits=ref_logits, ref_generated=ref_gen)
 
 
-def run_fast_bloom(rank, world_size, port, tp, state, ids, ref_loss, ref_grads, ref_logits):
+def run_fast_bloom(rank, world_size, port, tp, state, ids, ref_loss, ref_grads, ref_logits, ref_generated):
     ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
     cfg = BloomConfig(vocab_size=128, hidden_size=32, n_layer=2, n_head=4)
     model = BloomForCausalLM(cfg)
@@ -87,6 +87,8 @@ def run_fast_bloom(rank, world_size, port, tp, state, ids, ref_loss, ref_grads, 
         g = p.grad.clone()
         want = shard(name, ref_grads[name])
         assert torch.allclose(g, want, atol=2e-5), name
+    # generation under token sharding: odd prompt lengths are right-padded internally (3 rows x 5, 6, 7 tokens)
+    assert torch.equal(model.generate(ids[:3, :5], max_new_tokens=3), ref_generated)
     ctx.destroy()
 
 
@@ -104,8 +106,9 @@ def test_fast_bloom_sequence_parallel_matches_unsharded():
     grads = {n: p.grad.clone() for n, p in model.named_parameters()}
     with torch.no_grad():
         logits = model(ids).logits
+        generated = model.generate(ids[:3, :5], max_new_tokens=3)
     spawn(run_fast_bloom, world_size=2, tp=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach(),
-          ref_grads=grads, ref_logits=logits)
+          ref_grads=grads, ref_logits=logits, ref_generated=generated)
 
 
 def run_tp_only_training(rank, world_size, port, state, ids, ref_losses, ref_ln_grad):
