@@ -259,6 +259,7 @@ class PipelineEngine:
         mbs = self._prepare(inputs)
         dev = self._device()
         m = len(mbs)
+        weights = self._microbatch_weights(mbs) if self.is_last else None
         order: List[Task] = self.scheduler.get_stage_order(self.partition_idx)
         saved_in: Dict[int, torch.Tensor] = {}
         saved_out: Dict[int, torch.Tensor] = {}
@@ -305,11 +306,11 @@ class PipelineEngine:
                 saved_in[i] = x
                 extra = self._moe_auxiliary_loss()   # router losses of THIS stage's MoE layers for this micro-batch
                 if self.is_last:
-                    loss = out / m
+                    loss = out * weights[i]
                     if extra is not None:
                         loss = loss + extra / m
                     saved_out[i] = loss
-                    losses.append((out / m).detach())   # reported: the language-model loss, as without pipelining
+                    losses.append((out * weights[i]).detach())   # reported: the language-model loss, as without pipelining
                 else:
                     saved_out[i] = out
                     if extra is not None:
@@ -347,6 +348,19 @@ class PipelineEngine:
         else:
             total = torch.zeros((), device=dev)
         return broadcast_loss_from_last_stage(total, self.parallel_context)
+
+    @staticmethod
+    def _microbatch_weights(mbs: List[Dict]) -> List:
+        """Share of the step's target tokens that each micro-batch holds, so that the sum of the weighted micro-batch
+        (mean) losses IS the mean over all target tokens of the batch — exactly what the unpartitioned model computes,
+        also when micro-batches differ in size or in the number of ignored (-100) labels.  Counted on the device."""
+        m = len(mbs)
+        labels = [mb.get("labels") for mb in mbs]
+        if any(not isinstance(l, torch.Tensor) for l in labels):
+            return [1.0 / m] * m
+        counts = torch.stack([(l[..., 1:] != -100).sum() for l in labels]).float()
+        share = counts / counts.sum().clamp(min=1.0)
+        return list(share.unbind(0))
 
     def _moe_auxiliary_loss(self) -> Optional[torch.Tensor]:
         """Drain the expert context after a stage forward: ``aux_weight * sum(load-balancing) + z_weight * sum(router-z)``

@@ -280,3 +280,32 @@ def test_pipeline_engine_facade_runs_a_pipelined_step():
     ids = torch.randint(0, 96, (4, 8))
     ref = torch.stack([model(c, labels=c).loss for c in ids.chunk(2)]).mean().detach()
     spawn(run_engine_facade, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=ref)
+
+
+def run_uneven_microbatches(rank, world_size, port, state, ids, labels, n_mb, ref_loss, ref_grads):
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=n_mb, parallel_context=ctx).parallelize()
+    out = model(ids, labels=labels)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+    out.loss.backward()
+    for p in model._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("batch,n_mb", [(5, 2), (6, 4)])
+def test_uneven_microbatches_and_ignored_labels_give_the_global_token_mean(batch, n_mb):
+    """Micro-batch losses are weighted by their share of target tokens: the pipelined loss and gradients equal the
+    unpartitioned model's even when the batch does not split evenly and some labels are -100."""
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    ids = torch.randint(0, 96, (batch, 8))
+    labels = ids.clone()
+    labels[0, 5:] = -100          # padding on one sequence
+    loss = model(ids, labels=labels).loss
+    loss.backward()
+    spawn(run_uneven_microbatches, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids, labels=labels, n_mb=n_mb,
+          ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
