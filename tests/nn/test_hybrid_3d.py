@@ -111,3 +111,33 @@ def test_pipeline_x_data_parallel_with_a_stock_optimizer():
         ref_losses.append(total)
     assert ref_losses[-1] < ref_losses[0]
     spawn(run_pp_dp_stock_optimizer, world_size=4, state=state, ids=ids, ref_losses=ref_losses)
+
+
+def run_3d_deparallelize(rank, world_size, port, state, ids, ref_logits):
+    ctx = init_parallel_context(rank, world_size, port, 2, 2, 2)
+    model = BloomForCausalLM(BloomConfig(vocab_size=101, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    tp = TensorParallel(model, ctx)
+    model = tp.parallelize()
+    pp = PipelineParallel(model, num_microbatches=2, parallel_context=ctx)
+    model = pp.parallelize()
+    dp = DataParallel(model, ctx)
+    model = dp.parallelize()
+    model(ids, labels=ids)                      # a scheduled step on the sharded model
+    for wrapper in (dp, pp, tp):                # undo in reverse order: every rank ends with the whole model
+        model = wrapper.deparallelize()
+    logits = model(ids).logits
+    assert logits.shape == ref_logits.shape and torch.allclose(logits, ref_logits, atol=1e-4)
+    consolidated = model.state_dict()
+    for k, v in state.items():
+        assert consolidated[k].shape == v.shape and torch.allclose(consolidated[k], v, atol=1e-6), k
+    ctx.destroy()
+
+
+def test_3d_deparallelize_gives_back_the_whole_model():
+    """TP x PP x DP (vocabulary 101: padded for TP) -> deparallelize all three -> the original state dict and logits."""
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=101, hidden_size=32, n_layer=4, n_head=4))
+    ids = torch.randint(0, 101, (4, 8))
+    spawn(run_3d_deparallelize, world_size=8, state=copy.deepcopy(model.state_dict()), ids=ids,
+          ref_logits=model(ids).logits.detach())
