@@ -176,6 +176,10 @@ class GradReducer:
         group = self.ctx.get_group(ParallelMode.DATA)
         want_fused = (existing is None and self.dp > 1 and p0.is_cuda and p0.dtype == torch.bfloat16
                       and dist.get_backend(group) == "nccl" and os.environ.get("PIPEGOOSE_B200_FUSED_DP", "1") == "1")
+        if want_fused:
+            from pipegoose_b200.distributed.symmetric import peers_share_a_node
+
+            want_fused = peers_share_a_node(self.ctx, ParallelMode.DATA)   # replicas on other hosts: NCCL reducer
         if not want_fused:
             return FlatModelState.of(module, pad_to_multiple_of=self.dp)
         from pipegoose_b200.ops.comm import FusedDPEngine

@@ -23,6 +23,37 @@ SIG_RS_ARRIVE = 128    # [128,136): tiles pushed into my reduce-scatter staging 
 SIG_CHUNK_CTR = 192    # [192,200): local: comm CTAs that finished copying chunk c
 
 
+_NODE_CACHE = {}
+
+
+def peers_share_a_node(parallel_context, parallel_mode) -> bool:
+    """True when every rank of the group runs on this host and the group fits one NVSwitch domain — the precondition of
+    CUDA-IPC peer mapping.  Groups that span hosts (e.g. the DATA group of a multi-node job) keep the NCCL paths.
+    Collective over the group (one ``all_gather_object`` of the host identities, cached per group)."""
+    import os
+    import socket
+
+    from pipegoose_b200.constants import MAX_NVLINK_PEERS
+
+    ranks = tuple(parallel_context.get_ranks_in_group(parallel_mode))
+    if ranks in _NODE_CACHE:
+        return _NODE_CACHE[ranks]
+    if len(ranks) == 1:
+        same = True
+    else:
+        boot = ""
+        try:
+            boot = open("/proc/sys/kernel/random/boot_id").read().strip()
+        except OSError:
+            pass
+        me = (socket.gethostname(), boot, os.environ.get("PIPEGOOSE_B200_FAKE_NODE", ""))
+        everyone = [None] * len(ranks)
+        dist.all_gather_object(everyone, me, group=parallel_context.get_group(parallel_mode))
+        same = all(e == everyone[0] for e in everyone) and len(ranks) <= MAX_NVLINK_PEERS
+    _NODE_CACHE[ranks] = same
+    return same
+
+
 class SymmetricWorkspace:
     def __init__(self, parallel_context, parallel_mode, nbytes: int):
         from pipegoose_b200.ops import native

@@ -77,6 +77,10 @@ class ExpertParallel(Parallel):
         ok = (isinstance(expert, BloomMLP) and hasattr(self.module, "hidden_states") and hasattr(self.router, "gate")
               and torch.cuda.is_available()
               and dist.get_backend(self.parallel_context.get_group(ParallelMode.TENSOR)) == "nccl")
+        if ok:
+            from pipegoose_b200.distributed.symmetric import peers_share_a_node
+
+            ok = peers_share_a_node(self.parallel_context, ParallelMode.TENSOR)   # NVLink all-to-all needs one host
         if self.fused is True and not ok:
             raise ValueError("fused=True needs a pipegoose_b200 Bloom model, BloomMLP experts, a gate router and NCCL")
         return ok

@@ -32,7 +32,12 @@ class TensorParallelComm:
     def enable_fused(self):
         """Create the NVLink peer-memory engine (symmetric workspace + fused kernels); collective call."""
         if self._want_fused and self._engine is None:
+            from pipegoose_b200.distributed.symmetric import peers_share_a_node
             from pipegoose_b200.ops.comm import FusedTPEngine
+
+            if not peers_share_a_node(self.ctx, self.mode):   # a tensor group across hosts: NCCL collectives + plain GEMMs
+                self._want_fused = False
+                return
 
             self._engine = FusedTPEngine(self)
             self.fused = True

@@ -41,3 +41,25 @@ def test_every_rank_is_in_exactly_one_group_per_mode(tp, pp, dp):
 def test_invalid_sizes():
     with pytest.raises(AssertionError):
         Topology(8, 2, 2, 3)
+
+
+def _run_node_probe(rank, world_size, port):
+    import os
+
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.distributed.symmetric import _NODE_CACHE, peers_share_a_node
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 2)
+    assert peers_share_a_node(ctx, ParallelMode.TENSOR) and peers_share_a_node(ctx, ParallelMode.DATA)
+    _NODE_CACHE.clear()
+    os.environ["PIPEGOOSE_B200_FAKE_NODE"] = str(rank // 2)   # pretend ranks {0,1} and {2,3} sit on two hosts
+    assert peers_share_a_node(ctx, ParallelMode.TENSOR)        # [0,1] / [2,3]
+    assert not peers_share_a_node(ctx, ParallelMode.DATA)      # [0,2] / [1,3]: peer mapping impossible -> NCCL paths
+    ctx.destroy()
+
+
+def test_groups_that_span_hosts_are_detected():
+    from pipegoose_b200.testing.utils import spawn
+
+    spawn(_run_node_probe, world_size=4)
