@@ -1,0 +1,200 @@
+"""Layouts and corner cases found worth pinning while probing (CPU / gloo): stock optimizers behind generic ZeRO-1 at
+dp=3, the fused ZeRO-1 path at dp=3, parameters that never receive a gradient, 🤗 Bloom (class-swap TP) with the fused
+optimizer, GPT-2 with a vocabulary that needs padding through TP x PP training, deparallelize and cached generation."""
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+from pipegoose_b200.nn import DataParallel, PipelineParallel, TensorParallel
+from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+CFG = dict(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)
+
+
+# ------------------------------------------------------------------ ZeRO-1 at dp=3 with several optimizers
+def _make_optim(name, params):
+    if name == "sgd":
+        return torch.optim.SGD(params, lr=0.1, momentum=0.9, nesterov=True)
+    if name == "adamw":
+        return torch.optim.AdamW(params, lr=1e-2, weight_decay=0.1)
+    if name == "rmsprop":
+        return torch.optim.RMSprop(params, lr=1e-3)
+    if name == "fused":
+        return FusedAdam(params, lr=1e-2)
+    return FusedAdam(params, lr=1e-2, weight_decay=0.1, adamw=True)
+
+
+def run_zero_dp3(rank, world_size, port, name, state, ids, ref_state):
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 3)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(_make_optim(name, model.parameters()), ctx)
+    local = ids.chunk(3)[ctx.get_local_rank(ParallelMode.DATA)]
+    for _ in range(3):
+        loss = model(local, labels=local).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+    for k, v in model.state_dict().items():
+        assert torch.allclose(v, ref_state[k], atol=2e-5), k
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("name", ["sgd", "adamw", "rmsprop", "fused", "fused_adamw"])
+def test_zero1_with_three_replicas(name):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (6, 8))
+    optim = _make_optim(name, model.parameters())
+    for _ in range(3):
+        loss = model(ids, labels=ids).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+    spawn(run_zero_dp3, world_size=3, name=name, state=state, ids=ids,
+          ref_state={k: v.clone() for k, v in model.state_dict().items()})
+
+
+# ------------------------------------------------------------------ parameters without gradients
+class _NetWithUnusedLayer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a, self.unused, self.b = nn.Linear(8, 8), nn.Linear(8, 8), nn.Linear(8, 4)
+
+    def forward(self, x):
+        return self.b(torch.tanh(self.a(x)))
+
+
+def run_unused(rank, world_size, port, state, x, ref_state, fused):
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 2)
+    model = _NetWithUnusedLayer()
+    model.load_state_dict(state)
+    model = DataParallel(model, ctx).parallelize()
+    inner = FusedAdam(model.parameters(), lr=1e-2) if fused else torch.optim.Adam(model.parameters(), lr=1e-2)
+    optim = DistributedOptimizer(inner, ctx)
+    for _ in range(3):
+        loss = model(x.chunk(2)[rank]).pow(2).mean()
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+    for k, v in model.state_dict().items():
+        assert torch.allclose(v, ref_state[k], atol=1e-5), k
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_parameters_that_never_get_a_gradient_do_not_stall_the_reducer(fused):
+    torch.manual_seed(0)
+    model = _NetWithUnusedLayer()
+    state = copy.deepcopy(model.state_dict())
+    x = torch.randn(8, 8)
+    optim = torch.optim.Adam(model.parameters(), lr=1e-2)
+    for _ in range(3):
+        loss = model(x).pow(2).mean()
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+    spawn(run_unused, world_size=2, state=state, x=x, ref_state={k: v.clone() for k, v in model.state_dict().items()},
+          fused=fused)
+
+
+# ------------------------------------------------------------------ 🤗 Bloom, class-swap TP x DP, fused ZeRO-1
+def _hf_bloom():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    return HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+
+
+def run_hf_fused(rank, world_size, port, state, ids, ref_losses):
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 2)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    model.train()
+    model = TensorParallel(model, ctx).parallelize()
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(2)[ctx.get_local_rank(ParallelMode.DATA)]
+    got = []
+    for _ in ref_losses:
+        loss = model(input_ids=local, labels=local).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        got.append(loss.item())
+    t = torch.tensor(got)
+    torch.distributed.all_reduce(t)
+    for a, b in zip((t / world_size).tolist(), ref_losses):
+        assert abs(a - b) < 2e-3, (t, ref_losses)
+    ctx.destroy()
+
+
+def test_hf_bloom_with_the_fused_optimizer():
+    torch.manual_seed(0)
+    model = _hf_bloom()
+    model.train()
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    optim, ref = torch.optim.Adam(model.parameters(), lr=1e-2), []
+    for _ in range(3):
+        optim.zero_grad()
+        total = 0.0
+        for chunk in ids.chunk(2):
+            loss = model(input_ids=chunk, labels=chunk).loss / 2
+            loss.backward()
+            total += loss.item()
+        optim.step()
+        ref.append(total)
+    spawn(run_hf_fused, world_size=4, state=state, ids=ids, ref_losses=ref)
+
+
+# ------------------------------------------------------------------ GPT-2, padded vocabulary, TP x PP, export
+GPT2 = dict(vocab_size=97, hidden_size=32, n_layer=4, n_head=4, n_positions=16)
+
+
+def run_gpt2_round_trip(rank, world_size, port, state, ids, ref_losses, ref_generated):
+    ctx = init_parallel_context(rank, world_size, port, 2, 2, 1)
+    model = GPT2LMHeadModel(GPT2Config(**GPT2))
+    model.load_state_dict(state)
+    tp = TensorParallel(model, ctx)
+    model = tp.parallelize()
+    pp = PipelineParallel(model, num_microbatches=2, parallel_context=ctx)
+    model = pp.parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    for want in ref_losses:
+        loss = model(ids, labels=ids).loss
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        assert abs(loss.item() - want) < 2e-4, (loss.item(), ref_losses)
+    model = pp.deparallelize()
+    model = tp.deparallelize()
+    assert torch.equal(model.generate(ids[:, :5], max_new_tokens=4), ref_generated)   # the trained, re-assembled model
+    ctx.destroy()
+
+
+def test_gpt2_padded_vocabulary_trains_under_tp_pp_and_exports():
+    torch.manual_seed(0)
+    model = GPT2LMHeadModel(GPT2Config(**GPT2))
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 97, (4, 8))
+    optim, ref = FusedAdam(model.parameters(), lr=1e-2), []
+    for _ in range(3):
+        optim.zero_grad()
+        total = 0.0
+        for chunk in ids.chunk(2):
+            loss = model(chunk, labels=chunk).loss / 2
+            loss.backward()
+            total += loss.item()
+        optim.step()
+        ref.append(total)
+    spawn(run_gpt2_round_trip, world_size=4, state=state, ids=ids, ref_losses=ref,
+          ref_generated=model.generate(ids[:, :5], max_new_tokens=4))
