@@ -102,3 +102,38 @@ def test_module_alias_attributes_and_native_bindings_exist(path):
             if node.attr not in bound:
                 missing.append(f"line {node.lineno}: native().{node.attr}")
     assert missing == []
+
+
+def test_native_call_sites_pass_a_valid_number_of_arguments():
+    """Every ``native().<fn>(...)`` call gives the bound C++ function between its required and its total number of
+    arguments (parsed from csrc/bindings.cpp) — the arity errors that otherwise only surface on a GPU box."""
+    import re
+
+    src = (ROOT / "pipegoose_b200" / "csrc" / "bindings.cpp").read_text()
+    n_params = {}
+    for m in re.finditer(r"^[\w:<>\s\*&]+?\b(\w+)\(([^{;]*?)\)\s*\{", src, re.M):
+        depth, n = 0, (1 if m.group(2).strip() else 0)
+        for ch in m.group(2):
+            depth += ch in "<([" 
+            depth -= ch in ">)]"
+            n += ch == "," and depth == 0
+        n_params[m.group(1)] = n
+    bounds = {}
+    for m in re.finditer(r'm\.def\("(\w+)",\s*&(\w+)([^;]*);', src):
+        total = n_params.get(m.group(2))
+        if total is not None:
+            bounds[m.group(1)] = (total - len(re.findall(r'py::arg\("\w+"\)\s*=', m.group(3))), total)
+    assert len(bounds) >= 20, "bindings.cpp was not parsed"
+    wrong = []
+    for path in SCRIPTS + PACKAGE:
+        for node in ast.walk(ast.parse(path.read_text())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Call)
+                    and isinstance(node.func.value.func, ast.Name) and node.func.value.func.id == "native"):
+                continue
+            if node.func.attr not in bounds or any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            given = len(node.args) + len(node.keywords)
+            lo, hi = bounds[node.func.attr]
+            if not lo <= given <= hi:
+                wrong.append(f"{path.relative_to(ROOT)}:{node.lineno} {node.func.attr}: {given} args, takes {lo}..{hi}")
+    assert wrong == []
