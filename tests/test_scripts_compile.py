@@ -137,3 +137,59 @@ def test_native_call_sites_pass_a_valid_number_of_arguments():
             if not lo <= given <= hi:
                 wrong.append(f"{path.relative_to(ROOT)}:{node.lineno} {node.func.attr}: {given} args, takes {lo}..{hi}")
     assert wrong == []
+
+
+@pytest.mark.parametrize("path", SCRIPTS + PACKAGE, ids=lambda p: str(p.relative_to(ROOT)))
+def test_calls_into_aliased_modules_bind_to_the_callee_signature(path):
+    """``K.layernorm_fwd(x, g, b, eps, out=stage)`` / ``PF.embedding_positions(...)`` style calls: the positional count and
+    every keyword are accepted by the function's signature (checked with ``inspect.signature(...).bind``), including the
+    calls that only execute on a GPU box."""
+    import inspect
+
+    tree = ast.parse(path.read_text())
+    aliases = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Import):
+            aliases.update({a.asname: a.name for a in node.names if a.asname and a.name.startswith("pipegoose_b200")})
+        elif isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("pipegoose_b200"):
+            for a in node.names:
+                try:
+                    if a.name != "*" and importlib.util.find_spec(f"{node.module}.{a.name}") is not None:
+                        aliases[a.asname or a.name] = f"{node.module}.{a.name}"
+                except ModuleNotFoundError:
+                    pass
+    # names imported directly: ``from pipegoose_b200.x import f`` (module-level imports only: no shadowing games)
+    direct = {}
+    for node in tree.body:
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("pipegoose_b200"):
+            for a in node.names:
+                if a.name != "*" and (a.asname or a.name) not in aliases:
+                    direct[a.asname or a.name] = (node.module, a.name)
+    assigned = {t.id for n in ast.walk(tree) if isinstance(n, (ast.Assign, ast.AugAssign, ast.AnnAssign))
+                for t in ast.walk(n.targets[0] if isinstance(n, ast.Assign) else n.target) if isinstance(t, ast.Name)}
+    assigned |= {a.arg for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.Lambda)) for a in n.args.args + n.args.kwonlyargs}
+    wrong = []
+    for node in ast.walk(tree):
+        if not isinstance(node, ast.Call):
+            continue
+        if isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name) and node.func.value.id in aliases:
+            target = getattr(importlib.import_module(aliases[node.func.value.id]), node.func.attr, None)
+            label = f"{node.func.value.id}.{node.func.attr}"
+        elif isinstance(node.func, ast.Name) and node.func.id in direct and node.func.id not in assigned:
+            module, name = direct[node.func.id]
+            target = getattr(importlib.import_module(module), name, None)
+            label = node.func.id
+        else:
+            continue
+        if any(isinstance(a, ast.Starred) for a in node.args) or any(k.arg is None for k in node.keywords):
+            continue
+        if not (inspect.isfunction(target) or inspect.isclass(target)):
+            continue
+        try:
+            sig = inspect.signature(target)
+            sig.bind(*[None] * len(node.args), **{k.arg: None for k in node.keywords})
+        except TypeError as e:
+            wrong.append(f"line {node.lineno}: {label}: {e}")
+        except ValueError:
+            pass  # no signature available (builtins)
+    assert wrong == []
