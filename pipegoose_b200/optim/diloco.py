@@ -27,6 +27,8 @@ from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
 
 class DiLoCoOptimizer:
+    BUCKET_ELEMS = 16 * 1024 * 1024   # fp32 elements per outer all-reduce (64 MB): bounds the transient memory
+
     def __init__(self, inner_optim: torch.optim.Optimizer, parallel_context, inner_steps: int = 500, outer_lr: float = 0.7,
                  outer_momentum: float = 0.9, nesterov: bool = True, parallel_mode: ParallelMode = ParallelMode.DATA):
         assert inner_steps >= 1
@@ -95,15 +97,34 @@ class DiLoCoOptimizer:
         tensors = self._tensors()
         deltas = [a - t.float() for a, t in zip(self._anchor, tensors)]
         if n_workers > 1 and deltas:
-            flat = torch.cat([d.reshape(-1) for d in deltas])
             group = ctx.get_group(mode)
-            buf = flat.cuda() if dist.get_backend(group) == "nccl" and not flat.is_cuda else flat
-            dist.all_reduce(buf, group=group)
-            flat = (buf / n_workers).to(flat.device)
-            offset = 0
+            to_cuda = dist.get_backend(group) == "nccl"
+
+            def average(tensors):   # one all-reduce per bucket; large tensors travel alone, in place
+                flat = tensors[0].reshape(-1) if len(tensors) == 1 else torch.cat([t.reshape(-1) for t in tensors])
+                buf = flat.cuda() if to_cuda and not flat.is_cuda else flat
+                dist.all_reduce(buf, group=group)
+                buf.div_(n_workers)
+                if buf is not flat:
+                    flat.copy_(buf)
+                if len(tensors) > 1:
+                    offset = 0
+                    for t in tensors:
+                        t.copy_(flat[offset:offset + t.numel()].view_as(t))
+                        offset += t.numel()
+
+            bucket, size = [], 0
             for d in deltas:
-                d.copy_(flat[offset:offset + d.numel()].view_as(d))
-                offset += d.numel()
+                if d.numel() >= self.BUCKET_ELEMS:
+                    average([d])
+                    continue
+                bucket.append(d)
+                size += d.numel()
+                if size >= self.BUCKET_ELEMS:
+                    average(bucket)
+                    bucket, size = [], 0
+            if bucket:
+                average(bucket)
         mu = self.outer_momentum
         for anchor, vel, delta, tensor in zip(self._anchor, self._momentum, deltas, tensors):
             vel.mul_(mu).add_(delta)
