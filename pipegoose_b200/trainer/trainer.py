@@ -20,12 +20,13 @@ class Trainer:
                  callbacks: Optional[List[Callback]] = None, loggers: Optional[List[DistributedLogger]] = None,
                  parallel_context=None, log_every: int = 10, grad_accum_steps: int = 1,
                  max_grad_norm: Optional[float] = None, lr_scheduler=None, checkpoint_dir: Optional[str] = None,
-                 checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None):
+                 checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None,
+                 max_steps: Optional[int] = None):
         """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
         norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
         and optimizer / RNG / step state (save_training_state) every N optimizer steps; ``resume=True`` restores the
-        latest one before training and skips the batches it had consumed.  ``watchdog_timeout_s``: start a
+        latest one before training and skips the batches it had consumed.  ``max_steps``: stop at that optimizer step.  ``watchdog_timeout_s``: start a
         :class:`RankWatchdog` for the duration of ``fit``."""
         assert grad_accum_steps >= 1
         self.module = module
@@ -44,6 +45,7 @@ class Trainer:
         self.checkpoint_every = checkpoint_every
         self.resume = resume
         self.watchdog_timeout_s = watchdog_timeout_s
+        self.max_steps = max_steps   # stop once this many optimizer steps exist in total (counting resumed ones)
         self.state = TrainerState()
         self._micro = 0
         self._skip_batches = 0
@@ -162,6 +164,8 @@ class Trainer:
             self.state.epoch = epoch
             self._call("on_epoch_start")
             for batch in self.train_loader:
+                if self.max_steps is not None and self.state.step >= self.max_steps and self._micro == 0:
+                    break
                 seen += 1
                 if seen <= self._skip_batches:   # consumed before the checkpoint this run resumed from
                     continue
