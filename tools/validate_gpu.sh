@@ -66,6 +66,31 @@ for l in sys.stdin:
   echo "-- fused MoE layer (T=8)"
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29538 tools/moe_bench.py 2>&1 | grep "^{" | cut -c1-400
 fi
+echo "== kernel variants built by tools/build_variants.sh (same Python, different _C_<name>.so): numerics, then A/B"
+bench_line() { python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('   ', round(d['ms_per_step'], 2), 'ms/step  loss', d['final_loss'])
+"; }
+if [ -f pipegoose_b200/_C_pdl.so ]; then
+  echo "-- pdl: kernel tests"; PIPEGOOSE_B200_EXT=pdl PIPEGOOSE_B200_PDL=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q 2>&1 | tail -2
+  echo "-- main 1 GPU";           python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
+  echo "-- pdl (attribute off)";  PIPEGOOSE_B200_EXT=pdl python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
+  echo "-- pdl (PDL=1)";          PIPEGOOSE_B200_EXT=pdl PIPEGOOSE_B200_PDL=1 python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
+fi
+if [ -f pipegoose_b200/_C_coresident.so ]; then
+  echo "-- coresident: kernel tests + GEMM table"; PIPEGOOSE_B200_EXT=coresident timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q 2>&1 | tail -2
+  PIPEGOOSE_B200_EXT=coresident timeout 400 python tools/gemm_check.py epi 2>&1 | grep "cta1:\|FAIL" | head -6
+  echo "-- coresident 1 GPU (cost of 152 registers)"; PIPEGOOSE_B200_EXT=coresident python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
+  if [ "$N" -ge 2 ]; then
+    echo "-- dp2 main (64 x 512-thread CTAs)";            python bench.py --gpus 2 --tp 1 --steps 10 --warmup 3 | bench_line
+    echo "-- dp2 coresident, old reducer";                PIPEGOOSE_B200_EXT=coresident python bench.py --gpus 2 --tp 1 --steps 10 --warmup 3 | bench_line
+    for ctas in -148 -296; do
+      echo "-- dp2 coresident, $ctas small CTAs";         PIPEGOOSE_B200_EXT=coresident PIPEGOOSE_B200_DP_OVERLAP_CTAS=$ctas python bench.py --gpus 2 --tp 1 --steps 10 --warmup 3 | bench_line
+    done
+  fi
+fi
 echo "== 1-GPU step breakdown (ncu launch list)"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py > /dev/null 2>&1
 python tools/step_profile.py --aggregate gpurun_out/step_launches.csv gpurun_out/step_breakdown.json | head -22
