@@ -1,18 +1,26 @@
 #!/usr/bin/env bash
-# One-call GPU validation (run under gpurun; pass the number of GPUs of the box):
-#   gpurun --gpus 4 --timeout 1200 -- 'bash tools/validate_gpu.sh 4'
-# Steps (each writes to gpurun_out/): kernel numerics + GEMM perf table, the gpu test-suite, bench at every
-# power-of-two N up to the box size, the fused-TP micro-bench (N>=2), a per-kernel step breakdown (N=1, ncu).
-# Box-to-box variance is ~10 %: compare numbers from ONE call only.
+# GPU validation in as few GPU-minutes as possible (run under gpurun; pass the number of GPUs of the box):
+#   gpurun --timeout 1500 -- 'bash tools/validate_gpu.sh 1 > gpurun_out/validate1.log 2>&1'            (1 GPU)
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/validate_gpu.sh 2 > gpurun_out/validate2.log 2>&1'   (2 GPUs)
+# N=1: kernel numerics + GEMM perf table, the whole gpu test-suite, bench, kernel-variant A/B, ncu step breakdown.
+# N=2: multi-GPU tests, bench, fused-TP / fused-MoE micro-benches, env-gated switches, reducer A/B.   N=4: + convergence.
+# N=8: bench at 4 and 8 GPUs + BASELINE configs #3-#5.   Box-to-box variance is ~10 %: compare numbers from ONE call only.
 set -uo pipefail
 N="${1:-1}"
 mkdir -p gpurun_out
-echo "== gemm_check (correctness of every layout / epilogue / CTA-pair variant + perf vs cuBLAS)"
-timeout 400 python tools/gemm_check.py epi > gpurun_out/gemm_check.log 2>&1; grep -c "^OK" gpurun_out/gemm_check.log; grep "FAIL" gpurun_out/gemm_check.log | head; grep "cta1:" gpurun_out/gemm_check.log
-echo "== pytest -m gpu"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+# GPU-minutes are charged x N: everything that needs ONE GPU runs only in the N=1 call, the N>=2 calls run only what
+# needs several GPUs.  Typical session: `validate_gpu.sh 1` (1-GPU box), then `validate_gpu.sh 2`, later `validate_gpu.sh 8`.
+if [ "$N" -eq 1 ]; then
+  echo "== gemm_check (correctness of every layout / epilogue / CTA-pair variant + perf vs cuBLAS)"
+  timeout 400 python tools/gemm_check.py epi > gpurun_out/gemm_check.log 2>&1; grep -c "^OK" gpurun_out/gemm_check.log; grep "FAIL" gpurun_out/gemm_check.log | head; grep "cta1:" gpurun_out/gemm_check.log
+  echo "== pytest -m gpu (multi-GPU tests skip themselves)"
+  timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+else
+  echo "== pytest -m gpu: the multi-GPU tests"
+  timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_hybrid.py -m gpu -x -q 2>&1 | tail -4
+fi
 for n in 1 2 4 8; do
-  if [ "$n" -le "$N" ]; then
+  if [ "$n" -eq "$N" ] || { [ "$N" -ge 4 ] && [ "$n" -ge 4 ] && [ "$n" -le "$N" ]; }; then
     echo "== bench N=$n"
     python bench.py --gpus "$n" --steps 10 --warmup 3 | tee "gpurun_out/bench_${n}gpu.json" | python -c "
 import sys, json
@@ -73,7 +81,7 @@ for l in sys.stdin:
     if l.startswith('{'):
         d = json.loads(l); print('   ', round(d['ms_per_step'], 2), 'ms/step  loss', d['final_loss'])
 "; }
-if [ -f pipegoose_b200/_C_pdl.so ]; then
+if [ -f pipegoose_b200/_C_pdl.so ] && [ "$N" -eq 1 ]; then
   echo "-- pdl: kernel tests"; PIPEGOOSE_B200_EXT=pdl PIPEGOOSE_B200_PDL=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q 2>&1 | tail -2
   echo "-- main 1 GPU";           python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
   echo "-- pdl (attribute off)";  PIPEGOOSE_B200_EXT=pdl python bench.py --gpus 1 --steps 10 --warmup 3 | bench_line
@@ -91,6 +99,7 @@ if [ -f pipegoose_b200/_C_coresident.so ]; then
     done
   fi
 fi
+[ "$N" -eq 1 ] || exit 0
 echo "== 1-GPU step breakdown (ncu launch list)"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/step_launches.csv python tools/step_profile.py > /dev/null 2>&1
 python tools/step_profile.py --aggregate gpurun_out/step_launches.csv gpurun_out/step_breakdown.json | head -22
