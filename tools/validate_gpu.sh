@@ -4,7 +4,7 @@
 #   gpurun --gpus 2 --timeout 1200 -- 'bash tools/validate_gpu.sh 2 > gpurun_out/validate2.log 2>&1'   (2 GPUs)
 # N=1: kernel numerics + GEMM perf table, the whole gpu test-suite, bench, kernel-variant A/B, ncu step breakdown.
 # N=2: multi-GPU tests, bench, fused-TP / fused-MoE micro-benches, env-gated switches, reducer A/B.   N=4: + convergence.
-# N=8: bench at 4 and 8 GPUs + BASELINE configs #3-#5.   Box-to-box variance is ~10 %: compare numbers from ONE call only.
+# N=8: bench + BASELINE configs #3-#5.   Box-to-box variance is ~10 %: compare numbers from ONE call only.
 set -uo pipefail
 N="${1:-1}"
 mkdir -p gpurun_out
@@ -20,7 +20,7 @@ else
   timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_hybrid.py -m gpu -x -q 2>&1 | tail -4
 fi
 for n in 1 2 4 8; do
-  if [ "$n" -eq "$N" ] || { [ "$N" -ge 4 ] && [ "$n" -ge 4 ] && [ "$n" -le "$N" ]; }; then
+  if [ "$n" -eq "$N" ]; then
     echo "== bench N=$n"
     python bench.py --gpus "$n" --steps 10 --warmup 3 | tee "gpurun_out/bench_${n}gpu.json" | python -c "
 import sys, json
@@ -30,7 +30,7 @@ for l in sys.stdin:
 "
   fi
 done
-if [ "$N" -ge 2 ]; then
+if [ "$N" -eq 2 ]; then
   echo "== fused TP kernels vs NCCL + GEMM (T=2)"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/tp_bench.py 2>&1 | grep "^{" | python -c "
 import sys, json
@@ -53,7 +53,7 @@ for l in sys.stdin:
   echo "== TP2 step breakdown (torch profiler, diagnosis only)"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -24
 fi
-if [ "$N" -ge 4 ]; then
+if [ "$N" -eq 4 ]; then
   echo "== convergence: TP2 x DP2 + ZeRO-1 (bf16, fused kernels) next to a single-GPU model"
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29535 examples/convergence_hybrid.py --tp 2 --dp 2 --steps 60 2>&1 | grep "^step\|^loss" | tee gpurun_out/convergence_tp2dp2.txt | tail -5
 fi
