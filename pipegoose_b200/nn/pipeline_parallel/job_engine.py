@@ -87,7 +87,9 @@ class JobPipelineEngine:
         inputs = {"input_ids": input_ids, "labels": labels}
         mbs = mb_utils.split({k: v for k, v in inputs.items() if v is not None}, self.scheduler.n_microbatches)
         m = len(mbs)
-        batch_seq = tuple(mbs[0]["input_ids"].shape)
+        from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import PipelineEngine
+
+        weights = PipelineEngine._microbatch_weights(mbs) if self.is_last else None   # share of the target tokens
         Q.clear_all()
         for p in self.module.parameters():
             p.grad = None
@@ -104,7 +106,7 @@ class JobPipelineEngine:
                 if self.is_last:
                     fn = (lambda mb: (lambda x: self.module(x, labels=mb["labels"], batch_seq=tuple(mb["input_ids"].shape))))(mbs[i])
                 else:
-                    fn = lambda x: self.module(x, batch_seq=batch_seq)  # noqa: E731
+                    fn = (lambda mb: (lambda x: self.module(x, batch_seq=tuple(mb["input_ids"].shape))))(mbs[i])
             if self.is_first and self.is_last:
                 fn = (lambda mb: (lambda x: self.module(x, labels=mb["labels"])))(mbs[i])
             outs[i] = self._run_job(create_job(fn, pkg, ctx, self.pipeline_context))
@@ -115,7 +117,7 @@ class JobPipelineEngine:
         for i in reversed(range(m)):
             if self.is_last:
                 y = schedule_backward_execution(outs[i])      # loss.backward() only records d loss / d output
-                loss = y / m
+                loss = y * weights[i]
                 losses.append(loss.detach())
                 loss.backward()
                 grad = Q.get_grad_loss(i, outs[i].metadata.partition_idx)

@@ -348,3 +348,37 @@ def test_job_runtime_engine_matches_sequential_training_step(pp):
     loss.backward()
     spawn(run_job_engine, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_loss=loss.detach(),
           ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
+
+
+def run_job_engine_uneven(rank, world_size, port, state, ids, labels, ref_loss, ref_grads):
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import PipelineParallel
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 3, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=6, n_head=4))
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx, runtime="jobs").parallelize()
+    out = model(ids, labels=labels)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+    for p in model._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
+    model._pg_pipeline_engine.destroy()
+    ctx.destroy()
+
+
+def test_job_runtime_with_uneven_micro_batches_and_ignored_labels():
+    """5 sequences in 2 micro-batches over 3 stages (a middle stage sees both shapes), one sequence partly ignored."""
+    import copy
+
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=6, n_head=4))
+    ids = torch.randint(0, 96, (5, 8))
+    labels = ids.clone()
+    labels[4, 4:] = -100
+    loss = model(ids, labels=labels).loss
+    loss.backward()
+    spawn(run_job_engine_uneven, world_size=3, state=copy.deepcopy(model.state_dict()), ids=ids, labels=labels,
+          ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
