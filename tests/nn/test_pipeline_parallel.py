@@ -283,7 +283,7 @@ def test_pipeline_engine_facade_runs_a_pipelined_step():
 
 
 def run_uneven_microbatches(rank, world_size, port, state, ids, labels, n_mb, ref_loss, ref_grads):
-    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    ctx = init_parallel_context(rank, world_size, port, 1, world_size, 1)
     model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
     model.load_state_dict(state)
     names = {id(p): n for n, p in model.named_parameters()}
@@ -296,8 +296,8 @@ def run_uneven_microbatches(rank, world_size, port, state, ids, labels, n_mb, re
     ctx.destroy()
 
 
-@pytest.mark.parametrize("batch,n_mb", [(5, 2), (6, 4)])
-def test_uneven_microbatches_and_ignored_labels_give_the_global_token_mean(batch, n_mb):
+@pytest.mark.parametrize("batch,n_mb,pp", [(5, 2, 2), (6, 4, 2), (5, 2, 4), (7, 3, 4)])
+def test_uneven_microbatches_and_ignored_labels_give_the_global_token_mean(batch, n_mb, pp):
     """Micro-batch losses are weighted by their share of target tokens: the pipelined loss and gradients equal the
     unpartitioned model's even when the batch does not split evenly and some labels are -100."""
     torch.manual_seed(0)
@@ -307,5 +307,5 @@ def test_uneven_microbatches_and_ignored_labels_give_the_global_token_mean(batch
     labels[0, 5:] = -100          # padding on one sequence
     loss = model(ids, labels=labels).loss
     loss.backward()
-    spawn(run_uneven_microbatches, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids, labels=labels, n_mb=n_mb,
+    spawn(run_uneven_microbatches, world_size=pp, state=copy.deepcopy(model.state_dict()), ids=ids, labels=labels, n_mb=n_mb,
           ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
