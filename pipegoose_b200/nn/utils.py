@@ -20,6 +20,14 @@ def _ckpt_file(ckp_path: str, ckp_name: str, parallel_context: ParallelContext) 
     return os.path.join(ckp_path, ckp_name.format(tp_rank, pp_rank))
 
 
+def _atomic_save(obj, path: str):
+    """Write next to the target and rename: a job killed mid-write never leaves a truncated checkpoint behind (the
+    previous complete file stays in place until the new one is whole)."""
+    tmp = f"{path}.tmp.{os.getpid()}"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
+
+
 def from_pretrained(module: nn.Module, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
                     ckp_name: str = CHECKPOINT_WEIGHTS_NAME):
     """Load this rank's (tp, pp) shard into an already parallelized ``module``."""
@@ -43,7 +51,7 @@ def save_pretrained(module: nn.Module, ckp_name: str = CHECKPOINT_WEIGHTS_NAME, 
     Path(ckp_path).mkdir(parents=True, exist_ok=True)
     if parallel_context.get_local_rank(ParallelMode.DATA) == 0:
         state = {k: v.detach().cpu() for k, v in module.state_dict().items()}
-        torch.save(state, _ckpt_file(ckp_path, ckp_name, parallel_context))
+        _atomic_save(state, _ckpt_file(ckp_path, ckp_name, parallel_context))
     if parallel_context.get_world_size(ParallelMode.DATA) > 1:
         import torch.distributed as dist
 
@@ -87,7 +95,7 @@ def save_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
             "rng": {"torch": torch.get_rng_state(),
                     "cuda": torch.cuda.get_rng_state() if torch.cuda.is_available() else None},
             "extra": extra or {}}
-    torch.save(blob, _optim_file(ckp_path, parallel_context))
+    _atomic_save(blob, _optim_file(ckp_path, parallel_context))
 
 
 def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
