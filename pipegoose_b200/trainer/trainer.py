@@ -21,11 +21,12 @@ class Trainer:
                  parallel_context=None, log_every: int = 10, grad_accum_steps: int = 1,
                  max_grad_norm: Optional[float] = None, lr_scheduler=None, checkpoint_dir: Optional[str] = None,
                  checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None,
-                 max_steps: Optional[int] = None):
+                 max_steps: Optional[int] = None, keep_checkpoints: int = 2):
         """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
         norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
-        and optimizer / RNG / step state (save_training_state) every N optimizer steps; ``resume=True`` restores the
+        and optimizer / RNG / step state (save_training_state) every N optimizer steps, each in its own ``step_<n>``
+        directory that becomes ``latest`` only when every rank has written its shard (``keep_checkpoints`` newest kept); ``resume=True`` restores the
         latest one before training and skips the batches it had consumed.  ``max_steps``: stop at that optimizer step.  ``watchdog_timeout_s``: start a
         :class:`RankWatchdog` for the duration of ``fit``."""
         assert grad_accum_steps >= 1
@@ -45,6 +46,7 @@ class Trainer:
         self.checkpoint_every = checkpoint_every
         self.resume = resume
         self.watchdog_timeout_s = watchdog_timeout_s
+        self.keep_checkpoints = max(1, keep_checkpoints)   # newest complete step directories kept on disk
         self.max_steps = max_steps   # stop once this many optimizer steps exist in total (counting resumed ones)
         self.state = TrainerState()
         self._micro = 0
@@ -103,37 +105,69 @@ class Trainer:
         return loss
 
     # ------------------------------------------------------------------ checkpoints
+    # layout:  <checkpoint_dir>/step_00000500/{pytorch_model_tp_*_pp_*.bin, optimizer_tp_*_pp_*_dp_*.bin}
+    #          <checkpoint_dir>/latest        <- name of the newest COMPLETE step directory (written last, atomically)
+    def _barrier(self):
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+
     def save_checkpoint(self):
+        import os
+        import shutil
+
         from pipegoose_b200.nn.utils import save_pretrained, save_training_state
 
         ctx = self.parallel_context
         assert ctx is not None, "checkpoints are sharded by (tp, pp, dp) rank: a ParallelContext is required"
-        save_pretrained(self.module, ckp_path=self.checkpoint_dir, parallel_context=ctx)
+        name = f"step_{self.state.step:08d}"
+        path = os.path.join(self.checkpoint_dir, name)
+        save_pretrained(self.module, ckp_path=path, parallel_context=ctx)
         extra = {"epoch": self.state.epoch, "tokens_seen": self.state.tokens_seen,
                  "lr_scheduler": self.lr_scheduler.state_dict() if hasattr(self.lr_scheduler, "state_dict") else None}
-        save_training_state(self.optim, self.checkpoint_dir, ctx, step=self.state.step, extra=extra)
-        self._log(f"checkpoint written at step {self.state.step} -> {self.checkpoint_dir}")
+        save_training_state(self.optim, path, ctx, step=self.state.step, extra=extra)
+        self._barrier()                       # every rank's shard is on disk ...
+        if ctx.get_global_rank() == 0:        # ... only then does the checkpoint become the one to resume from
+            tmp = os.path.join(self.checkpoint_dir, f".latest.{os.getpid()}")
+            with open(tmp, "w") as f:
+                f.write(name)
+            os.replace(tmp, os.path.join(self.checkpoint_dir, "latest"))
+            done = sorted(d for d in os.listdir(self.checkpoint_dir) if d.startswith("step_"))
+            for stale in done[:-self.keep_checkpoints]:
+                shutil.rmtree(os.path.join(self.checkpoint_dir, stale), ignore_errors=True)
+        self._barrier()
+        self._log(f"checkpoint written at step {self.state.step} -> {path}")
+
+    def _latest_checkpoint(self) -> Optional[str]:
+        import os
+
+        marker = os.path.join(self.checkpoint_dir, "latest")
+        if not os.path.exists(marker):
+            return None
+        with open(marker) as f:
+            path = os.path.join(self.checkpoint_dir, f.read().strip())
+        return path if os.path.isdir(path) else None
 
     def load_checkpoint(self) -> bool:
-        """Restore the latest checkpoint of ``checkpoint_dir`` if there is one; returns whether it did."""
-        from pipegoose_b200.nn.utils import _optim_file, from_pretrained, load_training_state
+        """Restore the newest complete checkpoint of ``checkpoint_dir`` if there is one; returns whether it did."""
+        from pipegoose_b200.nn.utils import from_pretrained, load_training_state
 
         ctx = self.parallel_context
         if ctx is None or not self.checkpoint_dir:
             return False
-        import os
-
-        if not os.path.exists(_optim_file(self.checkpoint_dir, ctx)):
+        path = self._latest_checkpoint()
+        if path is None:
             return False
-        from_pretrained(self.module, ckp_path=self.checkpoint_dir, parallel_context=ctx)
-        meta = load_training_state(self.optim, self.checkpoint_dir, ctx)
+        from_pretrained(self.module, ckp_path=path, parallel_context=ctx)
+        meta = load_training_state(self.optim, path, ctx)
         self.state.step = meta["step"]
         extra = meta.get("extra") or {}
         self.state.tokens_seen = extra.get("tokens_seen", 0)
         if self.lr_scheduler is not None and extra.get("lr_scheduler") is not None:
             self.lr_scheduler.load_state_dict(extra["lr_scheduler"])
         self._skip_batches = self.state.step * self.grad_accum_steps
-        self._log(f"resumed from step {self.state.step}")
+        self._log(f"resumed from step {self.state.step} ({path})")
         return True
 
     def fit(self):

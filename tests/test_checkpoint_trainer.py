@@ -203,3 +203,32 @@ def test_trainer_matches_a_hand_written_single_process_loop():
         sched.step()
     ref_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     spawn(run_trainer_vs_reference, world_size=4, tp=2, dp=dp, state=state, data_by_dp=data_by_dp, ref_state=ref_state)
+
+
+def run_ckpt_layout(rank, world_size, port, ckp_dir):
+    from pipegoose_b200.nn import DataParallel
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 2)
+    torch.manual_seed(0)
+    model = DataParallel(BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=32, n_layer=1, n_head=4)), ctx).parallelize()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    data = [{"input_ids": torch.randint(0, 64, (2, 8))} for _ in range(6)]
+    Trainer(model, data, optim=optim, parallel_context=ctx, checkpoint_dir=ckp_dir, checkpoint_every=2, keep_checkpoints=2).fit()
+    torch.distributed.barrier()
+    kept = sorted(d for d in os.listdir(ckp_dir) if d.startswith("step_"))
+    assert kept == ["step_00000004", "step_00000006"], kept                     # the two newest complete checkpoints
+    assert open(os.path.join(ckp_dir, "latest")).read() == "step_00000006"
+    files = sorted(os.listdir(os.path.join(ckp_dir, "step_00000006")))
+    assert files == ["optimizer_tp_0_pp_0_dp_0.bin", "optimizer_tp_0_pp_0_dp_1.bin", "pytorch_model_tp_0_pp_0.bin"], files
+    assert not [f for f in os.listdir(ckp_dir) if ".tmp." in f or f.startswith(".latest")]
+    # a half-written newer directory (crash before "latest" moved) is ignored by resume
+    os.makedirs(os.path.join(ckp_dir, "step_00000008"), exist_ok=True)
+    trainer = Trainer(model, data, optim=optim, parallel_context=ctx, checkpoint_dir=ckp_dir, resume=True)
+    assert trainer.load_checkpoint() and trainer.state.step == 6
+    ctx.destroy()
+
+
+def test_trainer_checkpoint_directories_and_latest_marker(tmp_path):
+    spawn(run_ckpt_layout, world_size=2, ckp_dir=str(tmp_path / "ckpt"))
