@@ -46,3 +46,24 @@ class DistributedLogger:
 
     def error(self, msg: str):
         self._log("ERROR", msg)
+
+
+class JsonlLogger(DistributedLogger):
+    """One JSON object per logged training step (``step, loss, tokens_per_s, grad_norm, lr, tokens_seen``) appended to a
+    file by the chosen global rank — what dashboards and regression checks read; text messages are recorded, not printed."""
+
+    def __init__(self, path: str, parallel_context=None, rank: int = 0):
+        import io
+
+        super().__init__(parallel_context, name="metrics", rank=rank, stream=io.StringIO())
+        self.path = path
+
+    def log_metrics(self, metrics: dict):
+        import json
+        import os
+
+        if not self._should_log():
+            return
+        os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
+        with open(self.path, "a") as f:
+            f.write(json.dumps(metrics) + "\n")

@@ -71,6 +71,15 @@ class Trainer:
         for lg in self.loggers:
             lg.info(msg)
 
+    def _log_metrics(self, metrics: dict):
+        for lg in self.loggers:
+            if hasattr(lg, "log_metrics"):
+                lg.log_metrics({k: v for k, v in metrics.items() if v == v})   # drop NaNs (e.g. no clipping configured)
+
+    def _current_lr(self) -> float:
+        groups = getattr(self.optim, "param_groups", None) or [{}]
+        return float(groups[0].get("lr", float("nan")))
+
     def train_step(self, batch) -> torch.Tensor:
         """One micro-batch: forward + backward; the optimizer steps on every ``grad_accum_steps``-th call."""
         from contextlib import nullcontext
@@ -211,6 +220,10 @@ class Trainer:
                         dt = max(time.time() - t0, 1e-9)
                         self._log(f"step {self.state.step} loss {self.state.last_loss:.4f} "
                                   f"tokens/s {(self.state.tokens_seen - tok0) / dt:.0f}")
+                        self._log_metrics({"step": self.state.step, "loss": self.state.last_loss,
+                                           "tokens_per_s": (self.state.tokens_seen - tok0) / dt,
+                                           "tokens_seen": self.state.tokens_seen, "grad_norm": self.state.last_grad_norm,
+                                           "lr": self._current_lr()})
                     self._call("on_step_end", loss)
             self._call("on_epoch_end")
 

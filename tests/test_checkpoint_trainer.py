@@ -56,10 +56,19 @@ def test_trainer_fits_and_logs():
         def on_fit_end(self, trainer):
             events.append("end")
 
+    import json
+    import tempfile
+
+    from pipegoose_b200.trainer import JsonlLogger
+
     stream = io.StringIO()
+    metrics_file = os.path.join(tempfile.mkdtemp(), "run", "metrics.jsonl")
     trainer = Trainer(model, data, optim=FusedAdam(model.parameters(), lr=1e-2), num_epochs=2, callbacks=[Rec()],
-                      loggers=[DistributedLogger(stream=stream)], log_every=3)
+                      loggers=[DistributedLogger(stream=stream), JsonlLogger(metrics_file)], log_every=3, max_grad_norm=10.0)
     state = trainer.fit()
+    rows = [json.loads(line) for line in open(metrics_file)]
+    assert [r["step"] for r in rows] == [3, 6, 9, 12] and rows[-1]["loss"] < rows[0]["loss"]
+    assert all({"tokens_per_s", "tokens_seen", "grad_norm", "lr"} <= set(r) for r in rows) and rows[0]["lr"] == 1e-2
     assert state.status is TrainerStatus.FINISHED and state.step == 12 and state.tokens_seen == 12 * 16
     assert events[0] == "start" and events[-1] == "end" and events[-2] < events[1]  # loss went down
     assert "tokens/s" in stream.getvalue()
