@@ -38,6 +38,9 @@ class DataParallel(Parallel):
             module._pg_grad_reducer = reducer
             module.no_sync = reducer.no_sync
             module._pg_dp_build_hook = module.register_forward_pre_hook(_build_on_first_forward)
+            reducer.ensure_built = lambda: _build_on_first_forward(module, None)
+            for p in module.parameters():   # lets an optimizer created before the first forward find (and build) it
+                p._pg_dp_reducer = reducer
             if self.broadcast_parameters:
                 module._pg_needs_param_broadcast = True
             self._save_metadata(module, ctx)
@@ -55,6 +58,8 @@ class DataParallel(Parallel):
                 del p._pg_autograd_hook
             if hasattr(p, "_pg_grad_ready"):
                 del p._pg_grad_ready
+            if hasattr(p, "_pg_dp_reducer"):
+                del p._pg_dp_reducer
         h = getattr(module, "_pg_dp_build_hook", None)
         if h is not None:
             h.remove()

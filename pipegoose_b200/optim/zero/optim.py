@@ -72,20 +72,23 @@ class DistributedOptimizer(BaseDistributedOptimizer):
     # ------------------------------------------------------------------ fused path
     def _setup_fused(self):
         optim = self.optim
+        self._reducer = None
+        if self.dp > 1:
+            # the module's gradient reducer (installed by DataParallel) owns the flat state.  It is normally built by the
+            # first forward; ``optim.zero_grad()`` BEFORE the first forward (the usual PyTorch order) builds it here.
+            reducer = next((getattr(p, "_pg_dp_reducer", None) for p in self._all_params
+                            if getattr(p, "_pg_dp_reducer", None) is not None), None)
+            assert reducer is not None, \
+                "DistributedOptimizer(FusedAdam) with dp>1 expects the module to be wrapped by DataParallel first"
+            if reducer.flat is None:
+                reducer.ensure_built()
+            self._reducer = reducer
         flat = optim.flat
         if flat is None:
             optim.ensure_flat()
             flat = optim.flat
-        self._reducer = None
         if self.dp > 1:
-            # the module's gradient reducer (installed by DataParallel) shares the flat state
-            for p in flat.params:
-                hook = getattr(p, "_pg_grad_ready", None)
-                if hook is not None:
-                    self._reducer = hook.__self__
-                    break
-            assert self._reducer is not None and self._reducer.flat is flat, \
-                "DistributedOptimizer(FusedAdam) with dp>1 expects the module to be wrapped by DataParallel first"
+            assert self._reducer.flat is flat, "the optimizer and the DataParallel reducer must share one flat state"
             self._reducer.mode = "reduce_scatter"
             optim.set_bucket_shards(self._reducer.bucket_numel, self.dp_rank, self.dp)
         self._zero_ready = True

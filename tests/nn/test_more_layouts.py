@@ -198,3 +198,43 @@ def test_gpt2_padded_vocabulary_trains_under_tp_pp_and_exports():
         ref.append(total)
     spawn(run_gpt2_round_trip, world_size=4, state=state, ids=ids, ref_losses=ref,
           ref_generated=model.generate(ids[:, :5], max_new_tokens=4))
+
+
+# ------------------------------------------------------------------ zero_grad() first, accumulation under no_sync()
+def _hf_bloom_accum():
+    from transformers import BloomConfig, BloomForCausalLM
+    return BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+def run_zero_grad_first(rank, world_size, port, tp, fused, state, ids, ref_state):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 2)
+    m = _hf_bloom_accum(); m.load_state_dict(state); m.train()
+    names = {id(p): n for n, p in m.named_parameters()}
+    m = TensorParallel(m, ctx).parallelize(); m = DataParallel(m, ctx).parallelize()
+    opt = DistributedOptimizer(FusedAdam(m.parameters(), lr=1e-2, eps=1e-3) if fused else torch.optim.SGD(m.parameters(), lr=0.5), ctx)
+    local = ids.chunk(2)[ctx.get_local_rank(ParallelMode.DATA)]
+    for step in range(2):
+        mbs = local.chunk(2)
+        opt.zero_grad()
+        with m.no_sync():
+            (m(input_ids=mbs[0], labels=mbs[0]).loss / 2).backward()
+        (m(input_ids=mbs[1], labels=mbs[1]).loss / 2).backward()
+        opt.step()
+    for p in m.parameters():
+        n = names.get(id(p))
+        if n is not None and p.shape == ref_state[n].shape:
+            assert torch.allclose(p.detach(), ref_state[n], atol=3e-5), n
+    ctx.destroy()
+@pytest.mark.parametrize("tp,fused", [(1, False), (1, True), (2, False), (2, True)])
+def test_zero_grad_before_the_first_forward_and_no_sync_accumulation(tp, fused):
+    """`optim.zero_grad()` first (the usual PyTorch order) must find and build the DataParallel reducer; micro-steps under
+    `no_sync()` accumulate locally — 🤗 Bloom class-swap TP x DP, stock SGD and the fused ZeRO-1 optimizer."""
+    torch.manual_seed(0)
+    m = _hf_bloom_accum(); m.train(); state = copy.deepcopy(m.state_dict())
+    ids = torch.randint(0, 96, (8, 8))
+    opt = FusedAdam(m.parameters(), lr=1e-2, eps=1e-3) if fused else torch.optim.SGD(m.parameters(), lr=0.5)
+    for step in range(2):
+        opt.zero_grad()
+        for rep in ids.chunk(2):
+            for mb in rep.chunk(2):
+                (m(input_ids=mb, labels=mb).loss / 4).backward()
+        opt.step()
+    spawn(run_zero_grad_first, world_size=2 * tp, tp=tp, fused=fused, state=state, ids=ids, ref_state={k: v.detach().clone() for k, v in m.state_dict().items()})
