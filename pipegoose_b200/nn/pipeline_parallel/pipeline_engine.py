@@ -235,6 +235,27 @@ class PipelineEngine:
             outputs.append(out if self.is_last else _SendToNext.apply(out, self.link))
         return outputs
 
+    @torch.no_grad()
+    def eval_loss(self, inputs: Dict) -> torch.Tensor:
+        """Mean loss over the batch's target tokens, forward only (``with torch.no_grad(): model(ids, labels=...)``)."""
+        mbs = self._prepare(inputs)
+        dev = self._device()
+        weights = self._microbatch_weights(mbs) if self.is_last else None
+        total = torch.zeros((), device=dev)
+        for i, mb in enumerate(mbs):
+            if self.is_first:
+                x = self._first_input(mb)
+            else:
+                shape, dtype = self._in_meta[self._mb_key(mb)]
+                x = torch.empty(shape, dtype=dtype, device=dev)
+                self.link.exchange([], [(x, self.link.prev)])
+            out = self._stage_forward(x, mb, True)
+            if self.is_last:
+                total = total + out.float() * weights[i]
+            else:
+                self.link.exchange([(out.contiguous(), self.link.next)], [])
+        return broadcast_loss_from_last_stage(total, self.parallel_context)
+
     # ------------------------------------------------------------------ scheduled training step
     def _flat_state(self):
         for p in self.module.parameters():
@@ -243,23 +264,47 @@ class PipelineEngine:
                 return st
         return None
 
-    def train_step(self, inputs: Dict) -> torch.Tensor:
+    def _optimizer_stepped_since_last_schedule(self, flat) -> bool:
+        """Did an optimizer consume the gradients of the previous schedule?  FusedAdam counts its steps; a stock optimizer
+        updates the parameters in place, which moves their version counters."""
+        from pipegoose_b200.optim.fused_adam import FusedAdam
+
+        now = (sum(p._version for p in self.module.parameters()), FusedAdam.steps_taken)
+        last = getattr(self, "_versions_after_schedule", None)
+        return last is None or now != last
+
+    def train_step(self, inputs: Dict, loss_scale: float = 1.0) -> torch.Tensor:
         # Backward runs inside this call, i.e. BEFORE the user's `optim.zero_grad()` of the canonical loop
         # (`out = model(...); optim.zero_grad(); out.loss.backward(); optim.step()`).  Flat fp32 main grads are
         # cleared here and then held until the optimizer consumed them; autograd `.grad`s are parked and
         # installed by `loss.backward()` (see _InstallGrads).
+        # Gradient accumulation: when NO optimizer step happened since the previous schedule, this schedule adds to
+        # the gradients that are already there (``loss_scale`` = 1 / number of accumulation steps scales its share).
         flat = self._flat_state()
-        if flat is not None:
-            flat.hold_grads = False
-            flat.zero_grad()
-        # the schedule produces this step's gradients from scratch: a ``.grad`` left over from the previous step
-        # (stock optimizers do not clear it, and zero_grad() only comes after forward) must not be accumulated into
-        for p in self.module.parameters():
-            p.grad = None
+        fresh = self._optimizer_stepped_since_last_schedule(flat)
+        tied_stash = None
+        if fresh:
+            if flat is not None:
+                flat.hold_grads = False
+                flat.zero_grad()
+            # the schedule produces this step's gradients from scratch: a ``.grad`` left over from the previous step
+            # (stock optimizers do not clear it, and zero_grad() only comes after forward) must not be accumulated into
+            for p in self.module.parameters():
+                p.grad = None
+        elif self.tied_group is not None and self.tied_param is not None and (self.is_first or self.is_last):
+            # the tied table's gradient is SUMMED over the first and last stage after every schedule: only this
+            # schedule's contribution may take part, what is already there was summed before
+            g = getattr(self.tied_param, "main_grad", None)
+            g = g if g is not None else self.tied_param.grad
+            if g is not None:
+                tied_stash = g.clone()
+                g.zero_()
         mbs = self._prepare(inputs)
         dev = self._device()
         m = len(mbs)
         weights = self._microbatch_weights(mbs) if self.is_last else None
+        if weights is not None and loss_scale != 1.0:
+            weights = [w * loss_scale for w in weights]
         order: List[Task] = self.scheduler.get_stage_order(self.partition_idx)
         saved_in: Dict[int, torch.Tensor] = {}
         saved_out: Dict[int, torch.Tensor] = {}
@@ -308,13 +353,13 @@ class PipelineEngine:
                 if self.is_last:
                     loss = out * weights[i]
                     if extra is not None:
-                        loss = loss + extra / m
+                        loss = loss + extra * (loss_scale / m)
                     saved_out[i] = loss
-                    losses.append((out * weights[i]).detach())   # reported: the language-model loss, as without pipelining
+                    losses.append((out * weights[i]).detach() / loss_scale)   # reported: the unscaled language-model loss
                 else:
                     saved_out[i] = out
                     if extra is not None:
-                        saved_aux[i] = extra / m
+                        saved_aux[i] = extra * (loss_scale / m)
                     pending_send = (out.detach(), self.link.next)
             else:
                 out = saved_out.pop(i)
@@ -341,8 +386,14 @@ class PipelineEngine:
                 else:
                     self.link.exchange([pending_send], [])
         self.sync_tied_embedding_grad()
+        if tied_stash is not None:
+            g = getattr(self.tied_param, "main_grad", None)
+            (g if g is not None else self.tied_param.grad).add_(tied_stash)
         if flat is not None:
             flat.hold_grads = True  # survive the zero_grad() that follows forward in the canonical loop
+        from pipegoose_b200.optim.fused_adam import FusedAdam
+
+        self._versions_after_schedule = (sum(p._version for p in self.module.parameters()), FusedAdam.steps_taken)
         if self.is_last:
             total = torch.stack(losses).sum()
         else:
@@ -392,13 +443,20 @@ class PipelineEngine:
 
     # ------------------------------------------------------------------ entry point used as module.forward
     def run(self, input_ids=None, attention_mask=None, labels=None, **kwargs):
+        """``loss_scale`` (keyword): factor on this call's gradients — pass ``1 / k`` on each of the ``k`` calls of a
+        gradient-accumulation step (the backward pass runs inside this call, a later ``(loss / k).backward()`` cannot
+        scale it any more).  The returned loss is unscaled."""
         inputs = {"input_ids": input_ids, "attention_mask": attention_mask, "labels": labels}
         inputs.update(kwargs)
         if labels is None:
             return self.forward_only(inputs)
         from pipegoose_b200.models.bloom import CausalLMOutput
 
-        loss = self.train_step(inputs)
+        if not torch.is_grad_enabled():   # evaluation: the loss only, no schedule, nothing touches the gradients
+            inputs.pop("loss_scale", None)
+            return CausalLMOutput(loss=self.eval_loss(inputs), logits=None)
+
+        loss = self.train_step(inputs, loss_scale=float(inputs.pop("loss_scale", 1.0) or 1.0))
         # backward already ran inside the schedule.  Gradients that live in `.grad` are parked and re-installed
         # by `loss.backward()`, so a `zero_grad()` between forward and backward does not lose them.
         parked = []

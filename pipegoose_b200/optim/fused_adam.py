@@ -16,6 +16,9 @@ from pipegoose_b200.ops import native, use_native
 
 
 class FusedAdam(torch.optim.Optimizer):
+    steps_taken = 0   # process-wide count of step() calls: lets the pipeline engine tell "gradients were consumed" apart
+                      # from "another accumulation micro-step" (the flat state may not exist yet during the first schedule)
+
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  adamw: bool = False, flat_state: Optional[FlatModelState] = None):
         params = list(params)
@@ -94,6 +97,7 @@ class FusedAdam(torch.optim.Optimizer):
                 master.addcdiv_(m / bc1, (v / bc2).sqrt() + eps, value=-lr)
                 param.copy_(master.to(param.dtype))
         self.flat.hold_grads = False
+        FusedAdam.steps_taken += 1
         return loss
 
     def _plan(self) -> List[Tuple[int, int, int, int]]:

@@ -90,12 +90,15 @@ class Trainer:
         first = self._micro == 0
         last = self._micro == self.grad_accum_steps - 1
         no_sync = getattr(self.module, "no_sync", None)
+        # a pipelined module runs its backward INSIDE forward: the 1/k of gradient accumulation has to go in with the call
+        pipelined = hasattr(self.module, "_pg_pipeline_engine") and self.grad_accum_steps > 1
+        extra = {"loss_scale": 1.0 / self.grad_accum_steps} if pipelined else {}
         with (no_sync() if (no_sync is not None and not last) else nullcontext()):
-            out = self.module(**batch, labels=labels)
+            out = self.module(**batch, labels=labels, **extra)
             loss = out.loss if hasattr(out, "loss") else out[0]
             if first:
                 self.optim.zero_grad()   # after the forward, as in the reference's README loop
-            (loss / self.grad_accum_steps if self.grad_accum_steps > 1 else loss).backward()
+            (loss / self.grad_accum_steps if (self.grad_accum_steps > 1 and not pipelined) else loss).backward()
         self.state.tokens_seen += int(batch["input_ids"].numel())
         self._micro += 1
         if last:
