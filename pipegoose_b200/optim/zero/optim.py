@@ -158,6 +158,9 @@ class DistributedOptimizer(BaseDistributedOptimizer):
         self.optim.step(*args, **kwargs)
         if self.dp > 1:
             self._broadcast_updated_params()
+        from pipegoose_b200.optim.fused_adam import FusedAdam
+
+        FusedAdam.steps_taken += 1   # "the gradients were consumed" for the pipeline engine, also on ranks whose shard is empty
 
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """Clip the norm of the whole model's gradient (every parameter counted once across the tensor / pipeline /
