@@ -90,3 +90,41 @@ def test_single_process_norm_matches_torch():
     want = torch.nn.utils.clip_grad_norm_([p for p in model.parameters()], 1e9)
     got = clip_grad_norm_(model, 1e9, _SingleRank())
     assert torch.allclose(got, want, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ MoE: gradient norm across layouts
+from pipegoose_b200.nn import ExpertParallel  # noqa: E402
+from pipegoose_b200.nn.expert_parallel import ExpertLoss, SwitchNoisePolicy, Top1Router  # noqa: E402
+
+
+def run_moe_norm(rank, world_size, port, tp, dp, state, gate_state, ids, out_file):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    model = BloomForCausalLM(BloomConfig(**CFG)); model.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 4, 32); router.load_state_dict(gate_state)
+    model = ExpertParallel(model, 4, mapping=[1], router=router, parallel_context=ctx).parallelize()
+    layer = model.transformer.h[1].mlp
+    first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+    for i, e in enumerate(layer.experts):
+        g = torch.Generator().manual_seed(500 + first + i)
+        for p in e.parameters():
+            p.data = p.data + 0.05 * torch.randn(p.shape, generator=g)
+    model = TensorParallel(model, ctx).parallelize(); model = DataParallel(model, ctx).parallelize()
+    model.eval()
+    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+    loss_fn = ExpertLoss(lambda out: out.loss, aux_weight=0.01, z_weight=0.001)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    loss = loss_fn(model(local, labels=local)); optim.zero_grad(); loss.backward()
+    norm = optim.clip_grad_norm_(1e9)
+    if rank == 0: torch.save(norm, out_file)
+    ctx.destroy()
+def test_global_gradient_norm_is_layout_independent_with_sharded_experts(tmp_path):
+    """Distinct experts sharded over the tensor group, router losses included, ZeRO-1 slices: the same norm in every layout."""
+    torch.manual_seed(0)
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
+    gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 4, 32).state_dict())
+    ids = torch.randint(0, 96, (4, 8)); res = {}
+    for name, (tp, dp) in {"a": (1, 1), "b": (2, 1), "c": (2, 2), "d": (1, 2)}.items():
+        f = str(tmp_path / name); spawn(run_moe_norm, world_size=tp * dp, tp=tp, dp=dp, state=state, gate_state=gate_state, ids=ids, out_file=f)
+        res[name] = torch.load(f).item()
+    assert abs(res["a"] - res["b"]) < 1e-4 * res["a"], res
+    assert abs(res["c"] - res["d"]) < 1e-4 * res["d"], res
