@@ -27,7 +27,7 @@ from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
 from pipegoose_b200.nn.pipeline_parallel._package import Metadata, Package, TrainingMetadata
 from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
 from pipegoose_b200.nn.pipeline_parallel._worker import WorkerManager
-from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import broadcast_loss_from_last_stage
+from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import PipelineEngine, _InstallGrads, broadcast_loss_from_last_stage
 from pipegoose_b200.nn.pipeline_parallel.scheduler import GPipeScheduler
 from pipegoose_b200.nn.pipeline_parallel.sync.handshake import ProgressTracker
 
@@ -87,12 +87,20 @@ class JobPipelineEngine:
         inputs = {"input_ids": input_ids, "labels": labels}
         mbs = mb_utils.split({k: v for k, v in inputs.items() if v is not None}, self.scheduler.n_microbatches)
         m = len(mbs)
-        from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import PipelineEngine
-
         weights = PipelineEngine._microbatch_weights(mbs) if self.is_last else None   # share of the target tokens
         Q.clear_all()
+        # the step's gradients are produced from scratch inside this call (see PipelineEngine.train_step): flat fp32
+        # main grads are cleared and then held until the optimizer consumed them, ``.grad``s are parked below
+        flat = PipelineEngine._flat_state(self)
+        if flat is not None:
+            flat.hold_grads = False
+            flat.zero_grad()
         for p in self.module.parameters():
             p.grad = None
+        # data-parallel reducer / tensor-parallel partial-gradient sync: reduce once, after the LAST micro-batch
+        reducer = getattr(self.full_module, "_pg_grad_reducer", None) if self.full_module is not None else None
+        if reducer is None and self.full_module is not None:
+            reducer = getattr(self.full_module, "_pg_tp_grad_sync", None)
 
         # ---- forward clock cycles
         self._init_progress(self.scheduler.get_forward_schedules())
@@ -114,7 +122,9 @@ class JobPipelineEngine:
         # ---- backward clock cycles (reverse micro-batch order, as GPipe)
         self._init_progress(self.scheduler.get_backward_schedules())
         losses = []
-        for i in reversed(range(m)):
+        from contextlib import nullcontext
+
+        for n_done, i in enumerate(reversed(range(m)), start=1):
             if self.is_last:
                 y = schedule_backward_execution(outs[i])      # loss.backward() only records d loss / d output
                 loss = y * weights[i]
@@ -124,8 +134,11 @@ class JobPipelineEngine:
                 pkg = Package(grad, self._meta(i, JobType.BACKWARD, me, me))
             else:
                 pkg = recv_package(nxt, ctx)
-            self._run_job(create_job(self.module, pkg, ctx, self.pipeline_context))
-        self._sync_tied_embedding_grad()
+            with (nullcontext() if (reducer is None or n_done == m) else reducer.no_sync()):
+                self._run_job(create_job(self.module, pkg, ctx, self.pipeline_context))
+        PipelineEngine.sync_tied_embedding_grad(self)
+        if flat is not None:
+            flat.hold_grads = True   # survive the zero_grad() that follows forward in the canonical loop
         # the job runtime mirrors the reference: router losses of MoE stages are not part of its objective; drain them so
         # that they (and their graphs) do not pile up across steps
         from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
@@ -133,17 +146,12 @@ class JobPipelineEngine:
         ExpertContext.get_instance().pop_all_aux_loss(), ExpertContext.get_instance().pop_all_z_loss()
         total = torch.stack(losses).sum() if self.is_last else torch.zeros(())
         total = broadcast_loss_from_last_stage(total, self.parallel_context)
-        return CausalLMOutput(loss=total.detach().requires_grad_(True), logits=None)
-
-    def _sync_tied_embedding_grad(self):
-        import torch.distributed as dist
-
-        if self.tied_group is None or self.tied_param is None or not (self.is_first or self.is_last):
-            return
-        p = self.tied_param
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-        dist.all_reduce(p.grad, group=self.tied_group)
+        parked = []
+        for p in self.module.parameters():   # re-installed by loss.backward(): a zero_grad() in between cannot lose them
+            if p.grad is not None:
+                parked.append((p, p.grad))
+                p.grad = None
+        return CausalLMOutput(loss=_InstallGrads.apply(total.detach().requires_grad_(True), parked), logits=None)
 
     def destroy(self):
         self.worker_manager.destroy()

@@ -17,12 +17,15 @@ CFG = dict(vocab_size=96, hidden_size=32, n_layer=4, n_head=4)
 STEPS = 3
 
 
-def run(rank, world_size, port, tp, pp, dp, n_mb, state, ids, ref_losses):
+def run(rank, world_size, port, tp, pp, dp, n_mb, state, ids, ref_losses, runtime="static", gpipe=False):
     ctx = init_parallel_context(rank, world_size, port, tp, pp, dp)
     model = BloomForCausalLM(BloomConfig(**CFG))
     model.load_state_dict(state)
     model = TensorParallel(model, ctx).parallelize()
-    model = PipelineParallel(model, num_microbatches=n_mb, parallel_context=ctx).parallelize()
+    from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType
+
+    model = PipelineParallel(model, num_microbatches=n_mb, parallel_context=ctx, runtime=runtime,
+                             scheduler_type=SchedulerType.GPIPE if gpipe else SchedulerType.ONE_F_ONE_B).parallelize()
     model = DataParallel(model, ctx).parallelize()
     optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
     local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
@@ -43,8 +46,9 @@ def run(rank, world_size, port, tp, pp, dp, n_mb, state, ids, ref_losses):
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,pp,dp", [(2, 2, 2), (1, 2, 2), (2, 2, 1), (1, 4, 2)])
-def test_3d_training_follows_single_process(tp, pp, dp):
+@pytest.mark.parametrize("tp,pp,dp,variant", [(2, 2, 2, "1f1b"), (1, 2, 2, "1f1b"), (2, 2, 1, "1f1b"), (1, 4, 2, "1f1b"),
+                                              (2, 2, 2, "gpipe"), (2, 2, 2, "jobs")])
+def test_3d_training_follows_single_process(tp, pp, dp, variant):
     torch.manual_seed(0)
     model = BloomForCausalLM(BloomConfig(**CFG))
     state = copy.deepcopy(model.state_dict())
@@ -63,7 +67,8 @@ def test_3d_training_follows_single_process(tp, pp, dp):
         opt.step()
         ref_losses.append(total)
     assert ref_losses[-1] < ref_losses[0]
-    spawn(run, world_size=tp * pp * dp, tp=tp, pp=pp, dp=dp, n_mb=n_mb, state=state, ids=ids, ref_losses=ref_losses)
+    spawn(run, world_size=tp * pp * dp, tp=tp, pp=pp, dp=dp, n_mb=n_mb, state=state, ids=ids, ref_losses=ref_losses,
+          runtime="jobs" if variant == "jobs" else "static", gpipe=variant == "gpipe")
 
 
 def run_pp_dp_stock_optimizer(rank, world_size, port, state, ids, ref_losses):

@@ -325,6 +325,7 @@ def run_job_engine(rank, world_size, port, pp, state, ids, ref_loss, ref_grads):
     for _ in range(2):  # a second step re-uses the workers and starts new tracker rounds
         out = model(ids, labels=ids)
         assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)  # broadcast from the last stage
+        out.loss.backward()   # installs the gradients the jobs computed (they survive a zero_grad() in between)
         for p in model._pg_pipeline_stage.parameters():
             assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
     # the tracker saw every task of the last (backward) schedule (earlier stages may still be finishing theirs)
@@ -361,6 +362,7 @@ def run_job_engine_uneven(rank, world_size, port, state, ids, labels, ref_loss, 
     model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx, runtime="jobs").parallelize()
     out = model(ids, labels=labels)
     assert torch.allclose(out.loss, ref_loss, atol=1e-5), (out.loss, ref_loss)
+    out.loss.backward()
     for p in model._pg_pipeline_stage.parameters():
         assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
     model._pg_pipeline_engine.destroy()
