@@ -440,6 +440,11 @@ class PipelineEngine:
             g = p.grad
         t = g if dist.get_backend(self.tied_group) != "nccl" or g.is_cuda else g.cuda()
         dist.all_reduce(t, group=self.tied_group)
+        if t is not g:
+            g.copy_(t)
+        if g is not p.grad and p.grad is not None:
+            # the data-parallel reducer already exposed the (pre-sum) main grad as ``.grad`` for a stock optimizer
+            p.grad = g.to(p.dtype)
 
     # ------------------------------------------------------------------ entry point used as module.forward
     def run(self, input_ids=None, attention_mask=None, labels=None, **kwargs):

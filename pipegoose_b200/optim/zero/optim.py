@@ -175,9 +175,13 @@ class DistributedOptimizer(BaseDistributedOptimizer):
                 self._setup_fused()
             self.optim.zero_grad()
             return
+        flat = next((p._pg_flat_state for p in self._all_params if getattr(p, "_pg_flat_state", None) is not None), None)
+        held = bool(getattr(flat, "hold_grads", False))
         for p in self._all_params:
             p.grad = None
-            if hasattr(p, "main_grad"):
+            if hasattr(p, "main_grad") and not held:
+                # (held: a pipeline schedule produced this step's gradients inside forward and the optimizer has not
+                #  consumed them yet — the fp32 main grads, which a materialised ``.grad`` may alias, must survive)
                 p._mg_fresh = p.dim() >= 2
                 if p.dim() < 2:
                     p.main_grad.zero_()

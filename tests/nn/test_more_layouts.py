@@ -238,3 +238,43 @@ def test_zero_grad_before_the_first_forward_and_no_sync_accumulation(tp, fused):
                 (m(input_ids=mb, labels=mb).loss / 4).backward()
         opt.step()
     spawn(run_zero_grad_first, world_size=2 * tp, tp=tp, fused=fused, state=state, ids=ids, ref_state={k: v.detach().clone() for k, v in m.state_dict().items()})
+
+
+# ------------------------------------------------------------------ 🤗 families through all three wrappers
+def _build_family(family):
+    import transformers as T
+    if family == "bloom":
+        return T.BloomForCausalLM(T.BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    if family == "gpt2":
+        return T.GPT2LMHeadModel(T.GPT2Config(vocab_size=96, n_embd=32, n_layer=4, n_head=4, n_positions=32, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0))
+    return T.LlamaForCausalLM(T.LlamaConfig(vocab_size=96, hidden_size=32, intermediate_size=64, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=32, tie_word_embeddings=True))
+def run_hf_3d(rank, world_size, port, family, fused, state, ids, ref_losses):
+    ctx = init_parallel_context(rank, world_size, port, 2, 2, 2)
+    m = _build_family(family); m.load_state_dict(state); m.train()
+    m = TensorParallel(m, ctx).parallelize()
+    m = PipelineParallel(m, num_microbatches=2, parallel_context=ctx).parallelize()
+    m = DataParallel(m, ctx).parallelize()
+    opt = DistributedOptimizer(FusedAdam(m.parameters(), lr=1e-2) if fused else torch.optim.Adam(m.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(2)[ctx.get_local_rank(ParallelMode.DATA)]
+    got = []
+    for _ in ref_losses:
+        loss = m(input_ids=local, labels=local).loss
+        opt.zero_grad(); loss.backward(); opt.step(); got.append(loss.item())
+    t = torch.tensor(got); torch.distributed.all_reduce(t); t /= world_size
+    for a, b in zip(t.tolist(), ref_losses):
+        assert abs(a - b) < 2e-3, (family, t.tolist(), ref_losses)
+    ctx.destroy()
+@pytest.mark.parametrize("family,fused", [("bloom", False), ("bloom", True), ("gpt2", False), ("llama", True)])
+def test_hf_families_through_tp_pp_dp_training(family, fused):
+    """🤗 Bloom / GPT-2 / LLaMA, class-swap TP x pipeline stages x DP, stock Adam (reads ``.grad``) and the fused ZeRO-1 optimizer."""
+    torch.manual_seed(0)
+    m = _build_family(family); m.train(); state = copy.deepcopy(m.state_dict())
+    ids = torch.randint(0, 96, (8, 8))
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2); ref = []
+    chunks = [mb for rep in ids.chunk(2) for mb in rep.chunk(2)]
+    for _ in range(3):
+        opt.zero_grad(); tot = 0
+        for c in chunks:
+            l = m(input_ids=c, labels=c).loss / len(chunks); l.backward(); tot += l.item()
+        opt.step(); ref.append(tot)
+    spawn(run_hf_3d, world_size=8, family=family, fused=fused, state=state, ids=ids, ref_losses=ref)
