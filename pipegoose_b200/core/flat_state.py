@@ -101,6 +101,7 @@ class FlatModelState:
         whose gradients are built with atomics, are cleared here."""
         if getattr(self, "hold_grads", False):
             return  # produced by a pipeline schedule inside forward and not consumed by the optimizer yet
+        self.grads_materialized = False
         if not lazy:
             self.flat_grad.zero_()
             for p in self.params:
@@ -131,6 +132,7 @@ class FlatModelState:
 
     def materialize_grads(self):
         """Expose ``main_grad`` as ``.grad`` in the parameter dtype (for stock torch optimizers)."""
+        self.grads_materialized = True   # (``.grad`` aliases main_grad when the dtypes agree, is a copy otherwise)
         for p in self.params:
             p.grad = p.main_grad.to(p.dtype)
 

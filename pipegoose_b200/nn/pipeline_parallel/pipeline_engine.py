@@ -442,8 +442,10 @@ class PipelineEngine:
         dist.all_reduce(t, group=self.tied_group)
         if t is not g:
             g.copy_(t)
-        if g is not p.grad and p.grad is not None:
-            # the data-parallel reducer already exposed the (pre-sum) main grad as ``.grad`` for a stock optimizer
+        flat = getattr(p, "_pg_flat_state", None)
+        if (flat is not None and getattr(flat, "grads_materialized", False) and p.grad is not None
+                and p.grad.data_ptr() != g.data_ptr()):
+            # the data-parallel reducer already exposed the (pre-sum) main grad as a ``.grad`` COPY for a stock optimizer
             p.grad = g.to(p.dtype)
 
     # ------------------------------------------------------------------ entry point used as module.forward
