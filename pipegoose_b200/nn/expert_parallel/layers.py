@@ -14,7 +14,9 @@ from pipegoose_b200.distributed.parallel_context import ParallelContext
 from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
 from pipegoose_b200.nn.expert_parallel.experts import Experts
 from pipegoose_b200.nn.expert_parallel.routers import RouterOutput
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
 from pipegoose_b200.nn.expert_parallel.utils import get_num_local_experts
+from pipegoose_b200.nn.tensor_parallel._functional import broadcast_to_tensor_group
 
 
 class ExpertLayer(nn.Module):
@@ -71,7 +73,15 @@ class ExpertLayer(nn.Module):
             # HF Bloom: mlp(layernorm_output, residual) -> keep the residual outside the experts
             residual = rest[0]
             rest[0] = torch.zeros_like(inputs)
-        out = self._experts(inputs, order, inputs, *rest, weights=weights, combine=not exchange, **kwargs)
+        expert_inputs = inputs
+        if self._experts.sharded and not exchange and self.parallel_context.get_world_size(ParallelMode.TENSOR) > 1:
+            # replicated tokens (class-swap TP, the reference's layout): every rank adds only its own experts' terms to
+            # the all-reduced output, so the gradients that flow back into the tokens and into the routing weights are
+            # partial sums — the conjugate op (identity forward, all-reduce backward) completes them on every rank
+            expert_inputs = broadcast_to_tensor_group(inputs, self.parallel_context)
+            if weights is not None:
+                weights = broadcast_to_tensor_group(weights, self.parallel_context)
+        out = self._experts(expert_inputs, order, expert_inputs, *rest, weights=weights, combine=not exchange, **kwargs)
         if exchange:
             out = comm.scatter_rows(out.reshape(-1, local_shape[-1])).view(local_shape)
         if residual is not None:

@@ -278,3 +278,44 @@ def test_hf_families_through_tp_pp_dp_training(family, fused):
             l = m(input_ids=c, labels=c).loss / len(chunks); l.backward(); tot += l.item()
         opt.step(); ref.append(tot)
     spawn(run_hf_3d, world_size=8, family=family, fused=fused, state=state, ids=ids, ref_losses=ref)
+
+
+# ------------------------------------------------------------------ 🤗 Bloom + MoE, replicated tokens
+from pipegoose_b200.nn import ExpertParallel  # noqa: E402
+from pipegoose_b200.nn.expert_parallel import ExpertLoss, SwitchNoisePolicy, Top1Router  # noqa: E402
+
+
+def _hf_bloom_for_moe():
+    import transformers as T
+    return T.BloomForCausalLM(T.BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+def run_hf_moe(rank, world_size, port, tp, dp, state, gate_state, ids, out_file):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    m = _hf_bloom_for_moe(); m.load_state_dict(state)
+    router = Top1Router(SwitchNoisePolicy(), 4, 32); router.load_state_dict(gate_state)
+    m = ExpertParallel(m, 4, mapping=[1], router=router, parallel_context=ctx).parallelize()
+    layer = m.transformer.h[1].mlp
+    first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+    for i, e in enumerate(layer.experts):
+        g = torch.Generator().manual_seed(500 + first + i)
+        for p in e.parameters():
+            p.data = p.data + 0.05 * torch.randn(p.shape, generator=g)
+    m = TensorParallel(m, ctx).parallelize(); m = DataParallel(m, ctx).parallelize(); m.eval()
+    opt = DistributedOptimizer(torch.optim.Adam(m.parameters(), lr=1e-2), ctx)
+    loss_fn = ExpertLoss(lambda out: out.loss, aux_weight=0.01, z_weight=0.001)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    losses = []
+    for _ in range(3):
+        loss = loss_fn(m(input_ids=local, labels=local)); opt.zero_grad(); loss.backward(); opt.step(); losses.append(loss.item())
+    t = torch.tensor(losses); torch.distributed.all_reduce(t)
+    if rank == 0: torch.save(t / world_size, out_file)
+    ctx.destroy()
+def test_hf_bloom_moe_with_sharded_experts_trains_like_unsharded(tmp_path):
+    """Replicated tokens (class-swap TP), distinct experts sharded over the tensor group, DP + generic ZeRO-1 Adam: the
+    gradients that flow back into the tokens and the router through the local experts are completed over the group."""
+    torch.manual_seed(0)
+    state = copy.deepcopy(_hf_bloom_for_moe().state_dict()); gate_state = copy.deepcopy(Top1Router(SwitchNoisePolicy(), 4, 32).state_dict())
+    ids = torch.randint(0, 96, (4, 8)); res = {}
+    for name, (tp, dp) in {"a": (1, 2), "b": (2, 2)}.items():
+        f = str(tmp_path / name); spawn(run_hf_moe, world_size=tp * dp, tp=tp, dp=dp, state=state, gate_state=gate_state, ids=ids, out_file=f); res[name] = torch.load(f)
+    assert torch.allclose(res["a"], res["b"], atol=2e-4), res
+    assert res["a"][-1] < res["a"][0]
