@@ -37,6 +37,16 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
         return
     group = parallel_context.get_group(ParallelMode.TENSOR)
     if flat is not None and all(getattr(p, "main_grad", None) is not None for p in ps):
+        for p in ps:
+            if p.grad is not None:
+                # delivered through autograd (e.g. a router's nn.Linear) and not folded yet — without a DataParallel
+                # reducer nobody does that before the optimizer step: fold it now so that the sum covers it
+                if getattr(p, "_mg_fresh", False):
+                    p.main_grad.copy_(p.grad)
+                    p._mg_fresh = False
+                else:
+                    p.main_grad.add_(p.grad)
+                p.grad = None
         fresh = [p.main_grad for p in ps if getattr(p, "_mg_fresh", False)]
         if fresh:
             torch._foreach_zero_(fresh)

@@ -82,6 +82,14 @@ class ExpertLayer(nn.Module):
             if weights is not None:
                 weights = broadcast_to_tensor_group(weights, self.parallel_context)
         out = self._experts(expert_inputs, order, expert_inputs, *rest, weights=weights, combine=not exchange, **kwargs)
+        if expert_inputs is not inputs or exchange:
+            # The communication ops around the local experts have collective BACKWARD passes.  A rank whose experts got
+            # no token this step would otherwise have no autograd path through them and skip those collectives while
+            # its peers wait: tie the output to the exchanged tensors so that every rank runs the same backward graph.
+            anchor = expert_inputs.reshape(-1)[0] * 0.0
+            if isinstance(weights, torch.Tensor) and weights.requires_grad:
+                anchor = anchor + weights.reshape(-1)[0] * 0.0
+            out = out + anchor.to(out.dtype)
         if exchange:
             out = comm.scatter_rows(out.reshape(-1, local_shape[-1])).view(local_shape)
         if residual is not None:

@@ -319,3 +319,42 @@ def test_hf_bloom_moe_with_sharded_experts_trains_like_unsharded(tmp_path):
         f = str(tmp_path / name); spawn(run_hf_moe, world_size=tp * dp, tp=tp, dp=dp, state=state, gate_state=gate_state, ids=ids, out_file=f); res[name] = torch.load(f)
     assert torch.allclose(res["a"], res["b"], atol=2e-4), res
     assert res["a"][-1] < res["a"][0]
+
+
+# ------------------------------------------------------------------ fast-path MoE, tensor parallelism only
+from pipegoose_b200.nn.expert_parallel import Top2Router  # noqa: E402
+
+
+def run_moe_tp_only(rank, world_size, port, tp, stock, top2, state, gate_state, ids, out_file):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    R = Top2Router if top2 else Top1Router
+    router = R(SwitchNoisePolicy(), 4, 32); router.load_state_dict(gate_state)
+    m = ExpertParallel(m, 4, mapping=[0, 1], router=router, parallel_context=ctx).parallelize()
+    for li in (0, 1):
+        layer = m.transformer.h[li].mlp
+        first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+        for i, e in enumerate(layer.experts):
+            g = torch.Generator().manual_seed(500 + 10 * li + first + i)
+            for p in e.parameters():
+                p.data = p.data + 0.05 * torch.randn(p.shape, generator=g)
+    m = TensorParallel(m, ctx).parallelize(); m.eval()
+    opt = DistributedOptimizer(torch.optim.Adam(m.parameters(), lr=1e-2) if stock else FusedAdam(m.parameters(), lr=1e-2), ctx)
+    loss_fn = ExpertLoss(lambda out: out.loss, aux_weight=0.01, z_weight=0.001)
+    losses = []
+    for _ in range(3):
+        loss = loss_fn(m(ids, labels=ids)); opt.zero_grad(); loss.backward(); opt.step(); losses.append(loss.item())
+    if rank == 0: torch.save(torch.tensor(losses), out_file)
+    ctx.destroy()
+@pytest.mark.parametrize("stock,top2", [(False, False), (True, False), (False, True)])
+def test_fast_path_moe_without_data_parallel_is_tp_invariant(tmp_path, stock, top2):
+    """tp = 1, 2, 4 (one expert per rank at tp=4: some ranks' experts get no token in a step — the backward collectives
+    must still line up), no DataParallel reducer (the router's autograd gradients are folded before the tensor-group sum),
+    fused and stock optimizer, Top-1 and Top-2: identical loss trajectories."""
+    torch.manual_seed(0)
+    R = Top2Router if top2 else Top1Router
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict()); gate_state = copy.deepcopy(R(SwitchNoisePolicy(), 4, 32).state_dict())
+    ids = torch.randint(0, 96, (4, 8)); res = {}
+    for tp in (1, 2, 4):
+        f = str(tmp_path / f"t{tp}"); spawn(run_moe_tp_only, world_size=tp, tp=tp, stock=stock, top2=top2, state=state, gate_state=gate_state, ids=ids, out_file=f); res[tp] = torch.load(f)
+    assert torch.allclose(res[1], res[2], atol=2e-4) and torch.allclose(res[1], res[4], atol=2e-4), res
