@@ -38,7 +38,7 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
     group = parallel_context.get_group(ParallelMode.TENSOR)
     if flat is not None and all(getattr(p, "main_grad", None) is not None for p in ps):
         for p in ps:
-            if p.grad is not None:
+            if p.grad is not None and p.grad.data_ptr() != p.main_grad.data_ptr():   # (not a materialised alias)
                 # delivered through autograd (e.g. a router's nn.Linear) and not folded yet — without a DataParallel
                 # reducer nobody does that before the optimizer step: fold it now so that the sum covers it
                 if getattr(p, "_mg_fresh", False):
