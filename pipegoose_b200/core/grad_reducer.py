@@ -205,6 +205,7 @@ class GradReducer:
             b.pending = sum(getattr(p, "_pg_grad_contribs", 1) for p in b.params)
             b.launched = False
             b.work = None
+        self._cursor = len(self.buckets) - 1
         self._contribs_seen: Dict[int, int] = {}
 
     # ------------------------------------------------------------------ gradient arrival
@@ -236,8 +237,25 @@ class GradReducer:
             return
         for b in self._bucket_of[id(p)]:
             b.pending -= 1
-            if b.pending == 0 and not b.launched and not b.deferred:
+        self._launch_ready_in_order()
+
+    def _launch_ready_in_order(self):
+        """Reductions are collectives: every replica must issue them in the SAME order.  Buckets are therefore launched
+        strictly from the last one down (the order in which a backward pass completes them); a bucket that is ready
+        early waits for its predecessors.  A parameter that gets no gradient on THIS replica only (an expert without
+        tokens) stalls the cursor here until ``finalize`` launches the rest — in the same descending order — instead of
+        letting this replica's sequence of collectives differ from its peers'."""
+        i = self._cursor
+        while i >= 0:
+            b = self.buckets[i]
+            if b.deferred or b.launched:
+                i -= 1
+            elif b.pending == 0:
                 self._launch(b)
+                i -= 1
+            else:
+                break
+        self._cursor = i
 
     # ------------------------------------------------------------------ collectives
     def _group_for(self, b: _Bucket):

@@ -358,3 +358,51 @@ def test_fast_path_moe_without_data_parallel_is_tp_invariant(tmp_path, stock, to
     for tp in (1, 2, 4):
         f = str(tmp_path / f"t{tp}"); spawn(run_moe_tp_only, world_size=tp, tp=tp, stock=stock, top2=top2, state=state, gate_state=gate_state, ids=ids, out_file=f); res[tp] = torch.load(f)
     assert torch.allclose(res[1], res[2], atol=2e-4) and torch.allclose(res[1], res[4], atol=2e-4), res
+
+
+# ------------------------------------------------------------------ experts that idle on one replica only
+from pipegoose_b200.nn import ExpertParallel as _EP  # noqa: E402,F401
+
+
+class _RouteByReplica(torch.nn.Module):
+    """Routes every token of DP replica r to expert r: each replica leaves the other experts without gradients."""
+    def __init__(self, e): super().__init__(); self.e = e
+    def forward(self, x): return torch.full((x.reshape(-1, x.shape[-1]).shape[0],), self.e, dtype=torch.long)
+def run_replica_local_experts(rank, world_size, port, fused, state, ids, ref_state):
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 2)
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    m = ExpertParallel(m, 2, mapping=[0, 1], router=_RouteByReplica(rank), parallel_context=ctx).parallelize()
+    m = DataParallel(m, ctx, bucket_size_mb=0.01).parallelize()
+    opt = DistributedOptimizer(FusedAdam(m.parameters(), lr=1e-2) if fused else torch.optim.Adam(m.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(2)[rank]
+    for _ in range(3):
+        loss = m(local, labels=local).loss; opt.zero_grad(); loss.backward(); opt.step()
+    assert len(m._pg_grad_reducer.buckets) > 3
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    other = flat.clone(); torch.distributed.all_reduce(other)
+    assert torch.allclose(other / 2, flat, atol=1e-6), "replicas diverged"
+    for k, v in m.state_dict().items():
+        assert torch.allclose(v, ref_state[k], atol=3e-5), k
+    ctx.destroy()
+@pytest.mark.parametrize("fused", [True, False])
+def test_parameters_unused_on_one_replica_only_keep_the_collective_order(fused):
+    """Every replica routes its tokens to a different expert: each leaves other experts without gradients, so buckets
+    complete in different orders on different replicas — the reducer must still issue its collectives in one order."""
+    torch.manual_seed(0)
+    base = BloomForCausalLM(BloomConfig(**CFG)); state = copy.deepcopy(base.state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    # single-process reference: same MoE model, replica r's half of the batch goes to expert r
+    from pipegoose_b200.testing.utils import find_free_port  # noqa: E402
+    ctx = init_parallel_context(0, 1, find_free_port(), 1, 1, 1)
+    class Split(torch.nn.Module):
+        def forward(self, x):
+            n = x.reshape(-1, x.shape[-1]).shape[0]; return (torch.arange(n) >= n // 2).long()
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    m = ExpertParallel(m, 2, mapping=[0, 1], router=Split(), parallel_context=ctx).parallelize()
+    opt = FusedAdam(m.parameters(), lr=1e-2) if fused else torch.optim.Adam(m.parameters(), lr=1e-2)
+    for _ in range(3):
+        opt.zero_grad()
+        loss = m(ids, labels=ids).loss; loss.backward(); opt.step()
+    ref_state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ctx.destroy()
+    spawn(run_replica_local_experts, world_size=2, fused=fused, state=state, ids=ids, ref_state=ref_state)
