@@ -406,3 +406,54 @@ def test_parameters_unused_on_one_replica_only_keep_the_collective_order(fused):
     ref_state = {k: v.detach().clone() for k, v in m.state_dict().items()}
     ctx.destroy()
     spawn(run_replica_local_experts, world_size=2, fused=fused, state=state, ids=ids, ref_state=ref_state)
+
+
+# ------------------------------------------------------------------ TP x DP MoE with idle experts
+class _ConstRouter(torch.nn.Module):
+    def __init__(self, e): super().__init__(); self.e = e
+    def forward(self, x): return torch.full((x.reshape(-1, x.shape[-1]).shape[0],), self.e, dtype=torch.long)
+class _SplitRouter(torch.nn.Module):
+    def __init__(self, a, b): super().__init__(); self.a, self.b = a, b
+    def forward(self, x):
+        n = x.reshape(-1, x.shape[-1]).shape[0]; return torch.where(torch.arange(n) >= n // 2, self.b, self.a)
+def _distinct_experts(m, ctx):
+    for li in (0, 1):
+        layer = m.transformer.h[li].mlp
+        first = ctx.get_local_rank(ParallelMode.TENSOR) * len(layer.experts)
+        for i, e in enumerate(layer.experts):
+            g = torch.Generator().manual_seed(900 + 10 * li + first + i)
+            for p in e.parameters(): p.data = p.data + 0.05 * torch.randn(p.shape, generator=g)
+def run_idle_experts(rank, world_size, port, experts_of_replica, fused, state, ids, ref_state):
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 2)
+    dp_rank = ctx.get_local_rank(ParallelMode.DATA)
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    names = {id(p): n for n, p in m.named_parameters()}
+    m = ExpertParallel(m, 4, mapping=[0, 1], router=_ConstRouter(experts_of_replica[dp_rank]), parallel_context=ctx).parallelize()
+    _distinct_experts(m, ctx)
+    m = TensorParallel(m, ctx).parallelize(); m = DataParallel(m, ctx, bucket_size_mb=0.01).parallelize()
+    opt = DistributedOptimizer(FusedAdam(m.parameters(), lr=1e-2) if fused else torch.optim.Adam(m.parameters(), lr=1e-2), ctx)
+    local = ids.chunk(2)[dp_rank]
+    for _ in range(3):
+        loss = m(local, labels=local).loss; opt.zero_grad(); loss.backward(); opt.step()
+    for p in m.parameters():
+        n = names.get(id(p))
+        if n is not None and n in ref_state and p.shape == ref_state[n].shape:
+            assert torch.allclose(p.detach(), ref_state[n], atol=3e-5), n
+    ctx.destroy()
+@pytest.mark.parametrize("experts_of_replica,fused", [((0, 1), True), ((0, 3), True), ((2, 1), False)])
+def test_tp_dp_moe_with_experts_that_idle_on_some_ranks(experts_of_replica, fused):
+    """Each replica sends all its tokens to ONE expert: some tensor ranks own no active expert (their backward must still
+    run the exchange collectives) and experts idle on one replica only (bucket order) — against the single-process model."""
+    torch.manual_seed(0)
+    state = copy.deepcopy(BloomForCausalLM(BloomConfig(**CFG)).state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    ctx = init_parallel_context(0, 1, find_free_port(), 1, 1, 1)
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    m = ExpertParallel(m, 4, mapping=[0, 1], router=_SplitRouter(*experts_of_replica), parallel_context=ctx).parallelize()
+    _distinct_experts(m, ctx)
+    opt = FusedAdam(m.parameters(), lr=1e-2) if fused else torch.optim.Adam(m.parameters(), lr=1e-2)
+    for _ in range(3):
+        loss = m(ids, labels=ids).loss; opt.zero_grad(); loss.backward(); opt.step()
+    ref_state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ctx.destroy()
+    spawn(run_idle_experts, world_size=4, experts_of_replica=experts_of_replica, fused=fused, state=state, ids=ids, ref_state=ref_state)
