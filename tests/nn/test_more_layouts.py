@@ -409,6 +409,9 @@ def test_parameters_unused_on_one_replica_only_keep_the_collective_order(fused):
 
 
 # ------------------------------------------------------------------ TP x DP MoE with idle experts
+from pipegoose_b200.testing.utils import find_free_port  # noqa: E402
+
+
 class _ConstRouter(torch.nn.Module):
     def __init__(self, e): super().__init__(); self.e = e
     def forward(self, x): return torch.full((x.reshape(-1, x.shape[-1]).shape[0],), self.e, dtype=torch.long)
