@@ -109,6 +109,10 @@ def clip_grad_norm_(target, max_norm: float, parallel_context, eps: float = 1e-6
     from pipegoose_b200.optim.fused_adam import FusedAdam
     from pipegoose_b200.optim.zero.optim import DistributedOptimizer
 
+    from pipegoose_b200.optim.diloco import DiLoCoOptimizer
+
+    if isinstance(target, DiLoCoOptimizer):   # every worker clips its own (un-averaged) gradient: unwrap the inner optimizer
+        target = target.optim
     fused = None
     if isinstance(target, DistributedOptimizer):
         if target._fused:

@@ -8,7 +8,7 @@ import torch
 from pipegoose_b200.distributed.parallel_mode import ParallelMode
 from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
 from pipegoose_b200.nn import TensorParallel
-from pipegoose_b200.optim import FusedAdam
+from pipegoose_b200.optim import FusedAdam, clip_grad_norm_
 from pipegoose_b200.optim.diloco import DiLoCoOptimizer
 from pipegoose_b200.testing.utils import init_parallel_context, spawn
 
@@ -70,6 +70,8 @@ def run_diloco(rank, world_size, port, tp, fused, state, want):
         loss = model(ids, labels=ids).loss
         optim.zero_grad()
         loss.backward()
+        norm = clip_grad_norm_(optim, 1e9, ctx)     # (unwraps to the worker's inner optimizer; 1e9: never bites)
+        assert torch.isfinite(norm) and norm > 0
         optim.step()
     assert optim.outer_step_count == ROUNDS and optim.local_step == H * ROUNDS
     for p in model.parameters():
