@@ -21,7 +21,7 @@ class Trainer:
                  parallel_context=None, log_every: int = 10, grad_accum_steps: int = 1,
                  max_grad_norm: Optional[float] = None, lr_scheduler=None, checkpoint_dir: Optional[str] = None,
                  checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None,
-                 max_steps: Optional[int] = None, keep_checkpoints: int = 2):
+                 max_steps: Optional[int] = None, keep_checkpoints: int = 2, moe_loss_weights=(0.01, 0.001)):
         """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
         norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
@@ -46,6 +46,7 @@ class Trainer:
         self.checkpoint_every = checkpoint_every
         self.resume = resume
         self.watchdog_timeout_s = watchdog_timeout_s
+        self.moe_loss_weights = moe_loss_weights   # (load-balancing, router-z) weights for MoE models
         self.keep_checkpoints = max(1, keep_checkpoints)   # newest complete step directories kept on disk
         self.max_steps = max_steps   # stop once this many optimizer steps exist in total (counting resumed ones)
         self.state = TrainerState()
@@ -96,6 +97,7 @@ class Trainer:
         with (no_sync() if (no_sync is not None and not last) else nullcontext()):
             out = self.module(**batch, labels=labels, **extra)
             loss = out.loss if hasattr(out, "loss") else out[0]
+            loss = self._add_router_losses(loss)
             if first:
                 self.optim.zero_grad()   # after the forward, as in the reference's README loop
             (loss / self.grad_accum_steps if (self.grad_accum_steps > 1 and not pipelined) else loss).backward()
@@ -114,6 +116,20 @@ class Trainer:
             self.state.step += 1
             if self.checkpoint_dir and self.checkpoint_every and self.state.step % self.checkpoint_every == 0:
                 self.save_checkpoint()
+        return loss
+
+    def _add_router_losses(self, loss: torch.Tensor) -> torch.Tensor:
+        """Mixture-of-experts layers push their load-balancing / router-z losses into the ExpertContext on every forward:
+        add them with ``moe_loss_weights`` and drain the context (a pipelined module has done both inside its stages)."""
+        from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+        store = ExpertContext.get_instance()
+        aux, z = store.pop_all_aux_loss(), store.pop_all_z_loss()
+        w_aux, w_z = self.moe_loss_weights
+        for weight, terms in ((w_aux, aux), (w_z, z)):
+            terms = [t for t in terms if isinstance(t, torch.Tensor)]
+            if weight and terms:
+                loss = loss + weight * torch.stack([t.float().reshape(()) for t in terms]).sum().to(loss.dtype)
         return loss
 
     # ------------------------------------------------------------------ checkpoints

@@ -242,3 +242,24 @@ def run_ckpt_layout(rank, world_size, port, ckp_dir):
 
 def test_trainer_checkpoint_directories_and_latest_marker(tmp_path):
     spawn(run_ckpt_layout, world_size=2, ckp_dir=str(tmp_path / "ckpt"))
+
+
+def test_trainer_adds_and_drains_router_losses():
+    from pipegoose_b200.nn import ExpertParallel
+    from pipegoose_b200.nn.expert_parallel import ExpertContext, SwitchNoisePolicy, Top1Router
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.testing.utils import find_free_port
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(0, 1, find_free_port(), 1, 1, 1)
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=32, n_layer=2, n_head=4))
+    router = Top1Router(SwitchNoisePolicy(), 2, 32)
+    model = ExpertParallel(model, 2, router=router, parallel_context=ctx).parallelize()
+    data = [{"input_ids": torch.randint(0, 64, (2, 8))} for _ in range(4)]
+    gate_before = router.gate.weight.detach().clone()
+    Trainer(model, data, optim=FusedAdam(model.parameters(), lr=1e-2), parallel_context=ctx).fit()
+    store = ExpertContext.get_instance()
+    assert not store.aux_loss and not store.z_loss            # drained every step
+    assert not torch.equal(router.gate.weight.detach(), gate_before)
+    ctx.destroy()
