@@ -259,6 +259,7 @@ class Trainer:
             out = self.module(**batch, labels=labels)
             total += float((out.loss if hasattr(out, "loss") else out[0]).item())
             n += 1
+            self._add_router_losses(torch.zeros(()))   # evaluation reports the task loss; just drain the expert context
         return total / max(n, 1)
 
 
