@@ -38,23 +38,24 @@ def scatter(tensor: torch.Tensor, dim: int, parallel_context: Optional[ParallelC
 
 def reduce(tensor: torch.Tensor, dst: int, op: ReduceOp = ReduceOp.SUM, async_op: bool = False,
            parallel_context: Optional[ParallelContext] = None, parallel_mode: Optional[ParallelMode] = None):
-    """Reduce onto the rank whose *local* rank in the group is ``dst``."""
+    """Reduce onto ``dst`` — a GLOBAL rank that belongs to the group, as in ``torch.distributed`` and in the reference
+    (functional.py:49-69; its tests pass ``get_ranks_in_group(mode)[-1]``)."""
     if parallel_context.get_world_size(parallel_mode) == 1:
         return tensor
     group = parallel_context.get_group(parallel_mode)
-    dst_global = parallel_context.get_global_rank_from_local_rank(dst, parallel_mode)
-    work = dist.reduce(tensor, dst=dst_global, op=op, group=group, async_op=async_op)
+    assert dst in parallel_context.get_ranks_in_group(parallel_mode), f"global rank {dst} is not in this {parallel_mode} group"
+    work = dist.reduce(tensor, dst=dst, op=op, group=group, async_op=async_op)
     return _maybe_async(tensor, work, async_op)
 
 
 def broadcast(tensor: torch.Tensor, src: int, async_op: bool = False,
               parallel_context: Optional[ParallelContext] = None, parallel_mode: Optional[ParallelMode] = None):
-    """Broadcast from the rank whose *local* rank in the group is ``src``."""
+    """Broadcast from ``src`` — a GLOBAL rank that belongs to the group (reference functional.py:72-91)."""
     if parallel_context.get_world_size(parallel_mode) == 1:
         return tensor
     group = parallel_context.get_group(parallel_mode)
-    src_global = parallel_context.get_global_rank_from_local_rank(src, parallel_mode)
-    work = dist.broadcast(tensor, src=src_global, group=group, async_op=async_op)
+    assert src in parallel_context.get_ranks_in_group(parallel_mode), f"global rank {src} is not in this {parallel_mode} group"
+    work = dist.broadcast(tensor, src=src, group=group, async_op=async_op)
     return _maybe_async(tensor, work, async_op)
 
 

@@ -52,12 +52,13 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             self.optim.param_groups = sharded[self.dp_rank]
 
     def _broadcast_updated_params(self):
+        replicas = self.parallel_context.get_ranks_in_group(ParallelMode.DATA)   # local data rank -> global rank
         for owner in range(self.dp):
             params = [p for g in self._local_rank_to_param_groups[owner] for p in g["params"]]
             if not params:
                 continue
             flat = flatten_a_list_tensor([p.data for p in params])
-            broadcast(flat, src=owner, parallel_context=self.parallel_context, parallel_mode=ParallelMode.DATA)
+            broadcast(flat, src=replicas[owner], parallel_context=self.parallel_context, parallel_mode=ParallelMode.DATA)
             if owner != self.dp_rank:
                 copy_flatten_tensor_to_unflatten_tensors(flat, [p.data for p in params])
 

@@ -29,12 +29,12 @@ def run_collectives(rank, world_size, port, tp, pp, dp):
         g = F.all_gather(torch.tensor(float(rank)), parallel_context=ctx, parallel_mode=mode)
         if n > 1:
             assert g.tolist() == [float(r) for r in ranks]
-        # broadcast / reduce address ranks by their local index
+        # broadcast / reduce address ranks by their GLOBAL rank, like torch.distributed and the reference's tests
         b = torch.tensor([float(rank)])
-        F.broadcast(b, src=n - 1, parallel_context=ctx, parallel_mode=mode)
+        F.broadcast(b, src=ranks[-1], parallel_context=ctx, parallel_mode=mode)
         assert b.item() == float(ranks[-1])
         r = torch.tensor([1.0])
-        F.reduce(r, dst=0, parallel_context=ctx, parallel_mode=mode)
+        F.reduce(r, dst=ranks[0], parallel_context=ctx, parallel_mode=mode)
         if lr == 0:
             assert r.item() == float(n)
         # reduce_scatter
