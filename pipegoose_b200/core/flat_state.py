@@ -72,6 +72,7 @@ class FlatModelState:
             p._pg_flat_state = self
             p._mg_fresh = False
             p.grad = None
+        self.begin_grad_window()
 
     @classmethod
     def of(cls, module: nn.Module, **kw) -> "FlatModelState":
@@ -102,6 +103,7 @@ class FlatModelState:
         if getattr(self, "hold_grads", False):
             return  # produced by a pipeline schedule inside forward and not consumed by the optimizer yet
         self.grads_materialized = False
+        self.begin_grad_window()
         if not lazy:
             self.flat_grad.zero_()
             for p in self.params:
@@ -114,6 +116,14 @@ class FlatModelState:
             torch._foreach_zero_(small)  # one multi-tensor launch instead of one fill per bias / LN vector
         for p in self.params:
             p._mg_fresh = p.dim() >= 2
+
+    def begin_grad_window(self):
+        """The gradients of the previous window were consumed (optimizer step) or dropped (``zero_grad``): the next
+        synced backward is the first reduction of a new window.  The gradient reducers use this to keep a second synced
+        backward in ONE window correct (tensor-group SUM of partial gradients is not idempotent) or to refuse it
+        (ZeRO-1 reduce-scatter)."""
+        self.tp_reduced_base = None      # value of flat_grad[:tp_partial_numel] right after its last tensor-group sum
+        self.reduced_in_window = False   # a data-parallel reduction already ran in this window
 
     def finalize_grads(self):
         """Parameters that received no gradient this step (still fresh) must read as zero."""
@@ -131,10 +141,20 @@ class FlatModelState:
         return rank * n, (rank + 1) * n
 
     def materialize_grads(self):
-        """Expose ``main_grad`` as ``.grad`` in the parameter dtype (for stock torch optimizers)."""
-        self.grads_materialized = True   # (``.grad`` aliases main_grad when the dtypes agree, is a copy otherwise)
+        """Hand the (reduced) fp32 main grads to a stock torch optimizer as ``.grad`` in the parameter dtype — always a
+        COPY, added to a ``.grad`` that is already there (DDP semantics: several synced backward passes of one step
+        accumulate) — and start a new gradient window: a bare ``torch.optim`` optimizer never calls
+        :meth:`zero_grad` of this flat state, so the next backward must overwrite the main grads, not add to them."""
+        self.grads_materialized = True
         for p in self.params:
-            p.grad = p.main_grad.to(p.dtype)
+            g = p.main_grad.to(p.dtype, copy=True)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+            p._pg_materialized = p.grad   # (a copy of reduced main grads, not a gradient autograd delivered)
+            p._mg_fresh = True
+        self.begin_grad_window()
 
     def rebind(self):
         """Re-point the parameters after the module was moved (``.to`` creates new storages)."""

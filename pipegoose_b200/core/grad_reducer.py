@@ -38,7 +38,8 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
     group = parallel_context.get_group(ParallelMode.TENSOR)
     if flat is not None and all(getattr(p, "main_grad", None) is not None for p in ps):
         for p in ps:
-            if p.grad is not None and p.grad.data_ptr() != p.main_grad.data_ptr():   # (not a materialised alias)
+            if (p.grad is not None and p.grad.data_ptr() != p.main_grad.data_ptr()
+                    and p.grad is not getattr(p, "_pg_materialized", None)):   # (not what materialize_grads exposed)
                 # delivered through autograd (e.g. a router's nn.Linear) and not folded yet — without a DataParallel
                 # reducer nobody does that before the optimizer step: fold it now so that the sum covers it
                 if getattr(p, "_mg_fresh", False):
@@ -54,7 +55,18 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
             p._mg_fresh = False
         n = getattr(flat, "tp_partial_numel", 0)
         if all(sum(flat.param_range(p)) <= n for p in ps):
-            dist.all_reduce(flat.flat_grad[:n], group=group)
+            head = flat.flat_grad[:n]
+            # A SUM is not idempotent: a second synced backward in the same gradient window (no zero_grad / optimizer
+            # step in between) must only sum its OWN contribution — what the head held after the previous sum is
+            # already complete on every rank.
+            base = getattr(flat, "tp_reduced_base", None)
+            if base is not None and base.numel() == n:
+                head.sub_(base)
+                dist.all_reduce(head, group=group)
+                head.add_(base)
+            else:
+                dist.all_reduce(head, group=group)
+            flat.tp_reduced_base = head.clone()
             return
     grads = []
     for p in ps:
@@ -296,6 +308,15 @@ class GradReducer:
         if self._fused is not None:
             self._fused.end_overlap()
         if self._sync and self.dp > 1:
+            if self.mode == "reduce_scatter":
+                # after a reduce-scatter only slice ``dp_rank`` of a bucket holds reduced values: a second reduction
+                # of the same window would average them again.  Accumulate with ``no_sync()`` instead.
+                if getattr(self.flat, "reduced_in_window", False):
+                    raise RuntimeError(
+                        "a second synced backward() reached the ZeRO-1 gradient reduce-scatter before optimizer.step() / "
+                        "zero_grad(): wrap every backward of a gradient-accumulation step except the last one in "
+                        "`with module.no_sync():`")
+            self.flat.reduced_in_window = True
             for b in reversed(self.buckets):
                 if not b.launched:
                     self._launch(b, tail=True)

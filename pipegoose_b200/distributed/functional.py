@@ -86,9 +86,34 @@ def all_gather(tensor: torch.Tensor, dim: int = 0, async_op: bool = False,
         return out.reshape(shape)
 
     if async_op:
-        # the caller must ``work.wait()`` before touching the result
-        return finish(), work
+        if d == 0:
+            return finish(), work   # a view of the gather buffer: valid once ``work.wait()`` returned
+        # the permute to ``dim`` COPIES the gather buffer, so it may only run after the collective completed: the
+        # result is gathered along dim 0 into ``out`` now and put in place by ``wait()``
+        shape = list(src.shape)
+        shape[d] *= world_size
+        out = torch.empty(shape, dtype=src.dtype, device=src.device)
+        return out, _DeferredWork(work, lambda: out.copy_(finish()))
     return finish()
+
+
+class _DeferredWork:
+    """``Work``-like handle whose ``wait()`` first waits for the collective and then runs a post-processing step."""
+
+    def __init__(self, work, after=None):
+        self._work, self._after = work, after
+
+    def wait(self, *args, **kwargs):
+        if self._work is not None:
+            self._work.wait(*args, **kwargs)
+            self._work = None
+        if self._after is not None:
+            after, self._after = self._after, None
+            after()
+        return True
+
+    def is_completed(self):
+        return self._work is None or self._work.is_completed()
 
 
 def all_reduce(tensor: torch.Tensor, op: ReduceOp = ReduceOp.SUM, async_op: bool = False,
@@ -112,11 +137,13 @@ def reduce_scatter(tensor: torch.Tensor, dim: int = 0, op: ReduceOp = ReduceOp.S
     src = tensor.movedim(d, 0).contiguous() if d != 0 else tensor.contiguous()
     out = torch.empty((src.shape[0] // world_size,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     if dist.get_backend(group) == "gloo":
-        # gloo has no reduce_scatter: all-reduce then slice
-        work = dist.all_reduce(src, op=op, group=group)
+        # gloo has no reduce_scatter: all-reduce a COPY (the caller's tensor is an input, not scratch) then slice
+        if src.data_ptr() == tensor.data_ptr():
+            src = src.clone()
+        dist.all_reduce(src, op=op, group=group)
         rank = parallel_context.get_local_rank(parallel_mode)
         out.copy_(src.narrow(0, rank * out.shape[0], out.shape[0]))
-        work = None
+        work = _DeferredWork(None) if async_op else None   # already complete
     else:
         work = dist.reduce_scatter_tensor(out, src, op=op, group=group, async_op=async_op)
     result = out.movedim(0, d) if d != 0 else out

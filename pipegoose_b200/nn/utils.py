@@ -29,19 +29,30 @@ def _atomic_save(obj, path: str):
 
 
 def from_pretrained(module: nn.Module, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
-                    ckp_name: str = CHECKPOINT_WEIGHTS_NAME):
-    """Load this rank's (tp, pp) shard into an already parallelized ``module``."""
+                    ckp_name: str = CHECKPOINT_WEIGHTS_NAME, strict: bool = True):
+    """Load this rank's (tp, pp) shard into an already parallelized ``module``.  ``strict`` (default, as the
+    reference's ``load_state_dict``): every parameter and buffer of the module must be in the checkpoint."""
     path = _ckpt_file(ckp_path, ckp_name, parallel_context)
     if not os.path.exists(path):
         raise ValueError(f"ckp_path {path} does not exist")
     state_dict = torch.load(path, map_location="cpu")
     with torch.no_grad():
         own = module.state_dict()
+        # strict, like the reference's ``module.load_state_dict``: a stale or partial shard (another model config,
+        # parallel layout or MoE mapping) must not resume silently with randomly initialised leftovers
+        unexpected = [k for k in state_dict if k not in own]
+        if unexpected:
+            raise KeyError(f"unexpected key(s) {unexpected[:5]} in checkpoint {path}")
+        missing = [k for k in own if k not in state_dict]
+        if missing and strict:
+            raise KeyError(f"checkpoint {path} lacks {len(missing)} parameter(s) / buffer(s) of this module, e.g. "
+                           f"{missing[:5]}")
         for k, v in state_dict.items():
-            if k in own:
-                own[k].copy_(v)
-            else:
-                raise KeyError(f"unexpected key {k} in checkpoint {path}")
+            if tuple(own[k].shape) != tuple(v.shape):
+                raise ValueError(f"shape mismatch for {k} in {path}: checkpoint {tuple(v.shape)}, module "
+                                 f"{tuple(own[k].shape)} (different model config or parallel layout?)")
+        for k, v in state_dict.items():
+            own[k].copy_(v)
     return module
 
 
@@ -92,15 +103,44 @@ def save_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
         return x
 
     blob = {"optimizer": to_cpu(sd), "step": int(step), "layout": _layout(parallel_context),
-            "rng": {"torch": torch.get_rng_state(),
-                    "cuda": torch.cuda.get_rng_state() if torch.cuda.is_available() else None},
-            "extra": extra or {}}
+            "rng": capture_rng_state(), "extra": extra or {}}
     _atomic_save(blob, _optim_file(ckp_path, parallel_context))
+
+
+def capture_rng_state() -> dict:
+    """Every generator a training loop may draw from: torch CPU + CUDA, Python ``random``, numpy."""
+    import random
+
+    state = {"torch": torch.get_rng_state(),
+             "cuda": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+             "python": random.getstate()}
+    try:
+        import numpy as np
+
+        state["numpy"] = np.random.get_state()
+    except Exception:  # pragma: no cover - numpy missing
+        state["numpy"] = None
+    return state
+
+
+def restore_rng_state(state: dict):
+    import random
+
+    torch.set_rng_state(state["torch"])
+    if state.get("cuda") is not None and torch.cuda.is_available():
+        torch.cuda.set_rng_state(state["cuda"])
+    if state.get("python") is not None:
+        random.setstate(state["python"])
+    if state.get("numpy") is not None:
+        import numpy as np
+
+        np.random.set_state(state["numpy"])
 
 
 def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_context: ParallelContext = None,
                         restore_rng: bool = True) -> dict:
-    """Restore what :func:`save_training_state` wrote; returns ``{"step": ..., "extra": ...}``."""
+    """Restore what :func:`save_training_state` wrote; returns ``{"step": ..., "extra": ...}`` (plus ``"rng"``, the saved
+    generator states, when ``restore_rng=False`` leaves restoring them to the caller)."""
     path = _optim_file(ckp_path, parallel_context)
     if not os.path.exists(path):
         raise ValueError(f"optimizer checkpoint {path} does not exist")
@@ -109,8 +149,9 @@ def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
         raise ValueError(f"checkpoint was written for layout {blob['layout']}, this job runs {_layout(parallel_context)}: "
                          "optimizer shards are tied to the parallel layout")
     optim.load_state_dict(blob["optimizer"])
+    meta = {"step": blob["step"], "extra": blob["extra"]}
     if restore_rng:
-        torch.set_rng_state(blob["rng"]["torch"])
-        if blob["rng"]["cuda"] is not None and torch.cuda.is_available():
-            torch.cuda.set_rng_state(blob["rng"]["cuda"])
-    return {"step": blob["step"], "extra": blob["extra"]}
+        restore_rng_state(blob["rng"])
+    else:
+        meta["rng"] = blob["rng"]   # the caller restores it (the Trainer: after it replayed the consumed batches)
+    return meta

@@ -97,6 +97,7 @@ class FusedAdam(torch.optim.Optimizer):
                 master.addcdiv_(m / bc1, (v / bc2).sqrt() + eps, value=-lr)
                 param.copy_(master.to(param.dtype))
         self.flat.hold_grads = False
+        self.flat.begin_grad_window()   # the gradients were consumed
         FusedAdam.steps_taken += 1
         return loss
 

@@ -178,6 +178,8 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             return
         flat = next((p._pg_flat_state for p in self._all_params if getattr(p, "_pg_flat_state", None) is not None), None)
         held = bool(getattr(flat, "hold_grads", False))
+        if flat is not None and not held:
+            flat.begin_grad_window()
         for p in self._all_params:
             p.grad = None
             if hasattr(p, "main_grad") and not held:

@@ -52,6 +52,9 @@ class Trainer:
         self.state = TrainerState()
         self._micro = 0
         self._skip_batches = 0
+        self._resume = None               # set by load_checkpoint(): where in which epoch to continue, and the RNG states
+        self._batches_in_epoch = 0
+        self._epoch_start_rng = None      # torch CPU generator state when the current epoch's loader iterator was made
 
     def _device(self):
         return next(self.module.parameters()).device
@@ -152,7 +155,10 @@ class Trainer:
         name = f"step_{self.state.step:08d}"
         path = os.path.join(self.checkpoint_dir, name)
         save_pretrained(self.module, ckp_path=path, parallel_context=ctx)
+        # exact resume: the epoch's sampler permutation is drawn from the global torch RNG when the loader's iterator is
+        # created, so the state the generator had THEN is what lets a resumed run re-create the same order
         extra = {"epoch": self.state.epoch, "tokens_seen": self.state.tokens_seen,
+                 "batches_in_epoch": self._batches_in_epoch, "epoch_start_rng": self._epoch_start_rng,
                  "lr_scheduler": self.lr_scheduler.state_dict() if hasattr(self.lr_scheduler, "state_dict") else None}
         save_training_state(self.optim, path, ctx, step=self.state.step, extra=extra)
         self._barrier()                       # every rank's shard is on disk ...
@@ -188,13 +194,20 @@ class Trainer:
         if path is None:
             return False
         from_pretrained(self.module, ckp_path=path, parallel_context=ctx)
-        meta = load_training_state(self.optim, path, ctx)
+        # RNG states are restored by train() AFTER the consumed batches were replayed (replaying draws from the
+        # generators: the sampler permutation, the DataLoader's base seed)
+        meta = load_training_state(self.optim, path, ctx, restore_rng=False)
         self.state.step = meta["step"]
         extra = meta.get("extra") or {}
         self.state.tokens_seen = extra.get("tokens_seen", 0)
         if self.lr_scheduler is not None and extra.get("lr_scheduler") is not None:
             self.lr_scheduler.load_state_dict(extra["lr_scheduler"])
-        self._skip_batches = self.state.step * self.grad_accum_steps
+        if extra.get("epoch_start_rng") is not None:
+            self._resume = {"epoch": int(extra.get("epoch", 0)), "batches": int(extra.get("batches_in_epoch", 0)),
+                            "epoch_start_rng": extra["epoch_start_rng"], "rng": meta.get("rng")}
+        else:   # checkpoint of an older version: positional replay from the first epoch
+            self._skip_batches = self.state.step * self.grad_accum_steps
+            self._resume = {"epoch": 0, "batches": None, "epoch_start_rng": None, "rng": meta.get("rng")}
         self._log(f"resumed from step {self.state.step} ({path})")
         return True
 
@@ -222,14 +235,31 @@ class Trainer:
         self.module.train()
         t0, tok0 = time.time(), self.state.tokens_seen
         seen = 0
-        for epoch in range(self.num_epochs):
+        resume, self._resume = self._resume, None
+        first_epoch = resume["epoch"] if resume is not None else 0
+        for epoch in range(first_epoch, self.num_epochs):
             self.state.epoch = epoch
             self._call("on_epoch_start")
+            skip_here = 0
+            if resume is not None and epoch == first_epoch:
+                if resume["epoch_start_rng"] is not None:
+                    torch.set_rng_state(resume["epoch_start_rng"])   # same sampler permutation as the interrupted run
+                    skip_here = resume["batches"]
+                if not skip_here and not self._skip_batches:
+                    self._restore_rng(resume)
+                    resume = None
+            self._epoch_start_rng = torch.get_rng_state()
+            self._batches_in_epoch = 0
             for batch in self.train_loader:
                 if self.max_steps is not None and self.state.step >= self.max_steps and self._micro == 0:
                     break
                 seen += 1
-                if seen <= self._skip_batches:   # consumed before the checkpoint this run resumed from
+                self._batches_in_epoch += 1
+                if self._batches_in_epoch <= skip_here or seen <= self._skip_batches:
+                    # consumed before the checkpoint this run resumed from
+                    if resume is not None and (self._batches_in_epoch == skip_here or seen == self._skip_batches):
+                        self._restore_rng(resume)   # from here on the run continues exactly where it was cut
+                        resume = None
                     continue
                 before = self.state.step
                 loss = self.train_step(batch)
@@ -246,21 +276,35 @@ class Trainer:
                     self._call("on_step_end", loss)
             self._call("on_epoch_end")
 
+    @staticmethod
+    def _restore_rng(resume):
+        from pipegoose_b200.nn.utils import restore_rng_state
+
+        if resume.get("rng") is not None:
+            restore_rng_state(resume["rng"])
+
     @torch.no_grad()
     def evaluate(self) -> float:
         assert self.eval_loader is not None
+        # evaluate() may run in the middle of fit (from an on_step_end / on_epoch_end callback): the rest of training
+        # must continue in the mode and stage it was in (dropout, router noise, training capacity factor)
+        was_training, prev_stage = self.module.training, self.state.stage
         self.state.stage = TrainerStage.VALIDATING
         self.module.eval()
-        dev = self._device()
-        total, n = 0.0, 0
-        for batch in self.eval_loader:
-            batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
-            labels = batch.pop("labels", batch["input_ids"])
-            out = self.module(**batch, labels=labels)
-            total += float((out.loss if hasattr(out, "loss") else out[0]).item())
-            n += 1
-            self._add_router_losses(torch.zeros(()))   # evaluation reports the task loss; just drain the expert context
-        return total / max(n, 1)
+        try:
+            dev = self._device()
+            total, n = 0.0, 0
+            for batch in self.eval_loader:
+                batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+                labels = batch.pop("labels", batch["input_ids"])
+                out = self.module(**batch, labels=labels)
+                total += float((out.loss if hasattr(out, "loss") else out[0]).item())
+                n += 1
+                self._add_router_losses(torch.zeros(()))   # evaluation reports the task loss; just drain the expert context
+            return total / max(n, 1)
+        finally:
+            self.module.train(was_training)
+            self.state.stage = prev_stage
 
 
 class _SingleProcess:
