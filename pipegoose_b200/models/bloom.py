@@ -399,3 +399,68 @@ class BloomForCausalLM(nn.Module):
         model = cls(BloomConfig.from_hf(hf_model.config))
         model.load_state_dict(hf_model.state_dict(), strict=False)
         return model
+
+
+def is_hf_bloom(module: nn.Module) -> bool:
+    """A 🤗 transformers ``BloomForCausalLM`` (the model the reference's README wraps)?"""
+    cls = type(module)
+    return cls.__name__ == "BloomForCausalLM" and cls.__module__.startswith("transformers.")
+
+
+def hf_bloom_fast_path_blocker(hf_model) -> Optional[str]:
+    """Why this 🤗 Bloom cannot run on the fused path (None: it can)."""
+    c = hf_model.config
+    if getattr(c, "hidden_dropout", 0.0) != 0.0 or getattr(c, "attention_dropout", 0.0) != 0.0:
+        return "non-zero dropout"
+    if getattr(c, "apply_residual_connection_post_layernorm", False):
+        return "apply_residual_connection_post_layernorm"
+    if hf_model.lm_head.weight is not hf_model.transformer.word_embeddings.weight:
+        return "untied lm_head"
+    if c.hidden_size % c.n_head != 0:
+        return "hidden_size not divisible by n_head"
+    return None
+
+
+def convert_hf_bloom_(hf_model) -> "BloomForCausalLM":
+    """Turn a 🤗 ``BloomForCausalLM`` into this module's ``BloomForCausalLM`` IN PLACE: the same Python objects, the
+    same ``nn.Parameter``s under the same names (optimizers, state dicts and checkpoints written from either side keep
+    working) — only the container classes change, so that ``forward`` runs the fused sub-layer kernels (flash ALiBi
+    attention, GEMMs with fused epilogues, fused lm_head + cross entropy) and ``TensorParallel`` can take the
+    sequence-parallel path with the fused all-gather->GEMM / GEMM->reduce-scatter kernels.
+
+    This is what ``TensorParallel(hf_bloom, ctx).parallelize()`` does for the reference's canonical input
+    (reference README.md:21-69, examples/hybrid_parallelism.py:22-37)."""
+    why = hf_bloom_fast_path_blocker(hf_model)
+    if why is not None:
+        raise ValueError(f"this Bloom cannot use the fused path: {why}")
+    cfg = BloomConfig.from_hf(hf_model.config)
+    cfg.tie_word_embeddings = True
+    hf_config = hf_model.config
+    t = hf_model.transformer
+    def is_hf(mod, name):
+        return type(mod).__name__ == name and type(mod).__module__.startswith("transformers.")
+
+    for block in t.h:
+        attn = block.self_attention
+        attn._modules.pop("attention_dropout", None)
+        attn.__class__ = BloomAttention
+        attn.hidden_size, attn.num_heads, attn.head_dim = cfg.hidden_size, cfg.n_head, cfg.hidden_size // cfg.n_head
+        attn.use_alibi = True
+        attn._slopes_cache = {}
+        # the block's MLP, or — when ExpertParallel already replaced it by an ExpertLayer — the experts inside it
+        # (the ``mlp(layernorm_output, residual)`` contract is the same for both classes)
+        for mlp in [m for m in block.modules() if is_hf(m, "BloomMLP")]:
+            mlp._modules.pop("gelu_impl", None)
+            mlp.__class__ = BloomMLP
+        block.__class__ = BloomBlock
+        block.eps = cfg.layer_norm_epsilon
+        block.tp = None
+    t.__class__ = BloomModel
+    t.config = cfg
+    hf_model.__class__ = BloomForCausalLM
+    hf_model.config = cfg
+    hf_model.hf_config = hf_config          # what the user built the model from (save / export helpers can read it)
+    hf_model.tp = None
+    hf_model.vocab_start = 0
+    hf_model.lm_head.weight._pg_grad_contribs = 2   # tied table: lm_head wgrad + embedding backward
+    return hf_model

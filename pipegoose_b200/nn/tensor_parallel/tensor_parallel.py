@@ -35,12 +35,34 @@ class TensorParallel(Parallel):
     PARALLELIZERS = [EmbeddingParallelizer, LinearParallelizer, LayerNormParallelizer, LMHeadParallelizer]
 
     def __init__(self, module: nn.Module, parallel_context: ParallelContext, sequence_parallel: Optional[bool] = None):
+        """``sequence_parallel``: ``True`` forces the sequence-parallel fast path (a 🤗 ``BloomForCausalLM`` is
+        converted in place to ``pipegoose_b200.models.bloom.BloomForCausalLM`` first), ``False`` forces the
+        reference-style class swap, ``None`` (default) picks the fast path for ``pipegoose_b200.models`` models and for
+        🤗 Bloom models that are set up for the kernels (bf16 parameters, dropout 0) — the reference's canonical
+        input then trains on the fused kernels without any change to the user's script."""
         super().__init__(module, parallel_context)
         self.sequence_parallel = sequence_parallel
+
+    def _maybe_convert_hf(self, module: nn.Module) -> nn.Module:
+        import os
+
+        from pipegoose_b200.models.bloom import convert_hf_bloom_, hf_bloom_fast_path_blocker, is_hf_bloom
+
+        if not is_hf_bloom(module) or self.sequence_parallel is False:
+            return module
+        blocker = hf_bloom_fast_path_blocker(module)
+        if self.sequence_parallel is True:
+            return convert_hf_bloom_(module)   # raises with the reason when it cannot
+        env = os.environ.get("PIPEGOOSE_B200_HF_FAST_PATH", "auto")
+        bf16 = next(module.parameters()).dtype == torch.bfloat16
+        if blocker is None and env != "0" and (bf16 or env == "1"):
+            return convert_hf_bloom_(module)
+        return module
 
     @torch.no_grad()
     def parallelize(self) -> nn.Module:
         module, ctx = self.module, self.parallel_context
+        module = self.module = self._maybe_convert_hf(module)   # in place: the same object, now on the fused path
         if ctx.tensor_parallel_size > 1:
             from pipegoose_b200.models.bloom import BloomForCausalLM as FastBloom
 

@@ -1,0 +1,121 @@
+"""🤗 Bloom -> fused path: ``TensorParallel(hf_bloom, ctx).parallelize()`` converts the model IN PLACE to the
+pipegoose_b200 Bloom (same parameters, same names) and then takes the sequence-parallel path; losses, gradients,
+one optimizer step and ``generate`` agree with the untouched 🤗 model."""
+import copy
+
+import pytest
+import torch
+
+from pipegoose_b200.distributed.parallel_mode import ParallelMode
+from pipegoose_b200.models.bloom import BloomForCausalLM as FastBloom
+from pipegoose_b200.models.bloom import convert_hf_bloom_, is_hf_bloom
+from pipegoose_b200.nn import DataParallel, TensorParallel
+from pipegoose_b200.optim import DistributedOptimizer
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+def _hf_bloom(**kw):
+    from transformers import BloomConfig, BloomForCausalLM
+
+    return BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4, **kw))
+
+
+def test_in_place_conversion_keeps_parameters_and_matches_hf():
+    torch.manual_seed(0)
+    hf = _hf_bloom()
+    ref = copy.deepcopy(hf)
+    names = [n for n, _ in hf.named_parameters()]
+    params = {n: p for n, p in hf.named_parameters()}
+    assert is_hf_bloom(hf)
+    fast = convert_hf_bloom_(hf)
+    assert fast is hf and isinstance(hf, FastBloom) and not is_hf_bloom(hf)
+    assert [n for n, _ in hf.named_parameters()] == names
+    assert all(p is params[n] for n, p in hf.named_parameters())          # the very same Parameter objects
+    assert set(hf.state_dict()) == set(ref.state_dict())
+    ids = torch.randint(0, 96, (3, 10))
+    out = hf(input_ids=ids, attention_mask=torch.ones_like(ids), labels=ids)
+    want = ref(input_ids=ids, attention_mask=torch.ones_like(ids), labels=ids)
+    assert torch.allclose(out.loss, want.loss, atol=1e-5)
+    out.loss.backward()
+    want.loss.backward()
+    for (n, p), (_, q) in zip(hf.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p.grad, q.grad, atol=1e-5), n
+    assert torch.allclose(hf(input_ids=ids).logits, ref(input_ids=ids).logits, atol=1e-4)
+    assert torch.equal(hf.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=3),
+                       ref.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=3, do_sample=False))
+
+
+def test_models_the_fused_path_cannot_run_keep_the_class_swap_path():
+    hf = _hf_bloom(hidden_dropout=0.1)
+    with pytest.raises(ValueError, match="dropout"):
+        convert_hf_bloom_(hf)
+
+
+def _partition_of(name, full, tp, r):
+    if "query_key_value" in name or "dense_h_to_4h" in name:
+        return full.chunk(tp, 0)[r]
+    if name.endswith("self_attention.dense.weight") or name.endswith("dense_4h_to_h.weight"):
+        return full.chunk(tp, 1)[r]
+    if "word_embeddings.weight" in name or name == "lm_head.weight":
+        return full.chunk(tp, 0)[r]
+    return full
+
+
+def run_hf_fast(rank, world_size, port, tp, dp, state, ids, ref_loss, ref_params, ref_tokens):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    same = model
+    model = TensorParallel(model, ctx, sequence_parallel=True).parallelize()   # what bf16 🤗 models get by default
+    assert model is same and isinstance(model, FastBloom) and (model.tp is not None) == (tp > 1)
+    gen_in = ids[:2, :6]
+    assert torch.equal(model.generate(input_ids=gen_in, max_new_tokens=2), ref_tokens)
+    model = DataParallel(model, ctx).parallelize()
+    optim = DistributedOptimizer(torch.optim.Adam(model.parameters(), lr=1e-3), ctx)
+    local = ids.chunk(dp)[ctx.get_local_rank(ParallelMode.DATA)]
+    out = model(input_ids=local, attention_mask=torch.ones_like(local), labels=local)
+    optim.zero_grad()
+    out.loss.backward()
+    optim.step()
+    import torch.distributed as dist
+
+    t = out.loss.detach().clone()
+    dist.all_reduce(t, group=ctx.get_group(ParallelMode.DATA))
+    assert torch.allclose(t / dp, ref_loss, atol=1e-5)
+    r = ctx.get_local_rank(ParallelMode.TENSOR)
+    for name, p in model.named_parameters():
+        want = _partition_of(name, ref_params[name], tp, r)
+        assert p.shape == want.shape, name
+        assert torch.allclose(p.detach(), want, atol=2e-5), name
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,dp", [(1, 1), (2, 1), (2, 2)])
+def test_hf_bloom_takes_the_sequence_parallel_path(tp, dp):
+    torch.manual_seed(0)
+    model = _hf_bloom()
+    state = copy.deepcopy(model.state_dict())
+    ids = torch.randint(0, 96, (4, 8))
+    tokens = model.generate(input_ids=ids[:2, :6], attention_mask=torch.ones(2, 6, dtype=torch.long), max_new_tokens=2,
+                            do_sample=False)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loss = model(input_ids=ids, attention_mask=torch.ones_like(ids), labels=ids).loss
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    ref_params = {n: p.detach().clone() for n, p in model.named_parameters()}
+    ref_params["lm_head.weight"] = ref_params["transformer.word_embeddings.weight"]
+    spawn(run_hf_fast, world_size=tp * dp, tp=tp, dp=dp, state=state, ids=ids, ref_loss=loss.detach(),
+          ref_params=ref_params, ref_tokens=tokens)
+
+
+def test_default_picks_the_fast_path_for_bf16_hf_models_only():
+    class Ctx:   # tp == 1: parallelize() only decides about the conversion
+        tensor_parallel_size = 1
+
+    fp32 = _hf_bloom()
+    assert is_hf_bloom(TensorParallel(fp32, Ctx()).parallelize())               # reference-style handling
+    bf16 = _hf_bloom().to(torch.bfloat16)
+    assert isinstance(TensorParallel(bf16, Ctx()).parallelize(), FastBloom)     # ready for the kernels
+    off = _hf_bloom().to(torch.bfloat16)
+    assert is_hf_bloom(TensorParallel(off, Ctx(), sequence_parallel=False).parallelize())
