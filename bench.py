@@ -107,19 +107,62 @@ def parallel_layout(n_gpus: int):
     return 2, n_gpus // 2
 
 
+def layout_of(args):
+    """``(tp, pp, dp)`` of a run — the same for both arms.  Default: BASELINE.json's headline layout (N=1: tp1, N>=2:
+    tp2 x dp N/2); ``--tp / --pp`` select the other BASELINE configs."""
+    tp, dp = parallel_layout(args.gpus)
+    pp = max(args.pp, 1)
+    if args.tp > 0 or pp > 1:
+        tp = args.tp if args.tp > 0 else 1
+        assert args.gpus % (tp * pp) == 0, "--gpus must be a multiple of tp * pp"
+        dp = args.gpus // (tp * pp)
+    return tp, pp, dp
+
+
+def config_of(args, tp, pp, dp):
+    """The benchmark configuration, spelled identically by both arms (the driver compares these dicts)."""
+    return {
+        "model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": args.seq_len,
+        "parallelism": f"tp{tp}" + (f"pp{pp}(1f1b,{args.microbatches}mb)" if pp > 1 else "") + f"dp{dp}"
+        + ("+zero1" if dp > 1 else "") + (f"+moe{args.experts}e" if args.experts > 0 else ""),
+        "optimizer": "Adam", "batch_per_gpu": args.batch_per_gpu,
+        "l2": "no explicit flush: per-step working set (weights + activations, several GB) >> 126 MB L2",
+    }
+
+
+class _HostTimer:
+    """CPU dry runs (``--device cpu``: both arms on tiny shapes, to test this script without a GPU)."""
+
+    def __init__(self):
+        self.t = None
+
+    def record(self):
+        import time
+
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
 def timed_region(torch, dist, steps, fn):
     """barrier + sync, K steps between two CUDA events, sync + barrier; returns max-over-ranks ms."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    else:
+        start, end = _HostTimer(), _HostTimer()
     start.record()
     for i in range(steps):
         fn(i)
     end.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([start.elapsed_time(end)], device="cuda")
+    if cuda:
+        torch.cuda.synchronize()
+    ms = torch.tensor([start.elapsed_time(end)], device="cuda" if cuda else "cpu")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.barrier()
@@ -129,73 +172,167 @@ def timed_region(torch, dist, steps, fn):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+MODEL_SIZES = {"bloom-tiny": (128, 4, 8, 1024), "bloom-560m": (1024, 24, 16, 250880), "bloom-1b7": (2048, 24, 16, 250880),
+               "bloom-3b": (2560, 30, 32, 250880), "bloom-7b1": (4096, 30, 32, 250880)}   # hidden, layers, heads, vocab
+
+
+def _build_ours(args, ctx, torch, n_layer=None, vocab=None, hf=False, fused=True):
+    """Model -> ExpertParallel -> TensorParallel -> PipelineParallel -> DataParallel -> ZeRO-1(FusedAdam): the public API a
+    user of the reference calls, on this repo's kernels.  ``fused=False``: the same stack with the hand-written
+    compute+collective kernels switched off (NCCL collectives around plain kernels) — the numerics self-check's yardstick."""
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import DataParallel, TensorParallel
+    from pipegoose_b200.optim import DistributedOptimizer
+    from pipegoose_b200.optim.fused_adam import FusedAdam
+
+    switches = {"PIPEGOOSE_B200_FUSED_TP": "1" if fused else "0", "PIPEGOOSE_B200_FUSED_DP": "1" if fused else "0",
+                "PIPEGOOSE_B200_FUSED_MOE": "1" if fused else "0"}
+    saved = {k: os.environ.get(k) for k in switches}
+    if not fused:
+        os.environ.update(switches)
+    try:
+        pp = ctx.pipeline_parallel_size
+        dtype = torch.bfloat16 if args.device == "cuda" else torch.float32
+        if args.model.startswith("gpt2"):  # not a BASELINE.json config: the second model family on the same kernels
+            from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+            cfg = getattr(GPT2Config, args.model.replace("-", "_"))()
+            model = GPT2LMHeadModel(cfg).to(dtype)
+        elif hf:
+            # the reference's canonical input: a transformers BloomForCausalLM; TensorParallel converts it in place
+            from transformers import BloomConfig as HFConfig
+            from transformers import BloomForCausalLM as HFBloom
+
+            h, L, nh, V = MODEL_SIZES[args.model]
+            model = HFBloom(HFConfig(hidden_size=h, n_layer=n_layer or L, n_head=nh, vocab_size=vocab or V)).to(dtype)
+            cfg = model.config
+        else:
+            cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
+            if n_layer is not None:
+                cfg.n_layer = n_layer
+            if vocab is not None:
+                cfg.vocab_size = vocab
+            model = BloomForCausalLM(cfg).to(dtype)
+        if args.experts > 0:
+            from pipegoose_b200.nn import ExpertParallel
+            from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
+
+            router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
+            layers = list(range(0, cfg.n_layer, max(args.moe_every, 1)))
+            model = ExpertParallel(model, args.experts, mapping=layers, router=router.to(dtype),
+                                   parallel_context=ctx).parallelize()
+        model = TensorParallel(model, ctx, sequence_parallel=True if hf else None).parallelize()
+        if pp > 1:
+            from pipegoose_b200.nn import PipelineParallel
+
+            model = PipelineParallel(model, num_microbatches=args.microbatches, parallel_context=ctx).parallelize()
+        model = DataParallel(model, ctx).parallelize()
+        model.to(args.device)
+        optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=args.lr), ctx)
+        return model, optim, cfg
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _total_loss(model, ids, experts):
+    loss = model(ids, labels=ids).loss
+    if experts > 0:
+        # Switch training objective: task loss + load-balancing and router-z terms the MoE layers pushed
+        from pipegoose_b200.nn.expert_parallel import ExpertContext
+
+        store = ExpertContext.get_instance()
+        loss = loss + 0.01 * sum(store.pop_all_aux_loss()) + 0.001 * sum(store.pop_all_z_loss())
+    return loss
+
+
+def numerics_self_check(args, ctx, torch, dist):
+    """Multi-GPU correctness that travels with every N>1 bench line (outside the timed regions): 3 optimizer steps of a
+    2-layer model of the benchmark's width through the fused engines (AG->GEMM / GEMM->RS, in-kernel gradient
+    reduce-scatter, ZeRO-1 all-gather, fused MoE) and through the same stack with them switched off (NCCL collectives
+    around plain kernels), same init, same data.  Reports the largest relative loss difference and the relative
+    difference of the parameter checksums after the last step."""
+    from pipegoose_b200.distributed import ParallelMode
+
+    S = min(args.seq_len, 1024)
+    tp, pp = ctx.tensor_parallel_size, ctx.pipeline_parallel_size
+    b_rep = max(args.batch_per_gpu, 1) * tp * pp
+    gen = torch.Generator().manual_seed(77 + ctx.get_local_rank(ParallelMode.DATA))
+    ids = torch.randint(0, 8192, (b_rep, S), generator=gen).to(args.device)
+    out = {}
+    for name, fused in (("fused", True), ("library", False)):
+        torch.manual_seed(4321)
+        model, optim, _ = _build_ours(args, ctx, torch, n_layer=2 * pp, vocab=8192, hf=args.hf, fused=fused)
+        losses = []
+        for _ in range(3):
+            loss = _total_loss(model, ids, args.experts)
+            optim.zero_grad()
+            loss.backward()
+            optim.step()
+            losses.append(loss.detach().float())
+        seen, chk = set(), torch.zeros((), dtype=torch.float64, device=args.device)
+        for p in model.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                chk += p.detach().double().abs().sum()
+        losses = torch.stack(losses).double()
+        if dist.get_world_size() > 1:
+            dist.all_reduce(chk)
+            dist.all_reduce(losses)   # (pipelined models report the loss on every rank; sums are compared like for like)
+        out[name] = (losses, chk)
+        del model, optim
+    (lf, cf), (ll, cl) = out["fused"], out["library"]
+    loss_err = float(((lf - ll).abs() / ll.abs().clamp(min=1e-9)).max())
+    param_err = float((cf - cl).abs() / cl.abs().clamp(min=1e-9))
+    # bf16 kernels with different summation orders: losses agree to ~1e-3 relative; a protocol bug (a lost tile, a
+    # stale buffer, a double-counted gradient) shows up orders of magnitude above that
+    ok = bool(loss_err < 2e-2 and param_err < 1e-3 and torch.isfinite(lf).all())
+    return {"numerics_ok": ok, "max_rel_err_loss": loss_err, "rel_err_param_checksum": param_err,
+            "losses_fused": [float(x) / dist.get_world_size() for x in lf],
+            "losses_library": [float(x) / dist.get_world_size() for x in ll],
+            "what": "3 steps, 2-layer model of the benchmark width, fused NVLink engines vs NCCL + plain kernels"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from pipegoose_b200 import ops
     from pipegoose_b200.distributed import ParallelContext, ParallelMode
-    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
-    from pipegoose_b200.nn import DataParallel, TensorParallel
-    from pipegoose_b200.optim import DistributedOptimizer
-    from pipegoose_b200.optim.fused_adam import FusedAdam
 
-    tp, dp = parallel_layout(args.gpus)
-    pp = max(args.pp, 1)
-    if args.tp > 0 or pp > 1:
-        # the other BASELINE.json configs: --tp 8 (bloom-7b1), --tp 2 --pp 2 (bloom-3b, 1F1B), --experts 8 (Switch MoE)
-        tp = args.tp if args.tp > 0 else 1
-        assert args.gpus % (tp * pp) == 0, "--gpus must be a multiple of tp * pp"
-        dp = args.gpus // (tp * pp)
+    tp, pp, dp = layout_of(args)
     ctx = ParallelContext.from_torch(tensor_parallel_size=tp, pipeline_parallel_size=pp, data_parallel_size=dp,
-                                     backend="nccl")
+                                     backend="nccl" if args.device == "cuda" else "gloo")
     rank = ctx.get_global_rank()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device("cuda", torch.cuda.current_device()) if args.device == "cuda" else torch.device("cpu")
+    numerics = None
+    if args.gpus > 1 and not args.no_self_check:
+        try:
+            numerics = numerics_self_check(args, ctx, torch, dist)
+        except Exception as e:  # a failing check is reported, it does not hide the benchmark number
+            import traceback
+
+            traceback.print_exc()
+            numerics = {"numerics_ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+        if args.device == "cuda":
+            torch.cuda.empty_cache()
     torch.manual_seed(1234)
-    if args.model.startswith("gpt2"):  # not a BASELINE.json config: the second model family on the same kernels
-        from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
-
-        cfg = getattr(GPT2Config, args.model.replace("-", "_"))()
-        model = GPT2LMHeadModel(cfg).to(torch.bfloat16)
-    else:
-        cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
-        model = BloomForCausalLM(cfg).to(torch.bfloat16)
-    if args.experts > 0:
-        from pipegoose_b200.nn import ExpertParallel
-        from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
-
-        router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
-        layers = list(range(0, cfg.n_layer, max(args.moe_every, 1)))
-        model = ExpertParallel(model, args.experts, mapping=layers, router=router.to(torch.bfloat16),
-                               parallel_context=ctx).parallelize()
-    model = TensorParallel(model, ctx).parallelize()
-    if pp > 1:
-        from pipegoose_b200.nn import PipelineParallel
-
-        model = PipelineParallel(model, num_microbatches=args.microbatches, parallel_context=ctx).parallelize()
-    model = DataParallel(model, ctx).parallelize()
-    model.to("cuda")
-    optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=args.lr), ctx)
+    model, optim, cfg = _build_ours(args, ctx, torch, hf=args.hf)
 
     S = args.seq_len
     b_rep = args.batch_per_gpu * tp * pp  # sequences per model replica (DP rank)
     gen = torch.Generator().manual_seed(1000 + ctx.get_local_rank(ParallelMode.DATA))
     n_host = args.steps + args.warmup + 1
-    host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen).pin_memory() for _ in range(n_host)]
+    host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen) for _ in range(n_host)]
+    if args.device == "cuda":
+        host_ids = [t.pin_memory() for t in host_ids]
     dev_ids = host_ids[0].to(dev)
 
-    def total_loss(ids):
-        loss = model(ids, labels=ids).loss
-        if args.experts > 0:
-            # Switch training objective: task loss + load-balancing and router-z terms the MoE layers pushed
-            from pipegoose_b200.nn.expert_parallel import ExpertContext
-
-            store = ExpertContext.get_instance()
-            loss = loss + 0.01 * sum(store.pop_all_aux_loss()) + 0.001 * sum(store.pop_all_z_loss())
-        return loss
-
     def step_device(i):
-        loss = total_loss(dev_ids)
+        loss = _total_loss(model, dev_ids, args.experts)
         optim.zero_grad()
         loss.backward()
         optim.step()
@@ -205,7 +342,7 @@ def run_ours(args):
 
     def step_e2e(i):
         ids = host_ids[i % n_host].to(dev, non_blocking=True)
-        loss = total_loss(ids)
+        loss = _total_loss(model, ids, args.experts)
         optim.zero_grad()
         loss.backward()
         optim.step()
@@ -213,8 +350,8 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step_e2e(i)
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
+    sampler = ClockSampler(torch.cuda.current_device() if args.device == "cuda" else 0)
+    if rank == 0 and args.device == "cuda":
         sampler.start()
     ops.reset_launch_count()
     ms_dev = timed_region(torch, dist, args.steps, step_device)
@@ -224,8 +361,7 @@ def run_ours(args):
         sampler.stop()
     tokens_per_step = args.batch_per_gpu * args.gpus * S
     result = {
-        "metric": "bloom-560m training tokens/sec (whole job, device-timed, max over ranks)" if args.model == "bloom-560m"
-        else f"{args.model} training tokens/sec (whole job, device-timed, max over ranks)",
+        "metric": f"{args.model} training tokens/sec (whole job, device-timed, max over ranks)",
         "value": tokens_per_step * args.steps / (ms_dev / 1e3),
         "unit": "tokens/s",
         "n_gpus": args.gpus,
@@ -235,16 +371,13 @@ def run_ours(args):
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16",
+        "dtype": "bf16" if args.device == "cuda" else "fp32 (cpu dry run)",
         "data": "synthetic token ids (uniform random), random-init weights",
         "impl": "pipegoose_b200",
-        "config": {
-            "model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": S,
-            "parallelism": f"tp{tp}" + (f"pp{pp}(1f1b,{args.microbatches}mb)" if pp > 1 else "") + f"dp{dp}"
-            + ("+zero1" if dp > 1 else "") + (f"+moe{args.experts}e" if args.experts > 0 else ""),
-            "optimizer": "Adam (fp32 master + moments, fused)", "batch_per_gpu": args.batch_per_gpu,
-            "l2": "no explicit flush: per-step working set (1.1 GB bf16 weights + >6 GB activations) >> 126 MB L2",
-        },
+        "config": config_of(args, tp, pp, dp),
+        "impl_notes": {"optimizer": "fused Adam, fp32 master weights + moments, ZeRO-1 slices when dp > 1",
+                       "model_class": "transformers.BloomForCausalLM converted in place by TensorParallel" if args.hf
+                       else "pipegoose_b200.models"},
         "e2e": {
             "value": tokens_per_step * args.steps / (ms_e2e / 1e3), "unit": "tokens/s",
             "ms_per_step": ms_e2e / args.steps,
@@ -256,6 +389,9 @@ def run_ours(args):
         "mfu_vs_measured_sustained": None,
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    if numerics is not None:
+        result["numerics"] = numerics
+        result["numerics_ok"] = numerics.get("numerics_ok")
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         flops = model.flops_per_token(S) * tokens_per_step / args.gpus
@@ -292,56 +428,93 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": f"import failed: {type(e).__name__}: {e}"[:300]}))
         return
 
-    tp, dp = parallel_layout(args.gpus)
+    tp, pp, dp = layout_of(args)
+    note = None
+    if pp > 1:
+        # The reference's pipeline engine cannot run in this image: nn/pipeline_parallel/partitioner.py traces the model
+        # with transformers.utils.fx, which transformers 5 removed, and its RPC runtime was never
+        # finished.  The closest layout its stock code does run is the same model with the pipeline
+        # dimension folded into data parallelism: tp x (pp*dp) + ZeRO-1, same global batch.
+        note = (f"reference pipeline engine not runnable (transformers.utils.fx removed in transformers 5): ran tp{tp} x "
+                f"dp{dp * pp} + ZeRO-1 on the same global batch instead of tp{tp} x pp{pp} x dp{dp}")
+        dp, pp = dp * pp, 1
+    cuda = args.device == "cuda"
+    if cuda:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     # The reference issues collectives on CPU tensors during bring-up (parallel_context.py:263-287), which a
     # pure "nccl" group rejects; torch's per-device backend string gives it gloo for those and NCCL for CUDA
     # tensors.  This is an argument of the reference's public API, not a change to it.
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     ctx = ParallelContext.from_torch(tensor_parallel_size=tp, pipeline_parallel_size=1, data_parallel_size=dp,
-                                     backend="cpu:gloo,cuda:nccl")
-    ctx.set_device()
+                                     backend="cpu:gloo,cuda:nccl" if cuda else "gloo")
+    if cuda:
+        ctx.set_device()
     rank = ctx.get_global_rank()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    sizes = {"bloom-560m": (1024, 24, 16), "bloom-3b": (2560, 30, 32), "bloom-7b1": (4096, 30, 32), "bloom-1b7": (2048, 24, 16)}
-    h, L, nh = sizes[args.model]
+    dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
+    h, L, nh, V = MODEL_SIZES[args.model]
     torch.manual_seed(1234)
-    cfg = BloomConfig(hidden_size=h, n_layer=L, n_head=nh, vocab_size=250880)
-    model = BloomForCausalLM(cfg).to(torch.bfloat16)
+    cfg = BloomConfig(hidden_size=h, n_layer=L, n_head=nh, vocab_size=V)
+    model = BloomForCausalLM(cfg)
+    if cuda:
+        model = model.to(torch.bfloat16)
+    loss_terms = None
+    if args.experts > 0:
+        # the reference's Switch-MoE path: ExpertParallel (experts sharded over the TENSOR group, tokens replicated,
+        # all-reduce combine, nn/expert_parallel/experts.py:41-82) + ExpertLoss's auxiliary terms
+        from pipegoose.nn.expert_parallel import ExpertParallel, SwitchNoisePolicy, Top1Router
+        from pipegoose.nn.expert_parallel.expert_context import ExpertContext
+
+        router = Top1Router(SwitchNoisePolicy(), args.experts, h, expert_capacity=(1.25, 2.0))
+        if cuda:
+            router = router.to(torch.bfloat16)
+        layers = list(range(0, L, max(args.moe_every, 1)))
+        model = ExpertParallel(model, num_experts=args.experts, mapping=layers, router=router,
+                               parallel_context=ctx).parallelize()
+
+        def loss_terms(loss):   # ExpertLoss.__call__ (nn/expert_parallel/loss.py:26-31) with this benchmark's weights
+            store = ExpertContext.get_instance()
+            return loss + 0.01 * sum(store.pop_all_aux_loss()) + 0.001 * sum(store.pop_all_z_loss())
     model = TensorParallel(model, ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
     optim = torch.optim.Adam(model.parameters(), lr=args.lr)
     optim = DistributedOptimizer(optim, ctx)
-    model.to("cuda")
+    if cuda:
+        model.to("cuda")
     model.train()
 
     S = args.seq_len
     b_rep = args.batch_per_gpu * tp
     gen = torch.Generator().manual_seed(1000 + ctx.get_local_rank(ParallelMode.DATA))
     n_host = args.steps + args.warmup + 1
-    host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen).pin_memory() for _ in range(n_host)]
+    host_ids = [torch.randint(0, cfg.vocab_size, (b_rep, S), generator=gen) for _ in range(n_host)]
+    if cuda:
+        host_ids = [t.pin_memory() for t in host_ids]
     dev_ids = host_ids[0].to(dev)
     mask = torch.ones(b_rep, S, dtype=torch.long, device=dev)
 
+    def fwd(ids):
+        loss = model(input_ids=ids, attention_mask=mask, labels=ids).loss
+        return loss_terms(loss) if loss_terms is not None else loss
+
     def step_device(i):
-        out = model(input_ids=dev_ids, attention_mask=mask, labels=dev_ids)
+        loss = fwd(dev_ids)
         optim.zero_grad()
-        out.loss.backward()
+        loss.backward()
         optim.step()
 
     last = {}
 
     def step_e2e(i):
         ids = host_ids[i % n_host].to(dev, non_blocking=True)
-        out = model(input_ids=ids, attention_mask=mask, labels=ids)
+        loss = fwd(ids)
         optim.zero_grad()
-        out.loss.backward()
+        loss.backward()
         optim.step()
-        last["loss"] = out.loss.item()
+        last["loss"] = loss.item()
 
     for i in range(args.warmup):
         step_e2e(i)
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
+    sampler = ClockSampler(torch.cuda.current_device() if cuda else 0)
+    if rank == 0 and cuda:
         sampler.start()
     ms_dev = timed_region(torch, dist, args.steps, step_device)
     ms_e2e = timed_region(torch, dist, args.steps, step_e2e)
@@ -353,18 +526,19 @@ def run_reference(args):
         "metric": f"{args.model} training tokens/sec (whole job, device-timed, max over ranks)",
         "value": tokens_per_step * args.steps / (ms_dev / 1e3), "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if cuda else "fp32 (cpu dry run)",
         "data": "synthetic token ids (uniform random), random-init weights",
-        "config": {"model": args.model, "global_batch": args.batch_per_gpu * args.gpus, "seq_len": S,
-                   "parallelism": f"tp{tp}dp{dp}" + ("+zero1" if dp > 1 else ""),
-                   "optimizer": "torch.optim.Adam via reference DistributedOptimizer",
-                   "batch_per_gpu": args.batch_per_gpu},
+        "config": config_of(args, tp, pp, dp),
+        "impl_notes": {"optimizer": "torch.optim.Adam via the reference's DistributedOptimizer",
+                       "model_class": "transformers.BloomForCausalLM"},
         "e2e": {"value": tokens_per_step * args.steps / (ms_e2e / 1e3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(host_ids[0].numel() * host_ids[0].element_size()), "d2h_bytes_per_step": 4},
         "gpu_launches": 0,
         "final_loss": last.get("loss"),
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    if note is not None:
+        result["note"] = note
     if rank == 0:
         print(json.dumps(result), flush=True)
     try:
@@ -384,12 +558,17 @@ def main():
     ap.add_argument("--seq-len", type=int, default=1024)
     ap.add_argument("--batch-per-gpu", type=int, default=8)
     ap.add_argument("--lr", type=float, default=1e-4)
-    # non-default layouts (ours arm only): BASELINE.json configs #3-#5
+    # non-default layouts (both arms): BASELINE.json configs #3-#5
     ap.add_argument("--tp", type=int, default=0, help="tensor parallel size (0: 1 GPU -> 1, else 2)")
     ap.add_argument("--pp", type=int, default=1, help="pipeline stages (1F1B)")
     ap.add_argument("--microbatches", type=int, default=8)
     ap.add_argument("--experts", type=int, default=0, help="Switch-MoE experts (sharded over the tensor group)")
     ap.add_argument("--moe-every", type=int, default=2, help="every n-th block gets a MoE MLP")
+    ap.add_argument("--hf", action="store_true",
+                    help="ours arm: feed a transformers BloomForCausalLM (the reference's input) instead of pipegoose_b200.models")
+    ap.add_argument("--no-self-check", action="store_true", help="skip the N>1 numerics self-check (fused vs library engines)")
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                    help="cpu: dry run of this script on gloo with a tiny model (no benchmark value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     _env_defaults()
