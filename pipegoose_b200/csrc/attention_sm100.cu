@@ -15,6 +15,7 @@
 // staged (bf16, swizzled) for dV += P^T dO, dK += dS^T Q (TMEM accumulators across the loop) and
 // dQ_i = dS K (read back per block and reduced into an fp32 buffer with vector red.global.add).
 #include "launch.h"
+#include "pdl_launch.cuh"
 #include "ptx.cuh"
 #include <cstdio>
 #include <cstring>
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int num_qb = (args.S + ATT_BM - 1) / ATT_BM;
   const int qb = num_qb - 1 - blockIdx.x;  // longest (most key blocks) first
   const int head = blockIdx.y, batch = blockIdx.z;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(192, (D == 64) ? 2 : 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // prologue above overlapped the predecessor; Q/K/V, dO, lse, delta are read below
   const uint32_t tmem_S0 = tmem_base;              // SB x 128 columns
   const uint32_t tmem_O = tmem_base + SB * 128;    // D columns
 
@@ -365,6 +368,8 @@ __global__ void __launch_bounds__(256) attention_delta_kernel(const __nv_bfloat1
                                                               const __nv_bfloat16* __restrict__ out,
                                                               float* __restrict__ delta, int B, int S, int H,
                                                               int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B * S) return;
   const int cph = D / 8;                 // 16-byte chunks (= lanes) per head: 8 or 16
@@ -442,6 +447,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(dq_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const int num_qb = (args.S + ATT_BM - 1) / ATT_BM;
   const int jb = blockIdx.x;  // key block
   const int head = blockIdx.y, batch = blockIdx.z;
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // prologue above overlapped the predecessor; Q/K/V, dO, lse, delta are read below
   // TMEM columns: S [0,128) dP [128,256) dV [256,256+D) dK [256+D,256+2D); dQ aliases S when D == 128
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + D;
   const uint32_t tdQ = (D == 64) ? tmem_base + 384 : tmem_base;
@@ -695,6 +702,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 __global__ void __launch_bounds__(256) attention_dq_convert_kernel(const float* __restrict__ dq,
                                                                    __nv_bfloat16* __restrict__ dqkv, int64_t rows,
                                                                    int H, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t idx = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   const int64_t total = rows * H * D;
   if (idx >= total) return;
@@ -753,7 +762,7 @@ static int launch_att_fwd(const CUtensorMap& tm, const AttFwdArgs& a, cudaStream
     set = true;
   }
   dim3 grid((a.S + ATT_BM - 1) / ATT_BM, a.H, a.B);
-  attention_fwd_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(tm, a);
+  if (launch_pdl(attention_fwd_kernel<D>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, s, tm, a) != cudaSuccess) return -1;
   PG_CHECK_LAUNCH("attention_fwd");
   return 0;
 }
@@ -784,7 +793,7 @@ static int launch_att_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const A
     set = true;
   }
   dim3 grid((a.S + ATT_BN - 1) / ATT_BN, a.H, a.B);
-  attention_bwd_kernel<D><<<grid, kBwdThreads, Cfg::kSmemBytes, s>>>(tq, tdo, a);
+  if (launch_pdl(attention_bwd_kernel<D>, grid, dim3(kBwdThreads), Cfg::kSmemBytes, s, tq, tdo, a) != cudaSuccess) return -1;
   PG_CHECK_LAUNCH("attention_bwd");
   return 0;
 }
@@ -800,8 +809,8 @@ extern "C" int pg_attention_bwd(const void* qkv, const float* slopes, const void
   if (att_tmap(&tdo, dout, rows, static_cast<uint64_t>(H) * D) != 0) return -1;
   if (cudaMemsetAsync(dq_acc, 0, rows * H * D * sizeof(float), s) != cudaSuccess) return -1;
   {
-    attention_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
-        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, S, H, D);
+    if (launch_pdl(attention_delta_kernel, dim3((unsigned)((rows * 32 + 255) / 256)), dim3(256), 0, s,
+                   (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, delta, B, S, H, D) != cudaSuccess) return -1;
     PG_CHECK_LAUNCH("attention_delta");
   }
   AttBwdArgs a;
@@ -813,7 +822,8 @@ extern "C" int pg_attention_bwd(const void* qkv, const float* slopes, const void
   const int rc = D == 64 ? launch_att_bwd<64>(tq, tdo, a, s) : launch_att_bwd<128>(tq, tdo, a, s);
   if (rc != 0) return rc;
   const int64_t total = rows * H * D;
-  attention_dq_convert_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, s>>>(dq_acc, (__nv_bfloat16*)dqkv, rows, H, D);
+  if (launch_pdl(attention_dq_convert_kernel, dim3((unsigned)((total / 8 + 255) / 256)), dim3(256), 0, s, (const float*)dq_acc,
+                 (__nv_bfloat16*)dqkv, (int64_t)rows, H, D) != cudaSuccess) return -1;
   PG_CHECK_LAUNCH("attention_dq_convert");
   return 0;
 }

@@ -3,6 +3,7 @@
 // cross-entropy (stats / finalize+dlogits), fused Adam on flat fp32 shards, grad utilities.
 // All bf16 I/O is 16-byte vectorised; statistics and accumulation are fp32.
 #include "launch.h"
+#include "pdl_launch.cuh"
 #include "ptx.cuh"
 #include <cstdio>
 
@@ -21,6 +22,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(
     int vocab_end, const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
     __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     int rows, int h, float eps, int apply_ln) {
+  pdl_launch_dependents();
+  pdl_wait();  // before any exit: a kernel that completes must imply its predecessors completed
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(
     const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean,
     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dx_extra,
     __nv_bfloat16* __restrict__ dx, int rows, int h) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -180,6 +185,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
     float* __restrict__ dbeta, int rows, int h, int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int col0 = blockIdx.x * 256 + lane * 8;
@@ -229,6 +236,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int ld,
                                                      float* __restrict__ out, int rows, int cols,
                                                      int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int col0 = blockIdx.x * 256 + lane * 8;
@@ -527,10 +536,10 @@ extern "C" int pg_layernorm_fwd(const void* x, const int64_t* ids, int vocab_sta
   if (rows == 0) return 0;
   if (h % 8 != 0) return -1;
   const int blocks = (rows * 32 + 255) / 256;
-  PG_DISPATCH_CH(h, (layernorm_fwd_kernel<CH><<<blocks, 256, 0, s>>>(
-                        (const __nv_bfloat16*)x, ids, vocab_start, vocab_end,
-                        (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)y,
-                        mean, rstd, rows, h, eps, apply_ln)));
+  PG_DISPATCH_CH(h, (launch_pdl(layernorm_fwd_kernel<CH>, dim3(blocks), dim3(256), 0, s,
+                                (const __nv_bfloat16*)x, ids, vocab_start, vocab_end,
+                                (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (__nv_bfloat16*)y,
+                                mean, rstd, rows, h, eps, apply_ln)));
   PG_CHECK_LAUNCH("layernorm_fwd");
   return 0;
 }
@@ -541,10 +550,10 @@ extern "C" int pg_layernorm_bwd(const void* dy, const void* x, const void* gamma
   if (rows == 0) return 0;
   if (h % 8 != 0) return -1;
   const int blocks = (rows * 32 + 255) / 256;
-  PG_DISPATCH_CH(h, (layernorm_bwd_dx_kernel<CH><<<blocks, 256, 0, s>>>(
-                        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                        (const __nv_bfloat16*)gamma, mean, rstd, (const __nv_bfloat16*)dx_extra,
-                        (__nv_bfloat16*)dx, rows, h)));
+  PG_DISPATCH_CH(h, (launch_pdl(layernorm_bwd_dx_kernel<CH>, dim3(blocks), dim3(256), 0, s,
+                                (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                (const __nv_bfloat16*)gamma, mean, rstd, (const __nv_bfloat16*)dx_extra,
+                                (__nv_bfloat16*)dx, rows, h)));
   PG_CHECK_LAUNCH("layernorm_bwd_dx");
   if (dgamma != nullptr) {
     const int cb = (h + 255) / 256;
@@ -552,8 +561,8 @@ extern "C" int pg_layernorm_bwd(const void* dy, const void* x, const void* gamma
     if (rsplit > (rows + 63) / 64) rsplit = (rows + 63) / 64;
     if (rsplit < 1) rsplit = 1;
     const int rpb = (rows + rsplit - 1) / rsplit;
-    layernorm_bwd_params_kernel<<<dim3(cb, rsplit), 256, 0, s>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, dgamma, dbeta, rows, h, rpb);
+    launch_pdl(layernorm_bwd_params_kernel, dim3(cb, rsplit), dim3(256), 0, s,
+               (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, mean, rstd, dgamma, dbeta, rows, h, rpb);
     PG_CHECK_LAUNCH("layernorm_bwd_params");
   }
   return 0;
@@ -566,7 +575,7 @@ extern "C" int pg_colsum(const void* x, int ld, float* out, int rows, int cols, 
   if (rsplit > (rows + 63) / 64) rsplit = (rows + 63) / 64;
   if (rsplit < 1) rsplit = 1;
   const int rpb = (rows + rsplit - 1) / rsplit;
-  colsum_kernel<<<dim3(cb, rsplit), 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, rows, cols, rpb);
+  launch_pdl(colsum_kernel, dim3(cb, rsplit), dim3(256), 0, s, (const __nv_bfloat16*)x, ld, out, rows, cols, rpb);
   PG_CHECK_LAUNCH("colsum");
   return 0;
 }

@@ -2,6 +2,7 @@
 // run time so the library links without libcuda), tile-shape selection, launch.
 #include "gemm_sm100.cuh"
 #include "launch.h"
+#include "pdl_launch.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -135,13 +136,15 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tal, args);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) pdl_launch_dependents();  // the next kernel may start its prologue under this one's tail
 
   const int chunk_rows = (args.num_chunks > 1) ? args.chunk_rows : args.M;
   const int m_blks_per_chunk = (chunk_rows + BM_T - 1) / BM_T;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // One thread drives a ring of bulk copies: peer shard -> shared memory -> local gathered
     // matrix, 16 KB per copy, 8 loads in flight per CTA (~1 MB in flight over 8 CTAs: the NVLink
     // bandwidth-delay product).
+    pdl_wait();  // predecessors (the kernel that produced this rank's shard) are complete and visible
     constexpr uint32_t kSlice = 16 * 1024;
     constexpr int kCommStages = 12;  // smem ring slots
     constexpr int kLoadsInFlight = 10;  // => up to kCommStages - kLoadsInFlight stores may still be reading smem
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __syncthreads();
   if constexpr (CTA2) cluster_sync();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands / epilogue inputs are read below
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {

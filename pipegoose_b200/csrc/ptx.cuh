@@ -332,6 +332,15 @@ PG_DEVICE void fence_proxy_async_global() {
 }
 
 // ----------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): the next kernel of the stream may start its prologue (smem carve-up,
+// barrier init, TMEM allocation, tensor-map prefetch) while this one is still running; it blocks in pdl_wait()
+// until every predecessor has completed and its memory operations are visible.  Both are no-ops for kernels
+// that were not launched with the programmatic-stream-serialization attribute.
+// ----------------------------------------------------------------------------------
+PG_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+PG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------
 // vector global access
 // ----------------------------------------------------------------------------------
 PG_DEVICE uint4 ld_global_v4(const void* p) {
