@@ -41,21 +41,32 @@ class FlatModelState:
         assert len(self.params) > 0
         # parameters whose gradients are partial sums over the tensor-parallel group (sequence-parallel
         # LayerNorms / row-parallel biases) come first, contiguously: ONE all-reduce of flat_grad[:n] sums them
-        self.params.sort(key=lambda p: 0 if getattr(p, "tp_partial_grad", False) else 1)  # stable
+        # ... then the other small (< 2-D) parameters, then the matrices: [matrix_start, numel) holds only >= 2-D
+        # parameters with complete gradients — the region the fused ZeRO-1 path reduce-scatters inside the kernels that
+        # produce the gradients (wgrad epilogue, embedding backward), while [0, matrix_start) stays bucket-reduced
+        self.params.sort(key=lambda p: 0 if getattr(p, "tp_partial_grad", False) else (1 if p.dim() < 2 else 2))  # stable
         self.tp_partial_numel = 0
+        self.matrix_start = None
+        self.inline = None    # the engine that reduce-scatters [matrix_start, numel) in-kernel (ops.comm.FusedDPEngine)
         p0 = self.params[0]
         self.device, self.dtype = p0.device, p0.dtype
         assert all(p.device == self.device and p.dtype == self.dtype for p in self.params), \
             "all parameters of a flat state must share device and dtype"
         self.offsets: Dict[int, Tuple[int, int]] = {}
         off = 0
+        region_mult = max(pad_to_multiple_of, 1) * _ALIGN
         for p in self.params:
+            if self.matrix_start is None and p.dim() >= 2 and not getattr(p, "tp_partial_grad", False):
+                off = (off + region_mult - 1) // region_mult * region_mult   # slices of both regions stay aligned
+                self.matrix_start = off
             self.offsets[id(p)] = (off, p.numel())
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
             if getattr(p, "tp_partial_grad", False):
                 self.tp_partial_numel = off
         mult = max(pad_to_multiple_of, 1) * _ALIGN
         self.numel = (off + mult - 1) // mult * mult
+        if self.matrix_start is None:
+            self.matrix_start = self.numel
         if buffer_factory is not None:
             # externally owned storage (NVLink peer-mapped symmetric memory for the fused DP/ZeRO kernels)
             self.flat_param, self.flat_grad = buffer_factory(self.numel, self.dtype, grad_dtype)
@@ -104,8 +115,12 @@ class FlatModelState:
             return  # produced by a pipeline schedule inside forward and not consumed by the optimizer yet
         self.grads_materialized = False
         self.begin_grad_window()
+        if self.inline is not None:
+            # [matrix_start, numel) is reduce-scattered in-kernel: its owner slices are cleared by the optimizer step that
+            # consumes them; an explicit clear (gradients produced but never consumed) is a collective: memset + peer barrier
+            self.inline.clear_inline_region(force=not lazy)
         if not lazy:
-            self.flat_grad.zero_()
+            (self.flat_grad if self.inline is None else self.flat_grad[:self.matrix_start]).zero_()
             for p in self.params:
                 p._mg_fresh = False
             return
@@ -114,8 +129,9 @@ class FlatModelState:
             small = self._small_grads = [p.main_grad for p in self.params if p.dim() < 2]
         if small:
             torch._foreach_zero_(small)  # one multi-tensor launch instead of one fill per bias / LN vector
+        inline_from = self.matrix_start if self.inline is not None else self.numel
         for p in self.params:
-            p._mg_fresh = p.dim() >= 2
+            p._mg_fresh = p.dim() >= 2 and self.offsets[id(p)][0] < inline_from
 
     def begin_grad_window(self):
         """The gradients of the previous window were consumed (optimizer step) or dropped (``zero_grad``): the next

@@ -130,7 +130,7 @@ class TensorPartialGradSync:
 
 
 class _Bucket:
-    __slots__ = ("index", "start", "end", "params", "pending", "launched", "work", "deferred")
+    __slots__ = ("index", "start", "end", "params", "pending", "launched", "work", "deferred", "inline")
 
     def __init__(self, index, start, end):
         self.index, self.start, self.end = index, start, end
@@ -139,6 +139,7 @@ class _Bucket:
         self.launched = False
         self.work = None
         self.deferred = False  # holds TP-partial gradients: reduced over DATA only after the TENSOR all-reduce
+        self.inline = False    # reduce-scattered inside the kernels that produce the gradients: never launched here
 
 
 class GradReducer:
@@ -167,15 +168,29 @@ class GradReducer:
         self.flat = self._make_flat_state()
         # pad the flat buffers so that every bucket (including the last) divides by dp
         n = self.flat.numel
+        # With the NVLink engine the small parameters ([0, head): 1-D and tensor-parallel-partial gradients) get a bucket
+        # of their own, so that the matrices behind them can leave the bucketed reduction as a whole (enable_inline_rs)
+        self.head = self.flat.matrix_start if (self._fused is not None and 0 < self.flat.matrix_start < n) else 0
+        self.zero_bucket_numel = self.bucket_numel   # region length the ZeRO-1 slices are cut from (beyond the head)
+        self.inline = False
         self.buckets = []
         start, i = 0, 0
+        if self.head:
+            self.buckets.append(_Bucket(0, 0, self.head))
+            start, i = self.head, 1
         while start < n:
             end = min(n, start + self.bucket_numel)
             self.buckets.append(_Bucket(i, start, end))
             start, i = end, i + 1
+
+        def bucket_index(o):
+            if self.head:
+                return 0 if o < self.head else 1 + (o - self.head) // self.bucket_numel
+            return o // self.bucket_numel
+
         for p in self.flat.params:
             o, cnt = self.flat.param_range(p)
-            first, last = o // self.bucket_numel, (o + cnt - 1) // self.bucket_numel
+            first, last = bucket_index(o), bucket_index(o + cnt - 1)
             owners = self.buckets[first:last + 1]
             self._bucket_of[id(p)] = owners
             for b in owners:
@@ -212,10 +227,33 @@ class GradReducer:
         self._fused = engine
         return state
 
+    def enable_inline_rs(self) -> bool:
+        """ZeRO-1 with the NVLink engine: the gradients of the matrices ([head, numel), > 99.9 % of the bytes) are
+        reduce-scattered by the kernels that produce them — wgrad GEMM epilogue, embedding backward and gradient folds
+        ``red.global.add`` every contribution into the owner rank's buffer while backward runs — instead of by bucket
+        reductions after them.  Only the small head bucket is still reduced here.  Collective over the DATA group.
+        Replaces the reference's per-parameter blocking all-reduce hook (nn/data_parallel/data_parallel.py:28-43)."""
+        if self.inline:
+            return True
+        if self._fused is None or self.mode != "reduce_scatter" or not self.head:
+            return False
+        if not self._fused.enable_inline(self.head):
+            return False
+        self.inline = True
+        self.flat.inline = self._fused
+        self.zero_bucket_numel = self.flat.numel - self.head
+        for b in self.buckets:
+            b.inline = b.start >= self.head
+        for p in self.flat.params:
+            if self.flat.param_range(p)[0] >= self.head:
+                p._mg_fresh = False     # never overwritten locally: contributions are added at the owners
+        self._reset_pending()
+        return True
+
     def _reset_pending(self):
         for b in self.buckets:
             b.pending = sum(getattr(p, "_pg_grad_contribs", 1) for p in b.params)
-            b.launched = False
+            b.launched = b.inline
             b.work = None
         self._cursor = len(self.buckets) - 1
         self._contribs_seen: Dict[int, int] = {}
@@ -323,6 +361,9 @@ class GradReducer:
             for b in self.buckets:
                 if b.work is not None:
                     b.work.wait()
+            if self.inline:
+                # every rank's gradient adds into my slices are complete and visible before the optimizer reads them
+                self._fused.barrier()
         else:
             self.flat.finalize_grads()
         if self._sync and not self._fused_optimizer_attached():

@@ -11,6 +11,8 @@ namespace {
 
 cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
 
+bool parse_grad_rs(const py::dict& d, PgGradRS* out);
+
 void check_bf16_2d(const torch::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
   TORCH_CHECK(t.scalar_type() == torch::kBFloat16, name, " must be bf16");
@@ -102,6 +104,10 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
     d.rs_wait_value = (uint32_t)ag["rs_wait_value"].cast<int64_t>();
     d.my_rank = ag["rank"].cast<int>();
   }
+  if (ag.contains("grad_rs")) {
+    TORCH_CHECK(f32, "grad_rs needs an fp32 output");
+    parse_grad_rs(ag["grad_rs"].cast<py::dict>(), &d.grad_rs);
+  }
   if (ag.contains("k_splits")) d.k_splits = ag["k_splits"].cast<int>();
   if (ag.contains("cta_pair")) d.cta_pair = ag["cta_pair"].cast<int>();
   if (ag.contains("n_comm")) {
@@ -120,6 +126,22 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
   TORCH_CHECK(pg_gemm_bf16(&d, cur_stream()) == 0, "pg_gemm_bf16 failed");
 }
 
+
+// {"peer": [ptr per data-parallel rank], "local": ptr, "start": elems, "seg": elems, "scalar": 0/1} -> PgGradRS
+bool parse_grad_rs(const py::dict& d, PgGradRS* out) {
+  memset(out, 0, sizeof(*out));
+  if (!d.contains("peer")) return false;
+  auto peers = d["peer"].cast<std::vector<int64_t>>();
+  TORCH_CHECK(peers.size() >= 2 && peers.size() <= PG_MAX_PEERS, "grad_rs: 2..", PG_MAX_PEERS, " peers");
+  for (size_t i = 0; i < peers.size(); ++i) out->peer[i] = reinterpret_cast<float*>(peers[i]);
+  out->local = reinterpret_cast<const float*>(d["local"].cast<int64_t>());
+  out->start = d["start"].cast<int64_t>();
+  out->seg = d["seg"].cast<int64_t>();
+  out->world = (int)peers.size();
+  out->scalar_red = d.contains("scalar") ? d["scalar"].cast<int>() : 0;
+  TORCH_CHECK(out->seg > 0 && out->seg % 4 == 0 && out->start % 4 == 0, "grad_rs: start / seg must be multiples of 4");
+  return true;
+}
 
 #define PG_CUDA(t) TORCH_CHECK((t).is_cuda() && (t).is_contiguous(), #t " must be a contiguous CUDA tensor")
 #define PG_BF16(t) TORCH_CHECK((t).scalar_type() == torch::kBFloat16, #t " must be bf16")
@@ -165,13 +187,18 @@ void colsum(const torch::Tensor& x, torch::Tensor out) {
   TORCH_CHECK(pg_colsum(x.data_ptr(), (int)x.stride(0), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), cur_stream()) == 0, "colsum failed");
 }
 
-void embedding_bwd(const torch::Tensor& dx, const torch::Tensor& ids, torch::Tensor dw, int64_t vocab_start, int64_t vocab_end) {
+void embedding_bwd(const torch::Tensor& dx, const torch::Tensor& ids, torch::Tensor dw, int64_t vocab_start, int64_t vocab_end,
+                   const py::dict& grad_rs) {
   PG_CUDA(dx); PG_BF16(dx); PG_CUDA(ids); PG_CUDA(dw); PG_F32(dw);
   c10::cuda::CUDAGuard guard(dx.device());
   const int h = (int)dx.size(-1);
   const int rows = (int)(dx.numel() / h);
   TORCH_CHECK(ids.scalar_type() == torch::kInt64 && ids.numel() == rows, "ids must be int64 [rows]");
-  TORCH_CHECK(pg_embedding_bwd(dx.data_ptr(), ids.data_ptr<int64_t>(), dw.data_ptr<float>(), rows, h, (int)vocab_start, (int)vocab_end, cur_stream()) == 0, "embedding_bwd failed");
+  PgGradRS grs;
+  const bool inl = parse_grad_rs(grad_rs, &grs);
+  TORCH_CHECK(!inl || h % 8 == 0, "embedding_bwd with grad_rs: hidden size must be a multiple of 8");
+  TORCH_CHECK(pg_embedding_bwd(dx.data_ptr(), ids.data_ptr<int64_t>(), dw.data_ptr<float>(), rows, h, (int)vocab_start, (int)vocab_end,
+                               inl ? &grs : nullptr, cur_stream()) == 0, "embedding_bwd failed");
 }
 
 void ce_stats(const torch::Tensor& logits, const torch::Tensor& targets, torch::Tensor stats, int64_t vocab_start) {
@@ -194,7 +221,8 @@ void ce_finalize(torch::Tensor logits, const torch::Tensor& targets, const torch
 }
 
 void adam_step(torch::Tensor master, torch::Tensor m, torch::Tensor v, const torch::Tensor& grad, c10::optional<torch::Tensor> param_bf16,
-               double lr, double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale, bool adamw) {
+               double lr, double beta1, double beta2, double eps, double wd, int64_t step, double grad_scale, bool adamw,
+               bool zero_grad) {
   PG_CUDA(master); PG_F32(master); PG_CUDA(m); PG_F32(m); PG_CUDA(v); PG_F32(v); PG_CUDA(grad); PG_F32(grad);
   c10::cuda::CUDAGuard guard(master.device());
   const int64_t n = master.numel();
@@ -203,7 +231,7 @@ void adam_step(torch::Tensor master, torch::Tensor m, torch::Tensor v, const tor
   if (param_bf16.has_value()) { PG_CUDA(*param_bf16); PG_BF16(*param_bf16); TORCH_CHECK(param_bf16->numel() == n, "adam: bf16 param size mismatch"); pb = param_bf16->data_ptr(); }
   const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
   TORCH_CHECK(pg_adam(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), grad.data_ptr<float>(), pb, n, (float)lr, (float)beta1, (float)beta2,
-                      (float)eps, (float)wd, (float)bc1, (float)bc2, (float)grad_scale, adamw, cur_stream()) == 0, "adam failed");
+                      (float)eps, (float)wd, (float)bc1, (float)bc2, (float)grad_scale, adamw, zero_grad, cur_stream()) == 0, "adam failed");
 }
 
 void sgd_step(torch::Tensor master, c10::optional<torch::Tensor> mom, const torch::Tensor& grad, c10::optional<torch::Tensor> param_bf16,
@@ -226,6 +254,18 @@ void accum_bf16_to_f32(const torch::Tensor& src, torch::Tensor dst, double scale
   TORCH_CHECK(pg_accum_bf16_to_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), (float)scale, accumulate, cur_stream()) == 0, "accum failed");
 }
 
+
+// dst (a view into the local flat fp32 gradient buffer) += scale * src through the in-kernel reduce-scatter
+void grad_rs_accum(const torch::Tensor& src, torch::Tensor dst, double scale, const py::dict& grad_rs) {
+  PG_CUDA(src); PG_CUDA(dst); PG_F32(dst);
+  TORCH_CHECK(src.scalar_type() == torch::kBFloat16 || src.scalar_type() == torch::kFloat32, "src must be bf16 or fp32");
+  TORCH_CHECK(src.numel() == dst.numel(), "size mismatch");
+  c10::cuda::CUDAGuard guard(src.device());
+  PgGradRS grs;
+  TORCH_CHECK(parse_grad_rs(grad_rs, &grs), "grad_rs_accum needs a grad_rs descriptor");
+  TORCH_CHECK(pg_grad_rs_accum(src.data_ptr(), src.scalar_type() == torch::kFloat32, dst.data_ptr<float>(), src.numel(), (float)scale,
+                               &grs, cur_stream()) == 0, "grad_rs_accum failed");
+}
 
 void attention_fwd(const torch::Tensor& qkv, const torch::Tensor& slopes, torch::Tensor out, torch::Tensor lse,
                    int64_t B, int64_t S, int64_t H, int64_t D, double softmax_scale) {
@@ -304,21 +344,73 @@ void rs_reduce(int64_t staging_ptr, int64_t num_src, int64_t src_stride, int64_t
 }
 
 void allreduce_f32(std::vector<int64_t> peer_bufs, int64_t rank, int64_t offset, int64_t n, double scale, bool rs_only,
-                   std::vector<int64_t> peer_flags, int64_t epoch, int64_t blocks) {
+                   std::vector<int64_t> peer_flags, int64_t epoch, int64_t blocks, int64_t mc_buf) {
   float* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
   const int world = (int)peer_bufs.size();
   TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
   for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<float*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
-  TORCH_CHECK(pg_allreduce_f32(bufs, world, (int)rank, offset, n, (float)scale, rs_only, flags, (uint32_t)epoch, (int)blocks, cur_stream()) == 0, "allreduce_f32 failed");
+  TORCH_CHECK(pg_allreduce_f32(bufs, reinterpret_cast<float*>(mc_buf), world, (int)rank, offset, n, (float)scale, rs_only, flags,
+                               (uint32_t)epoch, (int)blocks, cur_stream()) == 0, "allreduce_f32 failed");
 }
 
 void allgather_bf16(std::vector<int64_t> peer_bufs, int64_t rank, int64_t bucket_elems, int64_t total_elems,
-                    std::vector<int64_t> peer_flags, int64_t epoch) {
+                    std::vector<int64_t> peer_flags, int64_t epoch, int64_t head_elems, int64_t mc_buf) {
   void* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
   const int world = (int)peer_bufs.size();
   TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
   for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<void*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
-  TORCH_CHECK(pg_allgather_bf16(bufs, world, (int)rank, 0, 0, bucket_elems, total_elems, flags, (uint32_t)epoch, cur_stream()) == 0, "allgather_bf16 failed");
+  TORCH_CHECK(pg_allgather_bf16(bufs, reinterpret_cast<void*>(mc_buf), world, (int)rank, head_elems, bucket_elems, total_elems, flags,
+                                (uint32_t)epoch, cur_stream()) == 0, "allgather_bf16 failed");
+}
+
+void multimem_selftest(int64_t mc_in, int64_t mc_out, torch::Tensor out) {
+  PG_CUDA(out); PG_F32(out);
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(pg_multimem_selftest(reinterpret_cast<const float*>(mc_in), reinterpret_cast<float*>(mc_out), out.data_ptr<float>(),
+                                   out.numel(), cur_stream()) == 0, "multimem_selftest failed");
+}
+
+void rs_reduce_mc(int64_t mc_partial, int64_t ctr_ptr, int64_t num_src, int64_t expected, const c10::optional<torch::Tensor>& bias,
+                  const c10::optional<torch::Tensor>& residual, torch::Tensor out) {
+  PG_CUDA(out); PG_BF16(out);
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(pg_rs_reduce_mc(reinterpret_cast<const void*>(mc_partial), reinterpret_cast<const uint32_t*>(ctr_ptr), (int)num_src,
+                              (uint32_t)expected, opt_ptr(bias), opt_ptr(residual), out.data_ptr(), (int)out.size(0), (int)out.size(1),
+                              cur_stream()) == 0, "rs_reduce_mc failed");
+}
+
+// ---- VMM + multicast symmetric memory (symm_vmm.cu)
+py::tuple vmm_probe(int64_t world) {
+  int mc = 0; int64_t gran = 0;
+  const int rc = pg_vmm_probe((int)world, &mc, &gran);
+  return py::make_tuple(rc == 0, mc != 0, gran);
+}
+py::tuple vmm_alloc(int64_t nbytes) {
+  void* ptr = nullptr; int fd = -1; uint64_t h = 0;
+  TORCH_CHECK(pg_vmm_alloc(nbytes, &ptr, &fd, &h) == 0, "vmm_alloc failed");
+  return py::make_tuple(reinterpret_cast<int64_t>(ptr), fd, (int64_t)h);
+}
+py::tuple vmm_import(int64_t fd, int64_t nbytes) {
+  void* ptr = nullptr; uint64_t h = 0;
+  TORCH_CHECK(pg_vmm_import((int)fd, nbytes, &ptr, &h) == 0, "vmm_import failed");
+  return py::make_tuple(reinterpret_cast<int64_t>(ptr), (int64_t)h);
+}
+void vmm_unmap(int64_t ptr, int64_t nbytes, int64_t handle) { pg_vmm_unmap(reinterpret_cast<void*>(ptr), nbytes, (uint64_t)handle); }
+py::tuple mc_create(int64_t world, int64_t nbytes) {
+  int fd = -1; uint64_t h = 0;
+  TORCH_CHECK(pg_mc_create((int)world, nbytes, &fd, &h) == 0, "mc_create failed");
+  return py::make_tuple(fd, (int64_t)h);
+}
+int64_t mc_import(int64_t fd) {
+  uint64_t h = 0;
+  TORCH_CHECK(pg_mc_import((int)fd, &h) == 0, "mc_import failed");
+  return (int64_t)h;
+}
+void mc_add_device(int64_t mc) { TORCH_CHECK(pg_mc_add_device((uint64_t)mc) == 0, "mc_add_device failed"); }
+int64_t mc_bind(int64_t mc, int64_t mem, int64_t nbytes) {
+  void* p = nullptr;
+  TORCH_CHECK(pg_mc_bind((uint64_t)mc, (uint64_t)mem, nbytes, &p) == 0, "mc_bind failed");
+  return reinterpret_cast<int64_t>(p);
 }
 
 void barrier_peers(std::vector<int64_t> peer_flags, int64_t rank, int64_t epoch) {
@@ -341,10 +433,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("colsum", &colsum);
-  m.def("embedding_bwd", &embedding_bwd);
+  m.def("embedding_bwd", &embedding_bwd, py::arg("dx"), py::arg("ids"), py::arg("dw"), py::arg("vocab_start"), py::arg("vocab_end"),
+        py::arg("grad_rs") = py::dict());
+  m.def("grad_rs_accum", &grad_rs_accum);
   m.def("ce_stats", &ce_stats);
   m.def("ce_finalize", &ce_finalize);
-  m.def("adam_step", &adam_step);
+  m.def("adam_step", &adam_step, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("grad"), py::arg("param_bf16"), py::arg("lr"),
+        py::arg("beta1"), py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale"), py::arg("adamw"),
+        py::arg("zero_grad") = false);
   m.def("sgd_step", &sgd_step);
   m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
   m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("slopes"), py::arg("out"), py::arg("lse"), py::arg("B"),
@@ -360,8 +456,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("rs_reduce", &rs_reduce);
   m.def("allreduce_f32", &allreduce_f32, py::arg("peer_bufs"), py::arg("rank"), py::arg("offset"), py::arg("n"),
-        py::arg("scale"), py::arg("rs_only"), py::arg("peer_flags"), py::arg("epoch"), py::arg("blocks") = 0);
+        py::arg("scale"), py::arg("rs_only"), py::arg("peer_flags"), py::arg("epoch"), py::arg("blocks") = 0, py::arg("mc_buf") = 0);
   m.def("set_gemm_cta_cap", [](int64_t n) { pg_set_gemm_cta_cap((int)n); });
-  m.def("allgather_bf16", &allgather_bf16);
+  m.def("allgather_bf16", &allgather_bf16, py::arg("peer_bufs"), py::arg("rank"), py::arg("bucket_elems"), py::arg("total_elems"),
+        py::arg("peer_flags"), py::arg("epoch"), py::arg("head_elems") = 0, py::arg("mc_buf") = 0);
+  m.def("multimem_selftest", &multimem_selftest);
+  m.def("rs_reduce_mc", &rs_reduce_mc);
+  m.def("vmm_probe", &vmm_probe);
+  m.def("vmm_alloc", &vmm_alloc);
+  m.def("vmm_import", &vmm_import);
+  m.def("vmm_unmap", &vmm_unmap);
+  m.def("mc_create", &mc_create);
+  m.def("mc_import", &mc_import);
+  m.def("mc_add_device", &mc_add_device);
+  m.def("mc_bind", &mc_bind);
   m.def("barrier_peers", &barrier_peers);
 }

@@ -20,9 +20,7 @@ __global__ void __launch_bounds__(256) rs_reduce_kernel(
     const uint32_t* __restrict__ arrive_ctr, uint32_t expected, const __nv_bfloat16* __restrict__ bias,
     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int rows, int cols) {
   if (threadIdx.x == 0) {
-    for (int s = 0; s < num_src; ++s)
-      while (ld_acquire_sys(arrive_ctr + s) < expected) {
-      }
+    for (int s = 0; s < num_src; ++s) spin_until_ge(arrive_ctr + s, expected, 10);
   }
   __syncthreads();
   const int64_t nvec = static_cast<int64_t>(rows) * cols / 8;
@@ -76,14 +74,13 @@ PG_DEVICE void peer_barrier(const PeerPtrs& p, int world, int rank, uint32_t val
   if (threadIdx.x < world) {
     fence_acq_rel_sys();
     st_release_sys(p.flag[threadIdx.x] + phase * PG_MAX_PEERS + rank, value);
-    while (ld_acquire_sys(p.flag[rank] + phase * PG_MAX_PEERS + threadIdx.x) < value) {
-    }
+    spin_until_ge(p.flag[rank] + phase * PG_MAX_PEERS + threadIdx.x, value, 11 + phase);
   }
 }
 
 // Two-shot all-reduce (average) of buf[offset : offset+n) in place on every rank.
 // grid-wide phases are separated by a device-wide counter (cooperative-free: all CTAs resident).
-__global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int world, int rank,
+__global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank,
                                                             int64_t offset, int64_t n, float scale,
                                                             int rs_only, uint32_t epoch,
                                                             uint32_t* __restrict__ grid_ctr) {
@@ -96,8 +93,7 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int worl
       __threadfence();
       atomicExch(grid_ctr, epoch);
     } else {
-      while (ld_acquire_sys(grid_ctr) < epoch) {
-      }
+      spin_until_ge(grid_ctr, epoch, 13);
     }
   }
   __syncthreads();
@@ -108,6 +104,30 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, int worl
   // peer are issued before any is consumed (NVLink latency ~2 us: bytes in flight, not threads, set the rate)
   constexpr int kU = 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if (mc != nullptr) {
+    // NVLS: ONE multimem.ld_reduce per 16 bytes returns the sum over all replicas (reduced inside the NVSwitch, 1/world
+    // of the bytes of a pull from every peer cross this GPU's links); the all-gather half is ONE multimem.st
+    for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        v[u] = (i < nvec) ? multimem_ld_reduce_add_v4_f32(mc + my0 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i >= nvec) continue;
+        float4 r = v[u];
+        r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+        if (rs_only) {
+          *reinterpret_cast<float4*>(p.buf[rank] + my0 + i * 4) = r;
+        } else {
+          multimem_st_v4_f32(mc + my0 + i * 4, r);
+        }
+      }
+    }
+  } else
   for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kU) {
     float4 acc[kU];
 #pragma unroll
@@ -164,14 +184,16 @@ struct PeerPtrsBf16 {
   uint32_t* flag[PG_MAX_PEERS];
 };
 
-// push my slice of every bucket of the flat bf16 parameter buffer to all peers
-__global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int world, int rank,
-                                                             int64_t bucket_elems, int64_t total_elems,
-                                                             uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
-  const int64_t nb = (total_elems + bucket_elems - 1) / bucket_elems;
-  for (int64_t b = 0; b < nb; ++b) {
-    const int64_t start = b * bucket_elems;
-    const int64_t len = min(bucket_elems, total_elems - start);
+// push my slice of every region of the flat bf16 parameter buffer to all peers.  Regions: [0, head) and then
+// [head + k*bucket, head + (k+1)*bucket) up to total; a region of length len is owned slice-wise (len / world each)
+__global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, __nv_bfloat16* __restrict__ mc, int world,
+                                                             int rank, int64_t head_elems, int64_t bucket_elems,
+                                                             int64_t total_elems, uint32_t epoch,
+                                                             uint32_t* __restrict__ grid_ctr) {
+  const int64_t nb = (total_elems - head_elems + bucket_elems - 1) / bucket_elems;
+  for (int64_t b = (head_elems > 0 ? -1 : 0); b < nb; ++b) {
+    const int64_t start = b < 0 ? 0 : head_elems + b * bucket_elems;
+    const int64_t len = b < 0 ? head_elems : min(bucket_elems, total_elems - start);
     const int64_t seg = len / world;
     const int64_t my0 = start + rank * seg;
     const int64_t nvec = seg / 8;
@@ -183,6 +205,15 @@ __global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int
       for (int u = 0; u < kU; ++u) {
         const int64_t i = i0 + u * stride;
         v[u] = (i < nvec) ? ld_global_v4(p.buf[rank] + my0 + i * 8) : make_uint4(0, 0, 0, 0);
+      }
+      if (mc != nullptr) {
+        // NVLS: one store, the switch writes every replica (this rank's own copy included: same value)
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int64_t i = i0 + u * stride;
+          if (i < nvec) multimem_st_v4_b32(mc + my0 + i * 8, v[u]);
+        }
+        continue;
       }
 #pragma unroll 1
       for (int s = 1; s < world; ++s) {
@@ -209,6 +240,66 @@ __global__ void __launch_bounds__(512) allgather_bf16_kernel(PeerPtrsBf16 p, int
     PeerPtrs q;
     for (int i = 0; i < PG_MAX_PEERS; ++i) q.flag[i] = p.flag[i];
     peer_barrier(q, world, rank, epoch, 1);
+  }
+}
+
+// NVLS self-test: out[i] = sum over replicas of in[i] (multimem.ld_reduce), then mc_out[i] = that (multimem.st)
+__global__ void multimem_selftest_kernel(const float* __restrict__ mc_in, float* __restrict__ mc_out, float* __restrict__ out,
+                                         int64_t nvec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = multimem_ld_reduce_add_v4_f32(mc_in + i * 4);
+    *reinterpret_cast<float4*>(out + i * 4) = v;
+    if (mc_out != nullptr) multimem_st_v4_f32(mc_out + i * 4, v);
+  }
+}
+
+// GEMM -> reduce-scatter, NVLS form: every rank keeps its partial product [T * rows, cols] in its own symmetric
+// buffer; rank r sums rows [r * rows, (r+1) * rows) of all replicas with multimem.ld_reduce (bf16x2, fp32 accumulation
+// inside the switch) once every source's tiles of that block are complete (+ bias + residual)
+__global__ void __launch_bounds__(256) rs_reduce_mc_kernel(
+    const __nv_bfloat16* __restrict__ mc_partial, const uint32_t* __restrict__ arrive_ctr, int num_src, uint32_t expected,
+    const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+    int rows, int cols) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_src; ++s) spin_until_ge(arrive_ctr + s, expected, 14);
+  }
+  __syncthreads();
+  const int64_t nvec = static_cast<int64_t>(rows) * cols / 8;
+  const int cvec = cols / 8;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = multimem_ld_reduce_add_v4_bf16x2(mc_partial + i * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      acc[2 * j] = f.x;
+      acc[2 * j + 1] = f.y;
+    }
+    if (bias != nullptr) {
+      const uint4 b = ld_global_nc_v4(bias + (i % cvec) * 8);
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(bw[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    if (residual != nullptr) {
+      const uint4 r = ld_global_nc_v4(residual + i * 8);
+      const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(rw[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    st_global_v4(out + i * 8, make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                         pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7])));
   }
 }
 
@@ -245,7 +336,7 @@ extern "C" int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride
 }
 
 // grid_ctr: two uint32 in LOCAL memory right after the flag area: peer_flags[rank] + 2*PG_MAX_PEERS
-extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems,
+extern "C" int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int world, int rank, int64_t offset_elems,
                                 int64_t n, float scale, int reduce_scatter_only,
                                 uint32_t* const* peer_flags, uint32_t epoch, int blocks, cudaStream_t s) {
   if (n == 0) return 0;
@@ -259,18 +350,17 @@ extern "C" int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, in
   // overlapped with backward: a handful of CTAs on the SMs the persistent GEMMs leave free (pg_set_gemm_cta_cap);
   // after backward (nothing else runs): enough CTAs to keep ~3 MB in flight over NVLink
   if (blocks <= 0) blocks = 24;
-  allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, world, rank, offset_elems, n, scale,
+  allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, scale,
                                               reduce_scatter_only, epoch,
                                               peer_flags[rank] + 2 * PG_MAX_PEERS);
   PG_CHECK_LAUNCH("allreduce_f32");
   return 0;
 }
 
-extern "C" int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, int64_t offset_elems,
-                                 int64_t n_per_rank, int64_t bucket_elems, int64_t total_elems,
+extern "C" int pg_allgather_bf16(void* const* peer_bufs, void* mc_buf, int world, int rank, int64_t head_elems,
+                                 int64_t bucket_elems, int64_t total_elems,
                                  uint32_t* const* peer_flags, uint32_t epoch, cudaStream_t s) {
-  (void)offset_elems;
-  (void)n_per_rank;
+  if (bucket_elems <= 0 || head_elems % (world * 8) != 0) return -1;
   PeerPtrsBf16 p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < world; ++i) {
@@ -278,9 +368,30 @@ extern "C" int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, in
     p.flag[i] = peer_flags[i];
   }
   const int blocks = 32;
-  allgather_bf16_kernel<<<blocks, 512, 0, s>>>(p, world, rank, bucket_elems, total_elems, epoch,
-                                               peer_flags[rank] + 2 * PG_MAX_PEERS);
+  allgather_bf16_kernel<<<blocks, 512, 0, s>>>(p, (__nv_bfloat16*)mc_buf, world, rank, head_elems, bucket_elems,
+                                               total_elems, epoch, peer_flags[rank] + 2 * PG_MAX_PEERS);
   PG_CHECK_LAUNCH("allgather_bf16");
+  return 0;
+}
+
+extern "C" int pg_multimem_selftest(const float* mc_in, float* mc_out, float* out, int64_t n, cudaStream_t s) {
+  if (n % 4 != 0) return -1;
+  multimem_selftest_kernel<<<64, 256, 0, s>>>(mc_in, mc_out, out, n / 4);
+  PG_CHECK_LAUNCH("multimem_selftest");
+  return 0;
+}
+
+extern "C" int pg_rs_reduce_mc(const void* mc_partial, const uint32_t* arrive_ctr, int num_src, uint32_t expected,
+                               const void* bias, const void* residual, void* out, int rows, int cols, cudaStream_t s) {
+  if (rows == 0) return 0;
+  if (cols % 8 != 0) return -1;
+  const int64_t nvec = static_cast<int64_t>(rows) * cols / 8;
+  int blocks = static_cast<int>((nvec + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rs_reduce_mc_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)mc_partial, arrive_ctr, num_src, expected,
+                                             (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual,
+                                             (__nv_bfloat16*)out, rows, cols);
+  PG_CHECK_LAUNCH("rs_reduce_mc");
   return 0;
 }
 

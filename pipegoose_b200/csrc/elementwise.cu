@@ -2,10 +2,12 @@
 // embedding gather), bias-gradient column sums, embedding backward, vocab-parallel
 // cross-entropy (stats / finalize+dlogits), fused Adam on flat fp32 shards, grad utilities.
 // All bf16 I/O is 16-byte vectorised; statistics and accumulation are fp32.
+#include "grad_rs.cuh"
 #include "launch.h"
 #include "pdl_launch.cuh"
 #include "ptx.cuh"
 #include <cstdio>
+#include <cstring>
 
 namespace pg {
 
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx,
                                                             const int64_t* __restrict__ ids,
                                                             float* __restrict__ dw, int rows, int h,
-                                                            int vocab_start, int vocab_end) {
+                                                            int vocab_start, int vocab_end, const PgGradRS grs) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -283,12 +285,42 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const __nv_bfloat16*
   for (int c = lane; c < (h >> 3); c += 32) {
     const uint4 v = ld_global_nc_v4(src + c * 8);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (grs.world > 1) {
+      // data-parallel reduce-scatter fused into the scatter-add: the row goes to the owner of its ZeRO-1 slice
+      const float2 a = unpack_bf16x2(w[0]), b = unpack_bf16x2(w[1]), c2 = unpack_bf16x2(w[2]), d = unpack_bf16x2(w[3]);
+      grs_add4(grs, dst + c * 8, make_float4(a.x, a.y, b.x, b.y));
+      grs_add4(grs, dst + c * 8 + 4, make_float4(c2.x, c2.y, d.x, d.y));
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(w[j]);
       atomicAdd(dst + c * 8 + 2 * j, f.x);
       atomicAdd(dst + c * 8 + 2 * j + 1, f.y);
     }
+  }
+}
+
+// dst_local[i] += scale * src[i], added into the buffers of the ranks that own the ZeRO-1 slices (see PgGradRS):
+// gradients that autograd delivered (or any torch-side gradient) join the in-kernel reduce-scatter here
+template <bool SRC_F32>
+__global__ void __launch_bounds__(256) grad_rs_accum_kernel(const void* __restrict__ src_, float* __restrict__ dst_local,
+                                                            int64_t n, float scale, const PgGradRS grs) {
+  const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  const int cnt = (n - i4) < 4 ? static_cast<int>(n - i4) : 4;
+  if (SRC_F32) {
+    const float* src = reinterpret_cast<const float*>(src_);
+    for (int j = 0; j < cnt; ++j) f[j] = src[i4 + j] * scale;
+  } else {
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(src_);
+    for (int j = 0; j < cnt; ++j) f[j] = __bfloat162float(src[i4 + j]) * scale;
+  }
+  if (cnt == 4) {
+    grs_add4(grs, dst_local + i4, make_float4(f[0], f[1], f[2], f[3]));
+  } else {
+    for (int j = 0; j < cnt; ++j) red_add_f32(grs_target(grs, dst_local + i4 + j), f[j]);
   }
 }
 
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ master,
                                                    __nv_bfloat16* __restrict__ param_bf16, int64_t n,
                                                    float lr, float beta1, float beta2, float eps,
                                                    float weight_decay, float bc1, float bc2,
-                                                   float grad_scale, int adamw) {
+                                                   float grad_scale, int adamw, int zero_grad) {
   const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
   if (i4 + 4 <= n) {
@@ -412,6 +444,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ master,
     float4 m = *reinterpret_cast<float4*>(exp_avg + i4);
     float4 v = *reinterpret_cast<float4*>(exp_avg_sq + i4);
     const float4 g4 = *reinterpret_cast<const float4*>(grad + i4);
+    // in-kernel gradient reduce-scatter: the owner clears its slice right after consuming it, so that the peers'
+    // next red.global.add contributions start from zero (no separate memset pass over the gradients)
+    if (zero_grad) *reinterpret_cast<float4*>(const_cast<float*>(grad) + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
     float pp[4] = {p.x, p.y, p.z, p.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
     const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -444,6 +479,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ master,
       exp_avg[i] = m;
       exp_avg_sq[i] = v;
       if (param_bf16) param_bf16[i] = __float2bfloat16(p);
+      if (zero_grad) const_cast<float*>(grad)[i] = 0.f;
     }
   }
 }
@@ -581,11 +617,29 @@ extern "C" int pg_colsum(const void* x, int ld, float* out, int rows, int cols, 
 }
 
 extern "C" int pg_embedding_bwd(const void* dx, const int64_t* ids, float* dw, int rows, int h,
-                                int vocab_start, int vocab_end, cudaStream_t s) {
+                                int vocab_start, int vocab_end, const PgGradRS* grad_rs, cudaStream_t s) {
   if (rows == 0) return 0;
+  PgGradRS grs;
+  memset(&grs, 0, sizeof(grs));
+  if (grad_rs != nullptr) grs = *grad_rs;
   embedding_bwd_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>((const __nv_bfloat16*)dx, ids, dw,
-                                                               rows, h, vocab_start, vocab_end);
+                                                               rows, h, vocab_start, vocab_end, grs);
   PG_CHECK_LAUNCH("embedding_bwd");
+  return 0;
+}
+
+extern "C" int pg_grad_rs_accum(const void* src, int src_is_f32, float* dst_local, int64_t n, float scale,
+                                const PgGradRS* grad_rs, cudaStream_t s) {
+  if (n == 0) return 0;
+  if (grad_rs == nullptr || grad_rs->world <= 1) return -1;
+  const int64_t threads = (n + 3) / 4;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (src_is_f32) {
+    grad_rs_accum_kernel<true><<<blocks, 256, 0, s>>>(src, dst_local, n, scale, *grad_rs);
+  } else {
+    grad_rs_accum_kernel<false><<<blocks, 256, 0, s>>>(src, dst_local, n, scale, *grad_rs);
+  }
+  PG_CHECK_LAUNCH("grad_rs_accum");
   return 0;
 }
 
@@ -612,12 +666,12 @@ extern "C" int pg_ce_finalize(void* logits, int ld, const int64_t* targets, cons
 
 extern "C" int pg_adam(float* master, float* m, float* v, const float* grad, void* param_bf16,
                        int64_t n, float lr, float beta1, float beta2, float eps, float wd,
-                       float bc1, float bc2, float grad_scale, int adamw, cudaStream_t s) {
+                       float bc1, float bc2, float grad_scale, int adamw, int zero_grad, cudaStream_t s) {
   if (n == 0) return 0;
   const int64_t threads = (n + 3) / 4;
   adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
       master, m, v, grad, (__nv_bfloat16*)param_bf16, n, lr, beta1, beta2, eps, wd, bc1, bc2,
-      grad_scale, adamw);
+      grad_scale, adamw, zero_grad);
   PG_CHECK_LAUNCH("adam");
   return 0;
 }

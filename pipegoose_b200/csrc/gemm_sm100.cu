@@ -238,6 +238,14 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   }
   args.rs_wait_ctr = d->rs_wait_ctr;
   args.rs_wait_value = d->rs_wait_value;
+  args.grad_rs = d->grad_rs;
+  if (args.grad_rs.world > 1) {
+    if (!(d->flags & EPI_OUT_F32) || args.num_chunks > 1 || (d->ldc % 4) != 0) {
+      fprintf(stderr, "pipegoose_b200: gradient reduce-scatter epilogue needs a plain fp32 output with ldc %% 4 == 0\n");
+      return -1;
+    }
+    args.flags |= EPI_ACCUM;  // contributions are ADDED into the owners' buffers (zeroed by the optimizer step)
+  }
   args.b_chunk_rows = d->b_chunk_rows;
   args.bias_chunk_stride = d->bias_chunk_stride;
   args.row_ret = d->row_ret;

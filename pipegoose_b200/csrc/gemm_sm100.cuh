@@ -17,6 +17,7 @@
 // The epilogue applies bias / tanh-GELU (also emitting the pre-activation) /
 // GELU-backward / residual add / fp32 accumulate, so none of those is a separate pass.
 #pragma once
+#include "grad_rs.cuh"
 #include "ptx.cuh"
 
 namespace pg {
@@ -81,6 +82,9 @@ struct GemmArgs {
   const __nv_bfloat16* rs_in[kMaxPeers];  // local staging slot of source s (rs_in[my_rank] unused); null = off
   const uint32_t* rs_wait_ctr;            // local arrival counters, one per source
   uint32_t rs_wait_value;
+  // wgrad -> data-parallel reduce-scatter (fp32 outputs): every 16-byte group of the tile is added into the gradient
+  // buffer of the rank that owns its ZeRO-1 slice (local L2 atomics / NVLink peer atomics); grad_rs.world <= 1: off
+  PgGradRS grad_rs;
 };
 
 constexpr int BM = 128;
@@ -217,8 +221,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         int src = args.my_rank + i;
         if (src >= args.num_chunks) src -= args.num_chunks;
         if (src != args.my_rank) {
-          while (ld_acquire_sys(args.ag_ready + src) < args.ag_epoch) {
-          }
+          spin_until_ge(args.ag_ready + src, args.ag_epoch, 1);
         }
         const uint8_t* from = reinterpret_cast<const uint8_t*>(args.ag_src[src]);
         uint8_t* to = reinterpret_cast<uint8_t*>(args.ag_dst) + static_cast<uint64_t>(src) * args.ag_chunk_bytes;
@@ -295,8 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const int kb_end = min(num_kb, kb_begin + kb_per_split);
       if (args.chunk_flags != nullptr && tc.chunk != seen_chunk && tc.chunk != args.a_local_chunk) {
         if (lane == 0) {
-          while (ld_acquire_sys(args.chunk_flags + tc.chunk) < args.flag_value) {
-          }
+          spin_until_ge(args.chunk_flags + tc.chunk, args.flag_value, 2);
           fence_proxy_async_global();
         }
         __syncwarp();
@@ -463,9 +465,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           // peers computed my chunk FIRST; by the time I reach it their tiles have normally landed
           if (lane == 0) {
             for (int s2 = 0; s2 < args.num_chunks; ++s2)
-              if (s2 != args.my_rank)
-                while (ld_acquire_sys(args.rs_wait_ctr + s2) < args.rs_wait_value) {
-                }
+              if (s2 != args.my_rank) spin_until_ge(args.rs_wait_ctr + s2, args.rs_wait_value, 3);
           }
           __syncwarp();
           rs_ready = true;
@@ -532,6 +532,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         if (out_f32) {
           // fp32 output (wgrad into the main-grad buffer): each thread owns a full 128-byte line
+          if (active && args.grad_rs.world > 1) {
+            // gradient reduce-scatter fused into the wgrad: the line goes to the owner of its ZeRO-1 slice
+            const float* o = reinterpret_cast<const float*>(out_base) + static_cast<size_t>(out_row) * args.ldc + col0;
+            const long long off = (o - args.grad_rs.local) - args.grad_rs.start;
+            const long long own0 = off / args.grad_rs.seg;
+            const bool one_owner = off - own0 * args.grad_rs.seg + 32 <= args.grad_rs.seg;
+            float* t0 = grs_target(args.grad_rs, o);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g * 4 < ncols) {
+                const float4 val = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                grs_add4_at(args.grad_rs, one_owner ? t0 + g * 4 : grs_target(args.grad_rs, o + g * 4), val);
+              }
+            }
+            continue;
+          }
           if (active) {
             float* o = reinterpret_cast<float*>(out_base) + static_cast<size_t>(out_row) * args.ldc + col0;
 #pragma unroll

@@ -10,6 +10,20 @@ extern "C" {
 
 #define PG_MAX_PEERS 8
 
+// In-kernel data-parallel gradient reduce-scatter (ZeRO-1): the flat fp32 gradient buffer of every data-parallel rank is
+// peer-mapped; elements [start, start + world * seg) are owned slice-wise (rank r owns [start + r*seg, start + (r+1)*seg)).
+// A kernel that produces a gradient (wgrad GEMM epilogue, embedding backward, gradient fold) adds it with
+// red.global.add straight into the OWNER's buffer — no local copy, no separate reduction kernel, nothing exposed
+// after backward except one peer barrier.  world <= 1: plain local accumulation.
+typedef struct PgGradRS {
+  float* peer[PG_MAX_PEERS];  // flat gradient buffer of data-parallel rank r (peer[my rank] is the local buffer)
+  const float* local;         // this rank's flat gradient buffer (gradient pointers handed to kernels point into it)
+  long long start;            // first element of the in-kernel reduce-scatter region
+  long long seg;              // elements per owner slice (multiple of 4)
+  int world;
+  int scalar_red;             // 1: four scalar red.global.add.f32 instead of one red.global.add.v4.f32
+} PgGradRS;
+
 typedef struct PgGemmDesc {
   const void* A;  // bf16
   const void* B;  // bf16
@@ -52,6 +66,8 @@ typedef struct PgGemmDesc {
   const int* row_ret;
   const float* row_scale;
   int scatter_rows_per_src;
+  // fp32 output (wgrad): add the tile into the owners' gradient buffers (see PgGradRS); world <= 1: off
+  PgGradRS grad_rs;
 } PgGemmDesc;
 
 // ---- attention_sm100.cu
@@ -78,13 +94,30 @@ int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride_elems, con
                  uint32_t expected, const void* bias, const void* residual, void* out, int rows, int cols,
                  cudaStream_t s);
 // flat fp32 gradient bucket: in-place all-reduce / reduce-scatter average over NVLink peers
-int pg_allreduce_f32(float* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n,
+// mc_buf != null: the reduce half is ONE multimem.ld_reduce per 16 bytes (summed inside the NVSwitch), the all-gather
+// half ONE multimem.st
+int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int world, int rank, int64_t offset_elems, int64_t n,
                      float scale, int reduce_scatter_only, uint32_t* const* peer_flags, uint32_t epoch,
                      int blocks, cudaStream_t s);
-int pg_allgather_bf16(void* const* peer_bufs, int world, int rank, int64_t offset_elems, int64_t n_per_rank,
+// ZeRO-1 parameter all-gather: regions [0, head) and then [head + k*bucket, ...) up to total; every rank pushes its
+// 1/world slice of each region to all peers (mc_buf != null: ONE multimem.st per 16 bytes through the NVSwitch)
+int pg_allgather_bf16(void* const* peer_bufs, void* mc_buf, int world, int rank, int64_t head_elems,
                       int64_t bucket_elems, int64_t total_elems, uint32_t* const* peer_flags, uint32_t epoch,
                       cudaStream_t s);
 int pg_barrier_peers(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, cudaStream_t s);
+// NVLS
+int pg_multimem_selftest(const float* mc_in, float* mc_out, float* out, int64_t n, cudaStream_t s);
+int pg_rs_reduce_mc(const void* mc_partial, const uint32_t* arrive_ctr, int num_src, uint32_t expected, const void* bias,
+                    const void* residual, void* out, int rows, int cols, cudaStream_t s);
+// symmetric memory (VMM + multicast; symm_vmm.cu)
+int pg_vmm_probe(int world, int* mc_supported, int64_t* gran);
+int pg_vmm_alloc(int64_t nbytes, void** ptr, int* fd, uint64_t* handle);
+int pg_vmm_import(int fd, int64_t nbytes, void** ptr, uint64_t* handle);
+int pg_vmm_unmap(void* ptr, int64_t nbytes, uint64_t handle);
+int pg_mc_create(int world, int64_t nbytes, int* fd, uint64_t* mc_handle);
+int pg_mc_import(int fd, uint64_t* mc_handle);
+int pg_mc_add_device(uint64_t mc_handle);
+int pg_mc_bind(uint64_t mc_handle, uint64_t mem_handle, int64_t nbytes, void** mc_ptr);
 // symmetric memory (cudaIpc)
 int pg_symm_alloc(int64_t nbytes, void** ptr, void* handle64);
 int pg_symm_open(const void* handle64, void** ptr);
@@ -104,7 +137,10 @@ int pg_layernorm_bwd(const void* dy, const void* x, const void* gamma, const flo
                      int rows, int h, cudaStream_t s);
 int pg_colsum(const void* x, int ld, float* out, int rows, int cols, cudaStream_t s);
 int pg_embedding_bwd(const void* dx, const int64_t* ids, float* dw, int rows, int h,
-                     int vocab_start, int vocab_end, cudaStream_t s);
+                     int vocab_start, int vocab_end, const PgGradRS* grad_rs, cudaStream_t s);
+// dst (a range of the local flat gradient buffer) += scale * src, added into the owners' buffers (src: bf16 or fp32)
+int pg_grad_rs_accum(const void* src, int src_is_f32, float* dst_local, int64_t n, float scale,
+                     const PgGradRS* grad_rs, cudaStream_t s);
 int pg_ce_stats(const void* logits, int ld, const int64_t* targets, float* stats, int rows,
                 int vocab_local, int vocab_start, cudaStream_t s);
 int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gstats,
@@ -112,7 +148,7 @@ int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gs
                    const float* grad_scale, int64_t ignore_index, int write_grad, cudaStream_t s);
 int pg_adam(float* master, float* m, float* v, const float* grad, void* param_bf16, int64_t n,
             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-            float grad_scale, int adamw, cudaStream_t s);
+            float grad_scale, int adamw, int zero_grad, cudaStream_t s);
 int pg_sgd(float* master, float* mom, const float* grad, void* param_bf16, int64_t n, float lr,
            float momentum, float wd, float grad_scale, int first_step, cudaStream_t s);
 int pg_accum_bf16_to_f32(const void* src, float* dst, int64_t n, float scale, int accumulate,

@@ -3,6 +3,7 @@
 // system-scope acquire/release flag traffic for cross-GPU protocols, and vector
 // global loads/stores.  No CUTLASS dependency: the bit layouts follow the PTX ISA.
 #pragma once
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -326,6 +327,26 @@ PG_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 PG_DEVICE void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Bounded spin on a monotonic flag / counter written by another CTA or another GPU (system-scope acquire).  A flag
+// that never arrives (a peer that died, a protocol bug) must not hang the node silently: after ~30 s of SM clocks
+// the waiting thread prints where it waited and what it saw, and traps — the host sees a launch failure with a
+// diagnostic instead of a wedged GPU.  `site` identifies the wait in the source (see the table in DESIGN.md).
+#ifndef PG_SPIN_BUDGET_CYCLES
+#define PG_SPIN_BUDGET_CYCLES 60000000000ll
+#endif
+PG_DEVICE void spin_until_ge(const uint32_t* p, uint32_t want, int site) {
+  if (ld_acquire_sys(p) >= want) return;
+  const long long t0 = clock64();
+  uint32_t seen;
+  while ((seen = ld_acquire_sys(p)) < want) {
+    if (clock64() - t0 > PG_SPIN_BUDGET_CYCLES) {
+      printf("pipegoose_b200: spin timeout at site %d: flag %p holds %u, waiting for >= %u (block %d thread %d)\n", site,
+             (const void*)p, seen, want, (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
 // generic-proxy writes (peer flags / data) -> later async-proxy (TMA) reads of global memory
 PG_DEVICE void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -372,6 +393,41 @@ PG_DEVICE void red_add_v4_f32(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+
+// ----------------------------------------------------------------------------------
+// NVLS: loads / stores on a multicast address are executed by the NVSwitch on every replica bound to the multicast
+// object — ld_reduce returns the SUM over the replicas (reduced inside the switch: one response crosses the link
+// instead of one per peer), st writes all replicas with one request.
+// ----------------------------------------------------------------------------------
+PG_DEVICE float4 multimem_ld_reduce_add_v4_f32(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+PG_DEVICE void multimem_st_v4_f32(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+// eight bf16 values summed over the replicas with fp32 accumulation inside the switch
+PG_DEVICE uint4 multimem_ld_reduce_add_v4_bf16x2(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+PG_DEVICE void multimem_st_v4_b32(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+PG_DEVICE void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 PG_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

@@ -259,8 +259,63 @@ class FusedDPEngine:
         grad = self.ws.local_tensor(self._grad_off, (numel,), torch.float32)
         param = self.ws.local_tensor(self._param_off, (numel,), torch.bfloat16)
         self._grad_base = grad.data_ptr()
+        self._grad = grad
         self.numel = numel
+        self.inline_start = None     # first element of the in-kernel reduce-scatter region (None: off)
+        self.inline_dirty = False    # a kernel added gradients into the region since the owners last cleared it
+        # NVLS (multicast object bound to the workspace): reduce with multimem.ld_reduce, all-gather with multimem.st
+        self._mc_grad = self.ws.mc_data_ptr(self._grad_off) if self.NVLS_REDUCE else 0
+        self._mc_param = self.ws.mc_data_ptr(self._param_off) if self.NVLS_ALLGATHER else 0
         return param, grad
+
+    NVLS_REDUCE = os.environ.get("PIPEGOOSE_B200_NVLS_REDUCE", "1") == "1"
+    NVLS_ALLGATHER = os.environ.get("PIPEGOOSE_B200_NVLS_ALLGATHER", "1") == "1"
+    # 0: never reduce-scatter gradients inside the kernels that produce them (bucketed reducer for everything)
+    INLINE_RS = os.environ.get("PIPEGOOSE_B200_DP_INLINE_RS", "1") == "1"
+    # 1: four scalar red.global.add.f32 per 16 bytes instead of one red.global.add.v4.f32 (diagnosis)
+    INLINE_SCALAR_RED = os.environ.get("PIPEGOOSE_B200_DP_INLINE_SCALAR", "0") == "1"
+
+    # ------------------------------------------------------------------ in-kernel gradient reduce-scatter (ZeRO-1)
+    def enable_inline(self, start: int) -> bool:
+        """Gradients of flat elements [start, numel) are from now on added by the kernels that produce them (wgrad GEMM
+        epilogue, embedding backward, gradient folds) straight into the buffer of the rank owning their ZeRO-1 slice
+        (``red.global.add`` over NVLink): no bucket reduction, nothing exposed after backward but one peer barrier."""
+        if not self.INLINE_RS or self.world < 2 or start >= self.numel:
+            return False
+        n = self.numel - start
+        assert n % (self.world * 4) == 0 and start % 4 == 0
+        self.inline_start = start
+        self.inline_seg = n // self.world
+        desc = {"peer": [self.ws.data_ptr(p, self._grad_off) for p in range(self.world)],
+                "local": self.ws.data_ptr(self.rank, self._grad_off), "start": start, "seg": self.inline_seg,
+                "scalar": 1 if self.INLINE_SCALAR_RED else 0}
+        K.register_grad_rs(self._grad_base + start * 4, self._grad_base + self.numel * 4, desc, self)
+        self._grad[start:].zero_()
+        self.barrier()
+        return True
+
+    def barrier(self):
+        """Peer barrier on the current stream: what every rank of the group enqueued before it (gradient adds into my
+        buffer included) is complete and visible to what I enqueue after it."""
+        self.epoch += 1
+        native().barrier_peers(self._flag_ptrs(), self.rank, self.epoch)
+
+    def clear_inline_region(self, force: bool = False):
+        """``zero_grad`` of the in-kernel region when its gradients were produced but not consumed by an optimizer step
+        (the step clears the owner slices while it reads them).  Collective: peers may not add before everyone cleared."""
+        if self.inline_start is None or not (self.inline_dirty or force):
+            return
+        self.barrier()                      # nobody is still adding into my buffer ...
+        self._grad[self.inline_start:].zero_()
+        self.barrier()                      # ... and nobody starts before every buffer is clear
+        self.inline_dirty = False
+
+    def inline_consumed(self):
+        self.inline_dirty = False
+
+    def close_inline(self):
+        K.unregister_grad_rs(self)
+        self.inline_start = None
 
     def _flag_ptrs(self):
         return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
@@ -294,12 +349,14 @@ class FusedDPEngine:
             self.stream.wait_event(ready)
             native().allreduce_f32([self.ws.data_ptr(p, self._grad_off) for p in range(self.world)], self.rank,
                                    offset, n, 1.0 / self.world, mode == "reduce_scatter", self._flag_ptrs(), self.epoch,
-                                   self.TAIL_CTAS if tail else self.OVERLAP_CTAS)
+                                   self.TAIL_CTAS if tail else self.OVERLAP_CTAS, self._mc_grad)
             done = torch.cuda.Event()
             done.record()
         return _StreamWork(done)
 
-    def all_gather_params(self, flat_param: torch.Tensor, bucket_numel: int):
+    def all_gather_params(self, flat_param: torch.Tensor, bucket_numel: int, head: int = 0):
+        """Regions [0, head) and [head + k * bucket_numel, ...): every rank pushes its 1/world slice of each region to all
+        peers — with NVLS one ``multimem.st`` per 16 bytes (the switch replicates), else one store per peer."""
         self.epoch += 1
         native().allgather_bf16([self.ws.data_ptr(p, self._param_off) for p in range(self.world)], self.rank,
-                                bucket_numel, flat_param.numel(), self._flag_ptrs(), self.epoch)
+                                bucket_numel, flat_param.numel(), self._flag_ptrs(), self.epoch, head, self._mc_param)

@@ -412,7 +412,7 @@ class EmbeddingPositions(torch.autograd.Function):
         mg_pos = _main_grad(positions)
         if mg_pos is not None:
             acc, accumulate = acquire_main_grad(positions, will_overwrite=True)
-            acc.add_(dpos) if accumulate else acc.copy_(dpos)
+            K.accumulate_grad(dpos, acc, accumulate)   # (goes through the in-kernel reduce-scatter when acc is in one)
             notify_grad_ready(positions)
             dpos = None
         else:

@@ -16,6 +16,35 @@ from pipegoose_b200.ops import native, use_native
 EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_OUT_F32, EPI_ACCUM, EPI_DGELU, EPI_SCATTER = 1, 2, 4, 8, 16, 32, 64
 
 
+# ----------------------------------------------------------------------------------------------
+# in-kernel data-parallel gradient reduce-scatter (ZeRO-1): address ranges of flat fp32 gradient buffers whose
+# contributions are added straight into the OWNER rank's buffer by the producing kernel (csrc/grad_rs.cuh).  Every
+# gradient writer below looks its destination up here, so a writer can never bypass the reduction by accident.
+# ----------------------------------------------------------------------------------------------
+_GRAD_RS_REGIONS = []   # [(first byte, end byte, descriptor dict for the kernels, engine)]
+
+
+def register_grad_rs(begin: int, end: int, desc: dict, engine) -> None:
+    unregister_grad_rs(engine)
+    _GRAD_RS_REGIONS.append((begin, end, desc, engine))
+
+
+def unregister_grad_rs(engine) -> None:
+    _GRAD_RS_REGIONS[:] = [r for r in _GRAD_RS_REGIONS if r[3] is not engine]
+
+
+def grad_rs_for(t: Optional[torch.Tensor]):
+    """The reduce-scatter descriptor if ``t`` (a view of a flat gradient buffer) lies in a registered region."""
+    if not _GRAD_RS_REGIONS or t is None or not t.is_cuda:
+        return None
+    ptr = t.data_ptr()
+    for begin, end, desc, engine in _GRAD_RS_REGIONS:
+        if begin <= ptr < end:
+            engine.inline_dirty = True
+            return desc
+    return None
+
+
 def gelu_tanh(x: torch.Tensor) -> torch.Tensor:
     """Bloom's GELU (tanh approximation; transformers BloomGelu)."""
     return x * 0.5 * (1.0 + torch.tanh(0.79788456 * x * (1.0 + 0.044715 * x * x)))
@@ -77,6 +106,12 @@ def gemm_tn(dy, x, accum_into: Optional[torch.Tensor] = None, accumulate: bool =
     if use_native(dy, x):
         N, K = dy.shape[1], x.shape[1]
         if accum_into is not None:
+            rs = grad_rs_for(accum_into)
+            if rs is not None:
+                # wgrad -> reduce-scatter in one kernel: the epilogue adds every tile into its owner's gradient buffer
+                kw = dict(kw)
+                kw["ag"] = dict(kw.get("ag") or {}, grad_rs=rs)
+                accumulate = True
             native().gemm(dy, x, accum_into.view(N, K), True, True, None, None, None,
                           EPI_ACCUM if accumulate else 0, **kw)
             return None
@@ -111,6 +146,12 @@ def colsum(dy, accum_into: Optional[torch.Tensor] = None):
 
 def accumulate_grad(grad, main_grad, accumulate: bool = True, scale: float = 1.0):
     """``main_grad (+)= scale * grad``: cast (bf16 -> fp32), scale and accumulate in one pass."""
+    rs = grad_rs_for(main_grad)
+    if rs is not None:
+        # the destination is reduce-scattered in-kernel: the contribution goes to the owners of its slices
+        src = grad if grad.dtype in (torch.bfloat16, torch.float32) else grad.float()
+        native().grad_rs_accum(src.contiguous().view(-1), main_grad.view(-1), scale, rs)
+        return
     if use_native(grad) and main_grad.dtype == torch.float32 and grad.is_contiguous():
         native().accum_bf16_to_f32(grad, main_grad, scale, accumulate)
         return
@@ -184,7 +225,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_extra=None, dgamma_acc=None, dbet
 def embedding_bwd(dx, ids, vocab_rows, vocab_start, vocab_end, accum_into=None):
     if use_native(dx):
         tgt = accum_into if accum_into is not None else torch.zeros(vocab_rows, dx.shape[-1], dtype=torch.float32, device=dx.device)
-        native().embedding_bwd(dx, ids.reshape(-1), tgt, vocab_start, vocab_end)
+        native().embedding_bwd(dx, ids.reshape(-1), tgt, vocab_start, vocab_end, grad_rs_for(accum_into) or {})
         return None if accum_into is not None else tgt.to(dx.dtype)
     flat = ids.reshape(-1)
     mask = (flat >= vocab_start) & (flat < vocab_end)

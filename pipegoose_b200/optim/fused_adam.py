@@ -44,16 +44,20 @@ class FusedAdam(torch.optim.Optimizer):
         assert self.master is None, "set_shard must be called before the first step"
         self._segments = [(start, end)]
 
-    def set_bucket_shards(self, bucket_numel: int, rank: int, world: int):
-        """This rank owns slice ``rank`` of every gradient bucket (what reduce-scatter leaves here)."""
+    def set_bucket_shards(self, bucket_numel: int, rank: int, world: int, head: int = 0, inline_from: Optional[int] = None):
+        """This rank owns slice ``rank`` of every gradient bucket (what reduce-scatter leaves here): the head bucket
+        ``[0, head)`` (if any) and then buckets of ``bucket_numel`` elements.  ``inline_from``: gradients at and beyond
+        this flat offset are reduce-scattered inside the kernels that produce them — the Adam kernel clears each owner
+        slice while it reads it, so that the next step's contributions are added to zero."""
         assert self.master is None, "sharding must be fixed before the first step"
         n = self.ensure_flat().numel
         segs = []
-        for start in range(0, n, bucket_numel):
-            end = min(n, start + bucket_numel)
+        bounds = ([(0, head)] if head else []) + [(s, min(n, s + bucket_numel)) for s in range(head, n, bucket_numel)]
+        for start, end in bounds:
             seg = (end - start) // world
             segs.append((start + rank * seg, start + (rank + 1) * seg))
         self._segments = segs
+        self._inline_from = inline_from
 
     def _lazy_init(self):
         self.ensure_flat()
@@ -84,7 +88,9 @@ class FusedAdam(torch.optim.Optimizer):
             param = self.flat.flat_param[s:e]
             master, m, v = self.master[off:off + n], self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n]
             if use_native(param):
-                native().adam_step(master, m, v, grad, param, lr, b1, b2, eps, wd, self._step, grad_scale, g["adamw"])
+                inline = getattr(self, "_inline_from", None)
+                native().adam_step(master, m, v, grad, param, lr, b1, b2, eps, wd, self._step, grad_scale, g["adamw"],
+                                   inline is not None and s >= inline)
             else:
                 gr = grad.float() * grad_scale
                 if wd != 0 and not g["adamw"]:
@@ -98,6 +104,8 @@ class FusedAdam(torch.optim.Optimizer):
                 param.copy_(master.to(param.dtype))
         self.flat.hold_grads = False
         self.flat.begin_grad_window()   # the gradients were consumed
+        if getattr(self.flat, "inline", None) is not None:
+            self.flat.inline.inline_consumed()   # ... and the owner slices of the in-kernel region cleared by the kernel
         FusedAdam.steps_taken += 1
         return loss
 
@@ -144,11 +152,15 @@ class FusedAdam(torch.optim.Optimizer):
     def _fold_autograd_grads(self):
         """Gradients delivered through autograd (``p.grad``: layers without a fused wgrad, or a backward that ran
         before the flat state existed) are added to the fp32 main grads the kernels update."""
+        from pipegoose_b200.ops import kernels as K
+
         for p in self.flat.params:
             if p.grad is not None:
                 if getattr(p, "_mg_fresh", False):
                     p.main_grad.copy_(p.grad)
                     p._mg_fresh = False
+                elif K.grad_rs_for(p.main_grad) is not None:
+                    K.accumulate_grad(p.grad, p.main_grad, True)   # joins the in-kernel reduce-scatter
                 else:
                     p.main_grad.add_(p.grad)
                 p.grad = None

@@ -91,7 +91,11 @@ class DistributedOptimizer(BaseDistributedOptimizer):
         if self.dp > 1:
             assert self._reducer.flat is flat, "the optimizer and the DataParallel reducer must share one flat state"
             self._reducer.mode = "reduce_scatter"
-            optim.set_bucket_shards(self._reducer.bucket_numel, self.dp_rank, self.dp)
+            # NVLink engine: the matrices' gradients are reduce-scattered inside the kernels that produce them
+            inline = self._reducer.enable_inline_rs()
+            head = getattr(self._reducer, "head", 0)
+            optim.set_bucket_shards(self._reducer.zero_bucket_numel, self.dp_rank, self.dp, head=head,
+                                    inline_from=head if inline else None)
         self._zero_ready = True
         pending = getattr(self, "_pending_state", None)
         if pending is not None:
@@ -104,14 +108,14 @@ class DistributedOptimizer(BaseDistributedOptimizer):
         flat = self.optim.flat
         group = self.parallel_context.get_group(ParallelMode.DATA)
         fused = getattr(self._reducer, "_fused", None)
+        head = getattr(self._reducer, "head", 0)
         if fused is not None:
-            fused.all_gather_params(flat.flat_param, self._reducer.bucket_numel)
+            fused.all_gather_params(flat.flat_param, self._reducer.zero_bucket_numel, head)
             return
-        B = self._reducer.bucket_numel
+        B = self._reducer.zero_bucket_numel
         n = flat.numel
         works = []
-        for start in range(0, n, B):
-            end = min(n, start + B)
+        for start, end in ([(0, head)] if head else []) + [(s0, min(n, s0 + B)) for s0 in range(head, n, B)]:
             seg = (end - start) // self.dp
             view = flat.flat_param[start:end]
             mine = view[self.dp_rank * seg:(self.dp_rank + 1) * seg]
