@@ -280,7 +280,7 @@ class GradReducer:
         seen = self._contribs_seen.get(id(p), 0) + 1
         self._contribs_seen[id(p)] = seen
         if seen > getattr(p, "_pg_grad_contribs", 1):
-            if any(b.launched for b in self._bucket_of[id(p)]):
+            if any(b.launched and not b.inline for b in self._bucket_of[id(p)]):
                 raise RuntimeError(
                     "a gradient contribution arrived after its bucket was reduced: set "
                     "`param._pg_grad_contribs` to the number of contributions per backward pass")
