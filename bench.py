@@ -406,11 +406,14 @@ def run_ours(args):
 # --------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference installed under baseline/_ref, stock code path
 # --------------------------------------------------------------------------------------------
-def run_reference(args):
+def _build_reference(args, n_layer=None, vocab=None):
+    """The reference's stock path: transformers Bloom -> [ExpertParallel] -> TensorParallel -> DataParallel ->
+    DistributedOptimizer(torch.optim.Adam).  Returns ``None`` (after printing the JSON "unavailable" line) when the
+    reference cannot be imported, else ``(ctx, model, optim, fwd, cfg, (tp, pp, dp), note)``."""
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_dir, "pipegoose")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/pipegoose not installed (see DESIGN.md)"}))
-        return
+        return None
     sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
     sys.path.insert(0, ref_dir)
     try:
@@ -418,15 +421,13 @@ def run_reference(args):
 
         hf_fx_shim.install()
         import torch
-        import torch.distributed as dist
         from pipegoose.distributed.parallel_context import ParallelContext
-        from pipegoose.distributed.parallel_mode import ParallelMode
         from pipegoose.nn import DataParallel, TensorParallel
         from pipegoose.optim import DistributedOptimizer
         from transformers import BloomConfig, BloomForCausalLM
     except Exception as e:  # pragma: no cover
         print(json.dumps({"impl": "reference", "unavailable": f"import failed: {type(e).__name__}: {e}"[:300]}))
-        return
+        return None
 
     tp, pp, dp = layout_of(args)
     note = None
@@ -448,9 +449,9 @@ def run_reference(args):
                                      backend="cpu:gloo,cuda:nccl" if cuda else "gloo")
     if cuda:
         ctx.set_device()
-    rank = ctx.get_global_rank()
     dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
     h, L, nh, V = MODEL_SIZES[args.model]
+    L, V = n_layer or L, vocab or V
     torch.manual_seed(1234)
     cfg = BloomConfig(hidden_size=h, n_layer=L, n_head=nh, vocab_size=V)
     model = BloomForCausalLM(cfg)
@@ -481,6 +482,26 @@ def run_reference(args):
         model.to("cuda")
     model.train()
 
+    def fwd(ids):
+        mask = torch.ones_like(ids)
+        loss = model(input_ids=ids, attention_mask=mask, labels=ids).loss
+        return loss_terms(loss) if loss_terms is not None else loss
+
+    return ctx, model, optim, fwd, cfg, (tp, pp, dp), note, dev
+
+
+def run_reference(args):
+    built = _build_reference(args)
+    if built is None:
+        return
+    import torch
+    import torch.distributed as dist
+    from pipegoose.distributed.parallel_mode import ParallelMode
+
+    ctx, model, optim, fwd, cfg, (tp, pp, dp), note, dev = built
+    cuda = args.device == "cuda"
+    rank = ctx.get_global_rank()
+
     S = args.seq_len
     b_rep = args.batch_per_gpu * tp
     gen = torch.Generator().manual_seed(1000 + ctx.get_local_rank(ParallelMode.DATA))
@@ -489,11 +510,6 @@ def run_reference(args):
     if cuda:
         host_ids = [t.pin_memory() for t in host_ids]
     dev_ids = host_ids[0].to(dev)
-    mask = torch.ones(b_rep, S, dtype=torch.long, device=dev)
-
-    def fwd(ids):
-        loss = model(input_ids=ids, attention_mask=mask, labels=ids).loss
-        return loss_terms(loss) if loss_terms is not None else loss
 
     def step_device(i):
         loss = fwd(dev_ids)
