@@ -234,6 +234,22 @@ class BasePartitioner:
 
 
 class UniformPartitioner(BasePartitioner):
+    # Model families beyond the built-in ones (nn.Sequential, Bloom-, GPT-2- and LLaMA-style causal LMs):
+    # [(matches(model) -> bool, blocks(model) -> list of blocks, stage_cls(model, start, end, is_first, is_last))].
+    # The reference reaches arbitrary 🤗 models by tracing them with transformers.utils.fx (partitioner.py:146-219);
+    # transformers 5 removed that tracer, so a family this partitioner does not know is described here instead, the way
+    # TensorParallelMapping.register describes a new family to the tensor-parallel wrapper.
+    _FAMILIES: List = []
+
+    @classmethod
+    def register_family(cls, matches, blocks, stage_cls) -> None:
+        """Teach the partitioner a new model family.  ``matches(model)`` recognises it, ``blocks(model)`` returns its
+        transformer blocks in order (they are balanced by parameter count), and ``stage_cls(model, start, end,
+        is_first, is_last)`` builds the ``nn.Module`` that runs blocks ``[start, end)`` — plus the embedding front end
+        when ``is_first`` and the final norm / head / loss when ``is_last`` — with the signature
+        ``forward(x, attention_mask=None, labels=None, batch_seq=None)`` of the built-in stages."""
+        cls._FAMILIES.insert(0, (matches, blocks, stage_cls))
+
     def __init__(self, model: nn.Module, parallel_context: ParallelContext):
         self.module = model
         self.parallel_context = parallel_context
@@ -260,10 +276,21 @@ class UniformPartitioner(BasePartitioner):
             costs = [sum(p.numel() for p in l.parameters()) or 1 for l in layers]
             b = _balanced_cuts(costs, n)
             return [SequentialStage(layers[b[i]:b[i + 1]]) for i in range(n)]
+        for matches, family_blocks, family_stage in self._FAMILIES:
+            if matches(model):
+                blocks = list(family_blocks(model))
+                assert len(blocks) >= n, "more pipeline stages than transformer blocks"
+                b = _balanced_cuts([sum(p.numel() for p in blk.parameters()) or 1 for blk in blocks], n)
+                return [family_stage(model, b[i], b[i + 1], i == 0, i == n - 1) for i in range(n)]
         blocks = self._block_list(model)
         rotary = blocks is not None and hasattr(getattr(model, "model", None), "rotary_emb") and hasattr(model, "lm_head")
-        assert blocks is not None and (hasattr(model, "transformer") or rotary), \
-            "UniformPartitioner supports nn.Sequential, Bloom-style, GPT-2-style and LLaMA-style causal LMs"
+        if blocks is None or not (hasattr(model, "transformer") or rotary):
+            raise NotImplementedError(
+                f"UniformPartitioner does not know how to cut a {type(model).__name__} into pipeline stages.  Built in: "
+                "nn.Sequential, Bloom-style (transformer.h + word_embeddings), GPT-2-style (transformer.wte/wpe/h) and "
+                "LLaMA-style (model.embed_tokens/layers/norm/rotary_emb + lm_head) causal LMs.  The reference traces any "
+                "🤗 model with transformers.utils.fx, which transformers >= 5 no longer ships; describe other "
+                "architectures with UniformPartitioner.register_family(matches, blocks, stage_cls) — see its docstring.")
         assert len(blocks) >= n, "more pipeline stages than transformer blocks"
         costs = [sum(p.numel() for p in blk.parameters()) for blk in blocks]  # embeddings excluded, as in the reference
         b = _balanced_cuts(costs, n)

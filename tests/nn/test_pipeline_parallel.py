@@ -309,3 +309,31 @@ def test_uneven_microbatches_and_ignored_labels_give_the_global_token_mean(batch
     loss.backward()
     spawn(run_uneven_microbatches, world_size=pp, state=copy.deepcopy(model.state_dict()), ids=ids, labels=labels, n_mb=n_mb,
           ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
+
+
+def test_partitioner_register_family_and_unknown_model_message():
+    """A model family the partitioner does not know is refused with an explanation, and ``register_family`` teaches it."""
+    import pytest
+    from torch import nn
+
+    from pipegoose_b200.nn.pipeline_parallel.partitioner import SequentialStage, UniformPartitioner
+
+    class Odd(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder_blocks = nn.ModuleList([nn.Linear(8, 8) for _ in range(4)])
+
+    class Ctx:
+        pipeline_parallel_size = 2
+
+    with pytest.raises(NotImplementedError, match="register_family"):
+        UniformPartitioner(Odd(), Ctx()).split()
+    saved = list(UniformPartitioner._FAMILIES)
+    try:
+        UniformPartitioner.register_family(
+            lambda m: isinstance(m, Odd), lambda m: m.encoder_blocks,
+            lambda m, a, b, first, last: SequentialStage(list(m.encoder_blocks[a:b])))
+        stages = UniformPartitioner(Odd(), Ctx()).split()
+        assert [len(s.layers) for s in stages] == [2, 2]
+    finally:
+        UniformPartitioner._FAMILIES[:] = saved
