@@ -176,6 +176,49 @@ MODEL_SIZES = {"bloom-tiny": (128, 4, 8, 1024), "bloom-560m": (1024, 24, 16, 250
                "bloom-3b": (2560, 30, 32, 250880), "bloom-7b1": (4096, 30, 32, 250880)}   # hidden, layers, heads, vocab
 
 
+def _init_on_gpu(args) -> bool:
+    """Initialise the weights on the GPU instead of on the host?  ``--init-device auto``: for the multi-billion
+    parameter configs only (filling 7B weights on the host takes minutes per rank)."""
+    if args.device != "cuda":
+        return False
+    mode = getattr(args, "init_device", "auto")
+    return mode == "cuda" or (mode == "auto" and args.model in ("bloom-1b7", "bloom-3b", "bloom-7b1"))
+
+
+def _make_model_ours(args, ctx, torch, n_layer, vocab, hf, dtype):
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+    if args.model.startswith("gpt2"):  # not a BASELINE.json config: the second model family on the same kernels
+        from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+        cfg = getattr(GPT2Config, args.model.replace("-", "_"))()
+        model = GPT2LMHeadModel(cfg).to(dtype)
+    elif hf:
+        # the reference's canonical input: a transformers BloomForCausalLM; TensorParallel converts it in place
+        from transformers import BloomConfig as HFConfig
+        from transformers import BloomForCausalLM as HFBloom
+
+        h, L, nh, V = MODEL_SIZES[args.model]
+        model = HFBloom(HFConfig(hidden_size=h, n_layer=n_layer or L, n_head=nh, vocab_size=vocab or V)).to(dtype)
+        cfg = model.config
+    else:
+        cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
+        if n_layer is not None:
+            cfg.n_layer = n_layer
+        if vocab is not None:
+            cfg.vocab_size = vocab
+        model = BloomForCausalLM(cfg).to(dtype)
+    if args.experts > 0:
+        from pipegoose_b200.nn import ExpertParallel
+        from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
+
+        router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
+        layers = list(range(0, cfg.n_layer, max(args.moe_every, 1)))
+        model = ExpertParallel(model, args.experts, mapping=layers, router=router.to(dtype),
+                               parallel_context=ctx).parallelize()
+    return model, cfg
+
+
 def _build_ours(args, ctx, torch, n_layer=None, vocab=None, hf=False, fused=True):
     """Model -> ExpertParallel -> TensorParallel -> PipelineParallel -> DataParallel -> ZeRO-1(FusedAdam): the public API a
     user of the reference calls, on this repo's kernels.  ``fused=False``: the same stack with the hand-written
@@ -190,37 +233,15 @@ def _build_ours(args, ctx, torch, n_layer=None, vocab=None, hf=False, fused=True
     saved = {k: os.environ.get(k) for k in switches}
     if not fused:
         os.environ.update(switches)
+    import contextlib
+
+    # weights are initialised ON the GPU (seeded: identical on every rank): a 7B model takes minutes to fill on the host
+    init_on = torch.device("cuda", torch.cuda.current_device()) if _init_on_gpu(args) else contextlib.nullcontext()
     try:
         pp = ctx.pipeline_parallel_size
         dtype = torch.bfloat16 if args.device == "cuda" else torch.float32
-        if args.model.startswith("gpt2"):  # not a BASELINE.json config: the second model family on the same kernels
-            from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
-
-            cfg = getattr(GPT2Config, args.model.replace("-", "_"))()
-            model = GPT2LMHeadModel(cfg).to(dtype)
-        elif hf:
-            # the reference's canonical input: a transformers BloomForCausalLM; TensorParallel converts it in place
-            from transformers import BloomConfig as HFConfig
-            from transformers import BloomForCausalLM as HFBloom
-
-            h, L, nh, V = MODEL_SIZES[args.model]
-            model = HFBloom(HFConfig(hidden_size=h, n_layer=n_layer or L, n_head=nh, vocab_size=vocab or V)).to(dtype)
-            cfg = model.config
-        else:
-            cfg = getattr(BloomConfig, args.model.replace("-", "_"))()
-            if n_layer is not None:
-                cfg.n_layer = n_layer
-            if vocab is not None:
-                cfg.vocab_size = vocab
-            model = BloomForCausalLM(cfg).to(dtype)
-        if args.experts > 0:
-            from pipegoose_b200.nn import ExpertParallel
-            from pipegoose_b200.nn.expert_parallel import SwitchNoisePolicy, Top1Router
-
-            router = Top1Router(SwitchNoisePolicy(), args.experts, cfg.hidden_size, expert_capacity=(1.25, 2.0))
-            layers = list(range(0, cfg.n_layer, max(args.moe_every, 1)))
-            model = ExpertParallel(model, args.experts, mapping=layers, router=router.to(dtype),
-                                   parallel_context=ctx).parallelize()
+        with init_on:
+            model, cfg = _make_model_ours(args, ctx, torch, n_layer, vocab, hf, dtype)
         model = TensorParallel(model, ctx, sequence_parallel=True if hf else None).parallelize()
         if pp > 1:
             from pipegoose_b200.nn import PipelineParallel
@@ -454,7 +475,10 @@ def _build_reference(args, n_layer=None, vocab=None):
     L, V = n_layer or L, vocab or V
     torch.manual_seed(1234)
     cfg = BloomConfig(hidden_size=h, n_layer=L, n_head=nh, vocab_size=V)
-    model = BloomForCausalLM(cfg)
+    import contextlib
+
+    with (dev if _init_on_gpu(args) else contextlib.nullcontext()):   # same rule in both arms
+        model = BloomForCausalLM(cfg)
     if cuda:
         model = model.to(torch.bfloat16)
     loss_terms = None
@@ -583,6 +607,8 @@ def main():
     ap.add_argument("--hf", action="store_true",
                     help="ours arm: feed a transformers BloomForCausalLM (the reference's input) instead of pipegoose_b200.models")
     ap.add_argument("--no-self-check", action="store_true", help="skip the N>1 numerics self-check (fused vs library engines)")
+    ap.add_argument("--init-device", default="auto", choices=["auto", "cpu", "cuda"],
+                    help="where the random weights are created (auto: on the GPU for the >= 1.7B configs)")
     ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
                     help="cpu: dry run of this script on gloo with a tiny model (no benchmark value)")
     args = ap.parse_args()
