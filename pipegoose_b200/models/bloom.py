@@ -7,8 +7,11 @@ activations are 2-D ``[tokens, hidden]`` bf16 tensors (token-sharded under tenso
 attention is the flash ALiBi kernel, the lm_head is fused with a vocab-parallel cross entropy
 (no ``[tokens, vocab]`` fp32 tensor, no all-gather of logits).
 
-Dropout: Bloom's ``hidden_dropout`` / ``attention_dropout`` default to 0.0 and the fused path
-supports exactly that.
+Dropout: Bloom's ``hidden_dropout`` / ``attention_dropout`` default to 0.0, which is what the fully fused sub-layers
+implement.  ``hidden_dropout > 0`` (🤗 Bloom's ``dropout_add`` after the attention projection and after the MLP) is
+supported in training through a composed path: the same kernels with the residual add taken out of the GEMM epilogue
+and ``dropout(.) + residual`` applied between them.  ``attention_dropout`` (on the attention probabilities) has no
+counterpart in the flash kernel and is refused.
 """
 from __future__ import annotations
 
@@ -129,10 +132,35 @@ class BloomBlock(nn.Module):
         self.self_attention = BloomAttention(config)
         self.post_attention_layernorm = nn.LayerNorm(h, eps=self.eps)
         self.mlp = BloomMLP(config)
+        self.hidden_dropout = float(getattr(config, "hidden_dropout", 0.0))
         self.tp = None  # set by TensorParallel (sequence-parallel communicator)
+
+    def _forward_with_dropout(self, x: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
+        """``hidden_dropout > 0`` in training: ``x + dropout(dense(attention))`` and ``x + dropout(mlp)`` — the kernels
+        of the fused path with the residual add applied after the dropout instead of in the GEMM epilogue."""
+        import torch.nn.functional as F
+
+        from pipegoose_b200.ops.attention import alibi_attention
+
+        attn, tp, p = self.self_attention, self.tp, self.hidden_dropout
+        n_head_local = attn.query_key_value.weight.shape[0] // (3 * attn.head_dim)
+        zero = torch.zeros_like(x)
+        qkv = PF.layernorm_linear(x, self.input_layernorm.weight, self.input_layernorm.bias,
+                                  attn.query_key_value.weight, attn.query_key_value.bias, self.eps, tp)
+        att = alibi_attention(qkv, attn.alibi_slopes_local(n_head_local), batch, seq, n_head_local, attn.head_dim)
+        x = x + F.dropout(PF.linear_residual(att, attn.dense.weight, attn.dense.bias, zero, tp), p, True)
+        mlp = self.mlp
+        if isinstance(mlp, BloomMLP):
+            h1 = K.gelu_tanh(PF.layernorm_linear(x, self.post_attention_layernorm.weight, self.post_attention_layernorm.bias,
+                                                 mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias, self.eps, tp))
+            return x + F.dropout(PF.linear_residual(h1, mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias, zero, tp), p, True)
+        ln = fused_layer_norm(x, self.post_attention_layernorm.weight, self.post_attention_layernorm.bias, self.eps)
+        return x + F.dropout(mlp(ln, zero), p, True)
 
     def forward(self, x: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
         """``x``: ``[tokens_local, hidden]`` (token-sharded when ``self.tp`` is set)."""
+        if getattr(self, "hidden_dropout", 0.0) > 0.0 and self.training:
+            return self._forward_with_dropout(x, batch, seq)
         attn = self.self_attention
         tp = self.tp
         n_head_local = attn.query_key_value.weight.shape[0] // (3 * attn.head_dim)
@@ -241,8 +269,8 @@ class BloomForCausalLM(nn.Module):
 
     def __init__(self, config: BloomConfig):
         super().__init__()
-        assert config.hidden_dropout == 0.0 and config.attention_dropout == 0.0, \
-            "the fused Bloom path implements Bloom's default (0.0) dropout"
+        assert config.attention_dropout == 0.0, \
+            "attention_dropout > 0 is not supported (the flash attention kernel keeps no [S, S] probabilities to drop)"
         assert not config.apply_residual_connection_post_layernorm
         self.config = config
         self.transformer = BloomModel(config)
@@ -410,8 +438,8 @@ def is_hf_bloom(module: nn.Module) -> bool:
 def hf_bloom_fast_path_blocker(hf_model) -> Optional[str]:
     """Why this 🤗 Bloom cannot run on the fused path (None: it can)."""
     c = hf_model.config
-    if getattr(c, "hidden_dropout", 0.0) != 0.0 or getattr(c, "attention_dropout", 0.0) != 0.0:
-        return "non-zero dropout"
+    if getattr(c, "attention_dropout", 0.0) != 0.0:
+        return "non-zero attention_dropout"
     if getattr(c, "apply_residual_connection_post_layernorm", False):
         return "apply_residual_connection_post_layernorm"
     if hf_model.lm_head.weight is not hf_model.transformer.word_embeddings.weight:
@@ -454,6 +482,7 @@ def convert_hf_bloom_(hf_model) -> "BloomForCausalLM":
             mlp.__class__ = BloomMLP
         block.__class__ = BloomBlock
         block.eps = cfg.layer_norm_epsilon
+        block.hidden_dropout = float(cfg.hidden_dropout)
         block.tp = None
     t.__class__ = BloomModel
     t.config = cfg

@@ -46,7 +46,7 @@ def test_in_place_conversion_keeps_parameters_and_matches_hf():
 
 
 def test_models_the_fused_path_cannot_run_keep_the_class_swap_path():
-    hf = _hf_bloom(hidden_dropout=0.1)
+    hf = _hf_bloom(attention_dropout=0.1)
     with pytest.raises(ValueError, match="dropout"):
         convert_hf_bloom_(hf)
 
@@ -119,3 +119,34 @@ def test_default_picks_the_fast_path_for_bf16_hf_models_only():
     assert isinstance(TensorParallel(bf16, Ctx()).parallelize(), FastBloom)     # ready for the kernels
     off = _hf_bloom().to(torch.bfloat16)
     assert is_hf_bloom(TensorParallel(off, Ctx(), sequence_parallel=False).parallelize())
+
+
+def test_hidden_dropout_trains_through_the_composed_path():
+    """``hidden_dropout > 0``: eval equals the 🤗 model, training applies dropout (stochastic, mean-preserving) and the
+    gradients flow to every parameter."""
+    torch.manual_seed(0)
+    hf = _hf_bloom(hidden_dropout=0.2)
+    ref = copy.deepcopy(hf)
+    fast = convert_hf_bloom_(hf)
+    ids = torch.randint(0, 96, (3, 10))
+    fast.eval(), ref.eval()
+    assert torch.allclose(fast(input_ids=ids, labels=ids).loss, ref(input_ids=ids, labels=ids).loss, atol=1e-5)
+    fast.train()
+    torch.manual_seed(1)
+    a = fast(input_ids=ids, labels=ids).loss
+    torch.manual_seed(2)
+    b = fast(input_ids=ids, labels=ids).loss
+    assert not torch.allclose(a, b)                      # different dropout masks
+    a.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in fast.parameters())
+    # with p -> 0 the composed path reproduces the fused one
+    for blk in fast.transformer.h:
+        blk.hidden_dropout = 1e-12
+    fast.zero_grad()
+    ref.train()
+    assert torch.allclose(fast(input_ids=ids, labels=ids).loss, _no_dropout_loss(ref, ids), atol=1e-5)
+
+
+def _no_dropout_loss(hf_model, ids):
+    hf_model.eval()   # 🤗 dropout off == p -> 0
+    return hf_model(input_ids=ids, labels=ids).loss
