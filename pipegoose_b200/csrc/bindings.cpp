@@ -104,6 +104,12 @@ void gemm(const torch::Tensor& a, const torch::Tensor& b, torch::Tensor out, boo
     d.rs_wait_value = (uint32_t)ag["rs_wait_value"].cast<int64_t>();
     d.my_rank = ag["rank"].cast<int>();
   }
+  if (ag.contains("ce_part")) {
+    // lm_head + cross entropy: the epilogue also writes the online-softmax partials (fp32 [M, 2 * ceil(N/256), 2])
+    TORCH_CHECK(!f32 && num_chunks >= 1, "ce_part needs a bf16 logits output");
+    d.ce_part = reinterpret_cast<float*>(ag["ce_part"].cast<int64_t>());
+    d.ce_valid = ag.contains("ce_valid") ? ag["ce_valid"].cast<int>() : 0;
+  }
   if (ag.contains("grad_rs")) {
     TORCH_CHECK(f32, "grad_rs needs an fp32 output");
     parse_grad_rs(ag["grad_rs"].cast<py::dict>(), &d.grad_rs);
@@ -207,6 +213,17 @@ void ce_stats(const torch::Tensor& logits, const torch::Tensor& targets, torch::
   const int rows = (int)logits.size(0);
   TORCH_CHECK(targets.scalar_type() == torch::kInt64 && targets.numel() == rows && stats.numel() == rows * 3, "bad targets/stats");
   TORCH_CHECK(pg_ce_stats(logits.data_ptr(), (int)logits.stride(0), targets.data_ptr<int64_t>(), stats.data_ptr<float>(), rows, (int)logits.size(1), (int)vocab_start, cur_stream()) == 0, "ce_stats failed");
+}
+
+void ce_combine(const torch::Tensor& part, const torch::Tensor& logits, const torch::Tensor& targets, torch::Tensor stats,
+                int64_t vocab_start) {
+  check_bf16_2d(logits, "logits"); PG_CUDA(part); PG_F32(part); PG_CUDA(targets); PG_CUDA(stats); PG_F32(stats);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = (int)logits.size(0);
+  TORCH_CHECK(part.dim() == 3 && part.size(0) == rows && part.size(2) == 2, "part must be [rows, nparts, 2]");
+  TORCH_CHECK(targets.scalar_type() == torch::kInt64 && targets.numel() == rows && stats.numel() == rows * 3, "bad targets/stats");
+  TORCH_CHECK(pg_ce_combine(part.data_ptr<float>(), (int)part.size(1), logits.data_ptr(), (int)logits.stride(0), targets.data_ptr<int64_t>(),
+                            stats.data_ptr<float>(), rows, (int)logits.size(1), (int)vocab_start, cur_stream()) == 0, "ce_combine failed");
 }
 
 void ce_finalize(torch::Tensor logits, const torch::Tensor& targets, const torch::Tensor& gstats, torch::Tensor loss_rows,
@@ -437,6 +454,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("grad_rs") = py::dict());
   m.def("grad_rs_accum", &grad_rs_accum);
   m.def("ce_stats", &ce_stats);
+  m.def("ce_combine", &ce_combine);
   m.def("ce_finalize", &ce_finalize);
   m.def("adam_step", &adam_step, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("grad"), py::arg("param_bf16"), py::arg("lr"),
         py::arg("beta1"), py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale"), py::arg("adamw"),

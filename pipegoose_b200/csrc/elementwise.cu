@@ -652,6 +652,54 @@ extern "C" int pg_ce_stats(const void* logits, int ld, const int64_t* targets, f
   return 0;
 }
 
+// one warp per row: merge the nparts (max, sumexp) partials of the lm_head GEMM epilogue, fetch the target logit
+__global__ void __launch_bounds__(256) ce_combine_kernel(const float2* __restrict__ part, int nparts,
+                                                         const __nv_bfloat16* __restrict__ logits, int ld,
+                                                         const int64_t* __restrict__ targets, float* __restrict__ stats,
+                                                         int rows, int vocab_local, int vocab_start) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float2* pr = part + static_cast<size_t>(row) * nparts;
+  float m = -INFINITY, s = 0.f;
+  for (int i = lane; i < nparts; i += 32) {
+    const float2 v = pr[i];
+    if (v.y > 0.f) {
+      const float nm = fmaxf(m, v.x);
+      s = s * __expf(m - nm) + v.y * __expf(v.x - nm);
+      m = nm;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, off);
+    const float os = __shfl_xor_sync(0xffffffffu, s, off);
+    const float nm = fmaxf(m, om);
+    if (nm > -INFINITY) {
+      s = s * __expf(m - nm) + os * __expf(om - nm);
+      m = nm;
+    }
+  }
+  if (lane == 0) {
+    const int64_t t = targets[row] - vocab_start;
+    float tl = 0.f;
+    if (t >= 0 && t < vocab_local) tl = __bfloat162float(logits[static_cast<size_t>(row) * ld + t]);
+    stats[row * 3 + 0] = m;
+    stats[row * 3 + 1] = s;
+    stats[row * 3 + 2] = tl;
+  }
+}
+
+extern "C" int pg_ce_combine(const float* part, int nparts, const void* logits, int ld, const int64_t* targets,
+                             float* stats, int rows, int vocab_local, int vocab_start, cudaStream_t s) {
+  if (rows == 0) return 0;
+  ce_combine_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float2*>(part), nparts,
+                                                           (const __nv_bfloat16*)logits, ld, targets, stats, rows,
+                                                           vocab_local, vocab_start);
+  PG_CHECK_LAUNCH("ce_combine");
+  return 0;
+}
+
 extern "C" int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gstats,
                               float* loss_rows, int rows, int vocab_local, int vocab_start,
                               const float* grad_scale, int64_t ignore_index, int write_grad,

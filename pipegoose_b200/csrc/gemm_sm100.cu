@@ -238,6 +238,8 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   }
   args.rs_wait_ctr = d->rs_wait_ctr;
   args.rs_wait_value = d->rs_wait_value;
+  args.ce_part = d->ce_part;
+  args.ce_valid = d->ce_valid > 0 ? d->ce_valid : d->N;
   args.grad_rs = d->grad_rs;
   if (args.grad_rs.world > 1) {
     if (!(d->flags & EPI_OUT_F32) || args.num_chunks > 1 || (d->ldc % 4) != 0) {
@@ -280,6 +282,11 @@ extern "C" int pg_gemm_bf16(const PgGemmDesc* d, cudaStream_t stream) {
   if (args.n_comm & 1) cta2 = -1;  // comm CTAs must fill whole clusters
   int bn = pick_bn(chunk_rows, args.N, args.K, args.num_chunks, max_ctas - args.n_comm, allow_split, d->b_mn != 0,
                    (args.flags & EPI_OUT_F32) != 0, &auto_splits, &cta2);
+  if (args.ce_part != nullptr && d->block_n <= 0) {
+    // the partials are laid out per 256-column tile (two per row and tile): fix the tile width, keep the pair choice
+    bn = 256;
+    auto_splits = 1;
+  }
   if (d->block_n > 0) {
     bn = d->block_n;
     auto_splits = 1;

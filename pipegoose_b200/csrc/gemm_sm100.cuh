@@ -34,6 +34,9 @@ enum EpiFlags : int {
   EPI_SCATTER = 64,    // MoE combine: out row -> out_peer[src][row_ret[row]], scaled by row_scale[row]
   EPI_ATOMIC = 128,    // fp32 out += acc with red.global.add (split-K partial sums)
 };
+// (GemmArgs::ce_part != null) lm_head: besides the bf16 logits the epilogue emits, per row and per half tile, the online
+// softmax partials (max, sum exp(x - max)) of the logits it holds in registers — the cross entropy never re-reads the
+// [tokens, vocab] logits for its statistics (csrc/elementwise.cu: ce_combine merges the partials)
 
 struct GemmArgs {
   int M, N, K;
@@ -82,6 +85,8 @@ struct GemmArgs {
   const __nv_bfloat16* rs_in[kMaxPeers];  // local staging slot of source s (rs_in[my_rank] unused); null = off
   const uint32_t* rs_wait_ctr;            // local arrival counters, one per source
   uint32_t rs_wait_value;
+  float* ce_part;  // [M, 2 * n_blks, 2] fp32 (max, sumexp) partials; slot 2 * n_blk + half (null: off)
+  int ce_valid;    // logits columns >= ce_valid are vocabulary padding: excluded from the statistics
   // wgrad -> data-parallel reduce-scatter (fp32 outputs): every 16-byte group of the tile is added into the gradient
   // buffer of the rank that owns its ZeRO-1 slice (local L2 atomics / NVLink peer atomics); grad_rs.world <= 1: off
   PgGradRS grad_rs;
@@ -492,6 +497,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       };
       if (use_in && h < NCH) prefetch_in(h);
+      float ce_m = -INFINITY, ce_s = 0.f;  // online softmax partial of this thread's row over this warp's chunks
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -588,6 +594,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 make_uint4(pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]), pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]),
                            pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]), pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]));
         };
+        if (args.ce_part != nullptr) {
+          // statistics of the values as they are STORED (rounded to bf16), so that the later softmax over the stored
+          // logits is normalised exactly
+          const int lim = min(ncols, args.ce_valid - col0);
+          if (lim > 0) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              f[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+              if (i < lim) cm = fmaxf(cm, f[i]);
+            }
+            const float nm = fmaxf(ce_m, cm);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < lim) sum += exp2f((f[i] - nm) * 1.4426950408889634f);
+            ce_s = ce_s * exp2f((ce_m - nm) * 1.4426950408889634f) + sum;
+            ce_m = nm;
+          }
+        }
         if (args.flags & EPI_GELU) {
           if (args.aux != nullptr) {
             // the pre-activation goes out through the same staged, coalesced path
@@ -671,6 +697,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         } else {
           store_block(reinterpret_cast<__nv_bfloat16*>(out_base), warp_out_row0, args.ldc);
         }
+      }
+      if (args.ce_part != nullptr && row_ok) {
+        float2* dst = reinterpret_cast<float2*>(args.ce_part) + static_cast<size_t>(row) * (2 * n_blks) + 2 * tc.n_blk + h;
+        *dst = make_float2(ce_m, ce_s);
       }
       // accumulator drained -> hand the TMEM stage back to the MMA warp
       tc_fence_before();

@@ -68,6 +68,10 @@ typedef struct PgGemmDesc {
   int scatter_rows_per_src;
   // fp32 output (wgrad): add the tile into the owners' gradient buffers (see PgGradRS); world <= 1: off
   PgGradRS grad_rs;
+  // lm_head: per-row online-softmax partials [M, 2 * ceil(N / block_n), 2] fp32 written by the epilogue (null: off);
+  // columns >= ce_valid are padding.  block_n is forced to 256 so that the caller can size the buffer.
+  float* ce_part;
+  int ce_valid;
 } PgGemmDesc;
 
 // ---- attention_sm100.cu
@@ -143,6 +147,9 @@ int pg_grad_rs_accum(const void* src, int src_is_f32, float* dst_local, int64_t 
                      const PgGradRS* grad_rs, cudaStream_t s);
 int pg_ce_stats(const void* logits, int ld, const int64_t* targets, float* stats, int rows,
                 int vocab_local, int vocab_start, cudaStream_t s);
+// merge the GEMM epilogue's partials [rows, nparts, 2] into stats [rows, 3] = (max, sumexp, logit[target] or 0)
+int pg_ce_combine(const float* part, int nparts, const void* logits, int ld, const int64_t* targets, float* stats,
+                  int rows, int vocab_local, int vocab_start, cudaStream_t s);
 int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gstats,
                    float* loss_rows, int rows, int vocab_local, int vocab_start,
                    const float* grad_scale, int64_t ignore_index, int write_grad, cudaStream_t s);

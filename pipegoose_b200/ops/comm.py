@@ -119,7 +119,7 @@ class FusedTPEngine:
         slot = (self.ag_epoch + 1) & 1
         return self.ws.local_tensor(self._ag_off(slot), (rows_local, cols), torch.bfloat16)
 
-    def _ag_gemm(self, x_shard, weight, b_mn, bias, flags, aux, out_cols):
+    def _ag_gemm(self, x_shard, weight, b_mn, bias, flags, aux, out_cols, extra=None):
         T, r = self.T, self.rank
         m_local, k = x_shard.shape
         m = m_local * T
@@ -140,16 +140,19 @@ class FusedTPEngine:
             src=[ws.data_ptr(p, self._ag_off(slot)) for p in range(T)],
             peer_flag=[ws.sig_ptr(p, S.SIG_AG_READY + r) for p in range(T)],
         )
+        if extra:
+            ag.update(extra)
         native().gemm(x_full, weight, out, False, b_mn, bias, None, aux, flags, 0, 0,
                       T, r, ws.sig_ptr(r, S.SIG_CHUNK_CTR), N_COMM_CTAS * self.ag_epoch, [], [], ag)
         return out, x_full
 
-    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
-        """``(gather(x) @ W^T + b [gelu], gather(x))`` with ``x_shard`` = this rank's token shard."""
+    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None, extra=None):
+        """``(gather(x) @ W^T + b [gelu], gather(x))`` with ``x_shard`` = this rank's token shard.  ``extra``: more
+        epilogue arguments for the kernel (``ce_part`` / ``ce_valid`` of the lm_head)."""
         if not self.supports(x_shard.shape[0]):
             x_full = self.comm.all_gather_rows(x_shard)
             z = torch.empty(x_full.shape[0], weight.shape[0], dtype=x_full.dtype, device=x_full.device) if gelu else None
-            y = K.gemm_nt(x_full, weight, bias, gelu=gelu, aux_out=z)
+            y = K.gemm_nt(x_full, weight, bias, gelu=gelu, aux_out=z, **({"ag": extra} if extra else {}))
             if aux_holder is not None:
                 aux_holder["aux"] = z
             return y, x_full
@@ -158,7 +161,8 @@ class FusedTPEngine:
             aux = torch.empty(x_shard.shape[0] * self.T, weight.shape[0], dtype=torch.bfloat16, device=x_shard.device)
             if aux_holder is not None:
                 aux_holder["aux"] = aux
-        return self._ag_gemm(x_shard.contiguous(), weight, False, bias, K.EPI_GELU if gelu else 0, aux, weight.shape[0])
+        return self._ag_gemm(x_shard.contiguous(), weight, False, bias, K.EPI_GELU if gelu else 0, aux, weight.shape[0],
+                             extra=extra)
 
     def ag_gemm_nn(self, dy_shard, weight, dgelu_aux=None):
         """``(gather(dy) @ W [* gelu'(aux)], gather(dy))`` — dgrad of a row-parallel linear."""

@@ -29,6 +29,9 @@ import os as _os
 _FUSED_LM_HEAD = _os.environ.get("PIPEGOOSE_B200_FUSED_LM_HEAD", "0") == "1"
 # LayerNorm backward writes dx into the staging slot of the next backward all-gather (same status: unvalidated, off)
 _LNBWD_TO_STAGE = _os.environ.get("PIPEGOOSE_B200_LNBWD_TO_STAGE", "0") == "1"
+# cross-entropy statistics from the lm_head GEMM's epilogue instead of a pass over the logits (written without GPU
+# access: off until tests/test_gpu_kernels.py::test_lm_head_ce_stats_in_epilogue has passed on a B200)
+_CE_IN_EPILOGUE = _os.environ.get("PIPEGOOSE_B200_CE_IN_EPILOGUE", "0") == "1"
 
 
 def _main_grad(p: Optional[torch.Tensor]):
@@ -436,24 +439,32 @@ class LMHeadCrossEntropy(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, table, labels, eps, vocab_start, ignore_index, tp, vocab_size=None):
+        from pipegoose_b200.ops import use_native
+
         fused = tp is not None and tp.fused and _FUSED_LM_HEAD
+        v_local = table.shape[0]
+        real = v_local if vocab_size is None else min(max(vocab_size - vocab_start, 0), v_local)
+        rows_full = x.shape[0] * (tp.size if tp is not None else 1)
+        # The logits GEMM's epilogue also emits the online-softmax partials (max, sum exp) of every half tile it holds in
+        # registers: the cross entropy's statistics pass over the [tokens, vocab] logits disappears
+        part = K.ce_partials_buffer(rows_full, v_local, x.device) if (_CE_IN_EPILOGUE and use_native(x, table)) else None
+        extra = {"ce_part": part.data_ptr(), "ce_valid": real} if part is not None else None
         if fused:
             # all-gather -> GEMM like every other column-parallel linear (LN writes into the gather staging buffer)
             stage = tp.ag_input_buffer(x.shape[0], x.shape[1])
             ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps, out=stage)
-            logits, ln_full = tp.ag_gemm(ln, table)
+            logits, ln_full = tp.ag_gemm(ln, table, extra=extra)
         else:
             ln, mean, rstd = K.layernorm_fwd(x, gamma, beta, eps)
             ln_full = tp.all_gather_rows(ln) if tp is not None else ln
-            logits = K.gemm_nt(ln_full, table)  # [M, V/T]
-        if vocab_size is not None:
+            logits = K.gemm_nt(ln_full, table, **({"ag": extra} if extra else {}))  # [M, V/T]
+        if real < logits.shape[1]:
             # rows the table was zero-padded with (vocabulary made divisible by the group size) are not classes: their
             # logits leave the softmax (-inf: exp 0, gradient 0).  Only the last shard(s) have any; no-op otherwise.
-            real = min(max(vocab_size - vocab_start, 0), logits.shape[1])
-            if real < logits.shape[1]:
-                logits[:, real:] = float("-inf")
+            logits[:, real:] = float("-inf")
         tgt = labels.reshape(-1)
-        stats = K.ce_local_stats(logits, tgt, vocab_start)
+        stats = K.ce_stats_from_partials(part, logits, tgt, vocab_start) if part is not None \
+            else K.ce_local_stats(logits, tgt, vocab_start)
         if tp is not None:
             gstats = K.ce_combine_stats(tp.all_gather_stack(stats))
         else:

@@ -255,6 +255,20 @@ def ce_local_stats(logits, targets, vocab_start):
     return torch.stack([m, s, tl], dim=1)
 
 
+def ce_partials_buffer(rows: int, vocab_local: int, device) -> torch.Tensor:
+    """Buffer for the online-softmax partials the lm_head GEMM epilogue emits: two (max, sumexp) pairs per row and
+    256-column tile."""
+    return torch.empty(rows, 2 * ((vocab_local + 255) // 256), 2, dtype=torch.float32, device=device)
+
+
+def ce_stats_from_partials(part, logits, targets, vocab_start):
+    """``[rows, 3]`` (max, sum exp(x - max), target logit or 0) from the GEMM epilogue's partials — the statistics pass
+    over the ``[rows, vocab]`` logits is gone, only ``rows x tiles x 16`` bytes are read."""
+    stats = torch.empty(logits.shape[0], 3, dtype=torch.float32, device=logits.device)
+    native().ce_combine(part, logits, targets, stats, vocab_start)
+    return stats
+
+
 def ce_combine_stats(all_stats: torch.Tensor) -> torch.Tensor:
     """Merge ``[T, rows, 3]`` per-shard stats into global ``[rows, 3]`` (max, sumexp, target logit)."""
     m = all_stats[..., 0].max(0).values

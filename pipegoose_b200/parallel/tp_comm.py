@@ -87,8 +87,8 @@ class TensorParallelComm:
     def ag_input_buffer(self, rows_local: int, cols: int):
         return self._engine.ag_input_buffer(rows_local, cols) if self.fused else None
 
-    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None):
-        return self._engine.ag_gemm(x_shard, weight, bias, gelu, aux_holder)
+    def ag_gemm(self, x_shard, weight, bias=None, gelu=False, aux_holder=None, extra=None):
+        return self._engine.ag_gemm(x_shard, weight, bias, gelu, aux_holder, extra=extra)
 
     def gemm_rs(self, a, weight, bias=None, residual=None):
         return self._engine.gemm_rs(a, weight, bias, residual)

@@ -200,3 +200,52 @@ def test_flash_alibi_attention(D, H, S, B):
     g, r = qkv_g.grad.view(B * S, H, 3, D).float(), ref_in.grad.view(B * S, H, 3, D)
     for i, name in enumerate("qkv"):
         assert _rel(g[:, :, i], r[:, :, i]) < 3e-2, name
+
+
+@pytest.mark.parametrize("M,V,valid", [(512, 4096, 4096), (384, 1000, 1000), (256, 2560, 2500)])
+def test_lm_head_ce_stats_in_epilogue(M, V, valid):
+    """The logits GEMM epilogue's online-softmax partials, merged by ce_combine, equal the statistics of a pass over the
+    stored logits (exactly the same bf16 values) — also with vocabulary padding and a last partial tile."""
+    from pipegoose_b200.ops import kernels as K
+
+    torch.manual_seed(0)
+    x = (torch.randn(M, 256, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(V, 256, device="cuda") * 0.2).to(torch.bfloat16)
+    tgt = torch.randint(0, valid, (M,), device="cuda")
+    part = K.ce_partials_buffer(M, V, x.device)
+    part.fill_(float("nan"))
+    logits = K.gemm_nt(x, w, ag={"ce_part": part.data_ptr(), "ce_valid": valid})
+    plain = K.gemm_nt(x, w)
+    assert torch.equal(logits, plain)
+    assert not torch.isnan(part).any(), "a (row, tile, half) slot was not written"
+    if valid < V:
+        logits[:, valid:] = float("-inf")
+    got = K.ce_stats_from_partials(part, logits, tgt, 0)
+    want = K.ce_local_stats(logits, tgt, 0)
+    lse_got = got[:, 0] + torch.log(got[:, 1])
+    lse_want = want[:, 0] + torch.log(want[:, 1])
+    assert torch.allclose(lse_got, lse_want, atol=1e-4, rtol=1e-5), (lse_got - lse_want).abs().max()
+    assert torch.equal(got[:, 2], want[:, 2])
+
+
+def test_lm_head_cross_entropy_with_epilogue_stats_matches(monkeypatch):
+    """LMHeadCrossEntropy with the statistics taken from the GEMM epilogue: same loss and gradients."""
+    from pipegoose_b200.ops import functional as PF
+
+    torch.manual_seed(1)
+    h, V, M = 256, 4096, 512
+    x = (torch.randn(M, h, device="cuda") * 0.5).to(torch.bfloat16)
+    gamma = torch.ones(h, device="cuda", dtype=torch.bfloat16)
+    beta = torch.zeros(h, device="cuda", dtype=torch.bfloat16)
+    table = (torch.randn(V, h, device="cuda") * 0.05).to(torch.bfloat16)
+    labels = torch.randint(0, V, (M,), device="cuda")
+    out = {}
+    for name, flag in (("pass", False), ("epilogue", True)):
+        monkeypatch.setattr(PF, "_CE_IN_EPILOGUE", flag)
+        xi, ti = x.clone().requires_grad_(True), table.clone().requires_grad_(True)
+        loss = PF.lm_head_cross_entropy(xi, gamma, beta, ti, labels)
+        loss.backward()
+        out[name] = (loss.item(), xi.grad.float(), ti.grad.float())
+    assert abs(out["pass"][0] - out["epilogue"][0]) < 1e-5
+    assert torch.allclose(out["pass"][1], out["epilogue"][1], atol=1e-5, rtol=1e-3)
+    assert torch.allclose(out["pass"][2], out["epilogue"][2], atol=1e-5, rtol=1e-3)
