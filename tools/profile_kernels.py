@@ -23,6 +23,13 @@ elif which == "gemm_big":
     a = torch.randn(M, Kd, device=dev, dtype=torch.bfloat16); b = torch.randn(N, Kd, device=dev, dtype=torch.bfloat16)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     for _ in range(6): n.gemm(a, b, out)
+elif which == "lm_head_ce":
+    # lm_head logits GEMM with the cross-entropy statistics in its epilogue (bloom-560m, 8192 tokens, TP2 shard of the vocabulary)
+    M, N, Kd = 8192, 125440, 1024
+    a = torch.randn(M, Kd, device=dev, dtype=torch.bfloat16); b = torch.randn(N, Kd, device=dev, dtype=torch.bfloat16) * 0.05
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    part = K.ce_partials_buffer(M, N, dev)
+    for _ in range(4): n.gemm(a, b, out, ag={"ce_part": part.data_ptr(), "ce_valid": N})
 elif which == "attn":
     B, S, H, D = 8, 1024, 16, 64
     qkv = torch.randn(B * S, H * 3 * D, device=dev, dtype=torch.bfloat16); slopes = K.alibi_slopes(H, device=dev)
