@@ -268,14 +268,25 @@ class FusedDPEngine:
         self.inline_start = None     # first element of the in-kernel reduce-scatter region (None: off)
         self.inline_dirty = False    # a kernel added gradients into the region since the owners last cleared it
         # NVLS (multicast object bound to the workspace): reduce with multimem.ld_reduce, all-gather with multimem.st
-        self._mc_grad = self.ws.mc_data_ptr(self._grad_off) if self.NVLS_REDUCE else 0
-        self._mc_param = self.ws.mc_data_ptr(self._param_off) if self.NVLS_ALLGATHER else 0
+        def want(mode):
+            return mode == "1" or (mode == "auto" and self.world >= 4)
+
+        self._mc_grad = self.ws.mc_data_ptr(self._grad_off) if want(self.NVLS_REDUCE) else 0
+        self._mc_param = self.ws.mc_data_ptr(self._param_off) if want(self.NVLS_ALLGATHER) else 0
         return param, grad
 
-    NVLS_REDUCE = os.environ.get("PIPEGOOSE_B200_NVLS_REDUCE", "1") == "1"
-    NVLS_ALLGATHER = os.environ.get("PIPEGOOSE_B200_NVLS_ALLGATHER", "1") == "1"
-    # 0: never reduce-scatter gradients inside the kernels that produce them (bucketed reducer for everything)
-    INLINE_RS = os.environ.get("PIPEGOOSE_B200_DP_INLINE_RS", "1") == "1"
+    # NVLS (multimem.ld_reduce / multimem.st through the NVSwitch multicast object): "auto" = groups of >= 4 ranks.
+    # Measured on 2 x B200 (dp=2, bloom-560m, profiles/validate_2gpu_r2.log): 45.76 ms/step with NVLS vs 45.14 without —
+    # with ONE peer the switch-side reduction saves no bytes and adds latency; from 4 ranks on a pull through the switch
+    # moves 1/world of the bytes of a pull from every peer.
+    NVLS_REDUCE = os.environ.get("PIPEGOOSE_B200_NVLS_REDUCE", "auto")
+    NVLS_ALLGATHER = os.environ.get("PIPEGOOSE_B200_NVLS_ALLGATHER", "auto")
+    # 1: reduce-scatter the matrices' gradients inside the kernels that produce them (red.global.add into the owner's
+    # buffer).  OFF by default — measured on 2 x B200 (dp=2, bloom-560m): 69.7 ms/step against 45.8 ms with the bucketed
+    # reducer (numerically identical, max rel. loss difference 4.5e-6): NVLink executes remote atomics at ~2.5-3 G
+    # operations/s whatever their width (v4.f32: ~46 GB/s; four scalar reds: 157 ms/step), far below the 750 GB/s that
+    # plain peer loads / stores reach, and the wgrad epilogues stall on them.  Kept as an option and as a tested kernel path.
+    INLINE_RS = os.environ.get("PIPEGOOSE_B200_DP_INLINE_RS", "0") == "1"
     # 1: four scalar red.global.add.f32 per 16 bytes instead of one red.global.add.v4.f32 (diagnosis)
     INLINE_SCALAR_RED = os.environ.get("PIPEGOOSE_B200_DP_INLINE_SCALAR", "0") == "1"
 

@@ -40,8 +40,9 @@ def run_workspace(rank, world_size, port):
     dist.barrier()
     # peer mappings: read every peer's buffer through its mapped pointer
     for peer in range(world_size):
-        view = native().tensor_from_ptr(ws.data_ptr(peer, 0), n * 4, torch.cuda.current_device()).view(torch.float32)
-        assert torch.equal(view, torch.arange(n, device="cuda", dtype=torch.float32) * (peer + 1)), peer
+        # (the pointer attributes of a peer mapping name the peer's device: ranks use device == rank here)
+        view = native().tensor_from_ptr(ws.data_ptr(peer, 0), n * 4, peer).view(torch.float32)
+        assert torch.equal(view.to("cuda"), torch.arange(n, device="cuda", dtype=torch.float32) * (peer + 1)), peer
     if ws.mc_ptr:
         out = torch.empty(n, dtype=torch.float32, device="cuda")
         # multimem.ld_reduce over the replicas of `a`; rank 0 multicasts the result into every replica of `b`
@@ -69,6 +70,7 @@ def run_grad_rs_kernels(rank, world_size, port, scalar):
     import torch.distributed as dist
 
     os.environ["PIPEGOOSE_B200_DP_INLINE_SCALAR"] = "1" if scalar else "0"
+    os.environ["PIPEGOOSE_B200_DP_INLINE_RS"] = "1"
     from pipegoose_b200.distributed.parallel_mode import ParallelMode
     from pipegoose_b200.ops import kernels as K
     from pipegoose_b200.ops.comm import FusedDPEngine
@@ -76,6 +78,7 @@ def run_grad_rs_kernels(rank, world_size, port, scalar):
 
     ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size, backend="nccl")
     FusedDPEngine.INLINE_SCALAR_RED = scalar
+    FusedDPEngine.INLINE_RS = True
     eng = FusedDPEngine(ctx, ParallelMode.DATA)
     N, Kd, M, V = 384, 256, 1024, 640            # wgrad [N, Kd] from M tokens; embedding table [V, Kd]
     head = world_size * 128                       # a small bucketed head in front of the in-kernel region
@@ -136,6 +139,7 @@ def run_zero_inline(rank, world_size, port, inline, nvls, state, ids, ref_losses
 
     os.environ["PIPEGOOSE_B200_DP_INLINE_RS"] = "1" if inline else "0"
     os.environ["PIPEGOOSE_B200_NVLS"] = "1" if nvls else "0"
+    os.environ["PIPEGOOSE_B200_NVLS_REDUCE"] = os.environ["PIPEGOOSE_B200_NVLS_ALLGATHER"] = "1" if nvls else "0"
     from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
     from pipegoose_b200.nn import DataParallel
     from pipegoose_b200.ops.comm import FusedDPEngine
