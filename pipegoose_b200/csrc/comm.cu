@@ -80,10 +80,10 @@ PG_DEVICE void peer_barrier(const PeerPtrs& p, int world, int rank, uint32_t val
 
 // Two-shot all-reduce (average) of buf[offset : offset+n) in place on every rank.
 // grid-wide phases are separated by a device-wide counter (cooperative-free: all CTAs resident).
-__global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank,
-                                                            int64_t offset, int64_t n, float scale,
-                                                            int rs_only, uint32_t epoch,
-                                                            uint32_t* __restrict__ grid_ctr) {
+template <int kU>
+__device__ __forceinline__ void allreduce_f32_body(const PeerPtrs& p, float* __restrict__ mc, int world, int rank,
+                                                   int64_t offset, int64_t n, float scale, int rs_only, uint32_t epoch,
+                                                   uint32_t* __restrict__ grid_ctr) {
   // phase 0: everyone's bucket is complete locally (kernel boundary) -> cross-rank barrier
   if (blockIdx.x == 0) peer_barrier(p, world, rank, epoch, 0);
   // release the other CTAs of this rank
@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* _
   const int64_t nvec = seg / 4;
   // reduce my slice: pull the same slice from every peer.  kU independent 16-byte loads per thread per
   // peer are issued before any is consumed (NVLink latency ~2 us: bytes in flight, not threads, set the rate)
-  constexpr int kU = 8;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   if (mc != nullptr) {
     // NVLS: ONE multimem.ld_reduce per 16 bytes returns the sum over all replicas (reduced inside the NVSwitch, 1/world
@@ -177,6 +176,22 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* _
   }
   __syncthreads();
   if (last) peer_barrier(p, world, rank, epoch, 1);
+}
+
+__global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank,
+                                                            int64_t offset, int64_t n, float scale, int rs_only,
+                                                            uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
+  allreduce_f32_body<8>(p, mc, world, rank, offset, n, scale, rs_only, epoch, grid_ctr);
+}
+
+// Co-resident form: 128 threads x <= 64 registers and a few bytes of shared memory — small enough to be scheduled on an
+// SM that a persistent GEMM CTA occupies (the GEMM launches with 384 x 128 registers and ~210 KB of shared memory, see
+// gemm_sm100.cuh), so the bucket reduction really runs WHILE backward computes instead of at kernel boundaries.
+// 2 CTAs per SM x 128 threads x 4 x 16 B = 16 KB in flight per SM (2.4 MB over the chip: the NVLink bandwidth-delay product)
+__global__ void __launch_bounds__(128, 8) /* <= 64 registers per thread */
+    allreduce_f32_small_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank, int64_t offset, int64_t n,
+                               float scale, int rs_only, uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
+  allreduce_f32_body<4>(p, mc, world, rank, offset, n, scale, rs_only, epoch, grid_ctr);
 }
 
 struct PeerPtrsBf16 {
@@ -349,7 +364,13 @@ extern "C" int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int worl
   }
   // overlapped with backward: a handful of CTAs on the SMs the persistent GEMMs leave free (pg_set_gemm_cta_cap);
   // after backward (nothing else runs): enough CTAs to keep ~3 MB in flight over NVLink
-  if (blocks <= 0) blocks = 24;
+  if (blocks < 0) {  // co-resident form: -blocks small CTAs that fit next to the persistent GEMM CTAs
+    allreduce_f32_small_kernel<<<-blocks, 128, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, scale,
+                                                       reduce_scatter_only, epoch, peer_flags[rank] + 2 * PG_MAX_PEERS);
+    PG_CHECK_LAUNCH("allreduce_f32_small");
+    return 0;
+  }
+  if (blocks == 0) blocks = 24;
   allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, scale,
                                               reduce_scatter_only, epoch,
                                               peer_flags[rank] + 2 * PG_MAX_PEERS);

@@ -155,8 +155,17 @@ PG_DEVICE TileCoord map_tile(int t, int m_blks_per_chunk, int n_blks, int num_ch
   return c;
 }
 
+// Launch-time register budget: 384 threads x 128 registers = 48 K of the SM's 64 K — the rest of the register file (and
+// ~15 KB of shared memory) stays free, so that a small communication CTA (the co-resident gradient reducer,
+// csrc/comm.cu) can run NEXT TO a persistent GEMM CTA instead of waiting for a kernel boundary.  The roles then
+// re-balance: warps 0-3 (TMA producer, MMA issuer, TMEM allocator) drop to 40 registers, the two epilogue warpgroups
+// rise to 168 — 128*40 + 256*168 = 48 K, i.e. the epilogue keeps the budget it had when the CTA owned the whole file.
+constexpr int kGemmLaunchRegs = 128;
+constexpr int kGemmLightRegs = 40;
+constexpr int kGemmEpilogueRegs = 168;
+
 template <int BN, bool A_MN, bool B_MN, bool CTA2>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(512, 1)  /* 65536 / 512 = 128 registers at launch; the block has 384 threads */
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_a_local, const GemmArgs args) {
@@ -292,6 +301,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   pdl_wait();  // everything above overlapped the previous kernel's tail; operands / epilogue inputs are read below
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // each register re-balancing instruction dominates the code of its warpgroup(s): ptxas allocates per region
+  if (warp < 4) {
+    setmaxnreg_dec<kGemmLightRegs>();
   if (warp == 0) {
     // ============================ TMA producer ============================
     int stage = 0;
@@ -413,7 +425,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<kGemmEpilogueRegs>();
     // ============================ epilogue ============================
     // 8 warps: warp e = 4 + q + 4h drains TMEM lanes [32q, 32q+32) (a warp may only touch the lane
     // quarter warp%4) and takes every second 32-column chunk (c = h, h+2, ...).  Every global access

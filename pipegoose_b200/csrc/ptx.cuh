@@ -328,6 +328,18 @@ PG_DEVICE void red_add_release_sys(uint32_t* p, uint32_t v) {
 }
 PG_DEVICE void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
+// Register re-balancing between the warpgroups (4 consecutive warps) of a CTA: a kernel launched with a small per-thread
+// register count (so that other CTAs fit next to it on the SM) lets its light warpgroups give registers back and its
+// heavy ones take them.  Must be executed by all four warps of a warpgroup.
+template <int N>
+PG_DEVICE void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+PG_DEVICE void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // Bounded spin on a monotonic flag / counter written by another CTA or another GPU (system-scope acquire).  A flag
 // that never arrives (a peer that died, a protocol bug) must not hang the node silently: after ~30 s of SM clocks
 // the waiting thread prints where it waited and what it saw, and traps — the host sees a launch failure with a
