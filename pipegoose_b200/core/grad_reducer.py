@@ -26,7 +26,15 @@ from pipegoose_b200.core.flat_state import FlatModelState, _ALIGN
 from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
 
-def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelState] = None):
+def _tp_all_reduce(t: torch.Tensor, group, comm=None):
+    """SUM over the TENSOR group: on the model's NVLink communicator when it offers one, else NCCL / gloo."""
+    if comm is not None and getattr(comm, "fused", False):
+        comm.all_reduce(t)
+    else:
+        dist.all_reduce(t, group=group)
+
+
+def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelState] = None, comm=None):
     """Sum the gradients of ``tp_partial_grad`` parameters over the TENSOR group, in place.  Gradients live in
     ``param.main_grad`` (flat fp32 buffer: one all-reduce of its head when the tagged parameters are laid out
     there) or, for parameters without a flat state, in ``param.grad`` (gathered into one flat tensor)."""
@@ -62,10 +70,10 @@ def reduce_tp_partial_grads(params, parallel_context, flat: Optional[FlatModelSt
             base = getattr(flat, "tp_reduced_base", None)
             if base is not None and base.numel() == n:
                 head.sub_(base)
-                dist.all_reduce(head, group=group)
+                _tp_all_reduce(head, group, comm)
                 head.add_(base)
             else:
-                dist.all_reduce(head, group=group)
+                _tp_all_reduce(head, group, comm)
             flat.tp_reduced_base = head.clone()
             return
     grads = []
@@ -118,7 +126,7 @@ class TensorPartialGradSync:
         if not self._sync or self._reducer_active():
             return
         flat = FlatModelState.find(self.params)
-        reduce_tp_partial_grads(self.params, self.ctx, flat)
+        reduce_tp_partial_grads(self.params, self.ctx, flat, comm=getattr(self.module, "tp", None))
 
     @contextmanager
     def no_sync(self):
@@ -382,7 +390,7 @@ class GradReducer:
         row-parallel biases) from their token shard only: sum them over the TENSOR group.  They sit at
         the head of the flat gradient buffer (FlatModelState sorts them first), so this is ONE in-place
         all-reduce; their buckets are held back (``deferred``) until it is enqueued."""
-        reduce_tp_partial_grads(self.flat.params, self.ctx, self.flat)
+        reduce_tp_partial_grads(self.flat.params, self.ctx, self.flat, comm=getattr(self.module, "tp", None))
 
     @contextmanager
     def no_sync(self):

@@ -380,6 +380,16 @@ void allgather_bf16(std::vector<int64_t> peer_bufs, int64_t rank, int64_t bucket
                                 (uint32_t)epoch, cur_stream()) == 0, "allgather_bf16 failed");
 }
 
+void rs_push(const torch::Tensor& x, int64_t num_chunks, int64_t first_chunk, std::vector<int64_t> out_peer,
+             std::vector<int64_t> arrive_ctr, int64_t blocks) {
+  PG_CUDA(x); PG_BF16(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK((int64_t)out_peer.size() == num_chunks && (int64_t)arrive_ctr.size() == num_chunks && x.numel() % num_chunks == 0, "rs_push: bad lists");
+  void* outs[PG_MAX_PEERS]; uint32_t* ctrs[PG_MAX_PEERS];
+  for (int i = 0; i < num_chunks; ++i) { outs[i] = reinterpret_cast<void*>(out_peer[i]); ctrs[i] = reinterpret_cast<uint32_t*>(arrive_ctr[i]); }
+  TORCH_CHECK(pg_rs_push(x.data_ptr(), (int)num_chunks, (int)first_chunk, x.numel() / num_chunks, outs, ctrs, (int)blocks, cur_stream()) == 0, "rs_push failed");
+}
+
 void multimem_selftest(int64_t mc_in, int64_t mc_out, torch::Tensor out) {
   PG_CUDA(out); PG_F32(out);
   c10::cuda::CUDAGuard guard(out.device());
@@ -478,6 +488,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_gemm_cta_cap", [](int64_t n) { pg_set_gemm_cta_cap((int)n); });
   m.def("allgather_bf16", &allgather_bf16, py::arg("peer_bufs"), py::arg("rank"), py::arg("bucket_elems"), py::arg("total_elems"),
         py::arg("peer_flags"), py::arg("epoch"), py::arg("head_elems") = 0, py::arg("mc_buf") = 0);
+  m.def("rs_push", &rs_push);
   m.def("multimem_selftest", &multimem_selftest);
   m.def("rs_reduce_mc", &rs_reduce_mc);
   m.def("vmm_probe", &vmm_probe);

@@ -68,6 +68,32 @@ struct PeerPtrs {
   uint32_t* flag[PG_MAX_PEERS];
 };
 
+// Reduce-scatter without a GEMM in front (vocab-parallel embedding: every rank holds a partial [T * rows, cols] matrix):
+// row block c goes to rank c's staging slot of this source, then this CTA bumps rank c's arrival counter — the same
+// protocol the GEMM -> reduce-scatter epilogue speaks, so the owner's rs_reduce kernel consumes both.
+struct RsPushArgs {
+  __nv_bfloat16* out_peer[PG_MAX_PEERS];
+  uint32_t* arrive_ctr[PG_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256) rs_push_kernel(const __nv_bfloat16* __restrict__ x, RsPushArgs a, int num_chunks,
+                                                      int first_chunk, int64_t chunk_elems) {
+  const int64_t nvec = chunk_elems / 8;
+  for (int i = 0; i < num_chunks; ++i) {
+    int c = first_chunk + i;
+    if (c >= num_chunks) c -= num_chunks;
+    const __nv_bfloat16* src = x + c * chunk_elems;
+    __nv_bfloat16* dst = a.out_peer[c];
+    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec;
+         v += static_cast<int64_t>(gridDim.x) * blockDim.x)
+      st_global_v4(dst + v * 8, ld_global_nc_v4(src + v * 8));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      fence_acq_rel_sys();
+      red_add_release_sys(a.arrive_ctr[c], 1u);
+    }
+  }
+}
+
 // flag layout per rank: flags[phase * PG_MAX_PEERS + src]
 PG_DEVICE void peer_barrier(const PeerPtrs& p, int world, int rank, uint32_t value, int phase) {
   // executed by one block; thread t < world signals peer t, then waits for peer t's signal
@@ -392,6 +418,20 @@ extern "C" int pg_allgather_bf16(void* const* peer_bufs, void* mc_buf, int world
   allgather_bf16_kernel<<<blocks, 512, 0, s>>>(p, (__nv_bfloat16*)mc_buf, world, rank, head_elems, bucket_elems,
                                                total_elems, epoch, peer_flags[rank] + 2 * PG_MAX_PEERS);
   PG_CHECK_LAUNCH("allgather_bf16");
+  return 0;
+}
+
+extern "C" int pg_rs_push(const void* x, int num_chunks, int first_chunk, int64_t chunk_elems, void* const* out_peer,
+                          uint32_t* const* arrive_ctr, int blocks, cudaStream_t s) {
+  if (chunk_elems % 8 != 0 || num_chunks > PG_MAX_PEERS) return -1;
+  RsPushArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < num_chunks; ++i) {
+    a.out_peer[i] = (__nv_bfloat16*)out_peer[i];
+    a.arrive_ctr[i] = arrive_ctr[i];
+  }
+  rs_push_kernel<<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, a, num_chunks, first_chunk, chunk_elems);
+  PG_CHECK_LAUNCH("rs_push");
   return 0;
 }
 

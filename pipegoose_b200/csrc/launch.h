@@ -109,6 +109,10 @@ int pg_allgather_bf16(void* const* peer_bufs, void* mc_buf, int world, int rank,
                       int64_t bucket_elems, int64_t total_elems, uint32_t* const* peer_flags, uint32_t epoch,
                       cudaStream_t s);
 int pg_barrier_peers(uint32_t* const* peer_flags, int world, int rank, uint32_t epoch, cudaStream_t s);
+// reduce-scatter without a GEMM: push row block c of x [num_chunks * chunk_elems] to rank c's staging slot and bump its
+// arrival counter by `blocks` (one per CTA); the owner runs pg_rs_reduce on the slots
+int pg_rs_push(const void* x, int num_chunks, int first_chunk, int64_t chunk_elems, void* const* out_peer,
+               uint32_t* const* arrive_ctr, int blocks, cudaStream_t s);
 // NVLS
 int pg_multimem_selftest(const float* mc_in, float* mc_out, float* out, int64_t n, cudaStream_t s);
 int pg_rs_reduce_mc(const void* mc_partial, const uint32_t* arrive_ctr, int num_src, uint32_t expected, const void* bias,

@@ -221,6 +221,83 @@ class FusedTPEngine:
         return self._gemm_rs(dy.contiguous(), weight, True, None, None, weight.shape[1])
 
 
+    # ------------------------------------------------------------------ small collectives on peer memory
+    # The vocab-parallel embedding (reduce-scatter forward, all-gather backward), the cross-entropy statistics exchange
+    # and the tensor-group sum of the sequence-parallel partial gradients: no GEMM to fuse them into, but they run on
+    # the same NVLink protocols instead of NCCL, so a tensor-parallel step contains no library collective.
+    PUSH_BLOCKS = 32
+
+    def reduce_scatter_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """``[T * rows, n]`` partial sums -> this rank's ``[rows, n]`` block of the sum: row block c is pushed into
+        rank c's staging slot (the GEMM -> reduce-scatter protocol without a GEMM), the owner sums the T slots."""
+        T, r = self.T, self.rank
+        x = x.contiguous()
+        m, n = x.shape
+        m_local = m // T
+        self._ensure(self._ag_slot_bytes, T * m_local * n * 2)
+        ws = self.ws
+        self.rs_calls += 1
+        slot = self.rs_calls & 1
+        self.rs_expected += self.PUSH_BLOCKS
+        src_stride = m_local * n
+        out_peer = [ws.data_ptr(p, self._rs_off(slot) + r * src_stride * 2) for p in range(T)]
+        arrive = [ws.sig_ptr(p, S.SIG_RS_ARRIVE + r) for p in range(T)]
+        native().rs_push(x, T, (r + 1) % T, out_peer, arrive, self.PUSH_BLOCKS)
+        out = torch.empty(m_local, n, dtype=torch.bfloat16, device=x.device)
+        native().rs_reduce(ws.data_ptr(r, self._rs_off(slot)), T, src_stride, ws.sig_ptr(r, S.SIG_RS_ARRIVE),
+                           self.rs_expected, None, None, out)
+        return out
+
+    def _misc(self, nbytes: int) -> S.SymmetricWorkspace:
+        """A second, small workspace (own flags) for the all-gather / all-reduce kernels below; grown collectively."""
+        nbytes = (nbytes + 4095) // 4096 * 4096
+        ws = getattr(self, "_misc_ws", None)
+        if ws is None or ws.nbytes < 2 * nbytes:
+            if ws is not None:
+                ws.close()
+            self._misc_ws = ws = S.SymmetricWorkspace(self.ctx, self.mode, 2 * nbytes)
+            self._misc_slot_bytes = nbytes
+            self._misc_epoch = 0
+            self._misc_calls = 0
+        return ws
+
+    def all_gather_rows(self, x_shard: torch.Tensor) -> torch.Tensor:
+        """``[rows, ...]`` -> ``[T * rows, ...]`` (any 2-byte or 4-byte dtype): every rank places its shard in its own
+        copy of the gathered buffer and pushes it to all peers in one kernel that ends with a peer barrier."""
+        T, r = self.T, self.rank
+        x_shard = x_shard.contiguous()
+        shard_bytes = x_shard.numel() * x_shard.element_size()
+        assert shard_bytes % 16 == 0
+        ws = self._misc(T * shard_bytes)
+        self._misc_calls += 1
+        off = (self._misc_calls & 1) * self._misc_slot_bytes
+        full = ws.local_tensor(off, (T * x_shard.shape[0],) + tuple(x_shard.shape[1:]), x_shard.dtype)
+        full[r * x_shard.shape[0]:(r + 1) * x_shard.shape[0]].copy_(x_shard)
+        self._misc_epoch += 1
+        total = T * shard_bytes // 2   # in bf16 elements
+        native().allgather_bf16([ws.data_ptr(p, off) for p in range(T)], r, total, total,
+                                [ws.sig_ptr(p, S.SIG_BARRIER) for p in range(T)], self._misc_epoch, 0, 0)
+        return full
+
+    def all_reduce_f32_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place SUM of a small contiguous fp32 tensor over the group (two-shot kernel on peer memory)."""
+        T, r = self.T, self.rank
+        n = t.numel()
+        pad = (n + T * 4 - 1) // (T * 4) * (T * 4)
+        ws = self._misc(pad * 4)
+        self._misc_calls += 1
+        off = (self._misc_calls & 1) * self._misc_slot_bytes
+        buf = ws.local_tensor(off, (pad,), torch.float32)
+        buf[:n].copy_(t.reshape(-1))
+        if pad > n:
+            buf[n:].zero_()
+        self._misc_epoch += 1
+        native().allreduce_f32([ws.data_ptr(p, off) for p in range(T)], r, 0, pad, 1.0, False,
+                               [ws.sig_ptr(p, S.SIG_BARRIER) for p in range(T)], self._misc_epoch, 8, 0)
+        t.reshape(-1).copy_(buf[:n])
+        return t
+
+
 class _StreamWork:
     """`Work`-like handle: the collective ran on a side stream; ``wait`` orders the caller's stream after it."""
 

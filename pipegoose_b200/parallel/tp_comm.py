@@ -42,9 +42,20 @@ class TensorParallelComm:
             self._engine = FusedTPEngine(self)
             self.fused = True
 
+    # 1: the collectives that have no GEMM to be fused into (vocab-parallel embedding reduce-scatter / all-gather, the
+    # cross-entropy statistics exchange, the partial-gradient sum) run on the NVLink peer-memory kernels as well, so a
+    # tensor-parallel step contains no NCCL kernel.  Written without GPU access: off until validated on 2 x B200.
+    PEER_COLLECTIVES = os.environ.get("PIPEGOOSE_B200_TP_PEER_COLLECTIVES", "0") == "1"
+
+    def _peer_ok(self, x: torch.Tensor) -> bool:
+        return (self.fused and self.PEER_COLLECTIVES and x.is_cuda and x.dtype in (torch.bfloat16, torch.float32)
+                and x.dim() >= 1 and (x.numel() * x.element_size()) % 16 == 0 and x.numel() > 0)
+
     # ------------------------------------------------------------------ library collectives
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
         x = x.detach().contiguous()
+        if self._peer_ok(x):
+            return self._engine.all_gather_rows(x)
         out = torch.empty((x.shape[0] * self.size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x, group=self.group)
         return out
@@ -60,6 +71,8 @@ class TensorParallelComm:
         x = x.detach().contiguous()
         assert x.shape[0] % self.size == 0
         rows = x.shape[0] // self.size
+        if self._peer_ok(x) and x.dtype == torch.bfloat16 and x.dim() == 2 and (rows * x.shape[1]) % 8 == 0:
+            return self._engine.reduce_scatter_rows(x)
         if dist.get_backend(self.group) == "gloo":
             dist.all_reduce(x, group=self.group)
             return x[self.rank * rows:(self.rank + 1) * rows].clone()
@@ -68,6 +81,8 @@ class TensorParallelComm:
         return out
 
     def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
+        if self._peer_ok(x) and x.dtype == torch.float32 and x.is_contiguous() and x.numel() <= (1 << 24):
+            return self._engine.all_reduce_f32_(x)
         dist.all_reduce(x, group=self.group)
         return x
 

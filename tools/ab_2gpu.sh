@@ -25,6 +25,10 @@ PIPEGOOSE_B200_DP_OVERLAP_CTAS=-296 PIPEGOOSE_B200_DP_TAIL_CTAS=-592 timeout 300
 echo "== TP2 (defaults now: fused lm_head, LN backward to stage)"
 timeout 300 python bench.py --gpus 2 $S | tee gpurun_out/bench_2gpu_tp2_v2.json | line
 PIPEGOOSE_B200_CE_IN_EPILOGUE=1 timeout 300 python bench.py --gpus 2 $S --no-self-check | line
+echo "-- peer-memory small collectives (no NCCL kernel in the TP step): numerics, then the step"
+PIPEGOOSE_B200_TP_PEER_COLLECTIVES=1 timeout 300 python -m pytest tests/test_gpu_multi.py -x -q -k "tp2_bloom" 2>&1 | tail -2
+PIPEGOOSE_B200_TP_PEER_COLLECTIVES=1 timeout 300 python bench.py --gpus 2 $S | line
+PIPEGOOSE_B200_TP_PEER_COLLECTIVES=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tools/dist_step_profile.py --tp 2 2>&1 | grep -i "nccl\|fwd" | head -8
 echo "== 1 GPU"
 timeout 300 python bench.py --gpus 1 $S | line
 echo "== MoE EP2 end to end (rehearsal of config #4) + PP2 (rehearsal of config #5's engine)"
