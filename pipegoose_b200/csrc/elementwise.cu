@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(512) ce_stats_kernel(const __nv_bfloat16* __re
       f[2 * j + 1] = t.y;
       cm = fmaxf(cm, fmaxf(t.x, t.y));
     }
+    if (cm == -INFINITY) continue;  // eight masked (-inf) logits, e.g. vocabulary padding: exp(-inf - -inf) would be NaN
     const float nm = fmaxf(m, cm);
     float add = 0.f;
 #pragma unroll
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(512) ce_stats_kernel(const __nv_bfloat16* __re
   }
   for (int c = nchunks * 8 + threadIdx.x; c < vocab_local; c += blockDim.x) {  // tail
     const float f = __bfloat162float(lr[c]);
+    if (f == -INFINITY) continue;
     const float nm = fmaxf(m, f);
     s = s * __expf(m - nm) + __expf(f - nm);
     m = nm;
