@@ -413,8 +413,11 @@ class FusedDPEngine:
         return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
 
     # CTAs of a gradient reduction that overlaps backward / runs after it (nothing else runs then: NVLink-bound)
-    OVERLAP_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_OVERLAP_CTAS", "64"))
-    TAIL_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_TAIL_CTAS", "96"))
+    # negative: that many CTAs of the CO-RESIDENT form (128 threads, 62 registers: fits next to a persistent GEMM CTA,
+    # see csrc/comm.cu); positive: 512-thread CTAs that only get SMs at GEMM kernel boundaries (round 1).  Measured on
+    # 2 x B200 at dp = 2 (profiles/ab_2gpu_r2.log): 64 / 96 big CTAs 45.57 ms, -296 / -592 small CTAs 44.64 ms per step.
+    OVERLAP_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_OVERLAP_CTAS", "-296"))
+    TAIL_CTAS = int(os.environ.get("PIPEGOOSE_B200_DP_TAIL_CTAS", "-592"))
     # 1: persistent GEMM grids leave OVERLAP_CTAS SMs free while reductions overlap backward
     CAP_GEMMS = os.environ.get("PIPEGOOSE_B200_DP_CAP_GEMMS", "0") == "1"
 

@@ -38,11 +38,18 @@ def run_workspace(rank, world_size, port):
     b.zero_()
     torch.cuda.synchronize()
     dist.barrier()
-    # peer mappings: read every peer's buffer through its mapped pointer
-    for peer in range(world_size):
-        # (the pointer attributes of a peer mapping name the peer's device: ranks use device == rank here)
-        view = native().tensor_from_ptr(ws.data_ptr(peer, 0), n * 4, peer).view(torch.float32)
-        assert torch.equal(view.to("cuda"), torch.arange(n, device="cuda", dtype=torch.float32) * (peer + 1)), peer
+    # peer mappings: every rank pushes its quarter of region c (bf16 view) into all peers with the all-gather kernel
+    c = ws.local_tensor(2 * n * 4, (n,), torch.float32)
+    c.zero_()
+    seg = n // world_size
+    c[rank * seg:(rank + 1) * seg] = float(rank + 1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    native().allgather_bf16([ws.data_ptr(p, 2 * n * 4) for p in range(world_size)], rank, 2 * n, 2 * n,
+                            [ws.sig_ptr(p, S.SIG_BARRIER) for p in range(world_size)], 1, 0, 0)
+    torch.cuda.synchronize()
+    want_c = torch.cat([torch.full((seg,), float(r + 1), device="cuda") for r in range(world_size)])
+    assert torch.equal(c, want_c), "peer stores did not arrive"
     if ws.mc_ptr:
         out = torch.empty(n, dtype=torch.float32, device="cuda")
         # multimem.ld_reduce over the replicas of `a`; rank 0 multicasts the result into every replica of `b`
