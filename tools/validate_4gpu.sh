@@ -19,6 +19,10 @@ timeout 900 python -m pytest tests/test_gpu_nvlink_engine.py tests/test_gpu_mult
 echo "== bench TP2 x DP2 + ZeRO-1 (with self-check); in-kernel gradient reduce-scatter off for comparison"
 timeout 300 python bench.py --gpus 4 --steps 10 --warmup 3 | tee gpurun_out/bench_4gpu.json | line
 PIPEGOOSE_B200_DP_INLINE_RS=0 timeout 300 python bench.py --gpus 4 --steps 10 --warmup 3 --no-self-check | line
+echo "== TP2 x DP2 step: phases and kernel table (torch profiler, diagnosis only)"
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29539 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -30
+echo "== NVLS off at dp = 2 x tp 2 for comparison"
+PIPEGOOSE_B200_NVLS=0 timeout 300 python bench.py --gpus 4 --steps 10 --warmup 3 --no-self-check | line
 echo "== dress rehearsal of configs #3-#5 at 4 GPUs"
 timeout 300 python bench.py --gpus 4 --steps 3 --warmup 3 --model bloom-7b1 --tp 4 --seq-len 2048 --batch-per-gpu 1 2>&1 | grep "^{\|Error" | line
 timeout 300 python bench.py --gpus 4 --steps 3 --warmup 3 --tp 4 --experts 4 2>&1 | grep "^{\|Error" | line
