@@ -251,6 +251,24 @@ void adam_step(torch::Tensor master, torch::Tensor m, torch::Tensor v, const tor
                       (float)eps, (float)wd, (float)bc1, (float)bc2, (float)grad_scale, adamw, zero_grad, cur_stream()) == 0, "adam failed");
 }
 
+// ZeRO-1: this rank's slice (seg elements at flat offset first + b * bucket_stride) of nb equally sized buckets in ONE launch;
+// master / m / v hold the nb slices back to back
+void adam_step_strided(torch::Tensor master, torch::Tensor m, torch::Tensor v, torch::Tensor flat_grad, c10::optional<torch::Tensor> flat_param,
+                       int64_t first, int64_t seg, int64_t bucket_stride, int64_t nb, double lr, double beta1, double beta2, double eps,
+                       double wd, int64_t step, double grad_scale, bool adamw, bool zero_grad) {
+  PG_CUDA(master); PG_F32(master); PG_CUDA(m); PG_F32(m); PG_CUDA(v); PG_F32(v); PG_CUDA(flat_grad); PG_F32(flat_grad);
+  c10::cuda::CUDAGuard guard(master.device());
+  TORCH_CHECK(master.numel() == seg * nb && m.numel() == seg * nb && v.numel() == seg * nb, "adam_strided: state size mismatch");
+  TORCH_CHECK(first >= 0 && first + (nb - 1) * bucket_stride + seg <= flat_grad.numel(), "adam_strided: range outside the flat buffer");
+  void* pb = nullptr;
+  if (flat_param.has_value()) { PG_CUDA(*flat_param); PG_BF16(*flat_param); TORCH_CHECK(flat_param->numel() == flat_grad.numel(), "flat sizes differ");
+    pb = reinterpret_cast<char*>(flat_param->data_ptr()) + 2 * first; }
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  TORCH_CHECK(pg_adam_strided(master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), flat_grad.data_ptr<float>() + first, pb, seg,
+                              bucket_stride, nb, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, (float)bc1, (float)bc2,
+                              (float)grad_scale, adamw, zero_grad, cur_stream()) == 0, "adam_strided failed");
+}
+
 void sgd_step(torch::Tensor master, c10::optional<torch::Tensor> mom, const torch::Tensor& grad, c10::optional<torch::Tensor> param_bf16,
               double lr, double momentum, double wd, double grad_scale, bool first_step) {
   PG_CUDA(master); PG_F32(master); PG_CUDA(grad); PG_F32(grad);
@@ -361,12 +379,12 @@ void rs_reduce(int64_t staging_ptr, int64_t num_src, int64_t src_stride, int64_t
 }
 
 void allreduce_f32(std::vector<int64_t> peer_bufs, int64_t rank, int64_t offset, int64_t n, double scale, bool rs_only,
-                   std::vector<int64_t> peer_flags, int64_t epoch, int64_t blocks, int64_t mc_buf) {
+                   std::vector<int64_t> peer_flags, int64_t epoch, int64_t blocks, int64_t mc_buf, int64_t bucket_elems) {
   float* bufs[PG_MAX_PEERS]; uint32_t* flags[PG_MAX_PEERS];
   const int world = (int)peer_bufs.size();
   TORCH_CHECK(world <= PG_MAX_PEERS && peer_flags.size() == peer_bufs.size(), "bad peer lists");
   for (int i = 0; i < world; ++i) { bufs[i] = reinterpret_cast<float*>(peer_bufs[i]); flags[i] = reinterpret_cast<uint32_t*>(peer_flags[i]); }
-  TORCH_CHECK(pg_allreduce_f32(bufs, reinterpret_cast<float*>(mc_buf), world, (int)rank, offset, n, (float)scale, rs_only, flags,
+  TORCH_CHECK(pg_allreduce_f32(bufs, reinterpret_cast<float*>(mc_buf), world, (int)rank, offset, n, bucket_elems, (float)scale, rs_only, flags,
                                (uint32_t)epoch, (int)blocks, cur_stream()) == 0, "allreduce_f32 failed");
 }
 
@@ -469,6 +487,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("adam_step", &adam_step, py::arg("master"), py::arg("m"), py::arg("v"), py::arg("grad"), py::arg("param_bf16"), py::arg("lr"),
         py::arg("beta1"), py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("grad_scale"), py::arg("adamw"),
         py::arg("zero_grad") = false);
+  m.def("adam_step_strided", &adam_step_strided);
   m.def("sgd_step", &sgd_step);
   m.def("accum_bf16_to_f32", &accum_bf16_to_f32);
   m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("slopes"), py::arg("out"), py::arg("lse"), py::arg("B"),
@@ -484,7 +503,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &tensor_from_ptr);
   m.def("rs_reduce", &rs_reduce);
   m.def("allreduce_f32", &allreduce_f32, py::arg("peer_bufs"), py::arg("rank"), py::arg("offset"), py::arg("n"),
-        py::arg("scale"), py::arg("rs_only"), py::arg("peer_flags"), py::arg("epoch"), py::arg("blocks") = 0, py::arg("mc_buf") = 0);
+        py::arg("scale"), py::arg("rs_only"), py::arg("peer_flags"), py::arg("epoch"), py::arg("blocks") = 0, py::arg("mc_buf") = 0, py::arg("bucket_elems") = 0);
   m.def("set_gemm_cta_cap", [](int64_t n) { pg_set_gemm_cta_cap((int)n); });
   m.def("allgather_bf16", &allgather_bf16, py::arg("peer_bufs"), py::arg("rank"), py::arg("bucket_elems"), py::arg("total_elems"),
         py::arg("peer_flags"), py::arg("epoch"), py::arg("head_elems") = 0, py::arg("mc_buf") = 0);

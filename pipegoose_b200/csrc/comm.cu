@@ -108,8 +108,8 @@ PG_DEVICE void peer_barrier(const PeerPtrs& p, int world, int rank, uint32_t val
 // grid-wide phases are separated by a device-wide counter (cooperative-free: all CTAs resident).
 template <int kU>
 __device__ __forceinline__ void allreduce_f32_body(const PeerPtrs& p, float* __restrict__ mc, int world, int rank,
-                                                   int64_t offset, int64_t n, float scale, int rs_only, uint32_t epoch,
-                                                   uint32_t* __restrict__ grid_ctr) {
+                                                   int64_t offset, int64_t n, int64_t bucket_elems, float scale,
+                                                   int rs_only, uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
   // phase 0: everyone's bucket is complete locally (kernel boundary) -> cross-rank barrier
   if (blockIdx.x == 0) peer_barrier(p, world, rank, epoch, 0);
   // release the other CTAs of this rank
@@ -123,12 +123,16 @@ __device__ __forceinline__ void allreduce_f32_body(const PeerPtrs& p, float* __r
     }
   }
   __syncthreads();
-  const int64_t seg = n / world;  // n is a multiple of world * 4
-  const int64_t my0 = offset + rank * seg;
+  // [offset, offset + n) is a run of buckets of bucket_elems elements (the last one may be shorter; every length is a
+  // multiple of world * 4): ONE launch, one barrier pair, reduces them all — each bucket slice-wise, so that the ZeRO-1
+  // ownership (rank r owns slice r of every bucket) is the same as with one launch per bucket
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t b0 = 0; b0 < n; b0 += bucket_elems) {
+  const int64_t seg = min(bucket_elems, n - b0) / world;
+  const int64_t my0 = offset + b0 + rank * seg;
   const int64_t nvec = seg / 4;
   // reduce my slice: pull the same slice from every peer.  kU independent 16-byte loads per thread per
   // peer are issued before any is consumed (NVLink latency ~2 us: bytes in flight, not threads, set the rate)
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   if (mc != nullptr) {
     // NVLS: ONE multimem.ld_reduce per 16 bytes returns the sum over all replicas (reduced inside the NVSwitch, 1/world
     // of the bytes of a pull from every peer cross this GPU's links); the all-gather half is ONE multimem.st
@@ -191,6 +195,7 @@ __device__ __forceinline__ void allreduce_f32_body(const PeerPtrs& p, float* __r
       }
     }
   }
+  }  // buckets
   // phase 1: all ranks finished reading my buffer / writing into it
   __syncthreads();
   __shared__ uint32_t last;
@@ -205,9 +210,9 @@ __device__ __forceinline__ void allreduce_f32_body(const PeerPtrs& p, float* __r
 }
 
 __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank,
-                                                            int64_t offset, int64_t n, float scale, int rs_only,
-                                                            uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
-  allreduce_f32_body<8>(p, mc, world, rank, offset, n, scale, rs_only, epoch, grid_ctr);
+                                                            int64_t offset, int64_t n, int64_t bucket_elems, float scale,
+                                                            int rs_only, uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
+  allreduce_f32_body<8>(p, mc, world, rank, offset, n, bucket_elems, scale, rs_only, epoch, grid_ctr);
 }
 
 // Co-resident form: 128 threads x <= 64 registers and a few bytes of shared memory — small enough to be scheduled on an
@@ -216,8 +221,9 @@ __global__ void __launch_bounds__(512) allreduce_f32_kernel(PeerPtrs p, float* _
 // 2 CTAs per SM x 128 threads x 4 x 16 B = 16 KB in flight per SM (2.4 MB over the chip: the NVLink bandwidth-delay product)
 __global__ void __launch_bounds__(128, 8) /* <= 64 registers per thread */
     allreduce_f32_small_kernel(PeerPtrs p, float* __restrict__ mc, int world, int rank, int64_t offset, int64_t n,
-                               float scale, int rs_only, uint32_t epoch, uint32_t* __restrict__ grid_ctr) {
-  allreduce_f32_body<4>(p, mc, world, rank, offset, n, scale, rs_only, epoch, grid_ctr);
+                               int64_t bucket_elems, float scale, int rs_only, uint32_t epoch,
+                               uint32_t* __restrict__ grid_ctr) {
+  allreduce_f32_body<4>(p, mc, world, rank, offset, n, bucket_elems, scale, rs_only, epoch, grid_ctr);
 }
 
 struct PeerPtrsBf16 {
@@ -378,10 +384,11 @@ extern "C" int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride
 
 // grid_ctr: two uint32 in LOCAL memory right after the flag area: peer_flags[rank] + 2*PG_MAX_PEERS
 extern "C" int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int world, int rank, int64_t offset_elems,
-                                int64_t n, float scale, int reduce_scatter_only,
+                                int64_t n, int64_t bucket_elems, float scale, int reduce_scatter_only,
                                 uint32_t* const* peer_flags, uint32_t epoch, int blocks, cudaStream_t s) {
   if (n == 0) return 0;
-  if (n % (world * 4) != 0) return -1;
+  if (bucket_elems <= 0 || bucket_elems > n) bucket_elems = n;
+  if (bucket_elems % (world * 4) != 0 || (n % bucket_elems) % (world * 4) != 0) return -1;
   PeerPtrs p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < world; ++i) {
@@ -391,13 +398,13 @@ extern "C" int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int worl
   // overlapped with backward: a handful of CTAs on the SMs the persistent GEMMs leave free (pg_set_gemm_cta_cap);
   // after backward (nothing else runs): enough CTAs to keep ~3 MB in flight over NVLink
   if (blocks < 0) {  // co-resident form: -blocks small CTAs that fit next to the persistent GEMM CTAs
-    allreduce_f32_small_kernel<<<-blocks, 128, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, scale,
+    allreduce_f32_small_kernel<<<-blocks, 128, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, bucket_elems, scale,
                                                        reduce_scatter_only, epoch, peer_flags[rank] + 2 * PG_MAX_PEERS);
     PG_CHECK_LAUNCH("allreduce_f32_small");
     return 0;
   }
   if (blocks == 0) blocks = 24;
-  allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, scale,
+  allreduce_f32_kernel<<<blocks, 512, 0, s>>>(p, mc_buf, world, rank, offset_elems, n, bucket_elems, scale,
                                               reduce_scatter_only, epoch,
                                               peer_flags[rank] + 2 * PG_MAX_PEERS);
   PG_CHECK_LAUNCH("allreduce_f32");

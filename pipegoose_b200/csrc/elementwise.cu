@@ -726,6 +726,54 @@ extern "C" int pg_adam(float* master, float* m, float* v, const float* grad, voi
   return 0;
 }
 
+// one thread per four consecutive elements of one bucket slice (seg % 4 == 0)
+__global__ void __launch_bounds__(256) adam_strided_kernel(float* __restrict__ master, float* __restrict__ exp_avg,
+                                                           float* __restrict__ exp_avg_sq, float* __restrict__ grad,
+                                                           __nv_bfloat16* __restrict__ param_bf16, int64_t seg,
+                                                           int64_t bucket_stride, int64_t total, float lr, float beta1,
+                                                           float beta2, float eps, float weight_decay, float bc1, float bc2,
+                                                           float grad_scale, int adamw, int zero_grad) {
+  const int64_t i4 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= total) return;
+  const int64_t b = i4 / seg;
+  const int64_t f4 = b * bucket_stride + (i4 - b * seg);  // offset in the flat gradient / parameter buffers
+  float4 p = *reinterpret_cast<float4*>(master + i4);
+  float4 m = *reinterpret_cast<float4*>(exp_avg + i4);
+  float4 v = *reinterpret_cast<float4*>(exp_avg_sq + i4);
+  const float4 g4 = *reinterpret_cast<const float4*>(grad + f4);
+  if (zero_grad) *reinterpret_cast<float4*>(grad + f4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float pp[4] = {p.x, p.y, p.z, p.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+  const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float g = gg[j] * grad_scale;
+    if (!adamw && weight_decay != 0.f) g += weight_decay * pp[j];
+    mm[j] = beta1 * mm[j] + (1.f - beta1) * g;
+    vv[j] = beta2 * vv[j] + (1.f - beta2) * g * g;
+    const float denom = sqrtf(vv[j] / bc2) + eps;
+    if (adamw && weight_decay != 0.f) pp[j] *= (1.f - lr * weight_decay);
+    pp[j] -= lr * (mm[j] / bc1) / denom;
+  }
+  *reinterpret_cast<float4*>(master + i4) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  *reinterpret_cast<float4*>(exp_avg + i4) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+  *reinterpret_cast<float4*>(exp_avg_sq + i4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  if (param_bf16) *reinterpret_cast<uint2*>(param_bf16 + f4) = make_uint2(pack_bf16x2(pp[0], pp[1]), pack_bf16x2(pp[2], pp[3]));
+}
+
+extern "C" int pg_adam_strided(float* master, float* m, float* v, float* grad, void* param_bf16, int64_t seg,
+                               int64_t bucket_stride, int64_t nb, float lr, float beta1, float beta2, float eps, float wd,
+                               float bc1, float bc2, float grad_scale, int adamw, int zero_grad, cudaStream_t s) {
+  if (nb <= 0 || seg <= 0) return 0;
+  if (seg % 4 != 0 || bucket_stride % 4 != 0) return -1;
+  const int64_t total = seg * nb;
+  const int64_t threads = total / 4;
+  adam_strided_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(master, m, v, grad, (__nv_bfloat16*)param_bf16, seg,
+                                                                       bucket_stride, total, lr, beta1, beta2, eps, wd, bc1,
+                                                                       bc2, grad_scale, adamw, zero_grad);
+  PG_CHECK_LAUNCH("adam_strided");
+  return 0;
+}
+
 extern "C" int pg_sgd(float* master, float* mom, const float* grad, void* param_bf16, int64_t n,
                       float lr, float momentum, float wd, float grad_scale, int first_step,
                       cudaStream_t s) {

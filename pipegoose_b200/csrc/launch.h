@@ -100,9 +100,10 @@ int pg_rs_reduce(const void* staging, int num_src, int64_t src_stride_elems, con
 // flat fp32 gradient bucket: in-place all-reduce / reduce-scatter average over NVLink peers
 // mc_buf != null: the reduce half is ONE multimem.ld_reduce per 16 bytes (summed inside the NVSwitch), the all-gather
 // half ONE multimem.st
+// [offset, offset + n) may be a run of buckets of bucket_elems elements (0: one bucket): each is reduced slice-wise
 int pg_allreduce_f32(float* const* peer_bufs, float* mc_buf, int world, int rank, int64_t offset_elems, int64_t n,
-                     float scale, int reduce_scatter_only, uint32_t* const* peer_flags, uint32_t epoch,
-                     int blocks, cudaStream_t s);
+                     int64_t bucket_elems, float scale, int reduce_scatter_only, uint32_t* const* peer_flags,
+                     uint32_t epoch, int blocks, cudaStream_t s);
 // ZeRO-1 parameter all-gather: regions [0, head) and then [head + k*bucket, ...) up to total; every rank pushes its
 // 1/world slice of each region to all peers (mc_buf != null: ONE multimem.st per 16 bytes through the NVSwitch)
 int pg_allgather_bf16(void* const* peer_bufs, void* mc_buf, int world, int rank, int64_t head_elems,
@@ -160,6 +161,11 @@ int pg_ce_finalize(void* logits, int ld, const int64_t* targets, const float* gs
 int pg_adam(float* master, float* m, float* v, const float* grad, void* param_bf16, int64_t n,
             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
             float grad_scale, int adamw, int zero_grad, cudaStream_t s);
+// ZeRO-1 form: ONE launch updates this rank's slice of nb equally sized buckets — optimizer state element b * seg + w
+// belongs to flat element first + b * bucket_stride + w (w < seg)
+int pg_adam_strided(float* master, float* m, float* v, float* grad, void* param_bf16, int64_t seg, int64_t bucket_stride,
+                    int64_t nb, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                    float grad_scale, int adamw, int zero_grad, cudaStream_t s);
 int pg_sgd(float* master, float* mom, const float* grad, void* param_bf16, int64_t n, float lr,
            float momentum, float wd, float grad_scale, int first_step, cudaStream_t s);
 int pg_accum_bf16_to_f32(const void* src, float* dst, int64_t n, float scale, int accumulate,

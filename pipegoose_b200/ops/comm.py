@@ -434,7 +434,9 @@ class FusedDPEngine:
             native().set_gemm_cta_cap(0)
             self._capped = False
 
-    def reduce_bucket(self, view: torch.Tensor, mode: str, tail: bool = False):
+    def reduce_bucket(self, view: torch.Tensor, mode: str, tail: bool = False, bucket_numel: int = 0):
+        """``view``: one bucket, or (``bucket_numel`` > 0) a run of consecutive buckets of that size reduced by ONE
+        launch — each bucket slice-wise, so that ZeRO-1 ownership does not depend on how launches were merged."""
         offset = (view.data_ptr() - self._grad_base) // 4
         n = view.numel()
         ready = torch.cuda.Event()
@@ -444,7 +446,7 @@ class FusedDPEngine:
             self.stream.wait_event(ready)
             native().allreduce_f32([self.ws.data_ptr(p, self._grad_off) for p in range(self.world)], self.rank,
                                    offset, n, 1.0 / self.world, mode == "reduce_scatter", self._flag_ptrs(), self.epoch,
-                                   self.TAIL_CTAS if tail else self.OVERLAP_CTAS, self._mc_grad)
+                                   self.TAIL_CTAS if tail else self.OVERLAP_CTAS, self._mc_grad, bucket_numel)
             done = torch.cuda.Event()
             done.record()
         return _StreamWork(done)

@@ -80,7 +80,33 @@ class FusedAdam(torch.optim.Optimizer):
         self._fold_autograd_grads()
         grad_scale, self.pending_grad_scale = grad_scale * self.pending_grad_scale, 1.0
         self._step += 1
-        for off, s, e, gi in self._plan():
+        plan = self._plan()
+        done = set()
+        if use_native(self.flat.flat_param) and len(self.param_groups) == 1:
+            # ZeRO-1: the slices of equally sized buckets are equally long and equally spaced — ONE launch updates a
+            # whole run of them (87 launches -> 3 for bloom-560m at dp = 2)
+            g = self.param_groups[0]
+            lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
+            inline = getattr(self, "_inline_from", None)
+            i = 0
+            while i < len(plan):
+                off, s0, e0, _ = plan[i]
+                n = e0 - s0
+                j = i
+                while (j + 1 < len(plan) and plan[j + 1][2] - plan[j + 1][1] == n
+                       and (j == i or plan[j + 1][1] - plan[j][1] == plan[i + 1][1] - s0)):
+                    j += 1
+                if j > i and n % 4 == 0 and (plan[i + 1][1] - s0) % 4 == 0 and s0 % 4 == 0:
+                    nb = j - i + 1
+                    native().adam_step_strided(self.master[off:off + nb * n], self.exp_avg[off:off + nb * n],
+                                               self.exp_avg_sq[off:off + nb * n], self.flat.flat_grad, self.flat.flat_param,
+                                               s0, n, plan[i + 1][1] - s0, nb, lr, b1, b2, eps, wd, self._step, grad_scale,
+                                               g["adamw"], inline is not None and s0 >= inline)
+                    done.update(range(i, j + 1))
+                i = j + 1
+        for idx, (off, s, e, gi) in enumerate(plan):
+            if idx in done:
+                continue
             n = e - s
             g = self.param_groups[gi]
             lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]

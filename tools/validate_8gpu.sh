@@ -27,6 +27,8 @@ run() {  # run <tag> <bench args...>: both arms, JSON lines appended to gpurun_o
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm --format=csv | head -3
 echo "== config #2 (headline): bloom-560m TP2 x DP4 + ZeRO-1 (ours only; the driver runs both arms at round end)"
 timeout 300 python bench.py --gpus 8 --steps 8 --warmup 3 | tee gpurun_out/bench_8gpu_headline.json | line
+echo "-- NVLS off (multimem.ld_reduce / multimem.st not used by the dp = 4 reducer and all-gather)"
+PIPEGOOSE_B200_NVLS_REDUCE=0 PIPEGOOSE_B200_NVLS_ALLGATHER=0 timeout 300 python bench.py --gpus 8 --steps 8 --warmup 3 --no-self-check | line
 echo "== TP2 x DP4 step: phases and kernel table (torch profiler, diagnosis only)"
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29539 tools/dist_step_profile.py --tp 2 2>&1 | grep -v "^\*\|OMP\|^$\|arn" | head -30
 echo "== config #3: bloom-7b1 TP=8 seq 2048"
