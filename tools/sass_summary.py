@@ -41,8 +41,8 @@ for line in sass.splitlines():
 print("# SASS evidence per kernel (cuobjdump -sass pipegoose_b200/_C.so; sm_100a) — tools/sass_summary.py")
 print("# UTCHMMA = tcgen05.mma (.2CTA: cta_group::2), LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA tensor load/store,")
 print("# UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, LDGMC = multimem.ld_reduce (NVLS),")
-print("# (multimem.st compiles to STG.E.128.STRONG.SYS on the multicast address: the aperture, not the opcode, selects NVLS),
-# REDG = red.global (peer or local), USETMAXREG = setmaxnreg, ACQBULK / PREEXIT = griddepcontrol (PDL)")
+print("# (multimem.st compiles to STG.E.128.STRONG.SYS on the multicast address: the aperture, not the opcode, selects NVLS),")
+print("# REDG = red.global (peer or local), USETMAXREG = setmaxnreg, ACQBULK / PREEXIT = griddepcontrol (PDL)")
 print()
 merged = collections.OrderedDict()
 for k, c in counts.items():
