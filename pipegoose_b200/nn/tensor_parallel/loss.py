@@ -43,6 +43,15 @@ class _VocabParallelCrossEntropy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output: torch.Tensor):
         logits2, tgt, gstats = ctx.saved_tensors
+        from pipegoose_b200.ops import use_native
+
+        g = grad_output.reshape(-1)
+        if use_native(logits2) and g.numel() > 0 and (g.stride(0) == 0 or g.numel() == 1):
+            # every token carries the same upstream gradient (``loss.mean()`` / ``loss.sum()``): one pass of the fused
+            # kernel turns a bf16 copy of the logits into (softmax - onehot) * g — no fp32 [tokens, vocab/T] temporaries
+            work = logits2.clone()
+            K.ce_finalize(work, tgt, gstats, ctx.vocab_start, g[:1].float().contiguous(), ignore_index=-(1 << 62), write_grad=True)
+            return work.view(ctx.shape), None, None
         p = torch.exp(logits2.float() - gstats[:, 0:1]) / gstats[:, 1:2]
         t = tgt - ctx.vocab_start
         ok = (t >= 0) & (t < logits2.shape[1])
