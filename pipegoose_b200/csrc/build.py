@@ -26,8 +26,16 @@ NVCC_FLAGS = ARCH_FLAGS + [
 ]
 
 
+# PIPEGOOSE_B200_BUILD_VARIANT=<name> + PIPEGOOSE_B200_NVCC_EXTRA="-DFOO=1 ...": build pipegoose_b200/_C_<name>.so with extra
+# nvcc flags next to the main extension (loaded with PIPEGOOSE_B200_EXT=<name>): A/B of kernel variants in ONE gpurun call
+VARIANT = os.environ.get("PIPEGOOSE_B200_BUILD_VARIANT", "")
+NVCC_FLAGS = NVCC_FLAGS + os.environ.get("PIPEGOOSE_B200_NVCC_EXTRA", "").split()
+if VARIANT:
+    BUILD = CSRC / f"build_{VARIANT}"
+
+
 def so_path() -> Path:
-    return PKG / "_C.so"
+    return PKG / (f"_C_{VARIANT}.so" if VARIANT else "_C.so")
 
 
 def _hash(paths) -> str:

@@ -160,12 +160,20 @@ PG_DEVICE TileCoord map_tile(int t, int m_blks_per_chunk, int n_blks, int num_ch
 // csrc/comm.cu) can run NEXT TO a persistent GEMM CTA instead of waiting for a kernel boundary.  The roles then
 // re-balance: warps 0-3 (TMA producer, MMA issuer, TMEM allocator) drop to 40 registers, the two epilogue warpgroups
 // rise to 168 — 128*40 + 256*168 = 48 K, i.e. the epilogue keeps the budget it had when the CTA owned the whole file.
+#ifndef PG_GEMM_REBALANCE
+#define PG_GEMM_REBALANCE 1   // 0: the round-1 budget (384 x 168 registers, the CTA owns the SM's register file)
+#endif
 constexpr int kGemmLaunchRegs = 128;
 constexpr int kGemmLightRegs = 40;
 constexpr int kGemmEpilogueRegs = 168;
 
 template <int BN, bool A_MN, bool B_MN, bool CTA2>
-__global__ void __launch_bounds__(512, 1)  /* 65536 / 512 = 128 registers at launch; the block has 384 threads */
+__global__ void
+#if PG_GEMM_REBALANCE
+__launch_bounds__(512, 1)  /* 65536 / 512 = 128 registers at launch; the block has 384 threads */
+#else
+__launch_bounds__(kGemmThreads, 1)
+#endif
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_a_local, const GemmArgs args) {
@@ -303,7 +311,9 @@ __global__ void __launch_bounds__(512, 1)  /* 65536 / 512 = 128 registers at lau
 
   // each register re-balancing instruction dominates the code of its warpgroup(s): ptxas allocates per region
   if (warp < 4) {
+#if PG_GEMM_REBALANCE
     setmaxnreg_dec<kGemmLightRegs>();
+#endif
   if (warp == 0) {
     // ============================ TMA producer ============================
     int stage = 0;
@@ -427,7 +437,9 @@ __global__ void __launch_bounds__(512, 1)  /* 65536 / 512 = 128 registers at lau
     }
   }
   } else {
+#if PG_GEMM_REBALANCE
     setmaxnreg_inc<kGemmEpilogueRegs>();
+#endif
     // ============================ epilogue ============================
     // 8 warps: warp e = 4 + q + 4h drains TMEM lanes [32q, 32q+32) (a warp may only touch the lane
     // quarter warp%4) and takes every second 32-column chunk (c = h, h+2, ...).  Every global access
