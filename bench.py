@@ -488,9 +488,9 @@ def _build_reference(args, n_layer=None, vocab=None):
         from pipegoose.nn.expert_parallel import ExpertParallel, SwitchNoisePolicy, Top1Router
         from pipegoose.nn.expert_parallel.expert_context import ExpertContext
 
+        # (the reference's router computes its gate in fp32 — routers.py:109 `self.gate(inputs.float())` — so the router
+        #  keeps its fp32 parameters next to the bf16 model)
         router = Top1Router(SwitchNoisePolicy(), args.experts, h, expert_capacity=(1.25, 2.0))
-        if cuda:
-            router = router.to(torch.bfloat16)
         layers = list(range(0, L, max(args.moe_every, 1)))
         model = ExpertParallel(model, num_experts=args.experts, mapping=layers, router=router,
                                parallel_context=ctx).parallelize()
@@ -617,10 +617,15 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
-            # convenience: re-launch under torchrun
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                   "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__)] + sys.argv[1:]
-            os.execv(sys.executable, cmd)
+            # convenience: re-launch under torchrun (a port picked as free can be taken before torchrun binds it: retry)
+            for attempt in range(3):
+                cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                       "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+                res = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+                sys.stderr.write(res.stderr)
+                if res.returncode == 0 or "EADDRINUSE" not in res.stderr:
+                    raise SystemExit(res.returncode)
+            raise SystemExit(res.returncode)
         raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
     if args.impl == "reference":
         try:
