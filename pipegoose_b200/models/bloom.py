@@ -356,11 +356,11 @@ class BloomForCausalLM(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True, **_unused) -> torch.Tensor:
-        """Greedy decoding.  ``use_cache`` (unsharded model, dense MLPs): keys and values of every layer are kept, the
-        prompt is processed once and each new token costs one position; otherwise (tensor-parallel or MoE models)
-        every token recomputes the whole sequence through the training forward."""
+        """Greedy decoding.  ``use_cache`` (dense MLPs): keys and values of every layer are kept — under tensor
+        parallelism each rank caches the heads it owns — the prompt is processed once and each new token costs one
+        position; MoE models recompute the whole sequence through the training forward for every token."""
         dense = all(isinstance(b.mlp, BloomMLP) for b in self.transformer.h)
-        if not (use_cache and self.tp is None and dense):
+        if not (use_cache and dense):
             out = input_ids
             group = self.tp.size if self.tp is not None else 1
             for _ in range(max_new_tokens):
@@ -392,8 +392,11 @@ class BloomForCausalLM(nn.Module):
         B, T = ids.shape
         h, n_head = cfg.hidden_size, cfg.n_head
         D = h // n_head
+        tp = self.tp
+        if tp is not None:
+            return self._incremental_logits_tp(ids, cache, past)
         x = F.embedding(ids, t.word_embeddings.weight)
-        if cfg.position_embedding == "learned":
+        if getattr(cfg, "position_embedding", "alibi") == "learned":
             x = x + t.position_embeddings.weight[past:past + T]
         else:
             x = F.layer_norm(x, (h,), t.word_embeddings_layernorm.weight, t.word_embeddings_layernorm.bias, cfg.layer_norm_epsilon)
@@ -420,6 +423,59 @@ class BloomForCausalLM(nn.Module):
                              mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
         x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
         return F.linear(x, self.lm_head.weight)
+
+    def _incremental_logits_tp(self, ids: torch.Tensor, cache: list, past: int) -> torch.Tensor:
+        """:meth:`_incremental_logits` on a tensor-parallel model: activations are replicated ``[B, T, h]`` (decoding is
+        latency-bound: no sequence sharding), every rank runs the attention heads / MLP columns / vocabulary rows it owns
+        and caches ITS heads' keys and values; row-parallel products and the embedding are summed over the group, the
+        last position's logits are gathered along the vocabulary."""
+        import torch.distributed as dist
+        import torch.nn.functional as F
+
+        t, cfg, tp = self.transformer, self.config, self.tp
+        group, rank, world = tp.group, tp.rank, tp.size
+        B, T = ids.shape
+        h = cfg.hidden_size
+        D = h // cfg.n_head
+
+        def all_reduce(x):
+            dist.all_reduce(x, group=group)
+            return x
+
+        table = t.word_embeddings.weight                      # [V_padded / world, h]
+        local = ids - self.vocab_start
+        mine = (local >= 0) & (local < table.shape[0])
+        x = F.embedding(local.clamp(0, table.shape[0] - 1), table) * mine.unsqueeze(-1).to(table.dtype)
+        x = all_reduce(x)
+        if getattr(cfg, "position_embedding", "alibi") == "learned":
+            x = x + t.position_embeddings.weight[past:past + T]
+        else:
+            x = F.layer_norm(x, (h,), t.word_embeddings_layernorm.weight, t.word_embeddings_layernorm.bias, cfg.layer_norm_epsilon)
+        for li, block in enumerate(t.h):
+            attn, mlp = block.self_attention, block.mlp
+            n_local = attn.query_key_value.weight.shape[0] // (3 * D)
+            ln = F.layer_norm(x, (h,), block.input_layernorm.weight, block.input_layernorm.bias, block.eps)
+            qkv = F.linear(ln, attn.query_key_value.weight, attn.query_key_value.bias).view(B, T, n_local, 3, D)
+            q, k, v = (qkv[:, :, :, i].transpose(1, 2) for i in range(3))               # [B, H/world, T, D]
+            if cache[li] is not None:
+                k, v = torch.cat([cache[li][0], k], dim=2), torch.cat([cache[li][1], v], dim=2)
+            cache[li] = (k, v)
+            S = k.shape[2]
+            scores = torch.matmul(q.float(), k.float().transpose(-1, -2)) / math.sqrt(D)
+            key_pos = torch.arange(S, device=ids.device, dtype=torch.float32)
+            scores = scores + attn.alibi_slopes_local(n_local).view(1, n_local, 1, 1) * key_pos
+            query_pos = torch.arange(past, past + T, device=ids.device).view(T, 1)
+            scores = scores.masked_fill(key_pos.view(1, S) > query_pos, float("-inf"))
+            ctx = torch.matmul(scores.softmax(-1).to(v.dtype), v).transpose(1, 2).reshape(B, T, n_local * D)
+            x = x + all_reduce(F.linear(ctx, attn.dense.weight)) + attn.dense.bias      # row-parallel: bias once
+            ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
+            h1 = K.gelu_tanh(F.linear(ln, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias))
+            x = x + all_reduce(F.linear(h1, mlp.dense_4h_to_h.weight)) + mlp.dense_4h_to_h.bias
+        x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
+        part = F.linear(x, self.lm_head.weight).contiguous()                            # [B, 1, V_padded / world]
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part, group=group)
+        return torch.cat(parts, dim=-1)[..., : cfg.vocab_size]
 
     # ------------------------------------------------------------------ HF interop
     @classmethod

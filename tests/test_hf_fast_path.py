@@ -150,3 +150,23 @@ def test_hidden_dropout_trains_through_the_composed_path():
 def _no_dropout_loss(hf_model, ids):
     hf_model.eval()   # 🤗 dropout off == p -> 0
     return hf_model(input_ids=ids, labels=ids).loss
+
+
+def run_tp_cached_generate(rank, world_size, port, tp, state, ids, ref_tokens):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx, sequence_parallel=True).parallelize()
+    cached = model.generate(input_ids=ids, max_new_tokens=5)                     # KV cache, heads sharded over the group
+    assert torch.equal(cached, ref_tokens), (cached, ref_tokens)
+    assert torch.equal(model.generate(input_ids=ids, max_new_tokens=5, use_cache=False), ref_tokens)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp", [2, 4])
+def test_tensor_parallel_generation_with_kv_cache_matches_hf(tp):
+    torch.manual_seed(3)
+    model = _hf_bloom()
+    ids = torch.randint(0, 96, (2, 7))
+    ref = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=5, do_sample=False)
+    spawn(run_tp_cached_generate, world_size=tp, tp=tp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_tokens=ref)
