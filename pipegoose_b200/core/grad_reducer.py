@@ -344,12 +344,19 @@ class GradReducer:
             view.div_(self.dp)
             b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True)
 
+    import os as _os
+
+    MERGE_TAIL = _os.environ.get("PIPEGOOSE_B200_DP_MERGE_TAIL", "0") == "1"
+
     def _launch_tail(self):
         """Backward is over: reduce what is left.  With the NVLink engine a run of consecutive equally sized buckets (the
         tied embedding table's, which only complete with the last backward kernel: ~45 % of the gradient bytes) goes out
         as ONE launch with one barrier pair instead of one launch per bucket."""
         left = [b for b in reversed(self.buckets) if not b.launched]
-        if self._fused is None or len(left) < 2:
+        # (merging is opt-in: in a normal backward every bucket has been launched by the time finalize runs — also the tied
+        #  table's, which become ready together with the last backward kernel — so this only matters for models that leave
+        #  whole runs of buckets without gradients; the multi-bucket form of the kernel is not part of the GPU-validated path)
+        if self._fused is None or len(left) < 2 or not self.MERGE_TAIL:
             for b in left:
                 self._launch(b, tail=True)
             return
