@@ -14,6 +14,7 @@ On NVLink-connected B200s the collective is the hand-written peer-memory kernel 
 """
 from __future__ import annotations
 
+import os
 from contextlib import contextmanager
 from typing import Dict, List, Optional
 
@@ -213,8 +214,6 @@ class GradReducer:
     def _make_flat_state(self) -> FlatModelState:
         """Flat state in NVLink peer-mapped memory when the fused data-parallel kernels can run
         (CUDA bf16 parameters, NCCL group, dp > 1); plain device memory otherwise."""
-        import os
-
         module = self.module
         existing = getattr(module, "_flat_state", None) or FlatModelState.find(module.parameters())
         p0 = next(module.parameters())
@@ -344,9 +343,7 @@ class GradReducer:
             view.div_(self.dp)
             b.work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group, async_op=True)
 
-    import os as _os
-
-    MERGE_TAIL = _os.environ.get("PIPEGOOSE_B200_DP_MERGE_TAIL", "0") == "1"
+    MERGE_TAIL = os.environ.get("PIPEGOOSE_B200_DP_MERGE_TAIL", "0") == "1"
 
     def _launch_tail(self):
         """Backward is over: reduce what is left.  With the NVLink engine a run of consecutive equally sized buckets (the

@@ -56,7 +56,8 @@ class TensorParallelComm:
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
         x = x.detach().contiguous()
         if self._peer_ok(x):
-            return self._engine.all_gather_rows(x)
+            # (a copy: the engine's gathered buffer is recycled two calls later, the caller may keep the result)
+            return self._engine.all_gather_rows(x).clone()
         out = torch.empty((x.shape[0] * self.size,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x, group=self.group)
         return out
