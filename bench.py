@@ -5,16 +5,23 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3
     python bench.py --impl reference ...      # the unmodified reference (baseline/_ref) on the same config
+    python bench.py --gpus 2 --hf             # our arm fed with a transformers BloomForCausalLM (the reference's input)
+    python bench.py --device cpu --model bloom-tiny --seq-len 64 --batch-per-gpu 2 --gpus 2    # dry run of this script
 
 Metric/config follow BASELINE.json: bloom-560m, seq 1024, bf16, synthetic token ids, random-init
 weights, Adam; N=1 -> TP1xDP1, N>=2 -> TP2 x DP(N/2); per-GPU work is fixed (weak scaling):
-global batch = batch_per_gpu * N sequences.  One JSON line is printed by rank 0.
+global batch = batch_per_gpu * N sequences.  One JSON line is printed by rank 0; both arms spell the
+`config` dict identically (`config_of`).  `--model/--tp/--pp/--experts/--seq-len/--batch-per-gpu` select the
+other BASELINE.json configs for BOTH arms (bloom-7b1 TP8, Switch-MoE EP8, bloom-3b TP2xPP2xDP2).
 
 Two timed regions of K steps each, both bracketed by barrier + synchronize, timed with CUDA events
 on the device, max over ranks:
   value : full train step (fwd, bwd, grad sync, optimizer) with device-resident inputs
   e2e   : the same step through the public API including, every step, the pinned-host -> device
           copy of that step's token ids and a device -> host read of the loss.
+At N > 1 our arm first runs a numerics self-check (outside the timed regions): 3 steps of a 2-layer model of the
+benchmark's width through the fused NVLink engines and through NCCL + plain kernels; `numerics_ok`, the largest
+relative loss difference and the parameter-checksum difference travel in the JSON line.
 """
 from __future__ import annotations
 

@@ -21,12 +21,13 @@ def _load():
     global _C, _LOAD_ERROR
     if _C is not None or _LOAD_ERROR is not None:
         return
-    # PIPEGOOSE_B200_EXT=<name>: load an experimental build (pipegoose_b200/_C_<name>.so, made by tools/build_variants.sh
-    # from an exp/<name> branch) instead of the main one — lets ONE GPU call A/B kernel variants under identical Python
+    # PIPEGOOSE_B200_EXT=<name>: load a variant build (pipegoose_b200/_C_<name>.so, made with PIPEGOOSE_B200_BUILD_VARIANT=<name>
+    # PIPEGOOSE_B200_NVCC_EXTRA="-D..." python -m pipegoose_b200.csrc.build) instead of the main one — lets ONE GPU call A/B
+    # kernel variants under identical Python
     variant = os.environ.get("PIPEGOOSE_B200_EXT", "")
     so = Path(__file__).resolve().parent.parent / (f"_C_{variant}.so" if variant else "_C.so")
     if variant and not so.exists():
-        _LOAD_ERROR = FileNotFoundError(f"{so} not found: run tools/build_variants.sh")
+        _LOAD_ERROR = FileNotFoundError(f"{so} not found: build it with PIPEGOOSE_B200_BUILD_VARIANT={variant} (csrc/build.py)")
         return
     if not so.exists():
         if os.environ.get("PIPEGOOSE_B200_AUTOBUILD", "0") == "1":
