@@ -28,6 +28,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--microbatches", type=int, default=4)
     ap.add_argument("--backend", default="nccl" if torch.cuda.is_available() else "gloo")
+    ap.add_argument("--hf", action="store_true",
+                    help="start from a transformers BloomForCausalLM, exactly like the reference's README: TensorParallel "
+                         "converts it in place to the fused sequence-parallel path")
     args = ap.parse_args()
 
     parallel_context = ParallelContext.from_torch(
@@ -39,12 +42,20 @@ if __name__ == "__main__":
 
         cfg = getattr(GPT2Config, args.model)()
         model = GPT2LMHeadModel(cfg)
+    elif args.hf:
+        from transformers import BloomConfig as HFBloomConfig
+        from transformers import BloomForCausalLM as HFBloomForCausalLM
+
+        cfg = getattr(BloomConfig, args.model)()
+        model = HFBloomForCausalLM(HFBloomConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, n_layer=cfg.n_layer,
+                                                 n_head=cfg.n_head))
     else:
         cfg = getattr(BloomConfig, args.model)()
         model = BloomForCausalLM(cfg)
     if args.backend == "nccl":
         model = model.to(torch.bfloat16)
-    model = TensorParallel(model, parallel_context).parallelize()
+    # (bf16 transformers models take the fused path by default; sequence_parallel=True asks for it for fp32 CPU runs too)
+    model = TensorParallel(model, parallel_context, sequence_parallel=True if args.hf else None).parallelize()
     if args.pp > 1:
         model = PipelineParallel(model, num_microbatches=args.microbatches, parallel_context=parallel_context).parallelize()
     model = DataParallel(model, parallel_context).parallelize()
