@@ -172,16 +172,30 @@ class PipelineEngine:
         p = next(self.module.parameters(), None)
         return p.device if p is not None else torch.device("cpu")
 
+    def _stage_accepts(self, name: str) -> bool:
+        """Does this stage's ``forward`` take the keyword ``name``?  (Read once from its signature: stage modules are
+        plain ``nn.Module``s — the built-in Bloom / GPT-2 / LLaMA-style stages, ``SequentialStage``, or whatever a
+        ``UniformPartitioner.register_family`` stage class defines.)"""
+        sig = getattr(self, "_stage_signature", None)
+        if sig is None:
+            import inspect
+
+            try:
+                params = inspect.signature(self.module.forward).parameters
+                names = {n for n, p in params.items() if p.kind in (p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)}
+                var_kw = any(p.kind is p.VAR_KEYWORD for p in params.values())
+            except (TypeError, ValueError):
+                names, var_kw = set(), False
+            sig = self._stage_signature = (names, var_kw)
+        return name in sig[0] or sig[1]
+
     def _stage_forward(self, x, mb: Dict, with_labels: bool):
         kwargs = {}
-        fwd = self.module.forward
-        code = getattr(fwd, "__code__", None)
-        names = code.co_varnames[:code.co_argcount] if code is not None else ()
-        if "attention_mask" in names and mb.get("attention_mask") is not None:
+        if self._stage_accepts("attention_mask") and mb.get("attention_mask") is not None:
             kwargs["attention_mask"] = mb["attention_mask"]
-        if with_labels and self.is_last and "labels" in names:
+        if with_labels and self.is_last and self._stage_accepts("labels"):
             kwargs["labels"] = mb["labels"]
-        if "batch_seq" in names and "input_ids" in mb:
+        if self._stage_accepts("batch_seq") and "input_ids" in mb:
             kwargs["batch_seq"] = tuple(mb["input_ids"].shape[:2])
         return self.module(x, **kwargs)
 
