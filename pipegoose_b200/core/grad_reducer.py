@@ -111,6 +111,20 @@ class TensorPartialGradSync:
                 p._pg_grad_ready = self._on_ready
             if not hasattr(p, "_pg_tp_sync_hook"):
                 p._pg_tp_sync_hook = p.register_post_accumulate_grad_hook(self._on_ready)
+            if not hasattr(p, "_pg_tp_stash_hook"):
+                p._pg_tp_stash_hook = p.register_hook(lambda grad, p=p: self._stash(p, grad))
+
+    def _stash(self, p, grad):
+        """Parameters WITHOUT a flat fp32 main grad (a stock ``torch.optim`` on the sequence-parallel model): the partial
+        gradient of THIS backward is kept aside instead of being accumulated into ``p.grad``; ``finalize`` sums the
+        kept-aside parts over the tensor group and adds the result to ``p.grad``.  A SUM over the group is not idempotent:
+        summing ``p.grad`` itself would count an earlier, already complete contribution of the same step T times (two
+        backward passes before one optimizer step: gradient accumulation without ``no_sync``, or two losses)."""
+        if getattr(p, "main_grad", None) is not None or self._reducer_active():
+            return grad
+        pending = getattr(p, "_pg_tp_pending", None)
+        p._pg_tp_pending = grad.detach().clone() if pending is None else pending.add_(grad)
+        return torch.zeros_like(grad)
 
     def _reducer_active(self) -> bool:
         r = getattr(self.module, "_pg_grad_reducer", None)
@@ -126,8 +140,22 @@ class TensorPartialGradSync:
         self._queued = False
         if not self._sync or self._reducer_active():
             return
-        flat = FlatModelState.find(self.params)
-        reduce_tp_partial_grads(self.params, self.ctx, flat, comm=getattr(self.module, "tp", None))
+        comm = getattr(self.module, "tp", None)
+        stashed = [p for p in self.params if getattr(p, "_pg_tp_pending", None) is not None]
+        if stashed:
+            group = self.ctx.get_group(ParallelMode.TENSOR)
+            buf = torch.cat([p._pg_tp_pending.reshape(-1).float() for p in stashed])
+            _tp_all_reduce(buf, group, comm)
+            for p, part in zip(stashed, buf.split([p.numel() for p in stashed])):
+                total = part.view_as(p).to(p.dtype)
+                if p.grad is None:
+                    p.grad = total.clone()
+                else:
+                    p.grad.add_(total)
+                p._pg_tp_pending = None
+        rest = [p for p in self.params if getattr(p, "main_grad", None) is not None]
+        if rest:
+            reduce_tp_partial_grads(rest, self.ctx, FlatModelState.find(rest), comm=comm)
 
     @contextmanager
     def no_sync(self):

@@ -218,3 +218,34 @@ def run_shuffled_resume(rank, world_size, port, path):
 
 def test_resume_with_a_shuffled_dataloader_replays_the_same_batches(tmp_path):
     spawn(run_shuffled_resume, world_size=1, path=str(tmp_path / "ckpt"))
+
+
+def run_two_backwards_stock_optimizer(rank, world_size, port, state, ids, ref_params):
+    """Sequence-parallel model + plain torch.optim (no flat main grads), two synced backward passes, one step."""
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1)
+    model = BloomForCausalLM(BloomConfig(**CFG))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    opt.zero_grad()
+    model(ids[0], labels=ids[0]).loss.backward()
+    model(ids[1], labels=ids[1]).loss.backward()
+    opt.step()
+    for name, p in model.named_parameters():
+        if getattr(p, "tp_partial_grad", False):     # replicated parameters: compare in full
+            assert torch.allclose(p.detach(), ref_params[name], atol=2e-5), name
+    ctx.destroy()
+
+
+def test_stock_optimizer_on_the_sequence_parallel_model_two_backwards_per_step():
+    torch.manual_seed(2)
+    m = BloomForCausalLM(BloomConfig(**CFG))
+    state = copy.deepcopy(m.state_dict())
+    ids = torch.randint(0, 96, (2, 4, 16))
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    opt.zero_grad()
+    m(ids[0], labels=ids[0]).loss.backward()
+    m(ids[1], labels=ids[1]).loss.backward()
+    opt.step()
+    spawn(run_two_backwards_stock_optimizer, world_size=2, state=state, ids=ids,
+          ref_params={n: p.detach().clone() for n, p in m.named_parameters()})
