@@ -97,19 +97,23 @@ def exchange_fds(group, rank: int, world: int, my_fds: List[int], timeout_s: flo
     t.start()
     out: List[List[int]] = [[] for _ in range(world)]
     out[rank] = list(my_fds)
-    for r in range(world):
-        if r == rank:
-            continue
-        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
-            c.settimeout(timeout_s)
-            c.connect(names[r])
-            _msg, fds, _flags, _addr = socket.recv_fds(c, 16, len(my_fds))
-            out[r] = list(fds)
+    try:
+        for r in range(world):
+            if r == rank:
+                continue
+            with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+                c.settimeout(timeout_s)
+                c.connect(names[r])
+                _msg, fds, _flags, _addr = socket.recv_fds(c, 16, len(my_fds))
+                out[r] = list(fds)
+    except Exception as e:
+        errors.append(e)
     t.join(timeout_s)
     server.close()
     if errors:
         raise errors[0]
-    dist.barrier(group=group)
+    # (no collective here: a rank that failed above must not leave its peers in a barrier it never reaches — the caller
+    #  agrees on the outcome with one all-gather)
     return out
 
 
