@@ -409,6 +409,12 @@ class FusedDPEngine:
         K.unregister_grad_rs(self)
         self.inline_start = None
 
+    def __del__(self):   # a dead engine's address range must not capture gradients of later allocations
+        try:
+            K.unregister_grad_rs(self)
+        except Exception:
+            pass
+
     def _flag_ptrs(self):
         return [self.ws.sig_ptr(p, S.SIG_BARRIER) for p in range(self.world)]
 

@@ -25,12 +25,14 @@ _GRAD_RS_REGIONS = []   # [(first byte, end byte, descriptor dict for the kernel
 
 
 def register_grad_rs(begin: int, end: int, desc: dict, engine) -> None:
+    import weakref
+
     unregister_grad_rs(engine)
-    _GRAD_RS_REGIONS.append((begin, end, desc, engine))
+    _GRAD_RS_REGIONS.append((begin, end, desc, weakref.ref(engine)))   # (weak: a dropped engine unregisters itself)
 
 
 def unregister_grad_rs(engine) -> None:
-    _GRAD_RS_REGIONS[:] = [r for r in _GRAD_RS_REGIONS if r[3] is not engine]
+    _GRAD_RS_REGIONS[:] = [r for r in _GRAD_RS_REGIONS if r[3]() is not None and r[3]() is not engine]
 
 
 def grad_rs_for(t: Optional[torch.Tensor]):
@@ -38,8 +40,9 @@ def grad_rs_for(t: Optional[torch.Tensor]):
     if not _GRAD_RS_REGIONS or t is None or not t.is_cuda:
         return None
     ptr = t.data_ptr()
-    for begin, end, desc, engine in _GRAD_RS_REGIONS:
-        if begin <= ptr < end:
+    for begin, end, desc, ref in _GRAD_RS_REGIONS:
+        engine = ref()
+        if engine is not None and begin <= ptr < end:
             engine.inline_dirty = True
             return desc
     return None
