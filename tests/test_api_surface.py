@@ -132,3 +132,24 @@ def test_wrapper_and_parallelizer_shapes():
         assert hasattr(DistributedOptimizer, member), member
     assert {"module", "ckp_name", "ckp_path", "parallel_context"} <= set(_params(save_pretrained))
     assert _params(from_pretrained)[:3] == ["module", "ckp_path", "parallel_context"]
+
+
+def test_round2_public_surface():
+    """Names added in round 2 that scripts and docs rely on."""
+    import inspect
+
+    from pipegoose_b200.distributed import symmetric
+    from pipegoose_b200.models import bloom
+    from pipegoose_b200.nn import TensorParallel
+    from pipegoose_b200.nn.pipeline_parallel.partitioner import UniformPartitioner
+    from pipegoose_b200.nn.utils import capture_rng_state, from_pretrained, restore_rng_state
+    from pipegoose_b200.ops import kernels as K
+
+    assert callable(bloom.convert_hf_bloom_) and callable(bloom.is_hf_bloom) and callable(bloom.hf_bloom_fast_path_blocker)
+    assert "sequence_parallel" in inspect.signature(TensorParallel.__init__).parameters
+    assert callable(UniformPartitioner.register_family)
+    assert "strict" in inspect.signature(from_pretrained).parameters
+    assert set(capture_rng_state()) >= {"torch", "cuda", "python", "numpy"} and callable(restore_rng_state)
+    assert callable(symmetric.exchange_fds) and hasattr(symmetric.SymmetricWorkspace, "mc_data_ptr")
+    for name in ("register_grad_rs", "grad_rs_for", "ce_partials_buffer", "ce_stats_from_partials"):
+        assert callable(getattr(K, name)), name
