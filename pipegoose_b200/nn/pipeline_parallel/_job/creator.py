@@ -110,6 +110,39 @@ def create_job(function: Callable, package: Package, parallel_context, pipeline_
     return creator.create(function, package, parallel_context, pipeline_context)
 
 
+def schedule_backward_job(package: Package, pipeline_context=None, parallel_context=None) -> Package:
+    """Event-driven backward trigger (parity: reference _job/creator.py:162-180): the package's data passes through an
+    identity whose backward builds the :class:`BackwardJob` of this (micro-batch, partition) from the incoming
+    gradient and puts it into ``JobQueue.PENDING_JOBS`` for the worker pool.  The data is cut from the stage's graph
+    first (the backward job replays the gradient through the saved stage output; letting autograd also run on through
+    the stage would differentiate it twice).
+    The engines of this library drive backward from static schedule tables and do not need it; it is kept for code
+    written against the reference's job runtime."""
+    import torch
+
+    if parallel_context is None:
+        parallel_context = getattr(pipeline_context, "parallel_context", None)
+    if parallel_context is None:
+        from pipegoose_b200.distributed.parallel_context import ParallelContext
+
+        parallel_context = ParallelContext.get_context()
+
+    class _Trigger(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x.view_as(x)
+
+        @staticmethod
+        def backward(ctx, grad):
+            job = create_job(None, Package(grad.detach(), package.clone_metadata(job_type=JobType.BACKWARD)),
+                             parallel_context, pipeline_context)
+            Q.JobQueue.PENDING_JOBS.put(job)
+            return grad
+
+    package.data = _Trigger.apply(package.data.detach().requires_grad_(True))
+    return package
+
+
 def schedule_backward_execution(package: Package, pipeline_context=None):
     """Wrap the last stage's output so that ``loss.backward()`` records d loss / d output in the grad-loss
     store (``queue.get_grad_loss``) instead of flowing into the stage: backward jobs start from it."""

@@ -226,6 +226,11 @@ class RotaryDecoderStage(nn.Module):
         return logits
 
 
+# Names of the tensors a pipeline's first stage takes (parity: reference partitioner.py:14); ``split`` accepts the
+# argument for call compatibility, the stage modules here take these two by keyword.
+INPUT_NAMES = ["input_ids", "attention_mask"]
+
+
 class BasePartitioner:
     """``split(input_names) -> [stage modules]`` (parity: reference partitioner.py:20-26)."""
 

@@ -20,11 +20,19 @@ class TrainingState(Enum):
 
 
 class PipelineContext:
+    _current: "PipelineContext" = None    # the most recently constructed one of this process
+
     def __init__(self, scheduler: BaseScheduler, parallel_context: ParallelContext):
         self.scheduler = scheduler
         self.parallel_context = parallel_context
         self._clock_idx = 0
         self._state = TrainingState.IDLE
+        PipelineContext._current = self
+
+    @staticmethod
+    def get_context() -> "PipelineContext":
+        """The process's pipeline context (parity: reference pipeline_context.py:36-42, a module global)."""
+        return PipelineContext._current
 
     # ------------------------------------------------------------------ state
     @property

@@ -20,6 +20,7 @@ handshake and never sent again (the reference sends dtype/shape/requires_grad wi
 from __future__ import annotations
 
 from contextlib import nullcontext
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -34,6 +35,24 @@ from pipegoose_b200.nn.pipeline_parallel._utils import get_partition_idx
 from pipegoose_b200.nn.pipeline_parallel.scheduler import BaseScheduler
 from pipegoose_b200.nn.pipeline_parallel.task import Task
 
+
+
+@dataclass
+class Schedule:
+    """What one rank runs at one clock, in the reference's field order (parity: reference pipeline_engine.py:29-33).
+    The schedulers here produce :class:`~pipegoose_b200.nn.pipeline_parallel.task.Task` (hashable, micro-batch first);
+    ``Schedule.from_task`` / ``to_task`` convert."""
+
+    job_type: JobType
+    partition_idx: int
+    microbatch_idx: int
+
+    @classmethod
+    def from_task(cls, task: Task) -> "Schedule":
+        return cls(task.job_type, task.partition_idx, task.microbatch_idx)
+
+    def to_task(self) -> Task:
+        return Task(self.job_type, self.microbatch_idx, self.partition_idx)
 
 
 def broadcast_loss_from_last_stage(loss: torch.Tensor, parallel_context) -> torch.Tensor:
@@ -144,6 +163,8 @@ class _SendToNext(torch.autograd.Function):
 
 
 class PipelineEngine:
+    MASTER_RANK = 0   # the stage that owns the clock in the reference (pipeline_engine.py:39); also the first stage here
+
     def __init__(self, module: nn.Module, scheduler: BaseScheduler, worker_manager=None,
                  parallel_context: ParallelContext = None, pipeline_context=None, full_module: Optional[nn.Module] = None):
         # ``worker_manager``: the reference's third argument (pipeline_engine.py:36-58); the static runtime executes its

@@ -41,6 +41,13 @@ def _store_for(parallel_context: ParallelContext, parallel_mode: ParallelMode, t
 
 
 class Handshake(ABC):
+    # class-level defaults so the attributes can be read off the class like in the reference (handshake.py:34-38, where
+    # they are process-wide class state); here every handshake instance keeps its own
+    master_rank: Optional[int] = None
+    callbacks: List[Callback] = ()
+    parallel_context: ParallelContext = None
+    parallel_mode: ParallelMode = None
+
     def __init__(self, master_rank: int, callbacks: List[Callback] = (), parallel_context: ParallelContext = None,
                  parallel_mode: ParallelMode = ParallelMode.GLOBAL):
         self.master_rank = master_rank

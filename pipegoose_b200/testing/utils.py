@@ -100,6 +100,10 @@ def init_parallel_context(rank, world_size, port, tensor_parallel_size, pipeline
     )
 
 
+N_PARTITIONS = 3      # the reference's defaults for init_pipeline_context (testing/utils.py:66-67); the number of
+N_MICROBATCHES = 5    # partitions that is actually used is always the pipeline-parallel size
+
+
 def init_pipeline_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size, data_parallel_size,
                           n_partitions=None, n_microbatches=None):
     from pipegoose_b200.nn.pipeline_parallel.pipeline_context import PipelineContext
@@ -108,7 +112,7 @@ def init_pipeline_context(rank, world_size, port, tensor_parallel_size, pipeline
     parallel_context = init_parallel_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size,
                                              data_parallel_size)
     n_partitions = n_partitions or pipeline_parallel_size
-    n_microbatches = n_microbatches or 4
+    n_microbatches = n_microbatches or N_MICROBATCHES
     scheduler = get_scheduler(SchedulerType.GPIPE)(n_microbatches, n_partitions)
     pipeline_context = PipelineContext(scheduler, parallel_context)
     return pipeline_context, parallel_context

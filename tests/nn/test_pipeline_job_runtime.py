@@ -15,7 +15,7 @@ from pipegoose_b200.nn.pipeline_parallel import queue as Q
 from pipegoose_b200.nn.pipeline_parallel._comm import RECV_QUEUE, recv_package, send_package
 from pipegoose_b200.nn.pipeline_parallel._job.backward import BackwardJob
 from pipegoose_b200.nn.pipeline_parallel._job.callback import Callback, CallbackEvent
-from pipegoose_b200.nn.pipeline_parallel._job.creator import create_job, schedule_backward_execution
+from pipegoose_b200.nn.pipeline_parallel._job.creator import create_job, schedule_backward_execution, schedule_backward_job
 from pipegoose_b200.nn.pipeline_parallel._job.forward import ForwardJob
 from pipegoose_b200.nn.pipeline_parallel._job.job import Job, JobStatus
 from pipegoose_b200.nn.pipeline_parallel._job.job_type import JobType
@@ -179,7 +179,8 @@ def test_send_recv_package(dtype):
     spawn(run_send_recv_package, world_size=2, dtype=dtype)
 
 
-def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, ref_input_grad, ref_loss, use_callback=False):
+def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, ref_input_grad, ref_loss, use_callback=False,
+                         use_trigger=False):
     """Two stages, GPipe order, every step a job created by ``create_job`` from a package."""
     ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
     Q.clear_all()
@@ -214,6 +215,18 @@ def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, 
             outs.append(job.output)
         for i in reversed(range(n_mb)):
             # loss.backward() only records d loss / d output; the backward job replays it through the stage
+            if use_trigger:    # event-driven: loss.backward() itself leaves the backward job in the pending queue
+                assert Q.JobQueue.PENDING_JOBS.empty()
+                y = schedule_backward_job(outs[i], parallel_context=ctx).data
+                loss = y.pow(2).sum() / batch.shape[0]
+                losses.append(loss.item())
+                loss.backward()
+                bjob = Q.JobQueue.PENDING_JOBS.get_nowait()
+                assert isinstance(bjob, BackwardJob) and Q.JobQueue.PENDING_JOBS.empty()
+                m = bjob.input.metadata
+                assert (m.microbatch_idx, m.partition_idx, m.job_type) == (i, 1, JobType.BACKWARD)
+                bjob.compute()
+                continue
             if use_callback:   # ScheduleBackwardJobCallback already swapped the output for the recording wrapper
                 y = outs[i].data
                 assert y is Q._SAVED_SCHEDULED_ACTIVATIONS[(i, 1)] and y.requires_grad
@@ -231,7 +244,7 @@ def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, 
     ctx.destroy()
 
 
-@pytest.mark.parametrize("use_callback", [False, True])
+@pytest.mark.parametrize("use_callback", [False, True, "trigger"])
 def test_forward_backward_jobs_match_sequential_execution(use_callback):
     torch.manual_seed(1)
     stages = [nn.Sequential(nn.Linear(8, 8), nn.Tanh()) for _ in range(2)]
@@ -241,7 +254,8 @@ def test_forward_backward_jobs_match_sequential_execution(use_callback):
     loss.backward()
     ref_grads = [{n: p.grad.clone() for n, p in s.named_parameters()} for s in stages]
     spawn(run_pipeline_of_jobs, world_size=2, state_dicts=[s.state_dict() for s in stages], batch=batch,
-          ref_grads=ref_grads, ref_input_grad=x.grad.clone(), ref_loss=loss.item(), use_callback=use_callback)
+          ref_grads=ref_grads, ref_input_grad=x.grad.clone(), ref_loss=loss.item(), use_callback=use_callback is True,
+          use_trigger=use_callback == "trigger")
 
 
 # ------------------------------------------------------------------------------------------ sync

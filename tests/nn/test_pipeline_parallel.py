@@ -93,6 +93,7 @@ def test_partitioner_reproduces_model(pp):
 def run_pipeline_context(rank, world_size, port):
     pctx, ctx = init_pipeline_context(rank, world_size, port, 1, world_size, 1, n_microbatches=4)
     assert pctx.partition_idx == rank and pctx.num_microbatches == 4
+    assert type(pctx).get_context() is pctx
     assert pctx.is_first_stage == (rank == 0) and pctx.is_last_stage == (rank == world_size - 1)
     assert pctx.state is TrainingState.IDLE
     pctx.forward()

@@ -29,7 +29,11 @@ SURFACE = {
     "pipegoose_b200.nn.expert_parallel.utils": ["get_num_local_experts"],
     "pipegoose_b200.nn.pipeline_parallel": ["PipelineParallel"],
     "pipegoose_b200.nn.pipeline_parallel.scheduler": ["GPipeScheduler", "SchedulerType", "get_scheduler"],
-    "pipegoose_b200.nn.pipeline_parallel.partitioner": ["UniformPartitioner"],
+    "pipegoose_b200.nn.pipeline_parallel.partitioner": ["UniformPartitioner", "BasePartitioner", "PartitionPolicy", "INPUT_NAMES",
+                                                        "get_model_partition"],
+    "pipegoose_b200.nn.pipeline_parallel.pipeline_engine": ["PipelineEngine", "Schedule"],
+    "pipegoose_b200.nn.pipeline_parallel._job.creator": [
+        "create_job", "schedule_backward_job", "schedule_backward_execution", "ScheduleBackwardJobCallback", "JobCreator"],
     "pipegoose_b200.nn.pipeline_parallel.microbatch": ["split"],
     "pipegoose_b200.nn.pipeline_parallel.pipeline_context": ["PipelineContext"],
     "pipegoose_b200.nn.pipeline_parallel._utils": ["get_partition_idx", "is_last_stage"],
@@ -45,7 +49,8 @@ SURFACE = {
     "pipegoose_b200.core.bucket.exception": ["BucketFullError", "BucketClosedError"],
     "pipegoose_b200.testing.utils": [
         "spawn", "init_parallel_context", "find_free_port", "skip_if_no_cuda", "skip_in_github_actions",
-        "get_partition", "calculate_parameter_similarity", "count_model_parameters"],
+        "get_partition", "calculate_parameter_similarity", "count_model_parameters", "init_pipeline_context", "get_microbatch",
+        "N_PARTITIONS", "N_MICROBATCHES"],
     "pipegoose_b200.trainer": ["Trainer", "Callback", "DistributedLogger", "TrainerState"],
 }
 

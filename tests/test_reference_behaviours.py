@@ -223,3 +223,20 @@ def test_gpipe_full_schedule_is_forward_then_backward():
     order = sch.get_stage_order(1)
     assert [(t.job_type, t.microbatch_idx) for t in order] == [(JobType.FORWARD, 0), (JobType.FORWARD, 1), (JobType.FORWARD, 2),
                                                                (JobType.BACKWARD, 2), (JobType.BACKWARD, 1), (JobType.BACKWARD, 0)]
+
+
+# ---------------------------------------------------------------------------------------------------- small parity names
+def test_schedule_record_and_module_constants():
+    from pipegoose_b200.nn.pipeline_parallel.partitioner import INPUT_NAMES
+    from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import PipelineEngine, Schedule
+    from pipegoose_b200.nn.pipeline_parallel.sync.handshake import Handshake
+    from pipegoose_b200.nn.pipeline_parallel.task import Task
+    from pipegoose_b200.testing.utils import N_MICROBATCHES, N_PARTITIONS
+
+    s = Schedule(JobType.BACKWARD, 2, 5)    # the reference's field order: job type, partition, micro-batch
+    assert (s.partition_idx, s.microbatch_idx) == (2, 5)
+    t = s.to_task()
+    assert t == Task(JobType.BACKWARD, 5, 2) and Schedule.from_task(t) == s
+    assert INPUT_NAMES == ["input_ids", "attention_mask"] and PipelineEngine.MASTER_RANK == 0
+    assert (N_PARTITIONS, N_MICROBATCHES) == (3, 5)
+    assert Handshake.master_rank is None and Handshake.parallel_context is None
