@@ -60,6 +60,13 @@ class SavedActivation(_Store):
     _data = _SAVED_ACTIVATIONS
 
     @classmethod
+    def save_activations(cls, key: ActivationKey, data, is_by_schedule: bool = False):
+        """``is_by_schedule`` (accepted and ignored by the reference, queue.py:54-56): keep the output in the store of
+        the backward-trigger wrappers instead of the plain one."""
+        with _LOCK:
+            (_SAVED_SCHEDULED_ACTIVATIONS if is_by_schedule else cls._data)[key] = data
+
+    @classmethod
     def get_saved_activations(cls, key: ActivationKey):
         with _LOCK:
             return cls._data.pop(key)

@@ -180,6 +180,8 @@ def test_activation_queues():
         # SavedActivation.get_saved_activations consumes the entry (the backward job takes it exactly once)
         key = Q.SavedActivation.get_key(2, 1)
         assert Q.SavedActivation.get_saved_activations(key) is b and not Q.SavedActivation.is_saved(2, 1)
+        Q.SavedActivation.save_activations(key, b, is_by_schedule=True)   # goes to the store of the backward triggers
+        assert not Q.SavedActivation.is_saved(2, 1) and Q._SAVED_SCHEDULED_ACTIVATIONS[key] is b
         # the gradient of the loss of a micro-batch is consumed by its backward job
         g = torch.ones(4)
         Q.save_grad_loss(g, 0, 3)
