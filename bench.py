@@ -486,7 +486,7 @@ def _build_reference(args, n_layer=None, vocab=None):
 
     with (dev if _init_on_gpu(args) else contextlib.nullcontext()):   # same rule in both arms
         model = BloomForCausalLM(cfg)
-    if cuda:
+    if cuda or os.environ.get("PIPEGOOSE_B200_BENCH_CPU_BF16") == "1":   # the env switch: dtype flow of the dry run = GPU run
         model = model.to(torch.bfloat16)
     loss_terms = None
     if args.experts > 0:

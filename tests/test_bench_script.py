@@ -11,9 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 COMMON = ["--device", "cpu", "--model", "bloom-tiny", "--seq-len", "32", "--batch-per-gpu", "2", "--steps", "2", "--warmup", "3"]
 
 
-def _run(extra):
+def _run(extra, env=None):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + COMMON + extra, capture_output=True, text=True,
-                         timeout=600, cwd=ROOT)
+                         timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, out.stdout[-2000:] + out.stderr[-2000:]
     return json.loads(lines[0])
@@ -54,3 +54,15 @@ def test_both_arms_print_one_json_line_with_the_same_config(extra):
     assert ref["config"] == ours["config"] and ref["metric"] == ours["metric"]
     if extra[-1] != "1":
         assert ours["numerics_ok"] is True      # the self-check ran (on CPU both engines are the library path)
+
+
+def test_moe_config_both_arms_and_the_reference_arm_in_bf16():
+    """BASELINE.json config #4 shape (Switch-MoE, experts sharded over the tensor group).  The reference arm runs with the
+    model cast to bf16 as on the GPU: its router stays fp32 (it casts its own input), everything else must cope."""
+    extra = ["--gpus", "2", "--tp", "2", "--experts", "2"]
+    ours = _run(extra + ["--no-self-check"])
+    ref = _run(extra + ["--impl", "reference"], env={"PIPEGOOSE_B200_BENCH_CPU_BF16": "1"})
+    assert ref["impl"] == "reference" and ref["config"] == ours["config"]
+    assert ours["config"]["parallelism"] == "tp2dp1+moe2e"
+    for line in (ours, ref):
+        assert line["final_loss"] == line["final_loss"] and 0 < line["final_loss"] < 20   # finite, of the order of ln(vocab)
