@@ -3,6 +3,7 @@ parameters, multi-bucket tail launches, ZeRO slices and parameter all-gather reg
 CPU with a stand-in engine that speaks the engine's interface over gloo."""
 import copy
 
+import pytest
 import torch
 import torch.distributed as dist
 
@@ -71,7 +72,8 @@ class StandInEngine:
             flat_param[s:e] = torch.cat(parts)
 
 
-def run_engine(rank, world_size, port, state, ids, ref_state):
+def run_engine(rank, world_size, port, state, ids, ref_state, cfg=None, bucket_mb=0.02):
+    cfg = cfg or CFG
     ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size)
     engine = StandInEngine(ctx)
 
@@ -82,9 +84,9 @@ def run_engine(rank, world_size, port, state, ids, ref_state):
         return st
 
     GradReducer._make_flat_state = make_flat_state
-    model = BloomForCausalLM(BloomConfig(**CFG))
+    model = BloomForCausalLM(BloomConfig(**cfg))
     model.load_state_dict(state)
-    model = DataParallel(model, ctx, bucket_size_mb=0.02).parallelize()
+    model = DataParallel(model, ctx, bucket_size_mb=bucket_mb).parallelize()
     optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-3), ctx)
     local = ids.chunk(world_size)[rank]
     for _ in range(3):
@@ -95,7 +97,7 @@ def run_engine(rank, world_size, port, state, ids, ref_state):
     reducer = model._pg_grad_reducer
     flat = reducer.flat
     assert 0 < reducer.head == flat.matrix_start < flat.numel                       # small parameters got their own bucket
-    assert reducer.buckets[0].end == reducer.head and len(reducer.buckets) > 3
+    assert reducer.buckets[0].end == reducer.head and len(reducer.buckets) >= 3
     assert all(p.dim() < 2 for b in reducer.buckets[:1] for p in b.params)
     segs = optim.optim._segments
     assert segs[0][1] <= reducer.head and segs[1][0] >= reducer.head                # ZeRO slices are cut around the head
@@ -120,15 +122,21 @@ def run_engine(rank, world_size, port, state, ids, ref_state):
     ctx.destroy()
 
 
-def test_head_bucket_merged_tail_and_zero_slices_with_an_engine():
+@pytest.mark.parametrize("world,cfg,bucket_mb", [
+    (2, CFG, 0.02),
+    (3, dict(vocab_size=100, hidden_size=48, n_layer=2, n_head=4), 0.01),     # sizes that do not divide by the group size
+    (4, dict(vocab_size=50, hidden_size=32, n_layer=1, n_head=2), 0.008),     # buckets smaller than the embedding table
+])
+def test_head_bucket_merged_tail_and_zero_slices_with_an_engine(world, cfg, bucket_mb):
     torch.manual_seed(0)
-    model = BloomForCausalLM(BloomConfig(**CFG))
+    model = BloomForCausalLM(BloomConfig(**cfg))
     state = copy.deepcopy(model.state_dict())
-    ids = torch.randint(0, 96, (4, 16))
+    ids = torch.randint(0, cfg["vocab_size"], (12, 16))
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     for _ in range(3):
         loss = model(ids, labels=ids).loss
         opt.zero_grad()
         loss.backward()
         opt.step()
-    spawn(run_engine, world_size=2, state=state, ids=ids, ref_state={k: v.clone() for k, v in model.state_dict().items()})
+    spawn(run_engine, world_size=world, state=state, ids=ids, ref_state={k: v.clone() for k, v in model.state_dict().items()},
+          cfg=cfg, bucket_mb=bucket_mb)
