@@ -63,3 +63,41 @@ def test_groups_that_span_hosts_are_detected():
     from pipegoose_b200.testing.utils import spawn
 
     spawn(_run_node_probe, world_size=4)
+
+
+def test_exhaustive_small_layouts_are_orthogonal_partitions():
+    """Every (tp, pp, dp) with up to 48 ranks: groups of a mode partition the world into equally sized groups, groups
+    of two different modes meet in exactly one rank (the layouts are orthogonal axes of one grid), tensor-parallel peers
+    are adjacent ranks (they share NVLink inside a node) and the pipeline axis is the outermost one."""
+    axes = {ParallelMode.TENSOR: "tp", ParallelMode.PIPELINE: "pp", ParallelMode.DATA: "dp"}
+    n = 0
+    for tp in (1, 2, 3, 4, 8):
+        for pp in (1, 2, 3, 4):
+            for dp in (1, 2, 3, 4, 6):
+                world = tp * pp * dp
+                if world > 48:
+                    continue
+                n += 1
+                topo = Topology(world, tp, pp, dp)
+                size = {ParallelMode.TENSOR: tp, ParallelMode.PIPELINE: pp, ParallelMode.DATA: dp}
+                for mode in axes:
+                    groups = topo.groups(mode)
+                    assert all(len(g) == size[mode] for g in groups) and len(groups) == world // size[mode]
+                    assert sorted(r for g in groups for r in g) == list(range(world))
+                    assert all(g == sorted(g) for g in groups)
+                for g in topo.groups(ParallelMode.TENSOR):
+                    assert g == list(range(g[0], g[0] + tp))
+                for g in topo.groups(ParallelMode.PIPELINE):
+                    assert all(b - a == tp * dp for a, b in zip(g, g[1:]))
+                for m1 in axes:
+                    for m2 in axes:
+                        if m1 is m2 or size[m1] == 1 or size[m2] == 1:
+                            continue
+                        for g1 in topo.groups(m1):
+                            for g2 in topo.groups(m2):
+                                assert len(set(g1) & set(g2)) <= 1
+                        # ... and through every rank passes exactly one group of each mode
+                for r in range(world):
+                    for mode in axes:
+                        assert sum(r in g for g in topo.groups(mode)) == 1
+    assert n > 50
