@@ -112,7 +112,10 @@ class FlatModelState:
         overwrites instead of accumulating (``param._mg_fresh``); only the small 1-D parameters,
         whose gradients are built with atomics, are cleared here."""
         if getattr(self, "hold_grads", False):
-            return  # produced by a pipeline schedule inside forward and not consumed by the optimizer yet
+            # produced by a pipeline schedule inside forward; the caller's ``loss.backward()`` has not run yet: this is the
+            # ``zero_grad()`` of the canonical loop (forward, zero_grad, backward, step) and must not drop them
+            return
+        self.clears = getattr(self, "clears", 0) + 1    # (pipeline engines: a schedule after a real clear starts afresh)
         self.grads_materialized = False
         self.begin_grad_window()
         if self.inline is not None:

@@ -151,7 +151,7 @@ class JobPipelineEngine:
             if p.grad is not None:
                 parked.append((p, p.grad))
                 p.grad = None
-        return CausalLMOutput(loss=_InstallGrads.apply(total.detach().requires_grad_(True), parked), logits=None)
+        return CausalLMOutput(loss=_InstallGrads.apply(total.detach().requires_grad_(True), parked, flat), logits=None)
 
     def destroy(self):
         self.worker_manager.destroy()

@@ -115,8 +115,10 @@ class _InstallGrads(torch.autograd.Function):
     """Identity on the loss; backward adds the gradients the pipeline schedule already computed to ``.grad``."""
 
     @staticmethod
-    def forward(ctx, loss, parked):
+    def forward(ctx, loss, parked, flat=None, engine=None):
         ctx.parked = parked
+        ctx.flat = flat
+        ctx.engine = engine
         return loss.clone()
 
     @staticmethod
@@ -124,7 +126,18 @@ class _InstallGrads(torch.autograd.Function):
         for p, g in ctx.parked:
             p.grad = g if p.grad is None else p.grad + g
         ctx.parked = []
-        return None, None
+        flat, engine = ctx.flat, ctx.engine
+        if engine is not None:
+            flat = engine._flat_state()     # (a fused optimizer may have built the flat state after the forward)
+        if flat is not None:
+            # the window in which a ``zero_grad()`` must be ignored (between forward and this backward) is over: from
+            # here on the flat fp32 gradients behave like any accumulated gradients — a ``zero_grad()`` drops them
+            flat.hold_grads = False
+        if engine is not None:
+            # whatever was cleared up to here was cleared BEFORE these gradients were installed: only later clears drop them
+            engine._versions_after_schedule = engine._grad_epoch(flat)
+        ctx.flat = ctx.engine = None
+        return None, None, None, None
 
 
 class _RecvFromPrev(torch.autograd.Function):
@@ -299,14 +312,19 @@ class PipelineEngine:
                 return st
         return None
 
-    def _optimizer_stepped_since_last_schedule(self, flat) -> bool:
-        """Did an optimizer consume the gradients of the previous schedule?  FusedAdam counts its steps; a stock optimizer
-        updates the parameters in place, which moves their version counters."""
+    def _grad_epoch(self, flat):
+        """Changes whenever the gradients of a schedule were consumed or dropped: FusedAdam counts its steps, a stock
+        optimizer updates the parameters in place (their version counters move), a ``zero_grad()`` that really cleared
+        the flat fp32 gradients is counted by the flat state."""
         from pipegoose_b200.optim.fused_adam import FusedAdam
 
-        now = (sum(p._version for p in self.module.parameters()), FusedAdam.steps_taken)
+        return (sum(p._version for p in self.module.parameters()), FusedAdam.steps_taken, getattr(flat, "clears", 0))
+
+    def _optimizer_stepped_since_last_schedule(self, flat) -> bool:
+        """Does this schedule start from scratch (True) or add to the gradients of the previous one (gradient
+        accumulation: nothing consumed or dropped them in between)?"""
         last = getattr(self, "_versions_after_schedule", None)
-        return last is None or now != last
+        return last is None or self._grad_epoch(flat) != last
 
     def train_step(self, inputs: Dict, loss_scale: float = 1.0) -> torch.Tensor:
         # Backward runs inside this call, i.e. BEFORE the user's `optim.zero_grad()` of the canonical loop
@@ -425,10 +443,8 @@ class PipelineEngine:
             g = getattr(self.tied_param, "main_grad", None)
             (g if g is not None else self.tied_param.grad).add_(tied_stash)
         if flat is not None:
-            flat.hold_grads = True  # survive the zero_grad() that follows forward in the canonical loop
-        from pipegoose_b200.optim.fused_adam import FusedAdam
-
-        self._versions_after_schedule = (sum(p._version for p in self.module.parameters()), FusedAdam.steps_taken)
+            flat.hold_grads = True  # survive the zero_grad() that follows forward in the canonical loop (until backward)
+        self._versions_after_schedule = self._grad_epoch(flat)
         if self.is_last:
             total = torch.stack(losses).sum()
         else:
@@ -506,4 +522,4 @@ class PipelineEngine:
             if p.grad is not None:  # autograd grads, or main grads the data-parallel reducer materialised
                 parked.append((p, p.grad))
                 p.grad = None
-        return CausalLMOutput(loss=_InstallGrads.apply(loss.detach().requires_grad_(True), parked), logits=None)
+        return CausalLMOutput(loss=_InstallGrads.apply(loss.detach().requires_grad_(True), parked, None, self), logits=None)

@@ -184,6 +184,7 @@ class DistributedOptimizer(BaseDistributedOptimizer):
         held = bool(getattr(flat, "hold_grads", False))
         if flat is not None and not held:
             flat.begin_grad_window()
+            flat.clears = getattr(flat, "clears", 0) + 1
         for p in self._all_params:
             p.grad = None
             if hasattr(p, "main_grad") and not held:

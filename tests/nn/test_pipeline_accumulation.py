@@ -58,3 +58,33 @@ def test_pipelined_loss_under_no_grad_and_trainer_evaluate():
     with torch.no_grad():
         a = m(ids, labels=ids).loss; b = m(ids.flip(0), labels=ids.flip(0)).loss
     spawn(run_pp_eval, world_size=4, state=copy.deepcopy(m.state_dict()), ids=ids, ref_loss=a, ref_eval=((a + b) / 2).item())
+
+
+def run_pp_dropped_step(rank, world_size, port, state, batches, ref_state, fused):
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    m = BloomForCausalLM(BloomConfig(**CFG)); m.load_state_dict(state)
+    names = {id(p): n for n, p in m.named_parameters()}
+    m = PipelineParallel(m, num_microbatches=2, parallel_context=ctx).parallelize()
+    o = DistributedOptimizer(FusedAdam(m.parameters(), lr=1e-2, eps=1e-3) if fused else torch.optim.SGD(m.parameters(), lr=0.5), ctx)
+    # step 1 is abandoned after backward (what a loss scaler does on overflow): zero_grad BEFORE the next forward drops it
+    loss = m(batches[0], labels=batches[0]).loss
+    o.zero_grad()          # canonical position, between forward and backward: must NOT lose the schedule's gradients
+    loss.backward()
+    o.zero_grad()          # after backward: an ordinary zero_grad — the gradients are gone
+    loss = m(batches[1], labels=batches[1]).loss
+    loss.backward()
+    o.step()
+    for p in m._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.detach(), ref_state[names[id(p)]], atol=3e-5), names[id(p)]
+    ctx.destroy()
+@pytest.mark.parametrize("fused", [True, False])
+def test_zero_grad_is_only_ignored_between_pipelined_forward_and_backward(fused):
+    torch.manual_seed(0)
+    m = BloomForCausalLM(BloomConfig(**CFG)); state = copy.deepcopy(m.state_dict())
+    batches = [torch.randint(0, 96, (4, 8)) for _ in range(2)]
+    opt = FusedAdam(m.parameters(), lr=1e-2, eps=1e-3) if fused else torch.optim.SGD(m.parameters(), lr=0.5)
+    opt.zero_grad()
+    m(batches[1], labels=batches[1]).loss.backward()     # only the second batch counts
+    opt.step()
+    spawn(run_pp_dropped_step, world_size=2, state=state, batches=batches,
+          ref_state={k: v.detach().clone() for k, v in m.state_dict().items()}, fused=fused)
