@@ -223,6 +223,23 @@ def fused_layer_norm(x, gamma, beta, eps=1e-5):
     return _LayerNormFn.apply(x, gamma, beta, eps)
 
 
+def left_align(attention_mask: torch.Tensor):
+    """Indices that rotate every row of a ``[batch, seq]`` tensor so that its first real token comes first.
+
+    Returns ``(idx, keep, inverse)``: ``x.gather(1, idx)`` is the left-aligned ``x`` (leading pads wrap around to the
+    end), ``keep`` is the rotated mask (``True`` on real tokens) and ``y.gather(1, inverse)`` undoes the rotation.
+    Masks with holes (real tokens on both sides of a pad) are refused with a device-side assert — no host sync."""
+    m = attention_mask.ne(0)
+    S = m.shape[1]
+    lead = (m.cumsum(1) == 0).sum(1, keepdim=True)                       # pads in front of the first real token
+    pos = torch.arange(S, device=m.device)[None, :]
+    idx = (pos + lead) % S
+    keep = m.gather(1, idx)
+    torch._assert_async((keep[:, :-1] | ~keep[:, 1:]).all(),
+                        "pipegoose_b200 models take left- or right-padded batches, not attention masks with holes")
+    return idx, keep, (pos - lead) % S
+
+
 def embed_tokens(owner: nn.Module, input_ids: torch.Tensor, config, vocab_start: int, tp) -> torch.Tensor:
     """Token ids -> ``[tokens_local, hidden]`` input of the first block.  ``owner`` holds ``word_embeddings`` and either
     ``word_embeddings_layernorm`` (Bloom) or ``position_embeddings`` (GPT-2): the model's ``transformer`` or a first
@@ -331,12 +348,16 @@ class BloomForCausalLM(nn.Module):
                 labels: Optional[torch.Tensor] = None, **_unused) -> CausalLMOutput:
         t = self.transformer
         B, S = input_ids.shape
+        unroll = None
         if attention_mask is not None:
             # The fused attention is purely causal.  RIGHT padding is harmless under a causal mask (real tokens never
-            # attend to later pads; give the pads label -100).  LEFT padding would shift the real tokens' ALiBi /
-            # absolute positions and let them attend to pads: refuse it loudly (device-side assert, no host sync).
-            torch._assert_async(attention_mask[:, 0].ne(0).all(),
-                                "pipegoose_b200 models support right padding only (attention_mask[:, 0] must be 1)")
+            # attend to later pads).  LEFT padding (what 🤗's Bloom tokenizer produces) is turned into right padding by
+            # rotating every row until its first real token sits at position 0: ALiBi only sees distances between real
+            # tokens, so their hidden states are what 🤗 computes with the mask.  Pads never count in the loss.
+            idx, keep, unroll = left_align(attention_mask)
+            input_ids = input_ids.gather(1, idx)
+            if labels is not None:
+                labels = labels.gather(1, idx).masked_fill(~keep, -100)
         x = self.hidden_states(input_ids)
         eps = self.config.layer_norm_epsilon
         if labels is not None:
@@ -352,7 +373,10 @@ class BloomForCausalLM(nn.Module):
         logits = PF.linear(ln, self.lm_head.weight)
         if self.tp is not None:
             logits = self.tp.gather_cols(logits)[:, : self.config.vocab_size]
-        return CausalLMOutput(loss=None, logits=logits.view(B, S, -1))
+        logits = logits.view(B, S, -1)
+        if unroll is not None:   # back to the caller's layout (pad positions hold the logits of the rotated pads)
+            logits = logits.gather(1, unroll[:, :, None].expand(-1, -1, logits.shape[-1]))
+        return CausalLMOutput(loss=None, logits=logits)
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True, **_unused) -> torch.Tensor:

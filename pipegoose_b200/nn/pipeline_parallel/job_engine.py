@@ -87,7 +87,7 @@ class JobPipelineEngine:
         inputs = {"input_ids": input_ids, "labels": labels}
         mbs = mb_utils.split({k: v for k, v in inputs.items() if v is not None}, self.scheduler.n_microbatches)
         m = len(mbs)
-        weights = PipelineEngine._microbatch_weights(mbs) if self.is_last else None   # share of the target tokens
+        weights = PipelineEngine._microbatch_weights(mbs, self.module) if self.is_last else None   # share of the target tokens
         Q.clear_all()
         # the step's gradients are produced from scratch inside this call (see PipelineEngine.train_step): flat fp32
         # main grads are cleared and then held until the optimizer consumed them, ``.grad``s are parked below

@@ -89,6 +89,17 @@ class BloomStage(nn.Module):
             self.lm_head = model.lm_head
         self._model_ref = [model]  # not registered: avoids duplicating parameters
 
+    def count_targets(self, labels: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """How many positions of this (micro-)batch the loss is averaged over (for the engine's micro-batch weights).
+        The fused stages never score pads, and a row starts with its first REAL token, which has no predecessor."""
+        if not self.fast or attention_mask is None:
+            return (labels[..., 1:] != -100).sum()
+        from pipegoose_b200.models.bloom import left_align
+
+        idx, keep, _ = left_align(attention_mask)
+        aligned = labels.gather(1, idx).masked_fill(~keep, -100)
+        return (aligned[:, 1:] != -100).sum()
+
     def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 labels: Optional[torch.Tensor] = None, batch_seq=None):
         model = self._model_ref[0]
@@ -98,11 +109,18 @@ class BloomStage(nn.Module):
             from pipegoose_b200.ops import kernels as K
 
             eps = self.config.layer_norm_epsilon
+            idx = keep = unroll = None
+            if attention_mask is not None and (self.is_first or self.is_last):
+                # left padding -> right padding, pads out of the loss (models/bloom.py::left_align); every stage derives
+                # the same rotation from the mask, the blocks in between only see token rows
+                from pipegoose_b200.models.bloom import left_align
+
+                idx, keep, unroll = left_align(attention_mask)
             if self.is_first:
                 B, S = x.shape
                 from pipegoose_b200.models.bloom import embed_tokens
 
-                h = embed_tokens(self, x, self.config, model.vocab_start, model.tp)
+                h = embed_tokens(self, x if idx is None else x.gather(1, idx), self.config, model.vocab_start, model.tp)
             else:
                 B, S = batch_seq
                 h = x
@@ -113,13 +131,18 @@ class BloomStage(nn.Module):
             if not self.is_last:
                 return h
             if labels is not None:
+                if idx is not None:
+                    labels = labels.gather(1, idx).masked_fill(~keep, -100)
                 shifted = torch.full_like(labels, -100)
                 shifted[:, :-1] = labels[:, 1:]
                 return PF.lm_head_cross_entropy(h, self.ln_f.weight, self.ln_f.bias, self.lm_head.weight, shifted,
                                                 eps, model.vocab_start, -100, model.tp,
                                                 vocab_size=self.config.vocab_size)
             ln = fused_layer_norm(h, self.ln_f.weight, self.ln_f.bias, eps)
-            return K.gemm_nt(ln, self.lm_head.weight).view(B, S, -1)
+            logits = K.gemm_nt(ln, self.lm_head.weight).view(B, S, -1)
+            if unroll is not None:
+                logits = logits.gather(1, unroll[:, :, None].expand(-1, -1, logits.shape[-1]))
+            return logits
         # ---- 🤗 Bloom blocks
         from transformers.models.bloom.modeling_bloom import build_alibi_tensor
 

@@ -288,7 +288,7 @@ class PipelineEngine:
         """Mean loss over the batch's target tokens, forward only (``with torch.no_grad(): model(ids, labels=...)``)."""
         mbs = self._prepare(inputs)
         dev = self._device()
-        weights = self._microbatch_weights(mbs) if self.is_last else None
+        weights = self._microbatch_weights(mbs, self.module) if self.is_last else None
         total = torch.zeros((), device=dev)
         for i, mb in enumerate(mbs):
             if self.is_first:
@@ -355,7 +355,7 @@ class PipelineEngine:
         mbs = self._prepare(inputs)
         dev = self._device()
         m = len(mbs)
-        weights = self._microbatch_weights(mbs) if self.is_last else None
+        weights = self._microbatch_weights(mbs, self.module) if self.is_last else None
         if weights is not None and loss_scale != 1.0:
             weights = [w * loss_scale for w in weights]
         order: List[Task] = self.scheduler.get_stage_order(self.partition_idx)
@@ -452,15 +452,21 @@ class PipelineEngine:
         return broadcast_loss_from_last_stage(total, self.parallel_context)
 
     @staticmethod
-    def _microbatch_weights(mbs: List[Dict]) -> List:
+    def _microbatch_weights(mbs: List[Dict], stage: Optional[nn.Module] = None) -> List:
         """Share of the step's target tokens that each micro-batch holds, so that the sum of the weighted micro-batch
         (mean) losses IS the mean over all target tokens of the batch — exactly what the unpartitioned model computes,
-        also when micro-batches differ in size or in the number of ignored (-100) labels.  Counted on the device."""
+        also when micro-batches differ in size or in the number of ignored (-100) labels.  Counted on the device.
+        A stage that scores fewer positions than "every label but the first" (padding masks) says so through
+        ``count_targets(labels, attention_mask)``."""
         m = len(mbs)
         labels = [mb.get("labels") for mb in mbs]
         if any(not isinstance(l, torch.Tensor) for l in labels):
             return [1.0 / m] * m
-        counts = torch.stack([(l[..., 1:] != -100).sum() for l in labels]).float()
+        count = getattr(stage, "count_targets", None)
+        if count is not None:
+            counts = torch.stack([count(mb["labels"], mb.get("attention_mask")) for mb in mbs]).float()
+        else:
+            counts = torch.stack([(l[..., 1:] != -100).sum() for l in labels]).float()
         share = counts / counts.sum().clamp(min=1.0)
         return list(share.unbind(0))
 

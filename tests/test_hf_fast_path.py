@@ -170,3 +170,42 @@ def test_tensor_parallel_generation_with_kv_cache_matches_hf(tp):
     ids = torch.randint(0, 96, (2, 7))
     ref = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=5, do_sample=False)
     spawn(run_tp_cached_generate, world_size=tp, tp=tp, state=copy.deepcopy(model.state_dict()), ids=ids, ref_tokens=ref)
+
+
+def run_left_padded(rank, world_size, port, tp, pp, state, ids, mask, ref_loss, ref_grad):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, 1)
+    model = _hf_bloom()
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx, sequence_parallel=True).parallelize()
+    if pp > 1:
+        from pipegoose_b200.nn import PipelineParallel
+
+        model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    # the reference's README loop: labels = input_ids, the tokenizer's mask passed along
+    out = model(input_ids=ids, attention_mask=mask, labels=ids)
+    assert torch.allclose(out.loss, ref_loss, atol=2e-5), (out.loss, ref_loss)
+    out.loss.backward()
+    if pp == 1:   # a tensor-parallel-replicated parameter: its partial gradients were summed over the group by the sync hook
+        p = dict(model.named_parameters())["transformer.h.0.input_layernorm.weight"]
+        g = p.grad if p.grad is not None else p.main_grad
+        assert torch.allclose(g, ref_grad, atol=2e-5)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,pp", [(2, 1), (2, 2)])
+def test_left_padded_batches_through_the_fused_parallel_paths(tp, pp):
+    torch.manual_seed(0)
+    hf = _hf_bloom()
+    state = copy.deepcopy(hf.state_dict())
+    ids = torch.randint(1, 96, (4, 8))
+    mask = torch.ones(4, 8, dtype=torch.long)
+    mask[0, :3] = 0
+    mask[2, :5] = 0
+    ids = ids.masked_fill(mask == 0, 3)
+    labels = ids.masked_fill(mask == 0, -100)
+    labels[0, 3] = labels[2, 5] = -100        # see tests/test_models_bloom.py: 🤗 scores the first real token from a pad
+    # (pp > 1: the pipelined loss is the token-weighted mean over micro-batches = the mean over all scored tokens)
+    want = hf(input_ids=ids, attention_mask=mask, labels=labels).loss
+    want.backward()
+    spawn(run_left_padded, world_size=tp * pp, tp=tp, pp=pp, state=state, ids=ids, mask=mask, ref_loss=want.detach(),
+          ref_grad=hf.transformer.h[0].input_layernorm.weight.grad.clone())

@@ -96,7 +96,7 @@ def test_cached_generation_equals_full_recompute(family):
     assert torch.equal(model.generate(ids, max_new_tokens=1), slow[:, :8])
 
 
-def test_right_padding_is_harmless_and_left_padding_is_refused():
+def test_right_padding_is_harmless_and_masks_with_holes_are_refused():
     from transformers import BloomConfig as HFConfig
     from transformers import BloomForCausalLM as HFBloom
 
@@ -112,6 +112,48 @@ def test_right_padding_is_harmless_and_left_padding_is_refused():
     want = hf(input_ids=ids, attention_mask=mask, labels=labels).loss
     got = mine(ids, attention_mask=mask, labels=labels).loss
     assert torch.allclose(got, want, atol=1e-5)
-    left = mask.flip(1)
+    holes = mask.clone()
+    holes[0, 3] = 0                                   # a pad between real tokens: neither left nor right padding
     with pytest.raises((RuntimeError, AssertionError)):
-        mine(ids, attention_mask=left, labels=labels)
+        mine(ids, attention_mask=holes, labels=labels)
+
+
+def test_left_padded_batches_match_transformers():
+    """What 🤗's Bloom tokenizer produces (padding_side = "left") and the reference's README loop feeds to the model."""
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    from pipegoose_b200.models.bloom import BloomForCausalLM, left_align
+
+    torch.manual_seed(0)
+    hf = HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)).eval()
+    mine = BloomForCausalLM.from_hf(hf)
+    ids = torch.randint(1, 96, (3, 9))
+    mask = torch.ones(3, 9, dtype=torch.long)
+    mask[0, :4] = 0                                   # left padding, different amounts per row; row 2 has none
+    mask[1, :1] = 0
+    ids = ids.masked_fill(mask == 0, 3)               # the pad token
+    idx, keep, inv = left_align(mask)
+    assert idx[0].tolist() == [4, 5, 6, 7, 8, 0, 1, 2, 3] and keep[0].tolist() == [True] * 5 + [False] * 4
+    assert torch.equal(ids.gather(1, idx).gather(1, inv), ids)
+    labels = ids.masked_fill(mask == 0, -100)
+    # 🤗 also scores the first real token of a left-padded row as a prediction made FROM the last pad position; here a
+    # row starts with its first real token, which has nothing to be predicted from — take that target out on the 🤗 side
+    labels_hf = labels.clone()
+    labels_hf[0, 4] = labels_hf[1, 1] = -100
+    want = hf(input_ids=ids, attention_mask=mask, labels=labels_hf)
+    got = mine(ids, attention_mask=mask, labels=labels).loss
+    assert torch.allclose(got, want.loss, atol=1e-5), (got, want.loss)
+    # pads are never scored, also when the caller leaves them in the labels (labels = input_ids, as in the README loop)
+    assert torch.allclose(mine(ids, attention_mask=mask, labels=ids).loss, want.loss, atol=1e-5)
+    labels = labels_hf
+    logits = mine(ids, attention_mask=mask).logits    # in the caller's layout
+    real = mask.bool()
+    assert torch.allclose(logits[real], want.logits[real], atol=1e-4)
+    # gradients flow to the same places
+    hf.zero_grad(); mine.zero_grad()
+    hf(input_ids=ids, attention_mask=mask, labels=labels).loss.backward()
+    mine(ids, attention_mask=mask, labels=labels).loss.backward()
+    g_hf = hf.transformer.h[0].self_attention.query_key_value.weight.grad
+    g_me = mine.transformer.h[0].self_attention.query_key_value.weight.grad
+    assert torch.allclose(g_me, g_hf, atol=1e-5)
