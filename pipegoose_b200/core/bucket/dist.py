@@ -1,7 +1,7 @@
 """Bucketed asynchronous collectives (parity: reference core/bucket/dist.py:26-67, whose bucket path
 never flushed and crashed on first insert — Q10).
 
-``execute(tensor, parallel_mode)`` runs the collective immediately for tensors larger than a
+``execute(tensor, parallel_mode)`` runs the collective immediately (and completes it) for tensors larger than a
 bucket; smaller tensors are packed into the bucket of their ``(dtype, mode)`` and the bucket is
 reduced as one message when it fills up or on ``flush()``.  Results land in the original tensors
 because packing aliases their storage.
@@ -39,9 +39,12 @@ class BucketDistributor:
     def execute(self, tensor: torch.Tensor, parallel_mode: ParallelMode):
         capacity = mb_size_to_num_elements(self.bucket_size_mb, tensor.dtype)
         if tensor.numel() > capacity:
-            # too large for a bucket: reduce it on its own, right away
+            # too large for a bucket: reduce it on its own, right away — the result is in ``tensor`` when this returns
+            # (the reference's contract, tests/core/bucket/test_bucket_distributor.py; with NCCL ``wait()`` only orders
+            # the streams, the host does not block)
             work = self.op(tensor, group=self._group(parallel_mode), async_op=True)
-            self._pending.append(work)
+            if work is not None:
+                work.wait()
             return
         key = (tensor.dtype, parallel_mode)
         bucket = self.buckets.get(key)

@@ -70,7 +70,8 @@ def all_gather(tensor: torch.Tensor, dim: int = 0, async_op: bool = False,
     if world_size == 1:
         return tensor
     group = parallel_context.get_group(parallel_mode)
-    src = tensor.unsqueeze(0) if tensor.dim() == 0 else tensor
+    src = tensor.detach()    # (the collective is not differentiable; a tensor that requires grad must not reach gloo's
+    src = src.unsqueeze(0) if src.dim() == 0 else src   # in-place chunk copies — reference tests pass such tensors)
     src = src.contiguous()
     d = dim % src.dim()
     flat2d = torch.empty((world_size * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)

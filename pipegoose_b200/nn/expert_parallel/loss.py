@@ -12,8 +12,15 @@ import torch
 from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
 
 
-def _weighted_sum(weight: float, terms: List[torch.Tensor]):
-    return weight * torch.stack([t.float().reshape(()) for t in terms]).sum() if terms else None
+def _weighted_sum(weight: float, terms: List):
+    """``weight * sum(terms)``; terms are scalar tensors (what the routers push) or plain numbers (the reference's
+    tests push floats)."""
+    if not terms:
+        return None
+    tensors = [t.float().reshape(()) for t in terms if isinstance(t, torch.Tensor)]
+    numbers = sum(float(t) for t in terms if not isinstance(t, torch.Tensor))
+    total = torch.stack(tensors).sum() + numbers if tensors else torch.tensor(numbers)
+    return weight * total
 
 
 class ExpertLoss:
@@ -37,5 +44,5 @@ class ExpertLoss:
         for weight, terms in ((self.aux_weight, store.pop_all_aux_loss()), (self.z_weight, store.pop_all_z_loss())):
             extra = _weighted_sum(weight, terms)
             if extra is not None:
-                total = total + extra.to(total.dtype)
+                total = total + extra.to(device=total.device, dtype=total.dtype)
         return total

@@ -33,11 +33,15 @@ class _SaveGradLossFunction(torch.autograd.Function):
         return None, None, None
 
 
-def save_grad_loss(package: Package) -> torch.Tensor:
+def save_grad_loss(package: Package) -> Package:
+    """The package with its data behind a recording identity: whatever loss is computed from ``package.data``, its
+    ``backward()`` parks d loss / d data in the grad-loss store (``queue.get_grad_loss``) instead of flowing into the
+    stage (parity: reference _job/backward.py:17-37 — a Package in, the same Package out)."""
     m = package.metadata
     # a fresh leaf: the stage's own graph must stay untouched (and unfreed) until its backward job runs
     leaf = package.data.detach().requires_grad_(True)
-    return _SaveGradLossFunction.apply((m.microbatch_idx, m.partition_idx), m, leaf)
+    package.data = _SaveGradLossFunction.apply((m.microbatch_idx, m.partition_idx), m, leaf)
+    return package
 
 
 class BackwardJob(Job):

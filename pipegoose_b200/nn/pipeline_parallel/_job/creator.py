@@ -64,7 +64,7 @@ class ScheduleBackwardJobCallback(Callback):
             return
         package = self.job.output
         meta = package.metadata
-        recorded = schedule_backward_execution(package)
+        recorded = schedule_backward_execution(package).data
         Q._SAVED_SCHEDULED_ACTIVATIONS[(meta.microbatch_idx, meta.partition_idx)] = recorded
         self.job.output = Package(recorded, meta)
 
@@ -145,5 +145,6 @@ def schedule_backward_job(package: Package, pipeline_context=None, parallel_cont
 
 def schedule_backward_execution(package: Package, pipeline_context=None):
     """Wrap the last stage's output so that ``loss.backward()`` records d loss / d output in the grad-loss
-    store (``queue.get_grad_loss``) instead of flowing into the stage: backward jobs start from it."""
+    store (``queue.get_grad_loss``) instead of flowing into the stage: backward jobs start from it.  Returns the
+    package (its ``data`` is the wrapped tensor), like the reference."""
     return save_grad_loss(package)

@@ -126,7 +126,7 @@ class JobPipelineEngine:
 
         for n_done, i in enumerate(reversed(range(m)), start=1):
             if self.is_last:
-                y = schedule_backward_execution(outs[i])      # loss.backward() only records d loss / d output
+                y = schedule_backward_execution(outs[i]).data   # loss.backward() only records d loss / d output
                 loss = y * weights[i]
                 losses.append(loss.detach())
                 loss.backward()

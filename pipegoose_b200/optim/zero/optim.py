@@ -62,6 +62,12 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             if owner != self.dp_rank:
                 copy_flatten_tensor_to_unflatten_tensors(flat, [p.data for p in params])
 
+    def _params_in_shared_memory(self) -> bool:
+        """Could this rank's parameters be the same storage as another rank's?  Only CPU tensors can (shared memory);
+        the answer must be the same on every rank because a collective hangs on it, so it is "the model is on the CPU",
+        not "this rank's tensors happen to be shared"."""
+        return bool(self._all_params) and self._all_params[0].device.type == "cpu"
+
     def _materialize_grads_from_main(self):
         """Stock optimizers read ``p.grad``; the fused layers accumulate into ``p.main_grad``."""
         for g in self.optim.param_groups:
@@ -160,6 +166,11 @@ class DistributedOptimizer(BaseDistributedOptimizer):
                 self._all_gather_params()
             return
         self._materialize_grads_from_main()
+        if self.dp > 1 and self._params_in_shared_memory():
+            # CPU parameters can live in shared memory and then are the SAME storage in every rank of this host (a module
+            # handed to ``torch.multiprocessing.spawn`` as an argument — the reference's tests/optim/zero/test_optim.py
+            # does that): no owner may start writing before every replica finished reading them in its backward pass
+            dist.barrier(group=self.parallel_context.get_group(ParallelMode.DATA))
         self.optim.step(*args, **kwargs)
         if self.dp > 1:
             self._broadcast_updated_params()

@@ -231,7 +231,7 @@ def run_pipeline_of_jobs(rank, world_size, port, state_dicts, batch, ref_grads, 
                 y = outs[i].data
                 assert y is Q._SAVED_SCHEDULED_ACTIVATIONS[(i, 1)] and y.requires_grad
             else:
-                y = schedule_backward_execution(outs[i])
+                y = schedule_backward_execution(outs[i]).data
             loss = y.pow(2).sum() / batch.shape[0]
             losses.append(loss.item())
             loss.backward()

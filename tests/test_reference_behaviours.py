@@ -242,3 +242,93 @@ def test_schedule_record_and_module_constants():
     assert INPUT_NAMES == ["input_ids", "attention_mask"] and PipelineEngine.MASTER_RANK == 0
     assert (N_PARTITIONS, N_MICROBATCHES) == (3, 5)
     assert Handshake.master_rank is None and Handshake.parallel_context is None
+
+
+# ---------------------------------------------------------------------------------------------------- found by running the
+# reference's own tests against this package (tools/run_reference_tests.py)
+def test_expert_loss_accepts_plain_numbers():
+    import torch.nn.functional as F
+
+    from pipegoose_b200.nn.expert_parallel import ExpertLoss
+    from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+    store = ExpertContext.get_instance()
+    store.pop_all_aux_loss(), store.pop_all_z_loss()
+    logits, target = torch.randn(6, 3), torch.randn(6, 3)
+    loss_fn = ExpertLoss(torch.nn.MSELoss(), aux_weight=0.1, z_weight=0.2)
+    store.push_aux_loss(1.5), store.push_z_loss(2.5)                       # floats, as the reference's test pushes them
+    store.push_aux_loss(torch.tensor(0.5)), store.push_z_loss(torch.tensor(1.0))
+    assert loss_fn.aux_loss[0] == 1.5 and len(loss_fn.z_loss) == 2
+    got = loss_fn(logits, target)
+    assert torch.allclose(got, F.mse_loss(logits, target) + 0.1 * 2.0 + 0.2 * 3.5)
+    assert store.aux_loss == [] and store.z_loss == []
+
+
+def test_save_grad_loss_returns_the_package():
+    from pipegoose_b200.nn.pipeline_parallel._job.backward import save_grad_loss
+
+    Q.clear_all()
+    pkg = _package(torch.randn(3, 2))
+    pkg.metadata.microbatch_idx, pkg.metadata.partition_idx = 1, 2
+    out = save_grad_loss(pkg)
+    assert out is pkg and out.data.requires_grad
+    out.data.pow(2).sum().backward()
+    assert isinstance(Q.get_grad_loss(1, 2), torch.Tensor)
+    Q.clear_all()
+
+
+def _run_oversized_and_grad_inputs(rank, world_size, port):
+    import torch.distributed as dist
+
+    from pipegoose_b200.core.bucket.dist import BucketDistributor
+    from pipegoose_b200.core.bucket.utils import mb_size_to_num_elements
+    from pipegoose_b200.distributed.functional import all_gather
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size)
+    n = mb_size_to_num_elements(0.001, torch.float32)
+    big = torch.arange(2 * n, dtype=torch.float32)
+    BucketDistributor(dist.all_reduce, 0.001, ctx).execute(big, ParallelMode.DATA)
+    # larger than a bucket: reduced on its own and COMPLETE when execute() returns (no flush)
+    assert torch.equal(big, torch.arange(2 * n, dtype=torch.float32) * world_size)
+    leaf = torch.tensor(float(rank), requires_grad=True)      # a 0-d tensor that requires grad (reference test_functional)
+    assert all_gather(leaf, dim=0, parallel_context=ctx, parallel_mode=ParallelMode.DATA).tolist() == [0.0, 1.0]
+    ctx.destroy()
+
+
+def test_oversized_tensors_complete_in_execute_and_all_gather_takes_grad_leaves():
+    from pipegoose_b200.testing.utils import spawn
+
+    spawn(_run_oversized_and_grad_inputs, world_size=2)
+
+
+def _run_shared_model(rank, world_size, port, model, ref, x):
+    from pipegoose_b200.optim import DistributedOptimizer
+    from pipegoose_b200.testing.utils import init_parallel_context
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size)
+    opt = DistributedOptimizer(torch.optim.Adam(model.parameters()), ctx)
+    opt.zero_grad()
+    model(x).sum().backward()
+    opt.step()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p, q), "a rank wrote shared parameters while another one was still reading them"
+    ctx.destroy()
+
+
+def test_zero1_on_a_model_in_shared_memory():
+    """A module passed to the ranks as a spawn argument lives in shared memory: every rank works on the SAME parameter
+    storage (the reference's tests/optim/zero/test_optim.py).  Owners must not step before everybody finished backward."""
+    import copy
+
+    from pipegoose_b200.testing.utils import spawn
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.ReLU(), torch.nn.Linear(512, 64))
+    x = torch.randn(128, 256)
+    ref = copy.deepcopy(model)
+    o = torch.optim.Adam(ref.parameters())
+    ref(x).sum().backward()
+    o.step()
+    spawn(_run_shared_model, world_size=4, model=model, ref=ref, x=x)
