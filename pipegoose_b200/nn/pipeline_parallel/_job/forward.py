@@ -56,9 +56,13 @@ class CreateForwardOutputPackageCallback(Callback):
         out = self.job.output
         Q.save_output_activations(out, m.microbatch_idx, m.partition_idx)
         is_last = ctx.is_last_rank(ParallelMode.PIPELINE)
-        dst = ctx.get_global_rank() if is_last else ctx.get_next_global_rank(ParallelMode.PIPELINE)
-        meta = self.job.input.clone_metadata(partition_idx=m.partition_idx + (0 if is_last else 1),
-                                             src=ctx.get_global_rank(), dst=dst)
+        if is_last:
+            # the last partition's output stays where it is (it seeds this partition's own backward package): routing
+            # fields unchanged, like the reference (tests/nn/pipeline_parallel/job/test_forward.py:60-73)
+            meta = self.job.input.clone_metadata()
+        else:
+            meta = self.job.input.clone_metadata(partition_idx=m.partition_idx + 1, src=ctx.get_global_rank(),
+                                                 dst=ctx.get_next_global_rank(ParallelMode.PIPELINE))
         payload = out.detach() if isinstance(out, torch.Tensor) and not is_last else out
         self.job.output = Package(payload, meta)
 
