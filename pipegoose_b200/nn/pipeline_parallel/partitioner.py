@@ -66,7 +66,28 @@ def _hf_bloom_uses_boolean_mask() -> bool:
     return _HF_BLOOM_BOOL_MASK
 
 
-class BloomStage(nn.Module):
+class _ReferenceCallStyle:
+    """The reference's partitions are chained like ``out = stage0(**inputs); out = stage1(*out); ...`` (its
+    tests/nn/pipeline_parallel/test_partitioner.py): a first stage called with ``input_ids=...`` — or a later one called
+    with the positional tuple a previous stage returned — answers in that style: every stage but the last returns
+    ``(hidden, attention_mask, None, (batch, seq))``, i.e. the positional arguments of the next stage.  The engines of
+    this library call ``stage(x, attention_mask=..., batch_seq=...)`` and get plain tensors."""
+
+    def __call__(self, *args, input_ids=None, **kwargs):
+        chained = input_ids is not None or len(args) >= 2
+        if input_ids is not None:
+            args = (input_ids,) + args
+        out = super().__call__(*args, **kwargs)
+        if not chained or self.is_last:
+            return out
+        mask = kwargs.get("attention_mask", args[1] if len(args) > 1 else None)
+        batch_seq = kwargs.get("batch_seq", args[3] if len(args) > 3 else None)
+        if batch_seq is None and self.is_first:
+            batch_seq = tuple(args[0].shape[:2])
+        return (out, mask, None, batch_seq)
+
+
+class BloomStage(_ReferenceCallStyle, nn.Module):
     """A contiguous slice of a Bloom-style causal LM: [embedding +] blocks [+ final norm + lm head].
 
     Works for ``pipegoose_b200.models.BloomForCausalLM`` (fused blocks on 2-D token tensors) and for
@@ -173,7 +194,7 @@ class BloomStage(nn.Module):
         return logits
 
 
-class GPT2Stage(nn.Module):
+class GPT2Stage(_ReferenceCallStyle, nn.Module):
     """A contiguous slice of a 🤗 GPT-2 style causal LM (``transformer.{wte,wpe,drop,h,ln_f}`` + ``lm_head``) —
     the second model family the reference's partitioner is tested with (tests/nn/pipeline_parallel/test_partitioner.py)."""
 
@@ -208,7 +229,7 @@ class GPT2Stage(nn.Module):
         return logits
 
 
-class RotaryDecoderStage(nn.Module):
+class RotaryDecoderStage(_ReferenceCallStyle, nn.Module):
     """A contiguous slice of a 🤗 LLaMA-style causal LM (``model.{embed_tokens,layers,norm,rotary_emb}`` + ``lm_head``:
     LLaMA, Mistral, Qwen2, ... — pre-norm blocks with rotary position embeddings).  Every stage recomputes the rotary
     tables from its own (parameter-free) ``rotary_emb`` and builds the additive causal mask, so only hidden states

@@ -338,3 +338,30 @@ def test_partitioner_register_family_and_unknown_model_message():
         assert [len(s.layers) for s in stages] == [2, 2]
     finally:
         UniformPartitioner._FAMILIES[:] = saved
+
+
+@pytest.mark.parametrize("family", ["bloom", "gpt2"])
+def test_partitions_chain_in_the_reference_call_style(family):
+    """``out = stage0(**inputs); out = stage1(*out); ...`` — how the reference's partitioner test drives the stages."""
+    from transformers import BloomConfig as HFBloomConfig
+    from transformers import BloomForCausalLM as HFBloom
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    class Ctx:
+        pipeline_parallel_size = 3
+
+    torch.manual_seed(0)
+    if family == "bloom":
+        model = HFBloom(HFBloomConfig(vocab_size=128, hidden_size=32, n_layer=6, n_head=4)).eval()
+    else:
+        model = GPT2LMHeadModel(GPT2Config(vocab_size=128, n_embd=32, n_layer=6, n_head=4)).eval()
+    inputs = {"input_ids": torch.randint(0, 128, (2, 7)), "attention_mask": torch.ones(2, 7, dtype=torch.long)}
+    want = model(**inputs).logits
+    stages = UniformPartitioner(model, Ctx()).split()
+    out = inputs
+    for stage in stages:
+        out = stage(*out) if type(out) in (list, tuple) else stage(**out)
+    assert torch.allclose(out, want, atol=1e-6)
+    # the library's own call style still gets plain tensors
+    h = stages[0](inputs["input_ids"], attention_mask=inputs["attention_mask"])
+    assert isinstance(h, torch.Tensor) and h.shape == (2, 7, 32)
