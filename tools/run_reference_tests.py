@@ -82,6 +82,58 @@ KNOWN = [
 ]
 
 
+DATASET_STAND_IN = '''
+
+class _DS(list):
+    def map(self, fn):
+        return _DS([dict(r, **fn(r)) for r in self])
+
+
+def load_dataset(name, split=None):
+    import random
+
+    random.seed(0)
+    words = "the movie was a long slow beautiful mess of great acting and bad writing".split()
+    return _DS([{"text": " ".join(random.choice(words) for _ in range(random.randint(3, 12))), "label": 0} for _ in range(24)])
+'''
+
+
+def run_example(reference: str):
+    """The reference's examples/hybrid_parallelism.py (TP2 x DP2, 🤗 Bloom, tokenizer with padding, stock SGD) against this
+    package: imports rewritten, "cuda" -> "cpu", one epoch, the hub / datasets stand-ins; once through the class-swap path
+    (what an fp32 🤗 model gets) and once through the fused sequence-parallel path."""
+    path = os.path.join(reference, "examples", "hybrid_parallelism.py")
+    if not os.path.exists(path):
+        return []
+    tmp = tempfile.mkdtemp(prefix="pgb200_refexample_")
+    src = re.sub(r"\bpipegoose\b", "pipegoose_b200", open(path).read())
+    src = src.replace("from datasets import load_dataset", "from pgb200_hub_stand_in import load_dataset")
+    src = src.replace('model.to("cuda")', 'model.to("cpu")').replace("range(100)", "range(1)")
+    with open(os.path.join(tmp, "pgb200_hub_stand_in.py"), "w") as f:
+        f.write(HUB_STAND_IN + DATASET_STAND_IN)
+    variants = {"class-swap path": src,
+                "fused sequence-parallel path": src.replace("TensorParallel(model, parallel_context)",
+                                                            "TensorParallel(model, parallel_context, sequence_parallel=True)")}
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + tmp + os.pathsep + os.environ.get("PYTHONPATH", ""), HF_HUB_OFFLINE="1")
+    lines = []
+    for i, (name, text) in enumerate(variants.items()):
+        script = os.path.join(tmp, f"example_{i}.py")
+        with open(script, "w") as f:
+            f.write("import pgb200_hub_stand_in  # noqa: F401\n" + text)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+               "--master-port", str(29580 + i), script]
+        try:
+            out = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
+            losses = [float(x) for x in re.findall(r"rank=0, loss=([0-9.]+)", out.stdout)]
+            ok = out.returncode == 0 and len(losses) >= 2
+            lines.append(f"    {name}: {'ran' if ok else 'FAILED (exit %d)' % out.returncode}, {len(losses)} steps on rank 0, "
+                         f"loss {losses[0]:.4f} -> {losses[-1]:.4f}" if losses else f"    {name}: FAILED (exit {out.returncode})")
+        except subprocess.TimeoutExpired:
+            lines.append(f"    {name}: FAILED (timeout)")
+    shutil.rmtree(tmp, ignore_errors=True)
+    return lines
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -89,7 +141,11 @@ def main():
     ap.add_argument("--timeout", type=int, default=90, help="per test, seconds")
     ap.add_argument("--file-timeout", type=int, default=420, help="per test file, seconds (hard kill)")
     ap.add_argument("--only", default=None, help="sub-path under tests/ (default: everything but convergence/)")
+    ap.add_argument("--example-only", action="store_true", help="only run the reference's example script")
     args = ap.parse_args()
+    if args.example_only:
+        print("\n".join(["== the reference's examples/hybrid_parallelism.py against this package (4 CPU ranks)"] + run_example(args.reference)))
+        return 0
     src = os.path.join(args.reference, "tests")
     if not os.path.isdir(src):
         print(f"no reference tests at {src}")
@@ -195,6 +251,9 @@ def main():
     lines.append("")
     lines.append("== passing")
     lines += [f"    {t}" + ("   (on retry, alone)" if t in retried else "") for t in passed]
+    if not args.only:
+        lines += ["", "== the reference's examples/hybrid_parallelism.py against this package (4 CPU ranks, one epoch, stand-in data)"]
+        lines += run_example(args.reference)
     text = "\n".join(lines) + "\n"
     print(text)
     if args.out:
