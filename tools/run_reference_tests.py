@@ -94,40 +94,62 @@ def load_dataset(name, split=None):
 
     random.seed(0)
     words = "the movie was a long slow beautiful mess of great acting and bad writing".split()
-    return _DS([{"text": " ".join(random.choice(words) for _ in range(random.randint(3, 12))), "label": 0} for _ in range(24)])
+    return _DS([{"text": " ".join(random.choice(words) for _ in range(random.randint(3, 12))), "label": 0} for _ in range(64)])
 '''
 
 
 def run_example(reference: str):
-    """The reference's examples/hybrid_parallelism.py (TP2 x DP2, 🤗 Bloom, tokenizer with padding, stock SGD) against this
-    package: imports rewritten, "cuda" -> "cpu", one epoch, the hub / datasets stand-ins; once through the class-swap path
-    (what an fp32 🤗 model gets) and once through the fused sequence-parallel path."""
-    path = os.path.join(reference, "examples", "hybrid_parallelism.py")
-    if not os.path.exists(path):
-        return []
-    tmp = tempfile.mkdtemp(prefix="pgb200_refexample_")
-    src = re.sub(r"\bpipegoose\b", "pipegoose_b200", open(path).read())
-    src = src.replace("from datasets import load_dataset", "from pgb200_hub_stand_in import load_dataset")
-    src = src.replace('model.to("cuda")', 'model.to("cpu")').replace("range(100)", "range(1)")
+    """The reference's user scripts against this package on CPU ranks: imports rewritten, "cuda" -> "cpu", one epoch, the
+    hub / datasets / wandb stand-ins.
+
+    * examples/hybrid_parallelism.py (TP2 x DP2, 🤗 Bloom, tokenizer with padding, stock SGD): through the class-swap path
+      (what an fp32 🤗 model gets) and through the fused sequence-parallel path;
+    * tests/convergence/run_ep.py (Switch-MoE next to the dense model, ExpertLoss): experts on one rank and sharded over two."""
+    tmp = tempfile.mkdtemp(prefix="pgb200_refscripts_")
     with open(os.path.join(tmp, "pgb200_hub_stand_in.py"), "w") as f:
-        f.write(HUB_STAND_IN + DATASET_STAND_IN)
-    variants = {"class-swap path": src,
-                "fused sequence-parallel path": src.replace("TensorParallel(model, parallel_context)",
-                                                            "TensorParallel(model, parallel_context, sequence_parallel=True)")}
+        f.write(HUB_STAND_IN.replace("n_layer=2, n_head=8", "n_layer=4, n_head=8") + DATASET_STAND_IN
+                + "\n_Tok.add_special_tokens = lambda self, d: 0\n")
+    with open(os.path.join(tmp, "wandb.py"), "w") as f:
+        f.write("def init(*a, **k): pass\ndef log(*a, **k): pass\ndef finish(*a, **k): pass\n")
+
+    def prepare(path):
+        src = re.sub(r"\bpipegoose\b", "pipegoose_b200", open(path).read())
+        src = src.replace("from datasets import load_dataset", "from pgb200_hub_stand_in import load_dataset")
+        for a, b in (('model.to("cuda")', 'model.to("cpu")'), ("ref_model.cuda()", "ref_model.cpu()"), ("tensor.cuda()", "tensor.cpu()"),
+                     ("torch.cuda.manual_seed_all(seed)", "pass"), ("torch.cuda.empty_cache()", "pass"),
+                     ("range(100)", "range(1)"), ("NUM_EPOCHS = 100", "NUM_EPOCHS = 1")):
+            src = src.replace(a, b)
+        return "import pgb200_hub_stand_in  # noqa: F401\n" + src
+
+    runs = []
+    example = os.path.join(reference, "examples", "hybrid_parallelism.py")
+    if os.path.exists(example):
+        src = prepare(example)
+        runs.append(("examples/hybrid_parallelism.py, class-swap path", src, 4, r"rank=0, loss=([0-9.]+)"))
+        runs.append(("examples/hybrid_parallelism.py, fused sequence-parallel path",
+                     src.replace("TensorParallel(model, parallel_context)", "TensorParallel(model, parallel_context, sequence_parallel=True)"),
+                     4, r"rank=0, loss=([0-9.]+)"))
+    run_ep = os.path.join(reference, "tests", "convergence", "run_ep.py")
+    if os.path.exists(run_ep):
+        src = prepare(run_ep)
+        runs.append(("tests/convergence/run_ep.py, 4 experts on one rank", src, 1, r"rank=0, train_loss=([0-9.]+)"))
+        runs.append(("tests/convergence/run_ep.py, 4 experts sharded over 2 ranks",
+                     src.replace("TENSOR_PARALLEL_SIZE = 1", "TENSOR_PARALLEL_SIZE = 2"), 2, r"rank=0, train_loss=([0-9.]+)"))
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + tmp + os.pathsep + os.environ.get("PYTHONPATH", ""), HF_HUB_OFFLINE="1")
     lines = []
-    for i, (name, text) in enumerate(variants.items()):
-        script = os.path.join(tmp, f"example_{i}.py")
+    for i, (name, text, nproc, pattern) in enumerate(runs):
+        script = os.path.join(tmp, f"script_{i}.py")
         with open(script, "w") as f:
-            f.write("import pgb200_hub_stand_in  # noqa: F401\n" + text)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+            f.write(text)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
                "--master-port", str(29580 + i), script]
         try:
             out = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=900)
-            losses = [float(x) for x in re.findall(r"rank=0, loss=([0-9.]+)", out.stdout)]
-            ok = out.returncode == 0 and len(losses) >= 2
-            lines.append(f"    {name}: {'ran' if ok else 'FAILED (exit %d)' % out.returncode}, {len(losses)} steps on rank 0, "
-                         f"loss {losses[0]:.4f} -> {losses[-1]:.4f}" if losses else f"    {name}: FAILED (exit {out.returncode})")
+            losses = [float(x) for x in re.findall(pattern, out.stdout)]
+            if out.returncode == 0 and len(losses) >= 2:
+                lines.append(f"    {name}: ran, {len(losses)} training steps on rank 0, loss {losses[0]:.4f} -> {losses[-1]:.4f}")
+            else:
+                lines.append(f"    {name}: FAILED (exit {out.returncode})")
         except subprocess.TimeoutExpired:
             lines.append(f"    {name}: FAILED (timeout)")
     shutil.rmtree(tmp, ignore_errors=True)
@@ -144,7 +166,7 @@ def main():
     ap.add_argument("--example-only", action="store_true", help="only run the reference's example script")
     args = ap.parse_args()
     if args.example_only:
-        print("\n".join(["== the reference's examples/hybrid_parallelism.py against this package (4 CPU ranks)"] + run_example(args.reference)))
+        print("\n".join(["== the reference's user scripts against this package (CPU ranks, stand-in data)"] + run_example(args.reference)))
         return 0
     src = os.path.join(args.reference, "tests")
     if not os.path.isdir(src):
@@ -252,7 +274,7 @@ def main():
     lines.append("== passing")
     lines += [f"    {t}" + ("   (on retry, alone)" if t in retried else "") for t in passed]
     if not args.only:
-        lines += ["", "== the reference's examples/hybrid_parallelism.py against this package (4 CPU ranks, one epoch, stand-in data)"]
+        lines += ["", "== the reference's user scripts against this package (CPU ranks, one epoch, stand-in data)"]
         lines += run_example(args.reference)
     text = "\n".join(lines) + "\n"
     print(text)
