@@ -104,7 +104,8 @@ def run_example(reference: str):
 
     * examples/hybrid_parallelism.py (TP2 x DP2, 🤗 Bloom, tokenizer with padding, stock SGD): through the class-swap path
       (what an fp32 🤗 model gets) and through the fused sequence-parallel path;
-    * tests/convergence/run_ep.py (Switch-MoE next to the dense model, ExpertLoss): experts on one rank and sharded over two."""
+    * tests/convergence/run_ep.py (Switch-MoE next to the dense model, ExpertLoss): experts on one rank and sharded over two;
+    * tests/convergence/run_hybrid_parallel.py (TP2 x DP2 + ZeRO-1 DistributedOptimizer next to a DDP replica of the model)."""
     tmp = tempfile.mkdtemp(prefix="pgb200_refscripts_")
     with open(os.path.join(tmp, "pgb200_hub_stand_in.py"), "w") as f:
         f.write(HUB_STAND_IN.replace("n_layer=2, n_head=8", "n_layer=4, n_head=8") + DATASET_STAND_IN
@@ -117,7 +118,8 @@ def run_example(reference: str):
         src = src.replace("from datasets import load_dataset", "from pgb200_hub_stand_in import load_dataset")
         for a, b in (('model.to("cuda")', 'model.to("cpu")'), ("ref_model.cuda()", "ref_model.cpu()"), ("tensor.cuda()", "tensor.cpu()"),
                      ("torch.cuda.manual_seed_all(seed)", "pass"), ("torch.cuda.empty_cache()", "pass"),
-                     ("range(100)", "range(1)"), ("NUM_EPOCHS = 100", "NUM_EPOCHS = 1")):
+                     ("range(100)", "range(1)"), ("NUM_EPOCHS = 100", "NUM_EPOCHS = 1"), ("NUM_EPOCHS = 4", "NUM_EPOCHS = 1"),
+                     (", device_ids=[device]", "")):
             src = src.replace(a, b)
         return "import pgb200_hub_stand_in  # noqa: F401\n" + src
 
@@ -135,6 +137,10 @@ def run_example(reference: str):
         runs.append(("tests/convergence/run_ep.py, 4 experts on one rank", src, 1, r"rank=0, train_loss=([0-9.]+)"))
         runs.append(("tests/convergence/run_ep.py, 4 experts sharded over 2 ranks",
                      src.replace("TENSOR_PARALLEL_SIZE = 1", "TENSOR_PARALLEL_SIZE = 2"), 2, r"rank=0, train_loss=([0-9.]+)"))
+    hybrid = os.path.join(reference, "tests", "convergence", "run_hybrid_parallel.py")
+    if os.path.exists(hybrid):
+        runs.append(("tests/convergence/run_hybrid_parallel.py (TP2 x DP2 + DistributedOptimizer, next to a DDP replica)",
+                     prepare(hybrid), 4, r"rank=0, train_loss=([0-9.]+)"))
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + tmp + os.pathsep + os.environ.get("PYTHONPATH", ""), HF_HUB_OFFLINE="1")
     lines = []
     for i, (name, text, nproc, pattern) in enumerate(runs):
