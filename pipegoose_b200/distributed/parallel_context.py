@@ -88,7 +88,9 @@ class ParallelContext:
         data_parallel_size: int,
         enable_rpc: bool = False,
     ):
-        self._enable_rpc = enable_rpc
+        # (PIPEGOOSE_B200_ENABLE_RPC=1: the reference's behaviour — agents whenever there is more than one rank — without
+        #  touching call sites)
+        self._enable_rpc = enable_rpc or os.environ.get("PIPEGOOSE_B200_ENABLE_RPC", "0") == "1"
         self._rpc_started = False
         model_ranks = tensor_parallel_size * pipeline_parallel_size
         assert world_size % data_parallel_size == 0, "world size must be divisible by the data parallel size"

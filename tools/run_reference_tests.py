@@ -71,7 +71,6 @@ transformers.AutoTokenizer.from_pretrained = staticmethod(lambda *a, **k: _Tok()
 KNOWN = [
     (r"test_initialize_expert_parallel_group", "deliberate (MIGRATION Q3): EXPERT_DATA groups hold replicas of the SAME experts here; the "
                                                 "reference's are the tensor-parallel rank sets"),
-    (r"test_rpc", "deliberate: RPC workers are opt-in here (ParallelContext(enable_rpc=True)); nothing in the library needs RPC"),
     (r"with_expert_capacity", "deliberate: an expert takes `capacity` tokens here; the reference keeps positions < capacity of a 1-based "
                               "count, i.e. capacity - 1 (off by one), and its test asserts the strict bound"),
     (r"test_hybrid\.py", "the reference's own test compares EVERY parameter with a dim-0 shard, LayerNorms (replicated in both libraries) "
@@ -211,14 +210,17 @@ def main():
     if args.only and args.only.endswith(".py"):
         files = [os.path.join("reftests", args.only)]
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + tmp + os.pathsep + os.environ.get("PYTHONPATH", ""), HF_HUB_OFFLINE="1")
+    # RPC agents are opt-in here (enable_rpc=True / PIPEGOOSE_B200_ENABLE_RPC=1; nothing in the library needs them); the
+    # reference starts them whenever there is more than one rank, and its RPC test relies on that
+    env_rpc = dict(env, PIPEGOOSE_B200_ENABLE_RPC="1")
     results = {}
     import signal
 
     for t in sorted(files):
         cmd = [sys.executable, "-m", "pytest", t, "-q", "-p", "no:cacheprovider", "--timeout", str(args.timeout),
                "-rA", "--no-header", "-W", "ignore"]
-        proc = subprocess.Popen(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                                start_new_session=True)
+        proc = subprocess.Popen(cmd, cwd=tmp, env=env_rpc if "test_rpc" in t else env, stdout=subprocess.PIPE,
+                                stderr=subprocess.STDOUT, text=True, start_new_session=True)
         try:
             out, _ = proc.communicate(timeout=args.file_timeout)
         except subprocess.TimeoutExpired:
