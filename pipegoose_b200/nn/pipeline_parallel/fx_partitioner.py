@@ -1,0 +1,264 @@
+"""Graph-based pipeline partitioning of an arbitrary traceable ``nn.Module`` (parity: the part of the reference's
+nn/pipeline_parallel/partitioner.py:146-244 that is not tied to a model family — trace, balance by parameter count,
+rebuild one ``GraphModule`` per shard).
+
+The reference traces 🤗 models with ``transformers.utils.fx`` and threads every value that crosses a cut through the
+shards as a tuple.  The pipeline engine here moves ONE activation tensor per micro-batch between neighbouring stages
+(static shapes, one NCCL send/recv pair per boundary), so this partitioner looks for the cuts a pipeline wants anyway:
+
+* the model is traced with ``torch.fx`` (``symbolic_trace`` or a tracer / ``GraphModule`` the caller supplies);
+* every node is classified as *input-derived* (a placeholder, a buffer, or a parameter-free function of those: masks,
+  position ids, ALiBi slopes, ...) or as an *activation* (anything downstream of a parameter or of the first input);
+* a cut between two nodes is legal when exactly one activation is live across it — the residual stream at a block
+  boundary, the hidden state between two layers of an MLP or a CNN.  Input-derived values never cross a cut: every
+  stage that needs one re-computes it from the micro-batch's inputs, which every stage holds (no transfer at all);
+* the legal cuts divide the graph into segments; the segments are balanced over the stages by parameter count
+  (embeddings excluded, as in the reference) so that the largest stage is as small as possible.
+
+Each stage is a ``GraphModule`` rooted at the original model, so it owns exactly the sub-modules / parameters its
+nodes use.  ``stage(x, **inputs)``: ``x`` is the first input (first stage) or the carried activation; ``inputs`` are the
+model's other forward arguments by name (``stage.stage_inputs`` lists the ones this stage reads).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Set
+
+import torch
+from torch import fx, nn
+
+from pipegoose_b200.nn.pipeline_parallel.partitioner import BasePartitioner
+
+
+class NoLegalCut(NotImplementedError):
+    """The traced graph has fewer single-activation cut points than the pipeline has boundaries."""
+
+
+def _minmax_cuts(costs: List[int], n_parts: int) -> List[int]:
+    """Boundaries ``[0, b1, ..., len(costs)]`` of the contiguous split into ``n_parts`` non-empty groups whose largest
+    group is smallest (exact, O(parts * items^2): graphs have a few hundred cut points at most); ties go to the split
+    that is also best for the remaining groups."""
+    m = len(costs)
+    assert m >= n_parts
+    prefix = [0]
+    for c in costs:
+        prefix.append(prefix[-1] + c)
+    inf = float("inf")
+    best = [[inf] * (m + 1) for _ in range(n_parts + 1)]   # best[k][i]: first i items in k groups
+    arg = [[0] * (m + 1) for _ in range(n_parts + 1)]
+    best[0][0] = 0
+    for k in range(1, n_parts + 1):
+        for i in range(k, m - (n_parts - k) + 1):
+            for j in range(k - 1, i):
+                if best[k - 1][j] == inf:
+                    continue
+                v = max(best[k - 1][j], prefix[i] - prefix[j])
+                if v < best[k][i]:
+                    best[k][i], arg[k][i] = v, j
+    bounds, i = [m], m
+    for k in range(n_parts, 0, -1):
+        i = arg[k][i]
+        bounds.append(i)
+    return bounds[::-1]
+
+
+def _arg_nodes(node: fx.Node) -> List[fx.Node]:
+    return list(node.all_input_nodes)
+
+
+class GraphStage(nn.Module):
+    """One shard of a traced model.  ``forward(x, **inputs)`` (see the module docstring)."""
+
+    def __init__(self, graph_module: fx.GraphModule, carried_name: str, stage_inputs: Sequence[str],
+                 first_input_name: str, is_first: bool, is_last: bool):
+        super().__init__()
+        self.graph_module = graph_module
+        self.carried_name = carried_name
+        self.stage_inputs = tuple(stage_inputs)      # forward arguments of the model this stage reads by name
+        self.first_input_name = first_input_name     # the model's first forward argument (the engine's ``input_ids`` slot)
+        self.is_first, self.is_last = is_first, is_last
+
+    def forward(self, x, **inputs):
+        kwargs = {self.carried_name: x}
+        for name in self.stage_inputs:
+            if name == self.carried_name:
+                continue
+            kwargs[name] = inputs.get(name)
+        return self.graph_module(**kwargs)
+
+
+class GraphPartitioner(BasePartitioner):
+    """``GraphPartitioner(model, parallel_context).split() -> [GraphStage]`` for any model ``torch.fx`` can trace.
+
+    ``concrete_args`` / ``tracer`` are handed to the tracing step (a model whose forward branches on ``labels is None``
+    needs ``concrete_args={"labels": None}`` or a real ``labels`` placeholder, exactly as with ``torch.fx`` itself); a
+    ready ``GraphModule`` is taken as is."""
+
+    def __init__(self, model: nn.Module, parallel_context, concrete_args: Optional[Dict] = None,
+                 tracer: Optional[fx.Tracer] = None, n_partitions: Optional[int] = None):
+        self.module = model
+        self.parallel_context = parallel_context
+        self.concrete_args = concrete_args
+        self.tracer = tracer
+        self._n = n_partitions
+
+    # ------------------------------------------------------------------ tracing and node classes
+    def trace(self) -> fx.GraphModule:
+        if isinstance(self.module, fx.GraphModule):
+            return self.module
+        if self.tracer is not None:
+            graph = self.tracer.trace(self.module, concrete_args=self.concrete_args)
+            return fx.GraphModule(self.module, graph)
+        return fx.symbolic_trace(self.module, concrete_args=self.concrete_args)
+
+    @staticmethod
+    def _fetch(root: nn.Module, target: str):
+        obj = root
+        for part in target.split("."):
+            obj = getattr(obj, part)
+        return obj
+
+    def _node_cost(self, gm: fx.GraphModule, node: fx.Node, seen: Set[int]) -> int:
+        """Trainable parameters a node brings into its shard (each parameter counted once; embeddings count 0, the
+        reference's rule: they skew the balance of the blocks)."""
+        params: List[nn.Parameter] = []
+        if node.op == "call_module":
+            mod = self._fetch(gm, node.target)
+            if isinstance(mod, nn.Embedding):
+                for p in mod.parameters():
+                    seen.add(id(p))
+                return 0
+            params = list(mod.parameters())
+        elif node.op == "get_attr":
+            obj = self._fetch(gm, node.target)
+            if isinstance(obj, nn.Parameter):
+                params = [obj]
+        cost = 0
+        for p in params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                cost += p.numel()
+        return cost
+
+    def _input_derived(self, gm: fx.GraphModule, nodes: List[fx.Node], first: fx.Node) -> Set[fx.Node]:
+        """Nodes every stage can compute for itself: forward arguments other than the first one, buffers, and
+        parameter-free functions of those."""
+        free: Set[fx.Node] = set()
+        for n in nodes:
+            if n.op == "placeholder":
+                if n is not first:
+                    free.add(n)
+            elif n.op == "get_attr":
+                if not isinstance(self._fetch(gm, n.target), nn.Parameter):
+                    free.add(n)
+            elif n.op in ("call_function", "call_method"):
+                deps = _arg_nodes(n)
+                if all(d in free for d in deps):
+                    free.add(n)
+            elif n.op == "call_module":
+                mod = self._fetch(gm, n.target)
+                if next(mod.parameters(), None) is None and all(d in free for d in _arg_nodes(n)):
+                    free.add(n)
+        return free
+
+    # ------------------------------------------------------------------ cut points
+    def legal_cuts(self, gm: fx.GraphModule):
+        """``(nodes, free, cuts)``: ``cuts[k] = (position, carried node)`` — cutting before ``nodes[position]`` hands
+        exactly that one activation to the next stage."""
+        nodes = [n for n in gm.graph.nodes if n.op != "output"]
+        output = next(n for n in gm.graph.nodes if n.op == "output")
+        first = next((n for n in nodes if n.op == "placeholder"), None)
+        assert first is not None, "the traced forward takes no argument"
+        free = self._input_derived(gm, nodes, first)
+        index = {n: i for i, n in enumerate(nodes)}
+        index[output] = len(nodes)
+        last_use = {}
+        for n in nodes:
+            if n in free:
+                continue
+            uses = [index[u] for u in n.users if u in index]
+            last_use[n] = max(uses) if uses else -1
+        first_compute = next((i for i, n in enumerate(nodes) if n.op != "placeholder" and n not in free), len(nodes))
+        cuts = []
+        live: List[fx.Node] = []
+        for pos in range(1, len(nodes)):
+            prev = nodes[pos - 1]
+            if prev not in free:
+                live.append(prev)
+            live = [n for n in live if last_use[n] >= pos]
+            if pos <= first_compute or nodes[pos].op == "placeholder":
+                continue        # nothing computed yet: an empty first stage is no stage
+            if len(live) == 1 and live[0].op != "placeholder":
+                cuts.append((pos, live[0]))
+        return nodes, free, cuts
+
+    # ------------------------------------------------------------------ split
+    def _n_partitions(self) -> int:
+        return self._n if self._n is not None else self.parallel_context.pipeline_parallel_size
+
+    def split(self, input_names: Optional[List[str]] = None) -> List[nn.Module]:
+        n = self._n_partitions()
+        gm = self.trace()
+        nodes, free, cuts = self.legal_cuts(gm)
+        if len(cuts) < n - 1:
+            raise NoLegalCut(
+                f"{type(self.module).__name__}: {n} pipeline stages need {n - 1} cut points where exactly one activation "
+                f"tensor is live, the traced graph has {len(cuts)}.  (Values computed from the forward arguments alone "
+                "are re-computed by each stage and do not count; long skip connections do.)")
+        seen: Set[int] = set()
+        costs = [self._node_cost(gm, node, seen) for node in nodes]
+        # segments between consecutive legal cuts, balanced like blocks
+        edges = [0] + [pos for pos, _ in cuts] + [len(nodes)]
+        seg_costs = [sum(costs[edges[i]:edges[i + 1]]) or 1 for i in range(len(edges) - 1)]
+        b = _minmax_cuts(seg_costs, n)
+        carried_at = {pos: node for pos, node in cuts}
+        bounds = [edges[i] for i in b]          # node positions where each stage starts (+ the end)
+        first = next(x for x in nodes if x.op == "placeholder")
+        output = next(x for x in gm.graph.nodes if x.op == "output")
+        stages = []
+        for s in range(n):
+            lo, hi = bounds[s], bounds[s + 1]
+            carried_in = first if s == 0 else carried_at[lo]
+            carried_out = None if s == n - 1 else carried_at[hi]
+            stages.append(self._build_stage(gm, nodes, free, lo, hi, carried_in, carried_out, output, first,
+                                            is_first=(s == 0), is_last=(s == n - 1)))
+        return stages
+
+    def _build_stage(self, gm, nodes, free, lo, hi, carried_in, carried_out, output, first, is_first, is_last) -> GraphStage:
+        graph = fx.Graph()
+        env: Dict[fx.Node, fx.Node] = {}
+        carried_name = carried_in.name if is_first else "carried_activation"
+        env[carried_in] = graph.placeholder(carried_name)
+        body = [x for x in nodes[lo:hi] if x.op != "placeholder" and x not in free]
+        # input-derived values the body (or the model's output) needs, in graph order, with their own dependencies
+        needed: Set[fx.Node] = set()
+        stack = [d for x in body for d in _arg_nodes(x)]
+        if is_last:
+            stack += _arg_nodes(output)
+        while stack:
+            d = stack.pop()
+            if d in free and d not in needed:
+                needed.add(d)
+                stack.extend(_arg_nodes(d))
+        stage_inputs = []
+        for x in nodes:
+            if x in needed and x.op == "placeholder":
+                env[x] = graph.placeholder(x.name, default_value=None)
+                stage_inputs.append(x.name)
+        if not is_first and first in needed:
+            pass  # (cannot happen: the first argument is an activation, never input-derived)
+        for x in nodes:
+            if x in needed and x.op != "placeholder":
+                env[x] = graph.node_copy(x, lambda a: env[a])
+        for x in body:
+            missing = [d for d in _arg_nodes(x) if d not in env]
+            if missing:
+                raise NoLegalCut(f"stage [{lo}, {hi}) reads {[m.name for m in missing]} which an earlier stage computed: "
+                                 "not a single-activation cut (internal error in legal_cuts)")
+            env[x] = graph.node_copy(x, lambda a: env[a])
+        if is_last:
+            graph.output(fx.node.map_arg(output.args[0], lambda a: env[a]))
+        else:
+            graph.output(env[carried_out])
+        graph.lint()
+        sub = fx.GraphModule(gm, graph, class_name=f"{type(self.module).__name__}Stage")
+        return GraphStage(sub, carried_name, stage_inputs, first.name, is_first, is_last)

@@ -334,12 +334,23 @@ class UniformPartitioner(BasePartitioner):
         blocks = self._block_list(model)
         rotary = blocks is not None and hasattr(getattr(model, "model", None), "rotary_emb") and hasattr(model, "lm_head")
         if blocks is None or not (hasattr(model, "transformer") or rotary):
+            # not a family this partitioner knows by structure: cut its torch.fx graph where one activation is live
+            from pipegoose_b200.nn.pipeline_parallel.fx_partitioner import GraphPartitioner, NoLegalCut
+
+            why = ""
+            try:
+                return GraphPartitioner(model, self.parallel_context, n_partitions=n).split(input_names)
+            except NoLegalCut as e:
+                why = f"  Its torch.fx graph cannot be cut either: {e}"
+            except Exception as e:   # torch.fx could not trace it (data-dependent control flow, ...)
+                why = f"  torch.fx could not trace it either ({type(e).__name__}: {str(e).splitlines()[0][:200] if str(e) else ''})."
             raise NotImplementedError(
                 f"UniformPartitioner does not know how to cut a {type(model).__name__} into pipeline stages.  Built in: "
                 "nn.Sequential, Bloom-style (transformer.h + word_embeddings), GPT-2-style (transformer.wte/wpe/h) and "
                 "LLaMA-style (model.embed_tokens/layers/norm/rotary_emb + lm_head) causal LMs.  The reference traces any "
                 "🤗 model with transformers.utils.fx, which transformers >= 5 no longer ships; describe other "
-                "architectures with UniformPartitioner.register_family(matches, blocks, stage_cls) — see its docstring.")
+                "architectures with UniformPartitioner.register_family(matches, blocks, stage_cls) — see its docstring."
+                + why)
         assert len(blocks) >= n, "more pipeline stages than transformer blocks"
         costs = [sum(p.numel() for p in blk.parameters()) for blk in blocks]  # embeddings excluded, as in the reference
         b = _balanced_cuts(costs, n)

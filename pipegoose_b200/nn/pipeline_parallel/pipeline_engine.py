@@ -210,6 +210,9 @@ class PipelineEngine:
         """Does this stage's ``forward`` take the keyword ``name``?  (Read once from its signature: stage modules are
         plain ``nn.Module``s — the built-in Bloom / GPT-2 / LLaMA-style stages, ``SequentialStage``, or whatever a
         ``UniformPartitioner.register_family`` stage class defines.)"""
+        declared = getattr(self.module, "stage_inputs", None)
+        if declared is not None:     # a graph stage lists what it reads
+            return name in declared
         sig = getattr(self, "_stage_signature", None)
         if sig is None:
             import inspect
@@ -231,6 +234,15 @@ class PipelineEngine:
             kwargs["labels"] = mb["labels"]
         if self._stage_accepts("batch_seq") and "input_ids" in mb:
             kwargs["batch_seq"] = tuple(mb["input_ids"].shape[:2])
+        # graph stages (fx_partitioner.GraphStage) name the forward arguments of the traced model they read: every stage
+        # holds the micro-batch, so these never travel between stages
+        for name in getattr(self.module, "stage_inputs", ()):
+            if name in kwargs or (name == "labels" and not (with_labels and self.is_last)):
+                continue
+            if name in mb:
+                kwargs[name] = mb[name]
+            elif name == getattr(self.module, "first_input_name", None):
+                kwargs[name] = self._first_input(mb)
         return self.module(x, **kwargs)
 
     def _first_input(self, mb: Dict):

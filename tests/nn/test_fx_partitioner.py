@@ -1,0 +1,184 @@
+"""Graph partitioning of models the structural partitioner does not know (reference: partitioner.py:146-244 traces and
+cuts any model; here ``torch.fx`` + single-activation cuts): stage chains reproduce the model, stages are balanced, values
+derived from the inputs are re-computed per stage, and the pipeline engine trains such a model like sequential code."""
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+from pipegoose_b200.nn import PipelineParallel
+from pipegoose_b200.nn.pipeline_parallel.fx_partitioner import GraphPartitioner, GraphStage, NoLegalCut, _minmax_cuts
+from pipegoose_b200.nn.pipeline_parallel.partitioner import UniformPartitioner
+from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+class _Block(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.ln, self.fc1, self.fc2 = nn.LayerNorm(d), nn.Linear(d, 4 * d), nn.Linear(4 * d, d)
+
+    def forward(self, x, mask):
+        return x + self.fc2(torch.relu(self.fc1(self.ln(x)))) * mask.unsqueeze(-1)
+
+
+class _TokenModel(nn.Module):
+    """Not a family the structural partitioner knows: no ``transformer`` attribute, custom argument names."""
+
+    def __init__(self, n_blocks=6, d=16, vocab=50):
+        super().__init__()
+        self.emb = nn.Embedding(vocab, d)
+        self.blocks = nn.ModuleList([_Block(d) for _ in range(n_blocks)])
+        self.head = nn.Linear(d, vocab)
+        self.register_buffer("scale", torch.tensor(2.0))
+        self.vocab = vocab
+
+    def forward(self, tokens, mask, labels=None):
+        m = mask.float() * self.scale          # input-derived: every stage re-computes it
+        x = self.emb(tokens)
+        for b in self.blocks:
+            x = b(x, m)
+        logits = self.head(x)
+        if labels is not None:
+            return nn.functional.cross_entropy(logits.view(-1, self.vocab), labels.view(-1))
+        return logits
+
+
+def _chain(stages, first, **inputs):
+    x = first
+    for st in stages:
+        x = st(x, **inputs)
+    return x
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_stage_chain_reproduces_the_model_and_is_balanced(n):
+    torch.manual_seed(0)
+    net = _TokenModel()
+    ids, mask = torch.randint(0, 50, (2, 5)), torch.ones(2, 5)
+    mask[1, 3:] = 0
+    stages = GraphPartitioner(net, None, n_partitions=n).split()
+    assert len(stages) == n and all(isinstance(s, GraphStage) for s in stages)
+    assert torch.allclose(_chain(stages, ids, mask=mask, labels=ids), net(ids, mask, ids))
+    # every parameter lives in exactly one stage; the embedding does not count towards the balance
+    owned = [id(p) for s in stages for p in s.parameters()]
+    assert sorted(owned) == sorted(id(p) for p in net.parameters())
+    sizes = [sum(p.numel() for p in s.parameters() if p is not net.emb.weight) for s in stages]
+    block = sum(p.numel() for p in net.blocks[0].parameters())
+    assert max(sizes) - min(sizes) <= block
+    # the mask is read by every stage from the micro-batch, only the last stage reads the labels
+    assert all("mask" in s.stage_inputs for s in stages)
+    assert ["labels" in s.stage_inputs for s in stages] == [False] * (n - 1) + [True]
+    assert stages[0].is_first and stages[-1].is_last and stages[0].first_input_name == "tokens"
+
+
+def test_concrete_args_select_the_traced_branch():
+    torch.manual_seed(0)
+    net = _TokenModel(n_blocks=4)
+    ids, mask = torch.randint(0, 50, (3, 4)), torch.ones(3, 4)
+    stages = GraphPartitioner(net, None, n_partitions=2, concrete_args={"labels": None}).split()
+    assert torch.allclose(_chain(stages, ids, mask=mask), net(ids, mask))
+
+
+def test_convolutional_model_without_named_inputs():
+    torch.manual_seed(0)
+
+    class Wrapped(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1, self.c2, self.c3 = nn.Conv2d(3, 8, 3, padding=1), nn.Conv2d(8, 8, 3, padding=1), nn.Conv2d(8, 4, 3, padding=1)
+            self.fc = nn.Linear(4 * 6 * 6, 10)
+
+        def forward(self, img):
+            y = torch.relu(self.c1(img))
+            y = torch.relu(self.c2(y)) + y
+            y = torch.relu(self.c3(y))
+            return self.fc(y.flatten(1))
+
+    net = Wrapped()
+    img = torch.randn(2, 3, 6, 6)
+    for n in (2, 3):
+        stages = GraphPartitioner(net, None, n_partitions=n).split()
+        assert torch.allclose(_chain(stages, img), net(img), atol=1e-6)
+        assert all(s.stage_inputs == () for s in stages)
+
+
+def test_long_skip_connection_limits_the_cuts():
+    class Skip(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = nn.Linear(4, 4), nn.Linear(4, 4), nn.Linear(4, 4)
+
+        def forward(self, x):
+            h = self.a(x)
+            return self.c(self.b(h)) + h     # h is live until the very end: nothing between a and the sum can be cut alone
+
+    net = Skip()
+    with pytest.raises(NoLegalCut, match="exactly one activation"):
+        GraphPartitioner(net, None, n_partitions=3).split()
+    stages = GraphPartitioner(net, None, n_partitions=2).split()   # the one legal cut: right after ``a``
+    x = torch.randn(3, 4)
+    assert torch.allclose(_chain(stages, x), net(x))
+    assert [sum(p.numel() for p in s.parameters()) for s in stages] == [20, 40]
+
+
+def test_uniform_partitioner_falls_back_to_the_graph_and_explains_failures():
+    class Ctx:
+        pipeline_parallel_size = 2
+
+    torch.manual_seed(0)
+    net = _TokenModel(n_blocks=4)
+    stages = UniformPartitioner(net, Ctx()).split()
+    assert len(stages) == 2 and isinstance(stages[0], GraphStage)
+
+    class DataDependent(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(4, 4), nn.Linear(4, 4)
+
+        def forward(self, x):
+            return self.a(x) if x.sum() > 0 else self.b(x)
+
+    with pytest.raises(NotImplementedError, match="register_family.*torch.fx could not trace"):
+        UniformPartitioner(DataDependent(), Ctx()).split()
+
+
+@pytest.mark.parametrize("costs,n,want", [([1, 1, 1, 1], 2, [0, 2, 4]), ([5, 1, 1, 1, 1, 1], 2, [0, 1, 6]),
+                                          ([1, 2160, 2160, 2160, 2160, 2160, 2160, 850], 2, [0, 4, 8]),
+                                          ([3, 3, 3], 3, [0, 1, 2, 3])])
+def test_minmax_cuts(costs, n, want):
+    assert _minmax_cuts(costs, n) == want
+
+
+def run_graph_pipeline(rank, world_size, port, pp, sched, state, ids, mask, ref_loss, ref_grads):
+    ctx = init_parallel_context(rank, world_size, port, 1, pp, 1)
+    model = _TokenModel()
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=4, parallel_context=ctx, scheduler_type=sched).parallelize()
+    assert isinstance(model._pg_pipeline_stage, GraphStage)
+    out = model(ids, mask=mask, labels=ids)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-5)
+    out.loss.backward()
+    n_checked = 0
+    for p in model._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=2e-5), names[id(p)]
+        n_checked += 1
+    assert n_checked > 0
+    with torch.no_grad():
+        assert torch.allclose(model(ids, mask=mask, labels=ids).loss, ref_loss, atol=1e-5)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("pp,sched", [(2, SchedulerType.ONE_F_ONE_B), (3, SchedulerType.GPIPE)])
+def test_pipeline_engine_trains_a_graph_partitioned_model(pp, sched):
+    torch.manual_seed(0)
+    model = _TokenModel()
+    ids = torch.randint(0, 50, (8, 6))
+    mask = (torch.rand(8, 6) > 0.2).float()
+    losses = [model(i, m, i) for i, m in zip(ids.chunk(4), mask.chunk(4))]
+    loss = torch.stack(losses).mean()
+    loss.backward()
+    spawn(run_graph_pipeline, world_size=pp, pp=pp, sched=sched, state=copy.deepcopy(model.state_dict()), ids=ids, mask=mask,
+          ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
