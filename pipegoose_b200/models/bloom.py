@@ -380,10 +380,13 @@ class BloomForCausalLM(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True, **_unused) -> torch.Tensor:
-        """Greedy decoding.  ``use_cache`` (dense MLPs): keys and values of every layer are kept — under tensor
-        parallelism each rank caches the heads it owns — the prompt is processed once and each new token costs one
-        position; MoE models recompute the whole sequence through the training forward for every token."""
-        dense = all(isinstance(b.mlp, BloomMLP) for b in self.transformer.h)
+        """Greedy decoding.  ``use_cache``: keys and values of every layer are kept — under tensor parallelism each rank
+        caches the heads it owns — the prompt is processed once and each new token costs one position.  Mixture-of-experts
+        blocks (``ExpertLayer``) decode incrementally too: the router sees the new positions only (an expert-capacity
+        limit then counts the tokens of one decoding step, not of the whole sequence — with a limit that binds, cached
+        and uncached decoding may drop different tokens).  Models with a fused NVLink MoE layer, whose kernels are built
+        around token-sharded full sequences, recompute the whole sequence through the training forward for every token."""
+        dense = all(isinstance(b.mlp, BloomMLP) or _decodes_incrementally(b.mlp) for b in self.transformer.h)
         if not (use_cache and dense):
             out = input_ids
             group = self.tp.size if self.tp is not None else 1
@@ -443,6 +446,9 @@ class BloomForCausalLM(nn.Module):
             x = x + F.linear(ctx, attn.dense.weight, attn.dense.bias)
             ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
             mlp = block.mlp
+            if not isinstance(mlp, BloomMLP):
+                x = _moe_on_replicated_tokens(mlp, ln, x)
+                continue
             x = x + F.linear(K.gelu_tanh(F.linear(ln, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias)),
                              mlp.dense_4h_to_h.weight, mlp.dense_4h_to_h.bias)
         x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
@@ -493,6 +499,9 @@ class BloomForCausalLM(nn.Module):
             ctx = torch.matmul(scores.softmax(-1).to(v.dtype), v).transpose(1, 2).reshape(B, T, n_local * D)
             x = x + all_reduce(F.linear(ctx, attn.dense.weight)) + attn.dense.bias      # row-parallel: bias once
             ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
+            if not isinstance(mlp, BloomMLP):
+                x = _moe_on_replicated_tokens(mlp, ln, x)    # experts sharded over the group: the layer all-reduces
+                continue
             h1 = K.gelu_tanh(F.linear(ln, mlp.dense_h_to_4h.weight, mlp.dense_h_to_4h.bias))
             x = x + all_reduce(F.linear(h1, mlp.dense_4h_to_h.weight)) + mlp.dense_4h_to_h.bias
         x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
@@ -507,6 +516,36 @@ class BloomForCausalLM(nn.Module):
         model = cls(BloomConfig.from_hf(hf_model.config))
         model.load_state_dict(hf_model.state_dict(), strict=False)
         return model
+
+
+def _decodes_incrementally(mlp: nn.Module) -> bool:
+    """Can this replaced MLP run on a few replicated positions (``mlp(layernorm_output, residual)``)?  ``ExpertLayer``
+    can (router + experts on whatever tokens it is given); the fused NVLink MoE layer cannot."""
+    from pipegoose_b200.nn.expert_parallel.layers import ExpertLayer
+
+    return type(mlp) is ExpertLayer
+
+
+def _moe_on_replicated_tokens(mlp: nn.Module, ln: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    """One decoding step through an ``ExpertLayer``: activations are replicated over the tensor group while decoding, so
+    the layer runs in its replicated-token layout (every rank routes all positions, applies the experts it owns, the
+    partial outputs are all-reduced) whatever layout training uses; the router's auxiliary terms are discarded."""
+    from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+    store = ExpertContext.get_instance()
+    kept_aux, kept_z = store.pop_all_aux_loss(), store.pop_all_z_loss()
+    comm = getattr(mlp, "token_comm", None)
+    mlp.token_comm = None
+    try:
+        out = mlp(ln, residual)
+    finally:
+        mlp.token_comm = comm
+        store.pop_all_aux_loss(), store.pop_all_z_loss()
+        for t in kept_aux:
+            store.push_aux_loss(t)
+        for t in kept_z:
+            store.push_z_loss(t)
+    return out
 
 
 def is_hf_bloom(module: nn.Module) -> bool:
