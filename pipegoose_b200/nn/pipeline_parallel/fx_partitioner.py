@@ -221,7 +221,29 @@ class GraphPartitioner(BasePartitioner):
             carried_out = None if s == n - 1 else carried_at[hi]
             stages.append(self._build_stage(gm, nodes, free, lo, hi, carried_in, carried_out, output, first,
                                             is_first=(s == 0), is_last=(s == n - 1)))
+        self._check_shared_parameters(stages)
         return stages
+
+    def _check_shared_parameters(self, stages: List["GraphStage"]) -> None:
+        """A parameter used by two stages would get only a part of its gradient on each of them.  The one sharing the
+        pipeline engine completes itself is the tied input / output embedding of a model that exposes it through
+        ``get_input_embeddings()`` / ``get_output_embeddings()`` (first and last stage); anything else is refused."""
+        names = {id(p): n for n, p in self.module.named_parameters()}
+        tied = None
+        get_in, get_out = getattr(self.module, "get_input_embeddings", None), getattr(self.module, "get_output_embeddings", None)
+        if callable(get_in) and callable(get_out):
+            emb, head = get_in(), get_out()
+            if emb is not None and head is not None and getattr(head, "weight", None) is getattr(emb, "weight", 0):
+                tied = id(emb.weight)
+        owners: Dict[int, List[int]] = {}
+        for s, stage in enumerate(stages):
+            for p in stage.parameters():
+                owners.setdefault(id(p), []).append(s)
+        for pid, where in owners.items():
+            if len(where) > 1 and not (pid == tied and where == [0, len(stages) - 1]):
+                raise NoLegalCut(f"parameter {names.get(pid, '?')} is used by pipeline stages {where}: its gradient would be "
+                                 "split between them (only a tied input/output embedding exposed through "
+                                 "get_input_embeddings()/get_output_embeddings() is summed across stages)")
 
     def _build_stage(self, gm, nodes, free, lo, hi, carried_in, carried_out, output, first, is_first, is_last) -> GraphStage:
         graph = fx.Graph()

@@ -182,3 +182,26 @@ def test_pipeline_engine_trains_a_graph_partitioned_model(pp, sched):
     loss.backward()
     spawn(run_graph_pipeline, world_size=pp, pp=pp, sched=sched, state=copy.deepcopy(model.state_dict()), ids=ids, mask=mask,
           ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
+
+
+def test_parameters_shared_between_stages_are_refused_unless_they_are_the_tied_embedding():
+    class Shared(nn.Module):
+        def __init__(self, expose):
+            super().__init__()
+            self.emb, self.mid, self.head = nn.Embedding(20, 8), nn.Linear(8, 8), nn.Linear(8, 20, bias=False)
+            self.head.weight = self.emb.weight
+            self.expose = expose
+
+        def get_input_embeddings(self):
+            return self.emb if self.expose else None
+
+        def get_output_embeddings(self):
+            return self.head if self.expose else None
+
+        def forward(self, tokens):
+            return self.head(torch.tanh(self.mid(self.emb(tokens))))
+
+    with pytest.raises(NoLegalCut, match="emb.weight is used by pipeline stages"):
+        GraphPartitioner(Shared(False), None, n_partitions=2).split()
+    stages = GraphPartitioner(Shared(True), None, n_partitions=2).split()     # the engine sums the tied table's gradient
+    assert any(p is stages[1].graph_module.head.weight for p in stages[0].parameters())
