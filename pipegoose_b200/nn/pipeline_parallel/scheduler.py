@@ -43,6 +43,60 @@ class BaseScheduler(ABC):
         return [[t for t in clock if t.job_type is JobType.BACKWARD] for clock in self.get_schedules()
                 if any(t.job_type is JobType.BACKWARD for t in clock)]
 
+    # ------------------------------------------------------------------ timing model of a schedule
+    def simulate(self, forward_cost: float = 1.0, backward_cost: float = 2.0, transfer_cost: float = 0.0):
+        """Event simulation of the per-stage task orders under their data dependencies: every stage runs its tasks
+        in order, a forward of micro-batch ``i`` on stage ``p`` starts once stage ``p - 1`` finished it (+ one transfer),
+        a backward once stage ``p + 1`` finished its backward (the last stage: its own forward).
+
+        Returns ``(makespan, busy, start)``: the length of the step, the busy time per stage, and ``start[task]``.
+        This is what the static runtime executes (one task at a time per stage, batched p2p between neighbours), so it
+        predicts the step time of a layout from a stage's measured forward / backward time."""
+        n = self.n_partitions
+        orders = [self.get_stage_order(p) for p in range(n)]
+        cost = {JobType.FORWARD: forward_cost, JobType.BACKWARD: backward_cost}
+        finish, start = {}, {}
+        cursor, clock = [0] * n, [0.0] * n
+        remaining = sum(len(o) for o in orders)
+        while remaining:
+            progressed = False
+            for p in range(n):
+                while cursor[p] < len(orders[p]):
+                    t = orders[p][cursor[p]]
+                    if t.job_type is JobType.FORWARD:
+                        dep = None if p == 0 else Task(JobType.FORWARD, t.microbatch_idx, p - 1)
+                    elif p == n - 1:
+                        dep = Task(JobType.FORWARD, t.microbatch_idx, p)
+                    else:
+                        dep = Task(JobType.BACKWARD, t.microbatch_idx, p + 1)
+                    if dep is not None and dep not in finish:
+                        break
+                    ready = 0.0 if dep is None else finish[dep] + (transfer_cost if dep.partition_idx != p else 0.0)
+                    start[t] = max(clock[p], ready)
+                    finish[t] = clock[p] = start[t] + cost[t.job_type]
+                    cursor[p] += 1
+                    remaining -= 1
+                    progressed = True
+            assert progressed, "schedule deadlocked"
+        makespan = max(finish.values())
+        busy = [sum(cost[t.job_type] for t in o) for o in orders]
+        return makespan, busy, start
+
+    def bubble_fraction(self, forward_cost: float = 1.0, backward_cost: float = 2.0, transfer_cost: float = 0.0) -> float:
+        """Share of the step a stage spends idle, averaged over the stages: ``1 - busy / makespan``.  With equal stages
+        and free transfers this is ``(n - 1) / (m + n - 1)`` for both GPipe and 1F1B."""
+        makespan, busy, _ = self.simulate(forward_cost, backward_cost, transfer_cost)
+        return 1.0 - sum(busy) / (len(busy) * makespan)
+
+    def peak_live_microbatches(self, partition_idx: int) -> int:
+        """Most micro-batches whose activations stage ``partition_idx`` holds at once (forward done, backward not yet):
+        ``m`` for GPipe, ``min(n - p, m)`` for 1F1B — the reason to prefer 1F1B at equal bubble."""
+        live = peak = 0
+        for t in self.get_stage_order(partition_idx):
+            live += 1 if t.job_type is JobType.FORWARD else -1
+            peak = max(peak, live)
+        return peak
+
     @property
     def total_clock_cycles(self) -> int:
         return len(self.get_schedules())

@@ -365,3 +365,18 @@ def test_partitions_chain_in_the_reference_call_style(family):
     # the library's own call style still gets plain tensors
     h = stages[0](inputs["input_ids"], attention_mask=inputs["attention_mask"])
     assert isinstance(h, torch.Tensor) and h.shape == (2, 7, 32)
+
+
+@pytest.mark.parametrize("m,n", [(8, 2), (4, 4), (16, 4), (3, 2)])
+def test_schedule_timing_model_bubble_and_live_activations(m, n):
+    """``simulate`` / ``bubble_fraction`` / ``peak_live_microbatches``: the closed forms for equal stages."""
+    for cls in (GPipeScheduler, OneFOneBScheduler):
+        sch = cls(m, n)
+        makespan, busy, start = sch.simulate(1.0, 2.0)
+        assert makespan == pytest.approx(3.0 * (m + n - 1)) and busy == [3.0 * m] * n
+        assert sch.bubble_fraction() == pytest.approx((n - 1) / (m + n - 1))
+        assert len(start) == 2 * m * n
+        # transfers stretch the critical path: 2 (n - 1) hops there and back
+        assert sch.simulate(1.0, 2.0, transfer_cost=0.5)[0] >= makespan + 2 * (n - 1) * 0.5 - 1e-9
+    assert [GPipeScheduler(m, n).peak_live_microbatches(p) for p in range(n)] == [m] * n
+    assert [OneFOneBScheduler(m, n).peak_live_microbatches(p) for p in range(n)] == [min(n - p, m) for p in range(n)]
