@@ -86,20 +86,35 @@ class GraphStage(nn.Module):
         return self.graph_module(**kwargs)
 
 
+class _LeafTracer(fx.Tracer):
+    def __init__(self, leaf_types):
+        super().__init__()
+        self._leaf_types = tuple(leaf_types)
+
+    def is_leaf_module(self, m: nn.Module, module_qualified_name: str) -> bool:
+        return isinstance(m, self._leaf_types) or super().is_leaf_module(m, module_qualified_name)
+
+
 class GraphPartitioner(BasePartitioner):
     """``GraphPartitioner(model, parallel_context).split() -> [GraphStage]`` for any model ``torch.fx`` can trace.
 
     ``concrete_args`` / ``tracer`` are handed to the tracing step (a model whose forward branches on ``labels is None``
     needs ``concrete_args={"labels": None}`` or a real ``labels`` placeholder, exactly as with ``torch.fx`` itself); a
-    ready ``GraphModule`` is taken as is."""
+    ready ``GraphModule`` is taken as is.  ``leaf_modules``: module classes to keep as single graph nodes."""
 
     def __init__(self, model: nn.Module, parallel_context, concrete_args: Optional[Dict] = None,
-                 tracer: Optional[fx.Tracer] = None, n_partitions: Optional[int] = None):
+                 tracer: Optional[fx.Tracer] = None, n_partitions: Optional[int] = None,
+                 leaf_modules: Sequence[type] = ()):
         self.module = model
         self.parallel_context = parallel_context
         self.concrete_args = concrete_args
         self.tracer = tracer
         self._n = n_partitions
+        # module classes the tracer does not look into (a block whose forward torch.fx cannot trace — data-dependent
+        # control flow, Python-side caches — is still one node of the graph, and block boundaries are the cuts anyway)
+        self.leaf_modules = tuple(leaf_modules)
+        if self.leaf_modules and tracer is None:
+            self.tracer = _LeafTracer(self.leaf_modules)
 
     # ------------------------------------------------------------------ tracing and node classes
     def trace(self) -> fx.GraphModule:

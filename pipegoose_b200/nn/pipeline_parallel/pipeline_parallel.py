@@ -17,10 +17,14 @@ from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType, get_sch
 class PipelineParallel(Parallel):
     def __init__(self, module: nn.Module, num_microbatches: int, parallel_context: ParallelContext,
                  scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B, runtime: str = "static",
-                 aux_loss_weight: float = 0.01, z_loss_weight: float = 0.001):
+                 aux_loss_weight: float = 0.01, z_loss_weight: float = 0.001, partitioner=None):
         """``runtime``: ``"static"`` (default) — schedule tables + batched p2p (pipeline_engine.py); ``"jobs"`` — the
-        reference's execution model: jobs from packages, worker threads, progress tracker (job_engine.py, GPipe)."""
+        reference's execution model: jobs from packages, worker threads, progress tracker (job_engine.py, GPipe).
+        ``partitioner``: ``None`` (the ``UniformPartitioner``: known families by structure, anything else through its
+        ``torch.fx`` graph) or a callable ``(module, parallel_context) -> partitioner with .split()`` — e.g.
+        ``lambda m, c: GraphPartitioner(m, c, leaf_modules=(MyBlock,), concrete_args={...})``."""
         super().__init__(module, parallel_context)
+        self.partitioner = partitioner
         assert runtime in ("static", "jobs")
         self.num_microbatches = num_microbatches
         self.scheduler_type = scheduler_type if runtime == "static" else SchedulerType.GPIPE
@@ -32,7 +36,9 @@ class PipelineParallel(Parallel):
     def parallelize(self) -> nn.Module:
         module, ctx = self.module, self.parallel_context
         if ctx.pipeline_parallel_size > 1:
-            partitions = UniformPartitioner(module, ctx).split(["input_ids"])
+            make = self.partitioner if self.partitioner is not None else UniformPartitioner
+            partitions = make(module, ctx).split(["input_ids"])
+            assert len(partitions) == ctx.pipeline_parallel_size, "the partitioner must return one stage per pipeline rank"
             stage = partitions[get_partition_idx(ctx)]
             scheduler = get_scheduler(self.scheduler_type)(self.num_microbatches, ctx.pipeline_parallel_size)
             pipeline_context = PipelineContext(scheduler, ctx)

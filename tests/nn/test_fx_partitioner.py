@@ -156,7 +156,8 @@ def run_graph_pipeline(rank, world_size, port, pp, sched, state, ids, mask, ref_
     model = _TokenModel()
     model.load_state_dict(state)
     names = {id(p): n for n, p in model.named_parameters()}
-    model = PipelineParallel(model, num_microbatches=4, parallel_context=ctx, scheduler_type=sched).parallelize()
+    custom = None if pp == 2 else (lambda m, c: GraphPartitioner(m, c, leaf_modules=(_Block,)))   # both entry points
+    model = PipelineParallel(model, num_microbatches=4, parallel_context=ctx, scheduler_type=sched, partitioner=custom).parallelize()
     assert isinstance(model._pg_pipeline_stage, GraphStage)
     out = model(ids, mask=mask, labels=ids)
     assert torch.allclose(out.loss, ref_loss, atol=1e-5)
@@ -205,3 +206,34 @@ def test_parameters_shared_between_stages_are_refused_unless_they_are_the_tied_e
         GraphPartitioner(Shared(False), None, n_partitions=2).split()
     stages = GraphPartitioner(Shared(True), None, n_partitions=2).split()     # the engine sums the tied table's gradient
     assert any(p is stages[1].graph_module.head.weight for p in stages[0].parameters())
+
+
+def test_leaf_modules_keep_untraceable_blocks_as_single_nodes():
+    class Gate(nn.Module):   # data-dependent control flow: torch.fx cannot look inside
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(6, 6), nn.Linear(6, 6)
+
+        def forward(self, x):
+            return x + (self.a(x) if float(x.detach().sum()) > 0 else self.b(x))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inp = nn.Linear(3, 6)
+            self.gates = nn.ModuleList([Gate() for _ in range(4)])
+
+        def forward(self, x):
+            x = self.inp(x)
+            for g in self.gates:
+                x = g(x)
+            return x
+
+    torch.manual_seed(0)
+    net = Net()
+    with pytest.raises(Exception):
+        GraphPartitioner(net, None, n_partitions=2).split()
+    stages = GraphPartitioner(net, None, n_partitions=2, leaf_modules=(Gate,)).split()
+    for x in (torch.randn(5, 3), -torch.rand(5, 3) - 5.0):
+        assert torch.allclose(_chain(stages, x), net(x), atol=1e-6)
+    assert [sum(isinstance(m, Gate) for m in s.modules()) for s in stages] == [2, 2]
