@@ -339,7 +339,10 @@ class UniformPartitioner(BasePartitioner):
 
             why = ""
             try:
-                return GraphPartitioner(model, self.parallel_context, n_partitions=n).split(input_names)
+                try:
+                    return GraphPartitioner(model, self.parallel_context, n_partitions=n).split(input_names)
+                except NoLegalCut:   # long skip connections: let up to four activations cross a cut (packed into one buffer)
+                    return GraphPartitioner(model, self.parallel_context, n_partitions=n, max_boundary_tensors=4).split(input_names)
             except NoLegalCut as e:
                 why = f"  Its torch.fx graph cannot be cut either: {e}"
             except Exception as e:   # torch.fx could not trace it (data-dependent control flow, ...)

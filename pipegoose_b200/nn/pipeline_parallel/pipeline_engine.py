@@ -102,6 +102,15 @@ class _P2PLink:
             meta[2 + i] = s
         dist.send(meta.to(self._device()), dst=peer, group=self.group)
 
+    def send_object(self, obj, peer):
+        """Small Python metadata to a neighbour (handshake only, never in a step)."""
+        dist.send_object_list([obj], dst=peer, group=self.group, device=self._device())
+
+    def recv_object(self, peer):
+        box = [None]
+        dist.recv_object_list(box, src=peer, group=self.group, device=self._device())
+        return box[0]
+
     def recv_shape(self, peer):
         from pipegoose_b200.distributed._p2p import ID_TO_DTYPE
 
@@ -236,6 +245,8 @@ class PipelineEngine:
             kwargs["batch_seq"] = tuple(mb["input_ids"].shape[:2])
         # graph stages (fx_partitioner.GraphStage) name the forward arguments of the traced model they read: every stage
         # holds the micro-batch, so these never travel between stages
+        if getattr(self.module, "multi_in", False):
+            self.module.select_boundary(self._mb_key(mb))     # which micro-batch shape's metadata unpacks ``x``
         for name in getattr(self.module, "stage_inputs", ()):
             if name in kwargs or (name == "labels" and not (with_labels and self.is_last)):
                 continue
@@ -266,9 +277,14 @@ class PipelineEngine:
                     shape, dtype = self.link.recv_shape(self.link.prev)
                     self._in_meta[key] = (shape, dtype)
                     x = torch.zeros(shape, dtype=dtype, device=dev)
+                    if getattr(self.module, "multi_in", False):
+                        # a graph stage that receives several activations packed into one buffer: their shapes / dtypes
+                        self.module.set_in_meta(key, self.link.recv_object(self.link.prev))
                 if not self.is_last:
                     out = self._stage_forward(x, {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in mb.items()}, False)
                     self.link.send_shape(tuple(out.shape), out.dtype, self.link.next)
+                    if getattr(self.module, "multi_out", False):
+                        self.link.send_object(self.module.last_out_meta, self.link.next)
 
     def _prepare(self, inputs: Dict) -> List[Dict]:
         n = self.scheduler.n_microbatches

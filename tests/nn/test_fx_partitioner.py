@@ -237,3 +237,95 @@ def test_leaf_modules_keep_untraceable_blocks_as_single_nodes():
     for x in (torch.randn(5, 3), -torch.rand(5, 3) - 5.0):
         assert torch.allclose(_chain(stages, x), net(x), atol=1e-6)
     assert [sum(isinstance(m, Gate) for m in s.modules()) for s in stages] == [2, 2]
+
+
+class _UNet(nn.Module):
+    """Long skip connections: between the encoder and the decoder TWO or THREE activations are live."""
+
+    def __init__(self, d=8):
+        super().__init__()
+        self.e1, self.e2, self.e3 = nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, d)
+        self.mid = nn.Linear(d, d)
+        self.d3, self.d2, self.d1 = nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, d)
+        self.out = nn.Linear(d, 1)
+
+    def forward(self, x, target=None):
+        a = torch.tanh(self.e1(x))
+        b = torch.tanh(self.e2(a))
+        c = torch.tanh(self.e3(b))
+        m = torch.tanh(self.mid(c))
+        y = torch.tanh(self.d3(m) + c)
+        y = torch.tanh(self.d2(y) + b)
+        y = torch.tanh(self.d1(y) + a)
+        pred = self.out(y).squeeze(-1)
+        if target is not None:
+            return ((pred - target) ** 2).mean()
+        return pred
+
+
+def test_cuts_through_skip_connections_pack_several_activations():
+    torch.manual_seed(0)
+    net = _UNet()
+    x, target = torch.randn(6, 8), torch.randn(6)
+    # single-activation cuts exist only before / after the whole U: one stage gets the encoder, the middle and the decoder
+    single = GraphPartitioner(net, None, n_partitions=4).split()
+    assert max(sum(p.numel() for p in s.parameters()) for s in single) >= 5 * 72
+    stages = GraphPartitioner(net, None, n_partitions=4, max_boundary_tensors=4).split()
+    assert any(s.multi_out for s in stages) and [s.multi_out for s in stages[:-1]] == [s.multi_in for s in stages[1:]]
+    sizes = [sum(p.numel() for p in s.parameters()) for s in stages]
+    assert max(sizes) <= 2 * 72 + 9       # 7 equal layers + the head over 4 stages
+    # chained by hand with tuples
+    for s in stages:
+        s.pack_outputs = False
+    assert torch.allclose(_chain(stages, x, target=target), net(x, target), atol=1e-6)
+    # chained through packed buffers, as the engine does: metadata from the producer, gradients through pack / unpack
+    for s in stages:
+        s.pack_outputs = True
+    net.zero_grad()
+    net(x, target).backward()
+    want = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    h = x
+    for i, s in enumerate(stages):
+        if s.multi_in:
+            assert h.dim() == 1
+            s.set_in_meta("k", stages[i - 1].last_out_meta)
+            s.select_boundary("k")
+        h = s(h, target=target)
+    assert torch.allclose(h, net(x, target), atol=1e-6)
+    h.backward()
+    for n, p in net.named_parameters():
+        assert torch.allclose(p.grad, want[n], atol=1e-6), n
+    with pytest.raises(TypeError, match="floating-point"):
+        GraphStage.pack([torch.zeros(2), torch.zeros(2, dtype=torch.long)])
+
+
+def run_unet_pipeline(rank, world_size, port, pp, state, x, target, ref_loss, ref_grads):
+    ctx = init_parallel_context(rank, world_size, port, 1, pp, 1)
+    model = _UNet()
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=3, parallel_context=ctx, scheduler_type=SchedulerType.ONE_F_ONE_B,
+                             partitioner=lambda m, c: GraphPartitioner(m, c, max_boundary_tensors=4)).parallelize()
+    # labels= switches the engine to its training schedule; the model's own name for them travels as a named input
+    out = model(x, target=target, labels=target)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-6)
+    out.loss.backward()
+    for p in model._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=1e-6), names[id(p)]
+    # a second step with a different micro-batch size: new handshake, new boundary metadata
+    out2 = model(x[:3], target=target[:3], labels=target[:3])
+    assert torch.isfinite(out2.loss)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("pp", [2, 4])
+def test_pipeline_engine_moves_packed_boundaries(pp):
+    torch.manual_seed(0)
+    model = _UNet()
+    x, target = torch.randn(6, 8), torch.randn(6)
+    losses = [model(a, b) for a, b in zip(x.chunk(3), target.chunk(3))]
+    loss = torch.stack(losses).mean()
+    loss.backward()
+    spawn(run_unet_pipeline, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), x=x, target=target,
+          ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
