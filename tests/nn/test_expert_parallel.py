@@ -220,3 +220,18 @@ def test_expert_parallel_on_a_llama_style_model():
         ctx.destroy()
 
     run(0, 1, __import__("pipegoose_b200.testing.utils", fromlist=["find_free_port"]).find_free_port())
+
+
+def test_fused_moe_switch_is_honoured(monkeypatch):
+    """``PIPEGOOSE_B200_FUSED_MOE=0`` (flipped by bench.py's numerics self-check together with _FUSED_TP / _FUSED_DP) keeps
+    ``ExpertParallel(fused=None)`` on the plain ``ExpertLayer`` whatever the automatic choice would be; ``fused=True`` is
+    an explicit request and not overridden."""
+    from pipegoose_b200.nn.expert_parallel import expert_parallel as EP
+
+    wrapper = EP.ExpertParallel.__new__(EP.ExpertParallel)
+    wrapper.fused, wrapper.enable_tensor_parallelism = None, False
+    monkeypatch.setenv("PIPEGOOSE_B200_FUSED_MOE", "0")
+    assert wrapper._use_fused(expert=None) is False          # decided before anything about the model is looked at
+    import pathlib
+
+    assert "PIPEGOOSE_B200_FUSED_MOE" in (pathlib.Path(__file__).resolve().parents[2] / "bench.py").read_text()
