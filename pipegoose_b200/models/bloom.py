@@ -379,36 +379,82 @@ class BloomForCausalLM(nn.Module):
         return CausalLMOutput(loss=None, logits=logits)
 
     @torch.no_grad()
-    def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True, **_unused) -> torch.Tensor:
-        """Greedy decoding.  ``use_cache``: keys and values of every layer are kept — under tensor parallelism each rank
-        caches the heads it owns — the prompt is processed once and each new token costs one position.  Mixture-of-experts
-        blocks (``ExpertLayer``) decode incrementally too: the router sees the new positions only (an expert-capacity
-        limit then counts the tokens of one decoding step, not of the whole sequence — with a limit that binds, cached
-        and uncached decoding may drop different tokens).  Models with a fused NVLink MoE layer, whose kernels are built
-        around token-sharded full sequences, recompute the whole sequence through the training forward for every token."""
+    def generate(self, input_ids: torch.Tensor, max_new_tokens: int = 1, use_cache: bool = True,
+                 attention_mask: Optional[torch.Tensor] = None, do_sample: bool = False, temperature: float = 1.0,
+                 top_k: int = 0, top_p: float = 1.0, eos_token_id: Optional[int] = None,
+                 pad_token_id: Optional[int] = None, generator: Optional[torch.Generator] = None, **_unused) -> torch.Tensor:
+        """Decoding with 🤗 ``generate``'s vocabulary for the common cases: greedy by default, ``do_sample`` with
+        ``temperature`` / ``top_k`` / ``top_p``; rows stop at ``eos_token_id`` (later positions hold ``pad_token_id``,
+        default: the eos id) and the loop ends when every row has stopped; returns ``input_ids`` followed by the new
+        tokens.  Under tensor parallelism every rank returns the same tokens (sampled on the group's first rank).
+
+        ``use_cache``: keys and values of every layer are kept — under tensor parallelism each rank caches the heads it
+        owns — the prompt is processed once and each new token costs one position.  Mixture-of-experts blocks
+        (``ExpertLayer``) decode incrementally too: the router sees the new positions only (an expert-capacity limit
+        then counts the tokens of one decoding step, not of the whole sequence — with a limit that binds, cached and
+        uncached decoding may drop different tokens).  Recomputed through the training forward for every token instead:
+        models with a fused NVLink MoE layer (kernels built around token-sharded full sequences) and batches whose
+        ``attention_mask`` has pads (🤗's left-padded prompts of unequal length: rows sit at different positions)."""
+        B, prompt_len = input_ids.shape
+        ragged = attention_mask is not None and bool((attention_mask == 0).any())
         dense = all(isinstance(b.mlp, BloomMLP) or _decodes_incrementally(b.mlp) for b in self.transformer.h)
-        if not (use_cache and dense):
-            out = input_ids
-            group = self.tp.size if self.tp is not None else 1
-            for _ in range(max_new_tokens):
-                B, S = out.shape
-                pad = 0
-                while (B * (S + pad)) % group:   # token-sharded activations: right-pad (harmless under a causal mask)
-                    pad += 1
-                padded = out if pad == 0 else torch.cat([out, out.new_zeros(B, pad)], dim=1)
-                logits = self(padded).logits
-                out = torch.cat([out, logits[:, S - 1, :].float().argmax(-1, keepdim=True)], dim=1)
-            return out
-        cache = [None] * len(self.transformer.h)
+        cached = use_cache and dense and not ragged
+        group = self.tp.size if self.tp is not None else 1
+        mask = attention_mask.to(input_ids.device).long() if ragged else None
         out = input_ids
-        logits = self._incremental_logits(input_ids, cache, 0)          # prefill
-        for _ in range(max_new_tokens):
-            nxt = logits[:, -1, :].float().argmax(-1, keepdim=True)
-            out = torch.cat([out, nxt], dim=1)
-            if out.shape[1] - input_ids.shape[1] == max_new_tokens:
+        finished = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
+        fill = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
+        cache = [None] * len(self.transformer.h)
+        for step in range(max_new_tokens):
+            if cached:
+                last = self._incremental_logits(out if step == 0 else out[:, -1:], cache, 0 if step == 0 else out.shape[1] - 1)[:, -1, :]
+            else:
+                S = out.shape[1]
+                pad = 0
+                while (B * (S + pad)) % group:   # token-sharded activations need a multiple of the group size
+                    pad += 1
+                if ragged:   # pads go in FRONT (mask 0): the batch stays left-padded, the last column the newest token
+                    ids = out if pad == 0 else torch.cat([out.new_zeros(B, pad), out], dim=1)
+                    m = mask if pad == 0 else torch.cat([mask.new_zeros(B, pad), mask], dim=1)
+                    last = self(ids, attention_mask=m).logits[:, -1, :]
+                else:        # right padding is harmless under a causal mask
+                    ids = out if pad == 0 else torch.cat([out, out.new_zeros(B, pad)], dim=1)
+                    last = self(ids).logits[:, S - 1, :]
+            nxt = self._select_token(last.float(), do_sample, temperature, top_k, top_p, generator)
+            if eos_token_id is not None:
+                nxt = torch.where(finished, torch.full_like(nxt, fill), nxt)
+                finished = finished | (nxt == eos_token_id)
+            out = torch.cat([out, nxt[:, None]], dim=1)
+            if ragged:
+                mask = torch.cat([mask, mask.new_ones(B, 1)], dim=1)
+            if eos_token_id is not None and bool(finished.all()):
                 break
-            logits = self._incremental_logits(nxt, cache, out.shape[1] - 1)
         return out
+
+    def _select_token(self, logits: torch.Tensor, do_sample: bool, temperature: float, top_k: int, top_p: float,
+                      generator: Optional[torch.Generator]) -> torch.Tensor:
+        """Next token of every row from its fp32 logits ``[B, V]``: arg-max, or a sample from the (temperature-scaled,
+        top-k / nucleus-filtered) distribution.  Sampled tokens are made identical on every tensor-parallel rank."""
+        if not do_sample:
+            return logits.argmax(-1)
+        if temperature != 1.0:
+            logits = logits / max(float(temperature), 1e-6)
+        if top_k and top_k > 0:
+            kth = logits.topk(min(int(top_k), logits.shape[-1]), dim=-1).values[:, -1:]
+            logits = logits.masked_fill(logits < kth, float("-inf"))
+        if top_p < 1.0:
+            sorted_logits, order = logits.sort(dim=-1, descending=True)
+            probs = sorted_logits.softmax(-1)
+            # drop a token when the mass BEFORE it already reaches top_p (the most likely token always stays)
+            drop = (probs.cumsum(-1) - probs) >= top_p
+            sorted_logits = sorted_logits.masked_fill(drop, float("-inf"))
+            logits = torch.full_like(logits, float("-inf")).scatter(-1, order, sorted_logits)
+        nxt = torch.multinomial(logits.softmax(-1), 1, generator=generator).squeeze(-1)
+        if self.tp is not None and self.tp.size > 1:
+            import torch.distributed as dist
+
+            dist.broadcast(nxt, src=dist.get_global_rank(self.tp.group, 0), group=self.tp.group)
+        return nxt
 
     def _incremental_logits(self, ids: torch.Tensor, cache: list, past: int) -> torch.Tensor:
         """Inference-only forward of ``ids`` (positions ``past .. past+T-1``) against the cached keys / values; plain

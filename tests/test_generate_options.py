@@ -1,0 +1,114 @@
+"""``generate()`` beyond greedy decoding of equal-length prompts: left-padded prompts of unequal length (what 🤗's Bloom
+tokenizer produces for a batch; the mask used to be ignored — pads were read as tokens), end-of-sequence handling, and
+sampling (temperature / top-k / top-p), identical on every tensor-parallel rank."""
+import copy
+
+import pytest
+import torch
+
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+
+def _pair():
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    torch.manual_seed(0)
+    hf = HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)).eval()
+    return hf, BloomForCausalLM.from_hf(hf).eval()
+
+
+def test_left_padded_prompts_of_unequal_length_match_transformers():
+    hf, mine = _pair()
+    ids = torch.randint(1, 96, (3, 7), generator=torch.Generator().manual_seed(1))
+    mask = torch.ones_like(ids)
+    mask[0, :3] = 0
+    mask[2, :5] = 0
+    ids = ids * mask                                           # pad id 0 in front
+    want = hf.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, do_sample=False, pad_token_id=0)
+    got = mine.generate(ids, attention_mask=mask, max_new_tokens=5)
+    assert torch.equal(got, want)
+    # every row equals what it generates alone, without padding
+    for r, skip in ((0, 3), (2, 5)):
+        alone = mine.generate(ids[r:r + 1, skip:], max_new_tokens=5)
+        assert torch.equal(alone[0, -5:], got[r, -5:])
+    # a mask without pads takes the cached path
+    full = torch.ones_like(ids)
+    assert torch.equal(mine.generate(ids, attention_mask=full, max_new_tokens=4), mine.generate(ids, max_new_tokens=4))
+
+
+def test_end_of_sequence_handling_matches_transformers():
+    hf, mine = _pair()
+    ids = torch.randint(1, 96, (4, 5), generator=torch.Generator().manual_seed(2))
+    greedy = mine.generate(ids, max_new_tokens=8)
+    eos = int(greedy[0, 6])                                    # a token row 0 emits as its second new token
+    want = hf.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=8, do_sample=False,
+                       eos_token_id=eos, pad_token_id=0)
+    for use_cache in (True, False):
+        got = mine.generate(ids, max_new_tokens=8, eos_token_id=eos, pad_token_id=0, use_cache=use_cache)
+        assert torch.equal(got, want)
+    first = int((got[0, 5:] == eos).float().argmax()) + 5      # row 0's first eos among the new tokens
+    assert first <= 6 and (got[0, first + 1:] == 0).all()
+    # all rows finished -> the loop stops early
+    one = mine.generate(ids[:1], max_new_tokens=8, eos_token_id=eos)
+    assert one.shape[1] == first + 1 and one[0, -1] == eos
+
+
+def test_sampling_filters_and_reproducibility():
+    _, mine = _pair()
+    ids = torch.randint(1, 96, (2, 6), generator=torch.Generator().manual_seed(3))
+    greedy = mine.generate(ids, max_new_tokens=6)
+    assert torch.equal(mine.generate(ids, max_new_tokens=6, do_sample=True, top_k=1), greedy)
+    assert torch.equal(mine.generate(ids, max_new_tokens=6, do_sample=True, top_p=1e-6), greedy)
+    assert torch.equal(mine.generate(ids, max_new_tokens=6, do_sample=True, temperature=1e-4), greedy)
+    a = mine.generate(ids, max_new_tokens=6, do_sample=True, temperature=1.5, generator=torch.Generator().manual_seed(7))
+    b = mine.generate(ids, max_new_tokens=6, do_sample=True, temperature=1.5, generator=torch.Generator().manual_seed(7))
+    assert torch.equal(a, b) and not torch.equal(a, greedy)
+    # the filters: a sampled token is always among the k most likely / inside the nucleus
+    logits = torch.randn(64, 96, generator=torch.Generator().manual_seed(4)) * 3
+    g = torch.Generator().manual_seed(5)
+    for _ in range(5):
+        tok = mine._select_token(logits, True, 1.0, 4, 1.0, g)
+        assert (logits.topk(4, -1).indices == tok[:, None]).any(-1).all()
+        tok = mine._select_token(logits, True, 1.0, 0, 0.5, g)
+        probs = logits.softmax(-1)
+        sorted_p, order = probs.sort(-1, descending=True)
+        before = sorted_p.cumsum(-1) - sorted_p
+        rank_of = (order == tok[:, None]).float().argmax(-1)
+        assert (before.gather(1, rank_of[:, None]) < 0.5).all()
+    # frequencies follow the distribution
+    row = torch.tensor([[2.0, 1.0, 0.0, -1.0] + [-30.0] * 92])
+    draws = torch.stack([mine._select_token(row, True, 1.0, 0, 1.0, g) for _ in range(2000)]).squeeze(1)
+    freq = torch.bincount(draws, minlength=96)[:4].float() / 2000
+    assert torch.allclose(freq, row.softmax(-1)[0, :4], atol=0.04)
+
+
+def run_tp_sampling(rank, world_size, port, state, ids, mask):
+    import torch.distributed as dist
+
+    from pipegoose_b200.nn import TensorParallel
+
+    ctx = init_parallel_context(rank, world_size, port, 2, 1, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize().eval()
+    torch.manual_seed(100 + rank)                              # different RNG streams: the group must still agree
+    sampled = model.generate(ids, max_new_tokens=6, do_sample=True, temperature=1.3, top_k=20)
+    ragged = model.generate(ids, attention_mask=mask, max_new_tokens=4)
+    both = [None, None]
+    dist.all_gather_object(both, (sampled.tolist(), ragged.tolist()))
+    assert both[0] == both[1]
+    ctx.destroy()
+    return None
+
+
+def test_tensor_parallel_ranks_agree_on_sampled_tokens_and_ragged_prompts():
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4)).eval()
+    ids = torch.randint(1, 96, (2, 5), generator=torch.Generator().manual_seed(6))
+    mask = torch.ones_like(ids)
+    mask[1, :2] = 0
+    want = model.generate(ids * mask, attention_mask=mask, max_new_tokens=4)
+    spawn(run_tp_sampling, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids * mask, mask=mask)
+    assert want.shape == (2, 9)
