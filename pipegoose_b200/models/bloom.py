@@ -10,8 +10,9 @@ attention is the flash ALiBi kernel, the lm_head is fused with a vocab-parallel 
 Dropout: Bloom's ``hidden_dropout`` / ``attention_dropout`` default to 0.0, which is what the fully fused sub-layers
 implement.  ``hidden_dropout > 0`` (🤗 Bloom's ``dropout_add`` after the attention projection and after the MLP) is
 supported in training through a composed path: the same kernels with the residual add taken out of the GEMM epilogue
-and ``dropout(.) + residual`` applied between them.  ``attention_dropout`` (on the attention probabilities) has no
-counterpart in the flash kernel and is refused.
+and ``dropout(.) + residual`` applied between them.  ``attention_dropout > 0`` (on the attention probabilities) takes
+the same composed path with the flash kernel replaced by ``ops.attention.alibi_attention_with_dropout`` (probabilities
+materialised a head group at a time).  Both only act in ``train()`` mode; ``eval()`` always runs the fused sub-layers.
 """
 from __future__ import annotations
 
@@ -136,8 +137,9 @@ class BloomBlock(nn.Module):
         self.tp = None  # set by TensorParallel (sequence-parallel communicator)
 
     def _forward_with_dropout(self, x: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
-        """``hidden_dropout > 0`` in training: ``x + dropout(dense(attention))`` and ``x + dropout(mlp)`` — the kernels
-        of the fused path with the residual add applied after the dropout instead of in the GEMM epilogue."""
+        """``hidden_dropout > 0`` or ``attention_dropout > 0`` in training: ``x + dropout(dense(attention))`` and
+        ``x + dropout(mlp)`` — the kernels of the fused path with the residual add applied after the dropout instead of
+        in the GEMM epilogue; attention probabilities are dropped in ``alibi_attention_with_dropout``."""
         import torch.nn.functional as F
 
         from pipegoose_b200.ops.attention import alibi_attention
@@ -147,7 +149,8 @@ class BloomBlock(nn.Module):
         zero = torch.zeros_like(x)
         qkv = PF.layernorm_linear(x, self.input_layernorm.weight, self.input_layernorm.bias,
                                   attn.query_key_value.weight, attn.query_key_value.bias, self.eps, tp)
-        att = alibi_attention(qkv, attn.alibi_slopes_local(n_head_local), batch, seq, n_head_local, attn.head_dim)
+        att = alibi_attention(qkv, attn.alibi_slopes_local(n_head_local), batch, seq, n_head_local, attn.head_dim,
+                              dropout_p=getattr(self, "attention_dropout", 0.0))
         x = x + F.dropout(PF.linear_residual(att, attn.dense.weight, attn.dense.bias, zero, tp), p, True)
         mlp = self.mlp
         if isinstance(mlp, BloomMLP):
@@ -159,7 +162,7 @@ class BloomBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, batch: int, seq: int) -> torch.Tensor:
         """``x``: ``[tokens_local, hidden]`` (token-sharded when ``self.tp`` is set)."""
-        if getattr(self, "hidden_dropout", 0.0) > 0.0 and self.training:
+        if self.training and (getattr(self, "hidden_dropout", 0.0) > 0.0 or getattr(self, "attention_dropout", 0.0) > 0.0):
             return self._forward_with_dropout(x, batch, seq)
         attn = self.self_attention
         tp = self.tp
@@ -286,8 +289,6 @@ class BloomForCausalLM(nn.Module):
 
     def __init__(self, config: BloomConfig):
         super().__init__()
-        assert config.attention_dropout == 0.0, \
-            "attention_dropout > 0 is not supported (the flash attention kernel keeps no [S, S] probabilities to drop)"
         assert not config.apply_residual_connection_post_layernorm
         self.config = config
         self.transformer = BloomModel(config)
@@ -392,22 +393,32 @@ class BloomForCausalLM(nn.Module):
         owns — the prompt is processed once and each new token costs one position.  Mixture-of-experts blocks
         (``ExpertLayer``) decode incrementally too: the router sees the new positions only (an expert-capacity limit
         then counts the tokens of one decoding step, not of the whole sequence — with a limit that binds, cached and
-        uncached decoding may drop different tokens).  Recomputed through the training forward for every token instead:
-        models with a fused NVLink MoE layer (kernels built around token-sharded full sequences) and batches whose
-        ``attention_mask`` has pads (🤗's left-padded prompts of unequal length: rows sit at different positions)."""
+        uncached decoding may drop different tokens).  🤗's left-padded prompts of unequal length (``attention_mask`` with
+        leading zeros) are cached too: pad keys are masked per row, ALiBi only sees distances between real tokens.
+        Masks that are not left-padded are refused (the new tokens go behind the last column).  Recomputed through the
+        training forward for every token instead: models with a fused NVLink MoE layer (kernels built around
+        token-sharded full sequences) and ``use_cache=False``."""
         B, prompt_len = input_ids.shape
         ragged = attention_mask is not None and bool((attention_mask == 0).any())
         dense = all(isinstance(b.mlp, BloomMLP) or _decodes_incrementally(b.mlp) for b in self.transformer.h)
-        cached = use_cache and dense and not ragged
         group = self.tp.size if self.tp is not None else 1
         mask = attention_mask.to(input_ids.device).long() if ragged else None
+        lead = None
+        if ragged:
+            # pads in front of each row; the KV-cache path takes LEFT-padded prompts (every row: zeros, then ones)
+            lead = (mask.cumsum(1) == 0).sum(1)
+            if not bool((mask.sum(1) + lead == prompt_len).all()):
+                raise ValueError("generate() takes LEFT-padded prompts (attention_mask rows: zeros, then ones): new tokens "
+                                 "are appended behind the last column, which must be every row's last real token")
+        cached = use_cache and dense
         out = input_ids
         finished = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
         fill = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
         cache = [None] * len(self.transformer.h)
         for step in range(max_new_tokens):
             if cached:
-                last = self._incremental_logits(out if step == 0 else out[:, -1:], cache, 0 if step == 0 else out.shape[1] - 1)[:, -1, :]
+                last = self._incremental_logits(out if step == 0 else out[:, -1:], cache,
+                                                0 if step == 0 else out.shape[1] - 1, lead)[:, -1, :]
             else:
                 S = out.shape[1]
                 pad = 0
@@ -456,9 +467,14 @@ class BloomForCausalLM(nn.Module):
             dist.broadcast(nxt, src=dist.get_global_rank(self.tp.group, 0), group=self.tp.group)
         return nxt
 
-    def _incremental_logits(self, ids: torch.Tensor, cache: list, past: int) -> torch.Tensor:
+    def _incremental_logits(self, ids: torch.Tensor, cache: list, past: int,
+                            lead: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Inference-only forward of ``ids`` (positions ``past .. past+T-1``) against the cached keys / values; plain
-        tensor ops on the module's weights (the fused training kernels are built around full sequences)."""
+        tensor ops on the module's weights (the fused training kernels are built around full sequences).  ``lead[b]``:
+        number of pad positions in front of row ``b`` (left-padded batch; None: no pads) — pad keys are masked with a
+        large finite negative (a pad QUERY then attends uniformly instead of producing NaNs that ``0 * NaN`` would
+        carry into real rows), learned absolute positions count from the first real token.  ALiBi needs no shift:
+        ``slope * key_position`` differs from 🤗's mask-derived bias by a per-row constant, which softmax ignores."""
         import torch.nn.functional as F
 
         t, cfg = self.transformer, self.config
@@ -467,10 +483,10 @@ class BloomForCausalLM(nn.Module):
         D = h // n_head
         tp = self.tp
         if tp is not None:
-            return self._incremental_logits_tp(ids, cache, past)
+            return self._incremental_logits_tp(ids, cache, past, lead)
         x = F.embedding(ids, t.word_embeddings.weight)
         if getattr(cfg, "position_embedding", "alibi") == "learned":
-            x = x + t.position_embeddings.weight[past:past + T]
+            x = x + _learned_positions(t.position_embeddings.weight, past, T, lead)
         else:
             x = F.layer_norm(x, (h,), t.word_embeddings_layernorm.weight, t.word_embeddings_layernorm.bias, cfg.layer_norm_epsilon)
         for li, block in enumerate(t.h):
@@ -488,6 +504,7 @@ class BloomForCausalLM(nn.Module):
                 scores = scores + K.alibi_slopes(n_head, device=ids.device).view(1, n_head, 1, 1) * key_pos
             query_pos = torch.arange(past, past + T, device=ids.device).view(T, 1)
             scores = scores.masked_fill(key_pos.view(1, S) > query_pos, float("-inf"))
+            scores = _mask_leading_pads(scores, key_pos, lead)
             ctx = torch.matmul(scores.softmax(-1).to(v.dtype), v).transpose(1, 2).reshape(B, T, h)
             x = x + F.linear(ctx, attn.dense.weight, attn.dense.bias)
             ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
@@ -500,7 +517,8 @@ class BloomForCausalLM(nn.Module):
         x = F.layer_norm(x[:, -1:], (h,), t.ln_f.weight, t.ln_f.bias, cfg.layer_norm_epsilon)
         return F.linear(x, self.lm_head.weight)
 
-    def _incremental_logits_tp(self, ids: torch.Tensor, cache: list, past: int) -> torch.Tensor:
+    def _incremental_logits_tp(self, ids: torch.Tensor, cache: list, past: int,
+                               lead: Optional[torch.Tensor] = None) -> torch.Tensor:
         """:meth:`_incremental_logits` on a tensor-parallel model: activations are replicated ``[B, T, h]`` (decoding is
         latency-bound: no sequence sharding), every rank runs the attention heads / MLP columns / vocabulary rows it owns
         and caches ITS heads' keys and values; row-parallel products and the embedding are summed over the group, the
@@ -524,7 +542,7 @@ class BloomForCausalLM(nn.Module):
         x = F.embedding(local.clamp(0, table.shape[0] - 1), table) * mine.unsqueeze(-1).to(table.dtype)
         x = all_reduce(x)
         if getattr(cfg, "position_embedding", "alibi") == "learned":
-            x = x + t.position_embeddings.weight[past:past + T]
+            x = x + _learned_positions(t.position_embeddings.weight, past, T, lead)
         else:
             x = F.layer_norm(x, (h,), t.word_embeddings_layernorm.weight, t.word_embeddings_layernorm.bias, cfg.layer_norm_epsilon)
         for li, block in enumerate(t.h):
@@ -542,6 +560,7 @@ class BloomForCausalLM(nn.Module):
             scores = scores + attn.alibi_slopes_local(n_local).view(1, n_local, 1, 1) * key_pos
             query_pos = torch.arange(past, past + T, device=ids.device).view(T, 1)
             scores = scores.masked_fill(key_pos.view(1, S) > query_pos, float("-inf"))
+            scores = _mask_leading_pads(scores, key_pos, lead)
             ctx = torch.matmul(scores.softmax(-1).to(v.dtype), v).transpose(1, 2).reshape(B, T, n_local * D)
             x = x + all_reduce(F.linear(ctx, attn.dense.weight)) + attn.dense.bias      # row-parallel: bias once
             ln = F.layer_norm(x, (h,), block.post_attention_layernorm.weight, block.post_attention_layernorm.bias, block.eps)
@@ -562,6 +581,24 @@ class BloomForCausalLM(nn.Module):
         model = cls(BloomConfig.from_hf(hf_model.config))
         model.load_state_dict(hf_model.state_dict(), strict=False)
         return model
+
+
+def _mask_leading_pads(scores: torch.Tensor, key_pos: torch.Tensor, lead: Optional[torch.Tensor]) -> torch.Tensor:
+    """``scores [B, H, T, S]``: keys in front of row ``b``'s first real token (``key_pos < lead[b]``) get the most
+    negative finite value."""
+    if lead is None:
+        return scores
+    pad = key_pos.view(1, 1, 1, -1) < lead.view(-1, 1, 1, 1).to(key_pos.dtype)
+    return scores.masked_fill(pad, torch.finfo(scores.dtype).min)
+
+
+def _learned_positions(table: torch.Tensor, past: int, T: int, lead: Optional[torch.Tensor]) -> torch.Tensor:
+    """Rows of a learned absolute position table for raw positions ``past .. past+T-1``; with left padding a row's
+    positions count from its first real token (pads read position 0)."""
+    if lead is None:
+        return table[past:past + T]
+    pos = (torch.arange(past, past + T, device=table.device).view(1, T) - lead.view(-1, 1)).clamp(min=0)
+    return table[pos]
 
 
 def _decodes_incrementally(mlp: nn.Module) -> bool:
@@ -603,8 +640,6 @@ def is_hf_bloom(module: nn.Module) -> bool:
 def hf_bloom_fast_path_blocker(hf_model) -> Optional[str]:
     """Why this 🤗 Bloom cannot run on the fused path (None: it can)."""
     c = hf_model.config
-    if getattr(c, "attention_dropout", 0.0) != 0.0:
-        return "non-zero attention_dropout"
     if getattr(c, "apply_residual_connection_post_layernorm", False):
         return "apply_residual_connection_post_layernorm"
     if hf_model.lm_head.weight is not hf_model.transformer.word_embeddings.weight:
@@ -648,6 +683,7 @@ def convert_hf_bloom_(hf_model) -> "BloomForCausalLM":
         block.__class__ = BloomBlock
         block.eps = cfg.layer_norm_epsilon
         block.hidden_dropout = float(cfg.hidden_dropout)
+        block.attention_dropout = float(cfg.attention_dropout)
         block.tp = None
     t.__class__ = BloomModel
     t.config = cfg

@@ -18,7 +18,9 @@ from pipegoose_b200.ops import has_kernel, native, use_native
 
 
 def alibi_attention_reference(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int,
-                              softmax_scale: float = 0.0) -> torch.Tensor:
+                              softmax_scale: float = 0.0, dropout_p: float = 0.0) -> torch.Tensor:
+    """``dropout_p > 0``: dropout on the attention probabilities (🤗 Bloom's ``attention_dropout``: zeroed entries, the
+    rest scaled by ``1 / (1 - p)``, rows not re-normalised)."""
     x = qkv.view(B, S, n_head, 3, D)
     q, k, v = (x[:, :, :, i].permute(0, 2, 1, 3).float() for i in range(3))  # [B, H, S, D]
     scores = torch.matmul(q, k.transpose(-1, -2)) * (softmax_scale if softmax_scale > 0 else 1.0 / math.sqrt(D))
@@ -27,8 +29,33 @@ def alibi_attention_reference(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S
     causal = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
     scores = scores.masked_fill(~causal, float("-inf"))
     p = torch.softmax(scores, dim=-1)
+    if dropout_p > 0.0:
+        p = torch.nn.functional.dropout(p, dropout_p, True)
     out = torch.matmul(p, v)  # [B, H, S, D]
     return out.permute(0, 2, 1, 3).reshape(B * S, n_head * D).to(qkv.dtype)
+
+
+def alibi_attention_with_dropout(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int,
+                                 dropout_p: float) -> torch.Tensor:
+    """Training-time attention with dropout on the probabilities.  The flash kernel never holds a row of probabilities
+    (online softmax), so this path materialises them: bf16 GEMMs around an fp32 softmax, one head group at a time so
+    that the live ``[B, heads, S, S]`` block stays below ~1 GiB whatever the model.  Differentiated by autograd."""
+    x = qkv.view(B, S, n_head, 3, D)
+    scale = 1.0 / math.sqrt(D)
+    pos = torch.arange(S, device=qkv.device, dtype=torch.float32)
+    causal = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    group = max(1, min(n_head, (1 << 28) // max(1, B * S * S)))     # heads per block: <= 2^28 fp32 scores
+    outs = []
+    for h0 in range(0, n_head, group):
+        h1 = min(n_head, h0 + group)
+        q, k, v = (x[:, :, h0:h1, i].permute(0, 2, 1, 3) for i in range(3))      # [B, g, S, D] views
+        scores = torch.matmul(q, k.transpose(-1, -2)).float() * scale
+        scores = scores + slopes[h0:h1].float().view(1, -1, 1, 1) * pos.view(1, 1, 1, S)
+        p = torch.softmax(scores.masked_fill(~causal, float("-inf")), dim=-1)
+        p = torch.nn.functional.dropout(p, dropout_p, True).to(qkv.dtype)
+        outs.append(torch.matmul(p, v))
+    out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+    return out.permute(0, 2, 1, 3).reshape(B * S, n_head * D)
 
 
 class _AlibiAttentionNative(torch.autograd.Function):
@@ -103,7 +130,10 @@ class _AlibiAttentionPadded(torch.autograd.Function):
         return unpad_heads(dqkv_p, n_head, 3, D, DP).contiguous(), None, None, None, None, None
 
 
-def alibi_attention(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int) -> torch.Tensor:
+def alibi_attention(qkv: torch.Tensor, slopes: torch.Tensor, B: int, S: int, n_head: int, D: int,
+                    dropout_p: float = 0.0) -> torch.Tensor:
+    if dropout_p > 0.0:
+        return alibi_attention_with_dropout(qkv, slopes, B, S, n_head, D, dropout_p)
     if use_native(qkv) and _native_attention_available(D):
         return _AlibiAttentionNative.apply(qkv, slopes, B, S, n_head, D)
     if use_native(qkv) and has_kernel("attention_fwd") and padded_head_dim(D) > 0 and D % 8 == 0:

@@ -27,8 +27,19 @@ def test_left_padded_prompts_of_unequal_length_match_transformers():
     mask[2, :5] = 0
     ids = ids * mask                                           # pad id 0 in front
     want = hf.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, do_sample=False, pad_token_id=0)
+    calls = []
+    inner = mine._incremental_logits
+    mine._incremental_logits = lambda *a, **k: (calls.append(a[0].shape[1]), inner(*a, **k))[1]
     got = mine.generate(ids, attention_mask=mask, max_new_tokens=5)
+    del mine._incremental_logits
     assert torch.equal(got, want)
+    assert calls == [7, 1, 1, 1, 1]                            # KV cache: prompt once, then one position per token
+    assert torch.equal(mine.generate(ids, attention_mask=mask, max_new_tokens=5, use_cache=False), want)
+    # a mask that is not left-padded (pads behind the prompt) is refused: the new tokens would follow pads
+    right = torch.ones_like(ids)
+    right[1, 5:] = 0
+    with pytest.raises(ValueError, match="LEFT-padded"):
+        mine.generate(ids * right, attention_mask=right, max_new_tokens=1)
     # every row equals what it generates alone, without padding
     for r, skip in ((0, 3), (2, 5)):
         alone = mine.generate(ids[r:r + 1, skip:], max_new_tokens=5)
@@ -84,7 +95,7 @@ def test_sampling_filters_and_reproducibility():
     assert torch.allclose(freq, row.softmax(-1)[0, :4], atol=0.04)
 
 
-def run_tp_sampling(rank, world_size, port, state, ids, mask):
+def run_tp_sampling(rank, world_size, port, state, ids, mask, want):
     import torch.distributed as dist
 
     from pipegoose_b200.nn import TensorParallel
@@ -95,7 +106,9 @@ def run_tp_sampling(rank, world_size, port, state, ids, mask):
     model = TensorParallel(model, ctx).parallelize().eval()
     torch.manual_seed(100 + rank)                              # different RNG streams: the group must still agree
     sampled = model.generate(ids, max_new_tokens=6, do_sample=True, temperature=1.3, top_k=20)
-    ragged = model.generate(ids, attention_mask=mask, max_new_tokens=4)
+    ragged = model.generate(ids, attention_mask=mask, max_new_tokens=4)          # KV cache, heads sharded, pad keys masked
+    assert torch.equal(ragged, want), (ragged, want)
+    assert torch.equal(model.generate(ids, attention_mask=mask, max_new_tokens=4, use_cache=False), want)
     both = [None, None]
     dist.all_gather_object(both, (sampled.tolist(), ragged.tolist()))
     assert both[0] == both[1]
@@ -110,5 +123,5 @@ def test_tensor_parallel_ranks_agree_on_sampled_tokens_and_ragged_prompts():
     mask = torch.ones_like(ids)
     mask[1, :2] = 0
     want = model.generate(ids * mask, attention_mask=mask, max_new_tokens=4)
-    spawn(run_tp_sampling, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids * mask, mask=mask)
+    spawn(run_tp_sampling, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids * mask, mask=mask, want=want)
     assert want.shape == (2, 9)

@@ -46,8 +46,8 @@ def test_in_place_conversion_keeps_parameters_and_matches_hf():
 
 
 def test_models_the_fused_path_cannot_run_keep_the_class_swap_path():
-    hf = _hf_bloom(attention_dropout=0.1)
-    with pytest.raises(ValueError, match="dropout"):
+    hf = _hf_bloom(apply_residual_connection_post_layernorm=True)
+    with pytest.raises(ValueError, match="post_layernorm"):
         convert_hf_bloom_(hf)
 
 
@@ -145,6 +145,51 @@ def test_hidden_dropout_trains_through_the_composed_path():
     fast.zero_grad()
     ref.train()
     assert torch.allclose(fast(input_ids=ids, labels=ids).loss, _no_dropout_loss(ref, ids), atol=1e-5)
+
+
+def test_attention_dropout_trains_through_the_composed_path():
+    """``attention_dropout > 0`` (refused until round 2): eval equals the 🤗 model, training drops attention probabilities
+    (stochastic), gradients reach every parameter, p -> 0 reproduces the fused path."""
+    torch.manual_seed(0)
+    hf = _hf_bloom(attention_dropout=0.3)
+    ref = copy.deepcopy(hf)
+    fast = convert_hf_bloom_(hf)
+    assert all(blk.attention_dropout == 0.3 for blk in fast.transformer.h)
+    ids = torch.randint(0, 96, (3, 10))
+    fast.eval(), ref.eval()
+    assert torch.allclose(fast(input_ids=ids, labels=ids).loss, ref(input_ids=ids, labels=ids).loss, atol=1e-5)
+    fast.train()
+    torch.manual_seed(1)
+    a = fast(input_ids=ids, labels=ids).loss
+    torch.manual_seed(2)
+    b = fast(input_ids=ids, labels=ids).loss
+    assert not torch.allclose(a, b)
+    a.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in fast.parameters())
+    for blk in fast.transformer.h:
+        blk.attention_dropout = 1e-12
+    assert torch.allclose(fast(input_ids=ids, labels=ids).loss, _no_dropout_loss(ref, ids), atol=1e-5)
+
+
+def test_attention_dropout_semantics():
+    """The head-grouped path equals dropout applied to the full fp32 probabilities (same generator state), and the
+    expectation over masks is the attention without dropout."""
+    from pipegoose_b200.ops.attention import alibi_attention, alibi_attention_reference
+    from pipegoose_b200.ops import kernels as K
+
+    B, S, H, D = 2, 12, 4, 8
+    torch.manual_seed(0)
+    qkv = torch.randn(B * S, H * 3 * D)
+    slopes = K.alibi_slopes(H)
+    torch.manual_seed(5)
+    got = alibi_attention(qkv, slopes, B, S, H, D, dropout_p=0.25)
+    torch.manual_seed(5)
+    want = alibi_attention_reference(qkv, slopes, B, S, H, D, dropout_p=0.25)
+    assert torch.allclose(got, want, atol=1e-5)
+    clean = alibi_attention_reference(qkv, slopes, B, S, H, D)
+    assert not torch.allclose(got, clean, atol=1e-3)
+    mean = torch.stack([alibi_attention(qkv, slopes, B, S, H, D, dropout_p=0.25) for _ in range(400)]).mean(0)
+    assert (mean - clean).abs().max() < 0.25
 
 
 def _no_dropout_loss(hf_model, ids):
