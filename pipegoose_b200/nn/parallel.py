@@ -26,6 +26,11 @@ class ParallelMetadata:
     device: Optional[int] = None
     local_device: Optional[int] = None
     is_sliced: bool = False
+    # how a sliced parameter was cut (checkpoint consolidation / resharding, nn/checkpoint_convert.py): the dimension
+    # split over the tensor group and that dimension's size in the unsharded model (before any zero padding)
+    partition_dim: Optional[int] = None
+    full_size: Optional[int] = None
+    is_vocab: bool = False      # a vocabulary table / lm_head: zero-padded to a multiple of the group before the cut
 
 
 class Parallel:

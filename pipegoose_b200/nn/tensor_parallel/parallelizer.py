@@ -30,8 +30,8 @@ def get_partition(data: torch.Tensor, parallel_context: ParallelContext, dim: in
     return data.narrow(dim, rank * width, width).clone().contiguous()
 
 
-def _mark_sliced(param: nn.Parameter):
-    param.parallel_metadata = ParallelMetadata(is_sliced=True)
+def _mark_sliced(param: nn.Parameter, dim: int = None, full_size: int = None, is_vocab: bool = False):
+    param.parallel_metadata = ParallelMetadata(is_sliced=True, partition_dim=dim, full_size=full_size, is_vocab=is_vocab)
 
 
 def _is_sliced(param) -> bool:
@@ -80,11 +80,13 @@ class LinearParallelizer(ModuleParallelizer):
     def _to_column(self, module: nn.Linear) -> nn.Module:
         ctx = self.parallel_context
         if not _is_sliced(module.weight):
+            full = module.weight.shape[0]
             module.weight = nn.Parameter(get_partition(module.weight.data, ctx, dim=0), requires_grad=module.weight.requires_grad)
-            _mark_sliced(module.weight)
+            _mark_sliced(module.weight, 0, full)
         if module.bias is not None and not _is_sliced(module.bias):
+            full = module.bias.shape[0]
             module.bias = nn.Parameter(get_partition(module.bias.data, ctx, dim=0), requires_grad=module.bias.requires_grad)
-            _mark_sliced(module.bias)
+            _mark_sliced(module.bias, 0, full)
         module.__class__ = ColumnParallelLinear
         module.gather_output = True
         module.parallel_context = ctx
@@ -93,8 +95,9 @@ class LinearParallelizer(ModuleParallelizer):
     def _to_row(self, module: nn.Linear) -> nn.Module:
         ctx = self.parallel_context
         if not _is_sliced(module.weight):
+            full = module.weight.shape[1]
             module.weight = nn.Parameter(get_partition(module.weight.data, ctx, dim=1), requires_grad=module.weight.requires_grad)
-            _mark_sliced(module.weight)
+            _mark_sliced(module.weight, 1, full)
         module.__class__ = RowParallelLinear
         module.parallel_context = ctx
         return module
@@ -124,7 +127,7 @@ class EmbeddingParallelizer(ModuleParallelizer):
             if padded != vocab:  # zero-pad so that the vocabulary splits evenly
                 weight = torch.cat([weight, weight.new_zeros(padded - vocab, weight.shape[1])], dim=0)
             module.weight = nn.Parameter(get_partition(weight, ctx, dim=0), requires_grad=module.weight.requires_grad)
-            _mark_sliced(module.weight)
+            _mark_sliced(module.weight, 0, vocab, is_vocab=True)
             # modules that shared the table (a tied lm_head) must pick up the shard, not slice their own copy
             for other in self.model.modules():
                 if other is not module and getattr(other, "weight", None) is old:
@@ -182,16 +185,17 @@ class LMHeadParallelizer(ModuleParallelizer):
             if padded != vocab:
                 weight = torch.cat([weight, weight.new_zeros(padded - vocab, weight.shape[1])], dim=0)
             module.weight = nn.Parameter(get_partition(weight, ctx, dim=0), requires_grad=module.weight.requires_grad)
-            _mark_sliced(module.weight)
+            _mark_sliced(module.weight, 0, vocab, is_vocab=True)
         if module.bias is not None and not _is_sliced(module.bias):
             # heads with an output bias (BERT's ``cls.predictions.decoder``): slice it like the rows of the weight
             world = ctx.get_world_size(ParallelMode.TENSOR)
             old, bias = module.bias, module.bias.data
+            full_bias = bias.shape[0]
             padded = module.weight.shape[0] * world
             if padded != bias.shape[0]:
                 bias = torch.cat([bias, bias.new_zeros(padded - bias.shape[0])])
             module.bias = nn.Parameter(get_partition(bias, ctx, dim=0), requires_grad=old.requires_grad)
-            _mark_sliced(module.bias)
+            _mark_sliced(module.bias, 0, full_bias, is_vocab=True)
             for other in self.model.modules():  # 🤗 keeps a second handle on the same bias (``predictions.bias``)
                 if other is not module and getattr(other, "bias", None) is old:
                     other.bias = module.bias

@@ -195,7 +195,7 @@ class TensorParallel(Parallel):
 
 def _slice_param(param: nn.Parameter, ctx, dim: int) -> nn.Parameter:
     new = nn.Parameter(get_partition(param.data, ctx, dim=dim), requires_grad=param.requires_grad)
-    _mark_sliced(new)
+    _mark_sliced(new, dim, param.shape[dim])
     return new
 
 
@@ -217,7 +217,7 @@ def _parallelize_fast_bloom(model, ctx: ParallelContext):
     if padded != vocab:
         table = torch.cat([table, table.new_zeros(padded - vocab, table.shape[1])], dim=0)
     sliced = nn.Parameter(get_partition(table, ctx, dim=0))
-    _mark_sliced(sliced)
+    _mark_sliced(sliced, 0, vocab, is_vocab=True)
     sliced._pg_grad_contribs = 2  # lm_head wgrad + embedding backward
     t.word_embeddings.weight = sliced
     model.lm_head.weight = sliced

@@ -1,6 +1,8 @@
 """Checkpoint I/O (parity: reference nn/utils.py:11-50): one file per (tp_rank, pp_rank) named
 ``pytorch_model_tp_{tp}_pp_{pp}.bin``.  Only data-parallel rank 0 writes (the reference has every
-replica write the same path) and the directory is created when missing."""
+replica write the same path) and the directory is created when missing.  Next to each shard goes
+``<shard>.layout.json`` (which keys were cut along which dimension), which ``nn/checkpoint_convert.py`` uses to
+merge the shards into one state dict or to re-cut them for another tensor-parallel size, offline."""
 from __future__ import annotations
 
 import os
@@ -62,7 +64,12 @@ def save_pretrained(module: nn.Module, ckp_name: str = CHECKPOINT_WEIGHTS_NAME, 
     Path(ckp_path).mkdir(parents=True, exist_ok=True)
     if parallel_context.get_local_rank(ParallelMode.DATA) == 0:
         state = {k: v.detach().cpu() for k, v in module.state_dict().items()}
-        _atomic_save(state, _ckpt_file(ckp_path, ckp_name, parallel_context))
+        path = _ckpt_file(ckp_path, ckp_name, parallel_context)
+        _atomic_save(state, path)
+        # how every key was cut, for the offline tools (nn/checkpoint_convert.py: consolidate / reshard)
+        from pipegoose_b200.nn.checkpoint_convert import write_layout
+
+        write_layout(module, path, parallel_context)
     if parallel_context.get_world_size(ParallelMode.DATA) > 1:
         import torch.distributed as dist
 

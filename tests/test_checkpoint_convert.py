@@ -1,0 +1,161 @@
+"""Offline checkpoint conversion (nn/checkpoint_convert.py): shards written by a TP / TP x PP / expert-parallel job are
+merged into the state dict of the unsharded model, and re-cut for another tensor-parallel size."""
+import copy
+import os
+
+import pytest
+import torch
+
+from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+from pipegoose_b200.nn import PipelineParallel, TensorParallel
+from pipegoose_b200.nn.checkpoint_convert import consolidate_checkpoint, main, reshard_checkpoint
+from pipegoose_b200.nn.utils import from_pretrained, save_pretrained
+from pipegoose_b200.testing.utils import init_parallel_context, spawn
+
+VOCAB = 90      # not a multiple of 8 * tp: the vocabulary is zero-padded before it is cut
+
+
+def _model(n_layer=4):
+    torch.manual_seed(0)
+    return BloomForCausalLM(BloomConfig(vocab_size=VOCAB, hidden_size=32, n_layer=n_layer, n_head=4))
+
+
+def run_save(rank, world_size, port, tp, pp, ckp_path, state, hf):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, 1)
+    if hf:
+        from transformers import BloomConfig as HFConfig
+        from transformers import BloomForCausalLM as HFBloom
+
+        model = HFBloom(HFConfig(vocab_size=VOCAB, hidden_size=32, n_layer=4, n_head=4))
+        model.load_state_dict(state)
+        model = TensorParallel(model, ctx, sequence_parallel=False).parallelize()      # class-swap path
+    else:
+        model = _model()
+        model.load_state_dict(state)
+        model = TensorParallel(model, ctx).parallelize()
+    if pp > 1:
+        model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp,pp,hf", [(2, 1, False), (2, 2, False), (1, 2, False), (2, 1, True)])
+def test_consolidated_checkpoint_is_the_unsharded_model(tmp_path, tp, pp, hf):
+    if hf:
+        from transformers import BloomConfig as HFConfig
+        from transformers import BloomForCausalLM as HFBloom
+
+        torch.manual_seed(0)
+        full = HFBloom(HFConfig(vocab_size=VOCAB, hidden_size=32, n_layer=4, n_head=4))
+    else:
+        full = _model()
+    state = copy.deepcopy(full.state_dict())
+    ckpt = str(tmp_path / "ckpt")
+    spawn(run_save, world_size=tp * pp, tp=tp, pp=pp, ckp_path=ckpt, state=state, hf=hf)
+    assert os.path.exists(os.path.join(ckpt, "pytorch_model_tp_0_pp_0.bin.layout.json"))
+    merged = consolidate_checkpoint(ckpt, tp, pp)
+    assert set(merged) == set(state), (set(merged) ^ set(state))
+    for k, v in state.items():
+        assert merged[k].shape == v.shape and torch.equal(merged[k], v), k
+    # the merged dict loads into a fresh unsharded model (strict)
+    fresh = copy.deepcopy(full)
+    with torch.no_grad():
+        for p in fresh.parameters():
+            p.zero_()
+    fresh.load_state_dict(merged)
+    # command line: python -m pipegoose_b200.nn.checkpoint_convert ckpt out.bin --tp .. --pp ..
+    out = str(tmp_path / "out" / "full.bin")
+    main([ckpt, out, "--tp", str(tp), "--pp", str(pp)])
+    again = torch.load(out)
+    assert all(torch.equal(again[k], v) for k, v in state.items())
+
+
+def run_load_resharded(rank, world_size, port, tp, ckp_path, state):
+    ctx = init_parallel_context(rank, world_size, port, tp, 1, 1)
+    want = TensorParallel(_model(), ctx)
+    want.module.load_state_dict(state)
+    want = want.parallelize()
+    got = _model()
+    with torch.no_grad():
+        for p in got.parameters():
+            p.normal_()
+    got = TensorParallel(got, ctx).parallelize()
+    from_pretrained(got, ckp_path=ckp_path, parallel_context=ctx)
+    for (k, a), (_, b) in zip(got.state_dict().items(), want.state_dict().items()):
+        assert torch.equal(a, b), k
+    ctx.destroy()
+
+
+def test_reshard_tp2_pp2_checkpoint_for_tp4(tmp_path):
+    state = copy.deepcopy(_model().state_dict())
+    src, dst = str(tmp_path / "src"), str(tmp_path / "dst")
+    spawn(run_save, world_size=4, tp=2, pp=2, ckp_path=src, state=state, hf=False)
+    reshard_checkpoint(src, dst, 2, 2, 4)
+    spawn(run_load_resharded, world_size=4, tp=4, ckp_path=dst, state=state)
+    # and back to one file set of a single rank
+    reshard_checkpoint(dst, str(tmp_path / "one"), 4, 1, 1)
+    one = torch.load(str(tmp_path / "one" / "pytorch_model_tp_0_pp_0.bin"))
+    assert all(torch.equal(one[k], v) for k, v in state.items())
+
+
+def test_stale_or_incomplete_shards_are_refused(tmp_path):
+    state = copy.deepcopy(_model().state_dict())
+    ckpt = str(tmp_path / "ckpt")
+    spawn(run_save, world_size=2, tp=2, pp=1, ckp_path=ckpt, state=state, hf=False)
+    with pytest.raises(FileNotFoundError):
+        consolidate_checkpoint(ckpt, 4, 1)
+    with pytest.raises(ValueError, match="written for tp=2"):
+        consolidate_checkpoint(ckpt, 1, 1)
+    shard = torch.load(os.path.join(ckpt, "pytorch_model_tp_1_pp_0.bin"))
+    shard["transformer.ln_f.weight"] += 1.0                     # a replicated parameter that differs between ranks
+    torch.save(shard, os.path.join(ckpt, "pytorch_model_tp_1_pp_0.bin"))
+    with pytest.raises(ValueError, match="differs between tensor-parallel ranks"):
+        consolidate_checkpoint(ckpt, 2, 1)
+    # without the layout files the name table of TensorParallelMapping decides (vocab_size cuts the padding off)
+    for f in os.listdir(ckpt):
+        if f.endswith(".layout.json"):
+            os.remove(os.path.join(ckpt, f))
+    merged = consolidate_checkpoint(ckpt, 2, 1, vocab_size=VOCAB, check_replicas=False)
+    for k, v in state.items():
+        assert merged[k].shape == v.shape, k
+        if k != "transformer.ln_f.weight":
+            assert torch.equal(merged[k], v), k
+
+
+def _moe(ctx, world):
+    """Bloom with 4 distinct experts in layers 0 and 2: global expert e of layer li is seeded by (li, e)."""
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.nn.expert_parallel import ExpertParallel, Top2Router
+
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=VOCAB, hidden_size=32, n_layer=3, n_head=4))
+    model = ExpertParallel(model, 4, mapping=[0, 2], router=Top2Router(None, 4, 32), parallel_context=ctx, fused=False).parallelize()
+    tp_rank = ctx.get_local_rank(ParallelMode.TENSOR)
+    for li in (0, 2):
+        layer = model.transformer.h[li].mlp
+        for i, e in enumerate(layer.experts):
+            g = torch.Generator().manual_seed(50 + 10 * li + tp_rank * len(layer.experts) + i)
+            for p in e.parameters():
+                p.data = torch.randn(p.shape, generator=g) * 0.3
+    return TensorParallel(model, ctx).parallelize()
+
+
+def run_moe_save(rank, world_size, port, ckp_path):
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1)
+    model = _moe(ctx, world_size)
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    ctx.destroy()
+
+
+def test_expert_parallel_checkpoint_renumbers_the_experts(tmp_path):
+    """Experts spread over the tensor group are saved under LOCAL indices; the merged dict has them under their global
+    indices — the state dict of the same model built on one rank."""
+    two, one = str(tmp_path / "two"), str(tmp_path / "one")
+    spawn(run_moe_save, world_size=2, ckp_path=two)
+    spawn(run_moe_save, world_size=1, ckp_path=one)
+    merged = consolidate_checkpoint(two, 2, 1)
+    want = torch.load(os.path.join(one, "pytorch_model_tp_0_pp_0.bin"))
+    assert set(merged) == set(want), set(merged) ^ set(want)
+    assert any(".experts.3." in k for k in merged)
+    for k, v in want.items():
+        assert torch.equal(merged[k], v), k
