@@ -230,7 +230,8 @@ def run_ckpt_layout(rank, world_size, port, ckp_dir):
     assert kept == ["step_00000004", "step_00000006"], kept                     # the two newest complete checkpoints
     assert open(os.path.join(ckp_dir, "latest")).read() == "step_00000006"
     files = sorted(os.listdir(os.path.join(ckp_dir, "step_00000006")))
-    assert files == ["optimizer_tp_0_pp_0_dp_0.bin", "optimizer_tp_0_pp_0_dp_1.bin", "pytorch_model_tp_0_pp_0.bin"], files
+    assert files == ["optimizer_tp_0_pp_0_dp_0.bin", "optimizer_tp_0_pp_0_dp_1.bin", "pytorch_model_tp_0_pp_0.bin",
+                         "pytorch_model_tp_0_pp_0.bin.layout.json"], files
     assert not [f for f in os.listdir(ckp_dir) if ".tmp." in f or f.startswith(".latest")]
     torch.distributed.barrier()   # every rank has looked at the directory before anyone adds to it
     # a half-written newer directory (crash before "latest" moved) is ignored by resume
