@@ -21,7 +21,10 @@ skip_in_github_actions = pytest.mark.skipif(os.getenv("GITHUB_ACTIONS") == "true
 skip_if_no_cuda = pytest.mark.skipif(not torch.cuda.is_available(), reason="Test requires CUDA")
 
 
-def find_free_port(min_port: int = 2000, max_port: int = 65000) -> int:
+def find_free_port(min_port: int = 10000, max_port: int = 32000) -> int:
+    """A port nobody listens on right now.  The default range stays BELOW Linux's ephemeral range (32768-60999): the
+    kernel hands ephemeral ports to outgoing connections (every gloo pair opens some), and one of those can take a port
+    between this probe and the rendezvous server's ``bind`` (seen as EADDRINUSE in a busy test run)."""
     while True:
         port = random.randint(min_port, max_port)
         try:
@@ -74,13 +77,19 @@ def _start_method() -> str:
 
 def spawn(func: Callable, world_size: int = 1, **kwargs):
     """Run ``func(rank, world_size, port, **kwargs)`` in ``world_size`` fresh processes."""
-    if kwargs.get("port") is None:
-        kwargs.pop("port", None)
-        port = find_free_port()
-    else:
-        port = kwargs.pop("port")
-    mp.start_processes(_entry, args=(world_size, port, func, kwargs), nprocs=world_size, join=True,
-                       start_method=_start_method())
+    pinned = kwargs.get("port") is not None
+    port = kwargs.pop("port", None)
+    for attempt in range(3):
+        if not pinned:
+            port = find_free_port()
+        try:
+            mp.start_processes(_entry, args=(world_size, port, func, kwargs), nprocs=world_size, join=True,
+                               start_method=_start_method())
+            return
+        except Exception as e:
+            # somebody else bound the port between the probe and the rendezvous: nothing ran yet, try another port
+            if pinned or attempt == 2 or not ("EADDRINUSE" in str(e) or "address already in use" in str(e)):
+                raise
 
 
 def init_parallel_context(rank, world_size, port, tensor_parallel_size, pipeline_parallel_size, data_parallel_size,

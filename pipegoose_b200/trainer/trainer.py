@@ -239,6 +239,9 @@ class Trainer:
         first_epoch = resume["epoch"] if resume is not None else 0
         for epoch in range(first_epoch, self.num_epochs):
             self.state.epoch = epoch
+            sampler = getattr(self.train_loader, "sampler", None)
+            if hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)     # DistributedSampler: another permutation every epoch, the same on resume
             self._call("on_epoch_start")
             skip_here = 0
             if resume is not None and epoch == first_epoch:
