@@ -110,8 +110,27 @@ def save_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
         return x
 
     blob = {"optimizer": to_cpu(sd), "step": int(step), "layout": _layout(parallel_context),
-            "rng": capture_rng_state(), "extra": extra or {}}
+            "rng": capture_rng_state(), "extra": extra or {}, "flat_index": _flat_index(optim)}
     _atomic_save(blob, _optim_file(ckp_path, parallel_context))
+
+
+def _fused_adam_of(optim):
+    """The :class:`FusedAdam` behind ``optim`` (itself, or wrapped by a ``DistributedOptimizer``), else None."""
+    from pipegoose_b200.optim.fused_adam import FusedAdam
+
+    inner = getattr(optim, "optim", optim)
+    return inner if isinstance(inner, FusedAdam) else None
+
+
+def _flat_index(optim):
+    """``[(offset, numel)]`` of every parameter in the optimizer's flat buffer, in ``param_groups`` order (None for
+    optimizers without a flat state).  The flat layout depends on the data-parallel size (region padding), the ORDER of
+    the parameters does not: this table is what lets a checkpoint be re-cut for another number of replicas."""
+    fa = _fused_adam_of(optim)
+    if fa is None:
+        return None
+    flat = fa.ensure_flat()
+    return [tuple(int(x) for x in flat.param_range(p)) for g in fa.param_groups for p in g["params"]]
 
 
 def capture_rng_state() -> dict:
@@ -150,11 +169,18 @@ def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
     generator states, when ``restore_rng=False`` leaves restoring them to the caller)."""
     path = _optim_file(ckp_path, parallel_context)
     if not os.path.exists(path):
+        elastic = _load_for_another_dp_size(optim, ckp_path, parallel_context, restore_rng)
+        if elastic is not None:
+            return elastic
         raise ValueError(f"optimizer checkpoint {path} does not exist")
     blob = torch.load(path, map_location="cpu", weights_only=False)
     if blob["layout"] != _layout(parallel_context):
+        elastic = _load_for_another_dp_size(optim, ckp_path, parallel_context, restore_rng)
+        if elastic is not None:
+            return elastic
         raise ValueError(f"checkpoint was written for layout {blob['layout']}, this job runs {_layout(parallel_context)}: "
-                         "optimizer shards are tied to the parallel layout")
+                         "optimizer shards are tied to the parallel layout (only the data-parallel size of a FusedAdam / "
+                         "ZeRO-1 checkpoint can change)")
     optim.load_state_dict(blob["optimizer"])
     meta = {"step": blob["step"], "extra": blob["extra"]}
     if restore_rng:
@@ -162,3 +188,88 @@ def load_training_state(optim, ckp_path: str = CHECKPOINT_PATH_NAME, parallel_co
     else:
         meta["rng"] = blob["rng"]   # the caller restores it (the Trainer: after it replayed the consumed batches)
     return meta
+
+
+# ------------------------------------------------------------------------------------------------
+# elastic resume: a ZeRO-1 (FusedAdam) checkpoint written by ``dp_old`` replicas, loaded by ``dp_new``
+# ------------------------------------------------------------------------------------------------
+def _load_for_another_dp_size(optim, ckp_path: str, parallel_context: ParallelContext, restore_rng: bool):
+    """The checkpoint has no shard for this rank's ``(tp, pp, dp)`` coordinates, or was written for another layout.  If
+    only the DATA-parallel size differs and the optimizer is a (ZeRO-1) ``FusedAdam``, every rank reads all old replicas'
+    shards of its ``(tp, pp)`` coordinates and cuts its own slices out of them; returns the metadata, or None when this
+    does not apply."""
+    import glob
+    import re
+
+    from pipegoose_b200.constants import CHECKPOINT_OPTIM_NAME
+
+    if _fused_adam_of(optim) is None:
+        return None
+    tp_rank = parallel_context.get_local_rank(ParallelMode.TENSOR)
+    pp_rank = parallel_context.get_local_rank(ParallelMode.PIPELINE)
+    pattern = os.path.join(ckp_path, CHECKPOINT_OPTIM_NAME.format(tp_rank, pp_rank, "*"))
+    found = {}
+    for f in glob.glob(pattern):
+        m = re.search(r"_dp_(\d+)\.bin$", f)
+        if m:
+            found[int(m.group(1))] = f
+    if not found:
+        return None
+    first = torch.load(found[min(found)], map_location="cpu", weights_only=False)
+    old, now = first["layout"], _layout(parallel_context)
+    if (old["tp"], old["pp"]) != (now["tp"], now["pp"]) or old["dp"] == now["dp"]:
+        return None
+    if sorted(found) != list(range(old["dp"])):
+        raise ValueError(f"{ckp_path}: the checkpoint was written by {old['dp']} replicas, found optimizer shards of "
+                         f"replicas {sorted(found)} for tp={tp_rank} pp={pp_rank}")
+    if first.get("flat_index") is None:
+        raise ValueError("this checkpoint predates the per-parameter index that re-cutting for another data-parallel size "
+                         "needs (save it again with this version at the old size)")
+    blobs = [first] + [torch.load(found[d], map_location="cpu", weights_only=False) for d in range(1, old["dp"])]
+    old_index = [tuple(x) for x in first["flat_index"]]
+
+    def provider(new_segments, new_index, new_numel):
+        return reshard_fused_state([b["optimizer"] for b in blobs], old_index, new_segments, new_index, new_numel)
+
+    load = getattr(optim, "load_resharded_state", None)
+    if load is not None:
+        load(provider)                       # DistributedOptimizer: now, or when its ZeRO-1 slices are laid out
+    else:
+        fa = _fused_adam_of(optim)
+        fa._lazy_init()
+        fa.load_state_dict(provider(list(fa._segments), _flat_index(optim), fa.flat.numel))
+    mine = blobs[parallel_context.get_local_rank(ParallelMode.DATA) % old["dp"]]
+    meta = {"step": mine["step"], "extra": mine["extra"], "resharded_from_dp": old["dp"]}
+    if restore_rng:
+        restore_rng_state(mine["rng"])       # (a replica's random stream: the closest there is with another replica count)
+    else:
+        meta["rng"] = mine["rng"]
+    return meta
+
+
+def reshard_fused_state(old_states: list, old_index: list, new_segments: list, new_index: list, new_numel: int) -> dict:
+    """Cut a FusedAdam state dict for ``new_segments`` (ranges of the NEW flat buffer) out of the state dicts of all old
+    replicas.  Parameters are matched by their position in ``param_groups`` (``*_index[i] = (offset, numel)`` in the
+    old / new flat buffer); every element of every parameter must be owned by exactly one old replica."""
+    assert len(old_index) == len(new_index), "the optimizers hold different numbers of parameters"
+    for i, ((_, a), (_, b)) in enumerate(zip(old_index, new_index)):
+        if a != b:
+            raise ValueError(f"parameter {i} has {a} elements in the checkpoint and {b} in this model")
+    old_numel = max(e for sd in old_states for _, e in sd["segments"])
+    out = {"step": old_states[0]["step"], "segments": [tuple(x) for x in new_segments],
+           "param_groups": old_states[0].get("param_groups", [])}
+    for key in ("master", "exp_avg", "exp_avg_sq"):
+        full = torch.full((old_numel,), float("nan"), dtype=torch.float32)
+        for sd in old_states:
+            off = 0
+            for s, e in sd["segments"]:
+                full[s:e] = sd[key][off:off + e - s].float()
+                off += e - s
+        new_full = torch.zeros(new_numel, dtype=torch.float32)
+        for (o_old, n), (o_new, _) in zip(old_index, new_index):
+            piece = full[o_old:o_old + n]
+            if torch.isnan(piece).any():
+                raise ValueError("the old replicas' slices do not cover every parameter (incomplete checkpoint?)")
+            new_full[o_new:o_new + n] = piece
+        out[key] = torch.cat([new_full[s:e] for s, e in new_segments]) if new_segments else new_full[:0]
+    return out

@@ -103,6 +103,10 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             optim.set_bucket_shards(self._reducer.zero_bucket_numel, self.dp_rank, self.dp, head=head,
                                     inline_from=head if inline else None)
         self._zero_ready = True
+        provider = getattr(self, "_pending_provider", None)
+        if provider is not None:
+            self._pending_provider = None
+            self._apply_resharded(provider)
         pending = getattr(self, "_pending_state", None)
         if pending is not None:
             self._pending_state = None
@@ -152,6 +156,23 @@ class DistributedOptimizer(BaseDistributedOptimizer):
             self._pending_state = (state_dict, args, kwargs)
             return
         self.optim.load_state_dict(state_dict, *args, **kwargs)
+
+    def load_resharded_state(self, provider):
+        """Elastic resume (nn/utils.py::load_training_state with another data-parallel size): ``provider(segments,
+        flat_index, numel)`` builds this rank's state from all old replicas' shards once the ZeRO-1 slices of THIS job
+        are laid out — now if they are, else with the first ``zero_grad()`` / ``step()``."""
+        assert self._fused, "only the fused (FusedAdam) ZeRO-1 state can be re-cut for another data-parallel size"
+        if not self._zero_ready and self.dp > 1:
+            self._pending_provider = provider
+            return
+        self._apply_resharded(provider)
+
+    def _apply_resharded(self, provider):
+        from pipegoose_b200.nn.utils import _flat_index
+
+        optim = self.optim
+        optim._lazy_init()
+        optim.load_state_dict(provider(list(optim._segments), _flat_index(optim), optim.flat.numel))
 
     def state_dict(self, *args, **kwargs):
         return self.optim.state_dict(*args, **kwargs)
