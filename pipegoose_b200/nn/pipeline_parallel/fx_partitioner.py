@@ -7,8 +7,9 @@ shards as a tuple.  The pipeline engine here moves ONE activation tensor per mic
 (static shapes, one NCCL send/recv pair per boundary), so this partitioner looks for the cuts a pipeline wants anyway:
 
 * the model is traced with ``torch.fx`` (``symbolic_trace`` or a tracer / ``GraphModule`` the caller supplies);
-* every node is classified as *input-derived* (a forward argument, a buffer, or a parameter-free function of those:
-  masks, position ids, sequence lengths, ALiBi slopes, ...) or as an *activation* (anything downstream of a parameter);
+* every node is classified as *input-derived* (a forward argument, a buffer, or a parameter-free DETERMINISTIC function
+  of those: masks, position ids, sequence lengths, ALiBi slopes, ...) or as an *activation* (anything downstream of a
+  parameter, and anything drawn from a random generator — dropout, ``torch.rand`` — which must be computed once);
 * a cut between two nodes is legal when exactly one activation is live across it — the residual stream at a block
   boundary, the hidden state between two layers of an MLP or a CNN.  Input-derived values never cross a cut: every
   stage that needs one re-computes it from the micro-batch's inputs, which every stage holds (no transfer at all).
@@ -69,6 +70,32 @@ def _arg_nodes(node: fx.Node) -> List[fx.Node]:
     return list(node.all_input_nodes)
 
 
+# Values drawn from a random generator must be computed ONCE: a stage that re-computed them "from the inputs" would
+# draw other numbers than its neighbour (a random mask, dropout on position features).  They count as activations.
+_RANDOM_FUNCTIONS = {torch.rand, torch.randn, torch.randint, torch.rand_like, torch.randn_like, torch.randint_like,
+                     torch.randperm, torch.bernoulli, torch.multinomial, torch.normal, torch.poisson, torch.dropout,
+                     torch.nn.functional.dropout, torch.nn.functional.dropout1d, torch.nn.functional.dropout2d,
+                     torch.nn.functional.dropout3d, torch.nn.functional.alpha_dropout,
+                     torch.nn.functional.feature_alpha_dropout, torch.nn.functional.gumbel_softmax,
+                     torch.nn.functional.rrelu}
+_RANDOM_METHODS = {"bernoulli", "bernoulli_", "normal_", "uniform_", "random_", "exponential_", "geometric_",
+                   "cauchy_", "log_normal_", "multinomial", "dropout"}
+_RANDOM_MODULES = (nn.Dropout, nn.Dropout1d, nn.Dropout2d, nn.Dropout3d, nn.AlphaDropout, nn.FeatureAlphaDropout, nn.RReLU)
+
+
+def _draws_random_numbers(gm: fx.GraphModule, node: fx.Node) -> bool:
+    if node.op == "call_function":
+        return node.target in _RANDOM_FUNCTIONS
+    if node.op == "call_method":
+        return node.target in _RANDOM_METHODS
+    if node.op == "call_module":
+        obj = gm
+        for part in node.target.split("."):
+            obj = getattr(obj, part)
+        return isinstance(obj, _RANDOM_MODULES)
+    return False
+
+
 class GraphStage(nn.Module):
     """One shard of a traced model.  ``forward(x, **inputs)`` (see the module docstring).
 
@@ -119,7 +146,7 @@ class GraphStage(nn.Module):
         sizes = [int(torch.Size(shape).numel()) for shape, _ in meta]
         return [part.view(shape).to(dtype) for part, (shape, dtype) in zip(flat.split(sizes), meta)]
 
-    def forward(self, x, **inputs):
+    def forward(self, x, /, **inputs):     # (positional-only: a traced model may call ITS first argument ``x`` too)
         if self.multi_in:
             values = list(x) if isinstance(x, (tuple, list)) else self.unpack(x)
             kwargs = dict(zip(self.carried_names, values))
@@ -217,6 +244,8 @@ class GraphPartitioner(BasePartitioner):
             elif n.op == "get_attr":
                 if not isinstance(self._fetch(gm, n.target), nn.Parameter):
                     free.add(n)
+            elif _draws_random_numbers(gm, n):
+                continue                      # computed once, carried like an activation
             elif n.op in ("call_function", "call_method"):
                 if all(d in free for d in _arg_nodes(n)):
                     free.add(n)

@@ -329,3 +329,47 @@ def test_pipeline_engine_moves_packed_boundaries(pp):
     loss.backward()
     spawn(run_unet_pipeline, world_size=pp, pp=pp, state=copy.deepcopy(model.state_dict()), x=x, target=target,
           ref_loss=loss.detach(), ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
+
+
+class _RandomMaskModel(nn.Module):
+    """A random keep-mask drawn from the inputs alone (no parameter upstream) and used by every block: a stage must not
+    draw its own."""
+
+    def __init__(self, d=8):
+        super().__init__()
+        self.fc = nn.ModuleList([nn.Linear(d, d) for _ in range(4)])
+        self.drop = nn.Dropout(0.5)
+
+    def forward(self, x):
+        keep = self.drop(torch.ones_like(x))                    # module without parameters, input-derived argument
+        noise = torch.rand_like(x)                              # function of the input alone
+        h = x
+        for fc in self.fc:
+            h = fc(h) * keep + noise
+        return h
+
+
+def test_random_values_are_computed_once_and_carried():
+    torch.manual_seed(0)
+    net = _RandomMaskModel().train()
+    x = torch.randn(3, 8)
+    def where(stages, what):
+        return [any(n.target == what for n in s.graph_module.graph.nodes) for s in stages]
+
+    # single-activation cuts: the only one is right behind the mask (before the noise is drawn) — everything else has
+    # mask + noise + hidden state live.  Three stages cannot be cut that way.
+    two = GraphPartitioner(net, None, n_partitions=2).split()
+    assert where(two, "drop") == [True, False] and where(two, torch.rand_like) == [False, True]
+    with pytest.raises(NoLegalCut):
+        GraphPartitioner(net, None, n_partitions=3).split()
+    # with room for three tensors the mask and the noise travel with the hidden state instead of being drawn again
+    three = GraphPartitioner(net, None, n_partitions=3, max_boundary_tensors=3).split()
+    assert sum(where(three, "drop")) == 1 and sum(where(three, torch.rand_like)) == 1
+    assert all(sum(p.numel() for p in s.parameters()) > 0 for s in three)
+    for stages in (two, three):
+        for s in stages:
+            s.pack_outputs = False
+        torch.manual_seed(7)
+        want = net(x)
+        torch.manual_seed(7)
+        assert torch.allclose(_chain(stages, x, x=x), want)      # (later stages read the input by name, as in the engine)
