@@ -373,3 +373,46 @@ def test_random_values_are_computed_once_and_carried():
         want = net(x)
         torch.manual_seed(7)
         assert torch.allclose(_chain(stages, x, x=x), want)      # (later stages read the input by name, as in the engine)
+
+
+class _InputSkipModel(nn.Module):
+    """``forward(self, x, labels)``: the raw input is added again at the end (every stage can read it from the micro-batch),
+    and the argument is called ``x`` like the stages' own carried value."""
+
+    def __init__(self, d=8):
+        super().__init__()
+        self.fc = nn.ModuleList([nn.Linear(d, d) for _ in range(4)])
+
+    def forward(self, x, labels=None):
+        h = x
+        for fc in self.fc:
+            h = torch.tanh(fc(h))
+        out = h + x
+        if labels is not None:
+            return ((out - labels) ** 2).mean()
+        return out
+
+
+def run_input_skip(rank, world_size, port, state, x, y, ref_loss, ref_grads):
+    ctx = init_parallel_context(rank, world_size, port, 1, world_size, 1)
+    model = _InputSkipModel()
+    model.load_state_dict(state)
+    names = {id(p): n for n, p in model.named_parameters()}
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx,
+                             partitioner=lambda m, c: GraphPartitioner(m, c)).parallelize()
+    out = model(x, labels=y)
+    assert torch.allclose(out.loss, ref_loss, atol=1e-6)
+    out.loss.backward()
+    for p in model._pg_pipeline_stage.parameters():
+        assert torch.allclose(p.grad, ref_grads[names[id(p)]], atol=1e-6), names[id(p)]
+    ctx.destroy()
+
+
+def test_engine_feeds_the_raw_input_to_later_stages_by_name():
+    torch.manual_seed(0)
+    model = _InputSkipModel()
+    x, y = torch.randn(4, 8), torch.randn(4, 8)
+    loss = torch.stack([model(a, b) for a, b in zip(x.chunk(2), y.chunk(2))]).mean()
+    loss.backward()
+    spawn(run_input_skip, world_size=2, state=copy.deepcopy(model.state_dict()), x=x, y=y, ref_loss=loss.detach(),
+          ref_grads={n: p.grad.clone() for n, p in model.named_parameters()})
