@@ -93,3 +93,25 @@ def test_parallel_layouts_follow_single_process_training(tp, pp, dp):
         ref_losses.append(total)
     assert ref_losses[-1] < ref_losses[0]
     spawn(run_layout, world_size=tp * pp * dp, tp=tp, pp=pp, dp=dp, state=state, ids=ids, ref_losses=ref_losses)
+
+
+def test_gpt2_generate_left_padded_prompts_match_transformers():
+    """Learned absolute positions count from each row's first real token (KV-cache path: ``_learned_positions``; training
+    forward: rows rotated to right padding)."""
+    from transformers import GPT2Config as HFConfig
+    from transformers import GPT2LMHeadModel as HFGPT2
+
+    from pipegoose_b200.models.gpt2 import GPT2LMHeadModel
+
+    torch.manual_seed(0)
+    hf = HFGPT2(HFConfig(vocab_size=96, n_embd=32, n_layer=2, n_head=4, n_positions=64, resid_pdrop=0.0, embd_pdrop=0.0,
+                         attn_pdrop=0.0)).eval()
+    mine = GPT2LMHeadModel.from_hf(hf).eval()
+    ids = torch.randint(1, 96, (3, 7), generator=torch.Generator().manual_seed(1))
+    mask = torch.ones_like(ids)
+    mask[0, :3] = 0
+    mask[2, :5] = 0
+    ids = ids * mask
+    want = hf.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, do_sample=False, pad_token_id=0)
+    for use_cache in (True, False):
+        assert torch.equal(mine.generate(ids, attention_mask=mask, max_new_tokens=5, use_cache=use_cache), want)
