@@ -119,3 +119,55 @@ def test_trainer_sets_the_sampler_epoch():
     data = Loader({"input_ids": torch.randint(0, 64, (2, 8))} for _ in range(2))
     Trainer(model, data, optim=FusedAdam(model.parameters(), lr=1e-2), num_epochs=3).fit()
     assert epochs == [0, 1, 2]
+
+
+def run_resume_with_sampler(rank, world_size, port, path, ckp_dir):
+    """Interrupted in the middle of the SECOND epoch of a shuffled, sharded loader; the resumed run must see the same
+    batches in the same order as the uninterrupted one (sampler epoch + position restored)."""
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import DataParallel, TensorParallel
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+    from pipegoose_b200.trainer import Callback, Trainer
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 2)
+    ds = TokenFileDataset(path, seq_len=8)                          # 24 sequences -> 12 per replica -> 6 batches per epoch
+
+    class Seen(Callback):
+        def __init__(self):
+            self.batches = []
+
+    def build(**kw):
+        torch.manual_seed(0)
+        model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=1, n_head=4))
+        model = DataParallel(TensorParallel(model, ctx).parallelize(), ctx).parallelize()
+        optim = DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2), ctx)
+        loader = build_dataloader(ds, ctx, batch_size=2, shuffle=True)
+        trainer = Trainer(model, loader, optim=optim, parallel_context=ctx, num_epochs=3, **kw)
+        seen = []
+        inner = trainer.train_step
+
+        def spy(batch):
+            seen.append(batch["input_ids"].clone())
+            return inner(batch)
+
+        trainer.train_step = spy
+        return model, trainer, seen
+
+    model_a, trainer_a, seen_a = build()
+    assert trainer_a.fit().step == 18
+    model_b, trainer_b, seen_b = build(checkpoint_dir=ckp_dir, checkpoint_every=3, max_steps=9)    # stops in epoch 1
+    assert trainer_b.fit().step == 9
+    model_c, trainer_c, seen_c = build(checkpoint_dir=ckp_dir, resume=True)
+    assert trainer_c.fit().step == 18
+    assert len(seen_b) == 9 and len(seen_c) == 9
+    for got, want in zip(seen_b + seen_c, seen_a):
+        assert torch.equal(got, want)
+    for (n, a), (_, c) in zip(model_a.named_parameters(), model_c.named_parameters()):
+        assert torch.allclose(a, c, atol=1e-6), n
+    ctx.destroy()
+
+
+def test_trainer_resumes_a_shuffled_sharded_loader_mid_epoch(tmp_path):
+    path = str(tmp_path / "tokens.bin")
+    write_token_file(path, torch.randint(0, 96, (24 * 8,), generator=torch.Generator().manual_seed(3)))
+    spawn(run_resume_with_sampler, world_size=2, path=path, ckp_dir=str(tmp_path / "run"))
