@@ -154,14 +154,36 @@ class ParallelContext:
             kwargs = {}
             if backend == "nccl" and torch.cuda.is_available():
                 kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
-            dist.init_process_group(
-                rank=rank, world_size=world_size, backend=backend, init_method=f"tcp://{host}:{port}", **kwargs
-            )
+            restart = os.environ.get("TORCHELASTIC_RESTART_COUNT", "0")
+            if restart not in ("", "0"):
+                # A relaunch by ``torchrun --max-restarts``: the workers of every attempt talk to the SAME key-value store
+                # (the agent's), which still holds the previous attempt's keys — the dead ranks' gloo addresses, group
+                # barriers.  Stock ``init_process_group`` + ``new_group`` then connects to addresses nobody listens on
+                # any more ("Gloo connectFullMesh failed ... Connection refused").  Give every attempt its own key space.
+                kwargs["store"] = dist.PrefixStore(f"pipegoose_b200/attempt_{restart}", self._rendezvous_store(host, port, rank, world_size))
+            else:
+                kwargs["init_method"] = f"tcp://{host}:{port}"
+            dist.init_process_group(rank=rank, world_size=world_size, backend=backend, **kwargs)
             self._owns_default_group = True
         ranks = list(range(world_size))
         group = dist.new_group(ranks=ranks)
         self._register_dist(rank, world_size, group, ranks_in_group=ranks, parallel_mode=ParallelMode.GLOBAL)
         self.add_global_rank(ParallelMode.GLOBAL, rank)
+
+    @staticmethod
+    def _rendezvous_store(host: str, port: int, rank: int, world_size: int):
+        """The store ``tcp://host:port`` would use (the launcher agent's when there is one, else hosted by rank 0)."""
+        from datetime import timedelta
+
+        timeout = timedelta(seconds=1800)
+        try:
+            from torch.distributed.rendezvous import _create_c10d_store
+
+            return _create_c10d_store(host, port, rank, world_size, timeout)
+        except ImportError:  # pragma: no cover - private helper moved: same logic with the public class
+            agent = os.environ.get("TORCHELASTIC_USE_AGENT_STORE") == "True"
+            return dist.TCPStore(host, port, world_size, is_master=(rank == 0 and not agent), timeout=timeout,
+                                 multi_tenant=True)
 
     def init_parallel_groups(self):
         """Create the TENSOR / PIPELINE / DATA / EXPERT_DATA (+ EXPERT) groups."""

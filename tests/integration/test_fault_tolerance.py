@@ -1,0 +1,39 @@
+"""Failure recovery end to end (the reference has neither): a replica dies mid-run without any
+clean-up, ``torchrun --max-restarts`` relaunches the job, ``Trainer(resume=True)`` continues from the last complete
+checkpoint, and the final parameters equal those of a run that never crashed.
+
+The relaunch only works because ``ParallelContext`` gives every restart attempt its own key space in the launcher's
+store (distributed/parallel_context.py::init_global_dist): stock ``init_process_group("gloo")`` + ``new_group`` reads the
+dead ranks' addresses of the previous attempt and fails with "connectFullMesh ... Connection refused"."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _launch(workdir, mode, max_restarts):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1", "--nnodes=1",
+           "--nproc-per-node=2", f"--max-restarts={max_restarts}", "--monitor-interval", "0.5",
+           os.path.join(HERE, "crashy_job.py"), workdir, mode]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+
+
+@pytest.mark.timeout(900)
+def test_job_survives_a_dead_replica(tmp_path):
+    workdir = str(tmp_path)
+    clean = _launch(workdir, "clean", 0)
+    assert clean.returncode == 0, clean.stderr[-3000:]
+    crashed = _launch(workdir, "crash", 1)
+    assert crashed.returncode == 0, crashed.stderr[-3000:]
+    assert os.path.exists(os.path.join(workdir, "crashed_once"))
+    want = json.load(open(os.path.join(workdir, "result_clean.json")))
+    got = json.load(open(os.path.join(workdir, "result_crash.json")))
+    assert got["restarts"] == 1 and want["restarts"] == 0
+    assert got["step"] == want["step"] == 8
+    assert want["started_at"] == 0 and got["started_at"] == 3               # checkpoints at 3 and 6; the crash came in 4
+    assert got["loss"] == pytest.approx(want["loss"], abs=1e-5)
+    assert got["checksum"] == pytest.approx(want["checksum"], abs=1e-4)
