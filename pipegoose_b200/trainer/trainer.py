@@ -138,6 +138,11 @@ class Trainer:
     # ------------------------------------------------------------------ checkpoints
     # layout:  <checkpoint_dir>/step_00000500/{pytorch_model_tp_*_pp_*.bin, optimizer_tp_*_pp_*_dp_*.bin}
     #          <checkpoint_dir>/latest        <- name of the newest COMPLETE step directory (written last, atomically)
+    def _tick(self):
+        wd = getattr(self, "_watchdog", None)
+        if wd is not None:
+            wd.tick()
+
     def _barrier(self):
         import torch.distributed as dist
 
@@ -171,6 +176,7 @@ class Trainer:
             for stale in done[:-self.keep_checkpoints]:
                 shutil.rmtree(os.path.join(self.checkpoint_dir, stale), ignore_errors=True)
         self._barrier()
+        self._tick()
         self._log(f"checkpoint written at step {self.state.step} -> {path}")
 
     def _latest_checkpoint(self) -> Optional[str]:
@@ -219,11 +225,16 @@ class Trainer:
         if self.watchdog_timeout_s is not None and self.parallel_context is not None:
             from pipegoose_b200.utils.watchdog import RankWatchdog
 
-            watchdog = RankWatchdog(self.parallel_context, timeout_s=self.watchdog_timeout_s).start()
+            # dead peers are noticed through their heartbeat, a wedged main thread (this one, or a peer's, which leaves
+            # this one blocked in a collective) through the progress ticks below
+            watchdog = RankWatchdog(self.parallel_context, timeout_s=self.watchdog_timeout_s,
+                                    stall_timeout_s=self.watchdog_timeout_s).start()
+        self._watchdog = watchdog
         self._call("on_fit_start")
         try:
             self.train()
         finally:
+            self._watchdog = None
             if watchdog is not None:
                 watchdog.stop()
         self._call("on_fit_end")
@@ -260,12 +271,14 @@ class Trainer:
                 self._batches_in_epoch += 1
                 if self._batches_in_epoch <= skip_here or seen <= self._skip_batches:
                     # consumed before the checkpoint this run resumed from
+                    self._tick()
                     if resume is not None and (self._batches_in_epoch == skip_here or seen == self._skip_batches):
                         self._restore_rng(resume)   # from here on the run continues exactly where it was cut
                         resume = None
                     continue
                 before = self.state.step
                 loss = self.train_step(batch)
+                self._tick()
                 if self.state.step != before:
                     if self.state.step % self.log_every == 0:
                         self.state.last_loss = float(loss.item())
@@ -303,6 +316,7 @@ class Trainer:
                 out = self.module(**batch, labels=labels)
                 total += float((out.loss if hasattr(out, "loss") else out[0]).item())
                 n += 1
+                self._tick()
                 self._add_router_losses(torch.zeros(()))   # evaluation reports the task loss; just drain the expert context
             return total / max(n, 1)
         finally:

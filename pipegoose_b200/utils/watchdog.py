@@ -9,6 +9,8 @@ Two small tools, both host-side and off the hot path:
   ``on_failure(dead_ranks)``; the default handler prints every thread's stack and sends the process a SIGINT, which
   turns a silent hang into a ``RankFailure`` (and, with ``abort_after_s``, ends a process whose main thread is stuck
   inside a CUDA / NCCL call so that the launcher can restart the job).
+  With ``stall_timeout_s`` it also watches its OWN process for progress (:meth:`RankWatchdog.tick`): a wedged main
+  thread — whose heartbeat thread would keep every peer happy forever — ends the process.
 * :func:`step_deadline` — ``with step_deadline(120): train_step()`` dumps all thread stacks (``faulthandler``) when a
   step overruns, which is what one wants to see from a job that is stuck inside NCCL or a spinning flag wait.
 """
@@ -24,6 +26,9 @@ from typing import Callable, Dict, List, Optional
 import torch.distributed as dist
 
 
+STALL_EXIT_CODE = 75      # EX_TEMPFAIL: "try again" — what a launcher with --max-restarts does
+
+
 class RankFailure(RuntimeError):
     """Raised in the main thread when peers stopped heart-beating."""
 
@@ -35,9 +40,15 @@ class RankFailure(RuntimeError):
 class RankWatchdog:
     def __init__(self, parallel_context=None, timeout_s: float = 60.0, interval_s: float = 1.0,
                  on_failure: Optional[Callable[[List[int]], None]] = None, ranks: Optional[List[int]] = None,
-                 store=None, tag: str = "watchdog", abort_after_s: Optional[float] = None):
+                 store=None, tag: str = "watchdog", abort_after_s: Optional[float] = None,
+                 stall_timeout_s: Optional[float] = None):
         """``ranks``: the global ranks to watch (default: the whole job).  ``store``: any c10d ``Store`` (default: the
-        job's own)."""
+        job's own).  ``stall_timeout_s``: the PROGRESS deadline — the owner calls :meth:`tick` whenever it makes progress
+        (the ``Trainer``: after every micro-step, evaluation batch and checkpoint); when no tick arrives for this long
+        the main thread is wedged (a sleeping callback, a spinning kernel, a collective whose peer is wedged — the
+        heartbeat THREAD of such a process keeps beating, so no peer would ever call it dead): every thread's stack is
+        dumped and the process ends with :data:`STALL_EXIT_CODE`, which takes the attempt down so that the launcher can
+        restart it.  Must exceed the longest legitimate gap between ticks (first step, checkpoint writes)."""
         self.rank = parallel_context.get_global_rank() if parallel_context is not None else dist.get_rank()
         world = dist.get_world_size()
         self.ranks = [r for r in (ranks if ranks is not None else range(world)) if r != self.rank]
@@ -51,10 +62,19 @@ class RankWatchdog:
         self._thread: Optional[threading.Thread] = None
         self._beat = 0
         self._pending_failure: Optional[RankFailure] = None
+        self.stall_timeout_s = stall_timeout_s
+        self._last_tick = time.monotonic()
+        self.ticks = 0
 
     # ------------------------------------------------------------------ lifecycle
+    def tick(self):
+        """The owner made progress (see ``stall_timeout_s``)."""
+        self.ticks += 1
+        self._last_tick = time.monotonic()
+
     def start(self) -> "RankWatchdog":
         assert self._thread is None, "already started"
+        self._last_tick = time.monotonic()
         self._publish()
         self._thread = threading.Thread(target=self._loop, name=f"pg-watchdog-{self.rank}", daemon=True)
         self._thread.start()
@@ -109,6 +129,9 @@ class RankWatchdog:
                 self._report([0] if self.rank != 0 else [])
                 return
             now = time.monotonic()
+            if self.stall_timeout_s is not None and now - self._last_tick > self.stall_timeout_s:
+                self._stalled(now - self._last_tick)
+                return
             dead = []
             for r in self.ranks:
                 if r in self.failed:
@@ -123,6 +146,16 @@ class RankWatchdog:
                     dead.append(r)
             if dead:
                 self._report(dead)
+
+    def _stalled(self, silent_for: float):
+        """The main thread cannot be asked to raise — it is the one that is stuck.  Say why, then end the process."""
+        import os
+
+        sys.stderr.write(f"[pipegoose_b200 watchdog] rank {self.rank}: no progress for {silent_for:.0f} s "
+                         f"(after {self.ticks} ticks), ending the process so that the launcher can restart the job\n")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(STALL_EXIT_CODE)
 
     def _report(self, dead: List[int]):
         new = [r for r in dead if r not in self.failed]

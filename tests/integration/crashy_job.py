@@ -17,7 +17,8 @@ from pipegoose_b200.trainer import Callback, Trainer
 
 
 def main():
-    workdir, crash = sys.argv[1], sys.argv[2] == "crash"
+    workdir, mode = sys.argv[1], sys.argv[2]
+    crash = mode in ("crash", "hang")
     ctx = ParallelContext.from_torch(tensor_parallel_size=1, pipeline_parallel_size=1, data_parallel_size=2, backend="gloo")
     dp_rank = ctx.get_local_rank(ParallelMode.DATA)
     torch.manual_seed(0)
@@ -37,15 +38,19 @@ def main():
         def on_step_end(self, trainer, loss):
             if crash and dp_rank == 1 and trainer.state.step == 4 and not os.path.exists(marker):
                 open(marker, "w").write("x")
+                if mode == "hang":
+                    import time
+
+                    time.sleep(3600)              # a wedged rank: alive, silent — only the peers' watchdog can tell
                 os._exit(17)                      # the other replica is left inside its next all-reduce
 
     trainer = Trainer(model, data, optim=optim, parallel_context=ctx, callbacks=[Crash()], log_every=1,
                       checkpoint_dir=os.path.join(workdir, "ckpt") if crash else None, checkpoint_every=3, resume=crash,
-                      watchdog_timeout_s=20)
+                      watchdog_timeout_s=4 if mode == "hang" else 20)
     state = trainer.fit()
     if ctx.get_global_rank() == 0:
         checksum = float(sum(p.detach().double().sum() for p in model.parameters()))
-        with open(os.path.join(workdir, "result_crash.json" if crash else "result_clean.json"), "w") as f:
+        with open(os.path.join(workdir, f"result_{mode}.json"), "w") as f:
             json.dump({"step": state.step, "loss": state.last_loss, "checksum": checksum,
                        "restarts": int(os.environ.get("TORCHELASTIC_RESTART_COUNT", "0")), "started_at": started_at[0]}, f)
     ctx.destroy()

@@ -37,3 +37,21 @@ def test_job_survives_a_dead_replica(tmp_path):
     assert want["started_at"] == 0 and got["started_at"] == 3               # checkpoints at 3 and 6; the crash came in 4
     assert got["loss"] == pytest.approx(want["loss"], abs=1e-5)
     assert got["checksum"] == pytest.approx(want["checksum"], abs=1e-4)
+
+
+@pytest.mark.timeout(900)
+def test_job_survives_a_hung_replica(tmp_path):
+    """The replica does not die, it stops making progress (it sleeps inside a callback; its heartbeat THREAD keeps beating,
+    so no peer would ever declare it dead, and its peer waits in the next all-reduce).  Both processes' progress
+    deadlines (``RankWatchdog(stall_timeout_s=...)``, ticked by the Trainer) expire, the processes end with
+    STALL_EXIT_CODE, the launcher starts the second attempt, which resumes from the checkpoint of step 3."""
+    workdir = str(tmp_path)
+    clean = _launch(workdir, "clean", 0)
+    assert clean.returncode == 0, clean.stderr[-3000:]
+    hung = _launch(workdir, "hang", 1)
+    assert hung.returncode == 0, hung.stderr[-3000:]
+    assert "no progress for" in hung.stderr
+    want = json.load(open(os.path.join(workdir, "result_clean.json")))
+    got = json.load(open(os.path.join(workdir, "result_hang.json")))
+    assert got["restarts"] == 1 and got["started_at"] == 3 and got["step"] == 8
+    assert got["checksum"] == pytest.approx(want["checksum"], abs=1e-4)

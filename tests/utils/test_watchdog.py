@@ -59,3 +59,27 @@ def test_step_deadline_dumps_stacks_on_overrun():
         time.sleep(0.05)
         f.seek(0)
         assert f.read() == ""
+
+
+def run_stall(rank, world_size, port):
+    from pipegoose_b200.utils.watchdog import STALL_EXIT_CODE  # noqa: F401
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size)
+    wd = RankWatchdog(ctx, timeout_s=30.0, interval_s=0.1, stall_timeout_s=1.0, tag="stall").start()
+    for _ in range(8):          # progress every 0.25 s for 2 s: twice the deadline, nothing happens
+        time.sleep(0.25)
+        wd.tick()
+    assert wd.ticks == 8
+    time.sleep(30)              # the main thread is wedged: the process must end with STALL_EXIT_CODE long before this returns
+    raise AssertionError("the stalled process was not ended")
+
+
+def test_stalled_main_thread_ends_the_process_with_the_restart_exit_code():
+    from torch.multiprocessing import ProcessExitedException
+
+    from pipegoose_b200.utils.watchdog import STALL_EXIT_CODE
+
+    t0 = time.monotonic()
+    with pytest.raises(ProcessExitedException) as info:
+        spawn(run_stall, world_size=1)
+    assert info.value.exit_code == STALL_EXIT_CODE and time.monotonic() - t0 < 25
