@@ -55,3 +55,25 @@ def test_job_survives_a_hung_replica(tmp_path):
     got = json.load(open(os.path.join(workdir, "result_hang.json")))
     assert got["restarts"] == 1 and got["started_at"] == 3 and got["step"] == 8
     assert got["checksum"] == pytest.approx(want["checksum"], abs=1e-4)
+
+
+@pytest.mark.timeout(600)
+def test_two_launcher_agents_like_two_nodes(tmp_path):
+    """``torchrun --nnodes 2`` (two agents, one rank each: LOCAL_RANK 0 on both, LOCAL_WORLD_SIZE 1 < WORLD_SIZE 2), the
+    shape of a multi-node job, against the single-agent run of the same job."""
+    from pipegoose_b200.testing.utils import find_free_port
+
+    one, two = str(tmp_path / "one"), str(tmp_path / "two")
+    os.makedirs(one), os.makedirs(two)
+    assert _launch(one, "clean", 0).returncode == 0
+    port = find_free_port()
+    procs = [subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=2", f"--node-rank={n}",
+                               "--nproc-per-node=1", "--rdzv-backend", "c10d", "--rdzv-endpoint", f"127.0.0.1:{port}",
+                               "--rdzv-id", "two-agents", "--local-addr", "127.0.0.1",
+                               os.path.join(HERE, "crashy_job.py"), two, "clean"],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for n in (0, 1)]
+    outs = [p.communicate(timeout=400) for p in procs]
+    assert [p.returncode for p in procs] == [0, 0], outs[0][1][-2000:] + outs[1][1][-2000:]
+    want = json.load(open(os.path.join(one, "result_clean.json")))
+    got = json.load(open(os.path.join(two, "result_clean.json")))
+    assert got["step"] == 8 and got["checksum"] == pytest.approx(want["checksum"], abs=1e-6)
