@@ -130,7 +130,9 @@ def _flat_index(optim):
     if fa is None:
         return None
     flat = fa.ensure_flat()
-    return [tuple(int(x) for x in flat.param_range(p)) for g in fa.param_groups for p in g["params"]]
+    # (None: a parameter the flat state does not hold — another pipeline stage's zero-size stand-in)
+    return [tuple(int(x) for x in flat.offsets[id(p)]) if id(p) in flat.offsets else None
+            for g in fa.param_groups for p in g["params"]]
 
 
 def capture_rng_state() -> dict:
@@ -226,7 +228,7 @@ def _load_for_another_dp_size(optim, ckp_path: str, parallel_context: ParallelCo
         raise ValueError("this checkpoint predates the per-parameter index that re-cutting for another data-parallel size "
                          "needs (save it again with this version at the old size)")
     blobs = [first] + [torch.load(found[d], map_location="cpu", weights_only=False) for d in range(1, old["dp"])]
-    old_index = [tuple(x) for x in first["flat_index"]]
+    old_index = [tuple(x) if x is not None else None for x in first["flat_index"]]
 
     def provider(new_segments, new_index, new_numel):
         return reshard_fused_state([b["optimizer"] for b in blobs], old_index, new_segments, new_index, new_numel)
@@ -252,9 +254,15 @@ def reshard_fused_state(old_states: list, old_index: list, new_segments: list, n
     replicas.  Parameters are matched by their position in ``param_groups`` (``*_index[i] = (offset, numel)`` in the
     old / new flat buffer); every element of every parameter must be owned by exactly one old replica."""
     assert len(old_index) == len(new_index), "the optimizers hold different numbers of parameters"
-    for i, ((_, a), (_, b)) in enumerate(zip(old_index, new_index)):
-        if a != b:
-            raise ValueError(f"parameter {i} has {a} elements in the checkpoint and {b} in this model")
+    pairs = []
+    for i, (o, n) in enumerate(zip(old_index, new_index)):
+        if (o is None) != (n is None):
+            raise ValueError(f"parameter {i} is held by this rank in one of the two jobs only (another pipeline layout?)")
+        if o is None:
+            continue        # another pipeline stage's parameter in both jobs
+        if o[1] != n[1]:
+            raise ValueError(f"parameter {i} has {o[1]} elements in the checkpoint and {n[1]} in this model")
+        pairs.append((tuple(o), tuple(n)))
     old_numel = max(e for sd in old_states for _, e in sd["segments"])
     out = {"step": old_states[0]["step"], "segments": [tuple(x) for x in new_segments],
            "param_groups": old_states[0].get("param_groups", [])}
@@ -266,7 +274,7 @@ def reshard_fused_state(old_states: list, old_index: list, new_segments: list, n
                 full[s:e] = sd[key][off:off + e - s].float()
                 off += e - s
         new_full = torch.zeros(new_numel, dtype=torch.float32)
-        for (o_old, n), (o_new, _) in zip(old_index, new_index):
+        for (o_old, n), (o_new, _) in pairs:
             piece = full[o_old:o_old + n]
             if torch.isnan(piece).any():
                 raise ValueError("the old replicas' slices do not cover every parameter (incomplete checkpoint?)")

@@ -21,6 +21,10 @@ def _build(ctx):
     torch.manual_seed(0)
     model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
     model = TensorParallel(model, ctx).parallelize()
+    if ctx.pipeline_parallel_size > 1:
+        from pipegoose_b200.nn import PipelineParallel
+
+        model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
     model = DataParallel(model, ctx).parallelize()
     return model, DistributedOptimizer(FusedAdam(model.parameters(), lr=1e-2, weight_decay=0.01, adamw=True), ctx)
 
@@ -43,8 +47,8 @@ def _full_params(model, ctx):
     return {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 
-def run_write(rank, world_size, port, tp, dp, ckp, out):
-    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+def run_write(rank, world_size, port, tp, dp, ckp, out, pp=1):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, dp)
     model, optim = _build(ctx)
     for i in range(2):
         _step(model, optim, ctx, i)
@@ -53,12 +57,12 @@ def run_write(rank, world_size, port, tp, dp, ckp, out):
     losses = [_step(model, optim, ctx, i) for i in (2, 3)]    # the uninterrupted run goes on
     if ctx.get_local_rank(ParallelMode.DATA) == 0:
         torch.save({"losses": losses, "params": _full_params(model, ctx)},
-                   os.path.join(out, f"want_tp{ctx.get_local_rank(ParallelMode.TENSOR)}.pt"))
+                   os.path.join(out, f"want_tp{ctx.get_local_rank(ParallelMode.TENSOR)}_pp{ctx.get_local_rank(ParallelMode.PIPELINE)}.pt"))
     ctx.destroy()
 
 
-def run_resume(rank, world_size, port, tp, dp, ckp, out, warm):
-    ctx = init_parallel_context(rank, world_size, port, tp, 1, dp)
+def run_resume(rank, world_size, port, tp, dp, ckp, out, warm, pp=1):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, dp)
     model, optim = _build(ctx)
     if warm:
         _step(model, optim, ctx, 99)          # optimizer state already laid out (and dirty) before the load
@@ -66,7 +70,7 @@ def run_resume(rank, world_size, port, tp, dp, ckp, out, warm):
     meta = load_training_state(optim, ckp_path=ckp, parallel_context=ctx)
     assert meta["step"] == 2 and meta["extra"] == {"tokens": 128} and meta["resharded_from_dp"] == 2
     losses = [_step(model, optim, ctx, i) for i in (2, 3)]
-    want = torch.load(os.path.join(out, f"want_tp{ctx.get_local_rank(ParallelMode.TENSOR)}.pt"))
+    want = torch.load(os.path.join(out, f"want_tp{ctx.get_local_rank(ParallelMode.TENSOR)}_pp{ctx.get_local_rank(ParallelMode.PIPELINE)}.pt"))
     assert losses == pytest.approx(want["losses"], abs=2e-5), (losses, want["losses"])
     for k, v in _full_params(model, ctx).items():
         assert torch.allclose(v, want["params"][k], atol=2e-5), k
@@ -79,6 +83,14 @@ def test_zero1_checkpoint_of_two_replicas_resumes_on_another_replica_count(tmp_p
     ckp, out = str(tmp_path / "ckpt"), str(tmp_path)
     spawn(run_write, world_size=tp * 2, tp=tp, dp=2, ckp=ckp, out=out)
     spawn(run_resume, world_size=tp * new_dp, tp=tp, dp=new_dp, ckp=ckp, out=out, warm=warm)
+
+
+def test_pipeline_stages_resume_on_another_replica_count(tmp_path):
+    """PP2 x DP2 -> PP2 x DP1: every stage re-cuts the optimizer state of ITS parameters (the other stage's zero-size
+    stand-ins are in the optimizer's parameter list but not in the flat state)."""
+    ckp, out = str(tmp_path / "ckpt"), str(tmp_path)
+    spawn(run_write, world_size=4, tp=1, dp=2, ckp=ckp, out=out, pp=2)
+    spawn(run_resume, world_size=2, tp=1, dp=1, ckp=ckp, out=out, warm=False, pp=2)
 
 
 def test_reshard_fused_state_unit():
@@ -106,6 +118,11 @@ def test_reshard_fused_state_unit():
         reshard_fused_state(olds[:1], old_index, [(0, 48)], new_index, 48)
     with pytest.raises(ValueError, match="elements in the checkpoint"):
         reshard_fused_state(olds, old_index, [(0, 48)], [(0, 4), (16, 3), (32, 4)], 48)
+    # parameters neither job holds on this rank (another pipeline stage's) are skipped; held by one job only: refused
+    skip = reshard_fused_state(olds, old_index + [None], [(0, 48)], new_index + [None], 48)
+    assert torch.equal(skip["master"], got["master"])
+    with pytest.raises(ValueError, match="one of the two jobs only"):
+        reshard_fused_state(olds, old_index + [None], [(0, 48)], new_index + [(40, 2)], 48)
 
 
 def run_refused(rank, world_size, port, ckp):
