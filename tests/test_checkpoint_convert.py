@@ -39,7 +39,7 @@ def run_save(rank, world_size, port, tp, pp, ckp_path, state, hf):
     ctx.destroy()
 
 
-@pytest.mark.parametrize("tp,pp,hf", [(2, 1, False), (2, 2, False), (1, 2, False), (2, 1, True)])
+@pytest.mark.parametrize("tp,pp,hf", [(2, 1, False), (2, 2, False), (1, 2, False), (2, 1, True), (2, 2, True)])
 def test_consolidated_checkpoint_is_the_unsharded_model(tmp_path, tp, pp, hf):
     if hf:
         from transformers import BloomConfig as HFConfig
@@ -140,9 +140,11 @@ def _moe(ctx, world):
     return TensorParallel(model, ctx).parallelize()
 
 
-def run_moe_save(rank, world_size, port, ckp_path):
-    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1)
+def run_moe_save(rank, world_size, port, ckp_path, pp=1):
+    ctx = init_parallel_context(rank, world_size, port, world_size // pp, pp, 1)
     model = _moe(ctx, world_size)
+    if pp > 1:
+        model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
     save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
     ctx.destroy()
 
@@ -153,9 +155,11 @@ def test_expert_parallel_checkpoint_renumbers_the_experts(tmp_path):
     two, one = str(tmp_path / "two"), str(tmp_path / "one")
     spawn(run_moe_save, world_size=2, ckp_path=two)
     spawn(run_moe_save, world_size=1, ckp_path=one)
-    merged = consolidate_checkpoint(two, 2, 1)
     want = torch.load(os.path.join(one, "pytorch_model_tp_0_pp_0.bin"))
-    assert set(merged) == set(want), set(merged) ^ set(want)
-    assert any(".experts.3." in k for k in merged)
-    for k, v in want.items():
-        assert torch.equal(merged[k], v), k
+    staged = str(tmp_path / "staged")
+    spawn(run_moe_save, world_size=4, ckp_path=staged, pp=2)              # experts over TP2, layers over PP2
+    for merged in (consolidate_checkpoint(two, 2, 1), consolidate_checkpoint(staged, 2, 2)):
+        assert set(merged) == set(want), set(merged) ^ set(want)
+        assert any(".experts.3." in k for k in merged)
+        for k, v in want.items():
+            assert torch.equal(merged[k], v), k
