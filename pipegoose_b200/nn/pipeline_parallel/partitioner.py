@@ -160,7 +160,16 @@ class BloomStage(_ReferenceCallStyle, nn.Module):
                                                 eps, model.vocab_start, -100, model.tp,
                                                 vocab_size=self.config.vocab_size)
             ln = fused_layer_norm(h, self.ln_f.weight, self.ln_f.bias, eps)
-            logits = K.gemm_nt(ln, self.lm_head.weight).view(B, S, -1)
+            # as the unpartitioned model (models/bloom.py): under tensor parallelism the rows are token-sharded and the
+            # table vocabulary-sharded — gather the tokens, multiply, gather the vocabulary; ``PF.linear`` (not the bare
+            # kernel) so that ``out.sum().backward()`` of the reference's forward-only usage reaches the lm_head
+            tp = model.tp
+            if tp is not None:
+                ln = tp.gather_rows(ln)
+            logits = PF.linear(ln, self.lm_head.weight)
+            if tp is not None:
+                logits = tp.gather_cols(logits)[:, : self.config.vocab_size]
+            logits = logits.view(B, S, -1)
             if unroll is not None:
                 logits = logits.gather(1, unroll[:, :, None].expand(-1, -1, logits.shape[-1]))
             return logits
