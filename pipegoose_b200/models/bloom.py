@@ -397,7 +397,8 @@ class BloomForCausalLM(nn.Module):
         leading zeros) are cached too: pad keys are masked per row, ALiBi only sees distances between real tokens.
         Masks that are not left-padded are refused (the new tokens go behind the last column).  Recomputed through the
         training forward for every token instead: models with a fused NVLink MoE layer (kernels built around
-        token-sharded full sequences) and ``use_cache=False``."""
+        token-sharded full sequences), ``use_cache=False``, and pipelined models (``PipelineParallel``: one forward-only
+        schedule per token, the last stage picks the token and broadcasts it to the other stages)."""
         B, prompt_len = input_ids.shape
         ragged = attention_mask is not None and bool((attention_mask == 0).any())
         dense = all(isinstance(b.mlp, BloomMLP) or _decodes_incrementally(b.mlp) for b in self.transformer.h)
@@ -410,7 +411,10 @@ class BloomForCausalLM(nn.Module):
             if not bool((mask.sum(1) + lead == prompt_len).all()):
                 raise ValueError("generate() takes LEFT-padded prompts (attention_mask rows: zeros, then ones): new tokens "
                                  "are appended behind the last column, which must be every row's last real token")
-        cached = use_cache and dense
+        # a pipelined model (PipelineParallel): every new token is one forward-only schedule through the stages — keys and
+        # values are not cached across stages — and the last stage, which holds the logits, tells the others the token
+        engine = getattr(self, "_pg_pipeline_engine", None)
+        cached = use_cache and dense and engine is None
         out = input_ids
         finished = torch.zeros(B, dtype=torch.bool, device=input_ids.device)
         fill = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
@@ -422,16 +426,24 @@ class BloomForCausalLM(nn.Module):
             else:
                 S = out.shape[1]
                 pad = 0
-                while (B * (S + pad)) % group:   # token-sharded activations need a multiple of the group size
+                # token-sharded activations need a multiple of the group size (per micro-batch under a pipeline engine:
+                # whole rows, so the row length itself is padded)
+                while ((S + pad) if engine is not None else (B * (S + pad))) % group:
                     pad += 1
                 if ragged:   # pads go in FRONT (mask 0): the batch stays left-padded, the last column the newest token
                     ids = out if pad == 0 else torch.cat([out.new_zeros(B, pad), out], dim=1)
                     m = mask if pad == 0 else torch.cat([mask.new_zeros(B, pad), mask], dim=1)
-                    last = self(ids, attention_mask=m).logits[:, -1, :]
+                    pos = -1
                 else:        # right padding is harmless under a causal mask
                     ids = out if pad == 0 else torch.cat([out, out.new_zeros(B, pad)], dim=1)
-                    last = self(ids).logits[:, S - 1, :]
-            nxt = self._select_token(last.float(), do_sample, temperature, top_k, top_p, generator)
+                    m, pos = None, S - 1
+                if engine is None:
+                    last = (self(ids, attention_mask=m) if m is not None else self(ids)).logits[:, pos, :]
+            if engine is not None:
+                nxt = self._pipelined_next_token(engine, ids, m, pos, lambda logits: self._select_token(
+                    logits, do_sample, temperature, top_k, top_p, generator))
+            else:
+                nxt = self._select_token(last.float(), do_sample, temperature, top_k, top_p, generator)
             if eos_token_id is not None:
                 nxt = torch.where(finished, torch.full_like(nxt, fill), nxt)
                 finished = finished | (nxt == eos_token_id)
@@ -441,6 +453,23 @@ class BloomForCausalLM(nn.Module):
             if eos_token_id is not None and bool(finished.all()):
                 break
         return out
+
+    def _pipelined_next_token(self, engine, ids: torch.Tensor, mask: Optional[torch.Tensor], pos: int, select) -> torch.Tensor:
+        """One decoding step of a pipelined model: a forward-only schedule (micro-batched like training), the token chosen
+        on the last stage from the logits at ``pos`` and broadcast over the PIPELINE group."""
+        import torch.distributed as dist
+
+        from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+        outs = self(ids, attention_mask=mask) if mask is not None else self(ids)
+        ctx = engine.parallel_context
+        if engine.is_last:
+            logits = torch.cat([o.logits if hasattr(o, "logits") else o for o in outs], dim=0)
+            nxt = select(logits[:, pos, :].float())
+        else:
+            nxt = torch.empty(ids.shape[0], dtype=torch.long, device=ids.device)
+        dist.broadcast(nxt, src=ctx.get_ranks_in_group(ParallelMode.PIPELINE)[-1], group=ctx.get_group(ParallelMode.PIPELINE))
+        return nxt
 
     def _select_token(self, logits: torch.Tensor, do_sample: bool, temperature: float, top_k: int, top_p: float,
                       generator: Optional[torch.Generator]) -> torch.Tensor:

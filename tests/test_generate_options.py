@@ -125,3 +125,44 @@ def test_tensor_parallel_ranks_agree_on_sampled_tokens_and_ragged_prompts():
     want = model.generate(ids * mask, attention_mask=mask, max_new_tokens=4)
     spawn(run_tp_sampling, world_size=2, state=copy.deepcopy(model.state_dict()), ids=ids * mask, mask=mask, want=want)
     assert want.shape == (2, 9)
+
+
+def run_pipelined_generate(rank, world_size, port, tp, state, ids, mask, want, want_ragged, eos):
+    import torch.distributed as dist
+
+    from pipegoose_b200.nn import PipelineParallel, TensorParallel
+
+    ctx = init_parallel_context(rank, world_size, port, tp, 2, 1)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()
+    model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize().eval()
+    assert torch.equal(model.generate(ids, max_new_tokens=5), want)                    # one forward-only schedule per token
+    got = model.generate(ids * mask, attention_mask=mask, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
+    assert torch.equal(got, want_ragged), (got, want_ragged)
+    torch.manual_seed(100 + rank)                                                      # ranks draw differently, must agree
+    sampled = model.generate(ids, max_new_tokens=5, do_sample=True, temperature=1.3, top_k=20)
+    everyone = [None] * world_size
+    dist.all_gather_object(everyone, sampled.tolist())
+    assert all(e == everyone[0] for e in everyone)
+    # training still works afterwards (the engine's forward-only runs left no state behind)
+    model.train()
+    loss = model(ids, labels=ids).loss
+    loss.backward()
+    assert torch.isfinite(loss)
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("tp", [1, 2])
+def test_generate_on_a_pipelined_model(tp):
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4)).eval()
+    ids = torch.randint(1, 96, (4, 6), generator=torch.Generator().manual_seed(8))
+    mask = torch.ones_like(ids)
+    mask[1, :2] = 0
+    mask[3, :4] = 0
+    want = model.generate(ids, max_new_tokens=5)
+    eos = int(model.generate(ids * mask, attention_mask=mask, max_new_tokens=5)[0, 8])
+    want_ragged = model.generate(ids * mask, attention_mask=mask, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
+    spawn(run_pipelined_generate, world_size=2 * tp, tp=tp, state=copy.deepcopy(model.state_dict()), ids=ids, mask=mask,
+          want=want, want_ragged=want_ragged, eos=eos)
