@@ -17,3 +17,7 @@ class Callback:
 
     def on_step_end(self, trainer, loss: float):
         pass
+
+    def on_evaluate(self, trainer, eval_loss: float):
+        """After a periodic evaluation (``Trainer(eval_every=N)``) or the one at the end of ``fit``."""
+        pass

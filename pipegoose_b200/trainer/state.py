@@ -25,3 +25,4 @@ class TrainerState:
     tokens_seen: int = 0
     last_loss: float = float("nan")
     last_grad_norm: float = float("nan")
+    last_eval_loss: float = float("nan")

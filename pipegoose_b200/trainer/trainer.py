@@ -21,14 +21,17 @@ class Trainer:
                  parallel_context=None, log_every: int = 10, grad_accum_steps: int = 1,
                  max_grad_norm: Optional[float] = None, lr_scheduler=None, checkpoint_dir: Optional[str] = None,
                  checkpoint_every: int = 0, resume: bool = False, watchdog_timeout_s: Optional[float] = None,
-                 max_steps: Optional[int] = None, keep_checkpoints: int = 2, moe_loss_weights=(0.01, 0.001)):
+                 max_steps: Optional[int] = None, keep_checkpoints: int = 2, moe_loss_weights=(0.01, 0.001),
+                 eval_every: int = 0):
         """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
         norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
         and optimizer / RNG / step state (save_training_state) every N optimizer steps, each in its own ``step_<n>``
         directory that becomes ``latest`` only when every rank has written its shard (``keep_checkpoints`` newest kept); ``resume=True`` restores the
         latest one before training and skips the batches it had consumed.  ``max_steps``: stop at that optimizer step.  ``watchdog_timeout_s``: start a
-        :class:`RankWatchdog` for the duration of ``fit``."""
+        :class:`RankWatchdog` for the duration of ``fit``.  ``eval_every``: evaluate on ``eval_loader`` every N optimizer
+        steps and once more when ``fit`` ends (``state.last_eval_loss``, the loggers' ``eval_loss``, ``on_evaluate``); the
+        random generators are put back afterwards, so a run trains identically with and without evaluations."""
         assert grad_accum_steps >= 1
         self.module = module
         self.train_loader = train_loader
@@ -48,6 +51,7 @@ class Trainer:
         self.watchdog_timeout_s = watchdog_timeout_s
         self.moe_loss_weights = moe_loss_weights   # (load-balancing, router-z) weights for MoE models
         self.keep_checkpoints = max(1, keep_checkpoints)   # newest complete step directories kept on disk
+        self.eval_every = int(eval_every or 0)
         self.max_steps = max_steps   # stop once this many optimizer steps exist in total (counting resumed ones)
         self.state = TrainerState()
         self._micro = 0
@@ -138,6 +142,25 @@ class Trainer:
     # ------------------------------------------------------------------ checkpoints
     # layout:  <checkpoint_dir>/step_00000500/{pytorch_model_tp_*_pp_*.bin, optimizer_tp_*_pp_*_dp_*.bin}
     #          <checkpoint_dir>/latest        <- name of the newest COMPLETE step directory (written last, atomically)
+    _last_eval_step = -1
+
+    def _evaluate_in_training(self):
+        """A periodic evaluation that leaves no trace in the training run: eval mode and stage are restored by
+        ``evaluate``; the random generators (a ``DataLoader`` iterator draws a base seed when it is created) here."""
+        from pipegoose_b200.nn.utils import capture_rng_state, restore_rng_state
+
+        rng = capture_rng_state()
+        try:
+            loss = float(self.evaluate())
+        finally:
+            restore_rng_state(rng)
+        self.state.last_eval_loss = loss
+        self._last_eval_step = self.state.step
+        self._log(f"step {self.state.step} eval loss {loss:.4f}")
+        self._log_metrics({"step": self.state.step, "eval_loss": loss})
+        self._call("on_evaluate", loss)
+        return loss
+
     def _tick(self):
         wd = getattr(self, "_watchdog", None)
         if wd is not None:
@@ -237,6 +260,8 @@ class Trainer:
             self._watchdog = None
             if watchdog is not None:
                 watchdog.stop()
+        if self.eval_every and self.eval_loader is not None and self._last_eval_step != self.state.step:
+            self._evaluate_in_training()
         self._call("on_fit_end")
         self.state.status = TrainerStatus.FINISHED
         return self.state
@@ -290,6 +315,8 @@ class Trainer:
                                            "tokens_seen": self.state.tokens_seen, "grad_norm": self.state.last_grad_norm,
                                            "lr": self._current_lr()})
                     self._call("on_step_end", loss)
+                    if self.eval_every and self.eval_loader is not None and self.state.step % self.eval_every == 0:
+                        self._evaluate_in_training()
             self._call("on_epoch_end")
 
     @staticmethod

@@ -297,3 +297,43 @@ def test_trainer_checkpoints_and_resumes_pipeline_stages(tmp_path):
     """PP2 x DP2 + ZeRO-1: the optimizer's parameter list holds the other stage's zero-size stand-ins, the flat state
     does not (the per-parameter index of the optimizer shard must cope)."""
     spawn(run_trainer_resume_pipeline, world_size=4, ckp=str(tmp_path / "run"))
+
+
+def test_periodic_evaluation_leaves_training_untouched(tmp_path):
+    """``eval_every``: evaluations at steps 2, 4 and at the end (5); the trained parameters equal those of a run without
+    evaluations although the model uses dropout and the eval loader is a DataLoader (whose iterator draws from the RNG)."""
+    import json
+
+    from torch.utils.data import DataLoader
+
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.trainer import Callback, JsonlLogger, Trainer
+
+    cfg = BloomConfig(vocab_size=64, hidden_size=32, n_layer=1, n_head=4, hidden_dropout=0.1)
+    g = torch.Generator().manual_seed(1)
+    train = [{"input_ids": torch.randint(0, 64, (2, 8), generator=g)} for _ in range(5)]
+    held_out = [{"input_ids": torch.randint(0, 64, (8,), generator=g)} for _ in range(6)]
+
+    def run(**kw):
+        torch.manual_seed(0)
+        model = BloomForCausalLM(cfg)
+        trainer = Trainer(model, train, optim=FusedAdam(model.parameters(), lr=1e-2), **kw)
+        trainer.fit()
+        return model, trainer
+
+    plain, _ = run()
+    seen = []
+
+    class Rec(Callback):
+        def on_evaluate(self, trainer, eval_loss):
+            seen.append((trainer.state.step, eval_loss, trainer.module.training))
+
+    path = str(tmp_path / "metrics.jsonl")
+    evaluated, trainer = run(eval_loader=DataLoader(held_out, batch_size=3, shuffle=True), eval_every=2, callbacks=[Rec()],
+                             loggers=[JsonlLogger(path)], log_every=100)
+    assert [s for s, _, _ in seen] == [2, 4, 5] and all(training for _, _, training in seen)
+    assert seen[-1][1] == trainer.state.last_eval_loss and seen[-1][1] < seen[0][1] + 0.5
+    rows = [json.loads(line) for line in open(path)]
+    assert [r["step"] for r in rows if "eval_loss" in r] == [2, 4, 5]
+    for (n, a), (_, b) in zip(plain.named_parameters(), evaluated.named_parameters()):
+        assert torch.equal(a, b), n
