@@ -80,7 +80,7 @@ def shard_layout(module: nn.Module, parallel_context) -> Dict:
                 entry["full"] = int(meta.full_size)
             if getattr(meta, "is_vocab", False):
                 entry["vocab"] = True
-        if key in stacked:
+        if key in stacked and not entry.get("absent"):
             entry = {"dim": 0, "full": stacked[key]}
         for prefix, g in expert_prefix.items():
             if key.startswith(prefix):

@@ -163,3 +163,34 @@ def test_expert_parallel_checkpoint_renumbers_the_experts(tmp_path):
         assert any(".experts.3." in k for k in merged)
         for k, v in want.items():
             assert torch.equal(merged[k], v), k
+
+
+def test_layout_of_a_fused_moe_layer_records_the_expert_dimension():
+    """The fused NVLink MoE layer keeps its experts stacked (``[E_local, ...]``): the layout file says "cut along
+    dimension 0, E experts in total"; another pipeline stage's zero-size stand-in stays "absent"."""
+    from torch import nn
+
+    import pipegoose_b200.ops.moe as moe
+    from pipegoose_b200.distributed.parallel_mode import ParallelMode
+    from pipegoose_b200.nn.checkpoint_convert import shard_layout, shard_state_dict
+
+    class Ctx:
+        tensor_parallel_size, pipeline_parallel_size = 2, 2
+
+        def get_local_rank(self, mode):
+            return 1 if mode is ParallelMode.TENSOR else 0
+
+    layer = moe.FusedExpertLayer.__new__(moe.FusedExpertLayer)     # (the constructor needs a process group: fields by hand)
+    nn.Module.__init__(layer)
+    layer.num_experts = 8
+    layer.w1, layer.b1 = nn.Parameter(torch.zeros(4, 16, 4)), nn.Parameter(torch.zeros(4, 16))
+    layer.w2, layer.b2 = nn.Parameter(torch.zeros(0)), nn.Parameter(torch.zeros(4, 4))
+    root = nn.Module()
+    root.mlp = layer
+    keys = shard_layout(root, Ctx())["keys"]
+    assert keys["mlp.w1"] == {"dim": 0, "full": 8} and keys["mlp.b1"] == {"dim": 0, "full": 8}
+    assert keys["mlp.w2"] == {"absent": True}
+    # re-cutting such a tensor splits the experts, without the vocabulary padding rule
+    full = {"mlp.b1": torch.arange(8 * 16.0).view(8, 16)}
+    part = shard_state_dict(full, keys, 4, 3)
+    assert torch.equal(part["mlp.b1"], full["mlp.b1"][6:8])
