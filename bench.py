@@ -53,6 +53,17 @@ def _env_defaults():
         os.environ["MASTER_PORT"] = str(_free_port())
 
 
+def _peak_mem_gb(torch, args):
+    """Peak bytes this rank's caching allocator handed out (GiB; the NVLink workspaces, mapped with the VMM API, are not
+    the allocator's and not counted).  Informational: how far the config is from the 180 GB of a B200."""
+    try:
+        if args.device == "cuda" and torch.cuda.is_available():
+            return round(torch.cuda.max_memory_allocated() / 2**30, 3)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -417,6 +428,7 @@ def run_ours(args):
         "mfu_vs_measured_sustained": None,
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    result["peak_mem_gb"] = _peak_mem_gb(torch, args)
     if numerics is not None:
         result["numerics"] = numerics
         result["numerics_ok"] = numerics.get("numerics_ok")
@@ -584,6 +596,7 @@ def run_reference(args):
         "final_loss": last.get("loss"),
         "clocks": sampler.summary() if rank == 0 else None,
     }
+    result["peak_mem_gb"] = _peak_mem_gb(torch, args)
     if note is not None:
         result["note"] = note
     if rank == 0:
