@@ -194,3 +194,34 @@ def test_layout_of_a_fused_moe_layer_records_the_expert_dimension():
     full = {"mlp.b1": torch.arange(8 * 16.0).view(8, 16)}
     part = shard_state_dict(full, keys, 4, 3)
     assert torch.equal(part["mlp.b1"], full["mlp.b1"][6:8])
+
+
+def _tiny_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    torch.manual_seed(0)
+    return LlamaForCausalLM(LlamaConfig(vocab_size=VOCAB, hidden_size=32, intermediate_size=64, num_hidden_layers=4,
+                                        num_attention_heads=4, num_key_value_heads=4, max_position_embeddings=64,
+                                        tie_word_embeddings=False))
+
+
+def run_llama_save(rank, world_size, port, tp, pp, ckp_path, state):
+    ctx = init_parallel_context(rank, world_size, port, tp, pp, 1)
+    model = _tiny_llama()
+    model.load_state_dict(state)
+    model = TensorParallel(model, ctx).parallelize()              # class-swap path (q/k/v/o, gate/up/down, untied lm_head)
+    if pp > 1:
+        model = PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+    save_pretrained(model, ckp_path=ckp_path, parallel_context=ctx)
+    ctx.destroy()
+
+
+def test_consolidation_is_driven_by_metadata_not_by_bloom_names(tmp_path):
+    """A LLaMA-style 🤗 model (other module names, untied lm_head, rotary stages): the layout files carry everything."""
+    state = copy.deepcopy(_tiny_llama().state_dict())
+    ckpt = str(tmp_path / "ckpt")
+    spawn(run_llama_save, world_size=4, tp=2, pp=2, ckp_path=ckpt, state=state)
+    merged = consolidate_checkpoint(ckpt, 2, 2)
+    assert set(merged) == set(state)
+    for k, v in state.items():
+        assert merged[k].shape == v.shape and torch.equal(merged[k], v), k
