@@ -64,6 +64,16 @@ class BloomConfig:
             apply_residual_connection_post_layernorm=hf_config.apply_residual_connection_post_layernorm,
         )
 
+    def to_hf(self):
+        """The 🤗 ``transformers.BloomConfig`` of this architecture."""
+        from transformers import BloomConfig as HFConfig
+
+        return HFConfig(vocab_size=self.vocab_size, hidden_size=self.hidden_size, n_layer=self.n_layer, n_head=self.n_head,
+                        layer_norm_epsilon=self.layer_norm_epsilon, initializer_range=self.initializer_range,
+                        hidden_dropout=self.hidden_dropout, attention_dropout=self.attention_dropout,
+                        apply_residual_connection_post_layernorm=self.apply_residual_connection_post_layernorm,
+                        tie_word_embeddings=True)
+
     @classmethod
     def bloom_tiny(cls):
         """A toy size for CPU smoke runs of the examples."""
@@ -610,6 +620,28 @@ class BloomForCausalLM(nn.Module):
         model = cls(BloomConfig.from_hf(hf_model.config))
         model.load_state_dict(hf_model.state_dict(), strict=False)
         return model
+
+    def to_hf(self):
+        """A 🤗 ``transformers.BloomForCausalLM`` with this model's weights (the way back from :meth:`from_hf` / the
+        in-place conversion of ``TensorParallel``): parameter names are the same, so this is a config translation and a
+        ``load_state_dict``.  The model must be whole — ``deparallelize()`` a live tensor- / pipeline-parallel model
+        first, or merge its checkpoint with ``nn.checkpoint_convert`` and load that."""
+        from transformers import BloomForCausalLM as HFBloom
+
+        if self.tp is not None or getattr(self, "_pg_pipeline_engine", None) is not None:
+            raise ValueError("to_hf() needs the unsharded model: deparallelize() first (or consolidate the checkpoint)")
+        if getattr(self.config, "position_embedding", "alibi") != "alibi":
+            raise ValueError("to_hf() exports Bloom-architecture models (GPT-2 family: GPT2LMHeadModel.to_hf_state_dict)")
+        hf = HFBloom(getattr(self, "hf_config", None) or self.config.to_hf())
+        hf = hf.to(next(self.parameters()).dtype)
+        missing, unexpected = hf.load_state_dict(self.state_dict(), strict=False)
+        assert not unexpected and all("lm_head" in k for k in missing), (missing, unexpected)      # (tied head)
+        hf.tie_weights()
+        return hf
+
+    def save_hf_pretrained(self, path: str, **kwargs) -> None:
+        """``to_hf().save_pretrained(path)``: a directory 🤗 ``from_pretrained`` reads (config.json + weights)."""
+        self.to_hf().save_pretrained(path, **kwargs)
 
 
 def _mask_leading_pads(scores: torch.Tensor, key_pos: torch.Tensor, lead: Optional[torch.Tensor]) -> torch.Tensor:

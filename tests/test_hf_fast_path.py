@@ -254,3 +254,40 @@ def test_left_padded_batches_through_the_fused_parallel_paths(tp, pp):
     want.backward()
     spawn(run_left_padded, world_size=tp * pp, tp=tp, pp=pp, state=state, ids=ids, mask=mask, ref_loss=want.detach(),
           ref_grad=hf.transformer.h[0].input_layernorm.weight.grad.clone())
+
+
+def test_round_trip_back_to_transformers(tmp_path):
+    """fused model -> 🤗: ``to_hf()`` (same logits), ``save_hf_pretrained`` (a directory ``from_pretrained`` reads), also
+    for a model that was converted in place and trained a step, and after ``deparallelize()``-style refusal of shards."""
+    from transformers import BloomForCausalLM as HFBloom
+
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+
+    torch.manual_seed(0)
+    mine = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=2, n_head=4))
+    ids = torch.randint(0, 96, (2, 7))
+    hf = mine.to_hf().eval()
+    assert type(hf).__module__.startswith("transformers.") and hf.lm_head.weight is hf.transformer.word_embeddings.weight
+    assert torch.allclose(hf(input_ids=ids).logits, mine(ids).logits, atol=1e-5)
+    mine.save_hf_pretrained(str(tmp_path / "export"))
+    again = HFBloom.from_pretrained(str(tmp_path / "export")).eval()
+    assert torch.allclose(again(input_ids=ids).logits, mine(ids).logits, atol=1e-5)
+    # converted in place from 🤗, trained, exported: the user's own config object comes back
+    start = _hf_bloom(hidden_dropout=0.0)
+    cfg = start.config
+    fast = convert_hf_bloom_(start)
+    loss = fast(input_ids=ids, labels=ids).loss
+    loss.backward()
+    with torch.no_grad():
+        for p in fast.parameters():
+            p -= 0.1 * (p.grad if p.grad is not None else p.main_grad).to(p.dtype)
+    back = fast.to_hf().eval()
+    assert back.config is cfg
+    assert torch.allclose(back(input_ids=ids).logits, fast.eval()(ids).logits, atol=1e-5)
+
+    class FakeTP:
+        pass
+
+    fast.tp = FakeTP()
+    with pytest.raises(ValueError, match="unsharded"):
+        fast.to_hf()
