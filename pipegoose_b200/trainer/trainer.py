@@ -328,6 +328,9 @@ class Trainer:
 
     @torch.no_grad()
     def evaluate(self) -> float:
+        """Mean loss over the batches of ``eval_loader`` — of ALL data-parallel replicas' loaders (each replica evaluates
+        its shard, sums and counts are combined over the DATA group: every rank returns the same number, and it does
+        not depend on how many replicas shared the work)."""
         assert self.eval_loader is not None
         # evaluate() may run in the middle of fit (from an on_step_end / on_epoch_end callback): the rest of training
         # must continue in the mode and stage it was in (dropout, router noise, training capacity factor)
@@ -345,6 +348,17 @@ class Trainer:
                 n += 1
                 self._tick()
                 self._add_router_losses(torch.zeros(()))   # evaluation reports the task loss; just drain the expert context
+            ctx = self.parallel_context
+            from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+            if ctx is not None and ctx.get_world_size(ParallelMode.DATA) > 1:
+                import torch.distributed as dist
+
+                group = ctx.get_group(ParallelMode.DATA)
+                acc = torch.tensor([total, float(n)], dtype=torch.float64,
+                                   device=dev if dist.get_backend(group) == "nccl" else "cpu")
+                dist.all_reduce(acc, group=group)
+                total, n = float(acc[0]), int(acc[1])
             return total / max(n, 1)
         finally:
             self.module.train(was_training)

@@ -337,3 +337,27 @@ def test_periodic_evaluation_leaves_training_untouched(tmp_path):
     assert [r["step"] for r in rows if "eval_loss" in r] == [2, 4, 5]
     for (n, a), (_, b) in zip(plain.named_parameters(), evaluated.named_parameters()):
         assert torch.equal(a, b), n
+
+
+def run_dp_evaluate(rank, world_size, port, state, batches, want):
+    from pipegoose_b200.nn import DataParallel, TensorParallel
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, world_size)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=1, n_head=4))
+    model.load_state_dict(state)
+    model = DataParallel(TensorParallel(model, ctx).parallelize(), ctx).parallelize()
+    mine = batches[rank::world_size]                               # replica 0 gets two batches, replica 1 one
+    trainer = Trainer(model, mine, eval_loader=mine, optim=FusedAdam(model.parameters(), lr=1e-2), parallel_context=ctx)
+    assert abs(trainer.evaluate() - want) < 1e-5                   # the mean over ALL replicas' batches, on every rank
+    ctx.destroy()
+
+
+def test_evaluate_averages_over_the_data_parallel_replicas():
+    torch.manual_seed(0)
+    model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=1, n_head=4))
+    batches = [{"input_ids": torch.randint(0, 96, (2, 8))} for _ in range(3)]
+    with torch.no_grad():
+        want = sum(float(model(b["input_ids"], labels=b["input_ids"]).loss) for b in batches) / 3
+    spawn(run_dp_evaluate, world_size=2, state=copy.deepcopy(model.state_dict()), batches=batches, want=want)
