@@ -49,7 +49,7 @@ class DistributedLogger:
 
 
 class JsonlLogger(DistributedLogger):
-    """One JSON object per logged training step (``step, loss, tokens_per_s, grad_norm, lr, tokens_seen``) appended to a
+    """One JSON object per logged training step (``step, loss, tokens_per_s`` of this replica, ``job_tokens_per_s`` = that times the replicas, ``grad_norm, lr, tokens_seen``) appended to a
     file by the chosen global rank — what dashboards and regression checks read; text messages are recorded, not printed."""
 
     def __init__(self, path: str, parallel_context=None, rank: int = 0):

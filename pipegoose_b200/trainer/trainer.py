@@ -161,6 +161,12 @@ class Trainer:
         self._call("on_evaluate", loss)
         return loss
 
+    def _replicas(self) -> int:
+        from pipegoose_b200.distributed.parallel_mode import ParallelMode
+
+        ctx = self.parallel_context
+        return ctx.get_world_size(ParallelMode.DATA) if ctx is not None else 1
+
     def _tick(self):
         wd = getattr(self, "_watchdog", None)
         if wd is not None:
@@ -308,10 +314,13 @@ class Trainer:
                     if self.state.step % self.log_every == 0:
                         self.state.last_loss = float(loss.item())
                         dt = max(time.time() - t0, 1e-9)
-                        self._log(f"step {self.state.step} loss {self.state.last_loss:.4f} "
-                                  f"tokens/s {(self.state.tokens_seen - tok0) / dt:.0f}")
+                        # this replica's tokens; the job's rate is that times the number of replicas
+                        replicas = self._replicas()
+                        rate = (self.state.tokens_seen - tok0) / dt
+                        self._log(f"step {self.state.step} loss {self.state.last_loss:.4f} tokens/s {rate * replicas:.0f}"
+                                  + (f" ({replicas} replicas x {rate:.0f})" if replicas > 1 else ""))
                         self._log_metrics({"step": self.state.step, "loss": self.state.last_loss,
-                                           "tokens_per_s": (self.state.tokens_seen - tok0) / dt,
+                                           "tokens_per_s": rate, "job_tokens_per_s": rate * replicas,
                                            "tokens_seen": self.state.tokens_seen, "grad_norm": self.state.last_grad_norm,
                                            "lr": self._current_lr()})
                     self._call("on_step_end", loss)
