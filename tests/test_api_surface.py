@@ -158,3 +158,31 @@ def test_round2_public_surface():
     assert callable(symmetric.exchange_fds) and hasattr(symmetric.SymmetricWorkspace, "mc_data_ptr")
     for name in ("register_grad_rs", "grad_rs_for", "ce_partials_buffer", "ce_stats_from_partials"):
         assert callable(getattr(K, name)), name
+
+
+def test_operations_layer_public_surface():
+    """Names of the operations layer (docs/OPERATIONS.md) that scripts and docs rely on."""
+    import inspect
+
+    from pipegoose_b200.models.bloom import BloomConfig, BloomForCausalLM
+    from pipegoose_b200.nn import checkpoint_convert as cc
+    from pipegoose_b200.nn import utils as nu
+    from pipegoose_b200.optim import DistributedOptimizer
+    from pipegoose_b200.partitioning import planner
+    from pipegoose_b200.trainer import Callback, Trainer
+    from pipegoose_b200.utils import data, watchdog
+
+    for name in ("consolidate_checkpoint", "reshard_checkpoint", "shard_state_dict", "shard_layout", "write_layout", "main"):
+        assert callable(getattr(cc, name)), name
+    assert callable(nu.reshard_fused_state) and callable(DistributedOptimizer.load_resharded_state)
+    for name in ("data_parallel_sampler", "build_dataloader", "TokenFileDataset", "write_token_file", "DevicePrefetcher"):
+        assert callable(getattr(data, name)), name
+    assert "stall_timeout_s" in inspect.signature(watchdog.RankWatchdog.__init__).parameters
+    assert callable(watchdog.RankWatchdog.tick) and watchdog.STALL_EXIT_CODE == 75
+    assert {"eval_every", "watchdog_timeout_s", "resume"} <= set(inspect.signature(Trainer.__init__).parameters)
+    assert callable(Callback.on_evaluate)
+    for name in ("estimate_memory", "plan", "local_param_count", "main"):
+        assert callable(getattr(planner, name)), name
+    assert callable(BloomForCausalLM.to_hf) and callable(BloomForCausalLM.save_hf_pretrained) and callable(BloomConfig.to_hf)
+    gen = inspect.signature(BloomForCausalLM.generate).parameters
+    assert {"attention_mask", "do_sample", "temperature", "top_k", "top_p", "eos_token_id", "pad_token_id", "use_cache"} <= set(gen)
