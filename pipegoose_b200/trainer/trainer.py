@@ -336,10 +336,11 @@ class Trainer:
             restore_rng_state(resume["rng"])
 
     @torch.no_grad()
-    def evaluate(self) -> float:
+    def evaluate(self, across_replicas: bool = True) -> float:
         """Mean loss over the batches of ``eval_loader`` — of ALL data-parallel replicas' loaders (each replica evaluates
         its shard, sums and counts are combined over the DATA group: every rank returns the same number, and it does
-        not depend on how many replicas shared the work)."""
+        not depend on how many replicas shared the work).  That makes it a COLLECTIVE over the DATA group;
+        ``across_replicas=False`` evaluates this replica's loader only (e.g. when one replica evaluates alone)."""
         assert self.eval_loader is not None
         # evaluate() may run in the middle of fit (from an on_step_end / on_epoch_end callback): the rest of training
         # must continue in the mode and stage it was in (dropout, router noise, training capacity factor)
@@ -360,7 +361,7 @@ class Trainer:
             ctx = self.parallel_context
             from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
-            if ctx is not None and ctx.get_world_size(ParallelMode.DATA) > 1:
+            if across_replicas and ctx is not None and ctx.get_world_size(ParallelMode.DATA) > 1:
                 import torch.distributed as dist
 
                 group = ctx.get_group(ParallelMode.DATA)
