@@ -14,6 +14,13 @@ from pipegoose_b200.nn.pipeline_parallel.pipeline_engine import PipelineEngine
 from pipegoose_b200.nn.pipeline_parallel.scheduler import SchedulerType, get_scheduler
 
 
+def _generate_not_pipelined(*args, **kwargs):
+    raise NotImplementedError(
+        "generate() of this model class is not pipeline-aware.  pipegoose_b200.models (BloomForCausalLM, GPT2LMHeadModel; a "
+        "🤗 Bloom converted by TensorParallel(model, ctx, sequence_parallel=True)) generate on pipelined layouts — one "
+        "forward-only schedule per token; otherwise call PipelineParallel(...).deparallelize() first.")
+
+
 class PipelineParallel(Parallel):
     def __init__(self, module: nn.Module, num_microbatches: int, parallel_context: ParallelContext,
                  scheduler_type: SchedulerType = SchedulerType.ONE_F_ONE_B, runtime: str = "static",
@@ -57,6 +64,10 @@ class PipelineParallel(Parallel):
             module._pg_pipeline_stage = stage
             module._pg_pipeline_engine = engine
             module.forward = engine.run
+            if callable(getattr(module, "generate", None)) and not hasattr(type(module), "_pipelined_next_token"):
+                # 🤗's GenerationMixin drives ``forward`` with cache / return_dict arguments and reads logits on every
+                # rank: on a pipelined model that ends in an obscure shape error on the stages without the head
+                module.generate = _generate_not_pipelined
             self._save_metadata(module, ctx)
         return module
 
@@ -93,6 +104,8 @@ class PipelineParallel(Parallel):
         for attr in ("_pg_pipeline_stage", "_pg_pipeline_engine"):
             if hasattr(module, attr):
                 delattr(module, attr)
+        if module.__dict__.get("generate") is _generate_not_pipelined:
+            del module.__dict__["generate"]
         if "forward" in module.__dict__:
             del module.__dict__["forward"]  # back to the class's forward
         return module

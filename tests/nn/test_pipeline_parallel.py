@@ -423,3 +423,28 @@ def test_forward_only_pipeline_returns_full_logits_and_backpropagates(tp):
     grads = {n: (p.grad if p.grad is not None else p.main_grad).detach().clone() for n, p in model.named_parameters()}
     spawn(run_forward_only_bloom, world_size=2 * tp, tp=tp, state=copy.deepcopy(model.state_dict()), ids=ids,
           ref_logits=logits.detach(), ref_grads=grads)
+
+
+def run_hf_generate_refused(rank, world_size, port):
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    from pipegoose_b200.nn import TensorParallel
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 2, 1)
+    torch.manual_seed(0)
+    model = HFBloom(HFConfig(vocab_size=96, hidden_size=32, n_layer=4, n_head=4))
+    model = TensorParallel(model, ctx, sequence_parallel=False).parallelize()
+    wrapper = PipelineParallel(model, num_microbatches=2, parallel_context=ctx)
+    model = wrapper.parallelize()
+    ids = torch.randint(0, 96, (2, 5))
+    with pytest.raises(NotImplementedError, match="not pipeline-aware"):
+        model.generate(input_ids=ids, max_new_tokens=2)
+    model = wrapper.deparallelize()                       # 🤗's own generate is back
+    out = model.generate(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=2, do_sample=False, pad_token_id=0)
+    assert out.shape == (2, 7)
+    ctx.destroy()
+
+
+def test_generate_of_a_pipelined_hf_model_is_refused_with_directions():
+    spawn(run_hf_generate_refused, world_size=2)
