@@ -224,6 +224,8 @@ def _load_for_another_dp_size(optim, ckp_path: str, parallel_context: ParallelCo
     if sorted(found) != list(range(old["dp"])):
         raise ValueError(f"{ckp_path}: the checkpoint was written by {old['dp']} replicas, found optimizer shards of "
                          f"replicas {sorted(found)} for tp={tp_rank} pp={pp_rank}")
+    if not (isinstance(first.get("optimizer"), dict) and "segments" in first["optimizer"]):
+        return None      # not a FusedAdam / ZeRO-1 state (e.g. DiLoCo workers: every replica's state is its own)
     if first.get("flat_index") is None:
         raise ValueError("this checkpoint predates the per-parameter index that re-cutting for another data-parallel size "
                          "needs (save it again with this version at the old size)")
