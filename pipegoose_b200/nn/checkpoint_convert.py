@@ -80,6 +80,7 @@ def shard_layout(module: nn.Module, parallel_context) -> Dict:
                 entry["full"] = int(meta.full_size)
             if getattr(meta, "is_vocab", False):
                 entry["vocab"] = True
+                entry["vocab_multiple"] = int(getattr(meta, "vocab_multiple", 1))
         if key in stacked and not entry.get("absent"):
             entry = {"dim": 0, "full": stacked[key]}
         for prefix, g in expert_prefix.items():
@@ -216,8 +217,8 @@ def shard_state_dict(full: Dict[str, torch.Tensor], layout_keys: Dict[str, Dict]
     """Rank ``tp_rank``'s shard of an unsharded state dict for a tensor group of ``tensor_parallel_size``:
     ``layout_keys[key] = {"dim": d[, "full": n]}`` says which keys are cut (the ``keys`` of any rank's layout file of the
     source checkpoint works: the SET of sliced keys does not depend on the group size).  Keys recorded with ``vocab``
-    (vocabulary tables, lm_head rows / bias) are zero-padded to a multiple of ``vocab_multiple * tensor_parallel_size`` first, the rule of
-    the sequence-parallel fast path (``vocab_multiple=1``: the class-swap path's rule)."""
+    (vocabulary tables, lm_head rows / bias) are zero-padded to a multiple of ``vocab_multiple * tensor_parallel_size`` first:
+    the multiple recorded in the layout (8 for the sequence-parallel fast path, 1 for the class-swap path), else the argument."""
     tp = tensor_parallel_size
     out = {}
     for key, t in full.items():
@@ -229,7 +230,7 @@ def shard_state_dict(full: Dict[str, torch.Tensor], layout_keys: Dict[str, Dict]
             continue
         d = rule["dim"]
         if rule.get("vocab") and d == 0:
-            mult = vocab_multiple * tp
+            mult = int(rule.get("vocab_multiple", vocab_multiple)) * tp     # the rule of the path that wrote the checkpoint
             padded = (t.shape[0] + mult - 1) // mult * mult
             if padded != t.shape[0]:
                 t = torch.cat([t, t.new_zeros(padded - t.shape[0], *t.shape[1:])], dim=0)

@@ -31,6 +31,7 @@ class ParallelMetadata:
     partition_dim: Optional[int] = None
     full_size: Optional[int] = None
     is_vocab: bool = False      # a vocabulary table / lm_head: zero-padded to a multiple of the group before the cut
+    vocab_multiple: int = 1     # ... of ``vocab_multiple x group size`` (8 on the sequence-parallel fast path: kernel tiles)
 
 
 class Parallel:

@@ -30,8 +30,9 @@ def get_partition(data: torch.Tensor, parallel_context: ParallelContext, dim: in
     return data.narrow(dim, rank * width, width).clone().contiguous()
 
 
-def _mark_sliced(param: nn.Parameter, dim: int = None, full_size: int = None, is_vocab: bool = False):
-    param.parallel_metadata = ParallelMetadata(is_sliced=True, partition_dim=dim, full_size=full_size, is_vocab=is_vocab)
+def _mark_sliced(param: nn.Parameter, dim: int = None, full_size: int = None, is_vocab: bool = False, vocab_multiple: int = 1):
+    param.parallel_metadata = ParallelMetadata(is_sliced=True, partition_dim=dim, full_size=full_size, is_vocab=is_vocab,
+                                               vocab_multiple=vocab_multiple)
 
 
 def _is_sliced(param) -> bool:

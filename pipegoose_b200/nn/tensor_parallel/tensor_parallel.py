@@ -217,7 +217,7 @@ def _parallelize_fast_bloom(model, ctx: ParallelContext):
     if padded != vocab:
         table = torch.cat([table, table.new_zeros(padded - vocab, table.shape[1])], dim=0)
     sliced = nn.Parameter(get_partition(table, ctx, dim=0))
-    _mark_sliced(sliced, 0, vocab, is_vocab=True)
+    _mark_sliced(sliced, 0, vocab, is_vocab=True, vocab_multiple=8)
     sliced._pg_grad_contribs = 2  # lm_head wgrad + embedding backward
     t.word_embeddings.weight = sliced
     model.lm_head.weight = sliced

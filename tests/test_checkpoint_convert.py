@@ -225,3 +225,42 @@ def test_consolidation_is_driven_by_metadata_not_by_bloom_names(tmp_path):
     assert set(merged) == set(state)
     for k, v in state.items():
         assert merged[k].shape == v.shape and torch.equal(merged[k], v), k
+
+
+def run_load_resharded_hf(rank, world_size, port, ckp_path, state):
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    ctx = init_parallel_context(rank, world_size, port, world_size, 1, 1)
+
+    def build(load):
+        torch.manual_seed(1)
+        model = HFBloom(HFConfig(vocab_size=VOCAB, hidden_size=32, n_layer=4, n_head=4))
+        if load:
+            model.load_state_dict(state)
+        return TensorParallel(model, ctx, sequence_parallel=False).parallelize()
+
+    want, got = build(True), build(False)
+    from_pretrained(got, ckp_path=ckp_path, parallel_context=ctx)
+    for (k, a), (_, b) in zip(got.state_dict().items(), want.state_dict().items()):
+        assert a.shape == b.shape and torch.equal(a, b), k
+    ctx.destroy()
+
+
+def test_reshard_keeps_the_vocabulary_padding_rule_of_the_path_that_wrote_the_checkpoint(tmp_path):
+    """The class-swap path pads the vocabulary to a multiple of the group (90 -> 92 at tp 4), the fast path to 8 x group
+    (90 -> 96): re-cut shards must load into a job of the SAME path, so the layout records the rule."""
+    import json
+
+    from transformers import BloomConfig as HFConfig
+    from transformers import BloomForCausalLM as HFBloom
+
+    torch.manual_seed(0)
+    state = copy.deepcopy(HFBloom(HFConfig(vocab_size=VOCAB, hidden_size=32, n_layer=4, n_head=4)).state_dict())
+    src, dst = str(tmp_path / "src"), str(tmp_path / "dst")
+    spawn(run_save, world_size=2, tp=2, pp=1, ckp_path=src, state=state, hf=True)
+    lay = json.load(open(os.path.join(src, "pytorch_model_tp_0_pp_0.bin.layout.json")))["keys"]
+    assert lay["transformer.word_embeddings.weight"] == {"dim": 0, "full": VOCAB, "vocab": True, "vocab_multiple": 1}
+    reshard_checkpoint(src, dst, 2, 1, 4)
+    assert torch.load(os.path.join(dst, "pytorch_model_tp_3_pp_0.bin"))["transformer.word_embeddings.weight"].shape[0] == 23
+    spawn(run_load_resharded_hf, world_size=4, ckp_path=dst, state=state)
