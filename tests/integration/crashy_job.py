@@ -46,7 +46,7 @@ def main():
 
     trainer = Trainer(model, data, optim=optim, parallel_context=ctx, callbacks=[Crash()], log_every=1,
                       checkpoint_dir=os.path.join(workdir, "ckpt") if crash else None, checkpoint_every=3, resume=crash,
-                      watchdog_timeout_s=4 if mode == "hang" else 20)
+                      watchdog_timeout_s=8 if mode == "hang" else 30)
     state = trainer.fit()
     if ctx.get_global_rank() == 0:
         checksum = float(sum(p.detach().double().sum() for p in model.parameters()))
