@@ -38,8 +38,9 @@ class TensorParallel(Parallel):
         """``sequence_parallel``: ``True`` forces the sequence-parallel fast path (a 🤗 ``BloomForCausalLM`` is
         converted in place to ``pipegoose_b200.models.bloom.BloomForCausalLM`` first), ``False`` forces the
         reference-style class swap, ``None`` (default) picks the fast path for ``pipegoose_b200.models`` models and for
-        🤗 Bloom models that are set up for the kernels (bf16 parameters; dropout, if configured, runs through the composed training path) — the reference's canonical
-        input then trains on the fused kernels without any change to the user's script."""
+        🤗 Bloom models that are set up for the kernels (bf16 parameters; dropout, if configured, runs through the composed
+        training path) — the reference's canonical input then trains on the fused kernels without any change to the
+        user's script."""
         super().__init__(module, parallel_context)
         self.sequence_parallel = sequence_parallel
 
