@@ -50,7 +50,8 @@ def _blocks_of_stage(n_layer: int, pp: int, stage: int) -> int:
 
 
 def local_param_count(config, tp: int, pp: int, stage: int) -> int:
-    """Parameters one rank of ``stage`` holds (Bloom family: tied table, embedding LayerNorm, ALiBi — no position table)."""
+    """Parameters one rank of ``stage`` holds (the fused model families: Bloom — tied table, embedding LayerNorm, ALiBi —
+    and GPT-2 — tied table, learned positions, no embedding LayerNorm)."""
     h, V = config.hidden_size, config.vocab_size
     mult = 8 * tp
     v_local = ((V + mult - 1) // mult * mult // tp) if tp > 1 else V
@@ -61,7 +62,11 @@ def local_param_count(config, tp: int, pp: int, stage: int) -> int:
     block += 4 * h                             # two LayerNorms
     n = _blocks_of_stage(config.n_layer, pp, stage) * block
     if stage == 0:
-        n += v_local * h + 2 * h               # table + embedding LayerNorm
+        n += v_local * h                       # token table
+        if getattr(config, "embedding_layernorm", True):
+            n += 2 * h                         # Bloom: LayerNorm right after the embedding
+        if getattr(config, "position_embedding", "alibi") == "learned":
+            n += int(getattr(config, "n_positions", 0)) * h      # GPT-2 family: learned absolute positions (replicated)
     if stage == pp - 1:
         n += 2 * h                             # ln_f
         if pp > 1:

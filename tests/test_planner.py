@@ -74,3 +74,14 @@ def test_plan_orders_layouts_and_respects_the_memory_limit(capsys):
     assert all(l.dp in (1, 2) for l in plan(cfg, 8, global_batch=2, seq_len=2048))
     main(["--model", "bloom_3b", "--gpus", "8", "--global-batch", "16", "--seq-len", "1024"])
     assert "GiB/GPU" in capsys.readouterr().out
+
+
+def test_parameter_count_of_the_gpt2_family():
+    from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+    for cfg in (GPT2Config.gpt2_tiny(), GPT2Config.gpt2()):
+        with torch.device("meta"):
+            model = GPT2LMHeadModel(cfg)
+        have = sum(p.numel() for p in {id(p): p for p in model.parameters()}.values())
+        assert local_param_count(cfg, 1, 1, 0) == have, (cfg, have)
+    assert abs(local_param_count(GPT2Config.gpt2(), 1, 1, 0) - 124.4e6) < 0.5e6      # "gpt2": 124 M
