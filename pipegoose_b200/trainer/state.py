@@ -26,3 +26,4 @@ class TrainerState:
     last_loss: float = float("nan")
     last_grad_norm: float = float("nan")
     last_eval_loss: float = float("nan")
+    skipped_steps: int = 0      # optimizer steps dropped because the gradient norm was not finite

@@ -24,7 +24,8 @@ class Trainer:
                  max_steps: Optional[int] = None, keep_checkpoints: int = 2, moe_loss_weights=(0.01, 0.001),
                  eval_every: int = 0):
         """``grad_accum_steps``: micro-batches per optimizer step.  ``max_grad_norm``: clip the whole model's gradient
-        norm (optim/clip.py).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
+        norm (optim/clip.py); a step whose norm is not finite is skipped (gradients dropped, weights and optimizer state
+        untouched, ``state.skipped_steps``).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
         and optimizer / RNG / step state (save_training_state) every N optimizer steps, each in its own ``step_<n>``
         directory that becomes ``latest`` only when every rank has written its shard (``keep_checkpoints`` newest kept); ``resume=True`` restores the
@@ -117,6 +118,12 @@ class Trainer:
 
                 ctx = self.parallel_context if self.parallel_context is not None else _SingleProcess()
                 self.state.last_grad_norm = float(clip_grad_norm_(self.optim, self.max_grad_norm, ctx))
+                if self.state.last_grad_norm != self.state.last_grad_norm or self.state.last_grad_norm == float("inf"):
+                    # a non-finite gradient (overflow, a poisoned batch): the clip coefficient would be NaN / 0 * inf and
+                    # one step would write NaNs into the fp32 master weights for good.  The norm is a global quantity
+                    # (all-reduced), so every rank takes this branch together: drop the gradients, keep the weights.
+                    self._skip_step()
+                    return loss
             self.optim.step()
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()
@@ -124,6 +131,15 @@ class Trainer:
             if self.checkpoint_dir and self.checkpoint_every and self.state.step % self.checkpoint_every == 0:
                 self.save_checkpoint()
         return loss
+
+    def _skip_step(self):
+        inner = getattr(self.optim, "optim", self.optim)
+        if hasattr(inner, "pending_grad_scale"):
+            inner.pending_grad_scale = 1.0          # (what clip_grad_norm_ left for the fused Adam kernel)
+        self.optim.zero_grad()
+        self.state.skipped_steps += 1
+        self._log(f"step {self.state.step + 1}: non-finite gradient norm, optimizer step skipped "
+                  f"({self.state.skipped_steps} skipped so far)")
 
     def _add_router_losses(self, loss: torch.Tensor) -> torch.Tensor:
         """Mixture-of-experts layers push their load-balancing / router-z losses into the ExpertContext on every forward:

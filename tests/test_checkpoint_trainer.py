@@ -361,3 +361,45 @@ def test_evaluate_averages_over_the_data_parallel_replicas():
     with torch.no_grad():
         want = sum(float(model(b["input_ids"], labels=b["input_ids"]).loss) for b in batches) / 3
     spawn(run_dp_evaluate, world_size=2, state=copy.deepcopy(model.state_dict()), batches=batches, want=want)
+
+
+def run_skip_nonfinite(rank, world_size, port, fused):
+    from pipegoose_b200.nn import DataParallel, TensorParallel
+    from pipegoose_b200.optim import DistributedOptimizer, FusedAdam
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, 2)
+    g = torch.Generator().manual_seed(4 + rank)
+    batches = [{"input_ids": torch.randint(0, 96, (2, 8), generator=g)} for _ in range(4)]
+
+    def run(data, poison_call):
+        torch.manual_seed(0)
+        model = BloomForCausalLM(BloomConfig(vocab_size=96, hidden_size=32, n_layer=1, n_head=4))
+        model = DataParallel(TensorParallel(model, ctx).parallelize(), ctx).parallelize()
+        inner = FusedAdam(model.parameters(), lr=1e-2) if fused else torch.optim.Adam(model.parameters(), lr=1e-2)
+        calls = [0]
+
+        class Poisoned(Trainer):                # only replica 1's loss (hence gradient) is poisoned: every rank sees the NORM
+            def _add_router_losses(self, loss):
+                calls[0] += 1
+                loss = super()._add_router_losses(loss)
+                return loss * float("nan") if (calls[0] == poison_call and rank == 1) else loss
+
+        trainer = Poisoned(model, data, optim=DistributedOptimizer(inner, ctx), parallel_context=ctx, max_grad_norm=1.0)
+        state = trainer.fit()
+        return model, state
+
+    poisoned, state = run(batches, poison_call=2)
+    assert state.step == 3 and state.skipped_steps == 1
+    clean, state = run([batches[0], batches[2], batches[3]], poison_call=-1)
+    assert state.step == 3 and state.skipped_steps == 0
+    for (n, a), (_, b) in zip(poisoned.named_parameters(), clean.named_parameters()):
+        assert torch.isfinite(a).all() and torch.allclose(a, b, atol=1e-6), n
+    ctx.destroy()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_trainer_skips_a_step_with_a_non_finite_gradient_norm(fused):
+    """One replica's gradient turns NaN in the second step: every rank drops that step (the norm is global), weights and
+    Adam state stay as they were — the run ends where a run without that batch ends."""
+    spawn(run_skip_nonfinite, world_size=2, fused=fused)
