@@ -6,4 +6,4 @@ Python orchestrates; the hot ops are hand-written sm_100a CUDA kernels in ``pipe
 extension ``pipegoose_b200/_C.so`` (see ``pipegoose_b200.ops``).
 """
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

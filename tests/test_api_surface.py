@@ -186,3 +186,18 @@ def test_operations_layer_public_surface():
     assert callable(BloomForCausalLM.to_hf) and callable(BloomForCausalLM.save_hf_pretrained) and callable(BloomConfig.to_hf)
     gen = inspect.signature(BloomForCausalLM.generate).parameters
     assert {"attention_mask", "do_sample", "temperature", "top_k", "top_p", "eos_token_id", "pad_token_id", "use_cache"} <= set(gen)
+
+
+def test_diagnostics_entry_point_runs(capsys):
+    """``python -m pipegoose_b200`` (bug-report helper): never raises, reports version and extension state."""
+    import pipegoose_b200
+    from pipegoose_b200.__main__ import main
+
+    assert main() == 0
+    out = capsys.readouterr().out
+    assert pipegoose_b200.__version__ in out and "extension (_C.so)" in out and "distributed backends" in out
+    import re
+    import pathlib
+
+    pyproject = (pathlib.Path(pipegoose_b200.__file__).resolve().parent.parent / "pyproject.toml").read_text()
+    assert re.search(r'^version = "(.+)"$', pyproject, re.M).group(1) == pipegoose_b200.__version__
