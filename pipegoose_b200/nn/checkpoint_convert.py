@@ -243,9 +243,11 @@ def shard_state_dict(full: Dict[str, torch.Tensor], layout_keys: Dict[str, Dict]
 
 def reshard_checkpoint(src: str, dst: str, tensor_parallel_size: int, pipeline_parallel_size: int,
                        new_tensor_parallel_size: int, ckp_name: str = CHECKPOINT_WEIGHTS_NAME,
-                       vocab_multiple: int = 8) -> None:
-    """Rewrite the checkpoint under ``src`` (tp x pp shards) as ``new_tensor_parallel_size`` x 1 shards under ``dst``
-    (``from_pretrained`` of a job with that tensor group and no pipeline loads them)."""
+                       vocab_multiple: int = 8, new_pipeline_parallel_size: int = 1) -> None:
+    """Rewrite the checkpoint under ``src`` (tp x pp shards) as ``new_tensor_parallel_size`` x
+    ``new_pipeline_parallel_size`` shards under ``dst`` for ``from_pretrained`` of a job with that layout.  Every pipeline
+    rank's file holds the whole (tensor-sliced) model — which blocks a stage owns is the partitioner's decision at run
+    time; ``from_pretrained`` takes what its stage holds and ignores the rest."""
     _, layouts = _read_shards(src, tensor_parallel_size, pipeline_parallel_size, ckp_name)
     if len(layouts) != tensor_parallel_size * pipeline_parallel_size:
         raise ValueError("resharding needs the layout files save_pretrained writes next to the shards")
@@ -258,11 +260,12 @@ def reshard_checkpoint(src: str, dst: str, tensor_parallel_size: int, pipeline_p
     Path(dst).mkdir(parents=True, exist_ok=True)
     for r in range(new_tensor_parallel_size):
         shard = shard_state_dict(full, keys, new_tensor_parallel_size, r, vocab_multiple)
-        path = os.path.join(dst, ckp_name.format(r, 0))
-        torch.save(shard, path)
-        with open(path + LAYOUT_SUFFIX, "w") as f:
-            json.dump({"tp": new_tensor_parallel_size, "pp": 1, "tp_rank": r, "pp_rank": 0,
-                       "keys": {k: e for k, e in keys.items() if "dim" in e}}, f)
+        for p in range(new_pipeline_parallel_size):
+            path = os.path.join(dst, ckp_name.format(r, p))
+            torch.save(shard, path)
+            with open(path + LAYOUT_SUFFIX, "w") as f:
+                json.dump({"tp": new_tensor_parallel_size, "pp": new_pipeline_parallel_size, "tp_rank": r, "pp_rank": p,
+                           "keys": {k: e for k, e in keys.items() if "dim" in e}}, f)
 
 
 def main(argv=None) -> None:
@@ -274,11 +277,12 @@ def main(argv=None) -> None:
     ap.add_argument("--tp", type=int, required=True)
     ap.add_argument("--pp", type=int, default=1)
     ap.add_argument("--new-tp", type=int, default=0)
+    ap.add_argument("--new-pp", type=int, default=1)
     ap.add_argument("--vocab-size", type=int, default=None)
     a = ap.parse_args(argv)
     if a.new_tp:
-        reshard_checkpoint(a.src, a.dst, a.tp, a.pp, a.new_tp)
-        print(f"wrote {a.new_tp} shard(s) to {a.dst}")
+        reshard_checkpoint(a.src, a.dst, a.tp, a.pp, a.new_tp, new_pipeline_parallel_size=a.new_pp)
+        print(f"wrote {a.new_tp} x {a.new_pp} shard(s) to {a.dst}")
     else:
         sd = consolidate_checkpoint(a.src, a.tp, a.pp, vocab_size=a.vocab_size)
         Path(os.path.dirname(os.path.abspath(a.dst))).mkdir(parents=True, exist_ok=True)

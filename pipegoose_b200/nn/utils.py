@@ -45,16 +45,25 @@ def from_pretrained(module: nn.Module, ckp_path: str = CHECKPOINT_PATH_NAME, par
         unexpected = [k for k in state_dict if k not in own]
         if unexpected:
             raise KeyError(f"unexpected key(s) {unexpected[:5]} in checkpoint {path}")
-        missing = [k for k in own if k not in state_dict]
+        # a pipelined module lists its stage's parameters a second time under ``_pg_pipeline_stage.`` (the same storage):
+        # shards re-cut offline (nn/checkpoint_convert.py) only carry the model's own names
+        missing = [k for k in own if k not in state_dict and not k.startswith("_pg_pipeline_stage.")]
         if missing and strict:
             raise KeyError(f"checkpoint {path} lacks {len(missing)} parameter(s) / buffer(s) of this module, e.g. "
                            f"{missing[:5]}")
+
+        def foreign(k, v):
+            """Another pipeline stage's parameter: this rank keeps a zero-size stand-in, a shard written for every stage
+            alike (re-cut offline) holds the tensor — nothing to load here."""
+            return own[k].numel() == 0 and own[k].dim() == 1 and v.numel() > 0
+
         for k, v in state_dict.items():
-            if tuple(own[k].shape) != tuple(v.shape):
+            if tuple(own[k].shape) != tuple(v.shape) and not foreign(k, v):
                 raise ValueError(f"shape mismatch for {k} in {path}: checkpoint {tuple(v.shape)}, module "
                                  f"{tuple(own[k].shape)} (different model config or parallel layout?)")
         for k, v in state_dict.items():
-            own[k].copy_(v)
+            if not foreign(k, v):
+                own[k].copy_(v)
     return module
 
 

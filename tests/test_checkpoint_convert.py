@@ -264,3 +264,41 @@ def test_reshard_keeps_the_vocabulary_padding_rule_of_the_path_that_wrote_the_ch
     reshard_checkpoint(src, dst, 2, 1, 4)
     assert torch.load(os.path.join(dst, "pytorch_model_tp_3_pp_0.bin"))["transformer.word_embeddings.weight"].shape[0] == 23
     spawn(run_load_resharded_hf, world_size=4, ckp_path=dst, state=state)
+
+
+def run_load_into_pipeline(rank, world_size, port, ckp_path, state):
+    ctx = init_parallel_context(rank, world_size, port, 2, 2, 1)
+
+    def build(load):
+        model = _model()
+        if load:
+            model.load_state_dict(state)
+        else:
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.normal_()
+        model = TensorParallel(model, ctx).parallelize()
+        return PipelineParallel(model, num_microbatches=2, parallel_context=ctx).parallelize()
+
+    want, got = build(True), build(False)
+    from_pretrained(got, ckp_path=ckp_path, parallel_context=ctx)
+    n = 0
+    for (k, a), (_, b) in zip(got.state_dict().items(), want.state_dict().items()):
+        assert a.shape == b.shape and torch.equal(a, b), k
+        n += a.numel() > 0
+    assert n > 0
+    ctx.destroy()
+
+
+def test_reshard_for_a_pipelined_job(tmp_path):
+    """TP2 checkpoint -> TP2 x PP2 job: every pipeline rank's file holds the whole tensor-sliced model, a stage loads what it
+    owns (its ``_pg_pipeline_stage.`` aliases share that storage) and ignores the other stages' tensors."""
+    state = copy.deepcopy(_model().state_dict())
+    src, dst = str(tmp_path / "src"), str(tmp_path / "dst")
+    spawn(run_save, world_size=2, tp=2, pp=1, ckp_path=src, state=state, hf=False)
+    main([src, dst, "--tp", "2", "--pp", "1", "--new-tp", "2", "--new-pp", "2"])
+    assert sorted(f for f in os.listdir(dst) if f.endswith(".bin")) == [
+        "pytorch_model_tp_0_pp_0.bin", "pytorch_model_tp_0_pp_1.bin", "pytorch_model_tp_1_pp_0.bin", "pytorch_model_tp_1_pp_1.bin"]
+    spawn(run_load_into_pipeline, world_size=4, ckp_path=dst, state=state)
+    merged = consolidate_checkpoint(dst, 2, 2)                    # and such a directory merges back like any other
+    assert all(torch.equal(merged[k], v) for k, v in state.items())
