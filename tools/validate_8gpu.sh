@@ -33,4 +33,6 @@ echo "== config #4: bloom-560m + Switch-MoE 8 experts, EP=8, Top-1"
 run cfg4 120 160 --tp 8 --experts 8
 echo "== config #5: bloom-3b TP2 x PP2 x DP2 + ZeRO-1, 1F1B, 8 micro-batches"
 run cfg5 150 180 --model bloom-3b --tp 2 --pp 2 --microbatches 8 --batch-per-gpu 2
+echo "== layout check (partitioning/planner.py ranks pure DP8 + ZeRO-1 ahead of the prescribed TP2 x DP4 for bloom-560m: dp 2 measured +7.6 %, tp 2 +12.7 %)"
+timeout 120 python bench.py --gpus 8 --tp 1 --steps 6 --warmup 3 --no-self-check | line
 echo "== done"
