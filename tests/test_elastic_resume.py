@@ -137,3 +137,39 @@ def test_other_layout_changes_are_still_refused(tmp_path):
     ckp = str(tmp_path / "ckpt")
     spawn(run_write, world_size=2, tp=1, dp=2, ckp=ckp, out=str(tmp_path))
     spawn(run_refused, world_size=2, ckp=ckp)
+
+
+def run_trainer_phase(rank, world_size, port, dp, path, ckp, out, phase):
+    """phase "full": 6 steps uninterrupted at this dp; "first": 3 steps + checkpoint; "rest": resume and finish."""
+    from pipegoose_b200.trainer import Trainer
+    from pipegoose_b200.utils.data import TokenFileDataset, build_dataloader
+
+    ctx = init_parallel_context(rank, world_size, port, 1, 1, dp)
+    model, optim = _build(ctx)
+    loader = build_dataloader(TokenFileDataset(path, seq_len=8), ctx, batch_size=GLOBAL_BATCH // dp, shuffle=True)
+    kw = {}
+    if phase == "first":
+        kw = dict(checkpoint_dir=ckp, checkpoint_every=3, max_steps=3)
+    elif phase == "rest":
+        kw = dict(checkpoint_dir=ckp, resume=True)
+    state = Trainer(model, loader, optim=optim, parallel_context=ctx, num_epochs=2, **kw).fit()
+    assert state.step == (3 if phase == "first" else 6)
+    if rank == 0 and phase != "first":
+        torch.save({k: v.detach().clone() for k, v in model.state_dict().items()}, os.path.join(out, f"{phase}.pt"))
+    ctx.destroy()
+
+
+def test_trainer_resumes_on_another_replica_count_with_the_same_global_batches(tmp_path):
+    """Trainer + build_dataloader: 3 steps on 2 replicas (4 sequences each), checkpoint, 3 more steps on ONE replica (8
+    sequences): the sharded sampler hands out the same global batches in both layouts, so the run ends where the
+    uninterrupted 2-replica run ends."""
+    from pipegoose_b200.utils.data import write_token_file
+
+    path, ckp, out = str(tmp_path / "tokens.bin"), str(tmp_path / "ckpt"), str(tmp_path)
+    write_token_file(path, torch.randint(0, 96, (24 * 8,), generator=torch.Generator().manual_seed(3)))   # 24 sequences: 3 steps/epoch
+    spawn(run_trainer_phase, world_size=2, dp=2, path=path, ckp=ckp, out=out, phase="full")
+    spawn(run_trainer_phase, world_size=2, dp=2, path=path, ckp=ckp, out=out, phase="first")
+    spawn(run_trainer_phase, world_size=1, dp=1, path=path, ckp=ckp, out=out, phase="rest")
+    want, got = torch.load(os.path.join(out, "full.pt")), torch.load(os.path.join(out, "rest.pt"))
+    for k, v in want.items():
+        assert torch.allclose(got[k], v, atol=2e-5), k
