@@ -127,6 +127,28 @@ class GPT2LMHeadModel(BloomForCausalLM):
         model.load_state_dict(state)
         return model.to(next(hf_model.parameters()).dtype)
 
+    def to_hf(self):
+        """A 🤗 ``transformers.GPT2LMHeadModel`` with this model's weights (unsharded model; ``to_hf_state_dict`` undoes the
+        weight transposes and the per-head QKV interleaving)."""
+        from transformers import GPT2Config as HFConfig
+        from transformers import GPT2LMHeadModel as HFGPT2
+
+        if self.tp is not None or getattr(self, "_pg_pipeline_engine", None) is not None:
+            raise ValueError("to_hf() needs the unsharded model: deparallelize() first (or consolidate the checkpoint)")
+        c = self.config
+        hf = HFGPT2(HFConfig(vocab_size=c.vocab_size, n_embd=c.hidden_size, n_layer=c.n_layer, n_head=c.n_head,
+                             n_positions=c.n_positions, layer_norm_epsilon=c.layer_norm_epsilon,
+                             initializer_range=c.initializer_range, activation_function="gelu_new",
+                             resid_pdrop=c.hidden_dropout, embd_pdrop=c.hidden_dropout, attn_pdrop=c.attention_dropout))
+        hf = hf.to(next(self.parameters()).dtype)
+        missing, unexpected = hf.load_state_dict(self.to_hf_state_dict(), strict=False)
+        assert not unexpected and all(k.endswith((".attn.bias", ".attn.masked_bias")) for k in missing), (missing, unexpected)
+        hf.tie_weights()
+        return hf
+
+    def save_hf_pretrained(self, path: str, **kwargs) -> None:
+        self.to_hf().save_pretrained(path, **kwargs)
+
     def to_hf_state_dict(self) -> dict:
         """The inverse of :meth:`convert_hf_state_dict` (unsharded model)."""
         n_head = self.config.n_head

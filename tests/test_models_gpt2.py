@@ -115,3 +115,20 @@ def test_gpt2_generate_left_padded_prompts_match_transformers():
     want = hf.generate(input_ids=ids, attention_mask=mask, max_new_tokens=5, do_sample=False, pad_token_id=0)
     for use_cache in (True, False):
         assert torch.equal(mine.generate(ids, attention_mask=mask, max_new_tokens=5, use_cache=use_cache), want)
+
+
+def test_gpt2_round_trip_back_to_transformers(tmp_path):
+    from transformers import GPT2LMHeadModel as HFGPT2
+
+    from pipegoose_b200.models.gpt2 import GPT2Config, GPT2LMHeadModel
+
+    torch.manual_seed(0)
+    mine = GPT2LMHeadModel(GPT2Config.gpt2_tiny()).eval()
+    ids = torch.randint(0, mine.config.vocab_size, (2, 9))
+    hf = mine.to_hf().eval()
+    assert torch.allclose(hf(input_ids=ids).logits, mine(ids).logits, atol=1e-5)
+    mine.save_hf_pretrained(str(tmp_path / "export"))
+    again = HFGPT2.from_pretrained(str(tmp_path / "export")).eval()
+    assert torch.allclose(again(input_ids=ids).logits, mine(ids).logits, atol=1e-5)
+    back = GPT2LMHeadModel.from_hf(again).eval()
+    assert torch.allclose(back(ids).logits, mine(ids).logits, atol=1e-5)
