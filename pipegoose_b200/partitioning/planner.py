@@ -179,12 +179,18 @@ def main(argv=None) -> None:
     from pipegoose_b200.models.bloom import BloomConfig
 
     ap = argparse.ArgumentParser(description="rank the (tp, pp, dp) layouts of a Bloom-family model on B200s")
-    ap.add_argument("--model", default="bloom_560m", help="a BloomConfig preset: bloom_560m, bloom_1b7, bloom_3b, bloom_7b1")
+    ap.add_argument("--model", default="bloom_560m", help="a preset of BloomConfig (bloom_560m, bloom_1b7, bloom_3b, bloom_7b1) "
+                    "or GPT2Config (gpt2, gpt2_medium, gpt2_large, gpt2_xl)")
     ap.add_argument("--gpus", type=int, default=8)
     ap.add_argument("--global-batch", type=int, default=64, help="sequences per optimizer step")
     ap.add_argument("--seq-len", type=int, default=1024)
     a = ap.parse_args(argv)
-    cfg = getattr(BloomConfig, a.model)()
+    from pipegoose_b200.models.gpt2 import GPT2Config
+
+    family = GPT2Config if a.model.startswith("gpt2") else BloomConfig
+    if not hasattr(family, a.model):
+        ap.error(f"unknown preset {a.model!r}")
+    cfg = getattr(family, a.model)()
     for layout in plan(cfg, a.gpus, a.global_batch, a.seq_len):
         print(layout)
 
