@@ -472,6 +472,12 @@ class BloomForCausalLM(nn.Module):
         from pipegoose_b200.distributed.parallel_mode import ParallelMode
 
         outs = self(ids, attention_mask=mask) if mask is not None else self(ids)
+        if not all(isinstance(b.mlp, BloomMLP) for b in self.transformer.h):
+            # mixture-of-experts stages push their router losses on every forward: nothing consumes them while decoding
+            from pipegoose_b200.nn.expert_parallel.expert_context import ExpertContext
+
+            store = ExpertContext.get_instance()
+            store.pop_all_aux_loss(), store.pop_all_z_loss()
         ctx = engine.parallel_context
         if engine.is_last:
             logits = torch.cat([o.logits if hasattr(o, "logits") else o for o in outs], dim=0)
