@@ -28,7 +28,8 @@ class Trainer:
         untouched, ``state.skipped_steps``).  ``lr_scheduler``: anything with ``step()`` (built on ``optim.optim`` for a
         ``DistributedOptimizer``).  ``checkpoint_dir`` + ``checkpoint_every``: sharded weights (nn.utils.save_pretrained)
         and optimizer / RNG / step state (save_training_state) every N optimizer steps, each in its own ``step_<n>``
-        directory that becomes ``latest`` only when every rank has written its shard (``keep_checkpoints`` newest kept); ``resume=True`` restores the
+        directory that becomes ``latest`` only when every rank has written its shard (``keep_checkpoints`` newest kept; one
+        more is written when ``fit`` ends between two periodic ones); ``resume=True`` restores the
         latest one before training and skips the batches it had consumed.  ``max_steps``: stop at that optimizer step.  ``watchdog_timeout_s``: start a
         :class:`RankWatchdog` for the duration of ``fit``.  ``eval_every``: evaluate on ``eval_loader`` every N optimizer
         steps and once more when ``fit`` ends (``state.last_eval_loss``, the loggers' ``eval_loss``, ``on_evaluate``); the
@@ -159,6 +160,7 @@ class Trainer:
     # layout:  <checkpoint_dir>/step_00000500/{pytorch_model_tp_*_pp_*.bin, optimizer_tp_*_pp_*_dp_*.bin}
     #          <checkpoint_dir>/latest        <- name of the newest COMPLETE step directory (written last, atomically)
     _last_eval_step = -1
+    _last_saved_step = -1
 
     def _evaluate_in_training(self):
         """A periodic evaluation that leaves no trace in the training run: eval mode and stage are restored by
@@ -222,6 +224,7 @@ class Trainer:
                 shutil.rmtree(os.path.join(self.checkpoint_dir, stale), ignore_errors=True)
         self._barrier()
         self._tick()
+        self._last_saved_step = self.state.step
         self._log(f"checkpoint written at step {self.state.step} -> {path}")
 
     def _latest_checkpoint(self) -> Optional[str]:
@@ -284,6 +287,9 @@ class Trainer:
                 watchdog.stop()
         if self.eval_every and self.eval_loader is not None and self._last_eval_step != self.state.step:
             self._evaluate_in_training()
+        if (self.checkpoint_dir and self.checkpoint_every and self.state.step % self.checkpoint_every != 0
+                and self.state.step != self._last_saved_step and self._micro == 0):
+            self.save_checkpoint()      # periodic checkpoints are on: the run's last steps are not left unsaved
         self._call("on_fit_end")
         self.state.status = TrainerStatus.FINISHED
         return self.state

@@ -403,3 +403,28 @@ def test_trainer_skips_a_step_with_a_non_finite_gradient_norm(fused):
     """One replica's gradient turns NaN in the second step: every rank drops that step (the norm is global), weights and
     Adam state stay as they were — the run ends where a run without that batch ends."""
     spawn(run_skip_nonfinite, world_size=2, fused=fused)
+
+
+def test_fit_saves_the_last_steps_when_periodic_checkpoints_are_on(tmp_path):
+    """5 steps, a checkpoint every 2: steps 2, 4 — and 5 when ``fit`` ends, so a finished run can be continued or exported
+    from its real end state (nothing extra when the run ends on a periodic checkpoint, or when checkpointing is off)."""
+    from pipegoose_b200.optim import FusedAdam
+    from pipegoose_b200.testing.utils import find_free_port
+    from pipegoose_b200.trainer import Trainer
+
+    ctx = init_parallel_context(0, 1, find_free_port(), 1, 1, 1)
+    try:
+        def run(n_batches, ckp, every):
+            torch.manual_seed(0)
+            model = BloomForCausalLM(BloomConfig(vocab_size=64, hidden_size=32, n_layer=1, n_head=4))
+            data = [{"input_ids": torch.randint(0, 64, (2, 8))} for _ in range(n_batches)]
+            Trainer(model, data, optim=FusedAdam(model.parameters(), lr=1e-2), parallel_context=ctx, checkpoint_dir=ckp,
+                    checkpoint_every=every, keep_checkpoints=5).fit()
+            return sorted(d for d in os.listdir(ckp) if d.startswith("step_")) if os.path.isdir(ckp) else []
+
+        assert run(5, str(tmp_path / "a"), 2) == ["step_00000002", "step_00000004", "step_00000005"]
+        assert open(str(tmp_path / "a" / "latest")).read() == "step_00000005"
+        assert run(4, str(tmp_path / "b"), 2) == ["step_00000002", "step_00000004"]
+        assert run(3, str(tmp_path / "c"), 0) == []
+    finally:
+        ctx.destroy()
