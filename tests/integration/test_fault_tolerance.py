@@ -19,7 +19,22 @@ def _launch(workdir, mode, max_restarts):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1", "--nnodes=1",
            "--nproc-per-node=2", f"--max-restarts={max_restarts}", "--monitor-interval", "0.5",
            os.path.join(HERE, "crashy_job.py"), workdir, mode]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    return _run_in_own_group(cmd, timeout=420)
+
+
+def _run_in_own_group(cmd, timeout):
+    """``subprocess.run`` that, on a timeout, ends the launcher AND its ranks (a killed torchrun leaves its workers behind):
+    the job gets its own process group, which is signalled as a whole."""
+    import signal
+
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        proc.communicate()
+        raise
+    return subprocess.CompletedProcess(cmd, proc.returncode, out, err)
 
 
 @pytest.mark.timeout(900)
@@ -71,8 +86,19 @@ def test_two_launcher_agents_like_two_nodes(tmp_path):
                                "--nproc-per-node=1", "--rdzv-backend", "c10d", "--rdzv-endpoint", f"127.0.0.1:{port}",
                                "--rdzv-id", "two-agents", "--local-addr", "127.0.0.1",
                                os.path.join(HERE, "crashy_job.py"), two, "clean"],
-                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for n in (0, 1)]
-    outs = [p.communicate(timeout=400) for p in procs]
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+             for n in (0, 1)]
+    try:
+        outs = [p.communicate(timeout=400) for p in procs]
+    except subprocess.TimeoutExpired:
+        import signal
+
+        for p in procs:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except ProcessLookupError:
+                pass
+        raise
     assert [p.returncode for p in procs] == [0, 0], outs[0][1][-2000:] + outs[1][1][-2000:]
     want = json.load(open(os.path.join(one, "result_clean.json")))
     got = json.load(open(os.path.join(two, "result_clean.json")))
